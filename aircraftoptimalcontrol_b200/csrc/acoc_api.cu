@@ -1,0 +1,1133 @@
+// acoc_api.cu -- libacoc.so: CUDA kernels (sm_100a) + C ABI declared in include/acoc.h.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+// (-fmad=false: every FMA in this library is written explicitly as fma(); see acoc_math.cuh).
+//
+// Execution model: one thread = one OCP instance for the sequential-in-time sweeps (backward Riccati /
+// costate sweep, LQ forward pass, rollouts); the Armijo candidates add a second thread dimension
+// (candidate x instance) so that the 10 candidates of 32 neighbouring instances share one CTA and hit the
+// same input/reference lines in L1.  All trajectory buffers are struct-of-arrays with the instance index
+// fastest (see acoc_kernels.cuh); host buffers use the reference's (N,6,TT) layout and are transposed on
+// the device through a staging buffer.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/acoc.h"
+#include "acoc_kernels.cuh"
+
+using namespace acoc;
+
+// ======================================================================================================
+// error plumbing
+// ======================================================================================================
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) return fail(ACOC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define REQUIRE(cond, ...)                                   \
+    do {                                                     \
+        if (!(cond)) return fail(ACOC_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+// ======================================================================================================
+// kernels
+// ======================================================================================================
+constexpr int ST_PAD = 4;  // padding lanes beyond N: never active
+
+constexpr int BWD_THREADS = 64;
+constexpr int FWD_THREADS = 64;
+constexpr int ROLL_THREADS = 64;
+constexpr int CAND_TILE = 32;  // instances per candidate CTA (one warp per candidate)
+
+__global__ void __launch_bounds__(128) k_traj_cost(Problem P, const double* __restrict__ X, const double* __restrict__ U,
+                                                  const int* __restrict__ status, double* __restrict__ J)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.N || status[i] != ST_ACTIVE) return;
+    J[i] = traj_cost_instance(P, X, U, i);
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(BWD_THREADS) k_backward(Problem P, const double* __restrict__ X, const double* __restrict__ U,
+                                                          double* __restrict__ KSG, const int* __restrict__ status, int* __restrict__ n_reg)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.N || status[i] != ST_ACTIVE) return;
+    const int r = backward_instance<EXACT>(P, X, U, KSG, i);
+    if (r) n_reg[i] += r;
+}
+
+__global__ void __launch_bounds__(FWD_THREADS) k_forward(Problem P, const double* __restrict__ X, const double* __restrict__ U,
+                                                         const double* __restrict__ KSG, double* __restrict__ DU, double* DX,
+                                                         const int* __restrict__ status, double* __restrict__ descent)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.N || status[i] != ST_ACTIVE) return;
+    descent[i] = forward_lq_instance(P, X, U, KSG, DU, DX, i);
+}
+
+// thread (x = instance within tile, y = candidate): J of candidate c0 + y for instance i
+// need (optional): only instances with need[i] != 0 are evaluated (lazy Armijo)
+__global__ void k_candidates(Problem P, const double* __restrict__ U, const double* __restrict__ DU,
+                             const double* __restrict__ cand_steps, int c0, const int* __restrict__ status,
+                             const int* __restrict__ need, double* __restrict__ Jcand)
+{
+    const int i = blockIdx.x * CAND_TILE + threadIdx.x;
+    const int c = c0 + threadIdx.y;
+    if (i >= P.N || status[i] != ST_ACTIVE) return;
+    if (need && !need[i]) return;
+    Jcand[(size_t)c * P.Np + i] = rollout_instance<false, true>(P, U, DU, cand_steps[c], nullptr, nullptr, i);
+}
+
+// lazy Armijo, first round: candidate 0 for every active instance, writing the trajectory tentatively into
+// the next slot (it IS the update whenever the candidate is accepted)
+__global__ void __launch_bounds__(ROLL_THREADS) k_candidate0_write(Problem P, const double* __restrict__ U, const double* __restrict__ DU,
+                                                                   const double* __restrict__ cand_steps, double* __restrict__ Xn,
+                                                                   double* __restrict__ Un, const int* __restrict__ status,
+                                                                   double* __restrict__ Jcand)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.N || status[i] != ST_ACTIVE) return;
+    Jcand[i] = rollout_instance<true, true>(P, U, DU, cand_steps[0], Xn, Un, i);
+}
+
+// lazy Armijo: after candidate 0, flag the instances that need the remaining candidates
+__global__ void k_lazy_need(NewtonOpts O, NewtonState S, const double* __restrict__ cand_steps, int N, int* __restrict__ need,
+                            int* __restrict__ n_need)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int nd = 0;
+    if (S.status[i] == ST_ACTIVE) {
+        const double JP = S.Jcur[i], d = S.descent[i];
+        nd = (S.Jcand[i] > JP + O.cc * cand_steps[0] * d) ? 1 : 0;
+    }
+    need[i] = nd;
+    if (nd) atomicAdd(n_need, 1);
+}
+
+__global__ void k_select(NewtonOpts O, NewtonState S, const double* __restrict__ cand_steps, int kk, int N, int Np)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N || S.status[i] != ST_ACTIVE) return;
+    armijo_select_instance(O, S, cand_steps, kk, Np, i);
+}
+
+// get_update with the per-instance step + termination bookkeeping.
+// only (optional): when non-null, instances with only[i] == 0 keep the trajectory already present in the next
+// slot (lazy Armijo: candidate 0 was accepted and is already there) and just run the bookkeeping.
+__global__ void __launch_bounds__(ROLL_THREADS) k_update(Problem P, NewtonOpts O, NewtonState S, const double* __restrict__ U,
+                                                         const double* __restrict__ DU, double* __restrict__ Xn, double* __restrict__ Un,
+                                                         const int* __restrict__ only, int kk, int bookkeeping)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.N || S.status[i] != ST_ACTIVE) return;
+    double Jn;
+    if (only && !only[i]) Jn = S.Jcand[i];
+    else Jn = rollout_instance<true, true>(P, U, DU, S.step[i], Xn, Un, i);
+    if (bookkeeping) newton_finish_instance(O, S, Jn, kk, i);
+    else S.Jcur[i] = Jn;
+}
+
+__global__ void k_count_active(const int* __restrict__ status, int N, int* __restrict__ count, long long* __restrict__ iters_sum,
+                               const int* __restrict__ iters)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int a = 0;
+    long long it = 0;
+    if (i < N) { a = status[i] == ST_ACTIVE; it = iters[i]; }
+    for (int o = 16; o; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); it += __shfl_down_sync(0xffffffffu, it, o); }
+    if ((threadIdx.x & 31) == 0) {
+        if (a) atomicAdd(count, a);
+        if (it) atomicAdd((unsigned long long*)iters_sum, (unsigned long long)it);
+    }
+}
+
+__global__ void __launch_bounds__(ROLL_THREADS) k_track(Problem P, const double* __restrict__ Kt, const double* __restrict__ xopt,
+                                                        const double* __restrict__ uopt, const double* __restrict__ xstart,
+                                                        double* __restrict__ Xn, double* __restrict__ Un)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.N) return;
+    track_instance(P, Kt, xopt, uopt, xstart, Xn, Un, i);
+}
+
+__global__ void __launch_bounds__(ROLL_THREADS) k_init_guess(Problem P, double kp, double kt, double* __restrict__ Xn, double* __restrict__ Un)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.N) return;
+    init_guess_instance(P, kp, kt, Xn, Un, i);
+}
+
+__global__ void k_step_batch(Model M, int q32, int n, const double* __restrict__ x, const double* __restrict__ u,
+                             const double* __restrict__ lam, double* xxp, double* A, double* B, double* fxx, double* fux)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    double xs[NS], us[NI], ls[NS];
+    for (int c = 0; c < NS; ++c) xs[c] = x[(size_t)s * NS + c];
+    for (int c = 0; c < NI; ++c) us[c] = u[(size_t)s * NI + c];
+    if (lam) for (int c = 0; c < NS; ++c) ls[c] = lam[(size_t)s * NS + c];
+    const size_t nxx = lam ? 36 : 216, nux = lam ? 12 : 72;
+    step_sample(M, q32 != 0, xs, us, lam ? ls : nullptr, xxp ? xxp + (size_t)s * NS : nullptr, A ? A + (size_t)s * 36 : nullptr,
+                B ? B + (size_t)s * 12 : nullptr, fxx ? fxx + s * nxx : nullptr, fux ? fux + s * nux : nullptr);
+}
+
+__global__ void k_cost_batch(Weights W, int n, const double* __restrict__ x, const double* __restrict__ u, const double* __restrict__ xr,
+                             const double* __restrict__ ur, double* ll, double* lx, double* lu, double* llT, double* lTx)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    double l1 = 0, l2 = 0, gx[NS], gu[NI], gT[NS];
+    cost_sample(W, x + (size_t)s * NS, u ? u + (size_t)s * NI : nullptr, xr + (size_t)s * NS, ur ? ur + (size_t)s * NI : nullptr,
+                (u && (ll || lx || lu)) ? &l1 : nullptr, gx, gu, (llT || lTx) ? &l2 : nullptr, gT);
+    if (ll) ll[s] = l1;
+    if (lx) for (int c = 0; c < NS; ++c) lx[(size_t)s * NS + c] = gx[c];
+    if (lu) for (int c = 0; c < NI; ++c) lu[(size_t)s * NI + c] = gu[c];
+    if (llT) llT[s] = l2;
+    if (lTx) for (int c = 0; c < NS; ++c) lTx[(size_t)s * NS + c] = gT[c];
+}
+
+template <int N>
+__global__ void k_lq_dense(int nb, int TT, const double* A, const double* B, const double* Q, const double* R, const double* S,
+                           const double* Qf, const double* x0, const double* q, const double* r, const double* qf, double* K, double* P,
+                           double* xout, double* uout, int* n_reg)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const size_t t = (size_t)b * TT;
+    lq_dense_problem<N>(TT, A + t * 36, B + t * 12, Q + t * 36, R + t * 4, S + t * 12, Qf + (size_t)b * 36, x0 + (size_t)b * NS,
+                        q ? q + t * NS : nullptr, r ? r + t * NI : nullptr, qf ? qf + (size_t)b * NS : nullptr, K + t * NI * N,
+                        P ? P + t * N * N : nullptr, xout + t * NS, uout + t * NI, n_reg ? n_reg + b : nullptr);
+}
+
+// ---- layout conversion: host (n, C, TT) chunk  <->  SoA [TT][C][Np] ------------------------------------
+__global__ void k_to_soa(const double* __restrict__ src, double* __restrict__ dst, int n0, int nchunk, int C, int TT, int Np)
+{
+    __shared__ double tile[32][33];
+    const int c = blockIdx.z, tb = blockIdx.x * 32, nb = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int n = nb + r, t = tb + threadIdx.x;
+        if (n < nchunk && t < TT) tile[r][threadIdx.x] = src[((size_t)n * C + c) * TT + t];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int t = tb + r, n = nb + threadIdx.x;
+        if (n < nchunk && t < TT) dst[((size_t)t * C + c) * Np + n0 + n] = tile[threadIdx.x][r];
+    }
+}
+
+// s0..s2: up to three source slots; slot[i] selects per instance (-1 -> zeros; NULL -> s0); dup_last: t = TT-1 reads TT-2
+__global__ void k_from_soa(const double* __restrict__ s0, const double* __restrict__ s1, const double* __restrict__ s2,
+                           const int* __restrict__ slot, double* __restrict__ dst, int n0, int nchunk, int C, int TT, int Np, int dup_last)
+{
+    __shared__ double tile[32][33];
+    const int c = blockIdx.z, tb = blockIdx.x * 32, nb = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int t = tb + r;
+        const int n = nb + threadIdx.x;
+        if (n < nchunk && t < TT) {
+            if (dup_last && t == TT - 1 && TT > 1) t = TT - 2;
+            const int sl = slot ? slot[n0 + n] : 0;
+            const double* s = sl == 0 ? s0 : (sl == 1 ? s1 : s2);
+            tile[r][threadIdx.x] = sl < 0 ? 0.0 : s[((size_t)t * C + c) * Np + n0 + n];
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int n = nb + r, t = tb + threadIdx.x;
+        if (n < nchunk && t < TT) dst[((size_t)n * C + c) * TT + t] = tile[r][threadIdx.x];
+    }
+}
+
+__global__ void k_fill_int(int* p, int n, int v_lo, int n_lo, int v_hi)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i < n_lo ? v_lo : v_hi;
+}
+
+__global__ void k_result_slot_default(const int* __restrict__ status, int* __restrict__ slot_out, const int* __restrict__ result_slot,
+                                      int newest, int N)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) slot_out[i] = status[i] == ST_ACTIVE ? newest : result_slot[i];
+}
+
+// ---- microbenchmarks for the roofline denominators ----------------------------------------------------
+__global__ void k_fp64_peak(double* out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+__global__ void k_copy(const double2* __restrict__ a, double2* __restrict__ b, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
+}
+
+// ======================================================================================================
+// context
+// ======================================================================================================
+struct acoc_ctx {
+    int device = 0, N = 0, Np = 0, TT = 0;
+    unsigned flags = 0;
+    cudaStream_t stream = nullptr;
+    Problem P;
+    NewtonOpts O;
+    NewtonState S;
+    bool have_model = false, have_weights = false, have_refs = false, have_init = false;
+    int kk = 0;  // Newton iterations (loop bodies) executed by the lock-step driver
+    double *X[3] = {nullptr, nullptr, nullptr}, *U[3] = {nullptr, nullptr, nullptr};
+    double *DU = nullptr, *KSG = nullptr, *xref = nullptr, *uref = nullptr, *x0 = nullptr, *cand_steps = nullptr;
+    double* stage = nullptr;  // device staging for layout conversion
+    size_t stage_doubles = 0;
+    int *need = nullptr, *counters = nullptr, *slot_tmp = nullptr;
+    long long* iters_sum = nullptr;
+    std::vector<void*> allocs;
+    unsigned long long bytes = 0;
+    // timing
+    bool profiling = false;
+    cudaEvent_t ev[8];
+    bool ev_ok = false;
+    double total_ms = 0, phase_ms[6] = {0, 0, 0, 0, 0, 0};
+    long long launches = 0;
+    bool weights_sym = true;
+};
+
+template <typename T>
+static int dalloc(acoc_ctx* c, T** p, size_t n)
+{
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+    if (e != cudaSuccess) return fail(ACOC_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    e = cudaMemsetAsync(q, 0, n * sizeof(T), c->stream);
+    if (e != cudaSuccess) return fail(ACOC_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    c->allocs.push_back(q);
+    c->bytes += n * sizeof(T);
+    *p = (T*)q;
+    return 0;
+}
+#define TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+
+static int use_device(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(ACOC_ERR_CUDA, "no CUDA device available (%s): libacoc has no CPU fallback", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(ACOC_ERR_INVALID, "device %d out of range (0..%d)", device, n - 1);
+    CK(cudaSetDevice(device));
+    return 0;
+}
+
+static void default_opts(NewtonOpts* o)
+{
+    o->max_iters = 200; o->armijo_maxiters = 10; o->exact_after = 8;
+    o->stepsize_0 = 1.0; o->cc = 0.5; o->beta = 0.7; o->term_cond = -1e-6;
+}
+
+static int alloc_history(acoc_ctx* c)
+{
+    const size_t Np = c->Np;
+    TRY(dalloc(c, &c->S.hist_J, (size_t)c->O.max_iters * Np));
+    TRY(dalloc(c, &c->S.hist_descent, (size_t)c->O.max_iters * Np));
+    TRY(dalloc(c, &c->S.hist_step, (size_t)c->O.max_iters * Np));
+    TRY(dalloc(c, &c->S.hist_ncand, (size_t)c->O.max_iters * Np));
+    TRY(dalloc(c, &c->S.Jcand, (size_t)(c->O.armijo_maxiters + 1) * Np));
+    TRY(dalloc(c, &c->cand_steps, (size_t)c->O.armijo_maxiters + 2));
+    std::vector<double> cs(c->O.armijo_maxiters + 1);
+    double s = c->O.stepsize_0;
+    for (int k = 0; k <= c->O.armijo_maxiters; ++k) { cs[k] = s; s = c->O.beta * s; }  // stepsize = beta*stepsize, optcon.py:270
+    CK(cudaMemcpyAsync(c->cand_steps, cs.data(), cs.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int reset_state(acoc_ctx* c)
+{
+    const int Np = c->Np, N = c->N;
+    k_fill_int<<<(Np + 255) / 256, 256, 0, c->stream>>>(c->S.status, Np, ST_ACTIVE, N, ST_PAD);
+    CK(cudaMemsetAsync(c->S.iters, 0, Np * sizeof(int), c->stream));
+    CK(cudaMemsetAsync(c->S.n_reg, 0, Np * sizeof(int), c->stream));
+    CK(cudaMemsetAsync(c->S.result_slot, 0, Np * sizeof(int), c->stream));
+    CK(cudaMemsetAsync(c->S.Jcur, 0, Np * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->S.descent, 0, Np * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->S.step, 0, Np * sizeof(double), c->stream));
+    CK(cudaGetLastError());
+    c->kk = 0;
+    return 0;
+}
+
+// host (n,C,TT) -> SoA, chunked through the staging buffer
+static int upload_soa(acoc_ctx* c, const double* host, double* dst, int n, int C, int Np)
+{
+    const int TT = c->TT;
+    const size_t per = (size_t)C * TT;
+    int chunk = (int)std::min<size_t>((size_t)n, std::max<size_t>(1, c->stage_doubles / per));
+    for (int n0 = 0; n0 < n; n0 += chunk) {
+        const int nc = std::min(chunk, n - n0);
+        CK(cudaMemcpyAsync(c->stage, host + (size_t)n0 * per, (size_t)nc * per * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        dim3 grid((TT + 31) / 32, (nc + 31) / 32, C), block(32, 8);
+        k_to_soa<<<grid, block, 0, c->stream>>>(c->stage, dst, n0, nc, C, TT, Np);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(c->stream));  // the staging buffer is reused by the next chunk
+    }
+    return 0;
+}
+
+static int download_soa(acoc_ctx* c, const double* s0, const double* s1, const double* s2, const int* slot, double* host, int n, int C,
+                        int Np, int dup_last)
+{
+    const int TT = c->TT;
+    const size_t per = (size_t)C * TT;
+    int chunk = (int)std::min<size_t>((size_t)n, std::max<size_t>(1, c->stage_doubles / per));
+    for (int n0 = 0; n0 < n; n0 += chunk) {
+        const int nc = std::min(chunk, n - n0);
+        dim3 grid((TT + 31) / 32, (nc + 31) / 32, C), block(32, 8);
+        k_from_soa<<<grid, block, 0, c->stream>>>(s0, s1, s2, slot, c->stage, n0, nc, C, TT, Np, dup_last);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(host + (size_t)n0 * per, c->stage, (size_t)nc * per * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+static bool is_diag(const double* M, int n)
+{
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) if (i != j && M[i * n + j] != 0.0) return false;
+    return true;
+}
+static bool is_sym(const double* M, int n)
+{
+    for (int i = 0; i < n; ++i) for (int j = 0; j < i; ++j) if (M[i * n + j] != M[j * n + i]) return false;
+    return true;
+}
+static void fill_weights(Weights* W, const double* Q, const double* R, const double* QT)
+{
+    memcpy(W->Q, Q, sizeof(W->Q)); memcpy(W->R, R, sizeof(W->R)); memcpy(W->QT, QT, sizeof(W->QT));
+    W->diag = is_diag(Q, 6) && is_diag(R, 2) && is_diag(QT, 6);
+}
+
+// ======================================================================================================
+// C ABI -- library
+// ======================================================================================================
+// (the functions below are declared extern "C" in acoc.h, which gives these definitions C linkage)
+
+int acoc_version(void) { return ACOC_VERSION; }
+const char* acoc_last_error(void) { return g_err.c_str(); }
+
+int acoc_device_count(int* count)
+{
+    REQUIRE(count, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; return fail(ACOC_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *count = n;
+    return 0;
+}
+
+int acoc_device_info(int device, char* name, int len, int* sm_count, unsigned long long* mem_bytes, int* cc)
+{
+    TRY(use_device(device));
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, device));
+    if (name && len > 0) { strncpy(name, p.name, len - 1); name[len - 1] = 0; }
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (mem_bytes) *mem_bytes = p.totalGlobalMem;
+    if (cc) *cc = p.major * 10 + p.minor;
+    return 0;
+}
+
+// ======================================================================================================
+// pointwise entry points
+// ======================================================================================================
+struct TmpBuf {
+    std::vector<void*> p;
+    ~TmpBuf() { for (void* q : p) cudaFree(q); }
+    template <typename T> int up(T** d, const T* h, size_t n)
+    {
+        *d = nullptr;
+        if (!h) return 0;
+        void* q;
+        CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+        p.push_back(q);
+        CK(cudaMemcpy(q, h, n * sizeof(T), cudaMemcpyHostToDevice));
+        *d = (T*)q;
+        return 0;
+    }
+    template <typename T> int out(T** d, const T* h, size_t n)
+    {
+        *d = nullptr;
+        if (!h) return 0;
+        void* q;
+        CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+        p.push_back(q);
+        CK(cudaMemset(q, 0, n * sizeof(T)));
+        *d = (T*)q;
+        return 0;
+    }
+};
+#define DOWN(h, d, n) do { if (h) CK(cudaMemcpy(h, d, (size_t)(n) * sizeof(*(h)), cudaMemcpyDeviceToHost)); } while (0)
+
+int acoc_step_batch(int device, int n, const double* params, int state_f64, const double* x, const double* u, const double* lmbd,
+                    double* xxp, double* A, double* B, double* fxx, double* fux)
+{
+    REQUIRE(n > 0 && params && x && u, "acoc_step_batch: n > 0 and params, x, u must be given");
+    TRY(use_device(device));
+    const Model M = make_model(params);
+    TmpBuf t;
+    double *dx, *du, *dl, *oxp, *oA, *oB, *oxx, *oux;
+    const size_t nxx = lmbd ? 36 : 216, nux = lmbd ? 12 : 72;
+    TRY(t.up(&dx, x, (size_t)n * 6)); TRY(t.up(&du, u, (size_t)n * 2)); TRY(t.up(&dl, lmbd, (size_t)n * 6));
+    TRY(t.out(&oxp, xxp, (size_t)n * 6)); TRY(t.out(&oA, A, (size_t)n * 36)); TRY(t.out(&oB, B, (size_t)n * 12));
+    TRY(t.out(&oxx, fxx, n * nxx)); TRY(t.out(&oux, fux, n * nux));
+    k_step_batch<<<(n + 127) / 128, 128>>>(M, state_f64 ? 0 : 1, n, dx, du, dl, oxp, oA, oB, oxx, oux);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    DOWN(xxp, oxp, (size_t)n * 6); DOWN(A, oA, (size_t)n * 36); DOWN(B, oB, (size_t)n * 12);
+    DOWN(fxx, oxx, n * nxx); DOWN(fux, oux, n * nux);
+    return 0;
+}
+
+int acoc_cost_batch(int device, int n, const double* Q, const double* R, const double* QT, const double* x, const double* u,
+                    const double* xr, const double* ur, double* ll, double* lx, double* lu, double* llT, double* lTx)
+{
+    REQUIRE(n > 0 && Q && R && QT && x && xr, "acoc_cost_batch: n > 0 and Q, R, QT, x, xr must be given");
+    REQUIRE((u == nullptr) == (ur == nullptr), "acoc_cost_batch: u and ur must be given together");
+    REQUIRE(u || !(ll || lx || lu), "acoc_cost_batch: stage outputs need u, ur");
+    TRY(use_device(device));
+    Weights W;
+    fill_weights(&W, Q, R, QT);
+    TmpBuf t;
+    double *dx, *du, *dxr, *dur, *oll, *olx, *olu, *ollT, *olTx;
+    TRY(t.up(&dx, x, (size_t)n * 6)); TRY(t.up(&du, u, (size_t)n * 2)); TRY(t.up(&dxr, xr, (size_t)n * 6)); TRY(t.up(&dur, ur, (size_t)n * 2));
+    TRY(t.out(&oll, ll, n)); TRY(t.out(&olx, lx, (size_t)n * 6)); TRY(t.out(&olu, lu, (size_t)n * 2));
+    TRY(t.out(&ollT, llT, n)); TRY(t.out(&olTx, lTx, (size_t)n * 6));
+    k_cost_batch<<<(n + 127) / 128, 128>>>(W, n, dx, du, dxr, dur, oll, olx, olu, ollT, olTx);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    DOWN(ll, oll, n); DOWN(lx, olx, (size_t)n * 6); DOWN(lu, olu, (size_t)n * 2); DOWN(llT, ollT, n); DOWN(lTx, olTx, (size_t)n * 6);
+    return 0;
+}
+
+static int lq_dense_dev(int nb, int TT, bool aug, const double* A, const double* B, const double* Q, const double* R, const double* S,
+                        const double* Qf, const double* x0, const double* q, const double* r, const double* qf, double* K, double* P,
+                        double* xo, double* uo, int* nreg, cudaStream_t st)
+{
+    if (aug) k_lq_dense<7><<<(nb + 31) / 32, 32, 0, st>>>(nb, TT, A, B, Q, R, S, Qf, x0, q, r, qf, K, P, xo, uo, nreg);
+    else k_lq_dense<6><<<(nb + 31) / 32, 32, 0, st>>>(nb, TT, A, B, Q, R, S, Qf, x0, nullptr, nullptr, nullptr, K, P, xo, uo, nreg);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int acoc_ltv_lqr(int device, int nb, int TT, const double* A, const double* B, const double* Q, const double* R, const double* S,
+                 const double* Qf, const double* x0, const double* q, const double* r, const double* qf, double* K, double* P,
+                 double* xout, double* uout, int* n_reg)
+{
+    REQUIRE(nb > 0 && TT >= 2, "acoc_ltv_lqr: nb > 0 and TT >= 2 required");
+    REQUIRE(A && B && Q && R && S && Qf && x0 && K && xout && uout, "acoc_ltv_lqr: NULL matrix argument");
+    const bool aug = q || r || qf;
+    REQUIRE(!aug || (q && r && qf), "acoc_ltv_lqr: give all of q, r, qf (zero-filled if absent) or none");
+    TRY(use_device(device));
+    const int n = aug ? 7 : 6;
+    const size_t T = (size_t)nb * TT;
+    TmpBuf t;
+    double *dA, *dB, *dQ, *dR, *dS, *dQf, *dx0, *dq, *dr, *dqf, *oK, *oP, *ox, *ou;
+    int* onr;
+    TRY(t.up(&dA, A, T * 36)); TRY(t.up(&dB, B, T * 12)); TRY(t.up(&dQ, Q, T * 36)); TRY(t.up(&dR, R, T * 4)); TRY(t.up(&dS, S, T * 12));
+    TRY(t.up(&dQf, Qf, (size_t)nb * 36)); TRY(t.up(&dx0, x0, (size_t)nb * 6));
+    TRY(t.up(&dq, q, T * 6)); TRY(t.up(&dr, r, T * 2)); TRY(t.up(&dqf, qf, (size_t)nb * 6));
+    TRY(t.out(&oK, K, T * 2 * n)); TRY(t.out(&oP, P, T * n * n)); TRY(t.out(&ox, xout, T * 6)); TRY(t.out(&ou, uout, T * 2));
+    TRY(t.out(&onr, n_reg, nb));
+    TRY(lq_dense_dev(nb, TT, aug, dA, dB, dQ, dR, dS, dQf, dx0, dq, dr, dqf, oK, oP, ox, ou, onr, 0));
+    CK(cudaDeviceSynchronize());
+    DOWN(K, oK, T * 2 * n); DOWN(P, oP, T * n * n); DOWN(xout, ox, T * 6); DOWN(uout, ou, T * 2); DOWN(n_reg, onr, nb);
+    return 0;
+}
+
+// ======================================================================================================
+// context life cycle
+// ======================================================================================================
+int acoc_ctx_create(int device, int n_instances, int TT, unsigned flags, acoc_ctx** out)
+{
+    REQUIRE(out, "out is NULL");
+    *out = nullptr;
+    REQUIRE(n_instances > 0 && TT >= 3, "need n_instances > 0 and TT >= 3 (got %d, %d)", n_instances, TT);
+    TRY(use_device(device));
+    acoc_ctx* c = new acoc_ctx();
+    c->device = device; c->N = n_instances; c->Np = (n_instances + 31) / 32 * 32; c->TT = TT; c->flags = flags;
+    memset(&c->P, 0, sizeof(c->P)); memset(&c->S, 0, sizeof(c->S));
+    default_opts(&c->O);
+    auto bail = [&](int rc) { acoc_ctx_destroy(c); return rc; };
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(ACOC_ERR_CUDA, "cudaStreamCreate failed"));
+    const size_t Np = c->Np, T = TT;
+    int rc = 0;
+    for (int s = 0; s < 3 && !rc; ++s) { rc = dalloc(c, &c->X[s], T * 6 * Np); if (!rc) rc = dalloc(c, &c->U[s], T * 2 * Np); }
+    if (!rc) rc = dalloc(c, &c->DU, T * 2 * Np);
+    if (!rc) rc = dalloc(c, &c->KSG, T * 16 * Np);
+    const bool shared = flags & ACOC_REFS_SHARED;
+    if (!rc) rc = dalloc(c, &c->xref, shared ? T * 6 : T * 6 * Np);
+    if (!rc) rc = dalloc(c, &c->uref, shared ? T * 2 : T * 2 * Np);
+    if (!rc) rc = dalloc(c, &c->x0, 6 * Np);
+    if (!rc) rc = dalloc(c, &c->S.status, Np);
+    if (!rc) rc = dalloc(c, &c->S.iters, Np);
+    if (!rc) rc = dalloc(c, &c->S.result_slot, Np);
+    if (!rc) rc = dalloc(c, &c->S.n_reg, Np);
+    if (!rc) rc = dalloc(c, &c->S.Jcur, Np);
+    if (!rc) rc = dalloc(c, &c->S.descent, Np);
+    if (!rc) rc = dalloc(c, &c->S.step, Np);
+    if (!rc) rc = dalloc(c, &c->need, Np);
+    if (!rc) rc = dalloc(c, &c->slot_tmp, Np);
+    if (!rc) rc = dalloc(c, &c->counters, 4);
+    if (!rc) rc = dalloc(c, &c->iters_sum, 2);
+    // staging: up to 256 MiB or the whole batch, whichever is smaller (at least one instance of 6*TT doubles)
+    c->stage_doubles = std::max<size_t>(6 * T, std::min<size_t>((size_t)n_instances * 6 * T, (size_t)32 << 20));
+    if (!rc) rc = dalloc(c, &c->stage, c->stage_doubles);
+    if (!rc) rc = alloc_history(c);
+    if (rc) return bail(rc);
+    c->P.N = c->N; c->P.Np = c->Np; c->P.TT = TT;
+    c->P.q32 = (flags & ACOC_STATE_F64) ? 0 : 1;
+    c->P.ref_shared = shared ? 1 : 0;
+    c->P.xref = c->xref; c->P.uref = c->uref; c->P.x0 = c->x0;
+    const double defp[9] = {0.1716, 2.395, 3.256, 12.0, 9.81, 0.61, 1.2, 0.24, 1e-3};
+    c->P.M = make_model(defp);
+    c->have_model = true;
+    for (int e = 0; e < 8; ++e) if (cudaEventCreate(&c->ev[e]) != cudaSuccess) return bail(fail(ACOC_ERR_CUDA, "cudaEventCreate failed"));
+    c->ev_ok = true;
+    rc = reset_state(c);
+    if (rc) return bail(rc);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail(fail(ACOC_ERR_CUDA, "stream sync failed"));
+    *out = c;
+    return 0;
+}
+
+int acoc_ctx_destroy(acoc_ctx* c)
+{
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->ev_ok) for (int e = 0; e < 8; ++e) cudaEventDestroy(c->ev[e]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int acoc_ctx_device_bytes(const acoc_ctx* c, unsigned long long* bytes)
+{
+    REQUIRE(c && bytes, "NULL argument");
+    *bytes = c->bytes;
+    return 0;
+}
+
+int acoc_set_model(acoc_ctx* c, const double* params)
+{
+    REQUIRE(c && params, "NULL argument");
+    REQUIRE(params[3] != 0.0 && params[7] != 0.0, "mass and inertia must be non-zero");
+    c->P.M = make_model(params);
+    return 0;
+}
+
+int acoc_set_weights(acoc_ctx* c, const double* Q, const double* R, const double* QT)
+{
+    REQUIRE(c && Q && R && QT, "NULL argument");
+    // the fused backward sweep keeps P symmetric (21 registers); that needs symmetric cost Hessians
+    REQUIRE(is_sym(Q, 6) && is_sym(R, 2) && is_sym(QT, 6), "Q, R and QT must be symmetric for the batched Newton path");
+    fill_weights(&c->P.W, Q, R, QT);
+    c->have_weights = true;
+    return 0;
+}
+
+int acoc_set_options(acoc_ctx* c, const acoc_newton_options* o)
+{
+    REQUIRE(c && o, "NULL argument");
+    REQUIRE(o->max_iters >= 2 && o->max_iters <= 100000, "max_iters out of range");
+    REQUIRE(o->armijo_maxiters >= 1 && o->armijo_maxiters <= 30, "armijo_maxiters must be in 1..30");
+    TRY(use_device(c->device));
+    c->O.max_iters = o->max_iters; c->O.armijo_maxiters = o->armijo_maxiters; c->O.exact_after = o->exact_after;
+    c->O.stepsize_0 = o->stepsize_0; c->O.cc = o->cc; c->O.beta = o->beta; c->O.term_cond = o->term_cond;
+    TRY(alloc_history(c));  // (old history buffers are released with the context)
+    return reset_state(c);
+}
+
+int acoc_set_refs(acoc_ctx* c, const double* xx_ref, const double* uu_ref)
+{
+    REQUIRE(c && xx_ref && uu_ref, "NULL argument");
+    TRY(use_device(c->device));
+    if (c->P.ref_shared) {
+        TRY(upload_soa(c, xx_ref, c->xref, 1, 6, 1));
+        TRY(upload_soa(c, uu_ref, c->uref, 1, 2, 1));
+    } else {
+        TRY(upload_soa(c, xx_ref, c->xref, c->N, 6, c->Np));
+        TRY(upload_soa(c, uu_ref, c->uref, c->N, 2, c->Np));
+    }
+    c->have_refs = true;
+    return 0;
+}
+
+int acoc_set_init(acoc_ctx* c, const double* xx_init, const double* uu_init)
+{
+    REQUIRE(c && xx_init && uu_init, "NULL argument");
+    TRY(use_device(c->device));
+    TRY(reset_state(c));
+    TRY(upload_soa(c, xx_init, c->X[0], c->N, 6, c->Np));
+    TRY(upload_soa(c, uu_init, c->U[0], c->N, 2, c->Np));
+    CK(cudaMemcpyAsync(c->x0, c->X[0], (size_t)6 * c->Np * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));  // x0 = xx[:,0,0], optcon.py:398
+    CK(cudaStreamSynchronize(c->stream));
+    c->have_init = true;
+    return 0;
+}
+
+int acoc_init_guess(acoc_ctx* c, double kp, double kt)
+{
+    REQUIRE(c, "NULL argument");
+    if (!c->have_refs) return fail(ACOC_ERR_STATE, "acoc_init_guess: set the references first");
+    TRY(use_device(c->device));
+    TRY(reset_state(c));
+    k_init_guess<<<(c->N + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, 0, c->stream>>>(c->P, kp, kt, c->X[0], c->U[0]);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->x0, c->X[0], (size_t)6 * c->Np * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->have_init = true;
+    return 0;
+}
+
+// ======================================================================================================
+// Newton pieces
+// ======================================================================================================
+static int ready(acoc_ctx* c)
+{
+    if (!c) return fail(ACOC_ERR_INVALID, "ctx is NULL");
+    if (!c->have_weights || !c->have_refs || !c->have_init)
+        return fail(ACOC_ERR_STATE, "context not ready: set weights (%d), references (%d) and the initial trajectory (%d) first",
+                    (int)c->have_weights, (int)c->have_refs, (int)c->have_init);
+    return use_device(c->device);
+}
+
+static int launch_cost(acoc_ctx* c)
+{
+    const int cur = c->kk % 3;
+    k_traj_cost<<<(c->N + 127) / 128, 128, 0, c->stream>>>(c->P, c->X[cur], c->U[cur], c->S.status, c->S.Jcur);
+    CK(cudaGetLastError());
+    ++c->launches;
+    return 0;
+}
+static int launch_backward(acoc_ctx* c, bool exact)
+{
+    const int cur = c->kk % 3, g = (c->N + BWD_THREADS - 1) / BWD_THREADS;
+    if (exact) k_backward<true><<<g, BWD_THREADS, 0, c->stream>>>(c->P, c->X[cur], c->U[cur], c->KSG, c->S.status, c->S.n_reg);
+    else k_backward<false><<<g, BWD_THREADS, 0, c->stream>>>(c->P, c->X[cur], c->U[cur], c->KSG, c->S.status, c->S.n_reg);
+    CK(cudaGetLastError());
+    ++c->launches;
+    return 0;
+}
+static int launch_forward(acoc_ctx* c)
+{
+    const int cur = c->kk % 3;
+    k_forward<<<(c->N + FWD_THREADS - 1) / FWD_THREADS, FWD_THREADS, 0, c->stream>>>(c->P, c->X[cur], c->U[cur], c->KSG, c->DU, nullptr,
+                                                                                    c->S.status, c->S.descent);
+    CK(cudaGetLastError());
+    ++c->launches;
+    return 0;
+}
+// Armijo: fills S.step and the history row kk.  Returns through *lazy_only whether the update may skip
+// instances whose candidate 0 is already in the next slot.
+static int launch_armijo(acoc_ctx* c, bool* lazy_only)
+{
+    const int cur = c->kk % 3, nxt = (c->kk + 1) % 3, N = c->N, nc = c->O.armijo_maxiters;
+    *lazy_only = false;
+    if ((c->flags & ACOC_ARMIJO_LAZY) && nc > 1) {
+        k_candidate0_write<<<(N + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, 0, c->stream>>>(c->P, c->U[cur], c->DU, c->cand_steps,
+                                                                                                c->X[nxt], c->U[nxt], c->S.status, c->S.Jcand);
+        CK(cudaGetLastError());
+        CK(cudaMemsetAsync(c->counters, 0, sizeof(int), c->stream));
+        k_lazy_need<<<(N + 255) / 256, 256, 0, c->stream>>>(c->O, c->S, c->cand_steps, N, c->need, c->counters);
+        CK(cudaGetLastError());
+        dim3 block(CAND_TILE, nc - 1);
+        k_candidates<<<(N + CAND_TILE - 1) / CAND_TILE, block, 0, c->stream>>>(c->P, c->U[cur], c->DU, c->cand_steps, 1, c->S.status, c->need, c->S.Jcand);
+        CK(cudaGetLastError());
+        c->launches += 3;
+        *lazy_only = true;
+    } else {
+        dim3 block(CAND_TILE, nc);
+        k_candidates<<<(N + CAND_TILE - 1) / CAND_TILE, block, 0, c->stream>>>(c->P, c->U[cur], c->DU, c->cand_steps, 0, c->S.status, nullptr, c->S.Jcand);
+        CK(cudaGetLastError());
+        ++c->launches;
+    }
+    k_select<<<(N + 255) / 256, 256, 0, c->stream>>>(c->O, c->S, c->cand_steps, c->kk, N, c->Np);
+    CK(cudaGetLastError());
+    ++c->launches;
+    return 0;
+}
+static int launch_update(acoc_ctx* c, bool lazy_only, bool bookkeeping)
+{
+    const int cur = c->kk % 3, nxt = (c->kk + 1) % 3;
+    k_update<<<(c->N + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, 0, c->stream>>>(c->P, c->O, c->S, c->U[cur], c->DU, c->X[nxt], c->U[nxt],
+                                                                                      lazy_only ? c->need : nullptr, c->kk, bookkeeping ? 1 : 0);
+    CK(cudaGetLastError());
+    ++c->launches;
+    return 0;
+}
+
+static int count_active(acoc_ctx* c, int* n_active, long long* iters_sum)
+{
+    CK(cudaMemsetAsync(c->counters, 0, sizeof(int), c->stream));
+    CK(cudaMemsetAsync(c->iters_sum, 0, sizeof(long long), c->stream));
+    k_count_active<<<(c->Np + 255) / 256, 256, 0, c->stream>>>(c->S.status, c->N, c->counters, c->iters_sum, c->S.iters);
+    CK(cudaGetLastError());
+    int h = 0;
+    long long s = 0;
+    CK(cudaMemcpyAsync(&h, c->counters, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&s, c->iters_sum, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (n_active) *n_active = h;
+    if (iters_sum) *iters_sum = s;
+    return 0;
+}
+
+int acoc_newton_iterate(acoc_ctx* c, int n_iters, int* n_active_out)
+{
+    TRY(ready(c));
+    REQUIRE(n_iters >= 0, "n_iters must be >= 0");
+    const bool prof = c->profiling;
+    c->total_ms = 0; for (int p = 0; p < 6; ++p) c->phase_ms[p] = 0;
+    c->launches = 0;
+    CK(cudaEventRecord(c->ev[6], c->stream));
+    for (int it = 0; it < n_iters; ++it) {
+        if (c->kk >= c->O.max_iters - 1) break;  // for kk in range(max_iters-1), optcon.py:415
+        bool lazy_only = false;
+        if (prof) CK(cudaEventRecord(c->ev[0], c->stream));
+        if (c->kk == 0) TRY(launch_cost(c));  // later iterations inherit the cost from the update rollout
+        if (prof) CK(cudaEventRecord(c->ev[1], c->stream));
+        TRY(launch_backward(c, c->kk > c->O.exact_after));  // optcon.py:443
+        if (prof) CK(cudaEventRecord(c->ev[2], c->stream));
+        TRY(launch_forward(c));
+        if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
+        TRY(launch_armijo(c, &lazy_only));
+        if (prof) CK(cudaEventRecord(c->ev[4], c->stream));
+        TRY(launch_update(c, lazy_only, true));
+        if (prof) {
+            CK(cudaEventRecord(c->ev[5], c->stream));
+            CK(cudaEventSynchronize(c->ev[5]));
+            // phases: cost, backward, forward, candidates+select, (select folded), update
+            for (int p = 0; p < 5; ++p) {
+                float ms = 0;
+                CK(cudaEventElapsedTime(&ms, c->ev[p], c->ev[p + 1]));
+                c->phase_ms[p == 4 ? 5 : p] += ms;
+            }
+        }
+        ++c->kk;
+    }
+    CK(cudaEventRecord(c->ev[7], c->stream));
+    CK(cudaEventSynchronize(c->ev[7]));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]));
+    c->total_ms = ms;
+    if (n_active_out) TRY(count_active(c, n_active_out, nullptr));
+    return 0;
+}
+
+int acoc_newton_solve(acoc_ctx* c, long long* total_iters)
+{
+    TRY(ready(c));
+    int active = 1;
+    double total_ms = 0, phase[6] = {0, 0, 0, 0, 0, 0};
+    long long launches = 0;
+    while (active > 0 && c->kk < c->O.max_iters - 1) {
+        // check for completion every 4 iterations: one tiny D2H per check keeps the stream busy in between
+        TRY(acoc_newton_iterate(c, 4, &active));
+        total_ms += c->total_ms; launches += c->launches;
+        for (int p = 0; p < 6; ++p) phase[p] += c->phase_ms[p];
+    }
+    c->total_ms = total_ms; c->launches = launches;
+    for (int p = 0; p < 6; ++p) c->phase_ms[p] = phase[p];
+    if (total_iters) TRY(count_active(c, nullptr, total_iters));
+    return 0;
+}
+
+int acoc_sync(acoc_ctx* c)
+{
+    REQUIRE(c, "ctx is NULL");
+    TRY(use_device(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int acoc_eval_cost(acoc_ctx* c, double* J)
+{
+    TRY(ready(c));
+    TRY(launch_cost(c));
+    if (J) { CK(cudaMemcpyAsync(J, c->S.Jcur, c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream)); }
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int acoc_backward(acoc_ctx* c, int exact)
+{
+    TRY(ready(c));
+    TRY(launch_backward(c, exact != 0));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int acoc_forward(acoc_ctx* c, double* descent)
+{
+    TRY(ready(c));
+    TRY(launch_forward(c));
+    if (descent) { CK(cudaMemcpyAsync(descent, c->S.descent, c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream)); }
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int acoc_armijo(acoc_ctx* c, double* stepsize, double* costs)
+{
+    TRY(ready(c));
+    REQUIRE(c->kk < c->O.max_iters, "iteration counter exhausted");
+    // always the speculative evaluation here: this entry point reports the cost of every candidate
+    const int cur = c->kk % 3, N = c->N, nc = c->O.armijo_maxiters;
+    dim3 block(CAND_TILE, nc);
+    k_candidates<<<(N + CAND_TILE - 1) / CAND_TILE, block, 0, c->stream>>>(c->P, c->U[cur], c->DU, c->cand_steps, 0, c->S.status, nullptr, c->S.Jcand);
+    CK(cudaGetLastError());
+    k_select<<<(N + 255) / 256, 256, 0, c->stream>>>(c->O, c->S, c->cand_steps, c->kk, N, c->Np);
+    CK(cudaGetLastError());
+    if (stepsize) CK(cudaMemcpyAsync(stepsize, c->S.step, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (costs) {  // device [nc][Np] -> host [N][nc]
+        std::vector<double> tmp((size_t)nc * c->Np);
+        CK(cudaMemcpy(tmp.data(), c->S.Jcand, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < N; ++i) for (int k = 0; k < nc; ++k) costs[(size_t)i * nc + k] = tmp[(size_t)k * c->Np + i];
+    }
+    return 0;
+}
+
+int acoc_update(acoc_ctx* c, const double* stepsize)
+{
+    TRY(ready(c));
+    REQUIRE(c->kk < c->O.max_iters - 1, "iteration counter exhausted");
+    if (stepsize) CK(cudaMemcpyAsync(c->S.step, stepsize, c->N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    TRY(launch_update(c, false, false));
+    ++c->kk;
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ======================================================================================================
+// read-back
+// ======================================================================================================
+int acoc_get_result(acoc_ctx* c, double* xx_star, double* uu_star)
+{
+    TRY(ready(c));
+    REQUIRE(xx_star && uu_star, "NULL output");
+    k_result_slot_default<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->S.status, c->slot_tmp, c->S.result_slot, c->kk % 3, c->N);
+    CK(cudaGetLastError());
+    TRY(download_soa(c, c->X[0], c->X[1], c->X[2], c->slot_tmp, xx_star, c->N, 6, c->Np, 0));
+    TRY(download_soa(c, c->U[0], c->U[1], c->U[2], c->slot_tmp, uu_star, c->N, 2, c->Np, 1));  // uu_star[:,-1] = uu_star[:,-2], optcon.py:505
+    return 0;
+}
+
+int acoc_get_iterate(acoc_ctx* c, int which, double* xx, double* uu)
+{
+    TRY(ready(c));
+    REQUIRE(which == 0 || which == 1, "which must be 0 (newest) or 1 (previous)");
+    REQUIRE(which == 0 || c->kk >= 1, "no previous iterate yet");
+    const int s = (c->kk - which) % 3;
+    if (xx) TRY(download_soa(c, c->X[s], nullptr, nullptr, nullptr, xx, c->N, 6, c->Np, 0));
+    if (uu) TRY(download_soa(c, c->U[s], nullptr, nullptr, nullptr, uu, c->N, 2, c->Np, 0));
+    return 0;
+}
+
+int acoc_get_deltau(acoc_ctx* c, double* deltau)
+{
+    TRY(ready(c));
+    REQUIRE(deltau, "NULL output");
+    return download_soa(c, c->DU, nullptr, nullptr, nullptr, deltau, c->N, 2, c->Np, 0);
+}
+
+int acoc_get_gains(acoc_ctx* c, double* K, double* sigma)
+{
+    TRY(ready(c));
+    // KSG is [TT][16][Np]; as a "C = 16" trajectory it downloads to (N,16,TT): rows 0..11 = K (2x6 row-major), 12..13 = sigma
+    std::vector<double> tmp((size_t)c->N * 16 * c->TT);
+    TRY(download_soa(c, c->KSG, nullptr, nullptr, nullptr, tmp.data(), c->N, 16, c->Np, 0));
+    const size_t TT = c->TT;
+    for (int i = 0; i < c->N; ++i) {
+        const double* src = tmp.data() + (size_t)i * 16 * TT;
+        if (K) memcpy(K + (size_t)i * 12 * TT, src, 12 * TT * sizeof(double));
+        if (sigma) memcpy(sigma + (size_t)i * 2 * TT, src + 12 * TT, 2 * TT * sizeof(double));
+    }
+    return 0;
+}
+
+template <typename T>
+static int get_hist(acoc_ctx* c, const T* dev, T* host)
+{
+    if (!host) return 0;
+    const int mi = c->O.max_iters;
+    std::vector<T> tmp((size_t)mi * c->Np);
+    CK(cudaMemcpyAsync(tmp.data(), dev, tmp.size() * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < c->N; ++i) for (int k = 0; k < mi; ++k) host[(size_t)i * mi + k] = tmp[(size_t)k * c->Np + i];
+    return 0;
+}
+
+int acoc_get_history(acoc_ctx* c, double* JJ, double* descent, double* stepsize, int* n_cand)
+{
+    REQUIRE(c, "ctx is NULL");
+    TRY(use_device(c->device));
+    TRY(get_hist(c, c->S.hist_J, JJ)); TRY(get_hist(c, c->S.hist_descent, descent));
+    TRY(get_hist(c, c->S.hist_step, stepsize)); TRY(get_hist(c, c->S.hist_ncand, n_cand));
+    return 0;
+}
+
+int acoc_get_stats(acoc_ctx* c, int* iters, int* status, double* J, double* descent, int* n_reg)
+{
+    REQUIRE(c, "ctx is NULL");
+    TRY(use_device(c->device));
+    const size_t N = c->N;
+    if (iters) CK(cudaMemcpyAsync(iters, c->S.iters, N * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (status) CK(cudaMemcpyAsync(status, c->S.status, N * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (J) CK(cudaMemcpyAsync(J, c->S.Jcur, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (descent) CK(cudaMemcpyAsync(descent, c->S.descent, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (n_reg) CK(cudaMemcpyAsync(n_reg, c->S.n_reg, N * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int acoc_get_timing(acoc_ctx* c, double* total_ms, double phase_ms[6], long long* kernel_launches)
+{
+    REQUIRE(c, "ctx is NULL");
+    if (total_ms) *total_ms = c->total_ms;
+    if (phase_ms) for (int p = 0; p < 6; ++p) phase_ms[p] = c->phase_ms[p];
+    if (kernel_launches) *kernel_launches = c->launches;
+    return 0;
+}
+
+int acoc_set_profiling(acoc_ctx* c, int on)
+{
+    REQUIRE(c, "ctx is NULL");
+    c->profiling = on != 0;
+    return 0;
+}
+
+// ======================================================================================================
+// lqr_tracking
+// ======================================================================================================
+int acoc_lqr_tracking(int device, int n, int TT, const double* params, int state_f64, const double* Q, const double* R, const double* QT,
+                      const double* xx_opt, const double* uu_opt, const double* delta, double* xx_reg, double* uu_reg, double* K)
+{
+    REQUIRE(n > 0 && TT >= 3 && params && Q && R && QT && xx_opt && uu_opt && delta && xx_reg && uu_reg, "acoc_lqr_tracking: bad argument");
+    acoc_ctx* c = nullptr;
+    TRY(acoc_ctx_create(device, n, TT, (state_f64 ? ACOC_STATE_F64 : 0) | ACOC_REFS_SHARED, &c));
+    struct Guard { acoc_ctx* c; ~Guard() { acoc_ctx_destroy(c); } } guard{c};
+    TRY(acoc_set_model(c, params));
+    const Model M = c->P.M;
+    // nominal trajectory, time-major [TT][6] / [TT][2] (this is exactly the "shared reference" SoA layout)
+    TRY(upload_soa(c, xx_opt, c->xref, 1, 6, 1));
+    TRY(upload_soa(c, uu_opt, c->uref, 1, 2, 1));
+    // linearise along the nominal at all TT points (lqr_tracking.py:268-273): one thread per time step
+    TmpBuf t;
+    double *dA, *dB, *dQ, *dR, *dS, *dQf, *dx0, *dK, *dxo, *duo, *dstart;
+    TRY(t.out(&dA, xx_reg, (size_t)TT * 36)); TRY(t.out(&dB, xx_reg, (size_t)TT * 12)); TRY(t.out(&dS, xx_reg, (size_t)TT * 12));
+    TRY(t.out(&dK, xx_reg, (size_t)TT * 12)); TRY(t.out(&dxo, xx_reg, (size_t)TT * 6)); TRY(t.out(&duo, xx_reg, (size_t)TT * 2));
+    std::vector<double> Qrep((size_t)TT * 36), Rrep((size_t)TT * 4);
+    for (int k = 0; k < TT; ++k) { memcpy(&Qrep[(size_t)k * 36], Q, 36 * sizeof(double)); memcpy(&Rrep[(size_t)k * 4], R, 4 * sizeof(double)); }  // .repeat(TT), optcon.py:603-606
+    TRY(t.up(&dQ, Qrep.data(), Qrep.size())); TRY(t.up(&dR, Rrep.data(), Rrep.size())); TRY(t.up(&dQf, QT, 36)); TRY(t.up(&dx0, delta, 6));
+    k_step_batch<<<(TT + 127) / 128, 128, 0, c->stream>>>(M, c->P.q32, TT, c->xref, c->uref, nullptr, nullptr, dA, dB, nullptr, nullptr);
+    CK(cudaGetLastError());
+    TRY(lq_dense_dev(1, TT, false, dA, dB, dQ, dR, dS, dQf, dx0, nullptr, nullptr, nullptr, dK, nullptr, dxo, duo, nullptr, c->stream));
+    // perturbed initial states: x_start[c][i] = xx_opt[c][0] + delta[i][c]   (lqr_tracking.py:265)
+    std::vector<double> xs((size_t)6 * c->Np, 0.0);
+    for (int i = 0; i < n; ++i) for (int k = 0; k < 6; ++k) xs[(size_t)k * c->Np + i] = xx_opt[(size_t)k * TT] + delta[(size_t)i * 6 + k];
+    TRY(t.up(&dstart, xs.data(), xs.size()));
+    k_track<<<(n + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, 0, c->stream>>>(c->P, dK, c->xref, c->uref, dstart, c->X[0], c->U[0]);
+    CK(cudaGetLastError());
+    TRY(download_soa(c, c->X[0], nullptr, nullptr, nullptr, xx_reg, n, 6, c->Np, 0));
+    TRY(download_soa(c, c->U[0], nullptr, nullptr, nullptr, uu_reg, n, 2, c->Np, 0));
+    if (K) CK(cudaMemcpy(K, dK, (size_t)TT * 12 * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ======================================================================================================
+// roofline denominators
+// ======================================================================================================
+int acoc_measure_fp64_peak(int device, double* tflops)
+{
+    REQUIRE(tflops, "NULL output");
+    TRY(use_device(device));
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, device));
+    const int blocks = p.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+    double* out;
+    CK(cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CK(cudaEventRecord(e0));
+        k_fp64_peak<<<blocks, threads>>>(out, iters, 1.0 + rep);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) * 1e-12;
+        if (rep > 0) best = std::max(best, tf);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *tflops = best;
+    return 0;
+}
+
+int acoc_measure_copy_bw(int device, double* gbs)
+{
+    REQUIRE(gbs, "NULL output");
+    TRY(use_device(device));
+    const size_t n = (size_t)1 << 27;  // 2 GiB per buffer of double2
+    double2 *a, *b;
+    CK(cudaMalloc(&a, n * sizeof(double2)));
+    if (cudaMalloc(&b, n * sizeof(double2)) != cudaSuccess) { cudaFree(a); return fail(ACOC_ERR_NOMEM, "copy benchmark allocation failed"); }
+    CK(cudaMemset(a, 1, n * sizeof(double2)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, device));
+    double best = 0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CK(cudaEventRecord(e0));
+        k_copy<<<p.multiProcessorCount * 16, 512>>>(a, b, n);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::max(best, 2.0 * n * sizeof(double2) / (ms * 1e-3) * 1e-9);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(a); cudaFree(b);
+    *gbs = best;
+    return 0;
+}
+

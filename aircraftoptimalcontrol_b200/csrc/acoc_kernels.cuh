@@ -1,0 +1,666 @@
+// acoc_kernels.cuh -- per-trajectory sweeps of the regularized-Newton loop (one thread = one OCP instance).
+//
+// Each *_instance() function is the complete body of one kernel for one instance: it walks the horizon
+// sequentially (the Riccati / costate / rollout recurrences are true recurrences, optcon.py:434-464,
+// :719-762, :196-198) with every per-step quantity in registers.  The __global__ wrappers at the bottom map
+// threadIdx -> instance.  Trajectories live in HBM as struct-of-arrays, time-major with the instance index
+// fastest:  X[(t*6 + c)*Np + i],  U[(t*2 + c)*Np + i],  KSG[(t*16 + c)*Np + i]  -- so the 32 lanes of a warp
+// touch 32 consecutive doubles (two full 128-byte lines) on every access.
+//
+// Reference call stack covered:
+//   traj_cost_instance    optcon.py:417-424            cost of the current iterate
+//   backward_instance     optcon.py:429-464 + the Riccati / gain loops of ltv_LQR (optcon.py:716-751),
+//                         fused: linearisation, costate, lambda-contracted Hessians, P/p recursion, K, sigma
+//   forward_lq_instance   optcon.py:756-762 (LQ forward pass) + :474-477 (descent)
+//   rollout_instance      optcon.py:247-264 (one Armijo candidate) and :176-200 (get_update)
+//   armijo_select_instance optcon.py:266-273, :327 and the bookkeeping of :488-501
+//   track_instance        lqr_tracking.py:279-281
+//   init_guess_instance   aircraft_simplified.py:142-147
+#pragma once
+#include "acoc_math.cuh"
+
+namespace acoc {
+
+// ------------------------------------------------------------------------------------------------------
+// problem description shared by all sweeps
+// ------------------------------------------------------------------------------------------------------
+struct Problem {
+    Model M;
+    Weights W;
+    int N;         // instances
+    int Np;        // padded instance count (multiple of 32) = stride between components
+    int TT;        // horizon samples
+    int q32;       // 1: round the next state to float32 like aircraft_simplified.py:300
+    int ref_shared;  // 1: xref/uref hold one trajectory shared by all instances (stride 1)
+    const double* xref;  // [TT][6][Np] or [TT][6][1]
+    const double* uref;  // [TT][2][Np] or [TT][2][1]
+    const double* x0;    // [6][Np]   x0 = xx_init[:,0]  (optcon.py:398)
+};
+
+ACOC_HD size_t at(int t, int C, int c, int Np, int i) { return ((size_t)t * C + c) * (size_t)Np + i; }
+
+ACOC_HD void load_ref(const Problem& P, int t, int i, double* xr, double* ur)
+{
+    const int Nr = P.ref_shared ? 1 : P.Np, ir = P.ref_shared ? 0 : i;
+#pragma unroll
+    for (int c = 0; c < NS; ++c) xr[c] = P.xref[at(t, NS, c, Nr, ir)];
+#pragma unroll
+    for (int c = 0; c < NI; ++c) ur[c] = P.uref[at(t, NI, c, Nr, ir)];
+}
+ACOC_HD void load_xref(const Problem& P, int t, int i, double* xr)
+{
+    const int Nr = P.ref_shared ? 1 : P.Np, ir = P.ref_shared ? 0 : i;
+#pragma unroll
+    for (int c = 0; c < NS; ++c) xr[c] = P.xref[at(t, NS, c, Nr, ir)];
+}
+
+// symmetric 6x6 in 21 registers, (i <= j)
+ACOC_HD constexpr int sym(int i, int j) { return i <= j ? i * 6 - (i * (i - 1)) / 2 + (j - i) : j * 6 - (j * (j - 1)) / 2 + (i - j); }
+
+// sum_c v[c] * A[c][J] : the dot product of v with column J of the sparse Jacobian (Appendix A of SURVEY.md)
+ACOC_HD double acol(const Lin& l, double dt, const double* v, int J)
+{
+    switch (J) {
+        case 0: return v[0];
+        case 1: return v[1];
+        case 2: return fma_(l.a52, v[5], fma_(l.a22, v[2], fma_(l.a12, v[1], l.a02 * v[0])));
+        case 3: return fma_(l.a53, v[5], fma_(l.a23, v[2], v[3]));
+        case 4: return fma_(dt, v[3], v[4]);
+        default: return fma_(l.a55, v[5], fma_(l.a25, v[2], fma_(l.a15, v[1], l.a05 * v[0])));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// cost of a stored trajectory, optcon.py:417-424
+// ------------------------------------------------------------------------------------------------------
+ACOC_HD double traj_cost_instance(const Problem& P, const double* X, const double* U, int i)
+{
+    double J = 0.0, dx[NS], du[NI], xr[NS], ur[NI];
+    for (int t = 0; t < P.TT - 1; ++t) {
+        load_ref(P, t, i, xr, ur);
+#pragma unroll
+        for (int c = 0; c < NS; ++c) dx[c] = X[at(t, NS, c, P.Np, i)] - xr[c];
+#pragma unroll
+        for (int c = 0; c < NI; ++c) du[c] = U[at(t, NI, c, P.Np, i)] - ur[c];
+        J += stage_cost(P.W, dx, du);
+    }
+    load_xref(P, P.TT - 1, i, xr);
+#pragma unroll
+    for (int c = 0; c < NS; ++c) dx[c] = X[at(P.TT - 1, NS, c, P.Np, i)] - xr[c];
+    J += term_cost(P.W, dx);
+    return J;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// one step of the fused backward recursion
+// ------------------------------------------------------------------------------------------------------
+// In : Pm (sym 6x6), p, lam  at t+1;  Lin at (x_t,u_t);  q = Q dx, r = R du;  Hess (used iff EXACT)
+// Out: Pm, p, lam at t;  K (2x6 row-major), sig (2), g (2) = B'lam_{t+1} + r
+// Equations (decomposition of the reference's 7x7 augmented recursion, optcon.py:673-689, :727-728, :743-751,
+// with P~ = [[pi, p'],[p, P]], S~ = [r/2, S], Q~ = [[0, q'/2],[q/2, Q]]):
+//   Mx = B'PA + S,  m = B'p + r/2,  G = R + B'PB
+//   P_t = Q + A'PA - Mx' G^-1 Mx          p_t = q/2 + A'p - Mx' G^-1 m
+//   MM  = G, or G + 0.5 I when G has a non-positive eigenvalue;  K = -MM^-1 Mx,  sigma = -MM^-1 m
+template <bool EXACT>
+ACOC_HD int riccati_step(const Model& M, const Weights& W, const Lin& l, const Hess& h, const double* q, const double* r,
+                         double* Pm, double* p, double* lam, double* K, double* sig, double* g)
+{
+    const double dt = M.dt, b41 = M.b41;
+    // g = B' lam_{t+1} + r  (optcon.py:475)
+    g[0] = fma_(l.b50, lam[5], fma_(l.b20, lam[2], r[0]));
+    g[1] = fma_(b41, lam[4], r[1]);
+    // G = R + B'PB, m = B'p + r/2  (need P_{t+1}, p_{t+1})
+    const double P22 = Pm[sym(2, 2)], P25 = Pm[sym(2, 5)], P55 = Pm[sym(5, 5)], P24 = Pm[sym(2, 4)], P45 = Pm[sym(4, 5)], P44 = Pm[sym(4, 4)];
+    const double pb2 = fma_(l.b50, P25, l.b20 * P22), pb5 = fma_(l.b50, P55, l.b20 * P25);
+    const double G00 = fma_(l.b50, pb5, fma_(l.b20, pb2, W.R[0]));
+    const double G01 = fma_(b41, fma_(l.b50, P45, l.b20 * P24), W.R[1]);
+    const double G11 = fma_(b41 * b41, P44, W.R[3]);
+    const double m0 = fma_(l.b50, p[5], fma_(l.b20, p[2], 0.5 * r[0]));
+    const double m1 = fma_(b41, p[4], 0.5 * r[1]);
+
+    // column sweep: W = P A (column j), N = A'W (upper triangle), Mx = B'W (+S)
+    double Pn[21], Mx0[NS], Mx1[NS];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        double Wc[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            double row[NS];
+#pragma unroll
+            for (int c = 0; c < NS; ++c) row[c] = Pm[sym(k, c)];
+            Wc[k] = acol(l, dt, row, j);
+        }
+#pragma unroll
+        for (int i = 0; i <= j; ++i) Pn[sym(i, j)] = acol(l, dt, Wc, i);
+        Mx0[j] = fma_(l.b50, Wc[5], l.b20 * Wc[2]);
+        Mx1[j] = b41 * Wc[4];
+    }
+    if (EXACT) { Mx0[2] += h.s2; Mx0[3] += h.s3; Mx0[5] += h.s5; }  // S = lux + fux (optcon.py:446)
+
+    // A'p and A'lam
+    double Atp[NS], Atl[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) { Atp[i] = acol(l, dt, p, i); Atl[i] = acol(l, dt, lam, i); }
+
+    // G^-1 (explicit inverse, optcon.py:728)
+    const double det = fma_(G00, G11, -(G01 * G01));
+    const double idet = 1.0 / det;
+    const double gi00 = G11 * idet, gi01 = -G01 * idet, gi11 = G00 * idet;
+    double Y0[NS], Y1[NS];  // G^-1 Mx
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        Y0[j] = fma_(gi01, Mx1[j], gi00 * Mx0[j]);
+        Y1[j] = fma_(gi11, Mx1[j], gi01 * Mx0[j]);
+    }
+    const double y0 = fma_(gi01, m1, gi00 * m0), y1 = fma_(gi11, m1, gi01 * m0);
+
+    // gains: positive-definiteness test on G (optcon.py:743-749) -- eigenvalues of the symmetric 2x2
+    const double hd = 0.5 * (G00 - G11), mid = 0.5 * (G00 + G11);
+    const double rad = sqrt(fma_(hd, hd, G01 * G01));
+    int reg = 0;
+    if (mid - rad > 0.0) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) { K[j] = -Y0[j]; K[NS + j] = -Y1[j]; }
+        sig[0] = -y0; sig[1] = -y1;
+    } else {  // regularised gain MM = G + 0.5 I; the Riccati update below still uses the plain G^-1
+        reg = 1;
+        const double H00 = G00 + 0.5, H11 = G11 + 0.5;
+        const double id2 = 1.0 / fma_(H00, H11, -(G01 * G01));
+        const double hi00 = H11 * id2, hi01 = -G01 * id2, hi11 = H00 * id2;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            K[j] = -fma_(hi01, Mx1[j], hi00 * Mx0[j]);
+            K[NS + j] = -fma_(hi11, Mx1[j], hi01 * Mx0[j]);
+        }
+        sig[0] = -fma_(hi01, m1, hi00 * m0);
+        sig[1] = -fma_(hi11, m1, hi01 * m0);
+    }
+
+    // P_t, p_t, lam_t
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+#pragma unroll
+        for (int j = i; j < NS; ++j) {
+            double qij = W.diag ? (i == j ? W.Q[i * 7] : 0.0) : W.Q[i * 6 + j];
+            const double corr = fma_(Mx1[i], Y1[j], Mx0[i] * Y0[j]);
+            Pm[sym(i, j)] = (Pn[sym(i, j)] + qij) - corr;
+        }
+        p[i] = fma_(0.5, q[i], Atp[i]) - fma_(Mx1[i], y1, Mx0[i] * y0);
+        lam[i] = Atl[i] + q[i];  // optcon.py:461
+    }
+    if (EXACT) {  // Q_t = lxx + fxx (optcon.py:444)
+        Pm[sym(2, 2)] += h.h22; Pm[sym(2, 3)] += h.h23; Pm[sym(2, 5)] += h.h25;
+        Pm[sym(3, 3)] += h.h33; Pm[sym(3, 5)] += h.h35; Pm[sym(5, 5)] += h.h55;
+    }
+    return reg;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// backward sweep of one Newton iteration
+// ------------------------------------------------------------------------------------------------------
+// KSG[t][0..11] = K_t (row-major 2x6), [12..13] = sigma_t, [14..15] = g_t ; t = 0..TT-2.
+// Returns the number of steps whose gain took the +0.5 I branch.
+template <bool EXACT>
+ACOC_HD int backward_instance(const Problem& P, const double* X, const double* U, double* KSG, int i)
+{
+    const int TT = P.TT, Np = P.Np;
+    double Pm[21], p[NS], lam[NS], x[NS], u[NI], xr[NS], ur[NI], dx[NS], du[NI], q[NS], r[NI];
+    // terminal condition: lam_{T-1} = QT dx (optcon.py:429-432), P_{T-1} = QT, p_{T-1} = lam/2 (:688-690, :716)
+    load_xref(P, TT - 1, i, xr);
+#pragma unroll
+    for (int c = 0; c < NS; ++c) dx[c] = X[at(TT - 1, NS, c, Np, i)] - xr[c];
+    wmul6(P.W.QT, P.W.diag, dx, lam);
+#pragma unroll
+    for (int a = 0; a < NS; ++a) {
+        p[a] = 0.5 * lam[a];
+#pragma unroll
+        for (int b = a; b < NS; ++b) Pm[sym(a, b)] = P.W.diag ? (a == b ? P.W.QT[a * 7] : 0.0) : P.W.QT[a * 6 + b];
+    }
+    int nreg = 0;
+    // software prefetch: the loads of step t-1 are issued before the arithmetic of step t
+    double nx[NS], nu[NI], nxr[NS], nur[NI];
+    {
+        const int t = TT - 2;
+        load_ref(P, t, i, nxr, nur);
+#pragma unroll
+        for (int c = 0; c < NS; ++c) nx[c] = X[at(t, NS, c, Np, i)];
+#pragma unroll
+        for (int c = 0; c < NI; ++c) nu[c] = U[at(t, NI, c, Np, i)];
+    }
+    for (int t = TT - 2; t >= 0; --t) {
+#pragma unroll
+        for (int c = 0; c < NS; ++c) { x[c] = nx[c]; xr[c] = nxr[c]; }
+#pragma unroll
+        for (int c = 0; c < NI; ++c) { u[c] = nu[c]; ur[c] = nur[c]; }
+        if (t > 0) {
+            load_ref(P, t - 1, i, nxr, nur);
+#pragma unroll
+            for (int c = 0; c < NS; ++c) nx[c] = X[at(t - 1, NS, c, Np, i)];
+#pragma unroll
+            for (int c = 0; c < NI; ++c) nu[c] = U[at(t - 1, NI, c, Np, i)];
+        }
+#pragma unroll
+        for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
+#pragma unroll
+        for (int c = 0; c < NI; ++c) du[c] = u[c] - ur[c];
+        wmul6(P.W.Q, P.W.diag, dx, q);   // lx = Q dx   (aircraft_simplified.py:63)
+        wmul2(P.W.R, P.W.diag, du, r);   // lu = R du   (:64)
+        const Trig tg = make_trig(x);
+        const Lin l = linearize(P.M, x, u, tg);
+        Hess h;
+        if (EXACT) h = hess_contract(P.M, x, u, tg, l, lam);
+        double K[2 * NS], sig[NI], g[NI];
+        nreg += riccati_step<EXACT>(P.M, P.W, l, h, q, r, Pm, p, lam, K, sig, g);
+#pragma unroll
+        for (int c = 0; c < 12; ++c) KSG[at(t, 16, c, Np, i)] = K[c];
+        KSG[at(t, 16, 12, Np, i)] = sig[0]; KSG[at(t, 16, 13, Np, i)] = sig[1];
+        KSG[at(t, 16, 14, Np, i)] = g[0];   KSG[at(t, 16, 15, Np, i)] = g[1];
+    }
+    return nreg;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// LQ forward pass + descent
+// ------------------------------------------------------------------------------------------------------
+// du_t = sigma_t + K_t dx_t ; dx_{t+1} = A_t dx_t + B_t du_t (optcon.py:759-760 with x~ = [1; dx], x0 = 0);
+// descent = sum_t g_t' du_t (optcon.py:474-477).  A_t, B_t are recomputed from (x_t,u_t) instead of being
+// stored by the backward sweep (12 doubles per step of HBM traffic saved for ~60 flops and two sincos).
+// DX (optional, [TT][6][Np]) receives the state increments for the drop-in ltv_LQR-style outputs.
+ACOC_HD double forward_lq_instance(const Problem& P, const double* X, const double* U, const double* KSG, double* DU, double* DX, int i)
+{
+    const int TT = P.TT, Np = P.Np;
+    double dx[NS] = {0, 0, 0, 0, 0, 0}, x[NS], u[NI], du[NI], descent = 0.0;
+    for (int t = 0; t < TT - 1; ++t) {
+#pragma unroll
+        for (int c = 0; c < NS; ++c) x[c] = X[at(t, NS, c, Np, i)];
+#pragma unroll
+        for (int c = 0; c < NI; ++c) u[c] = U[at(t, NI, c, Np, i)];
+        double K[12];
+#pragma unroll
+        for (int c = 0; c < 12; ++c) K[c] = KSG[at(t, 16, c, Np, i)];
+        const double s0 = KSG[at(t, 16, 12, Np, i)], s1 = KSG[at(t, 16, 13, Np, i)];
+        const double g0 = KSG[at(t, 16, 14, Np, i)], g1 = KSG[at(t, 16, 15, Np, i)];
+        if (DX) {
+#pragma unroll
+            for (int c = 0; c < NS; ++c) DX[at(t, NS, c, Np, i)] = dx[c];
+        }
+        du[0] = s0; du[1] = s1;
+#pragma unroll
+        for (int c = 0; c < NS; ++c) { du[0] = fma_(K[c], dx[c], du[0]); du[1] = fma_(K[NS + c], dx[c], du[1]); }
+        DU[at(t, NI, 0, Np, i)] = du[0];
+        DU[at(t, NI, 1, Np, i)] = du[1];
+        descent = fma_(g1, du[1], fma_(g0, du[0], descent));
+        const Trig tg = make_trig(x);
+        const Lin l = linearize(P.M, x, u, tg);
+        double nx[NS];
+        nx[0] = fma_(l.a05, dx[5], fma_(l.a02, dx[2], dx[0]));
+        nx[1] = fma_(l.a15, dx[5], fma_(l.a12, dx[2], dx[1]));
+        nx[2] = fma_(l.b20, du[0], fma_(l.a25, dx[5], fma_(l.a23, dx[3], l.a22 * dx[2])));
+        nx[3] = fma_(P.M.dt, dx[4], dx[3]);
+        nx[4] = fma_(P.M.b41, du[1], dx[4]);
+        nx[5] = fma_(l.b50, du[0], fma_(l.a55, dx[5], fma_(l.a53, dx[3], l.a52 * dx[2])));
+#pragma unroll
+        for (int c = 0; c < NS; ++c) dx[c] = nx[c];
+    }
+    DU[at(TT - 1, NI, 0, Np, i)] = 0.0;  // uuout[:, TT-1] stays zero (optcon.py:694)
+    DU[at(TT - 1, NI, 1, Np, i)] = 0.0;
+    if (DX) {
+#pragma unroll
+        for (int c = 0; c < NS; ++c) DX[at(TT - 1, NS, c, Np, i)] = dx[c];
+    }
+    return descent;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// open-loop rollout of u' = u + s*du from x0: one Armijo candidate (COST) and/or get_update (WRITE)
+// ------------------------------------------------------------------------------------------------------
+template <bool WRITE, bool COST>
+ACOC_HD double rollout_instance(const Problem& P, const double* U, const double* DU, double s, double* Xn, double* Un, int i)
+{
+    const int TT = P.TT, Np = P.Np;
+    const bool q32 = P.q32 != 0;
+    double x[NS], xn[NS], u[NI], xr[NS], ur[NI], dx[NS], du[NI], J = 0.0;
+#pragma unroll
+    for (int c = 0; c < NS; ++c) x[c] = P.x0[(size_t)c * Np + i];
+    for (int t = 0; t < TT - 1; ++t) {
+#pragma unroll
+        for (int c = 0; c < NI; ++c) u[c] = U[at(t, NI, c, Np, i)] + s * DU[at(t, NI, c, Np, i)];  // optcon.py:197 / :253
+        if (WRITE) {
+#pragma unroll
+            for (int c = 0; c < NS; ++c) Xn[at(t, NS, c, Np, i)] = x[c];
+#pragma unroll
+            for (int c = 0; c < NI; ++c) Un[at(t, NI, c, Np, i)] = u[c];
+        }
+        if (COST) {
+            load_ref(P, t, i, xr, ur);
+#pragma unroll
+            for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
+#pragma unroll
+            for (int c = 0; c < NI; ++c) du[c] = u[c] - ur[c];
+            J += stage_cost(P.W, dx, du);
+        }
+        const Trig tg = make_trig(x);
+        next_state(P.M, x, u, tg, q32, xn);
+#pragma unroll
+        for (int c = 0; c < NS; ++c) x[c] = xn[c];
+    }
+    if (WRITE) {
+#pragma unroll
+        for (int c = 0; c < NS; ++c) Xn[at(TT - 1, NS, c, Np, i)] = x[c];
+        Un[at(TT - 1, NI, 0, Np, i)] = 0.0;  // uu_temp[:, TT-1] is never written (optcon.py:193)
+        Un[at(TT - 1, NI, 1, Np, i)] = 0.0;
+    }
+    if (COST) {
+        load_xref(P, TT - 1, i, xr);
+#pragma unroll
+        for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
+        J += term_cost(P.W, dx);
+    }
+    return J;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Armijo decision + Newton bookkeeping for one instance (optcon.py:266-273, :327, :497-501)
+// ------------------------------------------------------------------------------------------------------
+struct NewtonOpts {
+    int max_iters;         // optcon.py:367 (loop runs max_iters-1 bodies, :415)
+    int armijo_maxiters;   // :230
+    int exact_after;       // exact Hessian iff kk > exact_after (:443; 8 in the reference)
+    double stepsize_0, cc, beta;  // :224-229
+    double term_cond;      // :368  (-1e-6, hard-coded in the reference)
+};
+
+enum InstStatus : int { ST_ACTIVE = 0, ST_CONVERGED = 1, ST_MAXITER = 2, ST_NONFINITE = 3 };
+
+struct NewtonState {          // all arrays of length Np unless noted
+    int* status;              // InstStatus
+    int* iters;               // loop bodies executed so far
+    int* result_slot;         // slot (0..2) holding what optimize() returns, -1 = the all-zero slot (:503 with kk = 0)
+    double* Jcur;             // cost of the current iterate
+    double* descent;          // descent of the current iterate
+    double* step;             // chosen step
+    double* Jcand;            // [armijo_maxiters][Np]
+    double* hist_J;           // [max_iters][Np]
+    double* hist_descent;     // [max_iters][Np]
+    double* hist_step;        // [max_iters][Np]
+    int* hist_ncand;          // [max_iters][Np]   candidates the sequential search would have rolled out
+    int* n_reg;               // accumulated +0.5 I firings
+};
+
+// cand_steps[c] = stepsize_0 * beta^c built by repeated multiplication like :270 (length armijo_maxiters+1)
+ACOC_HD void armijo_select_instance(const NewtonOpts& O, const NewtonState& S, const double* cand_steps, int kk, int Np, int i)
+{
+    const double JP = S.Jcur[i], d = S.descent[i];
+    int chosen = -1;
+    for (int c = 0; c < O.armijo_maxiters; ++c) {
+        const double Jc = S.Jcand[(size_t)c * Np + i];
+        const double sc = cand_steps[c];
+        if (!(Jc > JP + O.cc * sc * d)) { chosen = c; break; }   // :268, NaN accepts like the reference's else-branch
+    }
+    const double s = cand_steps[chosen >= 0 ? chosen : O.armijo_maxiters];  // untested step on exhaustion (:327)
+    S.step[i] = s;
+    S.hist_J[(size_t)kk * Np + i] = JP;
+    S.hist_descent[(size_t)kk * Np + i] = d;
+    S.hist_step[(size_t)kk * Np + i] = s;
+    S.hist_ncand[(size_t)kk * Np + i] = chosen >= 0 ? chosen + 1 : O.armijo_maxiters;
+}
+
+// after get_update: termination test (:499-501) and result-slot bookkeeping (:503)
+ACOC_HD void newton_finish_instance(const NewtonOpts& O, const NewtonState& S, double Jnext, int kk, int i)
+{
+    const double d = S.descent[i];
+    S.iters[i] = kk + 1;
+    S.Jcur[i] = Jnext;
+    if (d >= O.term_cond) {
+        S.status[i] = ST_CONVERGED;
+        S.result_slot[i] = kk == 0 ? -1 : (kk - 1) % 3;
+    } else if (!(fabs(d) <= 1.7e308) || !(fabs(Jnext) <= 1.7e308)) {
+        // NaN/Inf: the reference would keep iterating on NaNs until max_iters; we freeze the instance instead
+        S.status[i] = ST_NONFINITE;
+        S.result_slot[i] = (kk + 1) % 3;
+    } else if (kk + 1 >= O.max_iters - 1) {
+        S.status[i] = ST_MAXITER;
+        S.result_slot[i] = (kk + 1) % 3;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// closed-loop tracking rollout, lqr_tracking.py:279-281: u = u_opt + K (x - x_opt) with shared K, nominal
+// ------------------------------------------------------------------------------------------------------
+// Kt: [TT][12] (row-major 2x6), xopt [TT][6], uopt [TT][2] shared by all instances; x_start [6][Np].
+ACOC_HD void track_instance(const Problem& P, const double* Kt, const double* xopt, const double* uopt,
+                            const double* xstart, double* Xn, double* Un, int i)
+{
+    const int TT = P.TT, Np = P.Np;
+    const bool q32 = P.q32 != 0;
+    double x[NS], xn[NS], u[NI];
+#pragma unroll
+    for (int c = 0; c < NS; ++c) x[c] = xstart[(size_t)c * Np + i];
+    for (int t = 0; t < TT - 1; ++t) {
+        const double* K = Kt + (size_t)t * 12;
+        // K@(x - x_opt): plain sums in index order (the reference's 2x6 matvec), then u_opt + (.)
+#pragma unroll
+        for (int a = 0; a < NI; ++a) {
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < NS; ++c) s += K[a * NS + c] * (x[c] - xopt[t * NS + c]);
+            u[a] = uopt[t * NI + a] + s;
+        }
+#pragma unroll
+        for (int c = 0; c < NS; ++c) Xn[at(t, NS, c, Np, i)] = x[c];
+#pragma unroll
+        for (int c = 0; c < NI; ++c) Un[at(t, NI, c, Np, i)] = u[c];
+        const Trig tg = make_trig(x);
+        next_state(P.M, x, u, tg, q32, xn);
+#pragma unroll
+        for (int c = 0; c < NS; ++c) x[c] = xn[c];
+    }
+#pragma unroll
+    for (int c = 0; c < NS; ++c) Xn[at(TT - 1, NS, c, Np, i)] = x[c];
+    Un[at(TT - 1, NI, 0, Np, i)] = 0.0;
+    Un[at(TT - 1, NI, 1, Np, i)] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// initial guess, aircraft_simplified.py:126-148 (float64 arithmetic; see DESIGN.md "initial guess")
+// ------------------------------------------------------------------------------------------------------
+ACOC_HD void init_guess_instance(const Problem& P, double kp, double kt, double* Xn, double* Un, int i)
+{
+    const int TT = P.TT, Np = P.Np;
+    const bool q32 = P.q32 != 0;
+    double x[NS], xn[NS], u[NI], xr[NS];
+    load_xref(P, 0, i, x);  // x_temp = xx_ref[:,0]  (:139)
+    for (int t = 0; t < TT - 1; ++t) {
+        load_xref(P, t + 1, i, xr);
+        u[0] = kp * ((x[0] - xr[0]) + (x[1] - xr[1]));   // :143
+        u[1] = kt * ((x[3] - xr[3]) + (x[5] - xr[5]));   // :144
+#pragma unroll
+        for (int c = 0; c < NS; ++c) Xn[at(t, NS, c, Np, i)] = x[c];
+#pragma unroll
+        for (int c = 0; c < NI; ++c) Un[at(t, NI, c, Np, i)] = u[c];
+        const Trig tg = make_trig(x);
+        next_state(P.M, x, u, tg, q32, xn);
+#pragma unroll
+        for (int c = 0; c < NS; ++c) x[c] = xn[c];
+    }
+#pragma unroll
+    for (int c = 0; c < NS; ++c) Xn[at(TT - 1, NS, c, Np, i)] = x[c];
+    Un[at(TT - 1, NI, 0, Np, i)] = 0.0;
+    Un[at(TT - 1, NI, 1, Np, i)] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// pointwise entry points: Dynamics.step with all derivative tensors, Cost.stagecost / termcost
+// ------------------------------------------------------------------------------------------------------
+// Sample-major inputs x[n][6], u[n][2], lam[n][6] (NULL -> full tensors).  Outputs per sample:
+//   xxp[6]; A[36] = fx.T row-major; B[12] = fu.T (6x2 row-major);
+//   lam == NULL: fxx[216] ([i][j][k] = d2f_k/dx_i dx_j), fux[72] ([a][j][k]);  else fxx[36], fux[12] contracted.
+ACOC_HD void step_sample(const Model& M, bool q32, const double* x, const double* u, const double* lam,
+                         double* xxp, double* A, double* B, double* fxx, double* fux)
+{
+    const Trig tg = make_trig(x);
+    if (xxp) next_state(M, x, u, tg, q32, xxp);
+    const Lin l = linearize(M, x, u, tg);
+    if (A) {
+        for (int e = 0; e < 36; ++e) A[e] = 0.0;
+        A[0] = 1.0; A[2] = l.a02; A[5] = l.a05;
+        A[7] = 1.0; A[8] = l.a12; A[11] = l.a15;
+        A[14] = l.a22; A[15] = l.a23; A[17] = l.a25;
+        A[21] = 1.0; A[22] = M.dt;
+        A[28] = 1.0;
+        A[32] = l.a52; A[33] = l.a53; A[35] = l.a55;
+    }
+    if (B) {
+        for (int e = 0; e < 12; ++e) B[e] = 0.0;
+        B[4] = l.b20; B[9] = M.b41; B[10] = l.b50;
+    }
+    if (!fxx && !fux) return;
+    if (lam) {
+        const Hess h = hess_contract(M, x, u, tg, l, lam);
+        if (fxx) {
+            for (int e = 0; e < 36; ++e) fxx[e] = 0.0;
+            fxx[2 * 6 + 2] = h.h22; fxx[2 * 6 + 3] = h.h23; fxx[3 * 6 + 2] = h.h23; fxx[2 * 6 + 5] = h.h25; fxx[5 * 6 + 2] = h.h25;
+            fxx[3 * 6 + 3] = h.h33; fxx[3 * 6 + 5] = h.h35; fxx[5 * 6 + 3] = h.h35; fxx[5 * 6 + 5] = h.h55;
+        }
+        if (fux) {
+            for (int e = 0; e < 12; ++e) fux[e] = 0.0;
+            fux[2] = h.s2; fux[3] = h.s3; fux[5] = h.s5;
+        }
+    } else {
+        // full tensors: contract with unit costates, one output slice at a time
+        const int ks[4] = {0, 1, 2, 5};
+        if (fxx) for (int e = 0; e < 216; ++e) fxx[e] = 0.0;
+        if (fux) for (int e = 0; e < 72; ++e) fux[e] = 0.0;
+        for (int c = 0; c < 4; ++c) {
+            double e6[NS] = {0, 0, 0, 0, 0, 0};
+            e6[ks[c]] = 1.0;
+            const Hess h = hess_contract(M, x, u, tg, l, e6);
+            const int k = ks[c];
+            if (fxx) {
+                fxx[(2 * 6 + 2) * 6 + k] = h.h22; fxx[(2 * 6 + 3) * 6 + k] = h.h23; fxx[(3 * 6 + 2) * 6 + k] = h.h23;
+                fxx[(2 * 6 + 5) * 6 + k] = h.h25; fxx[(5 * 6 + 2) * 6 + k] = h.h25; fxx[(3 * 6 + 3) * 6 + k] = h.h33;
+                fxx[(3 * 6 + 5) * 6 + k] = h.h35; fxx[(5 * 6 + 3) * 6 + k] = h.h35; fxx[(5 * 6 + 5) * 6 + k] = h.h55;
+            }
+            if (fux) { fux[(0 * 6 + 2) * 6 + k] = h.s2; fux[(0 * 6 + 3) * 6 + k] = h.s3; fux[(0 * 6 + 5) * 6 + k] = h.s5; }
+        }
+    }
+}
+
+// stagecost / termcost for one sample: ll, lx[6], lu[2], llT, lTx[6]
+ACOC_HD void cost_sample(const Weights& W, const double* x, const double* u, const double* xr, const double* ur,
+                         double* ll, double* lx, double* lu, double* llT, double* lTx)
+{
+    double dx[NS], du[NI];
+    for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
+    if (u && ll) {
+        for (int c = 0; c < NI; ++c) du[c] = u[c] - ur[c];
+        *ll = stage_cost(W, dx, du);
+        wmul6(W.Q, W.diag, dx, lx);
+        wmul2(W.R, W.diag, du, lu);
+    }
+    if (llT) { *llT = term_cost(W, dx); wmul6(W.QT, W.diag, dx, lTx); }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// generic dense LTV-LQ solve: the drop-in for ltv_LQR (optcon.py:533-771) on arbitrary A_t, B_t, Q_t, R_t, S_t
+// ------------------------------------------------------------------------------------------------------
+// One thread solves one problem, literally: n = 7 (augmented by the affine terms, optcon.py:655-697) or 6.
+// Time-major row-major inputs A[t][6][6], B[t][6][2], Q[t][6][6], R[t][2][2], S[t][2][6], Qf[6][6], x0[6],
+// q[t][6], r[t][2], qf[6].  Outputs K[t][2][n], P[t][n][n] (optional), xout[t][6], uout[t][2].
+// Used by the ltv_LQR drop-in and by lqr_tracking (one shared solve); the Newton loop uses the fused
+// structure-exploiting sweeps above instead.
+template <int N>
+ACOC_HD void lq_dense_problem(int TT, const double* A, const double* B, const double* Q, const double* R, const double* S,
+                              const double* Qf, const double* x0, const double* q, const double* r, const double* qf,
+                              double* K, double* Pout, double* xout, double* uout, int* n_reg)
+{
+    constexpr int off = N - NS;  // 1 when augmented
+    double Pn[N * N], At[N * N], Bt[N * NI], Qt[N * N], St[NI * N];
+    for (int e = 0; e < N * N; ++e) Pn[e] = 0.0;
+    for (int i = 0; i < NS; ++i) {
+        if (off) { const double hq = 0.5 * qf[i]; Pn[(i + 1) * N] = hq; Pn[i + 1] = hq; }   // optcon.py:688-689
+        for (int j = 0; j < NS; ++j) Pn[(i + off) * N + (j + off)] = Qf[i * NS + j];            // :690 / :706
+    }
+    if (Pout) for (int e = 0; e < N * N; ++e) Pout[(size_t)(TT - 1) * N * N + e] = Pn[e];
+    for (int e = 0; e < NI * N; ++e) K[(size_t)(TT - 1) * NI * N + e] = 0.0;
+    int nreg = 0;
+    for (int t = TT - 2; t >= 0; --t) {
+        for (int e = 0; e < N * N; ++e) { At[e] = 0.0; Qt[e] = 0.0; }
+        for (int e = 0; e < N * NI; ++e) { Bt[e] = 0.0; St[e] = 0.0; }
+        if (off) {
+            At[0] = 1.0;  // :684
+            for (int i = 0; i < NS; ++i) { const double hq = 0.5 * q[(size_t)t * NS + i]; Qt[(i + 1) * N] = hq; Qt[i + 1] = hq; }  // :673-674
+            for (int a = 0; a < NI; ++a) St[a * N] = 0.5 * r[(size_t)t * NI + a];                                                 // :679
+        }
+        for (int i = 0; i < NS; ++i)
+            for (int j = 0; j < NS; ++j) {
+                At[(i + off) * N + (j + off)] = A[((size_t)t * NS + i) * NS + j];
+                Qt[(i + off) * N + (j + off)] = Q[((size_t)t * NS + i) * NS + j];
+            }
+        for (int i = 0; i < NS; ++i) for (int a = 0; a < NI; ++a) Bt[(i + off) * NI + a] = B[((size_t)t * NS + i) * NI + a];
+        for (int a = 0; a < NI; ++a) for (int j = 0; j < NS; ++j) St[a * N + (j + off)] = S[((size_t)t * NI + a) * NS + j];
+        // BtP = B'P (2xN), Mx = BtP A + S, G = R + BtP B
+        double BtP[NI * N], Mx[NI * N], G[4];
+        for (int a = 0; a < NI; ++a)
+            for (int j = 0; j < N; ++j) { double s = 0.0; for (int k = 0; k < N; ++k) s = fma_(Bt[k * NI + a], Pn[k * N + j], s); BtP[a * N + j] = s; }
+        for (int a = 0; a < NI; ++a)
+            for (int j = 0; j < N; ++j) { double s = 0.0; for (int k = 0; k < N; ++k) s = fma_(BtP[a * N + k], At[k * N + j], s); Mx[a * N + j] = s + St[a * N + j]; }
+        for (int a = 0; a < NI; ++a)
+            for (int b = 0; b < NI; ++b) { double s = 0.0; for (int k = 0; k < N; ++k) s = fma_(BtP[a * N + k], Bt[k * NI + b], s); G[a * NI + b] = R[(size_t)t * 4 + a * NI + b] + s; }
+        // explicit inverse of G (:728)
+        const double idet = 1.0 / fma_(G[0], G[3], -(G[1] * G[2]));
+        const double Gi[4] = {G[3] * idet, -G[1] * idet, -G[2] * idet, G[0] * idet};
+        // gain matrix: eigenvalue test (:745), +0.5 I (:749), K = -inv(MM) Mx (:751)
+        double MM[4] = {G[0], G[1], G[2], G[3]};
+        {
+            const double hd = 0.5 * (MM[0] - MM[3]), disc = fma_(hd, hd, MM[1] * MM[2]), mid = 0.5 * (MM[0] + MM[3]);
+            bool pd;
+            if (disc >= 0.0) { const double rad = sqrt(disc); pd = (mid - rad > 0.0) && (mid + rad > 0.0); }
+            else pd = (disc < 0.0) && (mid > 0.0);
+            if (!pd) { MM[0] += 0.5; MM[3] += 0.5; ++nreg; }
+        }
+        const double id2 = 1.0 / fma_(MM[0], MM[3], -(MM[1] * MM[2]));
+        const double Mi[4] = {MM[3] * id2, -MM[1] * id2, -MM[2] * id2, MM[0] * id2};
+        for (int a = 0; a < NI; ++a)
+            for (int j = 0; j < N; ++j)
+                K[((size_t)t * NI + a) * N + j] = -fma_(Mi[a * NI + 1], Mx[N + j], Mi[a * NI] * Mx[j]);
+        // P_t = Q + A'PA - Mx' Gi Mx (:727-728)
+        double AtP[N * N], Y[NI * N], Pt[N * N];
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) { double s = 0.0; for (int k = 0; k < N; ++k) s = fma_(At[k * N + i], Pn[k * N + j], s); AtP[i * N + j] = s; }
+        for (int a = 0; a < NI; ++a)
+            for (int j = 0; j < N; ++j) Y[a * N + j] = fma_(Gi[a * NI + 1], Mx[N + j], Gi[a * NI] * Mx[j]);
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) {
+                double s = 0.0;
+                for (int k = 0; k < N; ++k) s = fma_(AtP[i * N + k], At[k * N + j], s);
+                Pt[i * N + j] = (Qt[i * N + j] + s) - fma_(Mx[N + i], Y[N + j], Mx[i] * Y[j]);
+            }
+        for (int e = 0; e < N * N; ++e) Pn[e] = Pt[e];
+        if (Pout) for (int e = 0; e < N * N; ++e) Pout[(size_t)t * N * N + e] = Pt[e];
+    }
+    if (n_reg) *n_reg = nreg;
+    // forward pass (:756-762)
+    double xa[N], xb[N], ua[NI];
+    if (off) xa[0] = 1.0;
+    for (int i = 0; i < NS; ++i) { xa[i + off] = x0[i]; xout[i] = x0[i]; }
+    for (int t = 0; t < TT - 1; ++t) {
+        for (int a = 0; a < NI; ++a) {
+            double s = 0.0;
+            for (int j = 0; j < N; ++j) s = fma_(K[((size_t)t * NI + a) * N + j], xa[j], s);
+            ua[a] = s; uout[(size_t)t * NI + a] = s;
+        }
+        if (off) xb[0] = 1.0;
+        for (int i = 0; i < NS; ++i) {
+            double s1 = 0.0, s2 = 0.0;
+            for (int j = 0; j < NS; ++j) s1 = fma_(A[((size_t)t * NS + i) * NS + j], xa[j + off], s1);
+            for (int a = 0; a < NI; ++a) s2 = fma_(B[((size_t)t * NS + i) * NI + a], ua[a], s2);
+            xb[i + off] = s1 + s2;
+        }
+        for (int i = 0; i < N; ++i) xa[i] = xb[i];
+        for (int i = 0; i < NS; ++i) xout[(size_t)(t + 1) * NS + i] = xa[i + off];
+    }
+    uout[(size_t)(TT - 1) * NI] = 0.0; uout[(size_t)(TT - 1) * NI + 1] = 0.0;
+}
+
+}  // namespace acoc

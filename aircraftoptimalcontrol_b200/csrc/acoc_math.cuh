@@ -1,0 +1,252 @@
+// acoc_math.cuh -- per-time-step math of the aircraft OCP hot path, written once for the sm_100a kernels.
+//
+// Everything here is a __host__ __device__ inline function of scalars held in registers; the kernels in
+// acoc_kernels.cuh call them once per (instance, time step).  The host flavour exists only so that
+// tests/host_emul can replay the kernels' arithmetic on a CPU (no GPU in the build container); the product
+// library never runs it.
+//
+// What is restated (reference = MohamedAtwan/AirCraftOptimalControl):
+//   next_state()   aircraft_simplified.py:295-310 (+ dragForce :228, liftForce :253), operation order and
+//                  float32 rounding of the next state (:300) preserved so the rollouts match bit for bit
+//   linearize()    aircraft_simplified.py:316-325 -- only the 10 non-constant entries of A = fx.T and the
+//                  2 non-constant entries of B = fu.T
+//   hess_contract() aircraft_simplified.py:339-388, 397-404 -- sum_k lambda_k * d2f_k, which lives on the
+//                  {V,theta,gamma} block (6 numbers) and the thrust row of d2f/dudx (3 numbers)
+//   stage/terminal cost: aircraft_simplified.py:61-64, :92-94
+//
+// Floating-point contract: the translation unit is compiled with -fmad=false (nvcc) / -ffp-contract=off
+// (gcc), so a*b+c is two roundings unless written as fma_().  next_state() and the cost sums use plain
+// operators in the reference's order; the linearisation / Riccati code uses fma_() explicitly.
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define ACOC_HD __host__ __device__ __forceinline__
+#else
+#define ACOC_HD inline
+#endif
+
+namespace acoc {
+
+constexpr int NS = 6;  // state  [X, Z, V, theta, q, gamma]   aircraft_simplified.py:116, :264
+constexpr int NI = 2;  // input  [T, M]                       aircraft_simplified.py:117
+
+// Model constants (aircraft_simplified.py:108-118) plus products that the reference forms from python
+// scalars before touching the state; they are computed once on the host with the same operations.
+struct Model {
+    double cd0, cda, cla, m, g, S, rho, J, dt;
+    double half_rho;  // 0.5*rho          (:228, :253)
+    double mg;        // m*g              (:306, :310)
+    double dt_m;      // dt/m             (:306)
+    double k;         // S*rho
+    double cdk, clk;  // cda*k, cla*k
+    double b41;       // dt/J             (:324)
+    double gm;        // g*m              (:318, :321)
+};
+
+inline Model make_model(const double* p)
+{
+    Model M;
+    M.cd0 = p[0]; M.cda = p[1]; M.cla = p[2]; M.m = p[3]; M.g = p[4]; M.S = p[5]; M.rho = p[6]; M.J = p[7]; M.dt = p[8];
+    M.half_rho = 0.5 * M.rho;
+    M.mg = M.m * M.g;
+    M.dt_m = M.dt / M.m;
+    M.k = M.S * M.rho;
+    M.cdk = M.cda * M.k;
+    M.clk = M.cla * M.k;
+    M.b41 = M.dt / M.J;
+    M.gm = M.g * M.m;
+    return M;
+}
+
+// Quadratic weights.  diag != 0 promises that Q, R and QT are diagonal (every shipped configuration,
+// main_newton_method.py:52-63); the dense path keeps the API honest (aircraft_simplified.py:61 takes any matrix).
+struct Weights {
+    double Q[36], R[4], QT[36];
+    int diag;
+};
+
+ACOC_HD double fma_(double a, double b, double c) { return fma(a, b, c); }
+
+ACOC_HD void sincos_(double x, double& s, double& c)
+{
+#if defined(__CUDA_ARCH__)
+    sincos(x, &s, &c);
+#else
+    s = sin(x); c = cos(x);
+#endif
+}
+
+// aircraft_simplified.py:300 -- the reference stores the next state in a float32 array.
+ACOC_HD double quant_(double v, bool q32) { return q32 ? (double)(float)v : v; }
+
+struct Trig { double sg, cg, sa, ca, alpha; };
+
+ACOC_HD Trig make_trig(const double* x)
+{
+    Trig t;
+    t.alpha = x[3] - x[5];  // :295
+    sincos_(x[5], t.sg, t.cg);
+    sincos_(t.alpha, t.sa, t.ca);
+    return t;
+}
+
+// One forward-Euler step, aircraft_simplified.py:303-310, in the reference's evaluation order.
+ACOC_HD void next_state(const Model& M, const double* x, const double* u, const Trig& t, bool q32, double* xn)
+{
+    const double V = x[2];
+    const double V2 = V * V, a2 = t.alpha * t.alpha;
+    const double hv = M.half_rho * V2 * M.S;                       // 0.5*rho*V**2*S
+    const double D = hv * (M.cd0 + M.cda * a2);                    // :228
+    const double L = hv * M.cla * t.alpha;                         // :253
+    const double dtV = M.dt * V;
+    xn[0] = quant_(x[0] + dtV * t.cg, q32);
+    xn[1] = quant_(x[1] - dtV * t.sg, q32);
+    xn[2] = quant_(V + M.dt_m * (-D - M.mg * t.sg + u[0] * t.ca), q32);
+    xn[3] = quant_(x[3] + M.dt * x[4], q32);
+    xn[4] = quant_(x[4] + M.dt * (u[1] / M.J), q32);
+    xn[5] = quant_(x[5] + (M.dt / (M.m * V)) * (L - M.mg * t.cg + u[0] * t.sa), q32);
+}
+
+// Non-constant entries of A = df/dx and B = df/du.  Constant ones: A00=A11=A33=A44=1, A34=dt, B41=dt/J.
+struct Lin {
+    double a02, a05, a12, a15, a22, a23, a25, a52, a53, a55, b20, b50;
+    // by-products reused by hess_contract()
+    double iV, drag_c, lift, liftT, tsa, tca;
+};
+
+ACOC_HD Lin linearize(const Model& M, const double* x, const double* u, const Trig& t)
+{
+    Lin l;
+    const double V = x[2], T = u[0], al = t.alpha;
+    const double iV = 1.0 / V;
+    const double V2 = V * V;
+    const double dc = fma_(M.cda * al, al, M.cd0);          // Cd0 + Cda*alpha^2
+    const double tsa = T * t.sa, tca = T * t.ca;
+    const double cav = M.cdk * al * V2;                     // Cda*k*alpha*V^2
+    const double lift = 0.5 * M.clk * V2;                   // 0.5*Cla*k*V^2
+    const double dtV = M.dt * V;
+    l.a02 = M.dt * t.cg;
+    l.a05 = -dtV * t.sg;
+    l.a12 = -M.dt * t.sg;
+    l.a15 = -dtV * t.cg;
+    l.a22 = fma_(-M.dt_m * M.k * V, dc, 1.0);
+    l.a23 = -M.dt_m * (cav + tsa);
+    l.a25 = M.dt_m * (cav + tsa - M.gm * t.cg);
+    const double w = fma_(lift, al, tsa) - M.gm * t.cg;     // lift*alpha + T sin(alpha) - g m cos(gamma)
+    l.a52 = M.dt_m * fma_(-w * iV, iV, M.clk * al);
+    l.a53 = M.dt_m * (lift + tca) * iV;
+    l.a55 = fma_(-M.dt_m * (lift + tca - M.gm * t.sg), iV, 1.0);
+    l.b20 = M.dt_m * t.ca;
+    l.b50 = M.dt_m * t.sa * iV;
+    l.iV = iV; l.drag_c = dc; l.lift = lift; l.liftT = lift + tca; l.tsa = tsa; l.tca = tca;
+    return l;
+}
+
+// lambda-contracted second-order terms (optcon.py:437 with aircraft_simplified.py:384-388):
+// symmetric block on {V,theta,gamma} = indices {2,3,5} and the thrust row of fux.
+struct Hess { double h22, h23, h25, h33, h35, h55, s2, s3, s5; };
+
+ACOC_HD Hess hess_contract(const Model& M, const double* x, const double* u, const Trig& t, const Lin& l, const double* lam)
+{
+    Hess h;
+    const double V = x[2], al = t.alpha, iV = l.iV, iV2 = iV * iV;
+    const double l0 = lam[0], l1 = lam[1], l2 = lam[2], l5 = lam[5];
+    const double cv2 = M.cdk * V * V;
+    // d2 f_V
+    const double v22 = -M.dt_m * M.k * l.drag_c;
+    const double v23 = -M.dt_m * M.cdk * V * (2.0 * al);
+    const double v33 = -M.dt_m * (cv2 + l.tca);
+    const double v55 = -M.dt_m * (cv2 + l.tca - M.gm * t.sg);
+    // d2 f_gamma
+    const double w = fma_(l.lift, al, l.tsa) - M.gm * t.cg;
+    const double clkdtm = M.clk * M.dt_m;
+    const double g22 = fma_(2.0 * M.dt_m * w * iV2, iV, -clkdtm * al * iV);
+    const double g23 = fma_(-M.dt_m * l.liftT, iV2, clkdtm);
+    const double g25 = fma_(M.dt_m * (l.liftT - M.gm * t.sg), iV2, -clkdtm);
+    const double g33 = -M.dt_m * l.tsa * iV;
+    const double g55 = -M.dt_m * (l.tsa - M.gm * t.cg) * iV;
+    const double dtV = M.dt * V;
+    h.h22 = fma_(l2, v22, l5 * g22);
+    h.h23 = fma_(l2, v23, l5 * g23);
+    h.h25 = fma_(l0, -M.dt * t.sg, fma_(l1, -M.dt * t.cg, fma_(l2, -v23, l5 * g25)));
+    h.h33 = fma_(l2, v33, l5 * g33);
+    h.h35 = -h.h33;
+    h.h55 = fma_(l0, -dtV * t.cg, fma_(l1, dtV * t.sg, fma_(l2, v55, l5 * g55)));
+    h.s2 = l5 * (-M.dt_m * t.sa * iV2);
+    h.s3 = fma_(l2, -M.dt_m * t.sa, l5 * (M.dt_m * t.ca * iV));
+    h.s5 = -h.s3;
+    return h;
+}
+
+// Stage cost (aircraft_simplified.py:61): 0.5*dx'(Q dx) + 0.5*du'(R du), sums in ascending index order.
+ACOC_HD double stage_cost(const Weights& W, const double* dx, const double* du)
+{
+    double sx = 0.0, su = 0.0;
+    if (W.diag) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) sx += dx[i] * (W.Q[i * 7] * dx[i]);
+#pragma unroll
+        for (int i = 0; i < NI; ++i) su += du[i] * (W.R[i * 3] * du[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            double a = 0.0;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) a += W.Q[i * 6 + j] * dx[j];
+            sx += dx[i] * a;
+        }
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            double a = 0.0;
+#pragma unroll
+            for (int j = 0; j < NI; ++j) a += W.R[i * 2 + j] * du[j];
+            su += du[i] * a;
+        }
+    }
+    return 0.5 * sx + 0.5 * su;
+}
+
+// Terminal cost (aircraft_simplified.py:92): ((0.5*dx') QT) dx.
+ACOC_HD double term_cost(const Weights& W, const double* dx)
+{
+    double s = 0.0;
+    if (W.diag) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) s += ((0.5 * dx[j]) * W.QT[j * 7]) * dx[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            double a = 0.0;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) a += (0.5 * dx[i]) * W.QT[i * 6 + j];
+            s += a * dx[j];
+        }
+    }
+    return s;
+}
+
+// v = W (dx) for a 6x6 weight (gradient lx = Q dx, aircraft_simplified.py:63 / :94)
+ACOC_HD void wmul6(const double* Wm, int diag, const double* dx, double* out)
+{
+    if (diag) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) out[i] = Wm[i * 7] * dx[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            double a = 0.0;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) a = fma_(Wm[i * 6 + j], dx[j], a);
+            out[i] = a;
+        }
+    }
+}
+
+ACOC_HD void wmul2(const double* Wm, int diag, const double* du, double* out)
+{
+    if (diag) { out[0] = Wm[0] * du[0]; out[1] = Wm[3] * du[1]; }
+    else { out[0] = fma_(Wm[1], du[1], Wm[0] * du[0]); out[1] = fma_(Wm[3], du[1], Wm[2] * du[0]); }
+}
+
+}  // namespace acoc

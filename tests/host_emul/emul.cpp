@@ -1,0 +1,237 @@
+// emul.cpp -- TEST-ONLY host replay of the CUDA kernels' per-instance code.
+//
+// The build container has no GPU.  The per-instance bodies of every kernel (acoc_kernels.cuh) are
+// __host__ __device__, so this file compiles them with g++ (-ffp-contract=off, matching nvcc -fmad=false)
+// and drives them with plain loops over instances, using the same struct-of-arrays buffers and the same
+// iteration sequence as acoc_api.cu.  `-m "not gpu"` tests use it to check the kernel arithmetic against the
+// oracle before any GPU time is spent.  It is NOT part of the product: libacoc.so does not contain it and
+// the package never loads it.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "../../aircraftoptimalcontrol_b200/csrc/acoc_kernels.cuh"
+
+using namespace acoc;
+
+namespace {
+struct Soa {
+    int N, Np, TT;
+    std::vector<double> X[3], U[3], DU, KSG, xref, uref, x0;
+};
+
+void to_soa(const double* host, double* dst, int n, int C, int TT, int Np)
+{
+    for (int i = 0; i < n; ++i)
+        for (int c = 0; c < C; ++c)
+            for (int t = 0; t < TT; ++t) dst[((size_t)t * C + c) * Np + i] = host[((size_t)i * C + c) * TT + t];
+}
+void from_soa(const double* src, double* host, int i, int C, int TT, int Np)
+{
+    for (int c = 0; c < C; ++c)
+        for (int t = 0; t < TT; ++t) host[(size_t)c * TT + t] = src[((size_t)t * C + c) * Np + i];
+}
+void fill_weights(Weights* W, const double* Q, const double* R, const double* QT)
+{
+    memcpy(W->Q, Q, sizeof(W->Q)); memcpy(W->R, R, sizeof(W->R)); memcpy(W->QT, QT, sizeof(W->QT));
+    bool d = true;
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) if (i != j && (Q[i * 6 + j] != 0.0 || QT[i * 6 + j] != 0.0)) d = false;
+    if (R[1] != 0.0 || R[2] != 0.0) d = false;
+    W->diag = d;
+}
+}  // namespace
+
+extern "C" {
+
+void emul_step_batch(int n, const double* params, int state_f64, const double* x, const double* u, const double* lam,
+                     double* xxp, double* A, double* B, double* fxx, double* fux)
+{
+    const Model M = make_model(params);
+    const size_t nxx = lam ? 36 : 216, nux = lam ? 12 : 72;
+    for (int s = 0; s < n; ++s)
+        step_sample(M, !state_f64, x + (size_t)s * 6, u + (size_t)s * 2, lam ? lam + (size_t)s * 6 : nullptr, xxp ? xxp + (size_t)s * 6 : nullptr,
+                    A ? A + (size_t)s * 36 : nullptr, B ? B + (size_t)s * 12 : nullptr, fxx ? fxx + s * nxx : nullptr, fux ? fux + s * nux : nullptr);
+}
+
+void emul_cost_batch(int n, const double* Q, const double* R, const double* QT, const double* x, const double* u, const double* xr,
+                     const double* ur, double* ll, double* lx, double* lu, double* llT, double* lTx)
+{
+    Weights W;
+    fill_weights(&W, Q, R, QT);
+    for (int s = 0; s < n; ++s)
+        cost_sample(W, x + (size_t)s * 6, u + (size_t)s * 2, xr + (size_t)s * 6, ur + (size_t)s * 2, ll + s, lx + (size_t)s * 6, lu + (size_t)s * 2,
+                    llT + s, lTx + (size_t)s * 6);
+}
+
+void emul_ltv_lqr(int TT, const double* A, const double* B, const double* Q, const double* R, const double* S, const double* Qf,
+                  const double* x0, const double* q, const double* r, const double* qf, double* K, double* P, double* xout, double* uout, int* n_reg)
+{
+    if (q) lq_dense_problem<7>(TT, A, B, Q, R, S, Qf, x0, q, r, qf, K, P, xout, uout, n_reg);
+    else lq_dense_problem<6>(TT, A, B, Q, R, S, Qf, x0, nullptr, nullptr, nullptr, K, P, xout, uout, n_reg);
+}
+
+// The lock-step Newton driver of acoc_api.cu (acoc_newton_iterate) replayed on the host.
+// hist_* are (N, max_iters) row-major; xx_* (N,6,TT); uu_* (N,2,TT); K_last (N,12,TT); sigma_last (N,2,TT).
+int emul_newton_batch(int N, int TT, const double* params, int state_f64, const double* Q, const double* R, const double* QT,
+                      const double* xx_ref, const double* uu_ref, int ref_shared, const double* xx_init, const double* uu_init,
+                      int max_iters, double stepsize_0, double cc, double beta, int armijo_maxiters, int exact_after, double term_cond,
+                      int n_iters_cap, int lazy,
+                      double* hist_J, double* hist_descent, double* hist_step, int* hist_ncand, int* iters, int* status,
+                      double* xx_star, double* uu_star, double* xx_last, double* uu_last, double* du_last, double* K_last, double* sigma_last,
+                      int* n_reg_out)
+{
+    const int Np = (N + 31) / 32 * 32;
+    Soa b;
+    b.N = N; b.Np = Np; b.TT = TT;
+    for (int s = 0; s < 3; ++s) { b.X[s].assign((size_t)TT * 6 * Np, 0.0); b.U[s].assign((size_t)TT * 2 * Np, 0.0); }
+    b.DU.assign((size_t)TT * 2 * Np, 0.0); b.KSG.assign((size_t)TT * 16 * Np, 0.0);
+    const int Nr = ref_shared ? 1 : Np;
+    b.xref.assign((size_t)TT * 6 * Nr, 0.0); b.uref.assign((size_t)TT * 2 * Nr, 0.0); b.x0.assign((size_t)6 * Np, 0.0);
+    to_soa(xx_ref, b.xref.data(), ref_shared ? 1 : N, 6, TT, Nr);
+    to_soa(uu_ref, b.uref.data(), ref_shared ? 1 : N, 2, TT, Nr);
+    to_soa(xx_init, b.X[0].data(), N, 6, TT, Np);
+    to_soa(uu_init, b.U[0].data(), N, 2, TT, Np);
+    std::copy(b.X[0].begin(), b.X[0].begin() + (size_t)6 * Np, b.x0.begin());
+
+    Problem P;
+    P.M = make_model(params);
+    fill_weights(&P.W, Q, R, QT);
+    P.N = N; P.Np = Np; P.TT = TT; P.q32 = state_f64 ? 0 : 1; P.ref_shared = ref_shared;
+    P.xref = b.xref.data(); P.uref = b.uref.data(); P.x0 = b.x0.data();
+    NewtonOpts O;
+    O.max_iters = max_iters; O.armijo_maxiters = armijo_maxiters; O.exact_after = exact_after;
+    O.stepsize_0 = stepsize_0; O.cc = cc; O.beta = beta; O.term_cond = term_cond;
+    std::vector<int> st(Np, ST_ACTIVE), its(Np, 0), slot(Np, 0), ncand((size_t)max_iters * Np, 0), nreg(Np, 0);
+    std::vector<double> Jcur(Np, 0.0), desc(Np, 0.0), step(Np, 0.0), Jc((size_t)(armijo_maxiters + 1) * Np, 0.0);
+    std::vector<double> hJ((size_t)max_iters * Np, 0.0), hD((size_t)max_iters * Np, 0.0), hS((size_t)max_iters * Np, 0.0);
+    NewtonState S;
+    S.status = st.data(); S.iters = its.data(); S.result_slot = slot.data(); S.Jcur = Jcur.data(); S.descent = desc.data();
+    S.step = step.data(); S.Jcand = Jc.data(); S.hist_J = hJ.data(); S.hist_descent = hD.data(); S.hist_step = hS.data();
+    S.hist_ncand = ncand.data(); S.n_reg = nreg.data();
+    std::vector<double> cs(armijo_maxiters + 1);
+    { double s = stepsize_0; for (int k = 0; k <= armijo_maxiters; ++k) { cs[k] = s; s = beta * s; } }
+
+    int kk = 0;
+    for (;; ++kk) {
+        if (kk >= max_iters - 1) break;
+        if (n_iters_cap > 0 && kk >= n_iters_cap) break;
+        int active = 0;
+        for (int i = 0; i < N; ++i) active += st[i] == ST_ACTIVE;
+        if (!active) break;
+        const int cur = kk % 3, nxt = (kk + 1) % 3;
+        const double *X = b.X[cur].data(), *U = b.U[cur].data();
+        double *Xn = b.X[nxt].data(), *Un = b.U[nxt].data();
+        for (int i = 0; i < N; ++i) {
+            if (st[i] != ST_ACTIVE) continue;
+            if (kk == 0) Jcur[i] = traj_cost_instance(P, X, U, i);
+            nreg[i] += (kk > exact_after) ? backward_instance<true>(P, X, U, b.KSG.data(), i) : backward_instance<false>(P, X, U, b.KSG.data(), i);
+            desc[i] = forward_lq_instance(P, X, U, b.KSG.data(), b.DU.data(), nullptr, i);
+            bool cand0_in_place = false;
+            if (lazy && armijo_maxiters > 1) {
+                Jc[i] = rollout_instance<true, true>(P, U, b.DU.data(), cs[0], Xn, Un, i);
+                const bool need = Jc[i] > Jcur[i] + cc * cs[0] * desc[i];
+                if (need) for (int c = 1; c < armijo_maxiters; ++c) Jc[(size_t)c * Np + i] = rollout_instance<false, true>(P, U, b.DU.data(), cs[c], nullptr, nullptr, i);
+                cand0_in_place = !need;
+            } else {
+                for (int c = 0; c < armijo_maxiters; ++c) Jc[(size_t)c * Np + i] = rollout_instance<false, true>(P, U, b.DU.data(), cs[c], nullptr, nullptr, i);
+            }
+            armijo_select_instance(O, S, cs.data(), kk, Np, i);
+            const double Jn = cand0_in_place ? Jc[i] : rollout_instance<true, true>(P, U, b.DU.data(), step[i], Xn, Un, i);
+            newton_finish_instance(O, S, Jn, kk, i);
+        }
+    }
+    for (int i = 0; i < N; ++i) {
+        for (int k = 0; k < max_iters; ++k) {
+            if (hist_J) hist_J[(size_t)i * max_iters + k] = hJ[(size_t)k * Np + i];
+            if (hist_descent) hist_descent[(size_t)i * max_iters + k] = hD[(size_t)k * Np + i];
+            if (hist_step) hist_step[(size_t)i * max_iters + k] = hS[(size_t)k * Np + i];
+            if (hist_ncand) hist_ncand[(size_t)i * max_iters + k] = ncand[(size_t)k * Np + i];
+        }
+        if (iters) iters[i] = its[i];
+        if (status) status[i] = st[i];
+        if (n_reg_out) n_reg_out[i] = nreg[i];
+        const int sl = st[i] == ST_ACTIVE ? kk % 3 : slot[i];
+        if (xx_star) {
+            if (sl < 0) { memset(xx_star + (size_t)i * 6 * TT, 0, sizeof(double) * 6 * TT); memset(uu_star + (size_t)i * 2 * TT, 0, sizeof(double) * 2 * TT); }
+            else { from_soa(b.X[sl].data(), xx_star + (size_t)i * 6 * TT, i, 6, TT, Np); from_soa(b.U[sl].data(), uu_star + (size_t)i * 2 * TT, i, 2, TT, Np); }
+            for (int c = 0; c < 2; ++c) uu_star[((size_t)i * 2 + c) * TT + TT - 1] = uu_star[((size_t)i * 2 + c) * TT + TT - 2];
+        }
+        // newest iterate of instance i: the one written in its last executed body
+        const int last = its[i] % 3;
+        if (xx_last) from_soa(b.X[last].data(), xx_last + (size_t)i * 6 * TT, i, 6, TT, Np);
+        if (uu_last) from_soa(b.U[last].data(), uu_last + (size_t)i * 2 * TT, i, 2, TT, Np);
+        if (du_last) from_soa(b.DU.data(), du_last + (size_t)i * 2 * TT, i, 2, TT, Np);
+        if (K_last) {
+            std::vector<double> tmp((size_t)16 * TT);
+            from_soa(b.KSG.data(), tmp.data(), i, 16, TT, Np);
+            memcpy(K_last + (size_t)i * 12 * TT, tmp.data(), sizeof(double) * 12 * TT);
+            if (sigma_last) memcpy(sigma_last + (size_t)i * 2 * TT, tmp.data() + (size_t)12 * TT, sizeof(double) * 2 * TT);
+        }
+    }
+    return kk;
+}
+
+// rollout of u + s*du for a batch (get_update / one Armijo candidate)
+void emul_rollout_batch(int N, int TT, const double* params, int state_f64, const double* Q, const double* R, const double* QT,
+                        const double* xx_ref, const double* uu_ref, const double* x0, const double* uu, const double* du, const double* s,
+                        double* xx_out, double* uu_out, double* J)
+{
+    const int Np = (N + 31) / 32 * 32;
+    std::vector<double> U((size_t)TT * 2 * Np), DU((size_t)TT * 2 * Np), Xn((size_t)TT * 6 * Np), Un((size_t)TT * 2 * Np);
+    std::vector<double> xr((size_t)TT * 6 * Np), ur((size_t)TT * 2 * Np), x0s((size_t)6 * Np, 0.0);
+    to_soa(uu, U.data(), N, 2, TT, Np); to_soa(du, DU.data(), N, 2, TT, Np);
+    to_soa(xx_ref, xr.data(), N, 6, TT, Np); to_soa(uu_ref, ur.data(), N, 2, TT, Np);
+    for (int i = 0; i < N; ++i) for (int c = 0; c < 6; ++c) x0s[(size_t)c * Np + i] = x0[(size_t)i * 6 + c];
+    Problem P;
+    P.M = make_model(params); fill_weights(&P.W, Q, R, QT);
+    P.N = N; P.Np = Np; P.TT = TT; P.q32 = state_f64 ? 0 : 1; P.ref_shared = 0;
+    P.xref = xr.data(); P.uref = ur.data(); P.x0 = x0s.data();
+    for (int i = 0; i < N; ++i) {
+        J[i] = rollout_instance<true, true>(P, U.data(), DU.data(), s[i], Xn.data(), Un.data(), i);
+        from_soa(Xn.data(), xx_out + (size_t)i * 6 * TT, i, 6, TT, Np);
+        from_soa(Un.data(), uu_out + (size_t)i * 2 * TT, i, 2, TT, Np);
+    }
+}
+
+void emul_lqr_tracking(int N, int TT, const double* params, int state_f64, const double* Q, const double* R, const double* QT,
+                       const double* xx_opt, const double* uu_opt, const double* delta, double* xx_reg, double* uu_reg, double* K)
+{
+    const int Np = (N + 31) / 32 * 32;
+    const Model M = make_model(params);
+    std::vector<double> xo((size_t)TT * 6), uo((size_t)TT * 2), A((size_t)TT * 36), B((size_t)TT * 12), S((size_t)TT * 12, 0.0);
+    std::vector<double> Qr((size_t)TT * 36), Rr((size_t)TT * 4), Kt((size_t)TT * 12), xout((size_t)TT * 6), uout((size_t)TT * 2);
+    to_soa(xx_opt, xo.data(), 1, 6, TT, 1); to_soa(uu_opt, uo.data(), 1, 2, TT, 1);
+    for (int t = 0; t < TT; ++t) {
+        step_sample(M, !state_f64, &xo[(size_t)t * 6], &uo[(size_t)t * 2], nullptr, nullptr, &A[(size_t)t * 36], &B[(size_t)t * 12], nullptr, nullptr);
+        memcpy(&Qr[(size_t)t * 36], Q, sizeof(double) * 36); memcpy(&Rr[(size_t)t * 4], R, sizeof(double) * 4);
+    }
+    lq_dense_problem<6>(TT, A.data(), B.data(), Qr.data(), Rr.data(), S.data(), QT, delta, nullptr, nullptr, nullptr, Kt.data(), nullptr, xout.data(), uout.data(), nullptr);
+    if (K) memcpy(K, Kt.data(), sizeof(double) * TT * 12);
+    std::vector<double> xs((size_t)6 * Np, 0.0), Xn((size_t)TT * 6 * Np), Un((size_t)TT * 2 * Np);
+    for (int i = 0; i < N; ++i) for (int c = 0; c < 6; ++c) xs[(size_t)c * Np + i] = xx_opt[(size_t)c * TT] + delta[(size_t)i * 6 + c];
+    Problem P;
+    P.M = M; P.N = N; P.Np = Np; P.TT = TT; P.q32 = state_f64 ? 0 : 1; P.ref_shared = 1;
+    P.xref = xo.data(); P.uref = uo.data(); P.x0 = xs.data();
+    for (int i = 0; i < N; ++i) {
+        track_instance(P, Kt.data(), xo.data(), uo.data(), xs.data(), Xn.data(), Un.data(), i);
+        from_soa(Xn.data(), xx_reg + (size_t)i * 6 * TT, i, 6, TT, Np);
+        from_soa(Un.data(), uu_reg + (size_t)i * 2 * TT, i, 2, TT, Np);
+    }
+}
+
+void emul_init_guess(int N, int TT, const double* params, int state_f64, const double* xx_ref, double kp, double kt, double* xx, double* uu)
+{
+    const int Np = (N + 31) / 32 * 32;
+    std::vector<double> xr((size_t)TT * 6 * Np), Xn((size_t)TT * 6 * Np), Un((size_t)TT * 2 * Np);
+    to_soa(xx_ref, xr.data(), N, 6, TT, Np);
+    Problem P;
+    P.M = make_model(params); P.N = N; P.Np = Np; P.TT = TT; P.q32 = state_f64 ? 0 : 1; P.ref_shared = 0;
+    P.xref = xr.data(); P.uref = nullptr; P.x0 = nullptr;
+    for (int i = 0; i < N; ++i) {
+        init_guess_instance(P, kp, kt, Xn.data(), Un.data(), i);
+        from_soa(Xn.data(), xx + (size_t)i * 6 * TT, i, 6, TT, Np);
+        from_soa(Un.data(), uu + (size_t)i * 2 * TT, i, 2, TT, Np);
+    }
+}
+
+}  // extern "C"
