@@ -1,0 +1,184 @@
+"""Batched regularized-Newton solver: thousands to millions of independent aircraft OCP instances on one GPU.
+
+`BatchedNewton` is a thin handle on one libacoc context (include/acoc.h).  It mirrors
+`optcon.NewtonMethod` (reference optcon.py:329-529) with a leading instance axis on every array.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+class BatchedNewton:
+    """N independent instances of NewtonMethod.optimize (optcon.py:341) solved in lock-step on one GPU.
+
+    Parameters mirror NewtonMethod.__init__ (optcon.py:335-337); `term_cond` defaults to the value the
+    reference actually uses (-1e-6, optcon.py:368), `exact_after` to its hard-coded 8 (optcon.py:443).
+    state: "f32" reproduces aircraft_simplified.py:300 (next state rounded to float32), "f64" keeps float64.
+    armijo: "speculative" evaluates all candidates concurrently, "lazy" evaluates candidate 0 for everyone and
+    the rest only where it failed; both return exactly the step the reference's sequential search returns.
+    """
+
+    def __init__(self, n_instances, TT=1000, device=0, state="f32", refs_shared=False, armijo="speculative", params=None,
+                 max_iters=200, stepsize_0=1.0, cc=0.5, beta=0.7, armijo_maxiters=10, term_cond=-1e-6, exact_after=8):
+        if state not in ("f32", "f64"):
+            raise ValueError("state must be 'f32' or 'f64'")
+        if armijo not in ("speculative", "lazy"):
+            raise ValueError("armijo must be 'speculative' or 'lazy'")
+        self.N, self.TT, self.device = int(n_instances), int(TT), int(device)
+        self.refs_shared = bool(refs_shared)
+        flags = (L.STATE_F64 if state == "f64" else 0) | (L.REFS_SHARED if refs_shared else 0) | (L.ARMIJO_LAZY if armijo == "lazy" else 0)
+        self._h = C.c_void_p(None)
+        L.check(L.lib().acoc_ctx_create(self.device, self.N, self.TT, flags, C.addressof(self._h)))
+        self.opts = L.NewtonOptions(int(max_iters), int(armijo_maxiters), int(exact_after), 0, float(stepsize_0), float(cc), float(beta),
+                                    float(term_cond))
+        L.check(L.lib().acoc_set_options(self._h, C.addressof(self.opts)))
+        if params is not None:
+            self.set_model(params)
+
+    # -- life cycle -----------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            L.lib().acoc_ctx_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def device_bytes(self):
+        v = C.c_ulonglong(0)
+        L.check(L.lib().acoc_ctx_device_bytes(self._h, C.addressof(v)))
+        return v.value
+
+    # -- problem data ---------------------------------------------------------------------------------
+    def set_model(self, params):
+        p = L.f64(params, (9,), "params")
+        L.check(L.lib().acoc_set_model(self._h, L.ptr(p)))
+
+    def set_weights(self, QQt, RRt, QQT):
+        Q, R, QT = L.f64(QQt, (6, 6), "QQt"), L.f64(RRt, (2, 2), "RRt"), L.f64(QQT, (6, 6), "QQT")
+        L.check(L.lib().acoc_set_weights(self._h, L.ptr(Q), L.ptr(R), L.ptr(QT)))
+
+    def set_refs(self, xx_ref, uu_ref):
+        sx = (6, self.TT) if self.refs_shared else (self.N, 6, self.TT)
+        su = (2, self.TT) if self.refs_shared else (self.N, 2, self.TT)
+        xr, ur = L.f64(xx_ref, sx, "xx_ref"), L.f64(uu_ref, su, "uu_ref")
+        L.check(L.lib().acoc_set_refs(self._h, L.ptr(xr), L.ptr(ur)))
+
+    def set_init(self, xx_init, uu_init):
+        xi, ui = L.f64(xx_init, (self.N, 6, self.TT), "xx_init"), L.f64(uu_init, (self.N, 2, self.TT), "uu_init")
+        L.check(L.lib().acoc_set_init(self._h, L.ptr(xi), L.ptr(ui)))
+
+    def init_guess(self, kp=5.0, kt=2.5, dx0=None):
+        """Dynamics.get_initial_trajectory (aircraft_simplified.py:126-148) for every instance, on the device.
+        dx0 (N,6): start from xx_ref[:,0] + dx0 (perturbed-initial-state batches)."""
+        d = None if dx0 is None else L.f64(dx0, (self.N, 6), "dx0")
+        L.check(L.lib().acoc_init_guess(self._h, float(kp), float(kt), L.ptr(d)))
+
+    # -- solve ------------------------------------------------------------------------------------------
+    def iterate(self, n_iters=1, count_active=True):
+        na = C.c_int(-1)
+        L.check(L.lib().acoc_newton_iterate(self._h, int(n_iters), C.addressof(na) if count_active else None))
+        return na.value
+
+    def solve(self):
+        tot = C.c_longlong(0)
+        L.check(L.lib().acoc_newton_solve(self._h, C.addressof(tot)))
+        return tot.value
+
+    def sync(self):
+        L.check(L.lib().acoc_sync(self._h))
+
+    # -- pieces (parity tests, drop-in method names) ---------------------------------------------------------
+    def eval_cost(self):
+        J = np.zeros(self.N)
+        L.check(L.lib().acoc_eval_cost(self._h, L.ptr(J)))
+        return J
+
+    def backward(self, exact=False):
+        L.check(L.lib().acoc_backward(self._h, int(bool(exact))))
+
+    def forward(self):
+        d = np.zeros(self.N)
+        L.check(L.lib().acoc_forward(self._h, L.ptr(d)))
+        return d
+
+    def set_deltau(self, deltau):
+        du = L.f64(deltau, (self.N, 2, self.TT), "deltau")
+        L.check(L.lib().acoc_set_deltau(self._h, L.ptr(du)))
+
+    def set_scalars(self, J=None, descent=None):
+        Jc = None if J is None else L.f64(J, (self.N,), "J")
+        dc = None if descent is None else L.f64(descent, (self.N,), "descent")
+        L.check(L.lib().acoc_set_scalars(self._h, L.ptr(Jc), L.ptr(dc)))
+
+    def armijo(self):
+        s, costs = np.zeros(self.N), np.zeros((self.N, self.opts.armijo_maxiters))
+        L.check(L.lib().acoc_armijo(self._h, L.ptr(s), L.ptr(costs)))
+        return s, costs
+
+    def update(self, stepsize=None):
+        s = None if stepsize is None else L.f64(np.broadcast_to(np.asarray(stepsize, dtype=np.float64), (self.N,)), (self.N,), "stepsize")
+        L.check(L.lib().acoc_update(self._h, L.ptr(s)))
+
+    # -- read-back --------------------------------------------------------------------------------------
+    def result(self, out=None):
+        """(xx_star (N,6,TT), uu_star (N,2,TT)) with the reference's return semantics (optcon.py:503-505)."""
+        if out is None:
+            xs, us = np.empty((self.N, 6, self.TT)), np.empty((self.N, 2, self.TT))
+        else:
+            xs, us = out
+        L.check(L.lib().acoc_get_result(self._h, L.ptr(xs), L.ptr(us)))
+        return xs, us
+
+    def iterate_at(self, which=0):
+        xs, us = np.empty((self.N, 6, self.TT)), np.empty((self.N, 2, self.TT))
+        L.check(L.lib().acoc_get_iterate(self._h, int(which), L.ptr(xs), L.ptr(us)))
+        return xs, us
+
+    def deltau(self):
+        du = np.empty((self.N, 2, self.TT))
+        L.check(L.lib().acoc_get_deltau(self._h, L.ptr(du)))
+        return du
+
+    def gains(self):
+        K, s = np.empty((self.N, 2, 6, self.TT)), np.empty((self.N, 2, self.TT))
+        L.check(L.lib().acoc_get_gains(self._h, L.ptr(K), L.ptr(s)))
+        return K, s
+
+    def history(self):
+        mi = self.opts.max_iters
+        J, d, s = np.zeros((self.N, mi)), np.zeros((self.N, mi)), np.zeros((self.N, mi))
+        nc = np.zeros((self.N, mi), dtype=np.int32)
+        L.check(L.lib().acoc_get_history(self._h, L.ptr(J), L.ptr(d), L.ptr(s), L.ptr(nc)))
+        return dict(JJ=J, descent=d, stepsize=s, n_armijo=nc)
+
+    def stats(self):
+        it, st, nr = (np.zeros(self.N, dtype=np.int32) for _ in range(3))
+        J, d = np.zeros(self.N), np.zeros(self.N)
+        L.check(L.lib().acoc_get_stats(self._h, L.ptr(it), L.ptr(st), L.ptr(J), L.ptr(d), L.ptr(nr)))
+        return dict(iters=it, status=st, J=J, descent=d, n_reg=nr)
+
+    def set_profiling(self, on=True):
+        L.check(L.lib().acoc_set_profiling(self._h, int(bool(on))))
+
+    def timing(self):
+        tot = C.c_double(0)
+        ph = (C.c_double * 6)()
+        nl = C.c_longlong(0)
+        L.check(L.lib().acoc_get_timing(self._h, C.addressof(tot), C.addressof(ph), C.addressof(nl)))
+        names = ("cost", "backward", "forward", "candidates", "select", "update")
+        return dict(total_ms=tot.value, launches=nl.value, phases={k: ph[i] for i, k in enumerate(names)})

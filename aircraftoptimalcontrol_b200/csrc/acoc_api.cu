@@ -174,11 +174,12 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_track(Problem P, const double*
     track_instance(P, Kt, xopt, uopt, xstart, Xn, Un, i);
 }
 
-__global__ void __launch_bounds__(ROLL_THREADS) k_init_guess(Problem P, double kp, double kt, double* __restrict__ Xn, double* __restrict__ Un)
+__global__ void __launch_bounds__(ROLL_THREADS) k_init_guess(Problem P, double kp, double kt, const double* __restrict__ dx0,
+                                                             double* __restrict__ Xn, double* __restrict__ Un)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.N) return;
-    init_guess_instance(P, kp, kt, Xn, Un, i);
+    init_guess_instance(P, kp, kt, dx0, Xn, Un, i);
 }
 
 __global__ void k_step_batch(Model M, int q32, int n, const double* __restrict__ x, const double* __restrict__ u,
@@ -704,13 +705,21 @@ int acoc_set_init(acoc_ctx* c, const double* xx_init, const double* uu_init)
     return 0;
 }
 
-int acoc_init_guess(acoc_ctx* c, double kp, double kt)
+int acoc_init_guess(acoc_ctx* c, double kp, double kt, const double* dx0)
 {
     REQUIRE(c, "NULL argument");
     if (!c->have_refs) return fail(ACOC_ERR_STATE, "acoc_init_guess: set the references first");
     TRY(use_device(c->device));
     TRY(reset_state(c));
-    k_init_guess<<<(c->N + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, 0, c->stream>>>(c->P, kp, kt, c->X[0], c->U[0]);
+    double* d_dx0 = nullptr;
+    if (dx0) {  // host (N,6) -> device [6][Np] (x0 is overwritten below, so it doubles as scratch)
+        std::vector<double> tmp((size_t)6 * c->Np, 0.0);
+        for (int i = 0; i < c->N; ++i) for (int k = 0; k < 6; ++k) tmp[(size_t)k * c->Np + i] = dx0[(size_t)i * 6 + k];
+        CK(cudaMemcpyAsync(c->x0, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        d_dx0 = c->x0;
+    }
+    k_init_guess<<<(c->N + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, 0, c->stream>>>(c->P, kp, kt, d_dx0, c->X[0], c->U[0]);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(c->x0, c->X[0], (size_t)6 * c->Np * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -933,6 +942,23 @@ int acoc_update(acoc_ctx* c, const double* stepsize)
     if (stepsize) CK(cudaMemcpyAsync(c->S.step, stepsize, c->N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     TRY(launch_update(c, false, false));
     ++c->kk;
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int acoc_set_deltau(acoc_ctx* c, const double* deltau)
+{
+    REQUIRE(c && deltau, "NULL argument");
+    TRY(use_device(c->device));
+    return upload_soa(c, deltau, c->DU, c->N, 2, c->Np);
+}
+
+int acoc_set_scalars(acoc_ctx* c, const double* J, const double* descent)
+{
+    REQUIRE(c, "ctx is NULL");
+    TRY(use_device(c->device));
+    if (J) CK(cudaMemcpyAsync(c->S.Jcur, J, c->N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (descent) CK(cudaMemcpyAsync(c->S.descent, descent, c->N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }

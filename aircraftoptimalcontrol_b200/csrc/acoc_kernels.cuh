@@ -464,12 +464,17 @@ ACOC_HD void track_instance(const Problem& P, const double* Kt, const double* xo
 // ------------------------------------------------------------------------------------------------------
 // initial guess, aircraft_simplified.py:126-148 (float64 arithmetic; see DESIGN.md "initial guess")
 // ------------------------------------------------------------------------------------------------------
-ACOC_HD void init_guess_instance(const Problem& P, double kp, double kt, double* Xn, double* Un, int i)
+// dx0 (optional, [6][Np]): start from xx_ref[:,0] + dx0 instead (perturbed-initial-state batches, config 5)
+ACOC_HD void init_guess_instance(const Problem& P, double kp, double kt, const double* dx0, double* Xn, double* Un, int i)
 {
     const int TT = P.TT, Np = P.Np;
     const bool q32 = P.q32 != 0;
     double x[NS], xn[NS], u[NI], xr[NS];
     load_xref(P, 0, i, x);  // x_temp = xx_ref[:,0]  (:139)
+    if (dx0) {
+#pragma unroll
+        for (int c = 0; c < NS; ++c) x[c] += dx0[(size_t)c * Np + i];
+    }
     for (int t = 0; t < TT - 1; ++t) {
         load_xref(P, t + 1, i, xr);
         u[0] = kp * ((x[0] - xr[0]) + (x[1] - xr[1]));   // :143

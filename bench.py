@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- trajectory-Newton-iterations / second on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--instances M] [--workload step|acro]
+                    [--armijo lazy|speculative] [--state f32|f64] [--no-e2e] [--no-cpu]
+    torchrun --nproc-per-node N bench.py --gpus N ...          (one rank per GPU, launched by the driver)
+
+Workload (config.workload): BASELINE.json configs[3] -- "batched step-maneuver Newton, 65,536 randomised step
+references", per GPU (weak scaling: rank r of world w holds instances r::w of a 65,536*w batch).  A "step" is ONE
+Newton iteration (loop body of optcon.py:415-501: fused backward Riccati/costate sweep, LQ forward pass + descent,
+Armijo candidate rollouts, update rollout) over the whole batch.  W warm-up iterations, then K timed ones -- these
+are the iterations W..W+K-1 of the real solve from the device-generated initial guess; every instance is still
+active there.  Time = CUDA events on the context's stream around the K iterations, max over ranks.
+
+The JSON line carries: value (device-resident), e2e (full solve through the Python API from pinned host buffers:
+H2D of the references, device initial guess, solve to the reference's criterion, D2H of results and stats),
+roofline for the dominant kernel (HBM GB/s against MEASURED_PEAKS.json, FP64 TFLOP/s against a DFMA microbenchmark
+run here), cpu_baseline (the C port of the reference in oracle/, OpenMP over instances, bounded sample), clocks.
+
+--impl reference times that CPU port alone (the reference itself is Python and is not present on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "trajectory_newton_iterations_per_second"
+UNIT = "traj-Newton-it/s"
+TT = 1000
+
+# algorithmic FP64 flops / HBM bytes per instance per time step (dense ns=6, ni=2 accounting)
+FLOPS = dict(backward=2106, forward=126 + 30, cost=107, candidate=159, update=52 + 107)
+BYTES = dict(backward=128 + 128, forward=128 + 64 + 16, cost=128, candidate=32 + 64, update=32 + 64 + 64)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons of one GPU with nvidia-smi while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def make_problem(workload, n_total, lo_hi_stride, seed=None):
+    """Per-rank shard of the batched configuration: instances rank::world of the n_total-instance batch."""
+    from aircraftoptimalcontrol_b200 import refgen
+    r, w = lo_hi_stride
+    if workload == "step":
+        zf, xf = refgen.config4_params(n_total, 2024 if seed is None else seed)
+        xr, ur = refgen.step_problem(xf[r::w], zf[r::w], TT=TT)
+        return xr, ur, None, refgen.weights("step")
+    dx0, zf = refgen.config5_params(n_total, 7 if seed is None else seed)
+    xr, ur = refgen.acrobatic_problem(zf[r::w], TT=TT)
+    return xr, ur, np.ascontiguousarray(dx0[r::w]), refgen.weights("acro")
+
+
+def pinned_like(a):
+    """Copy a numpy array into pinned host memory (torch is only the allocator here)."""
+    import torch
+    t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+    t.numpy()[...] = a
+    return t  # keep the tensor alive; .numpy() is the view
+
+
+def cpu_port_rate(workload, sample, W, K, state):
+    """Newton iterations W..W+K-1 of `sample` instances with the C port of the reference on all host threads."""
+    from oracle import corcl
+    corcl.build()
+    xr, ur, dx0, (Q, R, QT) = make_problem(workload, sample, (0, 1))
+    xi = np.zeros((sample, 6, TT))
+    ui = np.zeros((sample, 2, TT))
+    for i in range(sample):  # the initial guess is an input of the hot path (float64 P-law rollout, same as the GPU's)
+        xref_i = xr[i].copy()
+        if dx0 is not None:
+            xref_i[:, 0] += dx0[i]
+        xi[i], ui[i] = corcl.initial_trajectory(xref_i if dx0 is not None else xr[i], quant_f32=(state == "f32"))
+    nt = corcl.max_threads()
+    kw = dict(quant_f32=(state == "f32"), n_threads=nt)
+    t0 = time.perf_counter()
+    a = corcl.newton_batch(xr, ur, xi, ui, Q, R, QT, n_iters_cap=W, **kw) if W > 0 else None
+    t1 = time.perf_counter()
+    b = corcl.newton_batch(xr, ur, xi, ui, Q, R, QT, n_iters_cap=W + K, **kw)
+    t2 = time.perf_counter()
+    its = int(b["iters"].sum()) - (int(a["iters"].sum()) if a is not None else 0)
+    dt = (t2 - t1) - (t1 - t0 if a is not None else 0.0)
+    return its / dt, nt, dt, its
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    sample = args.cpu_sample
+    rate, nt, dt, its = cpu_port_rate(args.workload, sample, args.warmup, args.steps, args.state)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config_dict(args, sample, world=1),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": nt, "kind": "port",
+                         "sample": "%d instances x Newton iterations %d..%d of the workload, C port of the reference (oracle/acoc_oracle.c), "
+                                   "OpenMP over instances; time(W+K iterations) - time(W iterations)" % (sample, args.warmup, args.warmup + args.steps - 1)},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, n_per_gpu, world):
+    return {"workload": ("BASELINE.json configs[3]: batched step-maneuver Newton, randomised step references (zf~U(1.5,3.5), xf~U(14,18), seed 2024)"
+                         if args.workload == "step" else
+                         "BASELINE.json configs[4]: acrobatic Newton OCP batch (x0 perturbed, bump height zf~U(2.0,3.4), seed 7)"),
+            "instances_per_gpu": n_per_gpu, "instances_total": n_per_gpu * world, "TT": TT, "ns": 6, "ni": 2,
+            "state_quant": args.state, "armijo": args.armijo, "armijo_maxiters": 10, "max_iters": 200,
+            "step": "one Newton iteration over the whole batch (iterations W..W+K-1 of the solve)",
+            "l2": "working set per GPU (%.1f GB) >> 126 MB L2, no flush needed" % (n_per_gpu * 400e3 / 1e9),
+            "parallelism": "instances sharded round-robin, %d per GPU, no hot-path collective" % n_per_gpu}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--instances", type=int, default=65536, help="instances per GPU")
+    ap.add_argument("--workload", default="step", choices=["step", "acro"])
+    ap.add_argument("--armijo", default="lazy", choices=["lazy", "speculative"])
+    ap.add_argument("--state", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--cpu-sample", type=int, default=512)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import aircraftoptimalcontrol_b200 as pkg
+    from aircraftoptimalcontrol_b200 import _lib, dist as D
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.instances
+    n_total = n * world
+    K, W = args.steps, args.warmup
+
+    xr, ur, dx0, (Q, R, QT) = make_problem(args.workload, n_total, (rank, world))
+    bn = pkg.BatchedNewton(n, TT=TT, device=local, state=args.state, armijo=args.armijo)
+    bn.set_weights(Q, R, QT)
+    bn.set_refs(xr, ur)
+    bn.init_guess(dx0=dx0)
+    if W:
+        bn.iterate(W, count_active=False)
+    bn.sync()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        bn.sync()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    active_after = bn.iterate(K, count_active=False)  # K Newton iterations, timed by CUDA events inside the library
+    bn.sync()
+    barrier()
+    tm = bn.timing()
+    clocks = sampler.summary() if sampler else None
+    ms = tm["total_ms"]
+    launches = tm["launches"]
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms, float(launches)], dtype=torch.float64, device="cuda")
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms, launches = float(tmax[0]), int(t[1])
+    st = bn.stats()
+    n_active = int((st["status"] == 0).sum())
+    value = n_total * K / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (rank 0): re-run iterations with per-phase events --------------------
+    roofline = fp64 = phases = None
+    peaks, peak_src = load_peaks()
+    if rank == 0 and not args.no_roofline:
+        bn.set_profiling(True)
+        bn.init_guess(dx0=dx0)
+        bn.iterate(W, count_active=False)
+        bn.iterate(K, count_active=False)
+        tp = bn.timing()
+        bn.set_profiling(False)
+        h = bn.history()
+        ncand = h["n_armijo"][:, W:W + K].astype(np.float64)
+        # candidates actually rolled out: lazy = 1 for everyone + (maxiters-1) where candidate 0 failed
+        if args.armijo == "lazy":
+            cand_rollouts = float(np.sum(1 + 9 * (ncand > 1)))
+            upd_rollouts = float(np.sum(ncand > 1))
+        else:
+            cand_rollouts = float(ncand.size * 10)
+            upd_rollouts = float(ncand.size)
+        phases = tp["phases"]
+        per_launch_ms = {k: v / K for k, v in phases.items()}
+        dom = max(("backward", "forward", "candidates", "update"), key=lambda k: phases[k])
+        units = {"backward": n * (TT - 1), "forward": n * (TT - 1), "candidates": cand_rollouts / K * (TT - 1), "update": max(upd_rollouts, 1) / K * (TT - 1)}
+        bkey = {"backward": "backward", "forward": "forward", "candidates": "candidate", "update": "update"}
+        fp64_peak = _lib.measure_fp64_peak(local)
+        tbl = {}
+        for k in ("backward", "forward", "candidates", "update"):
+            if per_launch_ms[k] <= 0:
+                continue
+            gbs = units[k] * BYTES[bkey[k]] / (per_launch_ms[k] * 1e-3) / 1e9
+            tfs = units[k] * FLOPS[bkey[k]] / (per_launch_ms[k] * 1e-3) / 1e12
+            tbl[k] = {"ms_per_launch": per_launch_ms[k], "hbm_gbs": gbs, "hbm_frac": gbs / peaks["hbm_gbs"], "fp64_tflops": tfs, "fp64_frac": tfs / fp64_peak}
+        d = tbl[dom]
+        bound = "hbm" if d["hbm_frac"] >= d["fp64_frac"] else "fp64"
+        roofline = {"kernel": "k_" + dom, "bound": bound,
+                    "achieved": d["hbm_gbs"] if bound == "hbm" else d["fp64_tflops"],
+                    "peak": peaks["hbm_gbs"] if bound == "hbm" else fp64_peak,
+                    "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+                    "frac": d["hbm_frac"] if bound == "hbm" else d["fp64_frac"],
+                    "traffic": None, "peak_source": peak_src if bound == "hbm" else "DFMA microbenchmark run in this process (acoc_measure_fp64_peak)",
+                    "per_kernel": tbl, "share_of_step": phases[dom] / max(sum(phases.values()), 1e-9),
+                    "algorithmic": {"bytes_per_instance_step": BYTES, "flops_per_instance_step": FLOPS, "note": "SURVEY.md 8(d) per-unit figures x (TT-1) x instances per launch"}}
+        fp64 = {"peak_tflops_measured": fp64_peak}
+
+    # ---- end to end through the public API, host buffers, full solve -----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        xr_p, ur_p = pinned_like(xr), pinned_like(ur)
+        import torch
+        xs_t = torch.empty((n, 6, TT), dtype=torch.float64, pin_memory=True)
+        us_t = torch.empty((n, 2, TT), dtype=torch.float64, pin_memory=True)
+        barrier()
+        t0 = time.perf_counter()
+        bn.set_refs(xr_p.numpy(), ur_p.numpy())          # H2D: references
+        bn.init_guess(dx0=dx0)                           # device-side initial guess (N1)
+        total_iters = bn.solve()                         # to the reference's criterion (descent >= -1e-6) for every instance
+        bn.result(out=(xs_t.numpy(), us_t.numpy()))      # D2H: optimal trajectories
+        st2 = bn.stats()                                 # D2H: iterations, status, cost, descent
+        barrier()
+        t1 = time.perf_counter()
+        wall = t1 - t0
+        g = D.gather_stats(st2, n_total)                 # NCCL all_gather of the per-instance statistics (off the hot path)
+        t2 = time.perf_counter()
+        tot = int(g["iters"].sum())
+        if dist is not None:
+            import torch
+            tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+            wall = float(tw[0])
+        steps_e2e = int(g["iters"].max())
+        h2d = (xr.nbytes + ur.nbytes) * world
+        d2h = (xs_t.numel() + us_t.numel()) * 8 * world + n_total * 28
+        e2e = {"value": tot / wall, "unit": UNIT, "h2d_bytes_per_step": h2d / max(steps_e2e, 1), "d2h_bytes_per_step": d2h / max(steps_e2e, 1),
+               "wall_s": wall, "total_newton_iterations": tot, "solver_steps": steps_e2e,
+               "converged": int((g["status"] == 1).sum()), "instances": n_total, "mean_iters": float(g["iters"].mean()),
+               "stats_gather_s": t2 - t1,
+               "what": "BatchedNewton.set_refs(pinned host) -> init_guess (device) -> solve() to descent >= -1e-6 -> result()/stats() to pinned host"}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        rate, nt, dt, its = cpu_port_rate(args.workload, args.cpu_sample, W, K, args.state)
+        cpu = {"value": rate, "unit": UNIT, "cores": nt, "kind": "port",
+               "sample": "%d instances x Newton iterations %d..%d of the same workload, C port of the reference (oracle/acoc_oracle.c), OpenMP over "
+                         "instances, %.1f s" % (args.cpu_sample, W, W + K - 1, dt)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / max(K, 1),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config_dict(args, n, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "active_after_timed_region": n_active, "roofline": roofline, "fp64": fp64, "phase_ms": phases, "cpu_baseline": cpu,
+                "device": pkg.device_info(local)["name"], "device_bytes": bn.device_bytes}
+        print(json.dumps(line), flush=True)
+    bn.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

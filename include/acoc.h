@@ -120,8 +120,9 @@ int acoc_set_refs(acoc_ctx* ctx, const double* xx_ref, const double* uu_ref);
  * Resets the Newton state (iteration counter, histories). */
 int acoc_set_init(acoc_ctx* ctx, const double* xx_init, const double* uu_init);
 /* Dynamics.get_initial_trajectory(xx_ref, tt) -- aircraft_simplified.py:126-148 -- computed on the device for
- * every instance from the references already set (float64 arithmetic), then used as the initial guess. */
-int acoc_init_guess(acoc_ctx* ctx, double kp, double kt);
+ * every instance from the references already set (float64 arithmetic), then used as the initial guess.
+ * dx0 (N,6) or NULL: start instance i from xx_ref[:,0] + dx0[i] (perturbed-initial-state batches). */
+int acoc_init_guess(acoc_ctx* ctx, double kp, double kt, const double* dx0);
 
 /* Run up to n_iters more Newton iterations (loop bodies of optcon.py:415-501) on every instance that is
  * still active.  *n_active_out (may be NULL) = instances still active afterwards (forces a device sync). */
@@ -154,6 +155,10 @@ int acoc_get_stats(acoc_ctx* ctx, int* iters, int* status, double* J, double* de
  *   acoc_armijo           GradientMethod.armijo_stepsize (optcon.py:204-327) -> stepsize[N], costs[N][armijo_maxiters]
  *   acoc_update           GradientMethod.get_update (optcon.py:176-200) with per-instance steps -> becomes the newest iterate */
 int acoc_eval_cost(acoc_ctx* ctx, double* J);
+/* Overwrite the descent direction deltau (N,2,TT) and/or the scalars the Armijo test uses (JP = J[N],
+ * descent[N]); lets GradientMethod.armijo_stepsize / get_update be called with caller-supplied arguments. */
+int acoc_set_deltau(acoc_ctx* ctx, const double* deltau);
+int acoc_set_scalars(acoc_ctx* ctx, const double* J, const double* descent);
 int acoc_backward(acoc_ctx* ctx, int exact);
 int acoc_forward(acoc_ctx* ctx, double* descent);
 int acoc_armijo(acoc_ctx* ctx, double* stepsize, double* costs);

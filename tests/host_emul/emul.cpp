@@ -228,7 +228,7 @@ void emul_init_guess(int N, int TT, const double* params, int state_f64, const d
     P.M = make_model(params); P.N = N; P.Np = Np; P.TT = TT; P.q32 = state_f64 ? 0 : 1; P.ref_shared = 0;
     P.xref = xr.data(); P.uref = nullptr; P.x0 = nullptr;
     for (int i = 0; i < N; ++i) {
-        init_guess_instance(P, kp, kt, Xn.data(), Un.data(), i);
+        init_guess_instance(P, kp, kt, nullptr, Xn.data(), Un.data(), i);
         from_soa(Xn.data(), xx + (size_t)i * 6 * TT, i, 6, TT, Np);
         from_soa(Un.data(), uu + (size_t)i * 2 * TT, i, 2, TT, Np);
     }

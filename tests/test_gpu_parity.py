@@ -1,0 +1,239 @@
+"""Parity of the CUDA path (through the C ABI, libacoc.so) with the live reference's golden fixtures and with
+the CPU oracle.  Runs on the B200 box: python -m pytest tests -m gpu.
+
+Tolerances: next-state / rollout values are compared bit for bit (the float32 rounding of
+aircraft_simplified.py:300 absorbs the <= 2 ulp difference between CUDA's and glibc's sin/cos); everything that
+goes through the Riccati recursion is compared at the north-star tolerance 1e-9 relative; Armijo steps and
+iteration counts must be IDENTICAL."""
+import numpy as np
+import pytest
+
+from tests.util import golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def test_step_batch_kat(gpu):
+    from aircraftoptimalcontrol_b200.aircraft_simplified import Dynamics
+    d = golden("step_kat.npz")
+    r32 = Dynamics(state="f32").step_batch(d["x"], d["u"])
+    r64 = Dynamics(state="f64").step_batch(d["x"], d["u"], d["lam"])
+    assert np.array_equal(r32["xxp"], d["xxp32"])
+    assert relerr(d["xxp64"], r64["xxp"]) < 1e-15
+    assert relerr(d["fx"], np.swapaxes(r32["A"], 1, 2)) < 1e-12 and relerr(d["fu"], np.swapaxes(r32["B"], 1, 2)) < 1e-12
+    assert relerr(d["fxx"], r32["fxx"]) < 1e-12 and relerr(d["fux"], r32["fux"]) < 1e-12
+    assert relerr(d["fxxc"], r64["fxx"]) < 1e-12 and relerr(d["fuxc"], r64["fux"]) < 1e-12
+
+
+def test_cost_batch_kat(gpu):
+    from aircraftoptimalcontrol_b200.aircraft_simplified import Cost
+    d = golden("cost_kat.npz")
+    for w in range(len(d["Q"])):
+        m = d["which"] == w
+        c = Cost(d["Q"][w], d["R"][w], d["QT"][w])
+        ll, lx, lu = c.stagecost_batch(d["x"][m], d["u"][m], d["xr"][m], d["ur"][m])
+        llT, lTx = c.termcost_batch(d["x"][m], d["xr"][m])
+        assert np.max(np.abs(ll - d["ll"][m]) / np.abs(d["ll"][m])) < 1e-13
+        assert np.max(np.abs(llT - d["llT"][m]) / np.abs(d["llT"][m])) < 1e-13
+        assert relerr(d["lx"][m], lx) < 1e-14 and relerr(d["lu"][m], lu) < 1e-14 and relerr(d["lTx"][m], lTx) < 1e-14
+
+
+def test_ltv_lqr_forced_regularisation(gpu):
+    from aircraftoptimalcontrol_b200.optcon import ltv_LQR
+    d = golden("lq_forced_reg.npz")
+    TT = d["A"].shape[2]
+    K, P, x, u, n = ltv_LQR(d["A"], d["B"], d["Q"], d["R"], d["S"], d["Qf"], TT, np.zeros(6), d["q"], d["r"], d["qf"], return_nreg=True)
+    assert n == int(d["n_reg_aug"]) > 0 and K.shape == (2, 7, TT) and P.shape == (7, 7, TT)
+    for got, ref in ((K, d["K_aug"]), (P, d["P_aug"]), (x, d["x_aug"]), (u, d["u_aug"])):
+        assert relerr(ref, got) < 1e-9
+    K, P, x, u, n = ltv_LQR(d["A"], d["B"], d["Q"], d["R"], d["S"], d["Qf"], TT, d["x0"], return_nreg=True)
+    assert n == int(d["n_reg_non"]) > 0 and K.shape == (2, 6, TT)
+    for got, ref in ((K, d["K_non"]), (P, d["P_non"]), (x, d["x_non"]), (u, d["u_non"])):
+        assert relerr(ref, got) < 1e-9
+    # constant (6,6)/(2,2) weights are broadcast along t like optcon.py:603-606
+    K2 = ltv_LQR(d["A"], d["B"], d["Q"][:, :, 0], np.eye(2), d["S"], d["Qf"], TT, d["x0"])[0]
+    K3 = ltv_LQR(d["A"], d["B"], np.repeat(d["Q"][:, :, :1], TT, 2), np.repeat(np.eye(2)[:, :, None], TT, 2), d["S"], d["Qf"], TT, d["x0"])[0]
+    assert np.array_equal(K2, K3)
+    with pytest.raises(ValueError):
+        ltv_LQR(d["A"], d["B"], np.eye(5), d["R"], d["S"], d["Qf"], TT, d["x0"])
+
+
+@pytest.mark.parametrize("name", ["newton_step_f32", "newton_step_f64", "newton_acro_f32", "newton_acro_f64"])
+@pytest.mark.parametrize("armijo", ["speculative", "lazy"])
+def test_newton_configs_1_2(gpu, name, armijo):
+    """BASELINE.json configs[0] and configs[1] (single trajectory, GPU vs the reference's numpy float64):
+    identical iteration count and Armijo step at every iteration, histories and trajectories within 1e-9."""
+    d = golden(name + ".npz")
+    f64 = name.endswith("f64")
+    TT = d["xx_ref"].shape[1]
+    with gpu.BatchedNewton(1, TT=TT, state="f64" if f64 else "f32", refs_shared=True, armijo=armijo) as bn:
+        bn.set_weights(d["Q"], d["R"], d["QT"])
+        bn.set_refs(d["xx_ref"], d["uu_ref"])
+        bn.set_init(d["xx_init"][None], d["uu_init"][None])
+        total = bn.solve()
+        xs, us = bn.result()
+        xl, ul = bn.iterate_at(0)
+        h, st = bn.history(), bn.stats()
+    k = int(d["iters"])
+    assert total == k and st["iters"][0] == k and st["status"][0] == 1 and st["n_reg"][0] == 0
+    assert np.array_equal(h["stepsize"][0, :k], d["stepsize"])
+    assert np.array_equal(h["n_armijo"][0, :k], d["n_armijo"])
+    assert np.max(np.abs(h["JJ"][0, :k] - d["JJ"]) / np.abs(d["JJ"])) < 1e-9
+    assert np.max(np.abs(h["descent"][0, :k] - d["descent"]) / np.abs(d["descent"])) < 1e-9
+    assert relerr(d["xx_star"], xs[0]) < 1e-9 and relerr(d["uu_star"], us[0]) < 1e-9
+    assert relerr(d["xx_last"], xl[0]) < 1e-9 and relerr(d["uu_last"], ul[0]) < 1e-9
+
+
+def test_fused_sweeps_match_reference_lq(gpu):
+    """K, sigma, deltau of the fused backward/forward kernels vs the reference's ltv_LQR inside live iterations."""
+    d = golden("newton_acro_f32.npz")
+    TT = d["xx_ref"].shape[1]
+    for kk in d["lq_at"]:
+        kk = int(kk)
+        with gpu.BatchedNewton(1, TT=TT, refs_shared=True) as bn:
+            bn.set_weights(d["Q"], d["R"], d["QT"])
+            bn.set_refs(d["xx_ref"], d["uu_ref"])
+            bn.set_init(d["it%d_xx" % kk][None], d["it%d_uu" % kk][None])
+            bn.backward(exact=kk > 8)
+            bn.forward()
+            K, sig = bn.gains()
+            du = bn.deltau()
+        KK = d["it%d_KK" % kk]
+        assert relerr(KK[:, 1:, :], K[0]) < 1e-9 and relerr(KK[:, 0, :], sig[0]) < 1e-9
+        assert relerr(d["it%d_deltau" % kk], du[0]) < 1e-9
+
+
+def _random_batch(n, TT, seed, tf):
+    from aircraftoptimalcontrol_b200 import refgen
+    rng = np.random.default_rng(seed)
+    zf, xf = rng.uniform(1.5, 3.5, n), rng.uniform(14, 18, n)
+    xr, ur = refgen.step_problem(xf, zf, tf=tf, TT=TT)
+    return (xr, ur) + refgen.weights("step")
+
+
+def test_rollouts_bit_exact_at_scale(gpu, oracle):
+    """4096 instances x 999 steps of get_update (optcon.py:176-200) with random inputs and steps: the float32-quantised
+    state trajectories must be bit-identical to the oracle's (glibc trig) for every instance."""
+    n, TT = 4096, 1000
+    rng = np.random.default_rng(5)
+    xr, ur, Q, R, QT = _random_batch(n, TT, 5, 1.0)
+    with gpu.BatchedNewton(n, TT=TT) as bn:
+        bn.set_weights(Q, R, QT)
+        bn.set_refs(xr, ur)
+        bn.init_guess()
+        xi, ui = bn.iterate_at(0)
+        du = rng.normal(size=(n, 2, TT)) * np.array([30.0, 5.0])[None, :, None]
+        s = rng.uniform(0.02, 1.0, n)
+        bn.set_deltau(du)
+        bn.update(s)
+        xn, un = bn.iterate_at(0)
+        Jn = bn.stats()["J"]
+    bad_init = bad_roll = 0
+    for i in range(0, n, 16):  # 256 sampled instances against the scalar CPU oracle
+        xo, uo = oracle.initial_trajectory(xr[i])
+        bad_init += not (np.array_equal(xo, xi[i]) and np.array_equal(uo, ui[i]))
+        xo, uo, Jo = oracle.rollout(xi[i, :, 0], ui[i], du[i], s[i], cost=(Q, R, QT), xr=xr[i], ur=ur[i])
+        bad_roll += not (np.array_equal(xo, xn[i]) and np.array_equal(uo, un[i]))
+        assert abs(Jo - Jn[i]) <= 1e-12 * abs(Jo)
+    assert bad_init == 0 and bad_roll == 0
+
+
+def test_batch_solve_matches_oracle(gpu, oracle):
+    """Config-4 style batch (randomised step references, device-side initial guess), 96 instances to convergence:
+    per-instance iteration counts, Armijo steps and results vs the CPU oracle."""
+    n, TT = 96, 1000
+    xr, ur, Q, R, QT = _random_batch(n, TT, 2024, 1.0)
+    with gpu.BatchedNewton(n, TT=TT, armijo="lazy") as bn:
+        bn.set_weights(Q, R, QT)
+        bn.set_refs(xr, ur)
+        bn.init_guess()
+        xi, ui = bn.iterate_at(0)
+        total = bn.solve()
+        xs, us = bn.result()
+        h, st = bn.history(), bn.stats()
+    o = oracle.newton_batch(xr, ur, xi, ui, Q, R, QT)
+    assert np.array_equal(st["iters"], o["iters"]) and total == int(o["iters"].sum())
+    assert np.all(st["status"] == 1)
+    for i in range(n):
+        k = o["iters"][i]
+        assert np.array_equal(h["stepsize"][i, :k], o["stepsize"][i, :k]), i
+        assert np.max(np.abs(h["descent"][i, :k] - o["descent"][i, :k]) / np.abs(o["descent"][i, :k])) < 1e-9
+    assert relerr(o["xx_star"], xs) < 1e-9 and relerr(o["uu_star"], us) < 1e-9
+
+
+@pytest.mark.parametrize("n", [1, 33, 100])
+def test_ragged_and_modes_agree(gpu, n):
+    """Instance counts that are not multiples of the warp/CTA size; speculative and lazy Armijo, shared and
+    per-instance reference storage must give bit-identical results."""
+    d = golden("newton_step_f32.npz")
+    TT = 1000
+    rng = np.random.default_rng(n)
+    xi = np.repeat(d["xx_init"][None], n, 0)
+    ui = np.repeat(d["uu_init"][None], n, 0) + rng.normal(size=(n, 2, TT)) * 0.5
+    ui[0] = d["uu_init"]
+    res = []
+    for armijo, shared in (("speculative", True), ("lazy", True), ("speculative", False)):
+        with gpu.BatchedNewton(n, TT=TT, refs_shared=shared, armijo=armijo) as bn:
+            bn.set_weights(d["Q"], d["R"], d["QT"])
+            if shared:
+                bn.set_refs(d["xx_ref"], d["uu_ref"])
+            else:
+                bn.set_refs(np.repeat(d["xx_ref"][None], n, 0), np.repeat(d["uu_ref"][None], n, 0))
+            bn.set_init(xi, ui)
+            bn.iterate(12)
+            res.append((bn.iterate_at(0), bn.history(), bn.stats()))
+    (x0, u0), h0, s0 = res[0]
+    for (x1, u1), h1, s1 in res[1:]:
+        assert np.array_equal(x0, x1) and np.array_equal(u0, u1)
+        assert np.array_equal(h0["stepsize"], h1["stepsize"]) and np.array_equal(h0["JJ"], h1["JJ"])
+        assert np.array_equal(s0["iters"], s1["iters"])
+    k = 12
+    assert np.array_equal(h0["stepsize"][0, :k], d["stepsize"][:k])  # instance 0 is config 1 itself
+
+
+def test_lqr_tracking_config3(gpu, oracle):
+    """BASELINE.json configs[2]: LQR tracking of Data/xx_star.npy from 4096 perturbed initial states."""
+    from aircraftoptimalcontrol_b200 import refgen
+    from aircraftoptimalcontrol_b200.lqr_tracking import lqr_tracking, lqr_tracking_batch
+    d = golden("lqr_tracking.npz")
+    xr, ur, K = lqr_tracking_batch(d["xx_opt"], d["uu_opt"], d["delta"], return_gains=True)
+    assert relerr(d["KK"], K) < 1e-9
+    assert np.array_equal(xr, d["xx_reg"]) and relerr(d["uu_reg"], ur) < 1e-9
+    x1, u1 = lqr_tracking(d["xx_opt"], d["uu_opt"], np.linspace(0, 1, 1000))
+    assert np.array_equal(x1, d["xx_reg"][0])
+    deltas = refgen.config3_deltas(4096)
+    xg, ug = lqr_tracking_batch(d["xx_opt"], d["uu_opt"], deltas)
+    xo, uo, _ = oracle.lqr_tracking(d["xx_opt"], d["uu_opt"], d["Q"], d["R"], d["QT"], deltas)
+    assert np.mean(np.all(xg == xo, axis=(1, 2))) == 1.0
+    assert relerr(uo, ug) < 1e-9
+
+
+def test_full_size_determinism(gpu):
+    """Size-independent property at BASELINE scale: 16384 copies of config 1 solved in one batch all reproduce the
+    single-instance golden history exactly (no cross-instance interference, no dependence on the lane/CTA)."""
+    d = golden("newton_step_f32.npz")
+    n, TT = 16384, 1000
+    with gpu.BatchedNewton(n, TT=TT, refs_shared=True, armijo="lazy") as bn:
+        bn.set_weights(d["Q"], d["R"], d["QT"])
+        bn.set_refs(d["xx_ref"], d["uu_ref"])
+        bn.set_init(np.ascontiguousarray(np.broadcast_to(d["xx_init"], (n, 6, TT))), np.ascontiguousarray(np.broadcast_to(d["uu_init"], (n, 2, TT))))
+        total = bn.solve()
+        h, st = bn.history(), bn.stats()
+        xs, _ = bn.result()
+    k = int(d["iters"])
+    assert total == n * k and np.all(st["iters"] == k)
+    assert np.all(h["stepsize"][:, :k] == d["stepsize"][None]) and np.all(h["JJ"] == h["JJ"][0])
+    assert np.all(xs == xs[0]) and np.array_equal(xs[0], d["xx_star"])
+
+
+def test_error_paths(gpu):
+    from aircraftoptimalcontrol_b200 import _lib
+    with pytest.raises(_lib.AcocError):
+        gpu.BatchedNewton(0)
+    with gpu.BatchedNewton(2, TT=50) as bn:
+        with pytest.raises(_lib.AcocError, match="not ready"):
+            bn.iterate(1)
+        with pytest.raises(ValueError):
+            bn.set_refs(np.zeros((2, 6, 49)), np.zeros((2, 2, 49)))
+        with pytest.raises(_lib.AcocError, match="symmetric"):
+            bn.set_weights(np.triu(np.ones((6, 6))), np.eye(2), np.eye(6))
