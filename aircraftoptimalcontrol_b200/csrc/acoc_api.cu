@@ -259,7 +259,7 @@ __global__ void k_from_soa(const double* __restrict__ s0, const double* __restri
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int n = nb + r, t = tb + threadIdx.x;
-        if (n < nchunk && t < TT) dst[((size_t)n * C + c) * TT + t] = tile[r][threadIdx.x];
+        if (n < nchunk && t < TT) dst[((size_t)n * C + c) * TT + t] = tile[threadIdx.x][r];
     }
 }
 

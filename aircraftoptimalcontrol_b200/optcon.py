@@ -147,7 +147,7 @@ class NewtonMethod(GradientMethod):
     def optimize_batch(self, xx_init, uu_init, tf, dt, xx_ref=None, uu_ref=None, armijo="speculative", return_solver=False):
         """N instances at once: xx_init (N,6,TT), uu_init (N,2,TT); references default to the constructor's
         (shared (6,TT) or per-instance (N,6,TT)).  Returns (xx_star (N,6,TT), uu_star (N,2,TT), info) where info has
-        per-instance histories JJ/descent/stepsize/n_armijo (N,max_iters) and iters/status/J (N,)."""
+        per-instance histories JJ/descent/stepsize/n_armijo (N,max_iters) and iters/status/J/last_descent/n_reg (N,)."""
         xx_init, uu_init = np.asarray(xx_init, dtype=np.float64), np.asarray(uu_init, dtype=np.float64)
         if xx_init.ndim != 3 or xx_init.shape[1] != 6:
             raise ValueError("xx_init must be (N,6,TT)")
@@ -162,8 +162,8 @@ class NewtonMethod(GradientMethod):
             total = bn.solve()
             xs, us = bn.result()
             info = bn.history()
-            info.update(bn.stats())
-            info["total_iters"] = total
+            st = bn.stats()
+            info.update(iters=st["iters"], status=st["status"], J=st["J"], last_descent=st["descent"], n_reg=st["n_reg"], total_iters=total)
         except Exception:
             bn.close()
             raise
