@@ -43,7 +43,10 @@ static int fail(int code, const char* fmt, ...)
 #define CK(call)                                                                                         \
     do {                                                                                                 \
         cudaError_t e__ = (call);                                                                        \
-        if (e__ != cudaSuccess) return fail(ACOC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        if (e__ != cudaSuccess) {                                                                        \
+            cudaGetLastError(); /* clear the per-thread error state */                                   \
+            return fail(ACOC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                                \
     } while (0)
 
 #define REQUIRE(cond, ...)                                   \
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_update(Problem P, NewtonOpts O
     if (only && !only[i]) Jn = S.Jcand[i];
     else Jn = rollout_instance<true, true>(P, U, DU, S.step[i], Xn, Un, i);
     if (bookkeeping) newton_finish_instance(O, S, Jn, kk, i);
-    else S.Jcur[i] = Jn;
+    else { S.Jcur[i] = Jn; S.iters[i] = kk + 1; }
 }
 
 __global__ void k_count_active(const int* __restrict__ status, int N, int* __restrict__ count, long long* __restrict__ iters_sum,
@@ -267,6 +270,14 @@ __global__ void k_fill_int(int* p, int n, int v_lo, int n_lo, int v_hi)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = i < n_lo ? v_lo : v_hi;
+}
+
+// slot of the (which = 0: newest, 1: previous) iterate of every instance: iterate k lives in slot k % 3 and a finished
+// instance stopped at its own iteration count
+__global__ void k_iterate_slot(const int* __restrict__ iters, int which, int* __restrict__ slot_out, int N)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) { const int k = iters[i] - which; slot_out[i] = k < 0 ? -1 : k % 3; }
 }
 
 __global__ void k_result_slot_default(const int* __restrict__ status, int* __restrict__ slot_out, const int* __restrict__ result_slot,
@@ -608,7 +619,7 @@ int acoc_ctx_create(int device, int n_instances, int TT, unsigned flags, acoc_ct
     if (!rc) rc = dalloc(c, &c->counters, 4);
     if (!rc) rc = dalloc(c, &c->iters_sum, 2);
     // staging: up to 256 MiB or the whole batch, whichever is smaller (at least one instance of 6*TT doubles)
-    c->stage_doubles = std::max<size_t>(6 * T, std::min<size_t>((size_t)n_instances * 6 * T, (size_t)32 << 20));
+    c->stage_doubles = std::max<size_t>(16 * T, std::min<size_t>((size_t)n_instances * 16 * T, (size_t)32 << 20));
     if (!rc) rc = dalloc(c, &c->stage, c->stage_doubles);
     if (!rc) rc = alloc_history(c);
     if (rc) return bail(rc);
@@ -981,10 +992,10 @@ int acoc_get_iterate(acoc_ctx* c, int which, double* xx, double* uu)
 {
     TRY(ready(c));
     REQUIRE(which == 0 || which == 1, "which must be 0 (newest) or 1 (previous)");
-    REQUIRE(which == 0 || c->kk >= 1, "no previous iterate yet");
-    const int s = (c->kk - which) % 3;
-    if (xx) TRY(download_soa(c, c->X[s], nullptr, nullptr, nullptr, xx, c->N, 6, c->Np, 0));
-    if (uu) TRY(download_soa(c, c->U[s], nullptr, nullptr, nullptr, uu, c->N, 2, c->Np, 0));
+    k_iterate_slot<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->S.iters, which, c->slot_tmp, c->N);
+    CK(cudaGetLastError());
+    if (xx) TRY(download_soa(c, c->X[0], c->X[1], c->X[2], c->slot_tmp, xx, c->N, 6, c->Np, 0));
+    if (uu) TRY(download_soa(c, c->U[0], c->U[1], c->U[2], c->slot_tmp, uu, c->N, 2, c->Np, 0));
     return 0;
 }
 

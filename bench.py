@@ -40,7 +40,7 @@ TT = 1000
 
 # algorithmic FP64 flops / HBM bytes per instance per time step (dense ns=6, ni=2 accounting)
 FLOPS = dict(backward=2106, forward=126 + 30, cost=107, candidate=159, update=52 + 107)
-BYTES = dict(backward=128 + 128, forward=128 + 64 + 16, cost=128, candidate=32 + 64, update=32 + 64 + 64)
+BYTES = dict(backward=128 + 128, forward=128 + 64 + 16, cost=128, candidate=32 + 64, candidate_write=32 + 64 + 64, update=32 + 64 + 64)
 
 
 def load_peaks():
@@ -242,26 +242,36 @@ def main():
         bn.set_profiling(False)
         h = bn.history()
         ncand = h["n_armijo"][:, W:W + K].astype(np.float64)
-        # candidates actually rolled out: lazy = 1 for everyone + (maxiters-1) where candidate 0 failed
+        steps_per = float(TT - 1)
+        # algorithmic bytes / flops of every phase over the K timed iterations (SURVEY.md 8(d) per-unit figures)
         if args.armijo == "lazy":
-            cand_rollouts = float(np.sum(1 + 9 * (ncand > 1)))
-            upd_rollouts = float(np.sum(ncand > 1))
+            # candidate 0 for everyone, written tentatively (it is the update when accepted); the other 9 candidates and a
+            # separate update rollout only for instances whose candidate 0 failed
+            n_fail = float(np.sum(ncand > 1))
+            cand_bytes = steps_per * (ncand.size * BYTES["candidate_write"] + 9 * n_fail * BYTES["candidate"])
+            cand_flops = steps_per * (ncand.size + 9 * n_fail) * FLOPS["candidate"]
+            upd_units = n_fail
         else:
-            cand_rollouts = float(ncand.size * 10)
-            upd_rollouts = float(ncand.size)
+            cand_bytes = steps_per * ncand.size * 10 * BYTES["candidate"]
+            cand_flops = steps_per * ncand.size * 10 * FLOPS["candidate"]
+            upd_units = float(ncand.size)
         phases = tp["phases"]
         per_launch_ms = {k: v / K for k, v in phases.items()}
         dom = max(("backward", "forward", "candidates", "update"), key=lambda k: phases[k])
-        units = {"backward": n * (TT - 1), "forward": n * (TT - 1), "candidates": cand_rollouts / K * (TT - 1), "update": max(upd_rollouts, 1) / K * (TT - 1)}
-        bkey = {"backward": "backward", "forward": "forward", "candidates": "candidate", "update": "update"}
+        tot_bytes = {"backward": steps_per * n * K * BYTES["backward"], "forward": steps_per * n * K * BYTES["forward"],
+                     "candidates": cand_bytes, "update": steps_per * upd_units * BYTES["update"]}
+        tot_flops = {"backward": steps_per * n * K * FLOPS["backward"], "forward": steps_per * n * K * FLOPS["forward"],
+                     "candidates": cand_flops, "update": steps_per * upd_units * FLOPS["update"]}
         fp64_peak = _lib.measure_fp64_peak(local)
         tbl = {}
         for k in ("backward", "forward", "candidates", "update"):
-            if per_launch_ms[k] <= 0:
+            if phases[k] <= 0 or tot_bytes[k] <= 0:
                 continue
-            gbs = units[k] * BYTES[bkey[k]] / (per_launch_ms[k] * 1e-3) / 1e9
-            tfs = units[k] * FLOPS[bkey[k]] / (per_launch_ms[k] * 1e-3) / 1e12
-            tbl[k] = {"ms_per_launch": per_launch_ms[k], "hbm_gbs": gbs, "hbm_frac": gbs / peaks["hbm_gbs"], "fp64_tflops": tfs, "fp64_frac": tfs / fp64_peak}
+            gbs = tot_bytes[k] / (phases[k] * 1e-3) / 1e9
+            tfs = tot_flops[k] / (phases[k] * 1e-3) / 1e12
+            tbl[k] = {"ms_per_iteration": per_launch_ms[k], "hbm_gbs": gbs, "hbm_frac": gbs / peaks["hbm_gbs"], "fp64_tflops": tfs, "fp64_frac": tfs / fp64_peak}
+        whole = sum(tot_bytes.values()) / (sum(phases.values()) * 1e-3) / 1e9
+        tbl["whole_iteration"] = {"ms_per_iteration": sum(phases.values()) / K, "hbm_gbs": whole, "hbm_frac": whole / peaks["hbm_gbs"]}
         d = tbl[dom]
         # HBM is the binding resource: the bytes are irreducible, while the kernels execute far fewer flops than the dense
         # accounting of SURVEY.md 8(d) (sparsity of A, B and symmetry of P), so the FP64 figure is reported beside it.

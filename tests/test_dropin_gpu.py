@@ -80,12 +80,12 @@ def test_armijo_stepsize_and_get_update(gpu, oracle):
     xt, ut = NM.get_update(s, uu, du, xx[:, 0])
     xo, uo = oracle.rollout(xx[:, 0], uu, du, s)
     assert np.array_equal(xt, xo) and np.array_equal(ut, uo) and not ut[:, -1].any()
-    # exhaustion: an ascent direction returns the untested stepsize_0*beta**10 (optcon.py:327)
-    bad = np.zeros_like(du)
-    bad[0] = 1e3
+    # exhaustion: with JP = 0 no candidate can satisfy J' <= JP + cc*s*descent (costs are positive), so the search
+    # returns the untested stepsize_0*beta**10 (optcon.py:327) and prints nothing (optcon.py:272)
     with redirect_stdout(io.StringIO()) as b:
-        s2 = NM.armijo_stepsize(uu, bad, d["xx_ref"], d["uu_ref"], xx[:, 0], 1000, d["JJ"][kk], -1.0, d["JJ"][kk])
+        s2 = NM.armijo_stepsize(uu, du, d["xx_ref"], d["uu_ref"], xx[:, 0], 1000, 0.0, -1.0, 0.0)
     assert s2 == NM._exhausted_step() and "Armijo stepsize" not in b.getvalue()
+    assert NM.last_armijo_costs.shape == (10,) and np.all(NM.last_armijo_costs > 0)
 
 
 def test_initial_trajectory_close_to_reference(gpu):
