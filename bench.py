@@ -116,7 +116,7 @@ def cpu_port_rate(workload, sample, W, K, state):
         if dx0 is not None:
             xref_i[:, 0] += dx0[i]
         xi[i], ui[i] = corcl.initial_trajectory(xref_i if dx0 is not None else xr[i], quant_f32=(state == "f32"))
-    nt = corcl.max_threads()
+    nt = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     kw = dict(quant_f32=(state == "f32"), n_threads=nt)
     t0 = time.perf_counter()
     a = corcl.newton_batch(xr, ur, xi, ui, Q, R, QT, n_iters_cap=W, **kw) if W > 0 else None
@@ -143,7 +143,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_dict(args, n_per_gpu, world):
@@ -157,7 +157,16 @@ def config_dict(args, n_per_gpu, world):
             "parallelism": "instances sharded round-robin, %d per GPU, no hot-path collective" % n_per_gpu}
 
 
+def emit(line: dict):
+    """Print the ONE JSON line on the process's original stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+
+
 def main():
+    os.dup2(2, 1)  # anything native code prints to fd 1 (e.g. the NCCL version banner) lands on stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
@@ -321,7 +330,7 @@ def main():
 
     clocks = sampler.summary() if sampler else None
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:
         rate, nt, dt, its = cpu_port_rate(args.workload, args.cpu_sample, W, K, args.state)
         cpu = {"value": rate, "unit": UNIT, "cores": nt, "kind": "port",
                "sample": "%d instances x Newton iterations %d..%d of the same workload, C port of the reference (oracle/acoc_oracle.c), OpenMP over "
@@ -333,7 +342,7 @@ def main():
                 "config": config_dict(args, n, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "active_after_timed_region": n_active, "roofline": roofline, "fp64": fp64, "phase_ms": phases, "cpu_baseline": cpu,
                 "device": pkg.device_info(local)["name"], "device_bytes": bn.device_bytes}
-        print(json.dumps(line), flush=True)
+        emit(line)
     bn.close()
     if dist is not None:
         dist.barrier()
