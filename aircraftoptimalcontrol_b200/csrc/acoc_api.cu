@@ -72,53 +72,101 @@ __global__ void __launch_bounds__(128) k_traj_cost(Problem P, const double* __re
     J[i] = traj_cost_instance(P, X, U, i);
 }
 
+// ---- work lists -----------------------------------------------------------------------------------------
+// Late in a solve most instances have terminated and, in the float32-noise phase, only some instances need the
+// remaining Armijo candidates.  Threads are therefore mapped to instances through a compacted, ORDERED list of
+// groups of G = 2^shift consecutive instances that still contain work.  G = 4 (one 32-byte sector of doubles)
+// for the bandwidth-bound sweeps keeps every sector fully used; G = 1 for the compute-bound candidate rollouts.
+struct WorkList {
+    const int* groups;  // nullptr: identity (thread j -> instance j)
+    const int* count;   // number of valid groups (device memory)
+    int shift;
+};
+
+__device__ __forceinline__ int work_instance(const WorkList& L, int j, int N)
+{
+    if (!L.groups) return j < N ? j : -1;
+    const int g = j >> L.shift;
+    if (g >= *L.count) return -1;
+    const int i = (L.groups[g] << L.shift) + (j & ((1 << L.shift) - 1));
+    return i < N ? i : -1;
+}
+
+// One CTA, ordered stream compaction.  mode 0: group alive iff any status[i] == ST_ACTIVE; mode 1: iff any flag[i] != 0.
+__global__ void __launch_bounds__(1024) k_build_list(const int* __restrict__ flag, int mode, int N, int shift, int* __restrict__ groups,
+                                                     int* __restrict__ count)
+{
+    __shared__ int warp_tot[32];
+    __shared__ int base;
+    const int G = 1 << shift, ngroups = (N + G - 1) >> shift;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int tile = 0; tile < ngroups; tile += 1024) {
+        const int g = tile + threadIdx.x;
+        bool alive = false;
+        if (g < ngroups) {
+            for (int k = 0; k < G; ++k) {
+                const int i = (g << shift) + k;
+                if (i < N) alive |= mode == 0 ? (flag[i] == ST_ACTIVE) : (flag[i] != 0);
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0) warp_tot[warp] = __popc(m);
+        __syncthreads();
+        int off = base;
+        for (int w = 0; w < warp; ++w) off += warp_tot[w];
+        if (alive) groups[off + __popc(m & ((1u << lane) - 1))] = g;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 32; ++w) t += warp_tot[w]; base += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base;
+}
+
 template <bool EXACT>
-__global__ void __launch_bounds__(BWD_THREADS) k_backward(Problem P, const double* __restrict__ X, const double* __restrict__ U,
+__global__ void __launch_bounds__(BWD_THREADS) k_backward(Problem P, WorkList L, const double* __restrict__ X, const double* __restrict__ U,
                                                           double* __restrict__ KSG, const int* __restrict__ status, int* __restrict__ n_reg)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.N || status[i] != ST_ACTIVE) return;
+    const int i = work_instance(L, blockIdx.x * blockDim.x + threadIdx.x, P.N);
+    if (i < 0 || status[i] != ST_ACTIVE) return;
     const int r = backward_instance<EXACT>(P, X, U, KSG, i);
     if (r) n_reg[i] += r;
 }
 
-__global__ void __launch_bounds__(FWD_THREADS) k_forward(Problem P, const double* __restrict__ X, const double* __restrict__ U,
+__global__ void __launch_bounds__(FWD_THREADS) k_forward(Problem P, WorkList L, const double* __restrict__ X, const double* __restrict__ U,
                                                          const double* __restrict__ KSG, double* __restrict__ DU, double* DX,
                                                          const int* __restrict__ status, double* __restrict__ descent)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.N || status[i] != ST_ACTIVE) return;
+    const int i = work_instance(L, blockIdx.x * blockDim.x + threadIdx.x, P.N);
+    if (i < 0 || status[i] != ST_ACTIVE) return;
     descent[i] = forward_lq_instance(P, X, U, KSG, DU, DX, i);
 }
 
-// thread (x = instance within tile, y = candidate): J of candidate c0 + y for instance i
-// need (optional): only instances with need[i] != 0 are evaluated (lazy Armijo)
-__global__ void k_candidates(Problem P, const double* __restrict__ U, const double* __restrict__ DU,
-                             const double* __restrict__ cand_steps, int c0, const int* __restrict__ status,
-                             const int* __restrict__ need, double* __restrict__ Jcand)
+// thread (x = position in the work list, y = candidate): J of candidate c0 + y for instance i
+__global__ void k_candidates(Problem P, WorkList L, const double* __restrict__ U, const double* __restrict__ DU,
+                             const double* __restrict__ cand_steps, int c0, const int* __restrict__ status, double* __restrict__ Jcand)
 {
-    const int i = blockIdx.x * CAND_TILE + threadIdx.x;
+    const int i = work_instance(L, blockIdx.x * CAND_TILE + threadIdx.x, P.N);
     const int c = c0 + threadIdx.y;
-    if (i >= P.N || status[i] != ST_ACTIVE) return;
-    if (need && !need[i]) return;
+    if (i < 0 || status[i] != ST_ACTIVE) return;
     Jcand[(size_t)c * P.Np + i] = rollout_instance<false, true>(P, U, DU, cand_steps[c], nullptr, nullptr, i);
 }
 
 // lazy Armijo, first round: candidate 0 for every active instance, writing the trajectory tentatively into
 // the next slot (it IS the update whenever the candidate is accepted)
-__global__ void __launch_bounds__(ROLL_THREADS) k_candidate0_write(Problem P, const double* __restrict__ U, const double* __restrict__ DU,
+__global__ void __launch_bounds__(ROLL_THREADS) k_candidate0_write(Problem P, WorkList L, const double* __restrict__ U, const double* __restrict__ DU,
                                                                    const double* __restrict__ cand_steps, double* __restrict__ Xn,
                                                                    double* __restrict__ Un, const int* __restrict__ status,
                                                                    double* __restrict__ Jcand)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.N || status[i] != ST_ACTIVE) return;
+    const int i = work_instance(L, blockIdx.x * blockDim.x + threadIdx.x, P.N);
+    if (i < 0 || status[i] != ST_ACTIVE) return;
     Jcand[i] = rollout_instance<true, true>(P, U, DU, cand_steps[0], Xn, Un, i);
 }
 
 // lazy Armijo: after candidate 0, flag the instances that need the remaining candidates
-__global__ void k_lazy_need(NewtonOpts O, NewtonState S, const double* __restrict__ cand_steps, int N, int* __restrict__ need,
-                            int* __restrict__ n_need)
+__global__ void k_lazy_need(NewtonOpts O, NewtonState S, const double* __restrict__ cand_steps, int N, int* __restrict__ need)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -128,7 +176,6 @@ __global__ void k_lazy_need(NewtonOpts O, NewtonState S, const double* __restric
         nd = (S.Jcand[i] > JP + O.cc * cand_steps[0] * d) ? 1 : 0;
     }
     need[i] = nd;
-    if (nd) atomicAdd(n_need, 1);
 }
 
 __global__ void k_select(NewtonOpts O, NewtonState S, const double* __restrict__ cand_steps, int kk, int N, int Np)
@@ -141,12 +188,12 @@ __global__ void k_select(NewtonOpts O, NewtonState S, const double* __restrict__
 // get_update with the per-instance step + termination bookkeeping.
 // only (optional): when non-null, instances with only[i] == 0 keep the trajectory already present in the next
 // slot (lazy Armijo: candidate 0 was accepted and is already there) and just run the bookkeeping.
-__global__ void __launch_bounds__(ROLL_THREADS) k_update(Problem P, NewtonOpts O, NewtonState S, const double* __restrict__ U,
+__global__ void __launch_bounds__(ROLL_THREADS) k_update(Problem P, WorkList L, NewtonOpts O, NewtonState S, const double* __restrict__ U,
                                                          const double* __restrict__ DU, double* __restrict__ Xn, double* __restrict__ Un,
                                                          const int* __restrict__ only, int kk, int bookkeeping)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.N || S.status[i] != ST_ACTIVE) return;
+    const int i = work_instance(L, blockIdx.x * blockDim.x + threadIdx.x, P.N);
+    if (i < 0 || S.status[i] != ST_ACTIVE) return;
     double Jn;
     if (only && !only[i]) Jn = S.Jcand[i];
     else Jn = rollout_instance<true, true>(P, U, DU, S.step[i], Xn, Un, i);
@@ -321,6 +368,7 @@ struct acoc_ctx {
     double* stage = nullptr;  // device staging for layout conversion
     size_t stage_doubles = 0;
     int *need = nullptr, *counters = nullptr, *slot_tmp = nullptr;
+    int *act_groups = nullptr, *need_groups = nullptr;  // work lists (see WorkList); counts live in counters[1], counters[2]
     long long* iters_sum = nullptr;
     std::vector<void*> allocs;
     unsigned long long bytes = 0;
@@ -617,6 +665,8 @@ int acoc_ctx_create(int device, int n_instances, int TT, unsigned flags, acoc_ct
     if (!rc) rc = dalloc(c, &c->need, Np);
     if (!rc) rc = dalloc(c, &c->slot_tmp, Np);
     if (!rc) rc = dalloc(c, &c->counters, 4);
+    if (!rc) rc = dalloc(c, &c->act_groups, Np);
+    if (!rc) rc = dalloc(c, &c->need_groups, Np);
     if (!rc) rc = dalloc(c, &c->iters_sum, 2);
     // staging: up to 256 MiB or the whole batch, whichever is smaller (at least one instance of 6*TT doubles)
     c->stage_doubles = std::max<size_t>(16 * T, std::min<size_t>((size_t)n_instances * 16 * T, (size_t)32 << 20));
@@ -758,11 +808,27 @@ static int launch_cost(acoc_ctx* c)
     ++c->launches;
     return 0;
 }
+static WorkList act_list(acoc_ctx* c)
+{
+    WorkList L;
+    L.groups = c->act_groups;
+    L.count = c->counters + 1;
+    L.shift = 2;  // groups of 4 instances = one 32-byte sector of doubles
+    return L;
+}
+// rebuild the list of instance groups that still have an active member (start of every iteration)
+static int launch_build_active(acoc_ctx* c)
+{
+    k_build_list<<<1, 1024, 0, c->stream>>>(c->S.status, 0, c->N, 2, c->act_groups, c->counters + 1);
+    CK(cudaGetLastError());
+    ++c->launches;
+    return 0;
+}
 static int launch_backward(acoc_ctx* c, bool exact)
 {
-    const int cur = c->kk % 3, g = (c->N + BWD_THREADS - 1) / BWD_THREADS;
-    if (exact) k_backward<true><<<g, BWD_THREADS, 0, c->stream>>>(c->P, c->X[cur], c->U[cur], c->KSG, c->S.status, c->S.n_reg);
-    else k_backward<false><<<g, BWD_THREADS, 0, c->stream>>>(c->P, c->X[cur], c->U[cur], c->KSG, c->S.status, c->S.n_reg);
+    const int cur = c->kk % 3, g = (c->Np + BWD_THREADS - 1) / BWD_THREADS;
+    if (exact) k_backward<true><<<g, BWD_THREADS, 0, c->stream>>>(c->P, act_list(c), c->X[cur], c->U[cur], c->KSG, c->S.status, c->S.n_reg);
+    else k_backward<false><<<g, BWD_THREADS, 0, c->stream>>>(c->P, act_list(c), c->X[cur], c->U[cur], c->KSG, c->S.status, c->S.n_reg);
     CK(cudaGetLastError());
     ++c->launches;
     return 0;
@@ -770,8 +836,8 @@ static int launch_backward(acoc_ctx* c, bool exact)
 static int launch_forward(acoc_ctx* c)
 {
     const int cur = c->kk % 3;
-    k_forward<<<(c->N + FWD_THREADS - 1) / FWD_THREADS, FWD_THREADS, 0, c->stream>>>(c->P, c->X[cur], c->U[cur], c->KSG, c->DU, nullptr,
-                                                                                    c->S.status, c->S.descent);
+    k_forward<<<(c->Np + FWD_THREADS - 1) / FWD_THREADS, FWD_THREADS, 0, c->stream>>>(c->P, act_list(c), c->X[cur], c->U[cur], c->KSG, c->DU, nullptr,
+                                                                                     c->S.status, c->S.descent);
     CK(cudaGetLastError());
     ++c->launches;
     return 0;
@@ -780,23 +846,28 @@ static int launch_forward(acoc_ctx* c)
 // instances whose candidate 0 is already in the next slot.
 static int launch_armijo(acoc_ctx* c, bool* lazy_only)
 {
-    const int cur = c->kk % 3, nxt = (c->kk + 1) % 3, N = c->N, nc = c->O.armijo_maxiters;
+    const int cur = c->kk % 3, nxt = (c->kk + 1) % 3, N = c->N, Np = c->Np, nc = c->O.armijo_maxiters;
     *lazy_only = false;
     if ((c->flags & ACOC_ARMIJO_LAZY) && nc > 1) {
-        k_candidate0_write<<<(N + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, 0, c->stream>>>(c->P, c->U[cur], c->DU, c->cand_steps,
-                                                                                                c->X[nxt], c->U[nxt], c->S.status, c->S.Jcand);
+        k_candidate0_write<<<(Np + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, 0, c->stream>>>(c->P, act_list(c), c->U[cur], c->DU, c->cand_steps,
+                                                                                                 c->X[nxt], c->U[nxt], c->S.status, c->S.Jcand);
         CK(cudaGetLastError());
-        CK(cudaMemsetAsync(c->counters, 0, sizeof(int), c->stream));
-        k_lazy_need<<<(N + 255) / 256, 256, 0, c->stream>>>(c->O, c->S, c->cand_steps, N, c->need, c->counters);
+        k_lazy_need<<<(N + 255) / 256, 256, 0, c->stream>>>(c->O, c->S, c->cand_steps, N, c->need);
         CK(cudaGetLastError());
+        WorkList L;  // per-instance list of the instances whose candidate 0 failed: the rollouts are compute-bound
+        L.groups = c->need_groups; L.count = c->counters + 2; L.shift = 0;
+        k_build_list<<<1, 1024, 0, c->stream>>>(c->need, 1, N, 0, c->need_groups, c->counters + 2);
+        CK(cudaGetLastError());
+        ++c->launches;
         dim3 block(CAND_TILE, nc - 1);
-        k_candidates<<<(N + CAND_TILE - 1) / CAND_TILE, block, 0, c->stream>>>(c->P, c->U[cur], c->DU, c->cand_steps, 1, c->S.status, c->need, c->S.Jcand);
+        k_candidates<<<(N + CAND_TILE - 1) / CAND_TILE, block, 0, c->stream>>>(c->P, L, c->U[cur], c->DU, c->cand_steps, 1,
+                                                                              c->S.status, c->S.Jcand);
         CK(cudaGetLastError());
         c->launches += 3;
         *lazy_only = true;
     } else {
         dim3 block(CAND_TILE, nc);
-        k_candidates<<<(N + CAND_TILE - 1) / CAND_TILE, block, 0, c->stream>>>(c->P, c->U[cur], c->DU, c->cand_steps, 0, c->S.status, nullptr, c->S.Jcand);
+        k_candidates<<<(Np + CAND_TILE - 1) / CAND_TILE, block, 0, c->stream>>>(c->P, act_list(c), c->U[cur], c->DU, c->cand_steps, 0, c->S.status, c->S.Jcand);
         CK(cudaGetLastError());
         ++c->launches;
     }
@@ -805,11 +876,13 @@ static int launch_armijo(acoc_ctx* c, bool* lazy_only)
     ++c->launches;
     return 0;
 }
-static int launch_update(acoc_ctx* c, bool lazy_only, bool bookkeeping)
+static int launch_update(acoc_ctx* c, bool lazy_only, bool bookkeeping, bool use_list)
 {
     const int cur = c->kk % 3, nxt = (c->kk + 1) % 3;
-    k_update<<<(c->N + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, 0, c->stream>>>(c->P, c->O, c->S, c->U[cur], c->DU, c->X[nxt], c->U[nxt],
-                                                                                      lazy_only ? c->need : nullptr, c->kk, bookkeeping ? 1 : 0);
+    WorkList L = act_list(c);
+    if (!use_list) L.groups = nullptr;
+    k_update<<<(c->Np + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, 0, c->stream>>>(c->P, L, c->O, c->S, c->U[cur], c->DU, c->X[nxt], c->U[nxt],
+                                                                                       lazy_only ? c->need : nullptr, c->kk, bookkeeping ? 1 : 0);
     CK(cudaGetLastError());
     ++c->launches;
     return 0;
@@ -843,6 +916,7 @@ int acoc_newton_iterate(acoc_ctx* c, int n_iters, int* n_active_out)
         if (c->kk >= c->O.max_iters - 1) break;  // for kk in range(max_iters-1), optcon.py:415
         bool lazy_only = false;
         if (prof) CK(cudaEventRecord(c->ev[0], c->stream));
+        TRY(launch_build_active(c));
         if (c->kk == 0) TRY(launch_cost(c));  // later iterations inherit the cost from the update rollout
         if (prof) CK(cudaEventRecord(c->ev[1], c->stream));
         TRY(launch_backward(c, c->kk > c->O.exact_after));  // optcon.py:443
@@ -851,7 +925,7 @@ int acoc_newton_iterate(acoc_ctx* c, int n_iters, int* n_active_out)
         if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
         TRY(launch_armijo(c, &lazy_only));
         if (prof) CK(cudaEventRecord(c->ev[4], c->stream));
-        TRY(launch_update(c, lazy_only, true));
+        TRY(launch_update(c, lazy_only, true, true));
         if (prof) {
             CK(cudaEventRecord(c->ev[5], c->stream));
             CK(cudaEventSynchronize(c->ev[5]));
@@ -911,6 +985,7 @@ int acoc_eval_cost(acoc_ctx* c, double* J)
 int acoc_backward(acoc_ctx* c, int exact)
 {
     TRY(ready(c));
+    TRY(launch_build_active(c));
     TRY(launch_backward(c, exact != 0));
     CK(cudaStreamSynchronize(c->stream));
     return 0;
@@ -919,6 +994,7 @@ int acoc_backward(acoc_ctx* c, int exact)
 int acoc_forward(acoc_ctx* c, double* descent)
 {
     TRY(ready(c));
+    TRY(launch_build_active(c));
     TRY(launch_forward(c));
     if (descent) { CK(cudaMemcpyAsync(descent, c->S.descent, c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream)); }
     CK(cudaStreamSynchronize(c->stream));
@@ -931,8 +1007,10 @@ int acoc_armijo(acoc_ctx* c, double* stepsize, double* costs)
     REQUIRE(c->kk < c->O.max_iters, "iteration counter exhausted");
     // always the speculative evaluation here: this entry point reports the cost of every candidate
     const int cur = c->kk % 3, N = c->N, nc = c->O.armijo_maxiters;
+    WorkList L;
+    L.groups = nullptr; L.count = c->counters + 1; L.shift = 0;
     dim3 block(CAND_TILE, nc);
-    k_candidates<<<(N + CAND_TILE - 1) / CAND_TILE, block, 0, c->stream>>>(c->P, c->U[cur], c->DU, c->cand_steps, 0, c->S.status, nullptr, c->S.Jcand);
+    k_candidates<<<(N + CAND_TILE - 1) / CAND_TILE, block, 0, c->stream>>>(c->P, L, c->U[cur], c->DU, c->cand_steps, 0, c->S.status, c->S.Jcand);
     CK(cudaGetLastError());
     k_select<<<(N + 255) / 256, 256, 0, c->stream>>>(c->O, c->S, c->cand_steps, c->kk, N, c->Np);
     CK(cudaGetLastError());
@@ -951,7 +1029,7 @@ int acoc_update(acoc_ctx* c, const double* stepsize)
     TRY(ready(c));
     REQUIRE(c->kk < c->O.max_iters - 1, "iteration counter exhausted");
     if (stepsize) CK(cudaMemcpyAsync(c->S.step, stepsize, c->N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    TRY(launch_update(c, false, false));
+    TRY(launch_update(c, false, false, false));
     ++c->kk;
     CK(cudaStreamSynchronize(c->stream));
     return 0;
