@@ -10,7 +10,7 @@ All arithmetic runs in hand-written sm_100a CUDA kernels inside libacoc.so (C AB
 no CPU fallback.
 """
 from ._lib import AcocError, device_count, device_info  # noqa: F401
-from .batch import BatchedNewton  # noqa: F401
+from .batch import BatchedNewton, PipelinedNewton  # noqa: F401
 
-__all__ = ["BatchedNewton", "AcocError", "device_count", "device_info"]
+__all__ = ["BatchedNewton", "PipelinedNewton", "AcocError", "device_count", "device_info"]
 __version__ = "0.1.0"

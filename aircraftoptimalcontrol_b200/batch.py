@@ -182,3 +182,71 @@ class BatchedNewton:
         L.check(L.lib().acoc_get_timing(self._h, C.addressof(tot), C.addressof(ph), C.addressof(nl)))
         names = ("cost", "backward", "forward", "candidates", "select", "update")
         return dict(total_ms=tot.value, launches=nl.value, phases={k: ph[i] for i, k in enumerate(names)})
+
+
+
+class PipelinedNewton:
+    """A large batch solved as `n_chunks` independent sub-batches, each with its own context/stream and its own host
+    thread, so that the host->device copy of one chunk, the Newton iterations of another and the device->host copy of
+    a third overlap.  Instances are independent, so chunking changes no result.  The sub-contexts are created once and
+    reused across `solve` calls.
+    """
+
+    def __init__(self, n_instances, n_chunks=4, TT=1000, device=0, **solver_kw):
+        self.N, self.TT = int(n_instances), int(TT)
+        n_chunks = max(1, min(int(n_chunks), self.N))
+        self.bounds = [(self.N * k) // n_chunks for k in range(n_chunks + 1)]
+        self.parts = [BatchedNewton(self.bounds[k + 1] - self.bounds[k], TT=TT, device=device, **solver_kw) for k in range(n_chunks)]
+
+    def close(self):
+        for p in self.parts:
+            p.close()
+        self.parts = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_weights(self, QQt, RRt, QQT):
+        for p in self.parts:
+            p.set_weights(QQt, RRt, QQT)
+
+    def solve(self, xx_ref, uu_ref, xx_init=None, uu_init=None, dx0=None, out=None):
+        """xx_ref (N,6,TT), uu_ref (N,2,TT) per-instance references (pinned host memory makes the copies fast); initial
+        guess = (xx_init, uu_init) if given, else the device P-law rollout (optionally started at xx_ref[:,0] + dx0).
+        Returns (xx_star, uu_star, stats) with stats = dict(iters, status, J, descent, n_reg), each of length N."""
+        import threading
+
+        N, TT = self.N, self.TT
+        xs, us = out if out is not None else (np.empty((N, 6, TT)), np.empty((N, 2, TT)))
+        stats = dict(iters=np.zeros(N, dtype=np.int32), status=np.zeros(N, dtype=np.int32), J=np.zeros(N), descent=np.zeros(N),
+                     n_reg=np.zeros(N, dtype=np.int32))
+        errors = []
+
+        def work(k):
+            lo, hi = self.bounds[k], self.bounds[k + 1]
+            bn = self.parts[k]
+            try:
+                bn.set_refs(xx_ref[lo:hi], uu_ref[lo:hi])
+                if xx_init is not None:
+                    bn.set_init(xx_init[lo:hi], uu_init[lo:hi])
+                else:
+                    bn.init_guess(dx0=None if dx0 is None else dx0[lo:hi])
+                bn.solve()
+                bn.result(out=(xs[lo:hi], us[lo:hi]))
+                st = bn.stats()
+                for key in stats:
+                    stats[key][lo:hi] = st[key]
+            except Exception as e:  # surfaced after the join
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(len(self.parts))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return xs, us, stats

@@ -237,3 +237,21 @@ def test_error_paths(gpu):
             bn.set_refs(np.zeros((2, 6, 49)), np.zeros((2, 2, 49)))
         with pytest.raises(_lib.AcocError, match="symmetric"):
             bn.set_weights(np.triu(np.ones((6, 6))), np.eye(2), np.eye(6))
+
+
+def test_pipelined_chunks_equal_single_batch(gpu):
+    """PipelinedNewton (independent sub-batches on their own streams/threads) returns exactly what one big batch does."""
+    n, TT = 200, 300
+    xr, ur, Q, R, QT = _random_batch(n, TT, 77, 0.3)
+    with gpu.BatchedNewton(n, TT=TT, armijo="lazy") as bn:
+        bn.set_weights(Q, R, QT)
+        bn.set_refs(xr, ur)
+        bn.init_guess()
+        bn.solve()
+        xs, us = bn.result()
+        st = bn.stats()
+    with gpu.PipelinedNewton(n, n_chunks=3, TT=TT, armijo="lazy") as pn:
+        pn.set_weights(Q, R, QT)
+        xp, up, sp = pn.solve(xr, ur)
+    assert np.array_equal(xs, xp) and np.array_equal(us, up)
+    assert np.array_equal(st["iters"], sp["iters"]) and np.array_equal(st["status"], sp["status"]) and np.array_equal(st["J"], sp["J"])
