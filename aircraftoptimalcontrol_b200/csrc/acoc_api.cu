@@ -64,6 +64,13 @@ constexpr int FWD_THREADS = 64;
 constexpr int ROLL_THREADS = 64;
 constexpr int CAND_TILE = 32;  // instances per candidate CTA (one warp per candidate)
 
+// launch a kernel templated on the state quantisation (float32 rounding of aircraft_simplified.py:300 or none)
+#define LAUNCH_Q32(q32, kernel, grid, block, stream, ...)                         \
+    do {                                                                        \
+        if (q32) kernel<true><<<grid, block, 0, stream>>>(__VA_ARGS__);          \
+        else kernel<false><<<grid, block, 0, stream>>>(__VA_ARGS__);             \
+    } while (0)
+
 __global__ void __launch_bounds__(128) k_traj_cost(Problem P, const double* __restrict__ X, const double* __restrict__ U,
                                                   const int* __restrict__ status, double* __restrict__ J)
 {
@@ -129,9 +136,12 @@ __global__ void __launch_bounds__(BWD_THREADS) k_backward(Problem P, WorkList L,
                                                           double* __restrict__ KSG, const int* __restrict__ status, int* __restrict__ n_reg)
 {
     const int i = work_instance(L, blockIdx.x * blockDim.x + threadIdx.x, P.N);
-    if (i < 0 || status[i] != ST_ACTIVE) return;
+    if (i < 0) return;
+    // Lanes of already finished instances inside a live group of 4 run the sweep too: K/sigma/g are per-iteration
+    // scratch, and writing all four lanes keeps every 32-byte sector fully written (a partially written sector costs
+    // a DRAM read-modify-write); the lane would otherwise idle for the same number of warp instructions.
     const int r = backward_instance<EXACT>(P, X, U, KSG, i);
-    if (r) n_reg[i] += r;
+    if (r && status[i] == ST_ACTIVE) n_reg[i] += r;
 }
 
 __global__ void __launch_bounds__(FWD_THREADS) k_forward(Problem P, WorkList L, const double* __restrict__ X, const double* __restrict__ U,
@@ -139,22 +149,25 @@ __global__ void __launch_bounds__(FWD_THREADS) k_forward(Problem P, WorkList L, 
                                                          const int* __restrict__ status, double* __restrict__ descent)
 {
     const int i = work_instance(L, blockIdx.x * blockDim.x + threadIdx.x, P.N);
-    if (i < 0 || status[i] != ST_ACTIVE) return;
-    descent[i] = forward_lq_instance(P, X, U, KSG, DU, DX, i);
+    if (i < 0) return;
+    const double d = forward_lq_instance(P, X, U, KSG, DU, DX, i);  // finished lanes of a live group: see k_backward
+    if (status[i] == ST_ACTIVE) descent[i] = d;
 }
 
 // thread (x = position in the work list, y = candidate): J of candidate c0 + y for instance i
+template <bool Q32>
 __global__ void k_candidates(Problem P, WorkList L, const double* __restrict__ U, const double* __restrict__ DU,
                              const double* __restrict__ cand_steps, int c0, const int* __restrict__ status, double* __restrict__ Jcand)
 {
     const int i = work_instance(L, blockIdx.x * CAND_TILE + threadIdx.x, P.N);
     const int c = c0 + threadIdx.y;
     if (i < 0 || status[i] != ST_ACTIVE) return;
-    Jcand[(size_t)c * P.Np + i] = rollout_instance<false, true>(P, U, DU, cand_steps[c], nullptr, nullptr, i);
+    Jcand[(size_t)c * P.Np + i] = rollout_instance<false, true, Q32>(P, U, DU, cand_steps[c], nullptr, nullptr, i);
 }
 
 // lazy Armijo, first round: candidate 0 for every active instance, writing the trajectory tentatively into
 // the next slot (it IS the update whenever the candidate is accepted)
+template <bool Q32>
 __global__ void __launch_bounds__(ROLL_THREADS) k_candidate0_write(Problem P, WorkList L, const double* __restrict__ U, const double* __restrict__ DU,
                                                                    const double* __restrict__ cand_steps, double* __restrict__ Xn,
                                                                    double* __restrict__ Un, const int* __restrict__ status,
@@ -162,7 +175,7 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_candidate0_write(Problem P, Wo
 {
     const int i = work_instance(L, blockIdx.x * blockDim.x + threadIdx.x, P.N);
     if (i < 0 || status[i] != ST_ACTIVE) return;
-    Jcand[i] = rollout_instance<true, true>(P, U, DU, cand_steps[0], Xn, Un, i);
+    Jcand[i] = rollout_instance<true, true, Q32>(P, U, DU, cand_steps[0], Xn, Un, i);
 }
 
 // lazy Armijo: after candidate 0, flag the instances that need the remaining candidates
@@ -188,6 +201,7 @@ __global__ void k_select(NewtonOpts O, NewtonState S, const double* __restrict__
 // get_update with the per-instance step + termination bookkeeping.
 // only (optional): when non-null, instances with only[i] == 0 keep the trajectory already present in the next
 // slot (lazy Armijo: candidate 0 was accepted and is already there) and just run the bookkeeping.
+template <bool Q32>
 __global__ void __launch_bounds__(ROLL_THREADS) k_update(Problem P, WorkList L, NewtonOpts O, NewtonState S, const double* __restrict__ U,
                                                          const double* __restrict__ DU, double* __restrict__ Xn, double* __restrict__ Un,
                                                          const int* __restrict__ only, int kk, int bookkeeping)
@@ -196,7 +210,7 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_update(Problem P, WorkList L, 
     if (i < 0 || S.status[i] != ST_ACTIVE) return;
     double Jn;
     if (only && !only[i]) Jn = S.Jcand[i];
-    else Jn = rollout_instance<true, true>(P, U, DU, S.step[i], Xn, Un, i);
+    else Jn = rollout_instance<true, true, Q32>(P, U, DU, S.step[i], Xn, Un, i);
     if (bookkeeping) newton_finish_instance(O, S, Jn, kk, i);
     else { S.Jcur[i] = Jn; S.iters[i] = kk + 1; }
 }
@@ -215,21 +229,23 @@ __global__ void k_count_active(const int* __restrict__ status, int N, int* __res
     }
 }
 
+template <bool Q32>
 __global__ void __launch_bounds__(ROLL_THREADS) k_track(Problem P, const double* __restrict__ Kt, const double* __restrict__ xopt,
                                                         const double* __restrict__ uopt, const double* __restrict__ xstart,
                                                         double* __restrict__ Xn, double* __restrict__ Un)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.N) return;
-    track_instance(P, Kt, xopt, uopt, xstart, Xn, Un, i);
+    track_instance<Q32>(P, Kt, xopt, uopt, xstart, Xn, Un, i);
 }
 
+template <bool Q32>
 __global__ void __launch_bounds__(ROLL_THREADS) k_init_guess(Problem P, double kp, double kt, const double* __restrict__ dx0,
                                                              double* __restrict__ Xn, double* __restrict__ Un)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.N) return;
-    init_guess_instance(P, kp, kt, dx0, Xn, Un, i);
+    init_guess_instance<Q32>(P, kp, kt, dx0, Xn, Un, i);
 }
 
 __global__ void k_step_batch(Model M, int q32, int n, const double* __restrict__ x, const double* __restrict__ u,
@@ -780,7 +796,7 @@ int acoc_init_guess(acoc_ctx* c, double kp, double kt, const double* dx0)
         CK(cudaStreamSynchronize(c->stream));
         d_dx0 = c->x0;
     }
-    k_init_guess<<<(c->N + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, 0, c->stream>>>(c->P, kp, kt, d_dx0, c->X[0], c->U[0]);
+    LAUNCH_Q32(c->P.q32, k_init_guess, (c->N + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, c->stream, c->P, kp, kt, d_dx0, c->X[0], c->U[0]);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(c->x0, c->X[0], (size_t)6 * c->Np * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -849,8 +865,8 @@ static int launch_armijo(acoc_ctx* c, bool* lazy_only)
     const int cur = c->kk % 3, nxt = (c->kk + 1) % 3, N = c->N, Np = c->Np, nc = c->O.armijo_maxiters;
     *lazy_only = false;
     if ((c->flags & ACOC_ARMIJO_LAZY) && nc > 1) {
-        k_candidate0_write<<<(Np + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, 0, c->stream>>>(c->P, act_list(c), c->U[cur], c->DU, c->cand_steps,
-                                                                                                 c->X[nxt], c->U[nxt], c->S.status, c->S.Jcand);
+        LAUNCH_Q32(c->P.q32, k_candidate0_write, (Np + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, c->stream, c->P, act_list(c), c->U[cur], c->DU,
+                   c->cand_steps, c->X[nxt], c->U[nxt], c->S.status, c->S.Jcand);
         CK(cudaGetLastError());
         k_lazy_need<<<(N + 255) / 256, 256, 0, c->stream>>>(c->O, c->S, c->cand_steps, N, c->need);
         CK(cudaGetLastError());
@@ -860,14 +876,15 @@ static int launch_armijo(acoc_ctx* c, bool* lazy_only)
         CK(cudaGetLastError());
         ++c->launches;
         dim3 block(CAND_TILE, nc - 1);
-        k_candidates<<<(N + CAND_TILE - 1) / CAND_TILE, block, 0, c->stream>>>(c->P, L, c->U[cur], c->DU, c->cand_steps, 1,
-                                                                              c->S.status, c->S.Jcand);
+        LAUNCH_Q32(c->P.q32, k_candidates, (N + CAND_TILE - 1) / CAND_TILE, block, c->stream, c->P, L, c->U[cur], c->DU, c->cand_steps, 1, c->S.status,
+                   c->S.Jcand);
         CK(cudaGetLastError());
         c->launches += 3;
         *lazy_only = true;
     } else {
         dim3 block(CAND_TILE, nc);
-        k_candidates<<<(Np + CAND_TILE - 1) / CAND_TILE, block, 0, c->stream>>>(c->P, act_list(c), c->U[cur], c->DU, c->cand_steps, 0, c->S.status, c->S.Jcand);
+        LAUNCH_Q32(c->P.q32, k_candidates, (Np + CAND_TILE - 1) / CAND_TILE, block, c->stream, c->P, act_list(c), c->U[cur], c->DU, c->cand_steps, 0,
+                   c->S.status, c->S.Jcand);
         CK(cudaGetLastError());
         ++c->launches;
     }
@@ -881,8 +898,8 @@ static int launch_update(acoc_ctx* c, bool lazy_only, bool bookkeeping, bool use
     const int cur = c->kk % 3, nxt = (c->kk + 1) % 3;
     WorkList L = act_list(c);
     if (!use_list) L.groups = nullptr;
-    k_update<<<(c->Np + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, 0, c->stream>>>(c->P, L, c->O, c->S, c->U[cur], c->DU, c->X[nxt], c->U[nxt],
-                                                                                       lazy_only ? c->need : nullptr, c->kk, bookkeeping ? 1 : 0);
+    LAUNCH_Q32(c->P.q32, k_update, (c->Np + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, c->stream, c->P, L, c->O, c->S, c->U[cur], c->DU, c->X[nxt],
+               c->U[nxt], lazy_only ? c->need : nullptr, c->kk, bookkeeping ? 1 : 0);
     CK(cudaGetLastError());
     ++c->launches;
     return 0;
@@ -1010,7 +1027,7 @@ int acoc_armijo(acoc_ctx* c, double* stepsize, double* costs)
     WorkList L;
     L.groups = nullptr; L.count = c->counters + 1; L.shift = 0;
     dim3 block(CAND_TILE, nc);
-    k_candidates<<<(N + CAND_TILE - 1) / CAND_TILE, block, 0, c->stream>>>(c->P, L, c->U[cur], c->DU, c->cand_steps, 0, c->S.status, c->S.Jcand);
+    LAUNCH_Q32(c->P.q32, k_candidates, (N + CAND_TILE - 1) / CAND_TILE, block, c->stream, c->P, L, c->U[cur], c->DU, c->cand_steps, 0, c->S.status, c->S.Jcand);
     CK(cudaGetLastError());
     k_select<<<(N + 255) / 256, 256, 0, c->stream>>>(c->O, c->S, c->cand_steps, c->kk, N, c->Np);
     CK(cudaGetLastError());
@@ -1180,7 +1197,7 @@ int acoc_lqr_tracking(int device, int n, int TT, const double* params, int state
     std::vector<double> xs((size_t)6 * c->Np, 0.0);
     for (int i = 0; i < n; ++i) for (int k = 0; k < 6; ++k) xs[(size_t)k * c->Np + i] = xx_opt[(size_t)k * TT] + delta[(size_t)i * 6 + k];
     TRY(t.up(&dstart, xs.data(), xs.size()));
-    k_track<<<(n + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, 0, c->stream>>>(c->P, dK, c->xref, c->uref, dstart, c->X[0], c->U[0]);
+    LAUNCH_Q32(c->P.q32, k_track, (n + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, c->stream, c->P, dK, c->xref, c->uref, dstart, c->X[0], c->U[0]);
     CK(cudaGetLastError());
     TRY(download_soa(c, c->X[0], nullptr, nullptr, nullptr, xx_reg, n, 6, c->Np, 0));
     TRY(download_soa(c, c->U[0], nullptr, nullptr, nullptr, uu_reg, n, 2, c->Np, 0));

@@ -42,6 +42,7 @@ struct Model {
     double cdk, clk;  // cda*k, cla*k
     double b41;       // dt/J             (:324)
     double gm;        // g*m              (:318, :321)
+    double rJ;        // RN(1/J): u/J is formed as a correctly rounded division from it (div_const)
 };
 
 inline Model make_model(const double* p)
@@ -56,6 +57,7 @@ inline Model make_model(const double* p)
     M.clk = M.cla * M.k;
     M.b41 = M.dt / M.J;
     M.gm = M.g * M.m;
+    M.rJ = 1.0 / M.J;
     return M;
 }
 
@@ -68,17 +70,83 @@ struct Weights {
 
 ACOC_HD double fma_(double a, double b, double c) { return fma(a, b, c); }
 
+// ---- sin/cos -------------------------------------------------------------------------------------------
+// Own implementation instead of CUDA's sincos(): same algorithm class (3-term Cody-Waite reduction by pi/2 with
+// FMAs, degree-13/12 minimax polynomials (the classic fdlibm k_sin/k_cos coefficient sets), quadrant fix-up), but
+// the coefficients are read as constant-bank operands, which removes ~100 UMOV/IMAD.MOV/spill instructions per
+// time step that nvcc emits to materialise the library routine's 64-bit immediates.  Error <= 1 ulp against glibc
+// on |x| < 1e5 (2 ulp in isolated cases); the float32 rounding of the next state absorbs it (tests: rollouts stay
+// bit-identical to the oracle).  The same code runs in the host replay, so replay and GPU agree bit for bit.
+#define ACOC_MATH_CONSTANTS                                                                                      \
+    {0x1.45f306dc9c883p-1, /* 0: 2/pi */                                                                          \
+     0x1.921fb54442d18p+0, 0x1.1a62633145c00p-54, 0x1.b839a252049c0p-104, /* 1-3: pi/2 in three parts */          \
+     -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04, /* 4-9: S1..S6 */      \
+     2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,                         \
+     4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05, /* 10-15: C1..C6 */     \
+     -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11}
+#if defined(__CUDACC__)
+__constant__ double c_math[16] = ACOC_MATH_CONSTANTS;
+#endif
+static const double h_math[16] = ACOC_MATH_CONSTANTS;
+#if defined(__CUDA_ARCH__)
+#define ACOC_K(i) c_math[i]
+#else
+#define ACOC_K(i) h_math[i]
+#endif
+
+// huge, Inf or NaN arguments: library routine, kept out of line so that its code (Payne-Hanek reduction, 64-bit
+// immediates) does not sit inside the time loops; never taken on a sane trajectory.  Returned by value so that the
+// caller's sin/cos stay in registers on the fast path.
+struct SinCos { double s, c; };
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+SinCos sincos_slow_(double x)
+{
+    SinCos r;
+#if defined(__CUDA_ARCH__)
+    sincos(x, &r.s, &r.c);
+#else
+    r.s = sin(x); r.c = cos(x);
+#endif
+    return r;
+}
+
 ACOC_HD void sincos_(double x, double& s, double& c)
 {
-#if defined(__CUDA_ARCH__)
-    sincos(x, &s, &c);
-#else
-    s = sin(x); c = cos(x);
-#endif
+    if (!(fabs(x) < 1.0e5)) { const SinCos r = sincos_slow_(x); s = r.s; c = r.c; return; }
+    const double jd = rint(x * ACOC_K(0));
+    const int j = (int)jd;
+    double r = fma_(-jd, ACOC_K(1), x);
+    r = fma_(-jd, ACOC_K(2), r);
+    r = fma_(-jd, ACOC_K(3), r);
+    const double z = r * r;
+    double ps = fma_(z, ACOC_K(9), ACOC_K(8));
+    ps = fma_(z, ps, ACOC_K(7)); ps = fma_(z, ps, ACOC_K(6)); ps = fma_(z, ps, ACOC_K(5)); ps = fma_(z, ps, ACOC_K(4));
+    const double sr = fma_(z * ps, r, r);
+    double pc = fma_(z, ACOC_K(15), ACOC_K(14));
+    pc = fma_(z, pc, ACOC_K(13)); pc = fma_(z, pc, ACOC_K(12)); pc = fma_(z, pc, ACOC_K(11)); pc = fma_(z, pc, ACOC_K(10));
+    const double cr = fma_(z, fma_(z, pc, -0.5), 1.0);
+    double a = (j & 1) ? cr : sr, b = (j & 1) ? sr : cr;
+    if (j & 2) a = -a;
+    if ((j + 1) & 2) b = -b;
+    s = a; c = b;
+}
+
+// a / d for a divisor whose correctly rounded reciprocal rd = RN(1/d) is known: q = RN(a*rd), r = a - q*d (exact, FMA),
+// RN(q + r*rd) is the correctly rounded quotient (Markstein) -- three FMA-pipe operations instead of a division routine.
+ACOC_HD double div_const(double a, double d, double rd)
+{
+    const double q = a * rd;
+    const double r = fma_(-q, d, a);
+    return fma_(r, rd, q);
 }
 
 // aircraft_simplified.py:300 -- the reference stores the next state in a float32 array.
-ACOC_HD double quant_(double v, bool q32) { return q32 ? (double)(float)v : v; }
+template <bool Q32>
+ACOC_HD double quant_(double v) { return Q32 ? (double)(float)v : v; }
 
 struct Trig { double sg, cg, sa, ca, alpha; };
 
@@ -92,7 +160,8 @@ ACOC_HD Trig make_trig(const double* x)
 }
 
 // One forward-Euler step, aircraft_simplified.py:303-310, in the reference's evaluation order.
-ACOC_HD void next_state(const Model& M, const double* x, const double* u, const Trig& t, bool q32, double* xn)
+template <bool Q32>
+ACOC_HD void next_state(const Model& M, const double* x, const double* u, const Trig& t, double* xn)
 {
     const double V = x[2];
     const double V2 = V * V, a2 = t.alpha * t.alpha;
@@ -100,12 +169,12 @@ ACOC_HD void next_state(const Model& M, const double* x, const double* u, const 
     const double D = hv * (M.cd0 + M.cda * a2);                    // :228
     const double L = hv * M.cla * t.alpha;                         // :253
     const double dtV = M.dt * V;
-    xn[0] = quant_(x[0] + dtV * t.cg, q32);
-    xn[1] = quant_(x[1] - dtV * t.sg, q32);
-    xn[2] = quant_(V + M.dt_m * (-D - M.mg * t.sg + u[0] * t.ca), q32);
-    xn[3] = quant_(x[3] + M.dt * x[4], q32);
-    xn[4] = quant_(x[4] + M.dt * (u[1] / M.J), q32);
-    xn[5] = quant_(x[5] + (M.dt / (M.m * V)) * (L - M.mg * t.cg + u[0] * t.sa), q32);
+    xn[0] = quant_<Q32>(x[0] + dtV * t.cg);
+    xn[1] = quant_<Q32>(x[1] - dtV * t.sg);
+    xn[2] = quant_<Q32>(V + M.dt_m * (-D - M.mg * t.sg + u[0] * t.ca));
+    xn[3] = quant_<Q32>(x[3] + M.dt * x[4]);
+    xn[4] = quant_<Q32>(x[4] + M.dt * div_const(u[1], M.J, M.rJ));
+    xn[5] = quant_<Q32>(x[5] + (M.dt / (M.m * V)) * (L - M.mg * t.cg + u[0] * t.sa));
 }
 
 // Non-constant entries of A = df/dx and B = df/du.  Constant ones: A00=A11=A33=A44=1, A34=dt, B41=dt/J.

@@ -136,7 +136,8 @@ int acoc_sync(acoc_ctx* ctx);
 int acoc_get_result(acoc_ctx* ctx, double* xx_star, double* uu_star);
 /* which: 0 = the newest iterate (last get_update), 1 = the one before it. */
 int acoc_get_iterate(acoc_ctx* ctx, int which, double* xx, double* uu);
-/* Descent direction of the last iteration: deltau (N,2,TT) (optcon.py:468). */
+/* Descent direction of the last iteration: deltau (N,2,TT) (optcon.py:468).  deltau and the gains are per-iteration
+ * scratch: they are meaningful for instances that were still active in that iteration. */
 int acoc_get_deltau(acoc_ctx* ctx, double* deltau);
 /* Gains of the last backward sweep: K (N,2,6,TT), sigma (N,2,TT) -- KK[:,1:,:] and KK[:,0,:] of optcon.py:468. */
 int acoc_get_gains(acoc_ctx* ctx, double* K, double* sigma);

@@ -15,6 +15,13 @@
 using namespace acoc;
 
 namespace {
+// dispatch on the runtime state-quantisation flag like LAUNCH_Q32 in acoc_api.cu
+template <bool WRITE, bool COST>
+double rollout_q(const Problem& P, const double* U, const double* DU, double s, double* Xn, double* Un, int i)
+{
+    return P.q32 ? rollout_instance<WRITE, COST, true>(P, U, DU, s, Xn, Un, i) : rollout_instance<WRITE, COST, false>(P, U, DU, s, Xn, Un, i);
+}
+
 struct Soa {
     int N, Np, TT;
     std::vector<double> X[3], U[3], DU, KSG, xref, uref, x0;
@@ -128,15 +135,15 @@ int emul_newton_batch(int N, int TT, const double* params, int state_f64, const 
             desc[i] = forward_lq_instance(P, X, U, b.KSG.data(), b.DU.data(), nullptr, i);
             bool cand0_in_place = false;
             if (lazy && armijo_maxiters > 1) {
-                Jc[i] = rollout_instance<true, true>(P, U, b.DU.data(), cs[0], Xn, Un, i);
+                Jc[i] = rollout_q<true, true>(P, U, b.DU.data(), cs[0], Xn, Un, i);
                 const bool need = Jc[i] > Jcur[i] + cc * cs[0] * desc[i];
-                if (need) for (int c = 1; c < armijo_maxiters; ++c) Jc[(size_t)c * Np + i] = rollout_instance<false, true>(P, U, b.DU.data(), cs[c], nullptr, nullptr, i);
+                if (need) for (int c = 1; c < armijo_maxiters; ++c) Jc[(size_t)c * Np + i] = rollout_q<false, true>(P, U, b.DU.data(), cs[c], nullptr, nullptr, i);
                 cand0_in_place = !need;
             } else {
-                for (int c = 0; c < armijo_maxiters; ++c) Jc[(size_t)c * Np + i] = rollout_instance<false, true>(P, U, b.DU.data(), cs[c], nullptr, nullptr, i);
+                for (int c = 0; c < armijo_maxiters; ++c) Jc[(size_t)c * Np + i] = rollout_q<false, true>(P, U, b.DU.data(), cs[c], nullptr, nullptr, i);
             }
             armijo_select_instance(O, S, cs.data(), kk, Np, i);
-            const double Jn = cand0_in_place ? Jc[i] : rollout_instance<true, true>(P, U, b.DU.data(), step[i], Xn, Un, i);
+            const double Jn = cand0_in_place ? Jc[i] : rollout_q<true, true>(P, U, b.DU.data(), step[i], Xn, Un, i);
             newton_finish_instance(O, S, Jn, kk, i);
         }
     }
@@ -187,7 +194,7 @@ void emul_rollout_batch(int N, int TT, const double* params, int state_f64, cons
     P.N = N; P.Np = Np; P.TT = TT; P.q32 = state_f64 ? 0 : 1; P.ref_shared = 0;
     P.xref = xr.data(); P.uref = ur.data(); P.x0 = x0s.data();
     for (int i = 0; i < N; ++i) {
-        J[i] = rollout_instance<true, true>(P, U.data(), DU.data(), s[i], Xn.data(), Un.data(), i);
+        J[i] = rollout_q<true, true>(P, U.data(), DU.data(), s[i], Xn.data(), Un.data(), i);
         from_soa(Xn.data(), xx_out + (size_t)i * 6 * TT, i, 6, TT, Np);
         from_soa(Un.data(), uu_out + (size_t)i * 2 * TT, i, 2, TT, Np);
     }
@@ -213,7 +220,8 @@ void emul_lqr_tracking(int N, int TT, const double* params, int state_f64, const
     P.M = M; P.N = N; P.Np = Np; P.TT = TT; P.q32 = state_f64 ? 0 : 1; P.ref_shared = 1;
     P.xref = xo.data(); P.uref = uo.data(); P.x0 = xs.data();
     for (int i = 0; i < N; ++i) {
-        track_instance(P, Kt.data(), xo.data(), uo.data(), xs.data(), Xn.data(), Un.data(), i);
+        if (P.q32) track_instance<true>(P, Kt.data(), xo.data(), uo.data(), xs.data(), Xn.data(), Un.data(), i);
+        else track_instance<false>(P, Kt.data(), xo.data(), uo.data(), xs.data(), Xn.data(), Un.data(), i);
         from_soa(Xn.data(), xx_reg + (size_t)i * 6 * TT, i, 6, TT, Np);
         from_soa(Un.data(), uu_reg + (size_t)i * 2 * TT, i, 2, TT, Np);
     }
@@ -228,7 +236,8 @@ void emul_init_guess(int N, int TT, const double* params, int state_f64, const d
     P.M = make_model(params); P.N = N; P.Np = Np; P.TT = TT; P.q32 = state_f64 ? 0 : 1; P.ref_shared = 0;
     P.xref = xr.data(); P.uref = nullptr; P.x0 = nullptr;
     for (int i = 0; i < N; ++i) {
-        init_guess_instance(P, kp, kt, nullptr, Xn.data(), Un.data(), i);
+        if (P.q32) init_guess_instance<true>(P, kp, kt, nullptr, Xn.data(), Un.data(), i);
+        else init_guess_instance<false>(P, kp, kt, nullptr, Xn.data(), Un.data(), i);
         from_soa(Xn.data(), xx + (size_t)i * 6 * TT, i, 6, TT, Np);
         from_soa(Un.data(), uu + (size_t)i * 2 * TT, i, 2, TT, Np);
     }

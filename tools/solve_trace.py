@@ -38,12 +38,17 @@ for rep in range(2):
                                   solve_device_ms=bn.timing()["total_ms"])
 # per-iteration trace
 bn.init_guess(dx0=dx0)
-trace = []
+bn.set_profiling(True)
+trace, phases = [], []
 active = n
 while active > 0 and len(trace) < 199:
     active = bn.iterate(1)
-    trace.append((round(bn.timing()["total_ms"], 3), active))
+    tm = bn.timing()
+    trace.append((round(tm["total_ms"], 3), active))
+    phases.append([round(tm["phases"][k], 2) for k in ("backward", "forward", "candidates", "update")])
 out["trace_ms_active"] = trace
+out["phases_bwd_fwd_cand_upd"] = phases
+out["n_armijo_mean_per_iter"] = [round(float(x), 2) for x in bn.history()["n_armijo"][:, :len(trace)].mean(axis=0)]
 st = bn.stats()
 out["iters_hist"] = np.bincount(st["iters"]).tolist()
 print(json.dumps(out))
