@@ -314,11 +314,10 @@ ACOC_HD double forward_lq_instance(const Problem& P, const double* X, const doub
 // ------------------------------------------------------------------------------------------------------
 // open-loop rollout of u' = u + s*du from x0: one Armijo candidate (COST) and/or get_update (WRITE)
 // ------------------------------------------------------------------------------------------------------
-template <bool WRITE, bool COST>
+template <bool WRITE, bool COST, bool Q32>
 ACOC_HD double rollout_instance(const Problem& P, const double* U, const double* DU, double s, double* Xn, double* Un, int i)
 {
     const int TT = P.TT, Np = P.Np;
-    const bool q32 = P.q32 != 0;
     double x[NS], xn[NS], u[NI], xr[NS], ur[NI], dx[NS], du[NI], J = 0.0;
 #pragma unroll
     for (int c = 0; c < NS; ++c) x[c] = P.x0[(size_t)c * Np + i];
@@ -340,7 +339,7 @@ ACOC_HD double rollout_instance(const Problem& P, const double* U, const double*
             J += stage_cost(P.W, dx, du);
         }
         const Trig tg = make_trig(x);
-        next_state(P.M, x, u, tg, q32, xn);
+        next_state<Q32>(P.M, x, u, tg, xn);
 #pragma unroll
         for (int c = 0; c < NS; ++c) x[c] = xn[c];
     }
@@ -428,11 +427,11 @@ ACOC_HD void newton_finish_instance(const NewtonOpts& O, const NewtonState& S, d
 // closed-loop tracking rollout, lqr_tracking.py:279-281: u = u_opt + K (x - x_opt) with shared K, nominal
 // ------------------------------------------------------------------------------------------------------
 // Kt: [TT][12] (row-major 2x6), xopt [TT][6], uopt [TT][2] shared by all instances; x_start [6][Np].
+template <bool Q32>
 ACOC_HD void track_instance(const Problem& P, const double* Kt, const double* xopt, const double* uopt,
                             const double* xstart, double* Xn, double* Un, int i)
 {
     const int TT = P.TT, Np = P.Np;
-    const bool q32 = P.q32 != 0;
     double x[NS], xn[NS], u[NI];
 #pragma unroll
     for (int c = 0; c < NS; ++c) x[c] = xstart[(size_t)c * Np + i];
@@ -451,7 +450,7 @@ ACOC_HD void track_instance(const Problem& P, const double* Kt, const double* xo
 #pragma unroll
         for (int c = 0; c < NI; ++c) Un[at(t, NI, c, Np, i)] = u[c];
         const Trig tg = make_trig(x);
-        next_state(P.M, x, u, tg, q32, xn);
+        next_state<Q32>(P.M, x, u, tg, xn);
 #pragma unroll
         for (int c = 0; c < NS; ++c) x[c] = xn[c];
     }
@@ -465,10 +464,10 @@ ACOC_HD void track_instance(const Problem& P, const double* Kt, const double* xo
 // initial guess, aircraft_simplified.py:126-148 (float64 arithmetic; see DESIGN.md "initial guess")
 // ------------------------------------------------------------------------------------------------------
 // dx0 (optional, [6][Np]): start from xx_ref[:,0] + dx0 instead (perturbed-initial-state batches, config 5)
+template <bool Q32>
 ACOC_HD void init_guess_instance(const Problem& P, double kp, double kt, const double* dx0, double* Xn, double* Un, int i)
 {
     const int TT = P.TT, Np = P.Np;
-    const bool q32 = P.q32 != 0;
     double x[NS], xn[NS], u[NI], xr[NS];
     load_xref(P, 0, i, x);  // x_temp = xx_ref[:,0]  (:139)
     if (dx0) {
@@ -484,7 +483,7 @@ ACOC_HD void init_guess_instance(const Problem& P, double kp, double kt, const d
 #pragma unroll
         for (int c = 0; c < NI; ++c) Un[at(t, NI, c, Np, i)] = u[c];
         const Trig tg = make_trig(x);
-        next_state(P.M, x, u, tg, q32, xn);
+        next_state<Q32>(P.M, x, u, tg, xn);
 #pragma unroll
         for (int c = 0; c < NS; ++c) x[c] = xn[c];
     }
@@ -504,7 +503,7 @@ ACOC_HD void step_sample(const Model& M, bool q32, const double* x, const double
                          double* xxp, double* A, double* B, double* fxx, double* fux)
 {
     const Trig tg = make_trig(x);
-    if (xxp) next_state(M, x, u, tg, q32, xxp);
+    if (xxp) { if (q32) next_state<true>(M, x, u, tg, xxp); else next_state<false>(M, x, u, tg, xxp); }
     const Lin l = linearize(M, x, u, tg);
     if (A) {
         for (int e = 0; e < 36; ++e) A[e] = 0.0;
