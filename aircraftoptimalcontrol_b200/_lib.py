@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libacoc.so")
+LIB_PATH = os.environ.get("ACOC_LIB", os.path.join(_HERE, "libacoc.so"))  # ACOC_LIB: tuning experiments only
 _lib = None
 
 DEFAULT_PARAMS = (0.1716, 2.395, 3.256, 12.0, 9.81, 0.61, 1.2, 0.24, 1e-3)  # aircraft_simplified.py:108-118
