@@ -285,8 +285,17 @@ def main():
         d = tbl[dom]
         # HBM is the binding resource: the bytes are irreducible, while the kernels execute far fewer flops than the dense
         # accounting of SURVEY.md 8(d) (sparsity of A, B and symmetry of P), so the FP64 figure is reported beside it.
+        traffic = None
+        try:  # DRAM bytes per launch of the dominant kernel from the committed ncu capture, scaled to this instance count
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            traffic = tj.get("k_" + dom)
+            if traffic is not None:
+                traffic = traffic * n / tj["instances"]
+        except Exception:
+            pass
         roofline = {"kernel": "k_" + dom, "bound": "hbm", "achieved": d["hbm_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": d["hbm_frac"], "traffic": None, "peak_source": peak_src,
+                    "frac": d["hbm_frac"], "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu --set full, per launch)",
+                    "algorithmic_bytes_per_launch": tot_bytes[dom] / K, "peak_source": peak_src,
                     "fp64": {"achieved_algorithmic_tflops": d["fp64_tflops"], "peak_tflops": fp64_peak, "frac_algorithmic": d["fp64_frac"],
                              "peak_source": "DFMA microbenchmark run in this process (acoc_measure_fp64_peak)",
                              "note": "algorithmic = dense ns=6/ni=2 flop count of SURVEY.md 8(d); executed flops are lower (structure-exploiting sweep)"},
