@@ -16,6 +16,7 @@ DEFAULT_PARAMS = (0.1716, 2.395, 3.256, 12.0, 9.81, 0.61, 1.2, 0.24, 1e-3)  # ai
 STATE_F64 = 1
 REFS_SHARED = 2
 ARMIJO_LAZY = 4
+SOLVE_IN_PLACE = 8
 
 INST_ACTIVE, INST_CONVERGED, INST_MAXITER, INST_NONFINITE = 0, 1, 2, 3
 

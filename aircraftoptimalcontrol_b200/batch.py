@@ -20,9 +20,11 @@ class BatchedNewton:
     state: "f32" reproduces aircraft_simplified.py:300 (next state rounded to float32), "f64" keeps float64.
     armijo: "speculative" evaluates all candidates concurrently, "lazy" evaluates candidate 0 for everyone and
     the rest only where it failed; both return exactly the step the reference's sequential search returns.
+    generations: let solve() gather the still-iterating instances into smaller internal batches as the others finish
+    (same results, faster tail).
     """
 
-    def __init__(self, n_instances, TT=1000, device=0, state="f32", refs_shared=False, armijo="speculative", params=None,
+    def __init__(self, n_instances, TT=1000, device=0, state="f32", refs_shared=False, armijo="speculative", params=None, generations=True,
                  max_iters=200, stepsize_0=1.0, cc=0.5, beta=0.7, armijo_maxiters=10, term_cond=-1e-6, exact_after=8):
         if state not in ("f32", "f64"):
             raise ValueError("state must be 'f32' or 'f64'")
@@ -30,7 +32,8 @@ class BatchedNewton:
             raise ValueError("armijo must be 'speculative' or 'lazy'")
         self.N, self.TT, self.device = int(n_instances), int(TT), int(device)
         self.refs_shared = bool(refs_shared)
-        flags = (L.STATE_F64 if state == "f64" else 0) | (L.REFS_SHARED if refs_shared else 0) | (L.ARMIJO_LAZY if armijo == "lazy" else 0)
+        flags = ((L.STATE_F64 if state == "f64" else 0) | (L.REFS_SHARED if refs_shared else 0) | (L.ARMIJO_LAZY if armijo == "lazy" else 0)
+                 | (0 if generations else L.SOLVE_IN_PLACE))
         self._h = C.c_void_p(None)
         L.check(L.lib().acoc_ctx_create(self.device, self.N, self.TT, flags, C.addressof(self._h)))
         self.opts = L.NewtonOptions(int(max_iters), int(armijo_maxiters), int(exact_after), 0, float(stepsize_0), float(cc), float(beta),

@@ -350,6 +350,40 @@ __global__ void k_result_slot_default(const int* __restrict__ status, int* __res
     if (i < N) slot_out[i] = status[i] == ST_ACTIVE ? newest : result_slot[i];
 }
 
+// ---- survivor generations (acoc_newton_solve) ----------------------------------------------------------
+// When at most half of a batch is still iterating, the survivors are gathered into a smaller child context so that
+// every lane of every warp does useful work again (the instances are independent; the parent keeps the finished
+// ones untouched).  origin[j] = index in the parent of child instance j.
+constexpr int ST_MOVED = 5;  // the instance continues in a child generation
+
+// dst[row][j] = src[row][origin[j]]   (coalesced writes, scattered reads)
+template <typename T>
+__global__ void k_gather_rows(const T* __restrict__ src, int src_stride, T* __restrict__ dst, int dst_stride, const int* __restrict__ origin,
+                              int n, int rows)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int o = origin[j];
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) dst[(size_t)r * dst_stride + j] = src[(size_t)r * src_stride + o];
+}
+
+// dst[row][origin[j]] = src[row][j]   (fold a finished child generation back into its parent)
+template <typename T>
+__global__ void k_scatter_rows(const T* __restrict__ src, int src_stride, T* __restrict__ dst, int dst_stride, const int* __restrict__ origin,
+                               int n, int rows)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int o = origin[j];
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) dst[(size_t)r * dst_stride + o] = src[(size_t)r * src_stride + j];
+}
+
+__global__ void k_mark_moved(int* __restrict__ status, const int* __restrict__ origin, int n)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) status[origin[j]] = ST_MOVED;
+}
+
 // ---- microbenchmarks for the roofline denominators ----------------------------------------------------
 __global__ void k_fp64_peak(double* out, int iters, double seed)
 {
@@ -395,6 +429,12 @@ struct acoc_ctx {
     double total_ms = 0, phase_ms[6] = {0, 0, 0, 0, 0, 0};
     long long launches = 0;
     bool weights_sym = true;
+    // survivor generations (see acoc_newton_solve)
+    acoc_ctx* child = nullptr;  // reusable smaller context (capacity N/2) for the instances that are still iterating
+    int* origin = nullptr;      // [capacity] index in the PARENT of each instance of this context (child contexts only)
+    int cap = 0;                // instance capacity (N may be smaller in a child)
+    int spawn_kk = 0;           // iteration at which this child took over its instances
+    double gen_ms = 0;          // device time spent moving instances between generations in the last solve
 };
 
 template <typename T>
@@ -658,6 +698,7 @@ int acoc_ctx_create(int device, int n_instances, int TT, unsigned flags, acoc_ct
     TRY(use_device(device));
     acoc_ctx* c = new acoc_ctx();
     c->device = device; c->N = n_instances; c->Np = (n_instances + 31) / 32 * 32; c->TT = TT; c->flags = flags;
+    c->cap = n_instances;
     memset(&c->P, 0, sizeof(c->P)); memset(&c->S, 0, sizeof(c->S));
     default_opts(&c->O);
     auto bail = [&](int rc) { acoc_ctx_destroy(c); return rc; };
@@ -680,6 +721,7 @@ int acoc_ctx_create(int device, int n_instances, int TT, unsigned flags, acoc_ct
     if (!rc) rc = dalloc(c, &c->S.step, Np);
     if (!rc) rc = dalloc(c, &c->need, Np);
     if (!rc) rc = dalloc(c, &c->slot_tmp, Np);
+    if (!rc) rc = dalloc(c, &c->origin, Np);
     if (!rc) rc = dalloc(c, &c->counters, 4);
     if (!rc) rc = dalloc(c, &c->act_groups, Np);
     if (!rc) rc = dalloc(c, &c->need_groups, Np);
@@ -708,6 +750,7 @@ int acoc_ctx_create(int device, int n_instances, int TT, unsigned flags, acoc_ct
 int acoc_ctx_destroy(acoc_ctx* c)
 {
     if (!c) return 0;
+    if (c->child) acoc_ctx_destroy(c->child);
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (void* p : c->allocs) cudaFree(p);
@@ -964,20 +1007,152 @@ int acoc_newton_iterate(acoc_ctx* c, int n_iters, int* n_active_out)
     return 0;
 }
 
+// gather/scatter every per-instance row set between a parent and its child; to_child = true: parent -> child
+template <typename T>
+static int move_rows(acoc_ctx* par, acoc_ctx* ch, T* pbuf, T* cbuf, int rows, bool to_child)
+{
+    const int n = ch->N;
+    dim3 grid((n + 127) / 128, std::min(rows, 2048));
+    if (to_child) k_gather_rows<T><<<grid, 128, 0, par->stream>>>(pbuf, par->Np, cbuf, ch->Np, ch->origin, n, rows);
+    else k_scatter_rows<T><<<grid, 128, 0, par->stream>>>(cbuf, ch->Np, pbuf, par->Np, ch->origin, n, rows);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// Move the n_active still-iterating instances of `par` into its child generation.  Returns 1 if no child could be made.
+static int spawn_child(acoc_ctx* par, int n_active, acoc_ctx** out)
+{
+    *out = nullptr;
+    const int cap = par->N / 2;
+    if (n_active > cap) return 1;
+    if (!par->child) {
+        acoc_ctx* ch = nullptr;
+        if (acoc_ctx_create(par->device, cap, par->TT, par->flags, &ch) != 0) return 1;  // e.g. out of memory: keep iterating in place
+        par->child = ch;
+    }
+    acoc_ctx* ch = par->child;
+    if (ch->O.max_iters != par->O.max_iters || ch->O.armijo_maxiters != par->O.armijo_maxiters) {
+        acoc_newton_options o;
+        o.max_iters = par->O.max_iters; o.armijo_maxiters = par->O.armijo_maxiters; o.exact_after = par->O.exact_after; o.reserved = 0;
+        o.stepsize_0 = par->O.stepsize_0; o.cc = par->O.cc; o.beta = par->O.beta; o.term_cond = par->O.term_cond;
+        TRY(acoc_set_options(ch, &o));
+    }
+    ch->O = par->O;
+    ch->N = n_active;
+    ch->P.M = par->P.M; ch->P.W = par->P.W; ch->P.q32 = par->P.q32; ch->P.N = n_active;
+    ch->have_model = ch->have_weights = ch->have_refs = ch->have_init = true;
+    ch->profiling = par->profiling;
+    TRY(use_device(par->device));
+    // everything below is ordered on the PARENT's stream; the child's stream waits for it through the final sync
+    const int TT = par->TT;
+    k_build_list<<<1, 1024, 0, par->stream>>>(par->S.status, 0, par->N, 0, ch->origin, par->counters + 3);
+    CK(cudaGetLastError());
+    k_fill_int<<<(ch->Np + 255) / 256, 256, 0, par->stream>>>(ch->S.status, ch->Np, ST_ACTIVE, n_active, ST_PAD);
+    CK(cudaGetLastError());
+    for (int sl = 0; sl < 3; ++sl) {
+        if (sl == (par->kk + 1) % 3) continue;  // the "next" slot is overwritten by the child's first update anyway
+        TRY(move_rows(par, ch, par->X[sl], ch->X[sl], 6 * TT, true));
+        TRY(move_rows(par, ch, par->U[sl], ch->U[sl], 2 * TT, true));
+    }
+    if (par->flags & ACOC_REFS_SHARED) {
+        CK(cudaMemcpyAsync(ch->xref, par->xref, (size_t)TT * 6 * sizeof(double), cudaMemcpyDeviceToDevice, par->stream));
+        CK(cudaMemcpyAsync(ch->uref, par->uref, (size_t)TT * 2 * sizeof(double), cudaMemcpyDeviceToDevice, par->stream));
+    } else {
+        TRY(move_rows(par, ch, par->xref, ch->xref, 6 * TT, true));
+        TRY(move_rows(par, ch, par->uref, ch->uref, 2 * TT, true));
+    }
+    TRY(move_rows(par, ch, par->x0, ch->x0, 6, true));
+    TRY(move_rows(par, ch, par->S.Jcur, ch->S.Jcur, 1, true));
+    TRY(move_rows(par, ch, par->S.descent, ch->S.descent, 1, true));
+    TRY(move_rows(par, ch, par->S.step, ch->S.step, 1, true));
+    TRY(move_rows(par, ch, par->S.iters, ch->S.iters, 1, true));
+    TRY(move_rows(par, ch, par->S.n_reg, ch->S.n_reg, 1, true));
+    TRY(move_rows(par, ch, par->S.result_slot, ch->S.result_slot, 1, true));
+    k_mark_moved<<<(n_active + 255) / 256, 256, 0, par->stream>>>(par->S.status, ch->origin, n_active);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(par->stream));
+    ch->kk = par->kk;
+    ch->spawn_kk = par->kk;
+    *out = ch;
+    return 0;
+}
+
+// Fold a finished child generation back into its parent: afterwards the parent looks as if it had iterated everything itself.
+static int fold_child(acoc_ctx* par, acoc_ctx* ch)
+{
+    TRY(use_device(par->device));
+    CK(cudaStreamSynchronize(ch->stream));
+    const int TT = par->TT, mi = par->O.max_iters;
+    for (int sl = 0; sl < 3; ++sl) {
+        TRY(move_rows(par, ch, par->X[sl], ch->X[sl], 6 * TT, false));
+        TRY(move_rows(par, ch, par->U[sl], ch->U[sl], 2 * TT, false));
+    }
+    TRY(move_rows(par, ch, par->S.Jcur, ch->S.Jcur, 1, false));
+    TRY(move_rows(par, ch, par->S.descent, ch->S.descent, 1, false));
+    TRY(move_rows(par, ch, par->S.step, ch->S.step, 1, false));
+    TRY(move_rows(par, ch, par->S.iters, ch->S.iters, 1, false));
+    TRY(move_rows(par, ch, par->S.n_reg, ch->S.n_reg, 1, false));
+    TRY(move_rows(par, ch, par->S.result_slot, ch->S.result_slot, 1, false));
+    TRY(move_rows(par, ch, par->S.status, ch->S.status, 1, false));
+    const int r0 = ch->spawn_kk, nr = ch->kk - ch->spawn_kk;  // history rows written by the child
+    if (nr > 0) {
+        TRY(move_rows(par, ch, par->S.hist_J + (size_t)r0 * par->Np, ch->S.hist_J + (size_t)r0 * ch->Np, nr, false));
+        TRY(move_rows(par, ch, par->S.hist_descent + (size_t)r0 * par->Np, ch->S.hist_descent + (size_t)r0 * ch->Np, nr, false));
+        TRY(move_rows(par, ch, par->S.hist_step + (size_t)r0 * par->Np, ch->S.hist_step + (size_t)r0 * ch->Np, nr, false));
+        TRY(move_rows(par, ch, par->S.hist_ncand + (size_t)r0 * par->Np, ch->S.hist_ncand + (size_t)r0 * ch->Np, nr, false));
+    }
+    (void)mi;
+    CK(cudaStreamSynchronize(par->stream));
+    par->kk = ch->kk;
+    return 0;
+}
+
+#ifndef ACOC_GEN_MIN
+#define ACOC_GEN_MIN 4096  // smallest batch that still spawns a survivor generation
+#endif
+
 int acoc_newton_solve(acoc_ctx* c, long long* total_iters)
 {
     TRY(ready(c));
     int active = 1;
-    double total_ms = 0, phase[6] = {0, 0, 0, 0, 0, 0};
+    double total_ms = 0, phase[6] = {0, 0, 0, 0, 0, 0}, gen_ms = 0;
     long long launches = 0;
-    while (active > 0 && c->kk < c->O.max_iters - 1) {
+    std::vector<acoc_ctx*> chain{c};
+    acoc_ctx* cur = c;
+    while (active > 0 && cur->kk < cur->O.max_iters - 1) {
         // check for completion every 4 iterations: one tiny D2H per check keeps the stream busy in between
-        TRY(acoc_newton_iterate(c, 4, &active));
-        total_ms += c->total_ms; launches += c->launches;
-        for (int p = 0; p < 6; ++p) phase[p] += c->phase_ms[p];
+        TRY(acoc_newton_iterate(cur, 4, &active));
+        total_ms += cur->total_ms; launches += cur->launches;
+        for (int p = 0; p < 6; ++p) phase[p] += cur->phase_ms[p];
+        if (active > 0 && !(c->flags & ACOC_SOLVE_IN_PLACE) && cur->N >= ACOC_GEN_MIN && 2 * active <= cur->N && cur->kk < cur->O.max_iters - 1) {
+            acoc_ctx* ch = nullptr;
+            CK(cudaEventRecord(cur->ev[6], cur->stream));
+            int rc = spawn_child(cur, active, &ch);
+            if (rc < 0) return rc;
+            if (rc == 0 && ch) {
+                CK(cudaEventRecord(cur->ev[7], cur->stream));
+                CK(cudaEventSynchronize(cur->ev[7]));
+                float ms = 0;
+                CK(cudaEventElapsedTime(&ms, cur->ev[6], cur->ev[7]));
+                gen_ms += ms;
+                chain.push_back(ch);
+                cur = ch;
+            }
+        }
     }
-    c->total_ms = total_ms; c->launches = launches;
+    for (size_t k = chain.size() - 1; k >= 1; --k) {
+        acoc_ctx* par = chain[k - 1];
+        CK(cudaEventRecord(par->ev[6], par->stream));
+        TRY(fold_child(par, chain[k]));
+        CK(cudaEventRecord(par->ev[7], par->stream));
+        CK(cudaEventSynchronize(par->ev[7]));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, par->ev[6], par->ev[7]));
+        gen_ms += ms;
+    }
+    c->total_ms = total_ms + gen_ms; c->launches = launches; c->gen_ms = gen_ms;
     for (int p = 0; p < 6; ++p) c->phase_ms[p] = phase[p];
+    c->phase_ms[4] = gen_ms;  // reported as the "select" slot of acoc_get_timing: time spent moving instances between generations
     if (total_iters) TRY(count_active(c, nullptr, total_iters));
     return 0;
 }

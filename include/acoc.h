@@ -42,6 +42,7 @@ typedef enum acoc_status {
 #define ACOC_REFS_SHARED 2u      /* one reference trajectory shared by all instances */
 #define ACOC_ARMIJO_SPECULATIVE 0u /* evaluate all armijo_maxiters candidates concurrently (default) */
 #define ACOC_ARMIJO_LAZY 4u      /* candidate 0 for everyone, the remaining candidates only for instances that failed it */
+#define ACOC_SOLVE_IN_PLACE 8u   /* acoc_newton_solve: never gather the still-iterating instances into a smaller survivor generation */
 
 /* per-instance status written by the Newton driver */
 #define ACOC_INST_ACTIVE 0
@@ -127,7 +128,10 @@ int acoc_init_guess(acoc_ctx* ctx, double kp, double kt, const double* dx0);
 /* Run up to n_iters more Newton iterations (loop bodies of optcon.py:415-501) on every instance that is
  * still active.  *n_active_out (may be NULL) = instances still active afterwards (forces a device sync). */
 int acoc_newton_iterate(acoc_ctx* ctx, int n_iters, int* n_active_out);
-/* Iterate until no instance is active.  *total_iters = sum over instances of loop bodies executed. */
+/* Iterate until no instance is active.  *total_iters = sum over instances of loop bodies executed.
+ * Whenever at most half of a batch (of >= 4096 instances) is still iterating, the survivors are gathered into a smaller
+ * internal context so that every warp lane does useful work again; they are folded back before the call returns, so
+ * results, histories and statistics are exactly those of iterating in place (ACOC_SOLVE_IN_PLACE disables this). */
 int acoc_newton_solve(acoc_ctx* ctx, long long* total_iters);
 /* Block until all work queued on the context's stream has finished. */
 int acoc_sync(acoc_ctx* ctx);

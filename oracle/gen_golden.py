@@ -16,7 +16,7 @@ Fixtures
                         sub-problem (KK, deltax, deltau) captured at selected iterations
   lq_forced_reg.npz     ltv_LQR on a synthetic indefinite problem that takes the +0.5*I branch
   lqr_tracking.npz      lqr_tracking.py on Data/xx_star.npy with the shipped delta and random deltas
-  batch_cfg4.npz / batch_cfg5.npz   sampled instances of the batched configs (BASELINE.json configs 4, 5)
+  newton_quirks.npz     optimize()'s return-slot corner cases: max_iters exhausted, and convergence at kk = 0 (zeros)
 """
 from __future__ import annotations
 
@@ -255,12 +255,30 @@ def gen_lqr_tracking():
           xx_reg=np.array(xs), uu_reg=np.array(us), KK=KK)
 
 
+def gen_newton_quirks():
+    """Return-value corner cases of NewtonMethod.optimize (optcon.py:499-505) from the live reference:
+    (a) max_iters = 4 never reaches the tolerance -> the result is the last iterate written (slot max_iters-1);
+    (b) starting from an already converged trajectory stops at kk = 0 -> slot -1 of the history array, i.e. all zeros."""
+    s = script_setup("step")
+    mods = pyref.load(True)
+    a = pyref.run_newton(mods, s["xx_ref"], s["uu_ref"], s["xx_init"], s["uu_init"], s["QQt"], s["RRt"], s["QQT"], max_iters=4)
+    full = np.load(os.path.join(GOLD, "newton_step_f64.npz"))
+    b = pyref.run_newton(mods, s["xx_ref"], s["uu_ref"], full["xx_last"], full["uu_last"], s["QQt"], s["RRt"], s["QQT"])
+    assert a["iters"] == 3 and b["iters"] == 1 and not b["xx_star"].any()
+    _save("newton_quirks.npz", xx_ref=s["xx_ref"], uu_ref=s["uu_ref"], Q=s["QQt"], R=s["RRt"], QT=s["QQT"],
+          a_xx_init=s["xx_init"], a_uu_init=s["uu_init"], a_JJ=a["JJ"], a_descent=a["descent"], a_stepsize=a["stepsize"], a_iters=a["iters"],
+          a_xx_star=a["xx_star"], a_uu_star=a["uu_star"],
+          b_xx_init=full["xx_last"], b_uu_init=full["uu_last"], b_JJ=b["JJ"], b_descent=b["descent"], b_stepsize=b["stepsize"], b_iters=b["iters"],
+          b_xx_star=b["xx_star"], b_uu_star=b["uu_star"])
+
+
 GENERATORS = {
     "step_kat": lambda a: gen_step_kat(),
     "cost_kat": lambda a: gen_cost_kat(),
     "lq_forced_reg": lambda a: gen_lq_forced_reg(),
     "lqr_tracking": lambda a: gen_lqr_tracking(),
     "newton": lambda a: gen_newton(a.jobs),
+    "newton_quirks": lambda a: gen_newton_quirks(),
 }
 
 

@@ -255,3 +255,74 @@ def test_pipelined_chunks_equal_single_batch(gpu):
         xp, up, sp = pn.solve(xr, ur)
     assert np.array_equal(xs, xp) and np.array_equal(us, up)
     assert np.array_equal(st["iters"], sp["iters"]) and np.array_equal(st["status"], sp["status"]) and np.array_equal(st["J"], sp["J"])
+
+
+def test_return_slot_quirks(gpu):
+    """optimize()'s return slot (optcon.py:499-505) in one mixed batch: instance 0 exhausts max_iters = 4 (-> last iterate),
+    instance 1 starts converged and stops at kk = 0 (-> all zeros)."""
+    d = golden("newton_quirks.npz")
+    xi = np.stack([d["a_xx_init"], d["b_xx_init"]])
+    ui = np.stack([d["a_uu_init"], d["b_uu_init"]])
+    with gpu.BatchedNewton(2, TT=1000, state="f64", refs_shared=True, max_iters=4) as bn:
+        bn.set_weights(d["Q"], d["R"], d["QT"])
+        bn.set_refs(d["xx_ref"], d["uu_ref"])
+        bn.set_init(xi, ui)
+        total = bn.solve()
+        xs, us = bn.result()
+        st, h = bn.stats(), bn.history()
+    assert total == 4 and list(st["iters"]) == [3, 1] and list(st["status"]) == [2, 1]
+    assert np.array_equal(h["stepsize"][0, :3], d["a_stepsize"]) and np.array_equal(h["stepsize"][1, :1], d["b_stepsize"])
+    assert relerr(d["a_xx_star"], xs[0]) < 1e-9 and relerr(d["a_uu_star"], us[0]) < 1e-9
+    assert not xs[1].any() and not us[1].any()
+
+
+def test_minimal_horizon_and_options(gpu, oracle):
+    """TT = 3 (two steps), non-default Armijo parameters and exact Hessian from the first iteration, vs the oracle."""
+    rng = np.random.default_rng(4)
+    n, TT = 5, 3
+    from aircraftoptimalcontrol_b200 import refgen
+    xr, ur = refgen.step_problem(rng.uniform(14, 18, n), rng.uniform(1.5, 3.5, n), tf=0.003, TT=TT)
+    Q, R, QT = refgen.weights("step")
+    kw = dict(max_iters=6, stepsize_0=0.8, cc=0.3, beta=0.5, armijo_maxiters=4, exact_after=-1)
+    with gpu.BatchedNewton(n, TT=TT, **kw) as bn:
+        bn.set_weights(Q, R, QT)
+        bn.set_refs(xr, ur)
+        bn.init_guess()
+        xi, ui = bn.iterate_at(0)
+        bn.solve()
+        xs, us = bn.result()
+        h, st = bn.history(), bn.stats()
+    o = oracle.newton_batch(xr, ur, xi, ui, Q, R, QT, **kw)
+    assert np.array_equal(st["iters"], o["iters"])
+    for i in range(n):
+        k = o["iters"][i]
+        assert np.array_equal(h["stepsize"][i, :k], o["stepsize"][i, :k]) and np.array_equal(h["n_armijo"][i, :k], o["n_armijo"][i, :k])
+    assert relerr(o["xx_star"], xs) < 1e-9 and relerr(o["uu_star"], us) < 1e-9
+
+
+def test_survivor_generations_equal_in_place(gpu, oracle):
+    """solve() gathers the still-iterating instances into smaller internal batches once half of a batch has finished
+    (and folds them back); results, histories and statistics must be bit-identical to iterating in place, and match
+    the oracle on a sample."""
+    n, TT = 8192, 200
+    xr, ur, Q, R, QT = _random_batch(n, TT, 99, 0.2)
+    out = []
+    for gen in (True, False):
+        with gpu.BatchedNewton(n, TT=TT, armijo="lazy", generations=gen) as bn:
+            bn.set_weights(Q, R, QT)
+            bn.set_refs(xr, ur)
+            bn.init_guess()
+            xi, ui = bn.iterate_at(0)
+            total = bn.solve()
+            out.append((total, bn.result(), bn.iterate_at(0), bn.history(), bn.stats()))
+    (t0, (x0, u0), (xl0, ul0), h0, s0), (t1, (x1, u1), (xl1, ul1), h1, s1) = out
+    assert t0 == t1 and np.array_equal(s0["iters"], s1["iters"]) and np.array_equal(s0["status"], s1["status"])
+    assert len(np.unique(s0["iters"])) > 3  # instances finish at different iterations, so generations were spawned
+    assert np.array_equal(x0, x1) and np.array_equal(u0, u1) and np.array_equal(xl0, xl1) and np.array_equal(ul0, ul1)
+    for k in ("JJ", "descent", "stepsize", "n_armijo"):
+        assert np.array_equal(h0[k], h1[k]), k
+    assert np.array_equal(s0["J"], s1["J"]) and np.array_equal(s0["n_reg"], s1["n_reg"])
+    idx = np.arange(0, n, 64)
+    o = oracle.newton_batch(xr[idx], ur[idx], xi[idx], ui[idx], Q, R, QT)
+    assert np.array_equal(s0["iters"][idx], o["iters"])
+    assert relerr(o["xx_star"], x0[idx]) < 1e-9 and relerr(o["uu_star"], u0[idx]) < 1e-9

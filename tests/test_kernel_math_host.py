@@ -128,3 +128,12 @@ def test_dense_weights_path(emul, oracle):
     assert np.array_equal(h["stepsize"][0, :4], o["stepsize"])
     assert np.max(np.abs(h["JJ"][0, :4] - o["JJ"]) / np.abs(o["JJ"])) < 1e-12
     assert relerr(o["xx_last"], h["xx_last"][0]) < 1e-9 and relerr(o["uu_last"], h["uu_last"][0]) < 1e-9
+
+
+def test_return_slot_quirks(emul):
+    d = golden("newton_quirks.npz")
+    a = emul.newton_batch(d["xx_ref"], d["uu_ref"], d["a_xx_init"][None], d["a_uu_init"][None], d["Q"], d["R"], d["QT"], state_f64=True, max_iters=4)
+    assert a["iters"][0] == 3 and a["status"][0] == 2 and np.array_equal(a["stepsize"][0, :3], d["a_stepsize"])
+    assert relerr(d["a_xx_star"], a["xx_star"][0]) < 1e-9 and relerr(d["a_uu_star"], a["uu_star"][0]) < 1e-9
+    b = emul.newton_batch(d["xx_ref"], d["uu_ref"], d["b_xx_init"][None], d["b_uu_init"][None], d["Q"], d["R"], d["QT"], state_f64=True)
+    assert b["iters"][0] == 1 and b["status"][0] == 1 and not b["xx_star"][0].any() and not b["uu_star"][0].any()

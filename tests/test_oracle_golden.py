@@ -122,3 +122,14 @@ def test_armijo_exhaustion_returns_untested_step(oracle):
     for _ in range(10):
         sref = 0.7 * sref
     assert not accepted and ntried == 10 and s == sref and np.all(costs > JP)
+
+
+def test_newton_return_slot_quirks(oracle):
+    """optcon.py:499-505: (a) max_iters exhausted -> last iterate written; (b) converged at kk = 0 -> the all-zero slot -1."""
+    d = golden("newton_quirks.npz")
+    a = oracle.newton(d["xx_ref"], d["uu_ref"], d["a_xx_init"], d["a_uu_init"], d["Q"], d["R"], d["QT"], quant_f32=False, max_iters=4)
+    assert a["iters"] == int(d["a_iters"]) == 3 and np.array_equal(a["stepsize"], d["a_stepsize"])
+    assert relerr(d["a_xx_star"], a["xx_star"]) < 1e-9 and relerr(d["a_uu_star"], a["uu_star"]) < 1e-9
+    b = oracle.newton(d["xx_ref"], d["uu_ref"], d["b_xx_init"], d["b_uu_init"], d["Q"], d["R"], d["QT"], quant_f32=False)
+    assert b["iters"] == int(d["b_iters"]) == 1 and np.array_equal(b["stepsize"], d["b_stepsize"])
+    assert not b["xx_star"].any() and not b["uu_star"].any() and not d["b_xx_star"].any()
