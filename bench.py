@@ -177,7 +177,7 @@ def main():
     ap.add_argument("--armijo", default="lazy", choices=["lazy", "speculative"])
     ap.add_argument("--state", default="f32", choices=["f32", "f64"])
     ap.add_argument("--cpu-sample", type=int, default=2048)
-    ap.add_argument("--chunks", type=int, default=4, help="sub-batches of the pipelined end-to-end solve")
+    ap.add_argument("--chunks", type=int, default=8, help="sub-batches of the pipelined end-to-end solve")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
