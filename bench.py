@@ -222,23 +222,25 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()  # keeps sampling through the timed region, the per-phase re-run and the end-to-end solve
+    its_before = int(bn.stats()["iters"].astype(np.int64).sum())
     barrier()
-    active_after = bn.iterate(K, count_active=False)  # K Newton iterations, timed by CUDA events inside the library
+    bn.iterate(K, count_active=False)  # K Newton iterations, timed by CUDA events inside the library
     bn.sync()
     barrier()
     tm = bn.timing()
     ms = tm["total_ms"]
     launches = tm["launches"]
+    st = bn.stats()
+    its_done = int(st["iters"].astype(np.int64).sum()) - its_before  # instance-iterations actually executed in the timed region
     if dist is not None:
         import torch
-        t = torch.tensor([ms, float(launches)], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, float(launches), float(its_done)], dtype=torch.float64, device="cuda")
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        ms, launches = float(tmax[0]), int(t[1])
-    st = bn.stats()
+        ms, launches, its_done = float(tmax[0]), int(t[1]), int(t[2])
     n_active = int((st["status"] == 0).sum())
-    value = n_total * K / (ms * 1e-3)
+    value = its_done / (ms * 1e-3)   # = instances x K while every instance is still iterating (the default W, K)
 
     # ---- roofline of the dominant kernel (rank 0): re-run iterations with per-phase events --------------------
     roofline = fp64 = phases = None
@@ -304,6 +306,14 @@ def main():
                                     "note": "SURVEY.md 8(d) per-unit figures x (TT-1) x instances per launch"}}
         fp64 = {"peak_tflops_measured": fp64_peak}
 
+    # ---- whole solve, device-resident (every instance to the reference's criterion; includes the float32-noise phase
+    #      with its full Armijo searches and the thinning tail) ------------------------------------------------------
+    bn.init_guess(dx0=dx0)
+    tot_solve = bn.solve()
+    tsolve = bn.timing()
+    whole = {"value": tot_solve / (tsolve["total_ms"] * 1e-3), "unit": UNIT, "device_ms": tsolve["total_ms"], "total_newton_iterations": int(tot_solve),
+             "lockstep_iterations": int(bn.stats()["iters"].max()), "gpu_launches": tsolve["launches"], "scope": "this rank"}
+
     # ---- end to end through the public API, host buffers, full solve -----------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -354,7 +364,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / max(K, 1),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config_dict(args, n, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "active_after_timed_region": n_active, "roofline": roofline, "fp64": fp64, "phase_ms": phases, "cpu_baseline": cpu,
+                "active_after_timed_region": n_active, "instance_iterations_timed": its_done, "whole_solve": whole, "roofline": roofline, "fp64": fp64, "phase_ms": phases, "cpu_baseline": cpu,
                 "device": pkg.device_info(local)["name"], "device_bytes": bn.device_bytes}
         emit(line)
     bn.close()
