@@ -495,6 +495,12 @@ static int reset_state(acoc_ctx* c)
     CK(cudaMemsetAsync(c->S.Jcur, 0, Np * sizeof(double), c->stream));
     CK(cudaMemsetAsync(c->S.descent, 0, Np * sizeof(double), c->stream));
     CK(cudaMemsetAsync(c->S.step, 0, Np * sizeof(double), c->stream));
+    // histories start from zero so that rows beyond an instance's own iteration count never show an earlier solve
+    const size_t hrows = (size_t)c->O.max_iters * Np;
+    CK(cudaMemsetAsync(c->S.hist_J, 0, hrows * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->S.hist_descent, 0, hrows * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->S.hist_step, 0, hrows * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->S.hist_ncand, 0, hrows * sizeof(int), c->stream));
     CK(cudaGetLastError());
     c->kk = 0;
     return 0;
@@ -1043,6 +1049,8 @@ static int spawn_child(acoc_ctx* par, int n_active, acoc_ctx** out)
     ch->have_model = ch->have_weights = ch->have_refs = ch->have_init = true;
     ch->profiling = par->profiling;
     TRY(use_device(par->device));
+    TRY(reset_state(ch));
+    CK(cudaStreamSynchronize(ch->stream));
     // everything below is ordered on the PARENT's stream; the child's stream waits for it through the final sync
     const int TT = par->TT;
     k_build_list<<<1, 1024, 0, par->stream>>>(par->S.status, 0, par->N, 0, ch->origin, par->counters + 3);

@@ -126,7 +126,8 @@ int acoc_set_init(acoc_ctx* ctx, const double* xx_init, const double* uu_init);
 int acoc_init_guess(acoc_ctx* ctx, double kp, double kt, const double* dx0);
 
 /* Run up to n_iters more Newton iterations (loop bodies of optcon.py:415-501) on every instance that is
- * still active.  *n_active_out (may be NULL) = instances still active afterwards (forces a device sync). */
+ * still active; returns after the device has finished them (the call is timed with CUDA events, see
+ * acoc_get_timing).  *n_active_out (may be NULL) = instances still active afterwards. */
 int acoc_newton_iterate(acoc_ctx* ctx, int n_iters, int* n_active_out);
 /* Iterate until no instance is active.  *total_iters = sum over instances of loop bodies executed.
  * Whenever at most half of a batch (of >= 4096 instances) is still iterating, the survivors are gathered into a smaller
@@ -143,7 +144,8 @@ int acoc_get_iterate(acoc_ctx* ctx, int which, double* xx, double* uu);
 /* Descent direction of the last iteration: deltau (N,2,TT) (optcon.py:468).  deltau and the gains are per-iteration
  * scratch: they are meaningful for instances that were still active in that iteration. */
 int acoc_get_deltau(acoc_ctx* ctx, double* deltau);
-/* Gains of the last backward sweep: K (N,2,6,TT), sigma (N,2,TT) -- KK[:,1:,:] and KK[:,0,:] of optcon.py:468. */
+/* Gains of the last backward sweep: K (N,2,6,TT), sigma (N,2,TT) -- KK[:,1:,:] and KK[:,0,:] of optcon.py:468.
+ * Stages N*16*TT doubles on the host: meant for inspection / parity tests on small batches. */
 int acoc_get_gains(acoc_ctx* ctx, double* K, double* sigma);
 /* Per-instance, per-iteration history, each (N, max_iters): JJ[k], descent[k] (optcon.py:497), the Armijo step
  * (optcon.py:327) and the number of candidates the sequential search rolls out.  Any pointer may be NULL. */

@@ -96,3 +96,28 @@ def test_initial_trajectory_close_to_reference(gpu):
     xx, uu = Dynamics().get_initial_trajectory(d["xx_ref"], np.linspace(0, 1, 1000))
     assert xx.shape == (6, 1000) and uu.shape == (2, 1000)
     assert relerr(d["xx_init"], xx) < 1e-4 and relerr(d["uu_init"], uu) < 1e-3
+
+
+def test_headless_scripts(gpu, tmp_path):
+    """scripts/main_newton_method.py and scripts/lqr_tracking.py: same constants, same output files as the reference's
+    scripts (Data/xx_star.npy, main_newton_method.py:184-186), fed with the reference's own initial guess."""
+    import os
+    import subprocess
+    import sys
+    from tests.util import GOLDEN, ROOT
+    d = golden("newton_step_f32.npz")
+    out = tmp_path / "Data"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "main_newton_method.py"), "--out", str(out),
+                        "--ref-init", os.path.join(GOLDEN, "newton_step_f32.npz")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.count("Iter = ") == int(d["iters"]) and "Newton iterations: 23" in r.stdout
+    xx, uu = np.load(out / "xx_star.npy"), np.load(out / "uu_star.npy")
+    assert xx.shape == (6, 1000) and uu.shape == (2, 1000) and xx.dtype == np.float64 and xx.flags["C_CONTIGUOUS"]
+    assert relerr(d["xx_star"], xx) < 1e-9 and relerr(d["uu_star"], uu) < 1e-9
+    t = golden("lqr_tracking.npz")
+    np.save(tmp_path / "xo.npy", t["xx_opt"])
+    np.save(tmp_path / "uo.npy", t["uu_opt"])
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "lqr_tracking.py"), "--xx", str(tmp_path / "xo.npy"), "--uu", str(tmp_path / "uo.npy"),
+                        "--out", str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert np.array_equal(np.load(out / "xx_lqr.npy"), t["xx_reg"][0])
