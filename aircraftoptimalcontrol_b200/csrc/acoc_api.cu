@@ -62,7 +62,14 @@ constexpr int ST_PAD = 4;  // padding lanes beyond N: never active
 constexpr int BWD_THREADS = 64;
 constexpr int FWD_THREADS = 64;
 constexpr int ROLL_THREADS = 64;
-constexpr int CAND_TILE = 32;  // instances per candidate CTA (one warp per candidate)
+#ifndef ACOC_CAND_TILE
+#define ACOC_CAND_TILE 32
+#endif
+#ifndef ACOC_CAND_MINB
+#define ACOC_CAND_MINB 3  // 64 registers (72 B of spills): 27 resident candidate warps per SM instead of 18
+#endif
+constexpr int CAND_TILE = ACOC_CAND_TILE;  // instances per candidate CTA (one warp per candidate)
+constexpr int CAND_MAXY = 10;              // candidates per CTA; more candidates than this loop inside the thread
 
 // launch a kernel templated on the state quantisation (float32 rounding of aircraft_simplified.py:300 or none)
 #define LAUNCH_Q32(q32, kernel, grid, block, stream, ...)                         \
@@ -156,13 +163,14 @@ __global__ void __launch_bounds__(FWD_THREADS) k_forward(Problem P, WorkList L, 
 
 // thread (x = position in the work list, y = candidate): J of candidate c0 + y for instance i
 template <bool Q32>
-__global__ void k_candidates(Problem P, WorkList L, const double* __restrict__ U, const double* __restrict__ DU,
-                             const double* __restrict__ cand_steps, int c0, const int* __restrict__ status, double* __restrict__ Jcand)
+__global__ void __launch_bounds__(CAND_TILE * CAND_MAXY, ACOC_CAND_MINB)
+k_candidates(Problem P, WorkList L, const double* __restrict__ U, const double* __restrict__ DU, const double* __restrict__ cand_steps, int c0,
+             int c1, const int* __restrict__ status, double* __restrict__ Jcand)
 {
     const int i = work_instance(L, blockIdx.x * CAND_TILE + threadIdx.x, P.N);
-    const int c = c0 + threadIdx.y;
     if (i < 0 || status[i] != ST_ACTIVE) return;
-    Jcand[(size_t)c * P.Np + i] = rollout_instance<false, true, Q32>(P, U, DU, cand_steps[c], nullptr, nullptr, i);
+    for (int c = c0 + threadIdx.y; c < c1; c += blockDim.y)
+        Jcand[(size_t)c * P.Np + i] = rollout_instance<false, true, Q32>(P, U, DU, cand_steps[c], nullptr, nullptr, i);
 }
 
 // lazy Armijo, first round: candidate 0 for every active instance, writing the trajectory tentatively into
@@ -924,15 +932,15 @@ static int launch_armijo(acoc_ctx* c, bool* lazy_only)
         k_build_list<<<1, 1024, 0, c->stream>>>(c->need, 1, N, 0, c->need_groups, c->counters + 2);
         CK(cudaGetLastError());
         ++c->launches;
-        dim3 block(CAND_TILE, nc - 1);
-        LAUNCH_Q32(c->P.q32, k_candidates, (N + CAND_TILE - 1) / CAND_TILE, block, c->stream, c->P, L, c->U[cur], c->DU, c->cand_steps, 1, c->S.status,
+        dim3 block(CAND_TILE, std::min(nc - 1, CAND_MAXY));
+        LAUNCH_Q32(c->P.q32, k_candidates, (N + CAND_TILE - 1) / CAND_TILE, block, c->stream, c->P, L, c->U[cur], c->DU, c->cand_steps, 1, nc, c->S.status,
                    c->S.Jcand);
         CK(cudaGetLastError());
         c->launches += 3;
         *lazy_only = true;
     } else {
-        dim3 block(CAND_TILE, nc);
-        LAUNCH_Q32(c->P.q32, k_candidates, (Np + CAND_TILE - 1) / CAND_TILE, block, c->stream, c->P, act_list(c), c->U[cur], c->DU, c->cand_steps, 0,
+        dim3 block(CAND_TILE, std::min(nc, CAND_MAXY));
+        LAUNCH_Q32(c->P.q32, k_candidates, (Np + CAND_TILE - 1) / CAND_TILE, block, c->stream, c->P, act_list(c), c->U[cur], c->DU, c->cand_steps, 0, nc,
                    c->S.status, c->S.Jcand);
         CK(cudaGetLastError());
         ++c->launches;
@@ -1209,8 +1217,8 @@ int acoc_armijo(acoc_ctx* c, double* stepsize, double* costs)
     const int cur = c->kk % 3, N = c->N, nc = c->O.armijo_maxiters;
     WorkList L;
     L.groups = nullptr; L.count = c->counters + 1; L.shift = 0;
-    dim3 block(CAND_TILE, nc);
-    LAUNCH_Q32(c->P.q32, k_candidates, (N + CAND_TILE - 1) / CAND_TILE, block, c->stream, c->P, L, c->U[cur], c->DU, c->cand_steps, 0, c->S.status, c->S.Jcand);
+    dim3 block(CAND_TILE, std::min(nc, CAND_MAXY));
+    LAUNCH_Q32(c->P.q32, k_candidates, (N + CAND_TILE - 1) / CAND_TILE, block, c->stream, c->P, L, c->U[cur], c->DU, c->cand_steps, 0, nc, c->S.status, c->S.Jcand);
     CK(cudaGetLastError());
     k_select<<<(N + 255) / 256, 256, 0, c->stream>>>(c->O, c->S, c->cand_steps, c->kk, N, c->Np);
     CK(cudaGetLastError());
