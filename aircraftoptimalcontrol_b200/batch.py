@@ -22,18 +22,30 @@ class BatchedNewton:
     the rest only where it failed; both return exactly the step the reference's sequential search returns.
     generations: let solve() gather the still-iterating instances into smaller internal batches as the others finish
     (same results, faster tail).
+    precision: "f64" (default) is the parity path -- float64 arithmetic like the reference's numpy code.  "f32" is the
+    optional FP32 mode: float32 arithmetic and trajectory storage with float64 cost/descent accumulation; it converges
+    like the reference does with its float32 state (final cost within 2e-6 relative, states within 2e-3, inputs within
+    2e-4 of their range) at roughly half the memory traffic.  `state` is irrelevant in that mode.
+    x_storage: "auto" keeps the state iterates as float32 in HBM whenever they are float32 values anyway (state="f32");
+    "f64" forces float64 buffers.  Results are bit-identical; "f64" only costs bandwidth (A/B measurements).
     """
 
     def __init__(self, n_instances, TT=1000, device=0, state="f32", refs_shared=False, armijo="speculative", params=None, generations=True,
-                 max_iters=200, stepsize_0=1.0, cc=0.5, beta=0.7, armijo_maxiters=10, term_cond=-1e-6, exact_after=8):
+                 max_iters=200, stepsize_0=1.0, cc=0.5, beta=0.7, armijo_maxiters=10, term_cond=-1e-6, exact_after=8, precision="f64",
+                 x_storage="auto"):
         if state not in ("f32", "f64"):
             raise ValueError("state must be 'f32' or 'f64'")
         if armijo not in ("speculative", "lazy"):
             raise ValueError("armijo must be 'speculative' or 'lazy'")
+        if precision not in ("f64", "f32"):
+            raise ValueError("precision must be 'f64' or 'f32'")
+        if x_storage not in ("auto", "f64"):
+            raise ValueError("x_storage must be 'auto' or 'f64'")
         self.N, self.TT, self.device = int(n_instances), int(TT), int(device)
         self.refs_shared = bool(refs_shared)
+        self.precision = precision
         flags = ((L.STATE_F64 if state == "f64" else 0) | (L.REFS_SHARED if refs_shared else 0) | (L.ARMIJO_LAZY if armijo == "lazy" else 0)
-                 | (0 if generations else L.SOLVE_IN_PLACE))
+                 | (0 if generations else L.SOLVE_IN_PLACE) | (L.FP32 if precision == "f32" else 0) | (L.X_F64 if x_storage == "f64" else 0))
         self._h = C.c_void_p(None)
         L.check(L.lib().acoc_ctx_create(self.device, self.N, self.TT, flags, C.addressof(self._h)))
         self.opts = L.NewtonOptions(int(max_iters), int(armijo_maxiters), int(exact_after), 0, float(stepsize_0), float(cc), float(beta),

@@ -9,6 +9,10 @@
 // same input/reference lines in L1.  All trajectory buffers are struct-of-arrays with the instance index
 // fastest (see acoc_kernels.cuh); host buffers use the reference's (N,6,TT) layout and are transposed on
 // the device through a staging buffer.
+//
+// Every sweep kernel is a template on the arithmetic/storage type F (double: the parity path; float: the optional FP32
+// mode, ACOC_FP32) and on the storage type XT of the state iterates (float whenever the states are float32 values anyway,
+// see acoc_kernels.cuh "Types").  The context keeps untyped device buffers; DISPATCH_FX / DISPATCH_F pick the instantiation.
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdint.h>
@@ -72,13 +76,20 @@ constexpr int CAND_TILE = ACOC_CAND_TILE;  // instances per candidate CTA (one w
 constexpr int CAND_MAXY = 10;              // candidates per CTA; more candidates than this loop inside the thread
 
 // launch a kernel templated on the state quantisation (float32 rounding of aircraft_simplified.py:300 or none)
-#define LAUNCH_Q32(q32, kernel, grid, block, stream, ...)                         \
-    do {                                                                        \
-        if (q32) kernel<true><<<grid, block, 0, stream>>>(__VA_ARGS__);          \
-        else kernel<false><<<grid, block, 0, stream>>>(__VA_ARGS__);             \
+#define LAUNCH_Q32(q32, kernel, targs, grid, block, stream, ...)                              \
+    do {                                                                                    \
+        if (q32) kernel<true, ACOC_UNPAREN targs><<<grid, block, 0, stream>>>(__VA_ARGS__);  \
+        else kernel<false, ACOC_UNPAREN targs><<<grid, block, 0, stream>>>(__VA_ARGS__);     \
     } while (0)
+#define ACOC_UNPAREN(...) __VA_ARGS__
 
-__global__ void __launch_bounds__(128) k_traj_cost(Problem P, const double* __restrict__ X, const double* __restrict__ U,
+// pick the instantiation of a host-side launch template for a context: <F, XT> or <F>
+#define DISPATCH_FX(c, fn, ...) \
+    ((c)->fp32 ? fn<float, float>(__VA_ARGS__) : ((c)->x_float ? fn<double, float>(__VA_ARGS__) : fn<double, double>(__VA_ARGS__)))
+#define DISPATCH_F(c, fn, ...) ((c)->fp32 ? fn<float>(__VA_ARGS__) : fn<double>(__VA_ARGS__))
+
+template <typename F, typename XT>
+__global__ void __launch_bounds__(128) k_traj_cost(ProblemT<F> P, const XT* __restrict__ X, const F* __restrict__ U,
                                                   const int* __restrict__ status, double* __restrict__ J)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -138,9 +149,9 @@ __global__ void __launch_bounds__(1024) k_build_list(const int* __restrict__ fla
     if (threadIdx.x == 0) *count = base;
 }
 
-template <bool EXACT>
-__global__ void __launch_bounds__(BWD_THREADS) k_backward(Problem P, WorkList L, const double* __restrict__ X, const double* __restrict__ U,
-                                                          double* __restrict__ KSG, const int* __restrict__ status, int* __restrict__ n_reg)
+template <bool EXACT, typename F, typename XT>
+__global__ void __launch_bounds__(BWD_THREADS) k_backward(ProblemT<F> P, WorkList L, const XT* __restrict__ X, const F* __restrict__ U,
+                                                          F* __restrict__ KSG, const int* __restrict__ status, int* __restrict__ n_reg)
 {
     const int i = work_instance(L, blockIdx.x * blockDim.x + threadIdx.x, P.N);
     if (i < 0) return;
@@ -151,8 +162,9 @@ __global__ void __launch_bounds__(BWD_THREADS) k_backward(Problem P, WorkList L,
     if (r && status[i] == ST_ACTIVE) n_reg[i] += r;
 }
 
-__global__ void __launch_bounds__(FWD_THREADS) k_forward(Problem P, WorkList L, const double* __restrict__ X, const double* __restrict__ U,
-                                                         const double* __restrict__ KSG, double* __restrict__ DU, double* DX,
+template <typename F, typename XT>
+__global__ void __launch_bounds__(FWD_THREADS) k_forward(ProblemT<F> P, WorkList L, const XT* __restrict__ X, const F* __restrict__ U,
+                                                         const F* __restrict__ KSG, F* __restrict__ DU, F* DX,
                                                          const int* __restrict__ status, double* __restrict__ descent)
 {
     const int i = work_instance(L, blockIdx.x * blockDim.x + threadIdx.x, P.N);
@@ -162,23 +174,23 @@ __global__ void __launch_bounds__(FWD_THREADS) k_forward(Problem P, WorkList L, 
 }
 
 // thread (x = position in the work list, y = candidate): J of candidate c0 + y for instance i
-template <bool Q32>
+template <bool Q32, typename F>
 __global__ void __launch_bounds__(CAND_TILE * CAND_MAXY, ACOC_CAND_MINB)
-k_candidates(Problem P, WorkList L, const double* __restrict__ U, const double* __restrict__ DU, const double* __restrict__ cand_steps, int c0,
+k_candidates(ProblemT<F> P, WorkList L, const F* __restrict__ U, const F* __restrict__ DU, const double* __restrict__ cand_steps, int c0,
              int c1, const int* __restrict__ status, double* __restrict__ Jcand)
 {
     const int i = work_instance(L, blockIdx.x * CAND_TILE + threadIdx.x, P.N);
     if (i < 0 || status[i] != ST_ACTIVE) return;
     for (int c = c0 + threadIdx.y; c < c1; c += blockDim.y)
-        Jcand[(size_t)c * P.Np + i] = rollout_instance<false, true, Q32>(P, U, DU, cand_steps[c], nullptr, nullptr, i);
+        Jcand[(size_t)c * P.Np + i] = rollout_instance<false, true, Q32>(P, U, DU, cand_steps[c], (F*)nullptr, (F*)nullptr, i);
 }
 
 // lazy Armijo, first round: candidate 0 for every active instance, writing the trajectory tentatively into
 // the next slot (it IS the update whenever the candidate is accepted)
-template <bool Q32>
-__global__ void __launch_bounds__(ROLL_THREADS) k_candidate0_write(Problem P, WorkList L, const double* __restrict__ U, const double* __restrict__ DU,
-                                                                   const double* __restrict__ cand_steps, double* __restrict__ Xn,
-                                                                   double* __restrict__ Un, const int* __restrict__ status,
+template <bool Q32, typename F, typename XT>
+__global__ void __launch_bounds__(ROLL_THREADS) k_candidate0_write(ProblemT<F> P, WorkList L, const F* __restrict__ U, const F* __restrict__ DU,
+                                                                   const double* __restrict__ cand_steps, XT* __restrict__ Xn,
+                                                                   F* __restrict__ Un, const int* __restrict__ status,
                                                                    double* __restrict__ Jcand)
 {
     const int i = work_instance(L, blockIdx.x * blockDim.x + threadIdx.x, P.N);
@@ -209,9 +221,9 @@ __global__ void k_select(NewtonOpts O, NewtonState S, const double* __restrict__
 // get_update with the per-instance step + termination bookkeeping.
 // only (optional): when non-null, instances with only[i] == 0 keep the trajectory already present in the next
 // slot (lazy Armijo: candidate 0 was accepted and is already there) and just run the bookkeeping.
-template <bool Q32>
-__global__ void __launch_bounds__(ROLL_THREADS) k_update(Problem P, WorkList L, NewtonOpts O, NewtonState S, const double* __restrict__ U,
-                                                         const double* __restrict__ DU, double* __restrict__ Xn, double* __restrict__ Un,
+template <bool Q32, typename F, typename XT>
+__global__ void __launch_bounds__(ROLL_THREADS) k_update(ProblemT<F> P, WorkList L, NewtonOpts O, NewtonState S, const F* __restrict__ U,
+                                                         const F* __restrict__ DU, XT* __restrict__ Xn, F* __restrict__ Un,
                                                          const int* __restrict__ only, int kk, int bookkeeping)
 {
     const int i = work_instance(L, blockIdx.x * blockDim.x + threadIdx.x, P.N);
@@ -247,13 +259,14 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_track(Problem P, const double*
     track_instance<Q32>(P, Kt, xopt, uopt, xstart, Xn, Un, i);
 }
 
-template <bool Q32>
-__global__ void __launch_bounds__(ROLL_THREADS) k_init_guess(Problem P, double kp, double kt, const double* __restrict__ dx0,
-                                                             double* __restrict__ Xn, double* __restrict__ Un)
+// dx0 and x0_out may alias (each thread reads its dx0 before it writes its x0)
+template <bool Q32, typename F, typename XT>
+__global__ void __launch_bounds__(ROLL_THREADS) k_init_guess(ProblemT<F> P, double kp, double kt, const F* dx0, XT* __restrict__ Xn,
+                                                             F* __restrict__ Un, F* x0_out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.N) return;
-    init_guess_instance<Q32>(P, kp, kt, dx0, Xn, Un, i);
+    init_guess_instance<Q32>(P, (F)kp, (F)kt, dx0, Xn, Un, x0_out, i);
 }
 
 __global__ void k_step_batch(Model M, int q32, int n, const double* __restrict__ x, const double* __restrict__ u,
@@ -299,7 +312,11 @@ __global__ void k_lq_dense(int nb, int TT, const double* A, const double* B, con
 }
 
 // ---- layout conversion: host (n, C, TT) chunk  <->  SoA [TT][C][Np] ------------------------------------
-__global__ void k_to_soa(const double* __restrict__ src, double* __restrict__ dst, int n0, int nchunk, int C, int TT, int Np)
+// D: device element type.  row0 (optional, [C][Np] of R0): receives the t = 0 column exactly (x0 = xx_init[:,0], optcon.py:398).
+// inexact (optional): set to 1 when a value at t >= 1 does not survive the conversion to D (float state slots).
+template <typename D, typename R0>
+__global__ void k_to_soa(const double* __restrict__ src, D* __restrict__ dst, int n0, int nchunk, int C, int TT, int Np, R0* __restrict__ row0,
+                         int* __restrict__ inexact)
 {
     __shared__ double tile[32][33];
     const int c = blockIdx.z, tb = blockIdx.x * 32, nb = blockIdx.y * 32;
@@ -310,13 +327,21 @@ __global__ void k_to_soa(const double* __restrict__ src, double* __restrict__ ds
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int t = tb + r, n = nb + threadIdx.x;
-        if (n < nchunk && t < TT) dst[((size_t)t * C + c) * Np + n0 + n] = tile[threadIdx.x][r];
+        if (n < nchunk && t < TT) {
+            const double v = tile[threadIdx.x][r];
+            const D d = (D)v;
+            dst[((size_t)t * C + c) * Np + n0 + n] = d;
+            if (row0 && t == 0) row0[(size_t)c * Np + n0 + n] = (R0)v;
+            if (inexact && t >= 1 && !((double)d == v) && v == v) *inexact = 1;
+        }
     }
 }
 
 // s0..s2: up to three source slots; slot[i] selects per instance (-1 -> zeros; NULL -> s0); dup_last: t = TT-1 reads TT-2
-__global__ void k_from_soa(const double* __restrict__ s0, const double* __restrict__ s1, const double* __restrict__ s2,
-                           const int* __restrict__ slot, double* __restrict__ dst, int n0, int nchunk, int C, int TT, int Np, int dup_last)
+// row0 (optional, [C][Np]): exact t = 0 column of float state slots (see acoc_kernels.cuh "Types")
+template <typename D>
+__global__ void k_from_soa(const D* __restrict__ s0, const D* __restrict__ s1, const D* __restrict__ s2, const int* __restrict__ slot,
+                           const double* __restrict__ row0, double* __restrict__ dst, int n0, int nchunk, int C, int TT, int Np, int dup_last)
 {
     __shared__ double tile[32][33];
     const int c = blockIdx.z, tb = blockIdx.x * 32, nb = blockIdx.y * 32;
@@ -326,8 +351,8 @@ __global__ void k_from_soa(const double* __restrict__ s0, const double* __restri
         if (n < nchunk && t < TT) {
             if (dup_last && t == TT - 1 && TT > 1) t = TT - 2;
             const int sl = slot ? slot[n0 + n] : 0;
-            const double* s = sl == 0 ? s0 : (sl == 1 ? s1 : s2);
-            tile[r][threadIdx.x] = sl < 0 ? 0.0 : s[((size_t)t * C + c) * Np + n0 + n];
+            const D* s = sl == 0 ? s0 : (sl == 1 ? s1 : s2);
+            tile[r][threadIdx.x] = sl < 0 ? 0.0 : ((row0 && t == 0) ? row0[(size_t)c * Np + n0 + n] : (double)s[((size_t)t * C + c) * Np + n0 + n]);
         }
     }
     __syncthreads();
@@ -416,14 +441,18 @@ struct acoc_ctx {
     int device = 0, N = 0, Np = 0, TT = 0;
     unsigned flags = 0;
     cudaStream_t stream = nullptr;
-    Problem P;
+    Problem P;   // float64 master copy of model, weights and sizes; the typed view handed to kernels is built by prob<F>()
     NewtonOpts O;
     NewtonState S;
     bool have_model = false, have_weights = false, have_refs = false, have_init = false;
     int kk = 0;  // Newton iterations (loop bodies) executed by the lock-step driver
-    double *X[3] = {nullptr, nullptr, nullptr}, *U[3] = {nullptr, nullptr, nullptr};
-    double *DU = nullptr, *KSG = nullptr, *xref = nullptr, *uref = nullptr, *x0 = nullptr, *cand_steps = nullptr;
-    double* stage = nullptr;  // device staging for layout conversion
+    // element types of the device buffers: F = float iff fp32 (else double) for U, DU, KSG, references, x0;
+    // the state slots X hold float iff x_float (FP32 mode, or float32-quantised states that are exactly representable)
+    bool fp32 = false, x_float = false;
+    void *X[3] = {nullptr, nullptr, nullptr}, *U[3] = {nullptr, nullptr, nullptr};
+    void *DU = nullptr, *KSG = nullptr, *xref = nullptr, *uref = nullptr, *x0 = nullptr;
+    double* cand_steps = nullptr;
+    double* stage = nullptr;  // device staging for layout conversion (always float64: the host side of the ABI)
     size_t stage_doubles = 0;
     int *need = nullptr, *counters = nullptr, *slot_tmp = nullptr;
     int *act_groups = nullptr, *need_groups = nullptr;  // work lists (see WorkList); counts live in counters[1], counters[2]
@@ -445,18 +474,36 @@ struct acoc_ctx {
     double gen_ms = 0;          // device time spent moving instances between generations in the last solve
 };
 
+static int dalloc_bytes(acoc_ctx* c, void** p, size_t bytes)
+{
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) return fail(ACOC_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    e = cudaMemsetAsync(q, 0, bytes, c->stream);
+    if (e != cudaSuccess) return fail(ACOC_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    c->allocs.push_back(q);
+    c->bytes += bytes;
+    *p = q;
+    return 0;
+}
 template <typename T>
 static int dalloc(acoc_ctx* c, T** p, size_t n)
 {
     void* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, n * sizeof(T));
-    if (e != cudaSuccess) return fail(ACOC_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
-    e = cudaMemsetAsync(q, 0, n * sizeof(T), c->stream);
-    if (e != cudaSuccess) return fail(ACOC_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
-    c->allocs.push_back(q);
-    c->bytes += n * sizeof(T);
+    const int rc = dalloc_bytes(c, &q, n * sizeof(T));
     *p = (T*)q;
-    return 0;
+    return rc;
+}
+// typed view of the problem for the kernels
+template <typename F>
+static ProblemT<F> prob(const acoc_ctx* c)
+{
+    ProblemT<F> P;
+    P.M = model_as<F>(c->P.M);
+    P.W = weights_as<F>(c->P.W);
+    P.N = c->P.N; P.Np = c->P.Np; P.TT = c->P.TT; P.q32 = c->P.q32; P.ref_shared = c->P.ref_shared;
+    P.xref = (const F*)c->xref; P.uref = (const F*)c->uref; P.x0 = (const F*)c->x0;
+    return P;
 }
 #define TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
 
@@ -514,8 +561,9 @@ static int reset_state(acoc_ctx* c)
     return 0;
 }
 
-// host (n,C,TT) -> SoA, chunked through the staging buffer
-static int upload_soa(acoc_ctx* c, const double* host, double* dst, int n, int C, int Np)
+// host (n,C,TT) float64 -> SoA of D, chunked through the staging buffer.  row0 / inexact: see k_to_soa.
+template <typename D, typename R0>
+static int upload_soa_t(acoc_ctx* c, const double* host, void* dst, int n, int C, int Np, R0* row0, int* inexact)
 {
     const int TT = c->TT;
     const size_t per = (size_t)C * TT;
@@ -524,15 +572,22 @@ static int upload_soa(acoc_ctx* c, const double* host, double* dst, int n, int C
         const int nc = std::min(chunk, n - n0);
         CK(cudaMemcpyAsync(c->stage, host + (size_t)n0 * per, (size_t)nc * per * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         dim3 grid((TT + 31) / 32, (nc + 31) / 32, C), block(32, 8);
-        k_to_soa<<<grid, block, 0, c->stream>>>(c->stage, dst, n0, nc, C, TT, Np);
+        k_to_soa<D, R0><<<grid, block, 0, c->stream>>>(c->stage, (D*)dst, n0, nc, C, TT, Np, row0, inexact);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(c->stream));  // the staging buffer is reused by the next chunk
     }
     return 0;
 }
+// buffers of the context's arithmetic type F (inputs, references, gains)
+static int upload_soa(acoc_ctx* c, const double* host, void* dst, int n, int C, int Np)
+{
+    return c->fp32 ? upload_soa_t<float, float>(c, host, dst, n, C, Np, nullptr, nullptr)
+                   : upload_soa_t<double, double>(c, host, dst, n, C, Np, nullptr, nullptr);
+}
 
-static int download_soa(acoc_ctx* c, const double* s0, const double* s1, const double* s2, const int* slot, double* host, int n, int C,
-                        int Np, int dup_last)
+template <typename D>
+static int download_soa_t(acoc_ctx* c, const void* s0, const void* s1, const void* s2, const int* slot, const double* row0, double* host, int n,
+                          int C, int Np, int dup_last)
 {
     const int TT = c->TT;
     const size_t per = (size_t)C * TT;
@@ -540,12 +595,25 @@ static int download_soa(acoc_ctx* c, const double* s0, const double* s1, const d
     for (int n0 = 0; n0 < n; n0 += chunk) {
         const int nc = std::min(chunk, n - n0);
         dim3 grid((TT + 31) / 32, (nc + 31) / 32, C), block(32, 8);
-        k_from_soa<<<grid, block, 0, c->stream>>>(s0, s1, s2, slot, c->stage, n0, nc, C, TT, Np, dup_last);
+        k_from_soa<D><<<grid, block, 0, c->stream>>>((const D*)s0, (const D*)s1, (const D*)s2, slot, row0, c->stage, n0, nc, C, TT, Np, dup_last);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(host + (size_t)n0 * per, c->stage, (size_t)nc * per * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     }
     return 0;
+}
+// buffers of type F
+static int download_soa(acoc_ctx* c, const void* s0, const void* s1, const void* s2, const int* slot, double* host, int n, int C, int Np,
+                        int dup_last)
+{
+    return c->fp32 ? download_soa_t<float>(c, s0, s1, s2, slot, nullptr, host, n, C, Np, dup_last)
+                   : download_soa_t<double>(c, s0, s1, s2, slot, nullptr, host, n, C, Np, dup_last);
+}
+// state slots (element type by x_float; exact t = 0 column from x0 when the slots are float but the arithmetic is float64)
+static int download_x(acoc_ctx* c, const int* slot, double* host)
+{
+    if (!c->x_float) return download_soa_t<double>(c, c->X[0], c->X[1], c->X[2], slot, nullptr, host, c->N, 6, c->Np, 0);
+    return download_soa_t<float>(c, c->X[0], c->X[1], c->X[2], slot, c->fp32 ? nullptr : (const double*)c->x0, host, c->N, 6, c->Np, 0);
 }
 
 static bool is_diag(const double* M, int n)
@@ -718,14 +786,17 @@ int acoc_ctx_create(int device, int n_instances, int TT, unsigned flags, acoc_ct
     auto bail = [&](int rc) { acoc_ctx_destroy(c); return rc; };
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(ACOC_ERR_CUDA, "cudaStreamCreate failed"));
     const size_t Np = c->Np, T = TT;
+    c->fp32 = (flags & ACOC_FP32) != 0;
+    c->x_float = c->fp32;
+    const size_t es = c->fp32 ? sizeof(float) : sizeof(double);  // the state slots are sized for es too: they may have to hold float64
     int rc = 0;
-    for (int s = 0; s < 3 && !rc; ++s) { rc = dalloc(c, &c->X[s], T * 6 * Np); if (!rc) rc = dalloc(c, &c->U[s], T * 2 * Np); }
-    if (!rc) rc = dalloc(c, &c->DU, T * 2 * Np);
-    if (!rc) rc = dalloc(c, &c->KSG, T * 16 * Np);
+    for (int s = 0; s < 3 && !rc; ++s) { rc = dalloc_bytes(c, &c->X[s], T * 6 * Np * es); if (!rc) rc = dalloc_bytes(c, &c->U[s], T * 2 * Np * es); }
+    if (!rc) rc = dalloc_bytes(c, &c->DU, T * 2 * Np * es);
+    if (!rc) rc = dalloc_bytes(c, &c->KSG, T * 16 * Np * es);
     const bool shared = flags & ACOC_REFS_SHARED;
-    if (!rc) rc = dalloc(c, &c->xref, shared ? T * 6 : T * 6 * Np);
-    if (!rc) rc = dalloc(c, &c->uref, shared ? T * 2 : T * 2 * Np);
-    if (!rc) rc = dalloc(c, &c->x0, 6 * Np);
+    if (!rc) rc = dalloc_bytes(c, &c->xref, (shared ? T * 6 : T * 6 * Np) * es);
+    if (!rc) rc = dalloc_bytes(c, &c->uref, (shared ? T * 2 : T * 2 * Np) * es);
+    if (!rc) rc = dalloc_bytes(c, &c->x0, 6 * Np * es);
     if (!rc) rc = dalloc(c, &c->S.status, Np);
     if (!rc) rc = dalloc(c, &c->S.iters, Np);
     if (!rc) rc = dalloc(c, &c->S.result_slot, Np);
@@ -748,7 +819,7 @@ int acoc_ctx_create(int device, int n_instances, int TT, unsigned flags, acoc_ct
     c->P.N = c->N; c->P.Np = c->Np; c->P.TT = TT;
     c->P.q32 = (flags & ACOC_STATE_F64) ? 0 : 1;
     c->P.ref_shared = shared ? 1 : 0;
-    c->P.xref = c->xref; c->P.uref = c->uref; c->P.x0 = c->x0;
+    c->P.xref = nullptr; c->P.uref = nullptr; c->P.x0 = nullptr;  // typed pointers are filled in by prob<F>()
     const double defp[9] = {0.1716, 2.395, 3.256, 12.0, 9.81, 0.61, 1.2, 0.24, 1e-3};
     c->P.M = make_model(defp);
     c->have_model = true;
@@ -831,11 +902,43 @@ int acoc_set_init(acoc_ctx* c, const double* xx_init, const double* uu_init)
     REQUIRE(c && xx_init && uu_init, "NULL argument");
     TRY(use_device(c->device));
     TRY(reset_state(c));
-    TRY(upload_soa(c, xx_init, c->X[0], c->N, 6, c->Np));
+    // x0 = xx[:,0,0] (optcon.py:398) is taken from the t = 0 column during the upload
+    if (c->fp32) {
+        TRY((upload_soa_t<float, float>(c, xx_init, c->X[0], c->N, 6, c->Np, (float*)c->x0, nullptr)));
+    } else {
+        c->x_float = false;
+        if (c->P.q32) {
+            // float32-quantised states: a trajectory produced by the reference's get_initial_trajectory (or by any rollout of
+            // Dynamics.step) consists of float32 values for t >= 1 and is stored as float; anything else keeps float64 slots
+            CK(cudaMemsetAsync(c->counters + 3, 0, sizeof(int), c->stream));
+            TRY((upload_soa_t<float, double>(c, xx_init, c->X[0], c->N, 6, c->Np, (double*)c->x0, c->counters + 3)));
+            int inexact = 0;
+            CK(cudaMemcpyAsync(&inexact, c->counters + 3, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            c->x_float = !inexact && !(c->flags & ACOC_X_F64);
+        }
+        if (!c->x_float) TRY((upload_soa_t<double, double>(c, xx_init, c->X[0], c->N, 6, c->Np, (double*)c->x0, nullptr)));
+    }
     TRY(upload_soa(c, uu_init, c->U[0], c->N, 2, c->Np));
-    CK(cudaMemcpyAsync(c->x0, c->X[0], (size_t)6 * c->Np * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));  // x0 = xx[:,0,0], optcon.py:398
     CK(cudaStreamSynchronize(c->stream));
     c->have_init = true;
+    return 0;
+}
+
+template <typename F, typename XT>
+static int init_guess_t(acoc_ctx* c, double kp, double kt, const double* dx0)
+{
+    F* d_dx0 = nullptr;
+    if (dx0) {  // host (N,6) -> device [6][Np]; x0 doubles as the scratch for it (the kernel writes x0 after reading dx0)
+        std::vector<F> tmp((size_t)6 * c->Np, F(0));
+        for (int i = 0; i < c->N; ++i) for (int k = 0; k < 6; ++k) tmp[(size_t)k * c->Np + i] = (F)dx0[(size_t)i * 6 + k];
+        CK(cudaMemcpyAsync(c->x0, tmp.data(), tmp.size() * sizeof(F), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        d_dx0 = (F*)c->x0;
+    }
+    LAUNCH_Q32(c->P.q32, k_init_guess, (F, XT), (c->N + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, c->stream, prob<F>(c), kp, kt, d_dx0,
+               (XT*)c->X[0], (F*)c->U[0], (F*)c->x0);
+    CK(cudaGetLastError());
     return 0;
 }
 
@@ -845,17 +948,8 @@ int acoc_init_guess(acoc_ctx* c, double kp, double kt, const double* dx0)
     if (!c->have_refs) return fail(ACOC_ERR_STATE, "acoc_init_guess: set the references first");
     TRY(use_device(c->device));
     TRY(reset_state(c));
-    double* d_dx0 = nullptr;
-    if (dx0) {  // host (N,6) -> device [6][Np] (x0 is overwritten below, so it doubles as scratch)
-        std::vector<double> tmp((size_t)6 * c->Np, 0.0);
-        for (int i = 0; i < c->N; ++i) for (int k = 0; k < 6; ++k) tmp[(size_t)k * c->Np + i] = dx0[(size_t)i * 6 + k];
-        CK(cudaMemcpyAsync(c->x0, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        d_dx0 = c->x0;
-    }
-    LAUNCH_Q32(c->P.q32, k_init_guess, (c->N + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, c->stream, c->P, kp, kt, d_dx0, c->X[0], c->U[0]);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(c->x0, c->X[0], (size_t)6 * c->Np * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    c->x_float = c->fp32 || (c->P.q32 && !(c->flags & ACOC_X_F64));  // a float32-quantised rollout produces float32 states
+    TRY(DISPATCH_FX(c, init_guess_t, c, kp, kt, dx0));
     CK(cudaStreamSynchronize(c->stream));
     c->have_init = true;
     return 0;
@@ -873,14 +967,16 @@ static int ready(acoc_ctx* c)
     return use_device(c->device);
 }
 
-static int launch_cost(acoc_ctx* c)
+template <typename F, typename XT>
+static int launch_cost_t(acoc_ctx* c)
 {
     const int cur = c->kk % 3;
-    k_traj_cost<<<(c->N + 127) / 128, 128, 0, c->stream>>>(c->P, c->X[cur], c->U[cur], c->S.status, c->S.Jcur);
+    k_traj_cost<F, XT><<<(c->N + 127) / 128, 128, 0, c->stream>>>(prob<F>(c), (const XT*)c->X[cur], (const F*)c->U[cur], c->S.status, c->S.Jcur);
     CK(cudaGetLastError());
     ++c->launches;
     return 0;
 }
+static int launch_cost(acoc_ctx* c) { return DISPATCH_FX(c, launch_cost_t, c); }
 static WorkList act_list(acoc_ctx* c)
 {
     WorkList L;
@@ -897,33 +993,44 @@ static int launch_build_active(acoc_ctx* c)
     ++c->launches;
     return 0;
 }
-static int launch_backward(acoc_ctx* c, bool exact)
+template <typename F, typename XT>
+static int launch_backward_t(acoc_ctx* c, bool exact)
 {
     const int cur = c->kk % 3, g = (c->Np + BWD_THREADS - 1) / BWD_THREADS;
-    if (exact) k_backward<true><<<g, BWD_THREADS, 0, c->stream>>>(c->P, act_list(c), c->X[cur], c->U[cur], c->KSG, c->S.status, c->S.n_reg);
-    else k_backward<false><<<g, BWD_THREADS, 0, c->stream>>>(c->P, act_list(c), c->X[cur], c->U[cur], c->KSG, c->S.status, c->S.n_reg);
+    const ProblemT<F> P = prob<F>(c);
+    const XT* X = (const XT*)c->X[cur];
+    const F* U = (const F*)c->U[cur];
+    if (exact) k_backward<true, F, XT><<<g, BWD_THREADS, 0, c->stream>>>(P, act_list(c), X, U, (F*)c->KSG, c->S.status, c->S.n_reg);
+    else k_backward<false, F, XT><<<g, BWD_THREADS, 0, c->stream>>>(P, act_list(c), X, U, (F*)c->KSG, c->S.status, c->S.n_reg);
     CK(cudaGetLastError());
     ++c->launches;
     return 0;
 }
-static int launch_forward(acoc_ctx* c)
+static int launch_backward(acoc_ctx* c, bool exact) { return DISPATCH_FX(c, launch_backward_t, c, exact); }
+
+template <typename F, typename XT>
+static int launch_forward_t(acoc_ctx* c)
 {
     const int cur = c->kk % 3;
-    k_forward<<<(c->Np + FWD_THREADS - 1) / FWD_THREADS, FWD_THREADS, 0, c->stream>>>(c->P, act_list(c), c->X[cur], c->U[cur], c->KSG, c->DU, nullptr,
-                                                                                     c->S.status, c->S.descent);
+    k_forward<F, XT><<<(c->Np + FWD_THREADS - 1) / FWD_THREADS, FWD_THREADS, 0, c->stream>>>(
+        prob<F>(c), act_list(c), (const XT*)c->X[cur], (const F*)c->U[cur], (const F*)c->KSG, (F*)c->DU, (F*)nullptr, c->S.status, c->S.descent);
     CK(cudaGetLastError());
     ++c->launches;
     return 0;
 }
+static int launch_forward(acoc_ctx* c) { return DISPATCH_FX(c, launch_forward_t, c); }
 // Armijo: fills S.step and the history row kk.  Returns through *lazy_only whether the update may skip
 // instances whose candidate 0 is already in the next slot.
-static int launch_armijo(acoc_ctx* c, bool* lazy_only)
+template <typename F, typename XT>
+static int launch_armijo_t(acoc_ctx* c, bool* lazy_only)
 {
     const int cur = c->kk % 3, nxt = (c->kk + 1) % 3, N = c->N, Np = c->Np, nc = c->O.armijo_maxiters;
+    const ProblemT<F> P = prob<F>(c);
+    const F *U = (const F*)c->U[cur], *DU = (const F*)c->DU;
     *lazy_only = false;
     if ((c->flags & ACOC_ARMIJO_LAZY) && nc > 1) {
-        LAUNCH_Q32(c->P.q32, k_candidate0_write, (Np + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, c->stream, c->P, act_list(c), c->U[cur], c->DU,
-                   c->cand_steps, c->X[nxt], c->U[nxt], c->S.status, c->S.Jcand);
+        LAUNCH_Q32(c->P.q32, k_candidate0_write, (F, XT), (Np + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, c->stream, P, act_list(c), U, DU,
+                   c->cand_steps, (XT*)c->X[nxt], (F*)c->U[nxt], c->S.status, c->S.Jcand);
         CK(cudaGetLastError());
         k_lazy_need<<<(N + 255) / 256, 256, 0, c->stream>>>(c->O, c->S, c->cand_steps, N, c->need);
         CK(cudaGetLastError());
@@ -933,14 +1040,14 @@ static int launch_armijo(acoc_ctx* c, bool* lazy_only)
         CK(cudaGetLastError());
         ++c->launches;
         dim3 block(CAND_TILE, std::min(nc - 1, CAND_MAXY));
-        LAUNCH_Q32(c->P.q32, k_candidates, (N + CAND_TILE - 1) / CAND_TILE, block, c->stream, c->P, L, c->U[cur], c->DU, c->cand_steps, 1, nc, c->S.status,
+        LAUNCH_Q32(c->P.q32, k_candidates, (F), (N + CAND_TILE - 1) / CAND_TILE, block, c->stream, P, L, U, DU, c->cand_steps, 1, nc, c->S.status,
                    c->S.Jcand);
         CK(cudaGetLastError());
         c->launches += 3;
         *lazy_only = true;
     } else {
         dim3 block(CAND_TILE, std::min(nc, CAND_MAXY));
-        LAUNCH_Q32(c->P.q32, k_candidates, (Np + CAND_TILE - 1) / CAND_TILE, block, c->stream, c->P, act_list(c), c->U[cur], c->DU, c->cand_steps, 0, nc,
+        LAUNCH_Q32(c->P.q32, k_candidates, (F), (Np + CAND_TILE - 1) / CAND_TILE, block, c->stream, P, act_list(c), U, DU, c->cand_steps, 0, nc,
                    c->S.status, c->S.Jcand);
         CK(cudaGetLastError());
         ++c->launches;
@@ -950,16 +1057,23 @@ static int launch_armijo(acoc_ctx* c, bool* lazy_only)
     ++c->launches;
     return 0;
 }
-static int launch_update(acoc_ctx* c, bool lazy_only, bool bookkeeping, bool use_list)
+static int launch_armijo(acoc_ctx* c, bool* lazy_only) { return DISPATCH_FX(c, launch_armijo_t, c, lazy_only); }
+
+template <typename F, typename XT>
+static int launch_update_t(acoc_ctx* c, bool lazy_only, bool bookkeeping, bool use_list)
 {
     const int cur = c->kk % 3, nxt = (c->kk + 1) % 3;
     WorkList L = act_list(c);
     if (!use_list) L.groups = nullptr;
-    LAUNCH_Q32(c->P.q32, k_update, (c->Np + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, c->stream, c->P, L, c->O, c->S, c->U[cur], c->DU, c->X[nxt],
-               c->U[nxt], lazy_only ? c->need : nullptr, c->kk, bookkeeping ? 1 : 0);
+    LAUNCH_Q32(c->P.q32, k_update, (F, XT), (c->Np + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, c->stream, prob<F>(c), L, c->O, c->S,
+               (const F*)c->U[cur], (const F*)c->DU, (XT*)c->X[nxt], (F*)c->U[nxt], lazy_only ? c->need : nullptr, c->kk, bookkeeping ? 1 : 0);
     CK(cudaGetLastError());
     ++c->launches;
     return 0;
+}
+static int launch_update(acoc_ctx* c, bool lazy_only, bool bookkeeping, bool use_list)
+{
+    return DISPATCH_FX(c, launch_update_t, c, lazy_only, bookkeeping, use_list);
 }
 
 static int count_active(acoc_ctx* c, int* n_active, long long* iters_sum)
@@ -1033,6 +1147,13 @@ static int move_rows(acoc_ctx* par, acoc_ctx* ch, T* pbuf, T* cbuf, int rows, bo
     return 0;
 }
 
+// untyped trajectory buffers: rows of float or double
+static int move_rows_e(acoc_ctx* par, acoc_ctx* ch, void* pbuf, void* cbuf, int rows, bool to_child, bool is_float)
+{
+    return is_float ? move_rows<float>(par, ch, (float*)pbuf, (float*)cbuf, rows, to_child)
+                    : move_rows<double>(par, ch, (double*)pbuf, (double*)cbuf, rows, to_child);
+}
+
 // Move the n_active still-iterating instances of `par` into its child generation.  Returns 1 if no child could be made.
 static int spawn_child(acoc_ctx* par, int n_active, acoc_ctx** out)
 {
@@ -1056,6 +1177,8 @@ static int spawn_child(acoc_ctx* par, int n_active, acoc_ctx** out)
     ch->P.M = par->P.M; ch->P.W = par->P.W; ch->P.q32 = par->P.q32; ch->P.N = n_active;
     ch->have_model = ch->have_weights = ch->have_refs = ch->have_init = true;
     ch->profiling = par->profiling;
+    ch->x_float = par->x_float;  // (fp32 follows from the creation flags)
+    const bool ff = par->fp32, xf = par->x_float;
     TRY(use_device(par->device));
     TRY(reset_state(ch));
     CK(cudaStreamSynchronize(ch->stream));
@@ -1067,17 +1190,18 @@ static int spawn_child(acoc_ctx* par, int n_active, acoc_ctx** out)
     CK(cudaGetLastError());
     for (int sl = 0; sl < 3; ++sl) {
         if (sl == (par->kk + 1) % 3) continue;  // the "next" slot is overwritten by the child's first update anyway
-        TRY(move_rows(par, ch, par->X[sl], ch->X[sl], 6 * TT, true));
-        TRY(move_rows(par, ch, par->U[sl], ch->U[sl], 2 * TT, true));
+        TRY(move_rows_e(par, ch, par->X[sl], ch->X[sl], 6 * TT, true, xf));
+        TRY(move_rows_e(par, ch, par->U[sl], ch->U[sl], 2 * TT, true, ff));
     }
     if (par->flags & ACOC_REFS_SHARED) {
-        CK(cudaMemcpyAsync(ch->xref, par->xref, (size_t)TT * 6 * sizeof(double), cudaMemcpyDeviceToDevice, par->stream));
-        CK(cudaMemcpyAsync(ch->uref, par->uref, (size_t)TT * 2 * sizeof(double), cudaMemcpyDeviceToDevice, par->stream));
+        const size_t es = ff ? sizeof(float) : sizeof(double);
+        CK(cudaMemcpyAsync(ch->xref, par->xref, (size_t)TT * 6 * es, cudaMemcpyDeviceToDevice, par->stream));
+        CK(cudaMemcpyAsync(ch->uref, par->uref, (size_t)TT * 2 * es, cudaMemcpyDeviceToDevice, par->stream));
     } else {
-        TRY(move_rows(par, ch, par->xref, ch->xref, 6 * TT, true));
-        TRY(move_rows(par, ch, par->uref, ch->uref, 2 * TT, true));
+        TRY(move_rows_e(par, ch, par->xref, ch->xref, 6 * TT, true, ff));
+        TRY(move_rows_e(par, ch, par->uref, ch->uref, 2 * TT, true, ff));
     }
-    TRY(move_rows(par, ch, par->x0, ch->x0, 6, true));
+    TRY(move_rows_e(par, ch, par->x0, ch->x0, 6, true, ff));
     TRY(move_rows(par, ch, par->S.Jcur, ch->S.Jcur, 1, true));
     TRY(move_rows(par, ch, par->S.descent, ch->S.descent, 1, true));
     TRY(move_rows(par, ch, par->S.step, ch->S.step, 1, true));
@@ -1100,8 +1224,8 @@ static int fold_child(acoc_ctx* par, acoc_ctx* ch)
     CK(cudaStreamSynchronize(ch->stream));
     const int TT = par->TT, mi = par->O.max_iters;
     for (int sl = 0; sl < 3; ++sl) {
-        TRY(move_rows(par, ch, par->X[sl], ch->X[sl], 6 * TT, false));
-        TRY(move_rows(par, ch, par->U[sl], ch->U[sl], 2 * TT, false));
+        TRY(move_rows_e(par, ch, par->X[sl], ch->X[sl], 6 * TT, false, par->x_float));
+        TRY(move_rows_e(par, ch, par->U[sl], ch->U[sl], 2 * TT, false, par->fp32));
     }
     TRY(move_rows(par, ch, par->S.Jcur, ch->S.Jcur, 1, false));
     TRY(move_rows(par, ch, par->S.descent, ch->S.descent, 1, false));
@@ -1209,17 +1333,26 @@ int acoc_forward(acoc_ctx* c, double* descent)
     return 0;
 }
 
+template <typename F>
+static int launch_all_candidates_t(acoc_ctx* c)
+{
+    const int cur = c->kk % 3, N = c->N, nc = c->O.armijo_maxiters;
+    WorkList L;
+    L.groups = nullptr; L.count = c->counters + 1; L.shift = 0;
+    dim3 block(CAND_TILE, std::min(nc, CAND_MAXY));
+    LAUNCH_Q32(c->P.q32, k_candidates, (F), (N + CAND_TILE - 1) / CAND_TILE, block, c->stream, prob<F>(c), L, (const F*)c->U[cur], (const F*)c->DU,
+               c->cand_steps, 0, nc, c->S.status, c->S.Jcand);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int acoc_armijo(acoc_ctx* c, double* stepsize, double* costs)
 {
     TRY(ready(c));
     REQUIRE(c->kk < c->O.max_iters, "iteration counter exhausted");
     // always the speculative evaluation here: this entry point reports the cost of every candidate
-    const int cur = c->kk % 3, N = c->N, nc = c->O.armijo_maxiters;
-    WorkList L;
-    L.groups = nullptr; L.count = c->counters + 1; L.shift = 0;
-    dim3 block(CAND_TILE, std::min(nc, CAND_MAXY));
-    LAUNCH_Q32(c->P.q32, k_candidates, (N + CAND_TILE - 1) / CAND_TILE, block, c->stream, c->P, L, c->U[cur], c->DU, c->cand_steps, 0, nc, c->S.status, c->S.Jcand);
-    CK(cudaGetLastError());
+    const int N = c->N, nc = c->O.armijo_maxiters;
+    TRY(DISPATCH_F(c, launch_all_candidates_t, c));
     k_select<<<(N + 255) / 256, 256, 0, c->stream>>>(c->O, c->S, c->cand_steps, c->kk, N, c->Np);
     CK(cudaGetLastError());
     if (stepsize) CK(cudaMemcpyAsync(stepsize, c->S.step, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1269,7 +1402,7 @@ int acoc_get_result(acoc_ctx* c, double* xx_star, double* uu_star)
     REQUIRE(xx_star && uu_star, "NULL output");
     k_result_slot_default<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->S.status, c->slot_tmp, c->S.result_slot, c->kk % 3, c->N);
     CK(cudaGetLastError());
-    TRY(download_soa(c, c->X[0], c->X[1], c->X[2], c->slot_tmp, xx_star, c->N, 6, c->Np, 0));
+    TRY(download_x(c, c->slot_tmp, xx_star));
     TRY(download_soa(c, c->U[0], c->U[1], c->U[2], c->slot_tmp, uu_star, c->N, 2, c->Np, 1));  // uu_star[:,-1] = uu_star[:,-2], optcon.py:505
     return 0;
 }
@@ -1280,7 +1413,7 @@ int acoc_get_iterate(acoc_ctx* c, int which, double* xx, double* uu)
     REQUIRE(which == 0 || which == 1, "which must be 0 (newest) or 1 (previous)");
     k_iterate_slot<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->S.iters, which, c->slot_tmp, c->N);
     CK(cudaGetLastError());
-    if (xx) TRY(download_soa(c, c->X[0], c->X[1], c->X[2], c->slot_tmp, xx, c->N, 6, c->Np, 0));
+    if (xx) TRY(download_x(c, c->slot_tmp, xx));
     if (uu) TRY(download_soa(c, c->U[0], c->U[1], c->U[2], c->slot_tmp, uu, c->N, 2, c->Np, 0));
     return 0;
 }
@@ -1381,14 +1514,17 @@ int acoc_lqr_tracking(int device, int n, int TT, const double* params, int state
     std::vector<double> Qrep((size_t)TT * 36), Rrep((size_t)TT * 4);
     for (int k = 0; k < TT; ++k) { memcpy(&Qrep[(size_t)k * 36], Q, 36 * sizeof(double)); memcpy(&Rrep[(size_t)k * 4], R, 4 * sizeof(double)); }  // .repeat(TT), optcon.py:603-606
     TRY(t.up(&dQ, Qrep.data(), Qrep.size())); TRY(t.up(&dR, Rrep.data(), Rrep.size())); TRY(t.up(&dQf, QT, 36)); TRY(t.up(&dx0, delta, 6));
-    k_step_batch<<<(TT + 127) / 128, 128, 0, c->stream>>>(M, c->P.q32, TT, c->xref, c->uref, nullptr, nullptr, dA, dB, nullptr, nullptr);
+    const double *d_xopt = (const double*)c->xref, *d_uopt = (const double*)c->uref;
+    k_step_batch<<<(TT + 127) / 128, 128, 0, c->stream>>>(M, c->P.q32, TT, d_xopt, d_uopt, nullptr, nullptr, dA, dB, nullptr, nullptr);
     CK(cudaGetLastError());
     TRY(lq_dense_dev(1, TT, false, dA, dB, dQ, dR, dS, dQf, dx0, nullptr, nullptr, nullptr, dK, nullptr, dxo, duo, nullptr, c->stream));
     // perturbed initial states: x_start[c][i] = xx_opt[c][0] + delta[i][c]   (lqr_tracking.py:265)
     std::vector<double> xs((size_t)6 * c->Np, 0.0);
     for (int i = 0; i < n; ++i) for (int k = 0; k < 6; ++k) xs[(size_t)k * c->Np + i] = xx_opt[(size_t)k * TT] + delta[(size_t)i * 6 + k];
     TRY(t.up(&dstart, xs.data(), xs.size()));
-    LAUNCH_Q32(c->P.q32, k_track, (n + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, c->stream, c->P, dK, c->xref, c->uref, dstart, c->X[0], c->U[0]);
+    const Problem P = prob<double>(c);
+    if (c->P.q32) k_track<true><<<(n + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, 0, c->stream>>>(P, dK, d_xopt, d_uopt, dstart, (double*)c->X[0], (double*)c->U[0]);
+    else k_track<false><<<(n + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, 0, c->stream>>>(P, dK, d_xopt, d_uopt, dstart, (double*)c->X[0], (double*)c->U[0]);
     CK(cudaGetLastError());
     TRY(download_soa(c, c->X[0], nullptr, nullptr, nullptr, xx_reg, n, 6, c->Np, 0));
     TRY(download_soa(c, c->U[0], nullptr, nullptr, nullptr, uu_reg, n, 2, c->Np, 0));

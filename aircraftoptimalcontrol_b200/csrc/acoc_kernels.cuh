@@ -16,7 +16,16 @@
 //   armijo_select_instance optcon.py:266-273, :327 and the bookkeeping of :488-501
 //   track_instance        lqr_tracking.py:279-281
 //   init_guess_instance   aircraft_simplified.py:142-147
+//
+// Types: F is the arithmetic type and the storage type of U, DU, KSG, the references and x0 (double = the parity path,
+// float = the optional FP32 mode).  XT is the storage type of the state iterates X.  With the reference's float32 state
+// quantisation (aircraft_simplified.py:300) every stored state x_t, t >= 1, IS a float32 value, so the parity path keeps
+// X as float (XT = float, F = double): 24 instead of 48 bytes per step, bit-identical results.  Row t = 0 of such a slot
+// is not exact (x0 is an arbitrary float64); readers take x_0 from P.x0 instead (it never changes, optcon.py:398/:194).
+// Costs and the descent are accumulated in float64 in every mode.
 #pragma once
+#include <type_traits>
+
 #include "acoc_math.cuh"
 
 namespace acoc {
@@ -24,22 +33,25 @@ namespace acoc {
 // ------------------------------------------------------------------------------------------------------
 // problem description shared by all sweeps
 // ------------------------------------------------------------------------------------------------------
-struct Problem {
-    Model M;
-    Weights W;
+template <typename F>
+struct ProblemT {
+    ModelT<F> M;
+    WeightsT<F> W;
     int N;         // instances
     int Np;        // padded instance count (multiple of 32) = stride between components
     int TT;        // horizon samples
     int q32;       // 1: round the next state to float32 like aircraft_simplified.py:300
     int ref_shared;  // 1: xref/uref hold one trajectory shared by all instances (stride 1)
-    const double* xref;  // [TT][6][Np] or [TT][6][1]
-    const double* uref;  // [TT][2][Np] or [TT][2][1]
-    const double* x0;    // [6][Np]   x0 = xx_init[:,0]  (optcon.py:398)
+    const F* xref;  // [TT][6][Np] or [TT][6][1]
+    const F* uref;  // [TT][2][Np] or [TT][2][1]
+    const F* x0;    // [6][Np]   x0 = xx_init[:,0]  (optcon.py:398)
 };
+using Problem = ProblemT<double>;
 
 ACOC_HD size_t at(int t, int C, int c, int Np, int i) { return ((size_t)t * C + c) * (size_t)Np + i; }
 
-ACOC_HD void load_ref(const Problem& P, int t, int i, double* xr, double* ur)
+template <typename F>
+ACOC_HD void load_ref(const ProblemT<F>& P, int t, int i, F* xr, F* ur)
 {
     const int Nr = P.ref_shared ? 1 : P.Np, ir = P.ref_shared ? 0 : i;
 #pragma unroll
@@ -47,18 +59,53 @@ ACOC_HD void load_ref(const Problem& P, int t, int i, double* xr, double* ur)
 #pragma unroll
     for (int c = 0; c < NI; ++c) ur[c] = P.uref[at(t, NI, c, Nr, ir)];
 }
-ACOC_HD void load_xref(const Problem& P, int t, int i, double* xr)
+template <typename F>
+ACOC_HD void load_xref(const ProblemT<F>& P, int t, int i, F* xr)
 {
     const int Nr = P.ref_shared ? 1 : P.Np, ir = P.ref_shared ? 0 : i;
 #pragma unroll
     for (int c = 0; c < NS; ++c) xr[c] = P.xref[at(t, NS, c, Nr, ir)];
 }
 
+// state iterate slot: x_t of instance i (see "Types" above for the t = 0 rule)
+// Split in two so that a sweep can issue the raw loads one step ahead (software prefetch) and convert where the value is
+// consumed: a conversion placed right after the load would wait for the data at the prefetch point.
+template <typename XT>
+ACOC_HD void load_x_raw(const XT* X, int t, int Np, int i, XT* raw)
+{
+#pragma unroll
+    for (int c = 0; c < NS; ++c) raw[c] = X[at(t, NS, c, Np, i)];
+}
+template <typename F, typename XT>
+ACOC_HD void finish_x(const ProblemT<F>& P, int t, int i, const XT* raw, F* x)
+{
+#pragma unroll
+    for (int c = 0; c < NS; ++c) x[c] = (F)raw[c];
+    if (!std::is_same<F, XT>::value && t == 0) {  // once per sweep
+#pragma unroll
+        for (int c = 0; c < NS; ++c) x[c] = P.x0[(size_t)c * P.Np + i];
+    }
+}
+template <typename F, typename XT>
+ACOC_HD void load_x(const ProblemT<F>& P, const XT* X, int t, int i, F* x)
+{
+    XT raw[NS];
+    load_x_raw(X, t, P.Np, i, raw);
+    finish_x(P, t, i, raw, x);
+}
+template <typename F, typename XT>
+ACOC_HD void store_x(XT* X, int t, int Np, int i, const F* x)
+{
+#pragma unroll
+    for (int c = 0; c < NS; ++c) X[at(t, NS, c, Np, i)] = (XT)x[c];
+}
+
 // symmetric 6x6 in 21 registers, (i <= j)
 ACOC_HD constexpr int sym(int i, int j) { return i <= j ? i * 6 - (i * (i - 1)) / 2 + (j - i) : j * 6 - (j * (j - 1)) / 2 + (i - j); }
 
 // sum_c v[c] * A[c][J] : the dot product of v with column J of the sparse Jacobian (Appendix A of SURVEY.md)
-ACOC_HD double acol(const Lin& l, double dt, const double* v, int J)
+template <typename F>
+ACOC_HD F acol(const Lin<F>& l, F dt, const F* v, int J)
 {
     switch (J) {
         case 0: return v[0];
@@ -73,21 +120,25 @@ ACOC_HD double acol(const Lin& l, double dt, const double* v, int J)
 // ------------------------------------------------------------------------------------------------------
 // cost of a stored trajectory, optcon.py:417-424
 // ------------------------------------------------------------------------------------------------------
-ACOC_HD double traj_cost_instance(const Problem& P, const double* X, const double* U, int i)
+template <typename F, typename XT>
+ACOC_HD double traj_cost_instance(const ProblemT<F>& P, const XT* X, const F* U, int i)
 {
-    double J = 0.0, dx[NS], du[NI], xr[NS], ur[NI];
+    double J = 0.0;
+    F x[NS], dx[NS], du[NI], xr[NS], ur[NI];
     for (int t = 0; t < P.TT - 1; ++t) {
         load_ref(P, t, i, xr, ur);
+        load_x(P, X, t, i, x);
 #pragma unroll
-        for (int c = 0; c < NS; ++c) dx[c] = X[at(t, NS, c, P.Np, i)] - xr[c];
+        for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
 #pragma unroll
         for (int c = 0; c < NI; ++c) du[c] = U[at(t, NI, c, P.Np, i)] - ur[c];
-        J += stage_cost(P.W, dx, du);
+        J += (double)stage_cost(P.W, dx, du);
     }
     load_xref(P, P.TT - 1, i, xr);
+    load_x(P, X, P.TT - 1, i, x);
 #pragma unroll
-    for (int c = 0; c < NS; ++c) dx[c] = X[at(P.TT - 1, NS, c, P.Np, i)] - xr[c];
-    J += term_cost(P.W, dx);
+    for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
+    J += (double)term_cost(P.W, dx);
     return J;
 }
 
@@ -101,31 +152,31 @@ ACOC_HD double traj_cost_instance(const Problem& P, const double* X, const doubl
 //   Mx = B'PA + S,  m = B'p + r/2,  G = R + B'PB
 //   P_t = Q + A'PA - Mx' G^-1 Mx          p_t = q/2 + A'p - Mx' G^-1 m
 //   MM  = G, or G + 0.5 I when G has a non-positive eigenvalue;  K = -MM^-1 Mx,  sigma = -MM^-1 m
-template <bool EXACT>
-ACOC_HD int riccati_step(const Model& M, const Weights& W, const Lin& l, const Hess& h, const double* q, const double* r,
-                         double* Pm, double* p, double* lam, double* K, double* sig, double* g)
+template <bool EXACT, typename F>
+ACOC_HD int riccati_step(const ModelT<F>& M, const WeightsT<F>& W, const Lin<F>& l, const Hess<F>& h, const F* q, const F* r,
+                         F* Pm, F* p, F* lam, F* K, F* sig, F* g)
 {
-    const double dt = M.dt, b41 = M.b41;
+    const F dt = M.dt, b41 = M.b41;
     // g = B' lam_{t+1} + r  (optcon.py:475)
     g[0] = fma_(l.b50, lam[5], fma_(l.b20, lam[2], r[0]));
     g[1] = fma_(b41, lam[4], r[1]);
     // G = R + B'PB, m = B'p + r/2  (need P_{t+1}, p_{t+1})
-    const double P22 = Pm[sym(2, 2)], P25 = Pm[sym(2, 5)], P55 = Pm[sym(5, 5)], P24 = Pm[sym(2, 4)], P45 = Pm[sym(4, 5)], P44 = Pm[sym(4, 4)];
-    const double pb2 = fma_(l.b50, P25, l.b20 * P22), pb5 = fma_(l.b50, P55, l.b20 * P25);
-    const double G00 = fma_(l.b50, pb5, fma_(l.b20, pb2, W.R[0]));
-    const double G01 = fma_(b41, fma_(l.b50, P45, l.b20 * P24), W.R[1]);
-    const double G11 = fma_(b41 * b41, P44, W.R[3]);
-    const double m0 = fma_(l.b50, p[5], fma_(l.b20, p[2], 0.5 * r[0]));
-    const double m1 = fma_(b41, p[4], 0.5 * r[1]);
+    const F P22 = Pm[sym(2, 2)], P25 = Pm[sym(2, 5)], P55 = Pm[sym(5, 5)], P24 = Pm[sym(2, 4)], P45 = Pm[sym(4, 5)], P44 = Pm[sym(4, 4)];
+    const F pb2 = fma_(l.b50, P25, l.b20 * P22), pb5 = fma_(l.b50, P55, l.b20 * P25);
+    const F G00 = fma_(l.b50, pb5, fma_(l.b20, pb2, W.R[0]));
+    const F G01 = fma_(b41, fma_(l.b50, P45, l.b20 * P24), W.R[1]);
+    const F G11 = fma_(b41 * b41, P44, W.R[3]);
+    const F m0 = fma_(l.b50, p[5], fma_(l.b20, p[2], F(0.5) * r[0]));
+    const F m1 = fma_(b41, p[4], F(0.5) * r[1]);
 
     // column sweep: W = P A (column j), N = A'W (upper triangle), Mx = B'W (+S)
-    double Pn[21], Mx0[NS], Mx1[NS];
+    F Pn[21], Mx0[NS], Mx1[NS];
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
-        double Wc[NS];
+        F Wc[NS];
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
-            double row[NS];
+            F row[NS];
 #pragma unroll
             for (int c = 0; c < NS; ++c) row[c] = Pm[sym(k, c)];
             Wc[k] = acol(l, dt, row, j);
@@ -138,35 +189,35 @@ ACOC_HD int riccati_step(const Model& M, const Weights& W, const Lin& l, const H
     if (EXACT) { Mx0[2] += h.s2; Mx0[3] += h.s3; Mx0[5] += h.s5; }  // S = lux + fux (optcon.py:446)
 
     // A'p and A'lam
-    double Atp[NS], Atl[NS];
+    F Atp[NS], Atl[NS];
 #pragma unroll
     for (int i = 0; i < NS; ++i) { Atp[i] = acol(l, dt, p, i); Atl[i] = acol(l, dt, lam, i); }
 
     // G^-1 (explicit inverse, optcon.py:728)
-    const double det = fma_(G00, G11, -(G01 * G01));
-    const double idet = 1.0 / det;
-    const double gi00 = G11 * idet, gi01 = -G01 * idet, gi11 = G00 * idet;
-    double Y0[NS], Y1[NS];  // G^-1 Mx
+    const F det = fma_(G00, G11, -(G01 * G01));
+    const F idet = F(1.0) / det;
+    const F gi00 = G11 * idet, gi01 = -G01 * idet, gi11 = G00 * idet;
+    F Y0[NS], Y1[NS];  // G^-1 Mx
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
         Y0[j] = fma_(gi01, Mx1[j], gi00 * Mx0[j]);
         Y1[j] = fma_(gi11, Mx1[j], gi01 * Mx0[j]);
     }
-    const double y0 = fma_(gi01, m1, gi00 * m0), y1 = fma_(gi11, m1, gi01 * m0);
+    const F y0 = fma_(gi01, m1, gi00 * m0), y1 = fma_(gi11, m1, gi01 * m0);
 
     // gains: positive-definiteness test on G (optcon.py:743-749) -- eigenvalues of the symmetric 2x2
-    const double hd = 0.5 * (G00 - G11), mid = 0.5 * (G00 + G11);
-    const double rad = sqrt(fma_(hd, hd, G01 * G01));
+    const F hd = F(0.5) * (G00 - G11), mid = F(0.5) * (G00 + G11);
+    const F rad = sqrt_(fma_(hd, hd, G01 * G01));
     int reg = 0;
-    if (mid - rad > 0.0) {
+    if (mid - rad > F(0.0)) {
 #pragma unroll
         for (int j = 0; j < NS; ++j) { K[j] = -Y0[j]; K[NS + j] = -Y1[j]; }
         sig[0] = -y0; sig[1] = -y1;
     } else {  // regularised gain MM = G + 0.5 I; the Riccati update below still uses the plain G^-1
         reg = 1;
-        const double H00 = G00 + 0.5, H11 = G11 + 0.5;
-        const double id2 = 1.0 / fma_(H00, H11, -(G01 * G01));
-        const double hi00 = H11 * id2, hi01 = -G01 * id2, hi11 = H00 * id2;
+        const F H00 = G00 + F(0.5), H11 = G11 + F(0.5);
+        const F id2 = F(1.0) / fma_(H00, H11, -(G01 * G01));
+        const F hi00 = H11 * id2, hi01 = -G01 * id2, hi11 = H00 * id2;
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
             K[j] = -fma_(hi01, Mx1[j], hi00 * Mx0[j]);
@@ -181,11 +232,11 @@ ACOC_HD int riccati_step(const Model& M, const Weights& W, const Lin& l, const H
     for (int i = 0; i < NS; ++i) {
 #pragma unroll
         for (int j = i; j < NS; ++j) {
-            double qij = W.diag ? (i == j ? W.Q[i * 7] : 0.0) : W.Q[i * 6 + j];
-            const double corr = fma_(Mx1[i], Y1[j], Mx0[i] * Y0[j]);
+            F qij = W.diag ? (i == j ? W.Q[i * 7] : F(0.0)) : W.Q[i * 6 + j];
+            const F corr = fma_(Mx1[i], Y1[j], Mx0[i] * Y0[j]);
             Pm[sym(i, j)] = (Pn[sym(i, j)] + qij) - corr;
         }
-        p[i] = fma_(0.5, q[i], Atp[i]) - fma_(Mx1[i], y1, Mx0[i] * y0);
+        p[i] = fma_(F(0.5), q[i], Atp[i]) - fma_(Mx1[i], y1, Mx0[i] * y0);
         lam[i] = Atl[i] + q[i];  // optcon.py:461
     }
     if (EXACT) {  // Q_t = lxx + fxx (optcon.py:444)
@@ -200,42 +251,43 @@ ACOC_HD int riccati_step(const Model& M, const Weights& W, const Lin& l, const H
 // ------------------------------------------------------------------------------------------------------
 // KSG[t][0..11] = K_t (row-major 2x6), [12..13] = sigma_t, [14..15] = g_t ; t = 0..TT-2.
 // Returns the number of steps whose gain took the +0.5 I branch.
-template <bool EXACT>
-ACOC_HD int backward_instance(const Problem& P, const double* X, const double* U, double* KSG, int i)
+template <bool EXACT, typename F, typename XT>
+ACOC_HD int backward_instance(const ProblemT<F>& P, const XT* X, const F* U, F* KSG, int i)
 {
     const int TT = P.TT, Np = P.Np;
-    double Pm[21], p[NS], lam[NS], x[NS], u[NI], xr[NS], ur[NI], dx[NS], du[NI], q[NS], r[NI];
+    F Pm[21], p[NS], lam[NS], x[NS], u[NI], xr[NS], ur[NI], dx[NS], du[NI], q[NS], r[NI];
     // terminal condition: lam_{T-1} = QT dx (optcon.py:429-432), P_{T-1} = QT, p_{T-1} = lam/2 (:688-690, :716)
     load_xref(P, TT - 1, i, xr);
+    load_x(P, X, TT - 1, i, x);
 #pragma unroll
-    for (int c = 0; c < NS; ++c) dx[c] = X[at(TT - 1, NS, c, Np, i)] - xr[c];
+    for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
     wmul6(P.W.QT, P.W.diag, dx, lam);
 #pragma unroll
     for (int a = 0; a < NS; ++a) {
-        p[a] = 0.5 * lam[a];
+        p[a] = F(0.5) * lam[a];
 #pragma unroll
-        for (int b = a; b < NS; ++b) Pm[sym(a, b)] = P.W.diag ? (a == b ? P.W.QT[a * 7] : 0.0) : P.W.QT[a * 6 + b];
+        for (int b = a; b < NS; ++b) Pm[sym(a, b)] = P.W.diag ? (a == b ? P.W.QT[a * 7] : F(0.0)) : P.W.QT[a * 6 + b];
     }
     int nreg = 0;
     // software prefetch: the loads of step t-1 are issued before the arithmetic of step t
-    double nx[NS], nu[NI], nxr[NS], nur[NI];
+    XT nx[NS];
+    F nu[NI], nxr[NS], nur[NI];
     {
         const int t = TT - 2;
         load_ref(P, t, i, nxr, nur);
-#pragma unroll
-        for (int c = 0; c < NS; ++c) nx[c] = X[at(t, NS, c, Np, i)];
+        load_x_raw(X, t, Np, i, nx);
 #pragma unroll
         for (int c = 0; c < NI; ++c) nu[c] = U[at(t, NI, c, Np, i)];
     }
     for (int t = TT - 2; t >= 0; --t) {
+        finish_x(P, t, i, nx, x);
 #pragma unroll
-        for (int c = 0; c < NS; ++c) { x[c] = nx[c]; xr[c] = nxr[c]; }
+        for (int c = 0; c < NS; ++c) xr[c] = nxr[c];
 #pragma unroll
         for (int c = 0; c < NI; ++c) { u[c] = nu[c]; ur[c] = nur[c]; }
         if (t > 0) {
             load_ref(P, t - 1, i, nxr, nur);
-#pragma unroll
-            for (int c = 0; c < NS; ++c) nx[c] = X[at(t - 1, NS, c, Np, i)];
+            load_x_raw(X, t - 1, Np, i, nx);
 #pragma unroll
             for (int c = 0; c < NI; ++c) nu[c] = U[at(t - 1, NI, c, Np, i)];
         }
@@ -245,12 +297,12 @@ ACOC_HD int backward_instance(const Problem& P, const double* X, const double* U
         for (int c = 0; c < NI; ++c) du[c] = u[c] - ur[c];
         wmul6(P.W.Q, P.W.diag, dx, q);   // lx = Q dx   (aircraft_simplified.py:63)
         wmul2(P.W.R, P.W.diag, du, r);   // lu = R du   (:64)
-        const Trig tg = make_trig(x);
-        const Lin l = linearize(P.M, x, u, tg);
-        Hess h;
+        const Trig<F> tg = make_trig(x);
+        const Lin<F> l = linearize(P.M, x, u, tg);
+        Hess<F> h;
         if (EXACT) h = hess_contract(P.M, x, u, tg, l, lam);
-        double K[2 * NS], sig[NI], g[NI];
-        nreg += riccati_step<EXACT>(P.M, P.W, l, h, q, r, Pm, p, lam, K, sig, g);
+        F K[2 * NS], sig[NI], g[NI];
+        nreg += riccati_step<EXACT, F>(P.M, P.W, l, h, q, r, Pm, p, lam, K, sig, g);
 #pragma unroll
         for (int c = 0; c < 12; ++c) KSG[at(t, 16, c, Np, i)] = K[c];
         KSG[at(t, 16, 12, Np, i)] = sig[0]; KSG[at(t, 16, 13, Np, i)] = sig[1];
@@ -266,20 +318,23 @@ ACOC_HD int backward_instance(const Problem& P, const double* X, const double* U
 // descent = sum_t g_t' du_t (optcon.py:474-477).  A_t, B_t are recomputed from (x_t,u_t) instead of being
 // stored by the backward sweep (12 doubles per step of HBM traffic saved for ~60 flops and two sincos).
 // DX (optional, [TT][6][Np]) receives the state increments for the drop-in ltv_LQR-style outputs.
-ACOC_HD double forward_lq_instance(const Problem& P, const double* X, const double* U, const double* KSG, double* DU, double* DX, int i)
+template <typename F, typename XT>
+ACOC_HD double forward_lq_instance(const ProblemT<F>& P, const XT* X, const F* U, const F* KSG, F* DU, F* DX, int i)
 {
     const int TT = P.TT, Np = P.Np;
-    double dx[NS] = {0, 0, 0, 0, 0, 0}, x[NS], u[NI], du[NI], descent = 0.0;
+    F dx[NS] = {0, 0, 0, 0, 0, 0}, x[NS], u[NI], du[NI];
+    double descent = 0.0;
     for (int t = 0; t < TT - 1; ++t) {
-#pragma unroll
-        for (int c = 0; c < NS; ++c) x[c] = X[at(t, NS, c, Np, i)];
+        XT xraw[NS];
+        load_x_raw(X, t, Np, i, xraw);
 #pragma unroll
         for (int c = 0; c < NI; ++c) u[c] = U[at(t, NI, c, Np, i)];
-        double K[12];
+        F K[12];
 #pragma unroll
         for (int c = 0; c < 12; ++c) K[c] = KSG[at(t, 16, c, Np, i)];
-        const double s0 = KSG[at(t, 16, 12, Np, i)], s1 = KSG[at(t, 16, 13, Np, i)];
-        const double g0 = KSG[at(t, 16, 14, Np, i)], g1 = KSG[at(t, 16, 15, Np, i)];
+        const F s0 = KSG[at(t, 16, 12, Np, i)], s1 = KSG[at(t, 16, 13, Np, i)];
+        const F g0 = KSG[at(t, 16, 14, Np, i)], g1 = KSG[at(t, 16, 15, Np, i)];
+        finish_x(P, t, i, xraw, x);  // conversion after every load of the step has been issued
         if (DX) {
 #pragma unroll
             for (int c = 0; c < NS; ++c) DX[at(t, NS, c, Np, i)] = dx[c];
@@ -289,10 +344,10 @@ ACOC_HD double forward_lq_instance(const Problem& P, const double* X, const doub
         for (int c = 0; c < NS; ++c) { du[0] = fma_(K[c], dx[c], du[0]); du[1] = fma_(K[NS + c], dx[c], du[1]); }
         DU[at(t, NI, 0, Np, i)] = du[0];
         DU[at(t, NI, 1, Np, i)] = du[1];
-        descent = fma_(g1, du[1], fma_(g0, du[0], descent));
-        const Trig tg = make_trig(x);
-        const Lin l = linearize(P.M, x, u, tg);
-        double nx[NS];
+        descent = fma_((double)g1, (double)du[1], fma_((double)g0, (double)du[0], descent));
+        const Trig<F> tg = make_trig(x);
+        const Lin<F> l = linearize(P.M, x, u, tg);
+        F nx[NS];
         nx[0] = fma_(l.a05, dx[5], fma_(l.a02, dx[2], dx[0]));
         nx[1] = fma_(l.a15, dx[5], fma_(l.a12, dx[2], dx[1]));
         nx[2] = fma_(l.b20, du[0], fma_(l.a25, dx[5], fma_(l.a23, dx[3], l.a22 * dx[2])));
@@ -302,8 +357,8 @@ ACOC_HD double forward_lq_instance(const Problem& P, const double* X, const doub
 #pragma unroll
         for (int c = 0; c < NS; ++c) dx[c] = nx[c];
     }
-    DU[at(TT - 1, NI, 0, Np, i)] = 0.0;  // uuout[:, TT-1] stays zero (optcon.py:694)
-    DU[at(TT - 1, NI, 1, Np, i)] = 0.0;
+    DU[at(TT - 1, NI, 0, Np, i)] = F(0.0);  // uuout[:, TT-1] stays zero (optcon.py:694)
+    DU[at(TT - 1, NI, 1, Np, i)] = F(0.0);
     if (DX) {
 #pragma unroll
         for (int c = 0; c < NS; ++c) DX[at(TT - 1, NS, c, Np, i)] = dx[c];
@@ -314,19 +369,20 @@ ACOC_HD double forward_lq_instance(const Problem& P, const double* X, const doub
 // ------------------------------------------------------------------------------------------------------
 // open-loop rollout of u' = u + s*du from x0: one Armijo candidate (COST) and/or get_update (WRITE)
 // ------------------------------------------------------------------------------------------------------
-template <bool WRITE, bool COST, bool Q32>
-ACOC_HD double rollout_instance(const Problem& P, const double* U, const double* DU, double s, double* Xn, double* Un, int i)
+template <bool WRITE, bool COST, bool Q32, typename F, typename XT>
+ACOC_HD double rollout_instance(const ProblemT<F>& P, const F* U, const F* DU, double step, XT* Xn, F* Un, int i)
 {
     const int TT = P.TT, Np = P.Np;
-    double x[NS], xn[NS], u[NI], xr[NS], ur[NI], dx[NS], du[NI], J = 0.0;
+    const F s = (F)step;
+    F x[NS], xn[NS], u[NI], xr[NS], ur[NI], dx[NS], du[NI];
+    double J = 0.0;
 #pragma unroll
     for (int c = 0; c < NS; ++c) x[c] = P.x0[(size_t)c * Np + i];
     for (int t = 0; t < TT - 1; ++t) {
 #pragma unroll
         for (int c = 0; c < NI; ++c) u[c] = U[at(t, NI, c, Np, i)] + s * DU[at(t, NI, c, Np, i)];  // optcon.py:197 / :253
         if (WRITE) {
-#pragma unroll
-            for (int c = 0; c < NS; ++c) Xn[at(t, NS, c, Np, i)] = x[c];
+            store_x(Xn, t, Np, i, x);
 #pragma unroll
             for (int c = 0; c < NI; ++c) Un[at(t, NI, c, Np, i)] = u[c];
         }
@@ -336,24 +392,23 @@ ACOC_HD double rollout_instance(const Problem& P, const double* U, const double*
             for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
 #pragma unroll
             for (int c = 0; c < NI; ++c) du[c] = u[c] - ur[c];
-            J += stage_cost(P.W, dx, du);
+            J += (double)stage_cost(P.W, dx, du);
         }
-        const Trig tg = make_trig(x);
+        const Trig<F> tg = make_trig(x);
         next_state<Q32>(P.M, x, u, tg, xn);
 #pragma unroll
         for (int c = 0; c < NS; ++c) x[c] = xn[c];
     }
     if (WRITE) {
-#pragma unroll
-        for (int c = 0; c < NS; ++c) Xn[at(TT - 1, NS, c, Np, i)] = x[c];
-        Un[at(TT - 1, NI, 0, Np, i)] = 0.0;  // uu_temp[:, TT-1] is never written (optcon.py:193)
-        Un[at(TT - 1, NI, 1, Np, i)] = 0.0;
+        store_x(Xn, TT - 1, Np, i, x);
+        Un[at(TT - 1, NI, 0, Np, i)] = F(0.0);  // uu_temp[:, TT-1] is never written (optcon.py:193)
+        Un[at(TT - 1, NI, 1, Np, i)] = F(0.0);
     }
     if (COST) {
         load_xref(P, TT - 1, i, xr);
 #pragma unroll
         for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
-        J += term_cost(P.W, dx);
+        J += (double)term_cost(P.W, dx);
     }
     return J;
 }
@@ -427,70 +482,71 @@ ACOC_HD void newton_finish_instance(const NewtonOpts& O, const NewtonState& S, d
 // closed-loop tracking rollout, lqr_tracking.py:279-281: u = u_opt + K (x - x_opt) with shared K, nominal
 // ------------------------------------------------------------------------------------------------------
 // Kt: [TT][12] (row-major 2x6), xopt [TT][6], uopt [TT][2] shared by all instances; x_start [6][Np].
-template <bool Q32>
-ACOC_HD void track_instance(const Problem& P, const double* Kt, const double* xopt, const double* uopt,
-                            const double* xstart, double* Xn, double* Un, int i)
+template <bool Q32, typename F, typename XT>
+ACOC_HD void track_instance(const ProblemT<F>& P, const F* Kt, const F* xopt, const F* uopt,
+                            const F* xstart, XT* Xn, F* Un, int i)
 {
     const int TT = P.TT, Np = P.Np;
-    double x[NS], xn[NS], u[NI];
+    F x[NS], xn[NS], u[NI];
 #pragma unroll
     for (int c = 0; c < NS; ++c) x[c] = xstart[(size_t)c * Np + i];
     for (int t = 0; t < TT - 1; ++t) {
-        const double* K = Kt + (size_t)t * 12;
+        const F* K = Kt + (size_t)t * 12;
         // K@(x - x_opt): plain sums in index order (the reference's 2x6 matvec), then u_opt + (.)
 #pragma unroll
         for (int a = 0; a < NI; ++a) {
-            double s = 0.0;
+            F s = F(0.0);
 #pragma unroll
             for (int c = 0; c < NS; ++c) s += K[a * NS + c] * (x[c] - xopt[t * NS + c]);
             u[a] = uopt[t * NI + a] + s;
         }
-#pragma unroll
-        for (int c = 0; c < NS; ++c) Xn[at(t, NS, c, Np, i)] = x[c];
+        store_x(Xn, t, Np, i, x);
 #pragma unroll
         for (int c = 0; c < NI; ++c) Un[at(t, NI, c, Np, i)] = u[c];
-        const Trig tg = make_trig(x);
+        const Trig<F> tg = make_trig(x);
         next_state<Q32>(P.M, x, u, tg, xn);
 #pragma unroll
         for (int c = 0; c < NS; ++c) x[c] = xn[c];
     }
-#pragma unroll
-    for (int c = 0; c < NS; ++c) Xn[at(TT - 1, NS, c, Np, i)] = x[c];
-    Un[at(TT - 1, NI, 0, Np, i)] = 0.0;
-    Un[at(TT - 1, NI, 1, Np, i)] = 0.0;
+    store_x(Xn, TT - 1, Np, i, x);
+    Un[at(TT - 1, NI, 0, Np, i)] = F(0.0);
+    Un[at(TT - 1, NI, 1, Np, i)] = F(0.0);
 }
 
 // ------------------------------------------------------------------------------------------------------
 // initial guess, aircraft_simplified.py:126-148 (float64 arithmetic; see DESIGN.md "initial guess")
 // ------------------------------------------------------------------------------------------------------
 // dx0 (optional, [6][Np]): start from xx_ref[:,0] + dx0 instead (perturbed-initial-state batches, config 5)
-template <bool Q32>
-ACOC_HD void init_guess_instance(const Problem& P, double kp, double kt, const double* dx0, double* Xn, double* Un, int i)
+// x0_out (optional, [6][Np], may alias dx0): receives the exact start state (row 0 of a float X slot is not exact)
+template <bool Q32, typename F, typename XT>
+ACOC_HD void init_guess_instance(const ProblemT<F>& P, F kp, F kt, const F* dx0, XT* Xn, F* Un, F* x0_out, int i)
 {
     const int TT = P.TT, Np = P.Np;
-    double x[NS], xn[NS], u[NI], xr[NS];
+    F x[NS], xn[NS], u[NI], xr[NS];
     load_xref(P, 0, i, x);  // x_temp = xx_ref[:,0]  (:139)
     if (dx0) {
 #pragma unroll
         for (int c = 0; c < NS; ++c) x[c] += dx0[(size_t)c * Np + i];
     }
+    if (x0_out) {
+#pragma unroll
+        for (int c = 0; c < NS; ++c) x0_out[(size_t)c * Np + i] = x[c];
+    }
     for (int t = 0; t < TT - 1; ++t) {
         load_xref(P, t + 1, i, xr);
         u[0] = kp * ((x[0] - xr[0]) + (x[1] - xr[1]));   // :143
         u[1] = kt * ((x[3] - xr[3]) + (x[5] - xr[5]));   // :144
-#pragma unroll
-        for (int c = 0; c < NS; ++c) Xn[at(t, NS, c, Np, i)] = x[c];
+        store_x(Xn, t, Np, i, x);
 #pragma unroll
         for (int c = 0; c < NI; ++c) Un[at(t, NI, c, Np, i)] = u[c];
-        const Trig tg = make_trig(x);
+        const Trig<F> tg = make_trig(x);
         next_state<Q32>(P.M, x, u, tg, xn);
 #pragma unroll
         for (int c = 0; c < NS; ++c) x[c] = xn[c];
     }
-#pragma unroll
-    for (int c = 0; c < NS; ++c) Xn[at(TT - 1, NS, c, Np, i)] = x[c];
-    Un[at(TT - 1, NI, 0, Np, i)] = 0.0;
-    Un[at(TT - 1, NI, 1, Np, i)] = 0.0;
+    store_x(Xn, TT - 1, Np, i, x);
+    Un[at(TT - 1, NI, 0, Np, i)] = F(0.0);
+    Un[at(TT - 1, NI, 1, Np, i)] = F(0.0);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -502,9 +558,9 @@ ACOC_HD void init_guess_instance(const Problem& P, double kp, double kt, const d
 ACOC_HD void step_sample(const Model& M, bool q32, const double* x, const double* u, const double* lam,
                          double* xxp, double* A, double* B, double* fxx, double* fux)
 {
-    const Trig tg = make_trig(x);
+    const Trig<double> tg = make_trig(x);
     if (xxp) { if (q32) next_state<true>(M, x, u, tg, xxp); else next_state<false>(M, x, u, tg, xxp); }
-    const Lin l = linearize(M, x, u, tg);
+    const Lin<double> l = linearize(M, x, u, tg);
     if (A) {
         for (int e = 0; e < 36; ++e) A[e] = 0.0;
         A[0] = 1.0; A[2] = l.a02; A[5] = l.a05;
@@ -520,7 +576,7 @@ ACOC_HD void step_sample(const Model& M, bool q32, const double* x, const double
     }
     if (!fxx && !fux) return;
     if (lam) {
-        const Hess h = hess_contract(M, x, u, tg, l, lam);
+        const Hess<double> h = hess_contract(M, x, u, tg, l, lam);
         if (fxx) {
             for (int e = 0; e < 36; ++e) fxx[e] = 0.0;
             fxx[2 * 6 + 2] = h.h22; fxx[2 * 6 + 3] = h.h23; fxx[3 * 6 + 2] = h.h23; fxx[2 * 6 + 5] = h.h25; fxx[5 * 6 + 2] = h.h25;
@@ -538,7 +594,7 @@ ACOC_HD void step_sample(const Model& M, bool q32, const double* x, const double
         for (int c = 0; c < 4; ++c) {
             double e6[NS] = {0, 0, 0, 0, 0, 0};
             e6[ks[c]] = 1.0;
-            const Hess h = hess_contract(M, x, u, tg, l, e6);
+            const Hess<double> h = hess_contract(M, x, u, tg, l, e6);
             const int k = ks[c];
             if (fxx) {
                 fxx[(2 * 6 + 2) * 6 + k] = h.h22; fxx[(2 * 6 + 3) * 6 + k] = h.h23; fxx[(3 * 6 + 2) * 6 + k] = h.h23;

@@ -17,6 +17,9 @@
 // Floating-point contract: the translation unit is compiled with -fmad=false (nvcc) / -ffp-contract=off
 // (gcc), so a*b+c is two roundings unless written as fma_().  next_state() and the cost sums use plain
 // operators in the reference's order; the linearisation / Riccati code uses fma_() explicitly.
+//
+// Everything is a template on the arithmetic type F.  F = double is the parity path (all statements above are
+// about it); F = float is the optional FP32 mode of the library (no bit-level contract, tolerance in DESIGN.md).
 #pragma once
 #include <math.h>
 
@@ -33,17 +36,19 @@ constexpr int NI = 2;  // input  [T, M]                       aircraft_simplifie
 
 // Model constants (aircraft_simplified.py:108-118) plus products that the reference forms from python
 // scalars before touching the state; they are computed once on the host with the same operations.
-struct Model {
-    double cd0, cda, cla, m, g, S, rho, J, dt;
-    double half_rho;  // 0.5*rho          (:228, :253)
-    double mg;        // m*g              (:306, :310)
-    double dt_m;      // dt/m             (:306)
-    double k;         // S*rho
-    double cdk, clk;  // cda*k, cla*k
-    double b41;       // dt/J             (:324)
-    double gm;        // g*m              (:318, :321)
-    double rJ;        // RN(1/J): u/J is formed as a correctly rounded division from it (div_const)
+template <typename F>
+struct ModelT {
+    F cd0, cda, cla, m, g, S, rho, J, dt;
+    F half_rho;  // 0.5*rho          (:228, :253)
+    F mg;        // m*g              (:306, :310)
+    F dt_m;      // dt/m             (:306)
+    F k;         // S*rho
+    F cdk, clk;  // cda*k, cla*k
+    F b41;       // dt/J             (:324)
+    F gm;        // g*m              (:318, :321)
+    F rJ;        // RN(1/J): u/J is formed as a correctly rounded division from it (div_const)
 };
+using Model = ModelT<double>;
 
 inline Model make_model(const double* p)
 {
@@ -61,14 +66,42 @@ inline Model make_model(const double* p)
     return M;
 }
 
+// the FP32 mode rounds the float64 constants once
+template <typename F>
+inline ModelT<F> model_as(const Model& m)
+{
+    ModelT<F> o;
+    o.cd0 = (F)m.cd0; o.cda = (F)m.cda; o.cla = (F)m.cla; o.m = (F)m.m; o.g = (F)m.g; o.S = (F)m.S; o.rho = (F)m.rho; o.J = (F)m.J; o.dt = (F)m.dt;
+    o.half_rho = (F)m.half_rho; o.mg = (F)m.mg; o.dt_m = (F)m.dt_m; o.k = (F)m.k; o.cdk = (F)m.cdk; o.clk = (F)m.clk; o.b41 = (F)m.b41;
+    o.gm = (F)m.gm; o.rJ = (F)m.rJ;
+    return o;
+}
+
 // Quadratic weights.  diag != 0 promises that Q, R and QT are diagonal (every shipped configuration,
 // main_newton_method.py:52-63); the dense path keeps the API honest (aircraft_simplified.py:61 takes any matrix).
-struct Weights {
-    double Q[36], R[4], QT[36];
+template <typename F>
+struct WeightsT {
+    F Q[36], R[4], QT[36];
     int diag;
 };
+using Weights = WeightsT<double>;
+
+template <typename F>
+inline WeightsT<F> weights_as(const Weights& w)
+{
+    WeightsT<F> o;
+    for (int e = 0; e < 36; ++e) { o.Q[e] = (F)w.Q[e]; o.QT[e] = (F)w.QT[e]; }
+    for (int e = 0; e < 4; ++e) o.R[e] = (F)w.R[e];
+    o.diag = w.diag;
+    return o;
+}
 
 ACOC_HD double fma_(double a, double b, double c) { return fma(a, b, c); }
+ACOC_HD float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+ACOC_HD double sqrt_(double a) { return sqrt(a); }
+ACOC_HD float sqrt_(float a) { return sqrtf(a); }
+ACOC_HD double abs_(double a) { return fabs(a); }
+ACOC_HD float abs_(float a) { return fabsf(a); }
 
 // ---- sin/cos -------------------------------------------------------------------------------------------
 // Own implementation instead of CUDA's sincos(): same algorithm class (3-term Cody-Waite reduction by pi/2 with
@@ -135,24 +168,57 @@ ACOC_HD void sincos_(double x, double& s, double& c)
     s = a; c = b;
 }
 
+// FP32 mode: same structure in float (Cody-Waite by pi/2 in three parts with FMAs, the cephes sinf/cosf minimax
+// polynomials on [-pi/4, pi/4]); ~1e-7 absolute error.  Huge/NaN arguments: library routine.
+ACOC_HD void sincos_(float x, float& s, float& c)
+{
+    if (!(fabsf(x) < 1.0e4f)) {
+#if defined(__CUDA_ARCH__)
+        sincosf(x, &s, &c);
+#else
+        s = sinf(x); c = cosf(x);
+#endif
+        return;
+    }
+    const float jf = rintf(x * 0x1.45f306p-1f);
+    const int j = (int)jf;
+    float r = fma_(-jf, 0x1.921fb6p+0f, x);
+    r = fma_(-jf, -0x1.777a5cp-25f, r);
+    r = fma_(-jf, -0x1.ee59dap-50f, r);
+    const float z = r * r;
+    const float ps = fma_(z, fma_(z, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f);
+    const float sr = fma_(z * ps, r, r);
+    const float pc = fma_(z, fma_(z, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f);
+    const float cr = fma_(z, fma_(z, pc, -0.5f), 1.0f);
+    float a = (j & 1) ? cr : sr, b = (j & 1) ? sr : cr;
+    if (j & 2) a = -a;
+    if ((j + 1) & 2) b = -b;
+    s = a; c = b;
+}
+
 // a / d for a divisor whose correctly rounded reciprocal rd = RN(1/d) is known: q = RN(a*rd), r = a - q*d (exact, FMA),
 // RN(q + r*rd) is the correctly rounded quotient (Markstein) -- three FMA-pipe operations instead of a division routine.
-ACOC_HD double div_const(double a, double d, double rd)
+template <typename F>
+ACOC_HD F div_const(F a, F d, F rd)
 {
-    const double q = a * rd;
-    const double r = fma_(-q, d, a);
+    const F q = a * rd;
+    const F r = fma_(-q, d, a);
     return fma_(r, rd, q);
 }
 
-// aircraft_simplified.py:300 -- the reference stores the next state in a float32 array.
+// aircraft_simplified.py:300 -- the reference stores the next state in a float32 array.  (FP32 mode: identity.)
 template <bool Q32>
 ACOC_HD double quant_(double v) { return Q32 ? (double)(float)v : v; }
+template <bool Q32>
+ACOC_HD float quant_(float v) { return v; }
 
-struct Trig { double sg, cg, sa, ca, alpha; };
+template <typename F>
+struct Trig { F sg, cg, sa, ca, alpha; };
 
-ACOC_HD Trig make_trig(const double* x)
+template <typename F>
+ACOC_HD Trig<F> make_trig(const F* x)
 {
-    Trig t;
+    Trig<F> t;
     t.alpha = x[3] - x[5];  // :295
     sincos_(x[5], t.sg, t.cg);
     sincos_(t.alpha, t.sa, t.ca);
@@ -160,15 +226,15 @@ ACOC_HD Trig make_trig(const double* x)
 }
 
 // One forward-Euler step, aircraft_simplified.py:303-310, in the reference's evaluation order.
-template <bool Q32>
-ACOC_HD void next_state(const Model& M, const double* x, const double* u, const Trig& t, double* xn)
+template <bool Q32, typename F>
+ACOC_HD void next_state(const ModelT<F>& M, const F* x, const F* u, const Trig<F>& t, F* xn)
 {
-    const double V = x[2];
-    const double V2 = V * V, a2 = t.alpha * t.alpha;
-    const double hv = M.half_rho * V2 * M.S;                       // 0.5*rho*V**2*S
-    const double D = hv * (M.cd0 + M.cda * a2);                    // :228
-    const double L = hv * M.cla * t.alpha;                         // :253
-    const double dtV = M.dt * V;
+    const F V = x[2];
+    const F V2 = V * V, a2 = t.alpha * t.alpha;
+    const F hv = M.half_rho * V2 * M.S;                       // 0.5*rho*V**2*S
+    const F D = hv * (M.cd0 + M.cda * a2);                    // :228
+    const F L = hv * M.cla * t.alpha;                         // :253
+    const F dtV = M.dt * V;
     xn[0] = quant_<Q32>(x[0] + dtV * t.cg);
     xn[1] = quant_<Q32>(x[1] - dtV * t.sg);
     xn[2] = quant_<Q32>(V + M.dt_m * (-D - M.mg * t.sg + u[0] * t.ca));
@@ -178,34 +244,36 @@ ACOC_HD void next_state(const Model& M, const double* x, const double* u, const 
 }
 
 // Non-constant entries of A = df/dx and B = df/du.  Constant ones: A00=A11=A33=A44=1, A34=dt, B41=dt/J.
+template <typename F>
 struct Lin {
-    double a02, a05, a12, a15, a22, a23, a25, a52, a53, a55, b20, b50;
+    F a02, a05, a12, a15, a22, a23, a25, a52, a53, a55, b20, b50;
     // by-products reused by hess_contract()
-    double iV, drag_c, lift, liftT, tsa, tca;
+    F iV, drag_c, lift, liftT, tsa, tca;
 };
 
-ACOC_HD Lin linearize(const Model& M, const double* x, const double* u, const Trig& t)
+template <typename F>
+ACOC_HD Lin<F> linearize(const ModelT<F>& M, const F* x, const F* u, const Trig<F>& t)
 {
-    Lin l;
-    const double V = x[2], T = u[0], al = t.alpha;
-    const double iV = 1.0 / V;
-    const double V2 = V * V;
-    const double dc = fma_(M.cda * al, al, M.cd0);          // Cd0 + Cda*alpha^2
-    const double tsa = T * t.sa, tca = T * t.ca;
-    const double cav = M.cdk * al * V2;                     // Cda*k*alpha*V^2
-    const double lift = 0.5 * M.clk * V2;                   // 0.5*Cla*k*V^2
-    const double dtV = M.dt * V;
+    Lin<F> l;
+    const F V = x[2], T = u[0], al = t.alpha;
+    const F iV = F(1.0) / V;
+    const F V2 = V * V;
+    const F dc = fma_(M.cda * al, al, M.cd0);          // Cd0 + Cda*alpha^2
+    const F tsa = T * t.sa, tca = T * t.ca;
+    const F cav = M.cdk * al * V2;                     // Cda*k*alpha*V^2
+    const F lift = F(0.5) * M.clk * V2;                // 0.5*Cla*k*V^2
+    const F dtV = M.dt * V;
     l.a02 = M.dt * t.cg;
     l.a05 = -dtV * t.sg;
     l.a12 = -M.dt * t.sg;
     l.a15 = -dtV * t.cg;
-    l.a22 = fma_(-M.dt_m * M.k * V, dc, 1.0);
+    l.a22 = fma_(-M.dt_m * M.k * V, dc, F(1.0));
     l.a23 = -M.dt_m * (cav + tsa);
     l.a25 = M.dt_m * (cav + tsa - M.gm * t.cg);
-    const double w = fma_(lift, al, tsa) - M.gm * t.cg;     // lift*alpha + T sin(alpha) - g m cos(gamma)
+    const F w = fma_(lift, al, tsa) - M.gm * t.cg;     // lift*alpha + T sin(alpha) - g m cos(gamma)
     l.a52 = M.dt_m * fma_(-w * iV, iV, M.clk * al);
     l.a53 = M.dt_m * (lift + tca) * iV;
-    l.a55 = fma_(-M.dt_m * (lift + tca - M.gm * t.sg), iV, 1.0);
+    l.a55 = fma_(-M.dt_m * (lift + tca - M.gm * t.sg), iV, F(1.0));
     l.b20 = M.dt_m * t.ca;
     l.b50 = M.dt_m * t.sa * iV;
     l.iV = iV; l.drag_c = dc; l.lift = lift; l.liftT = lift + tca; l.tsa = tsa; l.tca = tca;
@@ -214,28 +282,30 @@ ACOC_HD Lin linearize(const Model& M, const double* x, const double* u, const Tr
 
 // lambda-contracted second-order terms (optcon.py:437 with aircraft_simplified.py:384-388):
 // symmetric block on {V,theta,gamma} = indices {2,3,5} and the thrust row of fux.
-struct Hess { double h22, h23, h25, h33, h35, h55, s2, s3, s5; };
+template <typename F>
+struct Hess { F h22, h23, h25, h33, h35, h55, s2, s3, s5; };
 
-ACOC_HD Hess hess_contract(const Model& M, const double* x, const double* u, const Trig& t, const Lin& l, const double* lam)
+template <typename F>
+ACOC_HD Hess<F> hess_contract(const ModelT<F>& M, const F* x, const F* u, const Trig<F>& t, const Lin<F>& l, const F* lam)
 {
-    Hess h;
-    const double V = x[2], al = t.alpha, iV = l.iV, iV2 = iV * iV;
-    const double l0 = lam[0], l1 = lam[1], l2 = lam[2], l5 = lam[5];
-    const double cv2 = M.cdk * V * V;
+    Hess<F> h;
+    const F V = x[2], al = t.alpha, iV = l.iV, iV2 = iV * iV;
+    const F l0 = lam[0], l1 = lam[1], l2 = lam[2], l5 = lam[5];
+    const F cv2 = M.cdk * V * V;
     // d2 f_V
-    const double v22 = -M.dt_m * M.k * l.drag_c;
-    const double v23 = -M.dt_m * M.cdk * V * (2.0 * al);
-    const double v33 = -M.dt_m * (cv2 + l.tca);
-    const double v55 = -M.dt_m * (cv2 + l.tca - M.gm * t.sg);
+    const F v22 = -M.dt_m * M.k * l.drag_c;
+    const F v23 = -M.dt_m * M.cdk * V * (F(2.0) * al);
+    const F v33 = -M.dt_m * (cv2 + l.tca);
+    const F v55 = -M.dt_m * (cv2 + l.tca - M.gm * t.sg);
     // d2 f_gamma
-    const double w = fma_(l.lift, al, l.tsa) - M.gm * t.cg;
-    const double clkdtm = M.clk * M.dt_m;
-    const double g22 = fma_(2.0 * M.dt_m * w * iV2, iV, -clkdtm * al * iV);
-    const double g23 = fma_(-M.dt_m * l.liftT, iV2, clkdtm);
-    const double g25 = fma_(M.dt_m * (l.liftT - M.gm * t.sg), iV2, -clkdtm);
-    const double g33 = -M.dt_m * l.tsa * iV;
-    const double g55 = -M.dt_m * (l.tsa - M.gm * t.cg) * iV;
-    const double dtV = M.dt * V;
+    const F w = fma_(l.lift, al, l.tsa) - M.gm * t.cg;
+    const F clkdtm = M.clk * M.dt_m;
+    const F g22 = fma_(F(2.0) * M.dt_m * w * iV2, iV, -clkdtm * al * iV);
+    const F g23 = fma_(-M.dt_m * l.liftT, iV2, clkdtm);
+    const F g25 = fma_(M.dt_m * (l.liftT - M.gm * t.sg), iV2, -clkdtm);
+    const F g33 = -M.dt_m * l.tsa * iV;
+    const F g55 = -M.dt_m * (l.tsa - M.gm * t.cg) * iV;
+    const F dtV = M.dt * V;
     h.h22 = fma_(l2, v22, l5 * g22);
     h.h23 = fma_(l2, v23, l5 * g23);
     h.h25 = fma_(l0, -M.dt * t.sg, fma_(l1, -M.dt * t.cg, fma_(l2, -v23, l5 * g25)));
@@ -249,9 +319,10 @@ ACOC_HD Hess hess_contract(const Model& M, const double* x, const double* u, con
 }
 
 // Stage cost (aircraft_simplified.py:61): 0.5*dx'(Q dx) + 0.5*du'(R du), sums in ascending index order.
-ACOC_HD double stage_cost(const Weights& W, const double* dx, const double* du)
+template <typename F>
+ACOC_HD F stage_cost(const WeightsT<F>& W, const F* dx, const F* du)
 {
-    double sx = 0.0, su = 0.0;
+    F sx = F(0.0), su = F(0.0);
     if (W.diag) {
 #pragma unroll
         for (int i = 0; i < NS; ++i) sx += dx[i] * (W.Q[i * 7] * dx[i]);
@@ -260,35 +331,36 @@ ACOC_HD double stage_cost(const Weights& W, const double* dx, const double* du)
     } else {
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
-            double a = 0.0;
+            F a = F(0.0);
 #pragma unroll
             for (int j = 0; j < NS; ++j) a += W.Q[i * 6 + j] * dx[j];
             sx += dx[i] * a;
         }
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
-            double a = 0.0;
+            F a = F(0.0);
 #pragma unroll
             for (int j = 0; j < NI; ++j) a += W.R[i * 2 + j] * du[j];
             su += du[i] * a;
         }
     }
-    return 0.5 * sx + 0.5 * su;
+    return F(0.5) * sx + F(0.5) * su;
 }
 
 // Terminal cost (aircraft_simplified.py:92): ((0.5*dx') QT) dx.
-ACOC_HD double term_cost(const Weights& W, const double* dx)
+template <typename F>
+ACOC_HD F term_cost(const WeightsT<F>& W, const F* dx)
 {
-    double s = 0.0;
+    F s = F(0.0);
     if (W.diag) {
 #pragma unroll
-        for (int j = 0; j < NS; ++j) s += ((0.5 * dx[j]) * W.QT[j * 7]) * dx[j];
+        for (int j = 0; j < NS; ++j) s += ((F(0.5) * dx[j]) * W.QT[j * 7]) * dx[j];
     } else {
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
-            double a = 0.0;
+            F a = F(0.0);
 #pragma unroll
-            for (int i = 0; i < NS; ++i) a += (0.5 * dx[i]) * W.QT[i * 6 + j];
+            for (int i = 0; i < NS; ++i) a += (F(0.5) * dx[i]) * W.QT[i * 6 + j];
             s += a * dx[j];
         }
     }
@@ -296,7 +368,8 @@ ACOC_HD double term_cost(const Weights& W, const double* dx)
 }
 
 // v = W (dx) for a 6x6 weight (gradient lx = Q dx, aircraft_simplified.py:63 / :94)
-ACOC_HD void wmul6(const double* Wm, int diag, const double* dx, double* out)
+template <typename F>
+ACOC_HD void wmul6(const F* Wm, int diag, const F* dx, F* out)
 {
     if (diag) {
 #pragma unroll
@@ -304,7 +377,7 @@ ACOC_HD void wmul6(const double* Wm, int diag, const double* dx, double* out)
     } else {
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
-            double a = 0.0;
+            F a = F(0.0);
 #pragma unroll
             for (int j = 0; j < NS; ++j) a = fma_(Wm[i * 6 + j], dx[j], a);
             out[i] = a;
@@ -312,7 +385,8 @@ ACOC_HD void wmul6(const double* Wm, int diag, const double* dx, double* out)
     }
 }
 
-ACOC_HD void wmul2(const double* Wm, int diag, const double* du, double* out)
+template <typename F>
+ACOC_HD void wmul2(const F* Wm, int diag, const F* du, F* out)
 {
     if (diag) { out[0] = Wm[0] * du[0]; out[1] = Wm[3] * du[1]; }
     else { out[0] = fma_(Wm[1], du[1], Wm[0] * du[0]); out[1] = fma_(Wm[3], du[1], Wm[2] * du[0]); }

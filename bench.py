@@ -43,6 +43,17 @@ FLOPS = dict(backward=2106, forward=126 + 30, cost=107, candidate=159, update=52
 BYTES = dict(backward=128 + 128, forward=128 + 64 + 16, cost=128, candidate=32 + 64, candidate_write=32 + 64 + 64, update=32 + 64 + 64)
 
 
+def moved_bytes(args):
+    """Bytes per instance per time step the kernels actually move in the selected mode.  The parity path stores the float32-quantised
+    states as float (24 instead of 48 B per state read/write, bit-identical results); the FP32 mode halves everything."""
+    if args.precision == "f32":
+        return {k: v // 2 for k, v in BYTES.items()}
+    if args.state == "f32" and args.x_storage == "auto":
+        return dict(backward=BYTES["backward"] - 24, forward=BYTES["forward"] - 24, cost=BYTES["cost"] - 24, candidate=BYTES["candidate"],
+                    candidate_write=BYTES["candidate_write"] - 24, update=BYTES["update"] - 24)
+    return dict(BYTES)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -151,7 +162,10 @@ def config_dict(args, n_per_gpu, world):
                          if args.workload == "step" else
                          "BASELINE.json configs[4]: acrobatic Newton OCP batch (x0 perturbed, bump height zf~U(2.0,3.4), seed 7)"),
             "instances_per_gpu": n_per_gpu, "instances_total": n_per_gpu * world, "TT": TT, "ns": 6, "ni": 2,
-            "state_quant": args.state, "armijo": args.armijo, "armijo_maxiters": 10, "max_iters": 200,
+            "state_quant": args.state, "precision": args.precision,
+            "state_storage": "float32 in HBM (lossless: quantised states are float32 values)" if moved_bytes(args)["backward"] == 232 else
+                             ("float32" if args.precision == "f32" else "float64"),
+            "armijo": args.armijo, "armijo_maxiters": 10, "max_iters": 200,
             "step": "one Newton iteration over the whole batch (iterations W..W+K-1 of the solve)",
             "l2": "working set per GPU (%.1f GB) >> 126 MB L2, no flush needed" % (n_per_gpu * 400e3 / 1e9),
             "parallelism": "instances sharded round-robin, %d per GPU, no hot-path collective" % n_per_gpu}
@@ -176,6 +190,8 @@ def main():
     ap.add_argument("--workload", default="step", choices=["step", "acro"])
     ap.add_argument("--armijo", default="lazy", choices=["lazy", "speculative"])
     ap.add_argument("--state", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"], help="f64 = the parity path (default); f32 = the optional FP32 mode")
+    ap.add_argument("--x-storage", default="auto", choices=["auto", "f64"], help="f64: keep float32-valued states in float64 buffers (A/B)")
     ap.add_argument("--cpu-sample", type=int, default=2048)
     ap.add_argument("--chunks", type=int, default=8, help="sub-batches of the pipelined end-to-end solve")
     ap.add_argument("--no-e2e", action="store_true")
@@ -206,7 +222,7 @@ def main():
     K, W = args.steps, args.warmup
 
     xr, ur, dx0, (Q, R, QT) = make_problem(args.workload, n_total, (rank, world))
-    bn = pkg.BatchedNewton(n, TT=TT, device=local, state=args.state, armijo=args.armijo)
+    bn = pkg.BatchedNewton(n, TT=TT, device=local, state=args.state, armijo=args.armijo, precision=args.precision, x_storage=args.x_storage)
     bn.set_weights(Q, R, QT)
     bn.set_refs(xr, ur)
     bn.init_guess(dx0=dx0)
@@ -275,13 +291,19 @@ def main():
         tot_flops = {"backward": steps_per * n * K * FLOPS["backward"], "forward": steps_per * n * K * FLOPS["forward"],
                      "candidates": cand_flops, "update": steps_per * upd_units * FLOPS["update"]}
         fp64_peak = _lib.measure_fp64_peak(local)
+        MB = moved_bytes(args)
+        moved_ratio = {"backward": MB["backward"] / BYTES["backward"], "forward": MB["forward"] / BYTES["forward"],
+                       "update": MB["update"] / BYTES["update"],
+                       "candidates": ((ncand.size * MB["candidate_write"] + 9 * n_fail * MB["candidate"]) / (ncand.size * BYTES["candidate_write"] + 9 * n_fail * BYTES["candidate"])
+                                      if args.armijo == "lazy" else MB["candidate"] / BYTES["candidate"])}
         tbl = {}
         for k in ("backward", "forward", "candidates", "update"):
             if phases[k] <= 0 or tot_bytes[k] <= 0:
                 continue
             gbs = tot_bytes[k] / (phases[k] * 1e-3) / 1e9
             tfs = tot_flops[k] / (phases[k] * 1e-3) / 1e12
-            tbl[k] = {"ms_per_iteration": per_launch_ms[k], "hbm_gbs": gbs, "hbm_frac": gbs / peaks["hbm_gbs"], "fp64_tflops": tfs, "fp64_frac": tfs / fp64_peak}
+            tbl[k] = {"ms_per_iteration": per_launch_ms[k], "hbm_gbs": gbs, "hbm_frac": gbs / peaks["hbm_gbs"], "fp64_tflops": tfs, "fp64_frac": tfs / fp64_peak,
+                      "hbm_gbs_moved": gbs * moved_ratio[k], "hbm_frac_moved": gbs * moved_ratio[k] / peaks["hbm_gbs"]}
         whole = sum(tot_bytes.values()) / (sum(phases.values()) * 1e-3) / 1e9
         tbl["whole_iteration"] = {"ms_per_iteration": sum(phases.values()) / K, "hbm_gbs": whole, "hbm_frac": whole / peaks["hbm_gbs"]}
         d = tbl[dom]
@@ -303,11 +325,16 @@ def main():
                              "note": "algorithmic = dense ns=6/ni=2 flop count of SURVEY.md 8(d); executed flops are lower (structure-exploiting sweep)"},
                     "per_kernel": tbl, "share_of_step": phases[dom] / max(sum(phases.values()), 1e-9),
                     "algorithmic": {"bytes_per_instance_step": BYTES, "flops_per_instance_step": FLOPS,
-                                    "note": "SURVEY.md 8(d) per-unit figures x (TT-1) x instances per launch"}}
+                                    "note": "SURVEY.md 8(d) per-unit figures x (TT-1) x instances per launch"},
+                    "moved": {"bytes_per_instance_step": MB, "achieved": d["hbm_gbs_moved"], "frac": d["hbm_frac_moved"],
+                              "note": "bytes the kernels move in this mode (float32-valued states stored as float: -24 B per state access); "
+                                      "'achieved'/'frac' above use the SURVEY.md 8(d) float64 accounting, so they can exceed the moved figure"}}
         fp64 = {"peak_tflops_measured": fp64_peak}
 
     # ---- whole solve, device-resident (every instance to the reference's criterion; includes the float32-noise phase
     #      with its full Armijo searches and the thinning tail) ------------------------------------------------------
+    bn.init_guess(dx0=dx0)
+    bn.solve()  # untimed: the first solve allocates the survivor-generation contexts (cudaMalloc inside the timed span otherwise)
     bn.init_guess(dx0=dx0)
     tot_solve = bn.solve()
     tsolve = bn.timing()
@@ -321,7 +348,8 @@ def main():
         import torch
         xs_t = torch.empty((n, 6, TT), dtype=torch.float64, pin_memory=True)
         us_t = torch.empty((n, 2, TT), dtype=torch.float64, pin_memory=True)
-        pn = pkg.PipelinedNewton(n, n_chunks=args.chunks, TT=TT, device=local, state=args.state, armijo=args.armijo)
+        pn = pkg.PipelinedNewton(n, n_chunks=args.chunks, TT=TT, device=local, state=args.state, armijo=args.armijo, precision=args.precision,
+                                 x_storage=args.x_storage)
         pn.set_weights(Q, R, QT)
         pn.solve(xr_p.numpy(), ur_p.numpy(), dx0=dx0, out=(xs_t.numpy(), us_t.numpy()))   # untimed warm-up of the whole path
         barrier()
@@ -362,7 +390,7 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / max(K, 1),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": config_dict(args, n, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "active_after_timed_region": n_active, "instance_iterations_timed": its_done, "whole_solve": whole, "roofline": roofline, "fp64": fp64, "phase_ms": phases, "cpu_baseline": cpu,
                 "device": pkg.device_info(local)["name"], "device_bytes": bn.device_bytes}

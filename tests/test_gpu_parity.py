@@ -326,3 +326,105 @@ def test_survivor_generations_equal_in_place(gpu, oracle):
     o = oracle.newton_batch(xr[idx], ur[idx], xi[idx], ui[idx], Q, R, QT)
     assert np.array_equal(s0["iters"][idx], o["iters"])
     assert relerr(o["xx_star"], x0[idx]) < 1e-9 and relerr(o["uu_star"], u0[idx]) < 1e-9
+
+
+def test_float_state_slots_are_lossless(gpu):
+    """With the float32 state quantisation every stored state is a float32 value, so the library keeps the state iterates as
+    float in HBM.  Forcing float64 buffers (x_storage="f64") must give bit-identical results, histories and statistics --
+    including through survivor generations and for an exact-but-arbitrary float64 x0."""
+    n, TT = 8192, 200
+    xr, ur, Q, R, QT = _random_batch(n, TT, 5, 0.2)
+    dx0 = np.random.default_rng(3).normal(size=(n, 6)) * np.array([.05, .05, .2, .02, .05, .02])  # x0 is not a float32 value
+    out = []
+    for xs_mode in ("auto", "f64"):
+        with gpu.BatchedNewton(n, TT=TT, armijo="lazy", x_storage=xs_mode) as bn:
+            bn.set_weights(Q, R, QT)
+            bn.set_refs(xr, ur)
+            bn.init_guess(dx0=dx0)
+            first = bn.iterate_at(0)
+            total = bn.solve()
+            out.append((total, first, bn.result(), bn.iterate_at(0), bn.iterate_at(1), bn.history(), bn.stats()))
+    a, b = out
+    assert a[0] == b[0]
+    for k in (1, 2, 3, 4):
+        assert np.array_equal(a[k][0], b[k][0]) and np.array_equal(a[k][1], b[k][1]), k
+    assert np.array_equal(a[1][0][:, :, 0], xr[:, :, 0] + dx0)  # the exact float64 x0 comes back, not its float32 rounding
+    for k in ("JJ", "descent", "stepsize", "n_armijo"):
+        assert np.array_equal(a[5][k], b[5][k]), k
+    for k in ("iters", "status", "J", "descent", "n_reg"):
+        assert np.array_equal(a[6][k], b[6][k]), k
+
+
+def test_inexact_initial_states_keep_float64_slots(gpu, oracle):
+    """acoc_set_init with states that are NOT float32 values (nothing the reference would produce, but legal input): the
+    context falls back to float64 state buffers, the first iterate comes back unchanged and the solve matches the oracle."""
+    d = golden("newton_step_f32.npz")
+    n, TT = 8, 1000
+    rng = np.random.default_rng(11)
+    xi = np.repeat(d["xx_init"][None], n, 0)
+    xi[:, :, 1:] += rng.normal(size=(n, 6, TT - 1)) * 1e-7
+    ui = np.repeat(d["uu_init"][None], n, 0) + rng.normal(size=(n, 2, TT)) * 0.1
+    with gpu.BatchedNewton(n, TT=TT, refs_shared=True, armijo="lazy") as bn:
+        bn.set_weights(d["Q"], d["R"], d["QT"])
+        bn.set_refs(d["xx_ref"], d["uu_ref"])
+        bn.set_init(xi, ui)
+        x_back, u_back = bn.iterate_at(0)
+        bn.iterate(6)
+        xs, us = bn.iterate_at(0)
+        h = bn.history()
+    assert np.array_equal(x_back, xi) and np.array_equal(u_back, ui)
+    o = oracle.newton_batch(np.repeat(d["xx_ref"][None], n, 0), np.repeat(d["uu_ref"][None], n, 0), xi, ui, d["Q"], d["R"], d["QT"], n_iters_cap=6)
+    assert np.array_equal(h["stepsize"][:, :6], o["stepsize"][:, :6])
+    assert np.max(np.abs(h["JJ"][:, :6] - o["JJ"][:, :6]) / np.abs(o["JJ"][:, :6])) < 1e-9
+    # (the oracle's capped result is the newest iterate with optimize()'s uu[:, -1] = uu[:, -2] fix-up applied)
+    assert relerr(o["xx_star"], xs) < 1e-9 and relerr(o["uu_star"][:, :, :-1], us[:, :, :-1]) < 1e-9
+
+
+# FP32 mode (ACOC_FP32): stated tolerance against the float64 parity path / the reference
+# (the optimum is flat: where the float32-noise phase of the line search happens to stop moves the states by a few 1e-4; the
+# reference's own float32-state and float64-state variants differ from each other by the same amount)
+FP32_TOL = dict(J_rel=2e-6, x_abs=2e-3, u_rel_range=2e-4)
+
+
+@pytest.mark.parametrize("name", ["newton_step_f32", "newton_acro_f32"])
+def test_fp32_mode_configs_1_2(gpu, name):
+    """Optional FP32 mode on configs 1 and 2: converges by the reference's criterion in about as many iterations as the
+    reference needs with its float32 state (the float64-state variant of the same problem needs 17 / 20), to the same optimum
+    within FP32_TOL."""
+    d = golden(name + ".npz")
+    TT = d["xx_ref"].shape[1]
+    with gpu.BatchedNewton(1, TT=TT, refs_shared=True, armijo="lazy", precision="f32") as bn:
+        bn.set_weights(d["Q"], d["R"], d["QT"])
+        bn.set_refs(d["xx_ref"], d["uu_ref"])
+        bn.set_init(d["xx_init"][None], d["uu_init"][None])
+        bn.solve()
+        xl, ul = bn.iterate_at(0)
+        h, st = bn.history(), bn.stats()
+    k = int(st["iters"][0])
+    assert st["status"][0] == 1 and 0.7 * int(d["iters"]) <= k <= 1.5 * int(d["iters"])
+    assert abs(h["JJ"][0, k - 1] - d["JJ"][-1]) / d["JJ"][-1] < FP32_TOL["J_rel"]
+    assert np.max(np.abs(h["JJ"][0, :8] - d["JJ"][:8]) / d["JJ"][:8]) < 1e-4  # the clean phase follows the same path
+    assert np.max(np.abs(xl[0] - d["xx_last"])) < FP32_TOL["x_abs"]
+    assert np.max(np.abs(ul[0] - d["uu_last"])) < FP32_TOL["u_rel_range"] * np.max(np.abs(d["uu_last"]))
+
+
+def test_fp32_mode_batch_vs_float64_path(gpu):
+    """FP32 mode on a config-4 style batch against the float64 path on the same inputs: every instance converges, final costs
+    and trajectories within FP32_TOL, iteration counts of the same order."""
+    n, TT = 256, 1000
+    xr, ur, Q, R, QT = _random_batch(n, TT, 2024, 1.0)
+    res = {}
+    for prec in ("f64", "f32"):
+        with gpu.BatchedNewton(n, TT=TT, armijo="lazy", precision=prec) as bn:
+            bn.set_weights(Q, R, QT)
+            bn.set_refs(xr, ur)
+            bn.init_guess()
+            bn.solve()
+            res[prec] = (bn.iterate_at(0), bn.stats())
+    (x64, u64), s64 = res["f64"]
+    (x32, u32), s32 = res["f32"]
+    assert np.all(s32["status"] == 1) and np.all(s64["status"] == 1)
+    assert np.max(np.abs(s32["J"] - s64["J"]) / s64["J"]) < FP32_TOL["J_rel"]
+    assert np.max(np.abs(x32 - x64)) < FP32_TOL["x_abs"]
+    assert np.max(np.abs(u32 - u64)) < FP32_TOL["u_rel_range"] * np.max(np.abs(u64))
+    assert 0.6 < s32["iters"].mean() / s64["iters"].mean() < 1.6

@@ -137,3 +137,28 @@ def test_return_slot_quirks(emul):
     assert relerr(d["a_xx_star"], a["xx_star"][0]) < 1e-9 and relerr(d["a_uu_star"], a["uu_star"][0]) < 1e-9
     b = emul.newton_batch(d["xx_ref"], d["uu_ref"], d["b_xx_init"][None], d["b_uu_init"][None], d["Q"], d["R"], d["QT"], state_f64=True)
     assert b["iters"][0] == 1 and b["status"][0] == 1 and not b["xx_star"][0].any() and not b["uu_star"][0].any()
+
+
+def test_float_state_slots_lossless_on_host(emul):
+    """Host replay of the <F = double, XT = float> instantiation (float state slots, exact x0 kept aside) against the
+    <double, double> one: bit-identical histories and results on config 1 (the GPU test repeats this at scale)."""
+    d = golden("newton_step_f32.npz")
+    xi = d["xx_init"].copy()
+    xi[:, 0] += np.array([1e-9, 2e-9, 3e-9, 1e-10, 0.0, 7e-11])  # an x0 that is not a float32 value; later states stay float32
+    a, b = (emul.newton_batch(d["xx_ref"], d["uu_ref"], xi[None], d["uu_init"][None], d["Q"], d["R"], d["QT"], lazy=True, mode=m, n_iters_cap=12)
+            for m in (0, 1))
+    for k in ("JJ", "descent", "stepsize", "n_armijo", "xx_star", "uu_star", "xx_last", "uu_last", "deltau", "K"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["xx_last"][0][:, 0], xi[:, 0])
+
+
+def test_fp32_mode_on_host(emul):
+    """Host replay of the FP32 instantiation on config 1: same convergence behaviour as the reference with its float32 state,
+    same optimum within the tolerance stated for the mode (tests/test_gpu_parity.py FP32_TOL)."""
+    d = golden("newton_step_f32.npz")
+    h = emul.newton_batch(d["xx_ref"], d["uu_ref"], d["xx_init"][None], d["uu_init"][None], d["Q"], d["R"], d["QT"], lazy=True, mode=2)
+    k = int(h["iters"][0])
+    assert h["status"][0] == 1 and 16 <= k <= 35
+    assert abs(h["JJ"][0, k - 1] - d["JJ"][-1]) / d["JJ"][-1] < 2e-6
+    assert np.max(np.abs(h["xx_last"][0] - d["xx_last"])) < 2e-3
+    assert np.max(np.abs(h["uu_last"][0] - d["uu_last"])) < 2e-4 * np.max(np.abs(d["uu_last"]))
