@@ -312,7 +312,7 @@ def main():
         traffic = None
         try:  # DRAM bytes per launch of the dominant kernel from the committed ncu capture, scaled to this instance count
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            traffic = tj.get("k_" + dom)
+            traffic = (tj.get("float_state", {}) if MB["backward"] == 232 else tj).get("k_" + dom) if args.precision == "f64" else None
             if traffic is not None:
                 traffic = traffic * n / tj["instances"]
         except Exception:
