@@ -63,6 +63,10 @@ static int fail(int code, const char* fmt, ...)
 // ======================================================================================================
 constexpr int ST_PAD = 4;  // padding lanes beyond N: never active
 
+// granularity of the active-work list of the sweeps: groups of 2^shift consecutive instances that still contain an active one
+#ifndef ACOC_ACT_SHIFT
+#define ACOC_ACT_SHIFT 5  // whole tiles of 32 instances (one warp): measured 366 ms vs 374 ms (groups of 4) on the config-4 solve
+#endif
 constexpr int BWD_THREADS = 64;
 constexpr int FWD_THREADS = 64;
 constexpr int ROLL_THREADS = 64;
@@ -330,7 +334,7 @@ __global__ void k_to_soa(const double* __restrict__ src, D* __restrict__ dst, in
         if (n < nchunk && t < TT) {
             const double v = tile[threadIdx.x][r];
             const D d = (D)v;
-            dst[((size_t)t * C + c) * Np + n0 + n] = d;
+            dst[Np == 1 ? (size_t)t * C + c : at(t, C, c, Np, n0 + n)] = d;  // Np == 1: a shared reference, plain [TT][C]
             if (row0 && t == 0) row0[(size_t)c * Np + n0 + n] = (R0)v;
             if (inexact && t >= 1 && !((double)d == v) && v == v) *inexact = 1;
         }
@@ -352,7 +356,7 @@ __global__ void k_from_soa(const D* __restrict__ s0, const D* __restrict__ s1, c
             if (dup_last && t == TT - 1 && TT > 1) t = TT - 2;
             const int sl = slot ? slot[n0 + n] : 0;
             const D* s = sl == 0 ? s0 : (sl == 1 ? s1 : s2);
-            tile[r][threadIdx.x] = sl < 0 ? 0.0 : ((row0 && t == 0) ? row0[(size_t)c * Np + n0 + n] : (double)s[((size_t)t * C + c) * Np + n0 + n]);
+            tile[r][threadIdx.x] = sl < 0 ? 0.0 : ((row0 && t == 0) ? row0[(size_t)c * Np + n0 + n] : (double)s[Np == 1 ? (size_t)t * C + c : at(t, C, c, Np, n0 + n)]);
         }
     }
     __syncthreads();
@@ -389,26 +393,33 @@ __global__ void k_result_slot_default(const int* __restrict__ status, int* __res
 // ones untouched).  origin[j] = index in the parent of child instance j.
 constexpr int ST_MOVED = 5;  // the instance continues in a child generation
 
+// element (row r, instance i) of a per-instance array: C == 0 -> plain [rows][Np]; C > 0 -> warp-tiled trajectory with C components,
+// row r = t*C + c
+__device__ __forceinline__ size_t row_elem(int r, int C, int Np, int i)
+{
+    return C == 0 ? (size_t)r * Np + i : at(r / C, C, r % C, Np, i);
+}
+
 // dst[row][j] = src[row][origin[j]]   (coalesced writes, scattered reads)
 template <typename T>
 __global__ void k_gather_rows(const T* __restrict__ src, int src_stride, T* __restrict__ dst, int dst_stride, const int* __restrict__ origin,
-                              int n, int rows)
+                              int n, int rows, int C)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const int o = origin[j];
-    for (int r = blockIdx.y; r < rows; r += gridDim.y) dst[(size_t)r * dst_stride + j] = src[(size_t)r * src_stride + o];
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) dst[row_elem(r, C, dst_stride, j)] = src[row_elem(r, C, src_stride, o)];
 }
 
 // dst[row][origin[j]] = src[row][j]   (fold a finished child generation back into its parent)
 template <typename T>
 __global__ void k_scatter_rows(const T* __restrict__ src, int src_stride, T* __restrict__ dst, int dst_stride, const int* __restrict__ origin,
-                               int n, int rows)
+                               int n, int rows, int C)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const int o = origin[j];
-    for (int r = blockIdx.y; r < rows; r += gridDim.y) dst[(size_t)r * dst_stride + o] = src[(size_t)r * src_stride + j];
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) dst[row_elem(r, C, dst_stride, o)] = src[row_elem(r, C, src_stride, j)];
 }
 
 __global__ void k_mark_moved(int* __restrict__ status, const int* __restrict__ origin, int n)
@@ -982,13 +993,13 @@ static WorkList act_list(acoc_ctx* c)
     WorkList L;
     L.groups = c->act_groups;
     L.count = c->counters + 1;
-    L.shift = 2;  // groups of 4 instances = one 32-byte sector of doubles
+    L.shift = ACOC_ACT_SHIFT;
     return L;
 }
 // rebuild the list of instance groups that still have an active member (start of every iteration)
 static int launch_build_active(acoc_ctx* c)
 {
-    k_build_list<<<1, 1024, 0, c->stream>>>(c->S.status, 0, c->N, 2, c->act_groups, c->counters + 1);
+    k_build_list<<<1, 1024, 0, c->stream>>>(c->S.status, 0, c->N, ACOC_ACT_SHIFT, c->act_groups, c->counters + 1);
     CK(cudaGetLastError());
     ++c->launches;
     return 0;
@@ -1136,22 +1147,23 @@ int acoc_newton_iterate(acoc_ctx* c, int n_iters, int* n_active_out)
 }
 
 // gather/scatter every per-instance row set between a parent and its child; to_child = true: parent -> child
+// C: 0 for plain [rows][Np] arrays (scalars, histories, x0), else the component count of a warp-tiled trajectory (rows = TT*C)
 template <typename T>
-static int move_rows(acoc_ctx* par, acoc_ctx* ch, T* pbuf, T* cbuf, int rows, bool to_child)
+static int move_rows(acoc_ctx* par, acoc_ctx* ch, T* pbuf, T* cbuf, int rows, bool to_child, int C = 0)
 {
     const int n = ch->N;
     dim3 grid((n + 127) / 128, std::min(rows, 2048));
-    if (to_child) k_gather_rows<T><<<grid, 128, 0, par->stream>>>(pbuf, par->Np, cbuf, ch->Np, ch->origin, n, rows);
-    else k_scatter_rows<T><<<grid, 128, 0, par->stream>>>(cbuf, ch->Np, pbuf, par->Np, ch->origin, n, rows);
+    if (to_child) k_gather_rows<T><<<grid, 128, 0, par->stream>>>(pbuf, par->Np, cbuf, ch->Np, ch->origin, n, rows, C);
+    else k_scatter_rows<T><<<grid, 128, 0, par->stream>>>(cbuf, ch->Np, pbuf, par->Np, ch->origin, n, rows, C);
     CK(cudaGetLastError());
     return 0;
 }
 
 // untyped trajectory buffers: rows of float or double
-static int move_rows_e(acoc_ctx* par, acoc_ctx* ch, void* pbuf, void* cbuf, int rows, bool to_child, bool is_float)
+static int move_rows_e(acoc_ctx* par, acoc_ctx* ch, void* pbuf, void* cbuf, int rows, bool to_child, bool is_float, int C)
 {
-    return is_float ? move_rows<float>(par, ch, (float*)pbuf, (float*)cbuf, rows, to_child)
-                    : move_rows<double>(par, ch, (double*)pbuf, (double*)cbuf, rows, to_child);
+    return is_float ? move_rows<float>(par, ch, (float*)pbuf, (float*)cbuf, rows, to_child, C)
+                    : move_rows<double>(par, ch, (double*)pbuf, (double*)cbuf, rows, to_child, C);
 }
 
 // Move the n_active still-iterating instances of `par` into its child generation.  Returns 1 if no child could be made.
@@ -1190,18 +1202,18 @@ static int spawn_child(acoc_ctx* par, int n_active, acoc_ctx** out)
     CK(cudaGetLastError());
     for (int sl = 0; sl < 3; ++sl) {
         if (sl == (par->kk + 1) % 3) continue;  // the "next" slot is overwritten by the child's first update anyway
-        TRY(move_rows_e(par, ch, par->X[sl], ch->X[sl], 6 * TT, true, xf));
-        TRY(move_rows_e(par, ch, par->U[sl], ch->U[sl], 2 * TT, true, ff));
+        TRY(move_rows_e(par, ch, par->X[sl], ch->X[sl], 6 * TT, true, xf, 6));
+        TRY(move_rows_e(par, ch, par->U[sl], ch->U[sl], 2 * TT, true, ff, 2));
     }
     if (par->flags & ACOC_REFS_SHARED) {
         const size_t es = ff ? sizeof(float) : sizeof(double);
         CK(cudaMemcpyAsync(ch->xref, par->xref, (size_t)TT * 6 * es, cudaMemcpyDeviceToDevice, par->stream));
         CK(cudaMemcpyAsync(ch->uref, par->uref, (size_t)TT * 2 * es, cudaMemcpyDeviceToDevice, par->stream));
     } else {
-        TRY(move_rows_e(par, ch, par->xref, ch->xref, 6 * TT, true, ff));
-        TRY(move_rows_e(par, ch, par->uref, ch->uref, 2 * TT, true, ff));
+        TRY(move_rows_e(par, ch, par->xref, ch->xref, 6 * TT, true, ff, 6));
+        TRY(move_rows_e(par, ch, par->uref, ch->uref, 2 * TT, true, ff, 2));
     }
-    TRY(move_rows_e(par, ch, par->x0, ch->x0, 6, true, ff));
+    TRY(move_rows_e(par, ch, par->x0, ch->x0, 6, true, ff, 0));
     TRY(move_rows(par, ch, par->S.Jcur, ch->S.Jcur, 1, true));
     TRY(move_rows(par, ch, par->S.descent, ch->S.descent, 1, true));
     TRY(move_rows(par, ch, par->S.step, ch->S.step, 1, true));
@@ -1224,8 +1236,8 @@ static int fold_child(acoc_ctx* par, acoc_ctx* ch)
     CK(cudaStreamSynchronize(ch->stream));
     const int TT = par->TT, mi = par->O.max_iters;
     for (int sl = 0; sl < 3; ++sl) {
-        TRY(move_rows_e(par, ch, par->X[sl], ch->X[sl], 6 * TT, false, par->x_float));
-        TRY(move_rows_e(par, ch, par->U[sl], ch->U[sl], 2 * TT, false, par->fp32));
+        TRY(move_rows_e(par, ch, par->X[sl], ch->X[sl], 6 * TT, false, par->x_float, 6));
+        TRY(move_rows_e(par, ch, par->U[sl], ch->U[sl], 2 * TT, false, par->fp32, 2));
     }
     TRY(move_rows(par, ch, par->S.Jcur, ch->S.Jcur, 1, false));
     TRY(move_rows(par, ch, par->S.descent, ch->S.descent, 1, false));

@@ -3,9 +3,12 @@
 // Each *_instance() function is the complete body of one kernel for one instance: it walks the horizon
 // sequentially (the Riccati / costate / rollout recurrences are true recurrences, optcon.py:434-464,
 // :719-762, :196-198) with every per-step quantity in registers.  The __global__ wrappers at the bottom map
-// threadIdx -> instance.  Trajectories live in HBM as struct-of-arrays, time-major with the instance index
-// fastest:  X[(t*6 + c)*Np + i],  U[(t*2 + c)*Np + i],  KSG[(t*16 + c)*Np + i]  -- so the 32 lanes of a warp
-// touch 32 consecutive doubles (two full 128-byte lines) on every access.
+// threadIdx -> instance.  Trajectories live in HBM as warp-tiled struct-of-arrays (see at()): time-major, then
+// tiles of 32 consecutive instances, then the component, then the lane:
+//     X[((t*(Np/32) + i/32)*6 + c)*32 + i%32],   U[... *2 ...],   KSG[... *16 ...]
+// so a warp reads ONE contiguous block per array per step (X 1.5 KB as double / 768 B as float, KSG 4 KB), every
+// access is a full 128/256-byte line, and all components of a step sit at compile-time offsets from one base pointer
+// that advances by a constant stride per step (no per-access 64-bit address arithmetic in the time loops).
 //
 // Reference call stack covered:
 //   traj_cost_instance    optcon.py:417-424            cost of the current iterate
@@ -42,29 +45,42 @@ struct ProblemT {
     int TT;        // horizon samples
     int q32;       // 1: round the next state to float32 like aircraft_simplified.py:300
     int ref_shared;  // 1: xref/uref hold one trajectory shared by all instances (stride 1)
-    const F* xref;  // [TT][6][Np] or [TT][6][1]
-    const F* uref;  // [TT][2][Np] or [TT][2][1]
+    const F* xref;  // warp-tiled [TT][Np/32][6][32], or [TT][6] when shared
+    const F* uref;  // warp-tiled [TT][Np/32][2][32], or [TT][2] when shared
     const F* x0;    // [6][Np]   x0 = xx_init[:,0]  (optcon.py:398)
 };
 using Problem = ProblemT<double>;
 
-ACOC_HD size_t at(int t, int C, int c, int Np, int i) { return ((size_t)t * C + c) * (size_t)Np + i; }
-
-template <typename F>
-ACOC_HD void load_ref(const ProblemT<F>& P, int t, int i, F* xr, F* ur)
+constexpr int TILE = 32;  // instances per tile = lanes of a warp; Np is a multiple of it
+// element index of component c (of C) of instance i at time t in a warp-tiled trajectory array
+ACOC_HD size_t at(int t, int C, int c, int Np, int i)
 {
-    const int Nr = P.ref_shared ? 1 : P.Np, ir = P.ref_shared ? 0 : i;
-#pragma unroll
-    for (int c = 0; c < NS; ++c) xr[c] = P.xref[at(t, NS, c, Nr, ir)];
-#pragma unroll
-    for (int c = 0; c < NI; ++c) ur[c] = P.uref[at(t, NI, c, Nr, ir)];
+    return (((size_t)t * (size_t)(Np / TILE) + (size_t)(i / TILE)) * C + c) * TILE + (i % TILE);
 }
+
+// references: per instance (warp-tiled like the trajectories) or one shared trajectory stored time-major [TT][C]
 template <typename F>
 ACOC_HD void load_xref(const ProblemT<F>& P, int t, int i, F* xr)
 {
-    const int Nr = P.ref_shared ? 1 : P.Np, ir = P.ref_shared ? 0 : i;
+    if (P.ref_shared) {
 #pragma unroll
-    for (int c = 0; c < NS; ++c) xr[c] = P.xref[at(t, NS, c, Nr, ir)];
+        for (int c = 0; c < NS; ++c) xr[c] = P.xref[(size_t)t * NS + c];
+    } else {
+#pragma unroll
+        for (int c = 0; c < NS; ++c) xr[c] = P.xref[at(t, NS, c, P.Np, i)];
+    }
+}
+template <typename F>
+ACOC_HD void load_ref(const ProblemT<F>& P, int t, int i, F* xr, F* ur)
+{
+    load_xref(P, t, i, xr);
+    if (P.ref_shared) {
+#pragma unroll
+        for (int c = 0; c < NI; ++c) ur[c] = P.uref[(size_t)t * NI + c];
+    } else {
+#pragma unroll
+        for (int c = 0; c < NI; ++c) ur[c] = P.uref[at(t, NI, c, P.Np, i)];
+    }
 }
 
 // state iterate slot: x_t of instance i (see "Types" above for the t = 0 rule)

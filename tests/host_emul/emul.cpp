@@ -32,7 +32,7 @@ bool to_soa(const double* host, D* dst, int n, int C, int TT, int Np)
             for (int t = 0; t < TT; ++t) {
                 const double v = host[((size_t)i * C + c) * TT + t];
                 const D d = (D)v;
-                dst[((size_t)t * C + c) * Np + i] = d;
+                dst[Np == 1 ? (size_t)t * C + c : at(t, C, c, Np, i)] = d;  // Np == 1: shared reference, plain [TT][C]
                 if (t >= 1 && !((double)d == v) && v == v) inexact = true;
             }
     return inexact;
@@ -43,7 +43,7 @@ void from_soa(const D* src, double* host, int i, int C, int TT, int Np, const R0
 {
     for (int c = 0; c < C; ++c)
         for (int t = 0; t < TT; ++t)
-            host[(size_t)c * TT + t] = (row0 && t == 0) ? (double)row0[(size_t)c * Np + i] : (double)src[((size_t)t * C + c) * Np + i];
+            host[(size_t)c * TT + t] = (row0 && t == 0) ? (double)row0[(size_t)c * Np + i] : (double)src[Np == 1 ? (size_t)t * C + c : at(t, C, c, Np, i)];
 }
 template <typename D>
 void from_soa(const D* src, double* host, int i, int C, int TT, int Np) { from_soa<D, double>(src, host, i, C, TT, Np, nullptr); }
