@@ -25,6 +25,7 @@
 
 #include "../../include/acoc.h"
 #include "acoc_kernels.cuh"
+#include "acoc_tma.cuh"
 
 using namespace acoc;
 
@@ -988,6 +989,22 @@ static int launch_cost_t(acoc_ctx* c)
     return 0;
 }
 static int launch_cost(acoc_ctx* c) { return DISPATCH_FX(c, launch_cost_t, c); }
+// the sweeps run as warp-private TMA pipelines (acoc_tma.cuh) unless the context was created with ACOC_NO_TMA
+static bool use_tma(const acoc_ctx* c) { return ACOC_ACT_SHIFT == 5 && !(c->flags & ACOC_NO_TMA); }
+static TileList tile_list(acoc_ctx* c, bool use_list = true)
+{
+    TileList L;
+    L.tiles = use_list ? c->act_groups : nullptr;
+    L.count = c->counters + 1;
+    return L;
+}
+template <typename K>
+static int prefer_smem(K kernel)
+{
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    return 0;
+}
+
 static WorkList act_list(acoc_ctx* c)
 {
     WorkList L;
@@ -1011,7 +1028,16 @@ static int launch_backward_t(acoc_ctx* c, bool exact)
     const ProblemT<F> P = prob<F>(c);
     const XT* X = (const XT*)c->X[cur];
     const F* U = (const F*)c->U[cur];
-    if (exact) k_backward<true, F, XT><<<g, BWD_THREADS, 0, c->stream>>>(P, act_list(c), X, U, (F*)c->KSG, c->S.status, c->S.n_reg);
+    if (use_tma(c)) {
+        const size_t sm = WarpRing<BWD_STAGES, BwdStage<F, XT>::BYTES>::smem_bytes(BWD_THREADS / 32);
+        if (exact) {
+            TRY(prefer_smem(k_backward_tma<true, F, XT>));
+            k_backward_tma<true, F, XT><<<g, BWD_THREADS, sm, c->stream>>>(P, tile_list(c), X, U, (F*)c->KSG, c->S.status, c->S.n_reg);
+        } else {
+            TRY(prefer_smem(k_backward_tma<false, F, XT>));
+            k_backward_tma<false, F, XT><<<g, BWD_THREADS, sm, c->stream>>>(P, tile_list(c), X, U, (F*)c->KSG, c->S.status, c->S.n_reg);
+        }
+    } else if (exact) k_backward<true, F, XT><<<g, BWD_THREADS, 0, c->stream>>>(P, act_list(c), X, U, (F*)c->KSG, c->S.status, c->S.n_reg);
     else k_backward<false, F, XT><<<g, BWD_THREADS, 0, c->stream>>>(P, act_list(c), X, U, (F*)c->KSG, c->S.status, c->S.n_reg);
     CK(cudaGetLastError());
     ++c->launches;
@@ -1022,9 +1048,14 @@ static int launch_backward(acoc_ctx* c, bool exact) { return DISPATCH_FX(c, laun
 template <typename F, typename XT>
 static int launch_forward_t(acoc_ctx* c)
 {
-    const int cur = c->kk % 3;
-    k_forward<F, XT><<<(c->Np + FWD_THREADS - 1) / FWD_THREADS, FWD_THREADS, 0, c->stream>>>(
-        prob<F>(c), act_list(c), (const XT*)c->X[cur], (const F*)c->U[cur], (const F*)c->KSG, (F*)c->DU, (F*)nullptr, c->S.status, c->S.descent);
+    const int cur = c->kk % 3, g = (c->Np + FWD_THREADS - 1) / FWD_THREADS;
+    if (use_tma(c)) {
+        TRY(prefer_smem(k_forward_tma<F, XT>));
+        k_forward_tma<F, XT><<<g, FWD_THREADS, WarpRing<FWD_STAGES, FwdStage<F, XT>::BYTES>::smem_bytes(FWD_THREADS / 32), c->stream>>>(
+            prob<F>(c), tile_list(c), (const XT*)c->X[cur], (const F*)c->U[cur], (const F*)c->KSG, (F*)c->DU, c->S.status, c->S.descent);
+    } else
+        k_forward<F, XT><<<g, FWD_THREADS, 0, c->stream>>>(prob<F>(c), act_list(c), (const XT*)c->X[cur], (const F*)c->U[cur], (const F*)c->KSG,
+                                                           (F*)c->DU, (F*)nullptr, c->S.status, c->S.descent);
     CK(cudaGetLastError());
     ++c->launches;
     return 0;
@@ -1040,8 +1071,21 @@ static int launch_armijo_t(acoc_ctx* c, bool* lazy_only)
     const F *U = (const F*)c->U[cur], *DU = (const F*)c->DU;
     *lazy_only = false;
     if ((c->flags & ACOC_ARMIJO_LAZY) && nc > 1) {
-        LAUNCH_Q32(c->P.q32, k_candidate0_write, (F, XT), (Np + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, c->stream, P, act_list(c), U, DU,
-                   c->cand_steps, (XT*)c->X[nxt], (F*)c->U[nxt], c->S.status, c->S.Jcand);
+        if (use_tma(c)) {
+            const size_t sm = WarpRing<ROLL_STAGES, RollStage<F>::BYTES>::smem_bytes(ROLL_THREADS / 32);
+            const int g = (Np + ROLL_THREADS - 1) / ROLL_THREADS;
+            if (c->P.q32) {
+                TRY(prefer_smem(k_rollout_write_tma<true, F, XT, 0>));
+                k_rollout_write_tma<true, F, XT, 0><<<g, ROLL_THREADS, sm, c->stream>>>(P, tile_list(c), c->O, c->S, U, DU, c->cand_steps, (XT*)c->X[nxt],
+                                                                                       (F*)c->U[nxt], nullptr, c->kk, 0);
+            } else {
+                TRY(prefer_smem(k_rollout_write_tma<false, F, XT, 0>));
+                k_rollout_write_tma<false, F, XT, 0><<<g, ROLL_THREADS, sm, c->stream>>>(P, tile_list(c), c->O, c->S, U, DU, c->cand_steps, (XT*)c->X[nxt],
+                                                                                        (F*)c->U[nxt], nullptr, c->kk, 0);
+            }
+        } else
+            LAUNCH_Q32(c->P.q32, k_candidate0_write, (F, XT), (Np + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, c->stream, P, act_list(c), U, DU,
+                       c->cand_steps, (XT*)c->X[nxt], (F*)c->U[nxt], c->S.status, c->S.Jcand);
         CK(cudaGetLastError());
         k_lazy_need<<<(N + 255) / 256, 256, 0, c->stream>>>(c->O, c->S, c->cand_steps, N, c->need);
         CK(cudaGetLastError());
@@ -1076,8 +1120,24 @@ static int launch_update_t(acoc_ctx* c, bool lazy_only, bool bookkeeping, bool u
     const int cur = c->kk % 3, nxt = (c->kk + 1) % 3;
     WorkList L = act_list(c);
     if (!use_list) L.groups = nullptr;
-    LAUNCH_Q32(c->P.q32, k_update, (F, XT), (c->Np + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, c->stream, prob<F>(c), L, c->O, c->S,
-               (const F*)c->U[cur], (const F*)c->DU, (XT*)c->X[nxt], (F*)c->U[nxt], lazy_only ? c->need : nullptr, c->kk, bookkeeping ? 1 : 0);
+    if (use_tma(c)) {
+        const size_t sm = WarpRing<ROLL_STAGES, RollStage<F>::BYTES>::smem_bytes(ROLL_THREADS / 32);
+        const int g = (c->Np + ROLL_THREADS - 1) / ROLL_THREADS;
+        const int* only = lazy_only ? c->need : nullptr;
+        if (c->P.q32) {
+            TRY(prefer_smem(k_rollout_write_tma<true, F, XT, 1>));
+            k_rollout_write_tma<true, F, XT, 1><<<g, ROLL_THREADS, sm, c->stream>>>(prob<F>(c), tile_list(c, use_list), c->O, c->S, (const F*)c->U[cur],
+                                                                                   (const F*)c->DU, c->cand_steps, (XT*)c->X[nxt], (F*)c->U[nxt], only,
+                                                                                   c->kk, bookkeeping ? 1 : 0);
+        } else {
+            TRY(prefer_smem(k_rollout_write_tma<false, F, XT, 1>));
+            k_rollout_write_tma<false, F, XT, 1><<<g, ROLL_THREADS, sm, c->stream>>>(prob<F>(c), tile_list(c, use_list), c->O, c->S, (const F*)c->U[cur],
+                                                                                    (const F*)c->DU, c->cand_steps, (XT*)c->X[nxt], (F*)c->U[nxt], only,
+                                                                                    c->kk, bookkeeping ? 1 : 0);
+        }
+    } else
+        LAUNCH_Q32(c->P.q32, k_update, (F, XT), (c->Np + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, c->stream, prob<F>(c), L, c->O, c->S,
+                   (const F*)c->U[cur], (const F*)c->DU, (XT*)c->X[nxt], (F*)c->U[nxt], lazy_only ? c->need : nullptr, c->kk, bookkeeping ? 1 : 0);
     CK(cudaGetLastError());
     ++c->launches;
     return 0;

@@ -267,23 +267,50 @@ ACOC_HD int riccati_step(const ModelT<F>& M, const WeightsT<F>& W, const Lin<F>&
 // ------------------------------------------------------------------------------------------------------
 // KSG[t][0..11] = K_t (row-major 2x6), [12..13] = sigma_t, [14..15] = g_t ; t = 0..TT-2.
 // Returns the number of steps whose gain took the +0.5 I branch.
-template <bool EXACT, typename F, typename XT>
-ACOC_HD int backward_instance(const ProblemT<F>& P, const XT* X, const F* U, F* KSG, int i)
+// terminal condition: lam_{T-1} = QT dx (optcon.py:429-432), P_{T-1} = QT, p_{T-1} = lam/2 (:688-690, :716)
+template <typename F>
+ACOC_HD void backward_terminal(const WeightsT<F>& W, const F* x, const F* xr, F* Pm, F* p, F* lam)
 {
-    const int TT = P.TT, Np = P.Np;
-    F Pm[21], p[NS], lam[NS], x[NS], u[NI], xr[NS], ur[NI], dx[NS], du[NI], q[NS], r[NI];
-    // terminal condition: lam_{T-1} = QT dx (optcon.py:429-432), P_{T-1} = QT, p_{T-1} = lam/2 (:688-690, :716)
-    load_xref(P, TT - 1, i, xr);
-    load_x(P, X, TT - 1, i, x);
+    F dx[NS];
 #pragma unroll
     for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
-    wmul6(P.W.QT, P.W.diag, dx, lam);
+    wmul6(W.QT, W.diag, dx, lam);
 #pragma unroll
     for (int a = 0; a < NS; ++a) {
         p[a] = F(0.5) * lam[a];
 #pragma unroll
-        for (int b = a; b < NS; ++b) Pm[sym(a, b)] = P.W.diag ? (a == b ? P.W.QT[a * 7] : F(0.0)) : P.W.QT[a * 6 + b];
+        for (int b = a; b < NS; ++b) Pm[sym(a, b)] = W.diag ? (a == b ? W.QT[a * 7] : F(0.0)) : W.QT[a * 6 + b];
     }
+}
+
+// one time step of the backward sweep: (x_t, u_t, refs) and the carried (P, p, lam) -> K_t, sigma_t, g_t.  Returns 1 if the
+// gain took the +0.5 I branch.
+template <bool EXACT, typename F>
+ACOC_HD int backward_step(const ModelT<F>& M, const WeightsT<F>& W, const F* x, const F* u, const F* xr, const F* ur, F* Pm, F* p, F* lam,
+                          F* K, F* sig, F* g)
+{
+    F dx[NS], du[NI], q[NS], r[NI];
+#pragma unroll
+    for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
+#pragma unroll
+    for (int c = 0; c < NI; ++c) du[c] = u[c] - ur[c];
+    wmul6(W.Q, W.diag, dx, q);   // lx = Q dx   (aircraft_simplified.py:63)
+    wmul2(W.R, W.diag, du, r);   // lu = R du   (:64)
+    const Trig<F> tg = make_trig(x);
+    const Lin<F> l = linearize(M, x, u, tg);
+    Hess<F> h;
+    if (EXACT) h = hess_contract(M, x, u, tg, l, lam);
+    return riccati_step<EXACT, F>(M, W, l, h, q, r, Pm, p, lam, K, sig, g);
+}
+
+template <bool EXACT, typename F, typename XT>
+ACOC_HD int backward_instance(const ProblemT<F>& P, const XT* X, const F* U, F* KSG, int i)
+{
+    const int TT = P.TT, Np = P.Np;
+    F Pm[21], p[NS], lam[NS], x[NS], u[NI], xr[NS], ur[NI];
+    load_xref(P, TT - 1, i, xr);
+    load_x(P, X, TT - 1, i, x);
+    backward_terminal(P.W, x, xr, Pm, p, lam);
     int nreg = 0;
     // software prefetch: the loads of step t-1 are issued before the arithmetic of step t
     XT nx[NS];
@@ -307,18 +334,8 @@ ACOC_HD int backward_instance(const ProblemT<F>& P, const XT* X, const F* U, F* 
 #pragma unroll
             for (int c = 0; c < NI; ++c) nu[c] = U[at(t - 1, NI, c, Np, i)];
         }
-#pragma unroll
-        for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
-#pragma unroll
-        for (int c = 0; c < NI; ++c) du[c] = u[c] - ur[c];
-        wmul6(P.W.Q, P.W.diag, dx, q);   // lx = Q dx   (aircraft_simplified.py:63)
-        wmul2(P.W.R, P.W.diag, du, r);   // lu = R du   (:64)
-        const Trig<F> tg = make_trig(x);
-        const Lin<F> l = linearize(P.M, x, u, tg);
-        Hess<F> h;
-        if (EXACT) h = hess_contract(P.M, x, u, tg, l, lam);
         F K[2 * NS], sig[NI], g[NI];
-        nreg += riccati_step<EXACT, F>(P.M, P.W, l, h, q, r, Pm, p, lam, K, sig, g);
+        nreg += backward_step<EXACT>(P.M, P.W, x, u, xr, ur, Pm, p, lam, K, sig, g);
 #pragma unroll
         for (int c = 0; c < 12; ++c) KSG[at(t, 16, c, Np, i)] = K[c];
         KSG[at(t, 16, 12, Np, i)] = sig[0]; KSG[at(t, 16, 13, Np, i)] = sig[1];
@@ -334,6 +351,27 @@ ACOC_HD int backward_instance(const ProblemT<F>& P, const XT* X, const F* U, F* 
 // descent = sum_t g_t' du_t (optcon.py:474-477).  A_t, B_t are recomputed from (x_t,u_t) instead of being
 // stored by the backward sweep (12 doubles per step of HBM traffic saved for ~60 flops and two sincos).
 // DX (optional, [TT][6][Np]) receives the state increments for the drop-in ltv_LQR-style outputs.
+// one time step: ksg = (K row-major 2x6, sigma, g) of this step; dx is advanced in place, du returned, descent accumulated
+template <typename F>
+ACOC_HD void forward_step(const ModelT<F>& M, const F* x, const F* u, const F* ksg, F* dx, F* du, double& descent)
+{
+    du[0] = ksg[12]; du[1] = ksg[13];
+#pragma unroll
+    for (int c = 0; c < NS; ++c) { du[0] = fma_(ksg[c], dx[c], du[0]); du[1] = fma_(ksg[NS + c], dx[c], du[1]); }
+    descent = fma_((double)ksg[15], (double)du[1], fma_((double)ksg[14], (double)du[0], descent));
+    const Trig<F> tg = make_trig(x);
+    const Lin<F> l = linearize(M, x, u, tg);
+    F nx[NS];
+    nx[0] = fma_(l.a05, dx[5], fma_(l.a02, dx[2], dx[0]));
+    nx[1] = fma_(l.a15, dx[5], fma_(l.a12, dx[2], dx[1]));
+    nx[2] = fma_(l.b20, du[0], fma_(l.a25, dx[5], fma_(l.a23, dx[3], l.a22 * dx[2])));
+    nx[3] = fma_(M.dt, dx[4], dx[3]);
+    nx[4] = fma_(M.b41, du[1], dx[4]);
+    nx[5] = fma_(l.b50, du[0], fma_(l.a55, dx[5], fma_(l.a53, dx[3], l.a52 * dx[2])));
+#pragma unroll
+    for (int c = 0; c < NS; ++c) dx[c] = nx[c];
+}
+
 template <typename F, typename XT>
 ACOC_HD double forward_lq_instance(const ProblemT<F>& P, const XT* X, const F* U, const F* KSG, F* DU, F* DX, int i)
 {
@@ -345,33 +383,17 @@ ACOC_HD double forward_lq_instance(const ProblemT<F>& P, const XT* X, const F* U
         load_x_raw(X, t, Np, i, xraw);
 #pragma unroll
         for (int c = 0; c < NI; ++c) u[c] = U[at(t, NI, c, Np, i)];
-        F K[12];
+        F ksg[16];
 #pragma unroll
-        for (int c = 0; c < 12; ++c) K[c] = KSG[at(t, 16, c, Np, i)];
-        const F s0 = KSG[at(t, 16, 12, Np, i)], s1 = KSG[at(t, 16, 13, Np, i)];
-        const F g0 = KSG[at(t, 16, 14, Np, i)], g1 = KSG[at(t, 16, 15, Np, i)];
-        finish_x(P, t, i, xraw, x);  // conversion after every load of the step has been issued
+        for (int c = 0; c < 16; ++c) ksg[c] = KSG[at(t, 16, c, Np, i)];
+        finish_x(P, t, i, xraw, x);
         if (DX) {
 #pragma unroll
             for (int c = 0; c < NS; ++c) DX[at(t, NS, c, Np, i)] = dx[c];
         }
-        du[0] = s0; du[1] = s1;
-#pragma unroll
-        for (int c = 0; c < NS; ++c) { du[0] = fma_(K[c], dx[c], du[0]); du[1] = fma_(K[NS + c], dx[c], du[1]); }
+        forward_step(P.M, x, u, ksg, dx, du, descent);
         DU[at(t, NI, 0, Np, i)] = du[0];
         DU[at(t, NI, 1, Np, i)] = du[1];
-        descent = fma_((double)g1, (double)du[1], fma_((double)g0, (double)du[0], descent));
-        const Trig<F> tg = make_trig(x);
-        const Lin<F> l = linearize(P.M, x, u, tg);
-        F nx[NS];
-        nx[0] = fma_(l.a05, dx[5], fma_(l.a02, dx[2], dx[0]));
-        nx[1] = fma_(l.a15, dx[5], fma_(l.a12, dx[2], dx[1]));
-        nx[2] = fma_(l.b20, du[0], fma_(l.a25, dx[5], fma_(l.a23, dx[3], l.a22 * dx[2])));
-        nx[3] = fma_(P.M.dt, dx[4], dx[3]);
-        nx[4] = fma_(P.M.b41, du[1], dx[4]);
-        nx[5] = fma_(l.b50, du[0], fma_(l.a55, dx[5], fma_(l.a53, dx[3], l.a52 * dx[2])));
-#pragma unroll
-        for (int c = 0; c < NS; ++c) dx[c] = nx[c];
     }
     DU[at(TT - 1, NI, 0, Np, i)] = F(0.0);  // uuout[:, TT-1] stays zero (optcon.py:694)
     DU[at(TT - 1, NI, 1, Np, i)] = F(0.0);
@@ -385,12 +407,31 @@ ACOC_HD double forward_lq_instance(const ProblemT<F>& P, const XT* X, const F* U
 // ------------------------------------------------------------------------------------------------------
 // open-loop rollout of u' = u + s*du from x0: one Armijo candidate (COST) and/or get_update (WRITE)
 // ------------------------------------------------------------------------------------------------------
+// one step of a rollout: stage cost of (x_t, u_t) (COST) and x_{t+1} = f(x_t, u_t) in place
+template <bool COST, bool Q32, typename F>
+ACOC_HD void rollout_step(const ModelT<F>& M, const WeightsT<F>& W, F* x, const F* u, const F* xr, const F* ur, double& J)
+{
+    if (COST) {
+        F dx[NS], du[NI];
+#pragma unroll
+        for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
+#pragma unroll
+        for (int c = 0; c < NI; ++c) du[c] = u[c] - ur[c];
+        J += (double)stage_cost(W, dx, du);
+    }
+    const Trig<F> tg = make_trig(x);
+    F xn[NS];
+    next_state<Q32>(M, x, u, tg, xn);
+#pragma unroll
+    for (int c = 0; c < NS; ++c) x[c] = xn[c];
+}
+
 template <bool WRITE, bool COST, bool Q32, typename F, typename XT>
 ACOC_HD double rollout_instance(const ProblemT<F>& P, const F* U, const F* DU, double step, XT* Xn, F* Un, int i)
 {
     const int TT = P.TT, Np = P.Np;
     const F s = (F)step;
-    F x[NS], xn[NS], u[NI], xr[NS], ur[NI], dx[NS], du[NI];
+    F x[NS], u[NI], xr[NS], ur[NI], dx[NS];
     double J = 0.0;
 #pragma unroll
     for (int c = 0; c < NS; ++c) x[c] = P.x0[(size_t)c * Np + i];
@@ -402,18 +443,8 @@ ACOC_HD double rollout_instance(const ProblemT<F>& P, const F* U, const F* DU, d
 #pragma unroll
             for (int c = 0; c < NI; ++c) Un[at(t, NI, c, Np, i)] = u[c];
         }
-        if (COST) {
-            load_ref(P, t, i, xr, ur);
-#pragma unroll
-            for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
-#pragma unroll
-            for (int c = 0; c < NI; ++c) du[c] = u[c] - ur[c];
-            J += (double)stage_cost(P.W, dx, du);
-        }
-        const Trig<F> tg = make_trig(x);
-        next_state<Q32>(P.M, x, u, tg, xn);
-#pragma unroll
-        for (int c = 0; c < NS; ++c) x[c] = xn[c];
+        if (COST) load_ref(P, t, i, xr, ur);
+        rollout_step<COST, Q32>(P.M, P.W, x, u, xr, ur, J);
     }
     if (WRITE) {
         store_x(Xn, TT - 1, Np, i, x);

@@ -1,0 +1,330 @@
+// acoc_tma.cuh -- the time sweeps as warp-private TMA pipelines (sm_100a only; device code).
+//
+// With the warp-tiled layout (acoc_kernels.cuh, at()) everything one warp (= one tile of 32 instances) needs from an
+// array at time t is ONE contiguous block: X 6*32 elements, U/DU/uref 2*32, xref 6*32, KSG 16*32.  Each warp therefore
+// runs its own producer/consumer ring in shared memory: lane 0 issues one bulk asynchronous copy per array and step
+// (cp.async.bulk.shared.global, completion counted in bytes on an mbarrier), S steps ahead of the arithmetic; all lanes
+// wait on the step's mbarrier, read their column of the block from shared memory (conflict-free: lane-contiguous) and
+// hand the stage back with a __syncwarp().  The copies are in flight while the warp computes, independent of how ptxas
+// schedules the loop body, with no staging registers -- the DRAM latency that the plain-load sweeps pay once or twice
+// per time step is hidden by the ring depth.  No CTA-wide barrier exists in these kernels; warps never wait on each other.
+//
+// The arithmetic is the same *_step() code as in the plain sweeps (acoc_kernels.cuh), so results are bit-identical;
+// tests/test_gpu_parity.py runs every parity case through these kernels (they are the default) and A/B against the
+// plain-load kernels (ACOC_NO_TMA).
+#pragma once
+#include <stdint.h>
+
+#include "acoc_kernels.cuh"
+
+namespace acoc {
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// one arrival + the number of bytes the bulk copies of this phase will deliver
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy (TMA, 1-D): 16-byte aligned addresses, size a multiple of 16
+__device__ __forceinline__ void tma_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- warp-private ring ---------------------------------------------------------------------------------------
+// A stage holds up to four blocks (offsets are compile-time); step k uses stage k % S with mbarrier parity (k / S) & 1.
+template <int S, int STAGE_BYTES>
+struct WarpRing {
+    unsigned char* buf;  // S * STAGE_BYTES, 128-byte aligned
+    uint64_t* bar;       // S mbarriers
+    __device__ __forceinline__ void init(unsigned char* smem_base, int warp, int n_warps, int lane)
+    {
+        buf = smem_base + (size_t)warp * (S * STAGE_BYTES);
+        bar = reinterpret_cast<uint64_t*>(smem_base + (size_t)n_warps * (S * STAGE_BYTES)) + warp * S;
+        if (lane == 0) {
+            for (int s = 0; s < S; ++s) mbar_init(bar + s, 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ unsigned char* stage(int k) const { return buf + (k % S) * STAGE_BYTES; }
+    __device__ __forceinline__ uint64_t* barrier(int k) const { return bar + (k % S); }
+    __device__ __forceinline__ void wait(int k) const { mbar_wait(bar + (k % S), (uint32_t)((k / S) & 1)); }
+    static constexpr size_t smem_bytes(int n_warps) { return (size_t)n_warps * (S * STAGE_BYTES + S * sizeof(uint64_t)); }
+};
+
+// tile of this warp from the (tile-granular) work list, or -1
+struct TileList {
+    const int* tiles;  // nullptr: identity
+    const int* count;
+};
+__device__ __forceinline__ int warp_tile(const TileList& L, int w, int Np)
+{
+    if (!L.tiles) return w < Np / TILE ? w : -1;
+    return w < *L.count ? L.tiles[w] : -1;
+}
+
+// first element of the block of tile `tile` at time t in a warp-tiled array with C components
+__device__ __forceinline__ size_t tile_base(int t, int C, int Np, int tile) { return ((size_t)t * (size_t)(Np / TILE) + tile) * C * TILE; }
+
+// =================================================================================================================
+// LQ forward pass + descent (forward_lq_instance): in K/sigma/g, x, u per step; out du
+// =================================================================================================================
+constexpr int FWD_STAGES = 2;
+template <typename F, typename XT>
+struct FwdStage {
+    static constexpr int KSG_B = 16 * TILE * sizeof(F), X_B = NS * TILE * sizeof(XT), U_B = NI * TILE * sizeof(F);
+    static constexpr int KSG_O = 0, X_O = KSG_B, U_O = KSG_B + X_B, BYTES = KSG_B + X_B + U_B;
+};
+
+template <typename F, typename XT>
+__global__ void __launch_bounds__(64) k_forward_tma(ProblemT<F> P, TileList L, const XT* __restrict__ X, const F* __restrict__ U,
+                                                    const F* __restrict__ KSG, F* __restrict__ DU, const int* __restrict__ status,
+                                                    double* __restrict__ descent)
+{
+    using St = FwdStage<F, XT>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int tile = warp_tile(L, blockIdx.x * nw + warp, P.Np);
+    if (tile < 0) return;  // warp-uniform
+    WarpRing<FWD_STAGES, St::BYTES> ring;
+    ring.init(smem, warp, nw, lane);
+    const int TT = P.TT, Np = P.Np, i = tile * TILE + lane, nsteps = TT - 1;
+    const bool live = i < P.N;  // padding lanes of the last tile idle (but keep the warp converged for the ring)
+    auto issue = [&](int t) {   // lane 0: bulk copies of step t into its stage
+        unsigned char* st = ring.stage(t);
+        uint64_t* b = ring.barrier(t);
+        mbar_arrive_expect_tx(b, St::BYTES);
+        tma_load(st + St::KSG_O, KSG + tile_base(t, 16, Np, tile), St::KSG_B, b);
+        tma_load(st + St::X_O, X + tile_base(t, NS, Np, tile), St::X_B, b);
+        tma_load(st + St::U_O, U + tile_base(t, NI, Np, tile), St::U_B, b);
+    };
+    if (lane == 0)
+        for (int t = 0; t < FWD_STAGES && t < nsteps; ++t) issue(t);
+    F dx[NS] = {0, 0, 0, 0, 0, 0};
+    double d = 0.0;
+    for (int t = 0; t < nsteps; ++t) {
+        ring.wait(t);
+        const unsigned char* st = ring.stage(t);
+        F ksg[16], x[NS], u[NI], du[NI];
+        XT xraw[NS];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) ksg[c] = reinterpret_cast<const F*>(st + St::KSG_O)[c * TILE + lane];
+#pragma unroll
+        for (int c = 0; c < NS; ++c) xraw[c] = reinterpret_cast<const XT*>(st + St::X_O)[c * TILE + lane];
+#pragma unroll
+        for (int c = 0; c < NI; ++c) u[c] = reinterpret_cast<const F*>(st + St::U_O)[c * TILE + lane];
+        __syncwarp();  // every lane has read the stage: it can be refilled
+        if (lane == 0 && t + FWD_STAGES < nsteps) issue(t + FWD_STAGES);
+        if (live) {
+            finish_x(P, t, i, xraw, x);
+            forward_step(P.M, x, u, ksg, dx, du, d);
+            DU[at(t, NI, 0, Np, i)] = du[0];
+            DU[at(t, NI, 1, Np, i)] = du[1];
+        }
+    }
+    if (live) {
+        DU[at(TT - 1, NI, 0, Np, i)] = F(0.0);  // uuout[:, TT-1] stays zero (optcon.py:694)
+        DU[at(TT - 1, NI, 1, Np, i)] = F(0.0);
+        if (status[i] == ST_ACTIVE) descent[i] = d;
+    }
+}
+
+// =================================================================================================================
+// rollouts with cost that write the new iterate (rollout_instance<true, true>): candidate 0 of the lazy Armijo search
+// (MODE 0) and get_update with the per-instance step + Newton bookkeeping (MODE 1).  In: u, du, references per step.
+// =================================================================================================================
+constexpr int ROLL_STAGES = 3;
+template <typename F>
+struct RollStage {
+    static constexpr int U_B = NI * TILE * sizeof(F), XR_B = NS * TILE * sizeof(F);
+    static constexpr int U_O = 0, DU_O = U_B, UR_O = 2 * U_B, XR_O = 3 * U_B, BYTES = 3 * U_B + XR_B;
+};
+
+template <bool Q32, typename F, typename XT, int MODE>
+__global__ void __launch_bounds__(64, 7) k_rollout_write_tma(ProblemT<F> P, TileList L, NewtonOpts O, NewtonState S, const F* __restrict__ U,
+                                                          const F* __restrict__ DU, const double* __restrict__ cand_steps,
+                                                          XT* __restrict__ Xn, F* __restrict__ Un, const int* __restrict__ only, int kk,
+                                                          int bookkeeping)
+{
+    using St = RollStage<F>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int tile = warp_tile(L, blockIdx.x * nw + warp, P.Np);
+    if (tile < 0) return;
+    const int TT = P.TT, Np = P.Np, i = tile * TILE + lane, nsteps = TT - 1;
+    const bool act = i < P.N && S.status[i] == ST_ACTIVE;
+    // MODE 1: lanes whose candidate 0 was accepted keep the trajectory already in the next slot (lazy Armijo)
+    const bool roll = act && !(MODE == 1 && only && !only[i]);
+    double J = 0.0;
+    if (__any_sync(0xffffffffu, roll)) {
+        WarpRing<ROLL_STAGES, St::BYTES> ring;
+        ring.init(smem, warp, nw, lane);
+        const bool shared_ref = P.ref_shared != 0;
+        auto issue = [&](int t) {
+            unsigned char* st = ring.stage(t);
+            uint64_t* b = ring.barrier(t);
+            mbar_arrive_expect_tx(b, shared_ref ? 2 * St::U_B : St::BYTES);
+            tma_load(st + St::U_O, U + tile_base(t, NI, Np, tile), St::U_B, b);
+            tma_load(st + St::DU_O, DU + tile_base(t, NI, Np, tile), St::U_B, b);
+            if (!shared_ref) {
+                tma_load(st + St::UR_O, P.uref + tile_base(t, NI, Np, tile), St::U_B, b);
+                tma_load(st + St::XR_O, P.xref + tile_base(t, NS, Np, tile), St::XR_B, b);
+            }
+        };
+        if (lane == 0)
+            for (int t = 0; t < ROLL_STAGES && t < nsteps; ++t) issue(t);
+        const F s = (F)(MODE == 0 ? cand_steps[0] : (act ? S.step[i] : 0.0));
+        F x[NS], u[NI], xr[NS], ur[NI];
+#pragma unroll
+        for (int c = 0; c < NS; ++c) x[c] = (i < P.N) ? P.x0[(size_t)c * Np + i] : F(0.0);
+        for (int t = 0; t < nsteps; ++t) {
+            ring.wait(t);
+            const unsigned char* st = ring.stage(t);
+            F du[NI];
+#pragma unroll
+            for (int c = 0; c < NI; ++c) {
+                u[c] = reinterpret_cast<const F*>(st + St::U_O)[c * TILE + lane];
+                du[c] = reinterpret_cast<const F*>(st + St::DU_O)[c * TILE + lane];
+            }
+            if (!shared_ref) {
+#pragma unroll
+                for (int c = 0; c < NI; ++c) ur[c] = reinterpret_cast<const F*>(st + St::UR_O)[c * TILE + lane];
+#pragma unroll
+                for (int c = 0; c < NS; ++c) xr[c] = reinterpret_cast<const F*>(st + St::XR_O)[c * TILE + lane];
+            }
+            __syncwarp();
+            if (lane == 0 && t + ROLL_STAGES < nsteps) issue(t + ROLL_STAGES);
+            if (roll) {
+                if (shared_ref) load_ref(P, t, i, xr, ur);
+#pragma unroll
+                for (int c = 0; c < NI; ++c) u[c] = u[c] + s * du[c];  // optcon.py:197 / :253
+                store_x(Xn, t, Np, i, x);
+#pragma unroll
+                for (int c = 0; c < NI; ++c) Un[at(t, NI, c, Np, i)] = u[c];
+                rollout_step<true, Q32>(P.M, P.W, x, u, xr, ur, J);
+            }
+        }
+        if (roll) {
+            store_x(Xn, TT - 1, Np, i, x);
+            Un[at(TT - 1, NI, 0, Np, i)] = F(0.0);  // uu_temp[:, TT-1] is never written (optcon.py:193)
+            Un[at(TT - 1, NI, 1, Np, i)] = F(0.0);
+            load_xref(P, TT - 1, i, xr);
+            F dx[NS];
+#pragma unroll
+            for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
+            J += (double)term_cost(P.W, dx);
+        }
+    }
+    if (!act) return;
+    if (MODE == 0) {
+        S.Jcand[i] = J;
+    } else {
+        const double Jn = roll ? J : S.Jcand[i];
+        if (bookkeeping) newton_finish_instance(O, S, Jn, kk, i);
+        else { S.Jcur[i] = Jn; S.iters[i] = kk + 1; }
+    }
+}
+
+// =================================================================================================================
+// fused backward sweep (backward_instance): in x, u, references per step (walking t = TT-2 .. 0); out K/sigma/g
+// =================================================================================================================
+constexpr int BWD_STAGES = 3;
+template <typename F, typename XT>
+struct BwdStage {
+    static constexpr int X_B = NS * TILE * sizeof(XT), U_B = NI * TILE * sizeof(F), XR_B = NS * TILE * sizeof(F);
+    static constexpr int U_O = 0, UR_O = U_B, XR_O = 2 * U_B, X_O = 2 * U_B + XR_B, BYTES = 2 * U_B + XR_B + X_B;
+};
+
+template <bool EXACT, typename F, typename XT>
+__global__ void __launch_bounds__(64) k_backward_tma(ProblemT<F> P, TileList L, const XT* __restrict__ X, const F* __restrict__ U,
+                                                     F* __restrict__ KSG, const int* __restrict__ status, int* __restrict__ n_reg)
+{
+    using St = BwdStage<F, XT>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int tile = warp_tile(L, blockIdx.x * nw + warp, P.Np);
+    if (tile < 0) return;
+    WarpRing<BWD_STAGES, St::BYTES> ring;
+    ring.init(smem, warp, nw, lane);
+    const int TT = P.TT, Np = P.Np, i = tile * TILE + lane, nsteps = TT - 1;
+    const bool live = i < P.N;
+    const bool shared_ref = P.ref_shared != 0;
+    // ring step k <-> time t = TT-2-k
+    auto issue = [&](int k) {
+        const int t = TT - 2 - k;
+        unsigned char* st = ring.stage(k);
+        uint64_t* b = ring.barrier(k);
+        mbar_arrive_expect_tx(b, shared_ref ? St::U_B + St::X_B : St::BYTES);
+        tma_load(st + St::U_O, U + tile_base(t, NI, Np, tile), St::U_B, b);
+        tma_load(st + St::X_O, X + tile_base(t, NS, Np, tile), St::X_B, b);
+        if (!shared_ref) {
+            tma_load(st + St::UR_O, P.uref + tile_base(t, NI, Np, tile), St::U_B, b);
+            tma_load(st + St::XR_O, P.xref + tile_base(t, NS, Np, tile), St::XR_B, b);
+        }
+    };
+    if (lane == 0)
+        for (int k = 0; k < BWD_STAGES && k < nsteps; ++k) issue(k);
+    F Pm[21], p[NS], lam[NS], x[NS], u[NI], xr[NS], ur[NI];
+    int nreg = 0;
+    if (live) {
+        load_xref(P, TT - 1, i, xr);
+        load_x(P, X, TT - 1, i, x);
+        backward_terminal(P.W, x, xr, Pm, p, lam);
+    }
+    for (int k = 0; k < nsteps; ++k) {
+        const int t = TT - 2 - k;
+        ring.wait(k);
+        const unsigned char* st = ring.stage(k);
+        XT xraw[NS];
+#pragma unroll
+        for (int c = 0; c < NS; ++c) xraw[c] = reinterpret_cast<const XT*>(st + St::X_O)[c * TILE + lane];
+#pragma unroll
+        for (int c = 0; c < NI; ++c) u[c] = reinterpret_cast<const F*>(st + St::U_O)[c * TILE + lane];
+        if (!shared_ref) {
+#pragma unroll
+            for (int c = 0; c < NI; ++c) ur[c] = reinterpret_cast<const F*>(st + St::UR_O)[c * TILE + lane];
+#pragma unroll
+            for (int c = 0; c < NS; ++c) xr[c] = reinterpret_cast<const F*>(st + St::XR_O)[c * TILE + lane];
+        }
+        __syncwarp();
+        if (lane == 0 && k + BWD_STAGES < nsteps) issue(k + BWD_STAGES);
+        if (live) {
+            if (shared_ref) load_ref(P, t, i, xr, ur);
+            finish_x(P, t, i, xraw, x);
+            F K[2 * NS], sig[NI], g[NI];
+            nreg += backward_step<EXACT>(P.M, P.W, x, u, xr, ur, Pm, p, lam, K, sig, g);
+            F* out = KSG + tile_base(t, 16, Np, tile) + lane;
+#pragma unroll
+            for (int c = 0; c < 12; ++c) out[c * TILE] = K[c];
+            out[12 * TILE] = sig[0]; out[13 * TILE] = sig[1];
+            out[14 * TILE] = g[0];   out[15 * TILE] = g[1];
+        }
+    }
+    if (live && nreg && status[i] == ST_ACTIVE) n_reg[i] += nreg;
+}
+
+}  // namespace acoc

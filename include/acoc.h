@@ -45,6 +45,8 @@ typedef enum acoc_status {
 #define ACOC_SOLVE_IN_PLACE 8u   /* acoc_newton_solve: never gather the still-iterating instances into a smaller survivor generation */
 #define ACOC_FP32 16u            /* optional FP32 mode: float32 arithmetic and trajectory storage (costs/descent still accumulated in
                                     float64); NOT the parity path -- results agree with the float64 path to a tolerance only */
+#define ACOC_NO_TMA 64u          /* run the sweeps with plain global loads instead of the warp-private TMA (bulk async copy) rings;
+                                    results are bit-identical, this is for A/B measurements */
 #define ACOC_X_F64 32u           /* keep the state iterates in float64 device buffers even when every stored state is a float32 value
                                     (ACOC_STATE_F32); results are bit-identical either way, this only costs bandwidth (A/B tests) */
 
