@@ -242,23 +242,40 @@ class PipelinedNewton:
         stats = dict(iters=np.zeros(N, dtype=np.int32), status=np.zeros(N, dtype=np.int32), J=np.zeros(N), descent=np.zeros(N),
                      n_reg=np.zeros(N, dtype=np.int32))
         errors = []
+        # The host<->device link is the shared resource of the two copy phases, so they are serialised across sub-batches
+        # (uploads in sub-batch order, downloads as sub-batches finish): sub-batch 0 starts iterating as soon as ITS references
+        # have arrived while the others are still uploading, and the downloads trail the solves the same way.  Without this
+        # all sub-batches would copy, then iterate, then copy back in lock-step and nothing would overlap.
+        turn = threading.Condition()
+        state = {"next_upload": 0}
+        download = threading.Lock()
 
         def work(k):
             lo, hi = self.bounds[k], self.bounds[k + 1]
             bn = self.parts[k]
             try:
-                bn.set_refs(xx_ref[lo:hi], uu_ref[lo:hi])
-                if xx_init is not None:
-                    bn.set_init(xx_init[lo:hi], uu_init[lo:hi])
-                else:
+                with turn:
+                    turn.wait_for(lambda: state["next_upload"] == k or errors)
+                try:
+                    bn.set_refs(xx_ref[lo:hi], uu_ref[lo:hi])
+                    if xx_init is not None:
+                        bn.set_init(xx_init[lo:hi], uu_init[lo:hi])
+                finally:
+                    with turn:
+                        state["next_upload"] = k + 1
+                        turn.notify_all()
+                if xx_init is None:
                     bn.init_guess(dx0=None if dx0 is None else dx0[lo:hi])
                 bn.solve()
-                bn.result(out=(xs[lo:hi], us[lo:hi]))
-                st = bn.stats()
+                with download:
+                    bn.result(out=(xs[lo:hi], us[lo:hi]))
+                    st = bn.stats()
                 for key in stats:
                     stats[key][lo:hi] = st[key]
             except Exception as e:  # surfaced after the join
                 errors.append(e)
+                with turn:
+                    turn.notify_all()
 
         threads = [threading.Thread(target=work, args=(k,)) for k in range(len(self.parts))]
         for t in threads:
