@@ -94,10 +94,12 @@ __device__ __forceinline__ size_t tile_base(int t, int C, int Np, int tile) { re
 // LQ forward pass + descent (forward_lq_instance): in K/sigma/g, x, u per step; out du
 // =================================================================================================================
 constexpr int FWD_STAGES = 2;
+// Of the state only V, theta, gamma (components 2, 3, 5) enter the linearisation: the stage holds [V theta] and [gamma].
 template <typename F, typename XT>
 struct FwdStage {
-    static constexpr int KSG_B = 16 * TILE * sizeof(F), X_B = NS * TILE * sizeof(XT), U_B = NI * TILE * sizeof(F);
-    static constexpr int KSG_O = 0, X_O = KSG_B, U_O = KSG_B + X_B, BYTES = KSG_B + X_B + U_B;
+    static constexpr int KSG_B = 16 * TILE * sizeof(F), XC_B = TILE * sizeof(XT), U_B = NI * TILE * sizeof(F);
+    static constexpr int KSG_O = 0, X23_O = KSG_B, X5_O = KSG_B + 2 * XC_B, U_O = KSG_B + 3 * XC_B + (sizeof(XT) == 4 ? 128 : 0),
+                         BYTES_TX = KSG_B + 3 * XC_B + U_B, BYTES = U_O + U_B;
 };
 
 template <typename F, typename XT>
@@ -117,9 +119,10 @@ __global__ void __launch_bounds__(64) k_forward_tma(ProblemT<F> P, TileList L, c
     auto issue = [&](int t) {   // lane 0: bulk copies of step t into its stage
         unsigned char* st = ring.stage(t);
         uint64_t* b = ring.barrier(t);
-        mbar_arrive_expect_tx(b, St::BYTES);
+        mbar_arrive_expect_tx(b, St::BYTES_TX);
         tma_load(st + St::KSG_O, KSG + tile_base(t, 16, Np, tile), St::KSG_B, b);
-        tma_load(st + St::X_O, X + tile_base(t, NS, Np, tile), St::X_B, b);
+        tma_load(st + St::X23_O, X + tile_base(t, NS, Np, tile) + 2 * TILE, 2 * St::XC_B, b);
+        tma_load(st + St::X5_O, X + tile_base(t, NS, Np, tile) + 5 * TILE, St::XC_B, b);
         tma_load(st + St::U_O, U + tile_base(t, NI, Np, tile), St::U_B, b);
     };
     if (lane == 0)
@@ -133,8 +136,10 @@ __global__ void __launch_bounds__(64) k_forward_tma(ProblemT<F> P, TileList L, c
         XT xraw[NS];
 #pragma unroll
         for (int c = 0; c < 16; ++c) ksg[c] = reinterpret_cast<const F*>(st + St::KSG_O)[c * TILE + lane];
-#pragma unroll
-        for (int c = 0; c < NS; ++c) xraw[c] = reinterpret_cast<const XT*>(st + St::X_O)[c * TILE + lane];
+        xraw[0] = xraw[1] = xraw[4] = XT(0);  // X, Z, q do not enter the linearisation
+        xraw[2] = reinterpret_cast<const XT*>(st + St::X23_O)[lane];
+        xraw[3] = reinterpret_cast<const XT*>(st + St::X23_O)[TILE + lane];
+        xraw[5] = reinterpret_cast<const XT*>(st + St::X5_O)[lane];
 #pragma unroll
         for (int c = 0; c < NI; ++c) u[c] = reinterpret_cast<const F*>(st + St::U_O)[c * TILE + lane];
         __syncwarp();  // every lane has read the stage: it can be refilled
