@@ -76,6 +76,7 @@ def _sig(lib):
         "acoc_set_profiling": [vp, i],
         "acoc_measure_fp64_peak": [i, vp],
         "acoc_measure_copy_bw": [i, vp],
+        "acoc_measure_fp64_latency": [i, vp],
     }
     for name, args in table.items():
         fn = getattr(lib, name)
@@ -137,6 +138,12 @@ def device_info(device=0):
 def measure_fp64_peak(device=0) -> float:
     v = C.c_double(0)
     check(lib().acoc_measure_fp64_peak(device, C.addressof(v)))
+    return v.value
+
+
+def measure_fp64_latency(device=0) -> float:
+    v = C.c_double(0)
+    check(lib().acoc_measure_fp64_latency(device, C.addressof(v)))
     return v.value
 
 

@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "acoc_api.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "acoc_kernels.cuh"), os.path.join(HERE, "csrc", "acoc_math.cuh"),
+DEPS = [SRC, os.path.join(HERE, "csrc", "acoc_kernels.cuh"), os.path.join(HERE, "csrc", "acoc_math.cuh"), os.path.join(HERE, "csrc", "acoc_tma.cuh"),
         os.path.join(HERE, "..", "include", "acoc.h")]
 OUT = os.path.join(HERE, "libacoc.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",

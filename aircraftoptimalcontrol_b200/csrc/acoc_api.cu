@@ -456,6 +456,19 @@ __global__ void k_fp64_peak(double* out, int iters, double seed)
     out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+// one warp, one chain of dependent DFMAs: cycles per dependent FP64 operation (the sweeps are bound by this)
+__global__ void k_fp64_latency(double* out, long long* cycles, int iters, double seed)
+{
+    double a = seed + threadIdx.x;
+    const double b = 1.0000001, c = 1e-9;
+    const long long t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < iters; ++i) a = fma(a, b, c);
+    const long long t1 = clock64();
+    out[threadIdx.x] = a;
+    if (threadIdx.x == 0) *cycles = t1 - t0;
+}
+
 __global__ void k_copy(const double2* __restrict__ a, double2* __restrict__ b, size_t n)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
@@ -1646,6 +1659,27 @@ int acoc_measure_fp64_peak(int device, double* tflops)
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
     *tflops = best;
+    return 0;
+}
+
+int acoc_measure_fp64_latency(int device, double* cycles_per_op)
+{
+    REQUIRE(cycles_per_op, "NULL output");
+    TRY(use_device(device));
+    const int iters = 1 << 16;
+    double* out;
+    long long* cyc;
+    CK(cudaMalloc(&out, 32 * sizeof(double)));
+    CK(cudaMalloc(&cyc, sizeof(long long)));
+    long long h = 0, best = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        k_fp64_latency<<<1, 32>>>(out, cyc, iters, 1.0 + rep);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(&h, cyc, sizeof(h), cudaMemcpyDeviceToHost));
+        if (rep == 0 || h < best) best = h;
+    }
+    cudaFree(out); cudaFree(cyc);
+    *cycles_per_op = (double)best / iters;
     return 0;
 }
 

@@ -330,7 +330,7 @@ def main():
                     "moved": {"bytes_per_instance_step": MB, "achieved": d["hbm_gbs_moved"], "frac": d["hbm_frac_moved"],
                               "note": "bytes the kernels move in this mode (float32-valued states stored as float: -24 B per state access); "
                                       "'achieved'/'frac' above use the SURVEY.md 8(d) float64 accounting, so they can exceed the moved figure"}}
-        fp64 = {"peak_tflops_measured": fp64_peak}
+        fp64 = {"peak_tflops_measured": fp64_peak, "dependent_dfma_latency_cycles": _lib.measure_fp64_latency(local)}
 
     # ---- whole solve, device-resident (every instance to the reference's criterion; includes the float32-noise phase
     #      with its full Armijo searches and the thinning tail) ------------------------------------------------------

@@ -186,6 +186,9 @@ int acoc_set_profiling(acoc_ctx* ctx, int on);
 /* FP64 FMA throughput microbenchmark (register-resident DFMA chains on every SM): the measured denominator
  * for the FP64 side of the roofline.  Returns TFLOP/s (2 flops per DFMA). */
 int acoc_measure_fp64_peak(int device, double* tflops);
+/* Cycles per operation of one warp's chain of dependent DFMAs (8.7 on B200): the in-order latency a lone warp of the
+ * sequential sweeps pays per dependent instruction. */
+int acoc_measure_fp64_latency(int device, double* cycles_per_op);
 /* Device copy bandwidth microbenchmark (read + write bytes / time), GB/s. */
 int acoc_measure_copy_bw(int device, double* gbs);
 
