@@ -518,7 +518,10 @@ static int dalloc_bytes(acoc_ctx* c, void** p, size_t bytes)
 {
     void* q = nullptr;
     cudaError_t e = cudaMalloc(&q, bytes);
-    if (e != cudaSuccess) return fail(ACOC_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+        cudaGetLastError();  // clear the per-thread error state: the caller decides what an allocation failure means
+        return fail(ACOC_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
     e = cudaMemsetAsync(q, 0, bytes, c->stream);
     if (e != cudaSuccess) return fail(ACOC_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
     c->allocs.push_back(q);
@@ -1262,7 +1265,10 @@ static int spawn_child(acoc_ctx* par, int n_active, acoc_ctx** out)
     if (n_active > cap) return 1;
     if (!par->child) {
         acoc_ctx* ch = nullptr;
-        if (acoc_ctx_create(par->device, cap, par->TT, par->flags, &ch) != 0) return 1;  // e.g. out of memory: keep iterating in place
+        if (acoc_ctx_create(par->device, cap, par->TT, par->flags, &ch) != 0) {
+            cudaGetLastError();  // a failed cudaMalloc leaves its error behind; the parent simply keeps iterating in place
+            return 1;
+        }
         par->child = ch;
     }
     acoc_ctx* ch = par->child;

@@ -231,10 +231,13 @@ def main():
         bn.iterate(W, count_active=False)
     bn.sync()
 
+    state = {"bn_open": True}
+
     def barrier():
         if dist is not None:
             dist.barrier()
-        bn.sync()
+        if state["bn_open"]:
+            bn.sync()
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -342,6 +345,10 @@ def main():
     whole = {"value": tot_solve / (tsolve["total_ms"] * 1e-3), "unit": UNIT, "device_ms": tsolve["total_ms"], "total_newton_iterations": int(tot_solve),
              "lockstep_iterations": int(bn.stats()["iters"].max()), "gpu_launches": tsolve["launches"], "scope": "this rank"}
 
+    device_bytes = bn.device_bytes
+    bn.close()  # the end-to-end leg below builds its own contexts: release this one (and its survivor generations) first
+    state["bn_open"] = False
+
     # ---- end to end through the public API, host buffers, full solve -----------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -394,9 +401,8 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": config_dict(args, n, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "active_after_timed_region": n_active, "instance_iterations_timed": its_done, "whole_solve": whole, "roofline": roofline, "fp64": fp64, "phase_ms": phases, "cpu_baseline": cpu,
-                "device": pkg.device_info(local)["name"], "device_bytes": bn.device_bytes}
+                "device": pkg.device_info(local)["name"], "device_bytes": device_bytes}
         emit(line)
-    bn.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
