@@ -428,3 +428,29 @@ def test_fp32_mode_batch_vs_float64_path(gpu):
     assert np.max(np.abs(x32 - x64)) < FP32_TOL["x_abs"]
     assert np.max(np.abs(u32 - u64)) < FP32_TOL["u_rel_range"] * np.max(np.abs(u64))
     assert 0.6 < s32["iters"].mean() / s64["iters"].mean() < 1.6
+
+
+def test_tma_rings_and_plain_loads_identical(gpu):
+    """The warp-private TMA rings (default) and the plain-load sweeps (ACOC_NO_TMA) run the same per-step arithmetic: whole solves
+    must agree bit for bit -- ragged batch (padding lanes in the last tile), per-instance references, lazy Armijo with its Gauss-Newton
+    candidate split, survivor generations."""
+    n, TT = 4099, 200
+    xr, ur, Q, R, QT = _random_batch(n, TT, 17, 0.2)
+    out = []
+    for tma in (True, False):
+        with gpu.BatchedNewton(n, TT=TT, armijo="lazy", tma=tma) as bn:
+            bn.set_weights(Q, R, QT)
+            bn.set_refs(xr, ur)
+            bn.init_guess()
+            total = bn.solve()
+            out.append((total, bn.result(), bn.iterate_at(0), bn.history(), bn.stats(), bn.deltau(), bn.gains()))
+    a, b = out
+    assert a[0] == b[0]
+    for k in (1, 2):
+        assert np.array_equal(a[k][0], b[k][0]) and np.array_equal(a[k][1], b[k][1]), k
+    for k in ("JJ", "descent", "stepsize", "n_armijo"):
+        assert np.array_equal(a[3][k], b[3][k]), k
+    for k in ("iters", "status", "J", "descent", "n_reg"):
+        assert np.array_equal(a[4][k], b[4][k]), k
+    act = a[4]["iters"] == a[4]["iters"].max()  # deltau / gains are scratch of the last iteration an instance took part in
+    assert np.array_equal(a[5][act], b[5][act]) and np.array_equal(a[6][0][act], b[6][0][act])
