@@ -30,11 +30,13 @@ class BatchedNewton:
     "f64" forces float64 buffers.  Results are bit-identical; "f64" only costs bandwidth (A/B measurements).
     tma: run the time sweeps as warp-private TMA (bulk asynchronous copy) pipelines (default); False uses plain global loads
     (bit-identical results, A/B measurements).
+    split: sweep a fully active batch that needs more than one round of resident backward CTAs as two tile ranges on two streams
+    (default; identical results, A/B measurements).
     """
 
     def __init__(self, n_instances, TT=1000, device=0, state="f32", refs_shared=False, armijo="speculative", params=None, generations=True,
                  max_iters=200, stepsize_0=1.0, cc=0.5, beta=0.7, armijo_maxiters=10, term_cond=-1e-6, exact_after=8, precision="f64",
-                 x_storage="auto", tma=True):
+                 x_storage="auto", tma=True, split=True):
         if state not in ("f32", "f64"):
             raise ValueError("state must be 'f32' or 'f64'")
         if armijo not in ("speculative", "lazy"):
@@ -48,7 +50,7 @@ class BatchedNewton:
         self.precision = precision
         flags = ((L.STATE_F64 if state == "f64" else 0) | (L.REFS_SHARED if refs_shared else 0) | (L.ARMIJO_LAZY if armijo == "lazy" else 0)
                  | (0 if generations else L.SOLVE_IN_PLACE) | (L.FP32 if precision == "f32" else 0) | (L.X_F64 if x_storage == "f64" else 0)
-                 | (0 if tma else L.NO_TMA))
+                 | (0 if tma else L.NO_TMA) | (0 if split else L.NO_SPLIT))
         self._h = C.c_void_p(None)
         L.check(L.lib().acoc_ctx_create(self.device, self.N, self.TT, flags, C.addressof(self._h)))
         self.opts = L.NewtonOptions(int(max_iters), int(armijo_maxiters), int(exact_after), 0, float(stepsize_0), float(cc), float(beta),

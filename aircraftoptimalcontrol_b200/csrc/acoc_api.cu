@@ -17,6 +17,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -515,6 +516,14 @@ struct acoc_ctx {
     int cap = 0;                // instance capacity (N may be smaller in a child)
     int spawn_kk = 0;           // iteration at which this child took over its instances
     double gen_ms = 0;          // device time spent moving instances between generations in the last solve
+    // launch scope of the sweep kernels: stream and range of the tile list (see acoc_newton_iterate, "two ranges")
+    cudaStream_t ls_stream = nullptr;
+    int ls_off = 0, ls_end = 0x7fffffff;
+    bool ls_identity = false;
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool all_active = false;    // every instance was active at the last host-side count (reset, or acoc_newton_iterate's count)
+    int bwd_wave_ctas = 0;      // CTAs of the backward sweep that are resident at once on this device (occupancy x SMs)
 };
 
 static int dalloc_bytes(acoc_ctx* c, void** p, size_t bytes)
@@ -604,6 +613,7 @@ static int reset_state(acoc_ctx* c)
     CK(cudaMemsetAsync(c->S.hist_ncand, 0, hrows * sizeof(int), c->stream));
     CK(cudaGetLastError());
     c->kk = 0;
+    c->all_active = true;
     return 0;
 }
 
@@ -872,6 +882,10 @@ int acoc_ctx_create(int device, int n_instances, int TT, unsigned flags, acoc_ct
     c->have_model = true;
     for (int e = 0; e < 8; ++e) if (cudaEventCreate(&c->ev[e]) != cudaSuccess) return bail(fail(ACOC_ERR_CUDA, "cudaEventCreate failed"));
     c->ev_ok = true;
+    if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess)
+        return bail(fail(ACOC_ERR_CUDA, "stream/event creation failed"));
     rc = reset_state(c);
     if (rc) return bail(rc);
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail(fail(ACOC_ERR_CUDA, "stream sync failed"));
@@ -887,6 +901,9 @@ int acoc_ctx_destroy(acoc_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (void* p : c->allocs) cudaFree(p);
     if (c->ev_ok) for (int e = 0; e < 8; ++e) cudaEventDestroy(c->ev[e]);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -1029,9 +1046,17 @@ static bool use_tma(const acoc_ctx* c) { return ACOC_ACT_SHIFT == 5 && !(c->flag
 static TileList tile_list(acoc_ctx* c, bool use_list = true)
 {
     TileList L;
-    L.tiles = use_list ? c->act_groups : nullptr;
+    L.tiles = (use_list && !c->ls_identity) ? c->act_groups : nullptr;
     L.count = c->counters + 1;
+    L.off = c->ls_off; L.end = c->ls_end;
     return L;
+}
+// stream and grid of a sweep launch in the current launch scope (the whole padded batch, or a range of its tiles)
+static cudaStream_t sweep_stream(const acoc_ctx* c) { return c->ls_stream ? c->ls_stream : c->stream; }
+static int sweep_grid(const acoc_ctx* c, int threads)
+{
+    const int tiles = std::min(c->Np / 32, c->ls_end) - c->ls_off;
+    return (tiles * 32 + threads - 1) / threads;
 }
 template <typename K>
 static int prefer_smem(K kernel)
@@ -1065,12 +1090,20 @@ static int launch_backward_t(acoc_ctx* c, bool exact)
     const F* U = (const F*)c->U[cur];
     if (use_tma(c)) {
         const size_t sm = WarpRing<BWD_STAGES, BwdStage<F, XT>::BYTES>::smem_bytes(BWD_THREADS / 32);
+        const int gs = sweep_grid(c, BWD_THREADS);
+        cudaStream_t st = sweep_stream(c);
         if (exact) {
             TRY(prefer_smem(k_backward_tma<true, F, XT>));
-            k_backward_tma<true, F, XT><<<g, BWD_THREADS, sm, c->stream>>>(P, tile_list(c), X, U, (F*)c->KSG, c->S.status, c->S.n_reg);
+            k_backward_tma<true, F, XT><<<gs, BWD_THREADS, sm, st>>>(P, tile_list(c), X, U, (F*)c->KSG, c->S.status, c->S.n_reg);
         } else {
             TRY(prefer_smem(k_backward_tma<false, F, XT>));
-            k_backward_tma<false, F, XT><<<g, BWD_THREADS, sm, c->stream>>>(P, tile_list(c), X, U, (F*)c->KSG, c->S.status, c->S.n_reg);
+            k_backward_tma<false, F, XT><<<gs, BWD_THREADS, sm, st>>>(P, tile_list(c), X, U, (F*)c->KSG, c->S.status, c->S.n_reg);
+        }
+        if (!c->bwd_wave_ctas) {  // resident CTAs of this sweep on the whole device (for the two-range split of acoc_newton_iterate)
+            int nb = 0, sms = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_backward_tma<true, F, XT>, BWD_THREADS, sm));
+            CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+            c->bwd_wave_ctas = std::max(1, nb * sms);
         }
     } else if (exact) k_backward<true, F, XT><<<g, BWD_THREADS, 0, c->stream>>>(P, act_list(c), X, U, (F*)c->KSG, c->S.status, c->S.n_reg);
     else k_backward<false, F, XT><<<g, BWD_THREADS, 0, c->stream>>>(P, act_list(c), X, U, (F*)c->KSG, c->S.status, c->S.n_reg);
@@ -1086,8 +1119,9 @@ static int launch_forward_t(acoc_ctx* c)
     const int cur = c->kk % 3, g = (c->Np + FWD_THREADS - 1) / FWD_THREADS;
     if (use_tma(c)) {
         TRY(prefer_smem(k_forward_tma<F, XT>));
-        k_forward_tma<F, XT><<<g, FWD_THREADS, WarpRing<FWD_STAGES, FwdStage<F, XT>::BYTES>::smem_bytes(FWD_THREADS / 32), c->stream>>>(
-            prob<F>(c), tile_list(c), (const XT*)c->X[cur], (const F*)c->U[cur], (const F*)c->KSG, (F*)c->DU, c->S.status, c->S.descent);
+        k_forward_tma<F, XT><<<sweep_grid(c, FWD_THREADS), FWD_THREADS, WarpRing<FWD_STAGES, FwdStage<F, XT>::BYTES>::smem_bytes(FWD_THREADS / 32),
+                               sweep_stream(c)>>>(prob<F>(c), tile_list(c), (const XT*)c->X[cur], (const F*)c->U[cur], (const F*)c->KSG, (F*)c->DU,
+                                                  c->S.status, c->S.descent);
     } else
         k_forward<F, XT><<<g, FWD_THREADS, 0, c->stream>>>(prob<F>(c), act_list(c), (const XT*)c->X[cur], (const F*)c->U[cur], (const F*)c->KSG,
                                                            (F*)c->DU, (F*)nullptr, c->S.status, c->S.descent);
@@ -1098,37 +1132,54 @@ static int launch_forward_t(acoc_ctx* c)
 static int launch_forward(acoc_ctx* c) { return DISPATCH_FX(c, launch_forward_t, c); }
 // Armijo: fills S.step and the history row kk.  Returns through *lazy_only whether the update may skip
 // instances whose candidate 0 is already in the next slot.
+static bool is_lazy(const acoc_ctx* c) { return (c->flags & ACOC_ARMIJO_LAZY) && c->O.armijo_maxiters > 1; }
+
+// lazy Armijo, first round: candidate 0 for every active instance, written tentatively into the next slot
+template <typename F, typename XT>
+static int launch_cand0_t(acoc_ctx* c)
+{
+    const int cur = c->kk % 3, nxt = (c->kk + 1) % 3, Np = c->Np;
+    const ProblemT<F> P = prob<F>(c);
+    const F *U = (const F*)c->U[cur], *DU = (const F*)c->DU;
+    if (use_tma(c)) {
+        const size_t sm = WarpRing<ROLL_STAGES, RollStage<F>::BYTES>::smem_bytes(ROLL_THREADS / 32);
+        const int g = sweep_grid(c, ROLL_THREADS);
+        cudaStream_t st = sweep_stream(c);
+        if (c->P.q32) {
+            TRY(prefer_smem(k_rollout_write_tma<true, F, XT, 0>));
+            k_rollout_write_tma<true, F, XT, 0><<<g, ROLL_THREADS, sm, st>>>(P, tile_list(c), c->O, c->S, U, DU, c->cand_steps, (XT*)c->X[nxt],
+                                                                            (F*)c->U[nxt], nullptr, c->kk, 0);
+        } else {
+            TRY(prefer_smem(k_rollout_write_tma<false, F, XT, 0>));
+            k_rollout_write_tma<false, F, XT, 0><<<g, ROLL_THREADS, sm, st>>>(P, tile_list(c), c->O, c->S, U, DU, c->cand_steps, (XT*)c->X[nxt],
+                                                                             (F*)c->U[nxt], nullptr, c->kk, 0);
+        }
+    } else
+        LAUNCH_Q32(c->P.q32, k_candidate0_write, (F, XT), (Np + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, c->stream, P, act_list(c), U, DU,
+                   c->cand_steps, (XT*)c->X[nxt], (F*)c->U[nxt], c->S.status, c->S.Jcand);
+    CK(cudaGetLastError());
+    ++c->launches;
+    return 0;
+}
+static int launch_cand0(acoc_ctx* c) { return DISPATCH_FX(c, launch_cand0_t, c); }
+
+// Armijo after candidate 0 (lazy) or all candidates at once (speculative): fills S.step and the history row kk.  Returns through
+// *lazy_only whether the update may skip instances whose candidate 0 is already in the next slot.
 template <typename F, typename XT>
 static int launch_armijo_t(acoc_ctx* c, bool* lazy_only)
 {
-    const int cur = c->kk % 3, nxt = (c->kk + 1) % 3, N = c->N, Np = c->Np, nc = c->O.armijo_maxiters;
+    const int cur = c->kk % 3, N = c->N, Np = c->Np, nc = c->O.armijo_maxiters;
     const ProblemT<F> P = prob<F>(c);
     const F *U = (const F*)c->U[cur], *DU = (const F*)c->DU;
     *lazy_only = false;
-    if ((c->flags & ACOC_ARMIJO_LAZY) && nc > 1) {
-        if (use_tma(c)) {
-            const size_t sm = WarpRing<ROLL_STAGES, RollStage<F>::BYTES>::smem_bytes(ROLL_THREADS / 32);
-            const int g = (Np + ROLL_THREADS - 1) / ROLL_THREADS;
-            if (c->P.q32) {
-                TRY(prefer_smem(k_rollout_write_tma<true, F, XT, 0>));
-                k_rollout_write_tma<true, F, XT, 0><<<g, ROLL_THREADS, sm, c->stream>>>(P, tile_list(c), c->O, c->S, U, DU, c->cand_steps, (XT*)c->X[nxt],
-                                                                                       (F*)c->U[nxt], nullptr, c->kk, 0);
-            } else {
-                TRY(prefer_smem(k_rollout_write_tma<false, F, XT, 0>));
-                k_rollout_write_tma<false, F, XT, 0><<<g, ROLL_THREADS, sm, c->stream>>>(P, tile_list(c), c->O, c->S, U, DU, c->cand_steps, (XT*)c->X[nxt],
-                                                                                        (F*)c->U[nxt], nullptr, c->kk, 0);
-            }
-        } else
-            LAUNCH_Q32(c->P.q32, k_candidate0_write, (F, XT), (Np + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, c->stream, P, act_list(c), U, DU,
-                       c->cand_steps, (XT*)c->X[nxt], (F*)c->U[nxt], c->S.status, c->S.Jcand);
-        CK(cudaGetLastError());
+    if (is_lazy(c)) {
         k_lazy_need<<<(N + 255) / 256, 256, 0, c->stream>>>(c->O, c->S, c->cand_steps, N, Np, 1, c->need);
         CK(cudaGetLastError());
         WorkList L;  // per-instance list of the instances whose candidate 0 failed: the rollouts are compute-bound
         L.groups = c->need_groups; L.count = c->counters + 2; L.shift = 0;
         k_build_list<<<1, 1024, 0, c->stream>>>(c->need, 1, N, 0, c->need_groups, c->counters + 2);
         CK(cudaGetLastError());
-        c->launches += 3;
+        c->launches += 2;
         // In the Gauss-Newton iterations (kk <= exact_after) an instance that fails the full step is accepted within the next
         // few candidates (mean 2.6 / 1.9 candidates in iterations 0 / 1 of config 4): candidates 1..3 first, the rest only where
         // those failed too.  Later (float32-noise phase) the search usually runs to the end and one round of 1..9 is cheaper.
@@ -1171,7 +1222,7 @@ static int launch_update_t(acoc_ctx* c, bool lazy_only, bool bookkeeping, bool u
     if (!use_list) L.groups = nullptr;
     if (use_tma(c)) {
         const size_t sm = WarpRing<ROLL_STAGES, RollStage<F>::BYTES>::smem_bytes(ROLL_THREADS / 32);
-        const int g = (c->Np + ROLL_THREADS - 1) / ROLL_THREADS;
+        const int g = sweep_grid(c, ROLL_THREADS);
         const int* only = lazy_only ? c->need : nullptr;
         if (c->P.q32) {
             TRY(prefer_smem(k_rollout_write_tma<true, F, XT, 1>));
@@ -1209,6 +1260,7 @@ static int count_active(acoc_ctx* c, int* n_active, long long* iters_sum)
     CK(cudaStreamSynchronize(c->stream));
     if (n_active) *n_active = h;
     if (iters_sum) *iters_sum = s;
+    c->all_active = h == c->N;
     return 0;
 }
 
@@ -1227,10 +1279,42 @@ int acoc_newton_iterate(acoc_ctx* c, int n_iters, int* n_active_out)
         TRY(launch_build_active(c));
         if (c->kk == 0) TRY(launch_cost(c));  // later iterations inherit the cost from the update rollout
         if (prof) CK(cudaEventRecord(c->ev[1], c->stream));
-        TRY(launch_backward(c, c->kk > c->O.exact_after));  // optcon.py:443
-        if (prof) CK(cudaEventRecord(c->ev[2], c->stream));
-        TRY(launch_forward(c));
-        if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
+        const bool exact = c->kk > c->O.exact_after;  // optcon.py:443
+        // Two ranges.  The backward sweep keeps only bwd_wave_ctas CTAs resident (216 registers per thread), so a batch with more
+        // CTAs than that runs in rounds, and the last, partial round leaves most of the machine idle while every warp of it still
+        // needs its full latency-bound sweep time.  When the whole batch is active, the tiles of the full rounds (range A) and the
+        // tiles of the partial round (range B) go through backward -> forward -> candidate 0 on two streams: A's bandwidth-bound
+        // forward/rollout sweeps fill the machine while B's backward sweep is still running.  Instances are independent, so the
+        // split changes no result.
+        const int ctas = (c->Np / 32 + 1) / 2;
+        const int wave = c->bwd_wave_ctas;
+        const bool two = use_tma(c) && is_lazy(c) && !prof && c->all_active && !(c->flags & ACOC_NO_SPLIT) && wave > 0 && ctas > wave &&
+                         ctas % wave != 0;
+        if (two) {
+            int tiles_a = (ctas / wave) * wave * 2;
+            if (const char* e = getenv("ACOC_SPLIT_TILES")) tiles_a = std::max(2, std::min(c->Np / 32 - 2, atoi(e)));  // tuning experiments
+            CK(cudaEventRecord(c->ev_fork, c->stream));
+            CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+            c->ls_identity = true;
+            for (int r = 0; r < 2; ++r) {
+                c->ls_stream = r == 0 ? c->stream : c->stream2;
+                c->ls_off = r == 0 ? 0 : tiles_a;
+                c->ls_end = r == 0 ? tiles_a : 0x7fffffff;
+                int rc = launch_backward(c, exact);
+                if (!rc) rc = launch_forward(c);
+                if (!rc) rc = launch_cand0(c);
+                if (rc) { c->ls_stream = nullptr; c->ls_off = 0; c->ls_end = 0x7fffffff; c->ls_identity = false; return rc; }
+            }
+            c->ls_stream = nullptr; c->ls_off = 0; c->ls_end = 0x7fffffff; c->ls_identity = false;
+            CK(cudaEventRecord(c->ev_join, c->stream2));
+            CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        } else {
+            TRY(launch_backward(c, exact));
+            if (prof) CK(cudaEventRecord(c->ev[2], c->stream));
+            TRY(launch_forward(c));
+            if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
+            if (is_lazy(c)) TRY(launch_cand0(c));
+        }
         TRY(launch_armijo(c, &lazy_only));
         if (prof) CK(cudaEventRecord(c->ev[4], c->stream));
         TRY(launch_update(c, lazy_only, true, true));

@@ -80,11 +80,14 @@ struct WarpRing {
 struct TileList {
     const int* tiles;  // nullptr: identity
     const int* count;
+    int off, end;      // this launch covers list entries [off, end) (a batch may be swept as two ranges on two streams)
 };
 __device__ __forceinline__ int warp_tile(const TileList& L, int w, int Np)
 {
-    if (!L.tiles) return w < Np / TILE ? w : -1;
-    return w < *L.count ? L.tiles[w] : -1;
+    const int e = L.off + w;
+    if (e >= L.end) return -1;
+    if (!L.tiles) return e < Np / TILE ? e : -1;
+    return e < *L.count ? L.tiles[e] : -1;
 }
 
 // first element of the block of tile `tile` at time t in a warp-tiled array with C components

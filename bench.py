@@ -193,6 +193,7 @@ def main():
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"], help="f64 = the parity path (default); f32 = the optional FP32 mode")
     ap.add_argument("--x-storage", default="auto", choices=["auto", "f64"], help="f64: keep float32-valued states in float64 buffers (A/B)")
     ap.add_argument("--no-tma", action="store_true", help="plain-load sweeps instead of the TMA rings (A/B)")
+    ap.add_argument("--no-split", action="store_true", help="one stream for the whole batch instead of the two-range sweep (A/B)")
     ap.add_argument("--cpu-sample", type=int, default=16384, help="instances of the bounded CPU sample (about 10 s of work on 16 host threads)")
     ap.add_argument("--chunks", type=int, default=8, help="sub-batches of the pipelined end-to-end solve")
     ap.add_argument("--no-e2e", action="store_true")
@@ -223,7 +224,7 @@ def main():
     K, W = args.steps, args.warmup
 
     xr, ur, dx0, (Q, R, QT) = make_problem(args.workload, n_total, (rank, world))
-    bn = pkg.BatchedNewton(n, TT=TT, device=local, state=args.state, armijo=args.armijo, precision=args.precision, x_storage=args.x_storage, tma=not args.no_tma)
+    bn = pkg.BatchedNewton(n, TT=TT, device=local, state=args.state, armijo=args.armijo, precision=args.precision, x_storage=args.x_storage, tma=not args.no_tma, split=not args.no_split)
     bn.set_weights(Q, R, QT)
     bn.set_refs(xr, ur)
     bn.init_guess(dx0=dx0)
@@ -357,7 +358,7 @@ def main():
         xs_t = torch.empty((n, 6, TT), dtype=torch.float64, pin_memory=True)
         us_t = torch.empty((n, 2, TT), dtype=torch.float64, pin_memory=True)
         pn = pkg.PipelinedNewton(n, n_chunks=args.chunks, TT=TT, device=local, state=args.state, armijo=args.armijo, precision=args.precision,
-                                 x_storage=args.x_storage, tma=not args.no_tma)
+                                 x_storage=args.x_storage, tma=not args.no_tma, split=not args.no_split)
         pn.set_weights(Q, R, QT)
         pn.solve(xr_p.numpy(), ur_p.numpy(), dx0=dx0, out=(xs_t.numpy(), us_t.numpy()))   # untimed warm-up of the whole path
         barrier()

@@ -47,6 +47,7 @@ typedef enum acoc_status {
                                     float64); NOT the parity path -- results agree with the float64 path to a tolerance only */
 #define ACOC_NO_TMA 64u          /* run the sweeps with plain global loads instead of the warp-private TMA (bulk async copy) rings;
                                     results are bit-identical, this is for A/B measurements */
+#define ACOC_NO_SPLIT 128u        /* never sweep a fully active batch as two tile ranges on two streams (A/B measurements; identical results) */
 #define ACOC_X_F64 32u           /* keep the state iterates in float64 device buffers even when every stored state is a float32 value
                                     (ACOC_STATE_F32); results are bit-identical either way, this only costs bandwidth (A/B tests) */
 
