@@ -126,9 +126,12 @@ __device__ __forceinline__ int work_instance(const WorkList& L, int j, int N)
 // One CTA, ordered stream compaction.  mode 0: group alive iff any status[i] == ST_ACTIVE; mode 1: iff any flag[i] != 0.
 // Every thread owns a contiguous range of groups: count, one block-wide exclusive scan, write (two passes over the flags, which
 // stay in L1/L2; ~10 us for 65,536 entries instead of ~75 us for a tile-by-tile loop with two barriers per 1024 entries).
+// base: the list covers instances [base, base + N) and holds absolute group numbers (base must be a multiple of the group size).
 __global__ void __launch_bounds__(1024) k_build_list(const int* __restrict__ flag, int mode, int N, int shift, int* __restrict__ groups,
-                                                     int* __restrict__ count)
+                                                     int* __restrict__ count, int base = 0)
 {
+    flag += base;
+    const int gbase = base >> shift;
     __shared__ int warp_tot[32];
     const int G = 1 << shift, ngroups = (N + G - 1) >> shift;
     const int per = (ngroups + 1023) / 1024, lo = min(ngroups, (int)threadIdx.x * per), hi = min(ngroups, lo + per);
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(1024) k_build_list(const int* __restrict__ fla
     }
     __syncthreads();
     int off = warp_tot[warp] + incl - cnt;
-    for (int g = lo; g < hi; ++g) if (alive(g)) groups[off++] = g;
+    for (int g = lo; g < hi; ++g) if (alive(g)) groups[off++] = gbase + g;
 }
 
 template <bool EXACT, typename F, typename XT>
@@ -220,11 +223,11 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_candidate0_write(ProblemT<F> P
 }
 
 // lazy Armijo: flag the instances whose candidates 0 .. n_tested-1 all failed the test of optcon.py:268
-__global__ void k_lazy_need(NewtonOpts O, NewtonState S, const double* __restrict__ cand_steps, int N, int Np, int n_tested,
+__global__ void k_lazy_need(NewtonOpts O, NewtonState S, const double* __restrict__ cand_steps, int i0, int i1, int Np, int n_tested,
                             int* __restrict__ need)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i1) return;
     int nd = 0;
     if (S.status[i] == ST_ACTIVE) {
         const double JP = S.Jcur[i], d = S.descent[i];
@@ -235,10 +238,10 @@ __global__ void k_lazy_need(NewtonOpts O, NewtonState S, const double* __restric
     need[i] = nd;
 }
 
-__global__ void k_select(NewtonOpts O, NewtonState S, const double* __restrict__ cand_steps, int kk, int N, int Np)
+__global__ void k_select(NewtonOpts O, NewtonState S, const double* __restrict__ cand_steps, int kk, int i0, int i1, int Np)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N || S.status[i] != ST_ACTIVE) return;
+    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i1 || S.status[i] != ST_ACTIVE) return;
     armijo_select_instance(O, S, cand_steps, kk, Np, i);
 }
 
@@ -864,7 +867,7 @@ int acoc_ctx_create(int device, int n_instances, int TT, unsigned flags, acoc_ct
     if (!rc) rc = dalloc(c, &c->need2, Np);
     if (!rc) rc = dalloc(c, &c->slot_tmp, Np);
     if (!rc) rc = dalloc(c, &c->origin, Np);
-    if (!rc) rc = dalloc(c, &c->counters, 4);
+    if (!rc) rc = dalloc(c, &c->counters, 8);
     if (!rc) rc = dalloc(c, &c->act_groups, Np);
     if (!rc) rc = dalloc(c, &c->need_groups, Np);
     if (!rc) rc = dalloc(c, &c->iters_sum, 2);
@@ -1051,6 +1054,10 @@ static TileList tile_list(acoc_ctx* c, bool use_list = true)
     L.off = c->ls_off; L.end = c->ls_end;
     return L;
 }
+// instance range and need-list counter of the current launch scope
+static int scope_i0(const acoc_ctx* c) { return c->ls_off * 32; }
+static int scope_i1(const acoc_ctx* c) { return (int)std::min<long long>(c->N, (long long)std::min(c->Np / 32, c->ls_end) * 32); }
+static int* scope_need_count(acoc_ctx* c) { return c->counters + (c->ls_off == 0 ? 2 : 4); }
 // stream and grid of a sweep launch in the current launch scope (the whole padded batch, or a range of its tiles)
 static cudaStream_t sweep_stream(const acoc_ctx* c) { return c->ls_stream ? c->ls_stream : c->stream; }
 static int sweep_grid(const acoc_ctx* c, int threads)
@@ -1168,16 +1175,19 @@ static int launch_cand0(acoc_ctx* c) { return DISPATCH_FX(c, launch_cand0_t, c);
 template <typename F, typename XT>
 static int launch_armijo_t(acoc_ctx* c, bool* lazy_only)
 {
-    const int cur = c->kk % 3, N = c->N, Np = c->Np, nc = c->O.armijo_maxiters;
+    const int cur = c->kk % 3, Np = c->Np, nc = c->O.armijo_maxiters;
     const ProblemT<F> P = prob<F>(c);
     const F *U = (const F*)c->U[cur], *DU = (const F*)c->DU;
     *lazy_only = false;
+    cudaStream_t st = sweep_stream(c);
+    const int i0 = scope_i0(c), i1 = scope_i1(c), n = i1 - i0;
     if (is_lazy(c)) {
-        k_lazy_need<<<(N + 255) / 256, 256, 0, c->stream>>>(c->O, c->S, c->cand_steps, N, Np, 1, c->need);
+        int* cnt = scope_need_count(c);
+        k_lazy_need<<<(n + 255) / 256, 256, 0, st>>>(c->O, c->S, c->cand_steps, i0, i1, Np, 1, c->need);
         CK(cudaGetLastError());
         WorkList L;  // per-instance list of the instances whose candidate 0 failed: the rollouts are compute-bound
-        L.groups = c->need_groups; L.count = c->counters + 2; L.shift = 0;
-        k_build_list<<<1, 1024, 0, c->stream>>>(c->need, 1, N, 0, c->need_groups, c->counters + 2);
+        L.groups = c->need_groups + i0; L.count = cnt; L.shift = 0;
+        k_build_list<<<1, 1024, 0, st>>>(c->need, 1, n, 0, c->need_groups + i0, cnt, i0);
         CK(cudaGetLastError());
         c->launches += 2;
         // In the Gauss-Newton iterations (kk <= exact_after) an instance that fails the full step is accepted within the next
@@ -1185,17 +1195,17 @@ static int launch_armijo_t(acoc_ctx* c, bool* lazy_only)
         // those failed too.  Later (float32-noise phase) the search usually runs to the end and one round of 1..9 is cheaper.
         const int split = (c->kk <= c->O.exact_after && nc > 5) ? 4 : nc;
         dim3 block(CAND_TILE, std::min(split - 1, CAND_MAXY));
-        LAUNCH_Q32(c->P.q32, k_candidates, (F), (N + CAND_TILE - 1) / CAND_TILE, block, c->stream, P, L, U, DU, c->cand_steps, 1, split, c->S.status,
+        LAUNCH_Q32(c->P.q32, k_candidates, (F), (n + CAND_TILE - 1) / CAND_TILE, block, st, P, L, U, DU, c->cand_steps, 1, split, c->S.status,
                    c->S.Jcand);
         CK(cudaGetLastError());
         if (split < nc) {
-            k_lazy_need<<<(N + 255) / 256, 256, 0, c->stream>>>(c->O, c->S, c->cand_steps, N, Np, split, c->need2);
+            k_lazy_need<<<(n + 255) / 256, 256, 0, st>>>(c->O, c->S, c->cand_steps, i0, i1, Np, split, c->need2);
             CK(cudaGetLastError());
-            k_build_list<<<1, 1024, 0, c->stream>>>(c->need2, 1, N, 0, c->need_groups, c->counters + 2);
+            k_build_list<<<1, 1024, 0, st>>>(c->need2, 1, n, 0, c->need_groups + i0, cnt, i0);
             CK(cudaGetLastError());
             dim3 block2(CAND_TILE, std::min(nc - split, CAND_MAXY));
-            LAUNCH_Q32(c->P.q32, k_candidates, (F), (N + CAND_TILE - 1) / CAND_TILE, block2, c->stream, P, L, U, DU, c->cand_steps, split, nc,
-                       c->S.status, c->S.Jcand);
+            LAUNCH_Q32(c->P.q32, k_candidates, (F), (n + CAND_TILE - 1) / CAND_TILE, block2, st, P, L, U, DU, c->cand_steps, split, nc, c->S.status,
+                       c->S.Jcand);
             CK(cudaGetLastError());
             c->launches += 3;
         }
@@ -1207,7 +1217,7 @@ static int launch_armijo_t(acoc_ctx* c, bool* lazy_only)
         CK(cudaGetLastError());
         ++c->launches;
     }
-    k_select<<<(N + 255) / 256, 256, 0, c->stream>>>(c->O, c->S, c->cand_steps, c->kk, N, c->Np);
+    k_select<<<(n + 255) / 256, 256, 0, st>>>(c->O, c->S, c->cand_steps, c->kk, i0, i1, c->Np);
     CK(cudaGetLastError());
     ++c->launches;
     return 0;
@@ -1226,12 +1236,12 @@ static int launch_update_t(acoc_ctx* c, bool lazy_only, bool bookkeeping, bool u
         const int* only = lazy_only ? c->need : nullptr;
         if (c->P.q32) {
             TRY(prefer_smem(k_rollout_write_tma<true, F, XT, 1>));
-            k_rollout_write_tma<true, F, XT, 1><<<g, ROLL_THREADS, sm, c->stream>>>(prob<F>(c), tile_list(c, use_list), c->O, c->S, (const F*)c->U[cur],
+            k_rollout_write_tma<true, F, XT, 1><<<g, ROLL_THREADS, sm, sweep_stream(c)>>>(prob<F>(c), tile_list(c, use_list), c->O, c->S, (const F*)c->U[cur],
                                                                                    (const F*)c->DU, c->cand_steps, (XT*)c->X[nxt], (F*)c->U[nxt], only,
                                                                                    c->kk, bookkeeping ? 1 : 0);
         } else {
             TRY(prefer_smem(k_rollout_write_tma<false, F, XT, 1>));
-            k_rollout_write_tma<false, F, XT, 1><<<g, ROLL_THREADS, sm, c->stream>>>(prob<F>(c), tile_list(c, use_list), c->O, c->S, (const F*)c->U[cur],
+            k_rollout_write_tma<false, F, XT, 1><<<g, ROLL_THREADS, sm, sweep_stream(c)>>>(prob<F>(c), tile_list(c, use_list), c->O, c->S, (const F*)c->U[cur],
                                                                                     (const F*)c->DU, c->cand_steps, (XT*)c->X[nxt], (F*)c->U[nxt], only,
                                                                                     c->kk, bookkeeping ? 1 : 0);
         }
@@ -1264,6 +1274,20 @@ static int count_active(acoc_ctx* c, int* n_active, long long* iters_sum)
     return 0;
 }
 
+static void scope_reset(acoc_ctx* c) { c->ls_stream = nullptr; c->ls_off = 0; c->ls_end = 0x7fffffff; c->ls_identity = false; }
+
+// one Newton iteration (loop body of optcon.py:415-501) of the instances in the current launch scope, without the list rebuild
+static int launch_iteration_body(acoc_ctx* c)
+{
+    bool lazy_only = false;
+    TRY(launch_backward(c, c->kk > c->O.exact_after));  // optcon.py:443
+    TRY(launch_forward(c));
+    if (is_lazy(c)) TRY(launch_cand0(c));
+    TRY(launch_armijo(c, &lazy_only));
+    TRY(launch_update(c, lazy_only, true, true));
+    return 0;
+}
+
 int acoc_newton_iterate(acoc_ctx* c, int n_iters, int* n_active_out)
 {
     TRY(ready(c));
@@ -1272,49 +1296,30 @@ int acoc_newton_iterate(acoc_ctx* c, int n_iters, int* n_active_out)
     c->total_ms = 0; for (int p = 0; p < 6; ++p) c->phase_ms[p] = 0;
     c->launches = 0;
     CK(cudaEventRecord(c->ev[6], c->stream));
-    for (int it = 0; it < n_iters; ++it) {
+    int it = 0;
+    for (; it < n_iters; ++it) {
         if (c->kk >= c->O.max_iters - 1) break;  // for kk in range(max_iters-1), optcon.py:415
+        // Two ranges.  The backward sweep keeps only bwd_wave_ctas CTAs resident (216 registers per thread), so a batch with more
+        // CTAs than that runs in rounds, and the last, partial round leaves most of the machine idle while every warp of it still
+        // needs its full latency-bound sweep time.  While the whole batch is active, the tiles of the full rounds (range A) and
+        // the tiles of the partial round (range B) therefore run all remaining iterations of this call as two independent
+        // instance ranges on two streams (every kernel of an iteration takes a tile / instance range): one range's bandwidth-bound
+        // forward and rollout sweeps fill the machine while the other's backward sweep is latency-bound, across iteration
+        // boundaries too.  Instances are independent, so the split changes no result; the streams join before the call returns.
+        const int ctas = (c->Np / 32 + 1) / 2, wave = c->bwd_wave_ctas;
+        if (use_tma(c) && is_lazy(c) && !prof && c->all_active && !(c->flags & ACOC_NO_SPLIT) && c->kk > 0 && wave > 0 && ctas > wave &&
+            ctas % wave != 0)
+            break;
         bool lazy_only = false;
         if (prof) CK(cudaEventRecord(c->ev[0], c->stream));
         TRY(launch_build_active(c));
         if (c->kk == 0) TRY(launch_cost(c));  // later iterations inherit the cost from the update rollout
         if (prof) CK(cudaEventRecord(c->ev[1], c->stream));
-        const bool exact = c->kk > c->O.exact_after;  // optcon.py:443
-        // Two ranges.  The backward sweep keeps only bwd_wave_ctas CTAs resident (216 registers per thread), so a batch with more
-        // CTAs than that runs in rounds, and the last, partial round leaves most of the machine idle while every warp of it still
-        // needs its full latency-bound sweep time.  When the whole batch is active, the tiles of the full rounds (range A) and the
-        // tiles of the partial round (range B) go through backward -> forward -> candidate 0 on two streams: A's bandwidth-bound
-        // forward/rollout sweeps fill the machine while B's backward sweep is still running.  Instances are independent, so the
-        // split changes no result.
-        const int ctas = (c->Np / 32 + 1) / 2;
-        const int wave = c->bwd_wave_ctas;
-        const bool two = use_tma(c) && is_lazy(c) && !prof && c->all_active && !(c->flags & ACOC_NO_SPLIT) && wave > 0 && ctas > wave &&
-                         ctas % wave != 0;
-        if (two) {
-            int tiles_a = (ctas / wave) * wave * 2;
-            if (const char* e = getenv("ACOC_SPLIT_TILES")) tiles_a = std::max(2, std::min(c->Np / 32 - 2, atoi(e)));  // tuning experiments
-            CK(cudaEventRecord(c->ev_fork, c->stream));
-            CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-            c->ls_identity = true;
-            for (int r = 0; r < 2; ++r) {
-                c->ls_stream = r == 0 ? c->stream : c->stream2;
-                c->ls_off = r == 0 ? 0 : tiles_a;
-                c->ls_end = r == 0 ? tiles_a : 0x7fffffff;
-                int rc = launch_backward(c, exact);
-                if (!rc) rc = launch_forward(c);
-                if (!rc) rc = launch_cand0(c);
-                if (rc) { c->ls_stream = nullptr; c->ls_off = 0; c->ls_end = 0x7fffffff; c->ls_identity = false; return rc; }
-            }
-            c->ls_stream = nullptr; c->ls_off = 0; c->ls_end = 0x7fffffff; c->ls_identity = false;
-            CK(cudaEventRecord(c->ev_join, c->stream2));
-            CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
-        } else {
-            TRY(launch_backward(c, exact));
-            if (prof) CK(cudaEventRecord(c->ev[2], c->stream));
-            TRY(launch_forward(c));
-            if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
-            if (is_lazy(c)) TRY(launch_cand0(c));
-        }
+        TRY(launch_backward(c, c->kk > c->O.exact_after));  // optcon.py:443
+        if (prof) CK(cudaEventRecord(c->ev[2], c->stream));
+        TRY(launch_forward(c));
+        if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
+        if (is_lazy(c)) TRY(launch_cand0(c));
         TRY(launch_armijo(c, &lazy_only));
         if (prof) CK(cudaEventRecord(c->ev[4], c->stream));
         TRY(launch_update(c, lazy_only, true, true));
@@ -1329,6 +1334,29 @@ int acoc_newton_iterate(acoc_ctx* c, int n_iters, int* n_active_out)
             }
         }
         ++c->kk;
+    }
+    if (it < n_iters && c->kk < c->O.max_iters - 1) {  // the remaining iterations as two independent ranges (see above)
+        const int ctas = (c->Np / 32 + 1) / 2, wave = c->bwd_wave_ctas;
+        int tiles_a = (ctas / wave) * wave * 2;
+        if (const char* e = getenv("ACOC_SPLIT_TILES")) tiles_a = std::max(2, std::min(c->Np / 32 - 2, atoi(e)));  // tuning experiments
+        const int kk0 = c->kk;
+        const int todo = std::min(n_iters - it, c->O.max_iters - 1 - c->kk);
+        CK(cudaEventRecord(c->ev_fork, c->stream));
+        CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+        int rc = 0;
+        for (int r = 0; r < 2 && !rc; ++r) {
+            c->ls_identity = true;
+            c->ls_stream = r == 0 ? c->stream : c->stream2;
+            c->ls_off = r == 0 ? 0 : tiles_a;
+            c->ls_end = r == 0 ? tiles_a : 0x7fffffff;
+            c->kk = kk0;
+            for (int j = 0; j < todo && !rc; ++j, ++c->kk) rc = launch_iteration_body(c);
+        }
+        scope_reset(c);
+        c->kk = kk0 + todo;
+        if (rc) return rc;
+        CK(cudaEventRecord(c->ev_join, c->stream2));
+        CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     }
     CK(cudaEventRecord(c->ev[7], c->stream));
     CK(cudaEventSynchronize(c->ev[7]));
@@ -1561,7 +1589,7 @@ int acoc_armijo(acoc_ctx* c, double* stepsize, double* costs)
     // always the speculative evaluation here: this entry point reports the cost of every candidate
     const int N = c->N, nc = c->O.armijo_maxiters;
     TRY(DISPATCH_F(c, launch_all_candidates_t, c));
-    k_select<<<(N + 255) / 256, 256, 0, c->stream>>>(c->O, c->S, c->cand_steps, c->kk, N, c->Np);
+    k_select<<<(N + 255) / 256, 256, 0, c->stream>>>(c->O, c->S, c->cand_steps, c->kk, 0, N, c->Np);
     CK(cudaGetLastError());
     if (stepsize) CK(cudaMemcpyAsync(stepsize, c->S.step, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

@@ -454,3 +454,31 @@ def test_tma_rings_and_plain_loads_identical(gpu):
         assert np.array_equal(a[4][k], b[4][k]), k
     act = a[4]["iters"] == a[4]["iters"].max()  # deltau / gains are scratch of the last iteration an instance took part in
     assert np.array_equal(a[5][act], b[5][act]) and np.array_equal(a[6][0][act], b[6][0][act])
+
+
+def test_two_range_sweep_identical(gpu):
+    """A fully active batch with more backward CTAs than fit on the device at once (4 per SM x 148 SMs = 592 CTAs of 64 instances) is
+    swept as two independent tile ranges on two streams.  Instances are independent, so results, histories and statistics must be
+    bit-identical to the single-stream sweep -- checked on a ragged 40,001-instance batch (626 CTAs) through a whole solve."""
+    n, TT = 40001, 48
+    xr, ur, Q, R, QT = _random_batch(n, TT, 23, 0.048)
+    out = []
+    for split in (True, False):
+        with gpu.BatchedNewton(n, TT=TT, armijo="lazy", split=split) as bn:
+            bn.set_weights(Q, R, QT)
+            bn.set_refs(xr, ur)
+            bn.init_guess()
+            bn.iterate(3)
+            launches = bn.timing()["launches"]
+            mid = bn.iterate_at(0)
+            total = bn.solve()
+            out.append((total, mid, bn.result(), bn.iterate_at(0), bn.history(), bn.stats(), launches))
+    a, b = out
+    assert a[6] > b[6]  # the split path really ran: iterations 1 and 2 launched their kernels once per range
+    assert a[0] == b[0] and a[0] > 3 * n
+    for k in (1, 2, 3):
+        assert np.array_equal(a[k][0], b[k][0]) and np.array_equal(a[k][1], b[k][1]), k
+    for k in ("JJ", "descent", "stepsize", "n_armijo"):
+        assert np.array_equal(a[4][k], b[4][k]), k
+    for k in ("iters", "status", "J", "descent", "n_reg"):
+        assert np.array_equal(a[5][k], b[5][k]), k
