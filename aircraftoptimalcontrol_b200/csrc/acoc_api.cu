@@ -525,7 +525,7 @@ struct acoc_ctx {
     bool ls_identity = false;
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool all_active = false;    // every instance was active at the last host-side count (reset, or acoc_newton_iterate's count)
+    bool all_active = false;    // more than half of the instances were active at the last host-side count (reset: all of them)
     int bwd_wave_ctas = 0;      // CTAs of the backward sweep that are resident at once on this device (occupancy x SMs)
 };
 
@@ -1270,7 +1270,7 @@ static int count_active(acoc_ctx* c, int* n_active, long long* iters_sum)
     CK(cudaStreamSynchronize(c->stream));
     if (n_active) *n_active = h;
     if (iters_sum) *iters_sum = s;
-    c->all_active = h == c->N;
+    c->all_active = 2LL * h > c->N;  // (tile-granular lists are practically the identity until well below half of the batch)
     return 0;
 }
 
@@ -1301,7 +1301,7 @@ int acoc_newton_iterate(acoc_ctx* c, int n_iters, int* n_active_out)
         if (c->kk >= c->O.max_iters - 1) break;  // for kk in range(max_iters-1), optcon.py:415
         // Two ranges.  The backward sweep keeps only bwd_wave_ctas CTAs resident (216 registers per thread), so a batch with more
         // CTAs than that runs in rounds, and the last, partial round leaves most of the machine idle while every warp of it still
-        // needs its full latency-bound sweep time.  While the whole batch is active, the tiles of the full rounds (range A) and
+        // needs its full latency-bound sweep time.  While most of the batch is active, the tiles of the full rounds (range A) and
         // the tiles of the partial round (range B) therefore run all remaining iterations of this call as two independent
         // instance ranges on two streams (every kernel of an iteration takes a tile / instance range): one range's bandwidth-bound
         // forward and rollout sweeps fill the machine while the other's backward sweep is latency-bound, across iteration
