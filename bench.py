@@ -344,7 +344,8 @@ def main():
     tot_solve = bn.solve()
     tsolve = bn.timing()
     whole = {"value": tot_solve / (tsolve["total_ms"] * 1e-3), "unit": UNIT, "device_ms": tsolve["total_ms"], "total_newton_iterations": int(tot_solve),
-             "lockstep_iterations": int(bn.stats()["iters"].max()), "gpu_launches": tsolve["launches"], "scope": "this rank"}
+             "lockstep_iterations": int(bn.stats()["iters"].max()), "gpu_launches": tsolve["launches"],
+             "survivor_generation_moves_ms": tsolve["phases"]["select"], "scope": "this rank"}
 
     device_bytes = bn.device_bytes
     bn.close()  # the end-to-end leg below builds its own contexts: release this one (and its survivor generations) first
