@@ -523,8 +523,9 @@ struct acoc_ctx {
     cudaStream_t ls_stream = nullptr;
     int ls_off = 0, ls_end = 0x7fffffff;
     bool ls_identity = false;
-    cudaStream_t stream2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int ls_range = 0;           // index of the current range (its need-list counter)
+    cudaStream_t rstream[4] = {nullptr, nullptr, nullptr, nullptr};  // streams of ranges 1..3 (range 0 uses `stream`)
+    cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
     bool all_active = false;    // more than half of the instances were active at the last host-side count (reset: all of them)
     int bwd_wave_ctas = 0;      // CTAs of the backward sweep that are resident at once on this device (occupancy x SMs)
 };
@@ -885,10 +886,11 @@ int acoc_ctx_create(int device, int n_instances, int TT, unsigned flags, acoc_ct
     c->have_model = true;
     for (int e = 0; e < 8; ++e) if (cudaEventCreate(&c->ev[e]) != cudaSuccess) return bail(fail(ACOC_ERR_CUDA, "cudaEventCreate failed"));
     c->ev_ok = true;
-    if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess)
-        return bail(fail(ACOC_ERR_CUDA, "stream/event creation failed"));
+    if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(fail(ACOC_ERR_CUDA, "event creation failed"));
+    for (int r = 1; r < 4; ++r)
+        if (cudaStreamCreateWithFlags(&c->rstream[r], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_join[r], cudaEventDisableTiming) != cudaSuccess)
+            return bail(fail(ACOC_ERR_CUDA, "stream/event creation failed"));
     rc = reset_state(c);
     if (rc) return bail(rc);
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail(fail(ACOC_ERR_CUDA, "stream sync failed"));
@@ -905,8 +907,10 @@ int acoc_ctx_destroy(acoc_ctx* c)
     for (void* p : c->allocs) cudaFree(p);
     if (c->ev_ok) for (int e = 0; e < 8; ++e) cudaEventDestroy(c->ev[e]);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-    if (c->ev_join) cudaEventDestroy(c->ev_join);
-    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+    for (int r = 1; r < 4; ++r) {
+        if (c->ev_join[r]) cudaEventDestroy(c->ev_join[r]);
+        if (c->rstream[r]) { cudaStreamSynchronize(c->rstream[r]); cudaStreamDestroy(c->rstream[r]); }
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -1057,7 +1061,7 @@ static TileList tile_list(acoc_ctx* c, bool use_list = true)
 // instance range and need-list counter of the current launch scope
 static int scope_i0(const acoc_ctx* c) { return c->ls_off * 32; }
 static int scope_i1(const acoc_ctx* c) { return (int)std::min<long long>(c->N, (long long)std::min(c->Np / 32, c->ls_end) * 32); }
-static int* scope_need_count(acoc_ctx* c) { return c->counters + (c->ls_off == 0 ? 2 : 4); }
+static int* scope_need_count(acoc_ctx* c) { return c->counters + (c->ls_range == 0 ? 2 : 3 + c->ls_range); }
 // stream and grid of a sweep launch in the current launch scope (the whole padded batch, or a range of its tiles)
 static cudaStream_t sweep_stream(const acoc_ctx* c) { return c->ls_stream ? c->ls_stream : c->stream; }
 static int sweep_grid(const acoc_ctx* c, int threads)
@@ -1274,7 +1278,7 @@ static int count_active(acoc_ctx* c, int* n_active, long long* iters_sum)
     return 0;
 }
 
-static void scope_reset(acoc_ctx* c) { c->ls_stream = nullptr; c->ls_off = 0; c->ls_end = 0x7fffffff; c->ls_identity = false; }
+static void scope_reset(acoc_ctx* c) { c->ls_stream = nullptr; c->ls_off = 0; c->ls_end = 0x7fffffff; c->ls_identity = false; c->ls_range = 0; }
 
 // one Newton iteration (loop body of optcon.py:415-501) of the instances in the current launch scope, without the list rebuild
 static int launch_iteration_body(acoc_ctx* c)
@@ -1337,26 +1341,38 @@ int acoc_newton_iterate(acoc_ctx* c, int n_iters, int* n_active_out)
     }
     if (it < n_iters && c->kk < c->O.max_iters - 1) {  // the remaining iterations as two independent ranges (see above)
         const int ctas = (c->Np / 32 + 1) / 2, wave = c->bwd_wave_ctas;
-        int tiles_a = (ctas / wave) * wave * 2;
-        if (const char* e = getenv("ACOC_SPLIT_TILES")) tiles_a = std::max(2, std::min(c->Np / 32 - 2, atoi(e)));  // tuning experiments
+        const int tiles = c->Np / 32;
+        int bound[5] = {0, (ctas / wave) * wave * 2, tiles, tiles, tiles}, nr = 2;
+        if (const char* e = getenv("ACOC_RANGES")) {  // tuning experiments: up to three ascending tile boundaries "a,b,c"
+            nr = 1;
+            for (const char* q = e; *q && nr < 4; ++nr) {
+                bound[nr] = std::max(bound[nr - 1] + 2, std::min(tiles - 2, atoi(q)));
+                while (*q && *q != ',') ++q;
+                if (*q == ',') ++q;
+            }
+            for (int r = nr; r < 5; ++r) bound[r] = tiles;
+        }
         const int kk0 = c->kk;
         const int todo = std::min(n_iters - it, c->O.max_iters - 1 - c->kk);
         CK(cudaEventRecord(c->ev_fork, c->stream));
-        CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+        for (int r = 1; r < nr; ++r) CK(cudaStreamWaitEvent(c->rstream[r], c->ev_fork, 0));
         int rc = 0;
-        for (int r = 0; r < 2 && !rc; ++r) {
+        for (int r = 0; r < nr && !rc; ++r) {
             c->ls_identity = true;
-            c->ls_stream = r == 0 ? c->stream : c->stream2;
-            c->ls_off = r == 0 ? 0 : tiles_a;
-            c->ls_end = r == 0 ? tiles_a : 0x7fffffff;
+            c->ls_range = r;
+            c->ls_stream = r == 0 ? c->stream : c->rstream[r];
+            c->ls_off = bound[r];
+            c->ls_end = bound[r + 1];
             c->kk = kk0;
             for (int j = 0; j < todo && !rc; ++j, ++c->kk) rc = launch_iteration_body(c);
         }
         scope_reset(c);
         c->kk = kk0 + todo;
         if (rc) return rc;
-        CK(cudaEventRecord(c->ev_join, c->stream2));
-        CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        for (int r = 1; r < nr; ++r) {
+            CK(cudaEventRecord(c->ev_join[r], c->rstream[r]));
+            CK(cudaStreamWaitEvent(c->stream, c->ev_join[r], 0));
+        }
     }
     CK(cudaEventRecord(c->ev[7], c->stream));
     CK(cudaEventSynchronize(c->ev[7]));
