@@ -6,9 +6,10 @@
 // Execution model: one thread = one OCP instance for the sequential-in-time sweeps (backward Riccati /
 // costate sweep, LQ forward pass, rollouts); the Armijo candidates add a second thread dimension
 // (candidate x instance) so that the 10 candidates of 32 neighbouring instances share one CTA and hit the
-// same input/reference lines in L1.  All trajectory buffers are struct-of-arrays with the instance index
-// fastest (see acoc_kernels.cuh); host buffers use the reference's (N,6,TT) layout and are transposed on
-// the device through a staging buffer.
+// same input/reference lines in L1.  All trajectory buffers are warp-tiled struct-of-arrays (time, tile of 32 instances,
+// component, lane; see acoc_kernels.cuh); host buffers use the reference's (N,6,TT) layout and are transposed on
+// the device through a staging buffer.  The time sweeps of the Newton loop run as warp-private TMA pipelines
+// (acoc_tma.cuh); the plain-load versions of the same sweeps below are kept for A/B runs (ACOC_NO_TMA).
 //
 // Every sweep kernel is a template on the arithmetic/storage type F (double: the parity path; float: the optional FP32
 // mode, ACOC_FP32) and on the storage type XT of the state iterates (float whenever the states are float32 values anyway,
@@ -106,8 +107,8 @@ __global__ void __launch_bounds__(128) k_traj_cost(ProblemT<F> P, const XT* __re
 // ---- work lists -----------------------------------------------------------------------------------------
 // Late in a solve most instances have terminated and, in the float32-noise phase, only some instances need the
 // remaining Armijo candidates.  Threads are therefore mapped to instances through a compacted, ORDERED list of
-// groups of G = 2^shift consecutive instances that still contain work.  G = 4 (one 32-byte sector of doubles)
-// for the bandwidth-bound sweeps keeps every sector fully used; G = 1 for the compute-bound candidate rollouts.
+// groups of G = 2^shift consecutive instances that still contain work.  G = 32 (one tile = one warp = one TMA block) for the
+// sweeps; G = 1 for the compute-bound candidate rollouts.
 struct WorkList {
     const int* groups;  // nullptr: identity (thread j -> instance j)
     const int* count;   // number of valid groups (device memory)
@@ -179,9 +180,9 @@ __global__ void __launch_bounds__(BWD_THREADS) k_backward(ProblemT<F> P, WorkLis
 {
     const int i = work_instance(L, blockIdx.x * blockDim.x + threadIdx.x, P.N);
     if (i < 0) return;
-    // Lanes of already finished instances inside a live group of 4 run the sweep too: K/sigma/g are per-iteration
-    // scratch, and writing all four lanes keeps every 32-byte sector fully written (a partially written sector costs
-    // a DRAM read-modify-write); the lane would otherwise idle for the same number of warp instructions.
+    // Lanes of already finished instances inside a live group run the sweep too: K/sigma/g are per-iteration scratch, and
+    // writing all lanes keeps every 32-byte sector fully written (a partially written sector costs a DRAM read-modify-write);
+    // the lane would otherwise idle for the same number of warp instructions.
     const int r = backward_instance<EXACT>(P, X, U, KSG, i);
     if (r && status[i] == ST_ACTIVE) n_reg[i] += r;
 }
@@ -1680,7 +1681,7 @@ int acoc_get_deltau(acoc_ctx* c, double* deltau)
 int acoc_get_gains(acoc_ctx* c, double* K, double* sigma)
 {
     TRY(ready(c));
-    // KSG is [TT][16][Np]; as a "C = 16" trajectory it downloads to (N,16,TT): rows 0..11 = K (2x6 row-major), 12..13 = sigma
+    // KSG is a warp-tiled trajectory with 16 components; as a "C = 16" trajectory it downloads to (N,16,TT): rows 0..11 = K (2x6 row-major), 12..13 = sigma
     std::vector<double> tmp((size_t)c->N * 16 * c->TT);
     TRY(download_soa(c, c->KSG, nullptr, nullptr, nullptr, tmp.data(), c->N, 16, c->Np, 0));
     const size_t TT = c->TT;

@@ -350,7 +350,7 @@ ACOC_HD int backward_instance(const ProblemT<F>& P, const XT* X, const F* U, F* 
 // du_t = sigma_t + K_t dx_t ; dx_{t+1} = A_t dx_t + B_t du_t (optcon.py:759-760 with x~ = [1; dx], x0 = 0);
 // descent = sum_t g_t' du_t (optcon.py:474-477).  A_t, B_t are recomputed from (x_t,u_t) instead of being
 // stored by the backward sweep (12 doubles per step of HBM traffic saved for ~60 flops and two sincos).
-// DX (optional, [TT][6][Np]) receives the state increments for the drop-in ltv_LQR-style outputs.
+// DX (optional, warp-tiled like X) receives the state increments for the drop-in ltv_LQR-style outputs.
 // one time step: ksg = (K row-major 2x6, sigma, g) of this step; dx is advanced in place, du returned, descent accumulated
 template <typename F>
 ACOC_HD void forward_step(const ModelT<F>& M, const F* x, const F* u, const F* ksg, F* dx, F* du, double& descent)
