@@ -65,6 +65,7 @@ static int fail(int code, const char* fmt, ...)
 // kernels
 // ======================================================================================================
 constexpr int ST_PAD = 4;  // padding lanes beyond N: never active
+constexpr unsigned ACOC_CTX_LITE = 0x40000000u;  // internal flag of acoc_ctx_create (not part of the ABI), see there
 
 // granularity of the active-work list of the sweeps: groups of 2^shift consecutive instances that still contain an active one
 #ifndef ACOC_ACT_SHIFT
@@ -851,9 +852,11 @@ int acoc_ctx_create(int device, int n_instances, int TT, unsigned flags, acoc_ct
     c->x_float = c->fp32;
     const size_t es = c->fp32 ? sizeof(float) : sizeof(double);  // the state slots are sized for es too: they may have to hold float64
     int rc = 0;
-    for (int s = 0; s < 3 && !rc; ++s) { rc = dalloc_bytes(c, &c->X[s], T * 6 * Np * es); if (!rc) rc = dalloc_bytes(c, &c->U[s], T * 2 * Np * es); }
-    if (!rc) rc = dalloc_bytes(c, &c->DU, T * 2 * Np * es);
-    if (!rc) rc = dalloc_bytes(c, &c->KSG, T * 16 * Np * es);
+    // (internal) a context that only hosts one trajectory slot: acoc_lqr_tracking rolls out into X[0]/U[0] and needs no Newton state
+    const bool lite = (flags & ACOC_CTX_LITE) != 0;
+    for (int s = 0; s < (lite ? 1 : 3) && !rc; ++s) { rc = dalloc_bytes(c, &c->X[s], T * 6 * Np * es); if (!rc) rc = dalloc_bytes(c, &c->U[s], T * 2 * Np * es); }
+    if (!rc) rc = dalloc_bytes(c, &c->DU, lite ? 64 : T * 2 * Np * es);
+    if (!rc) rc = dalloc_bytes(c, &c->KSG, lite ? 64 : T * 16 * Np * es);
     const bool shared = flags & ACOC_REFS_SHARED;
     if (!rc) rc = dalloc_bytes(c, &c->xref, (shared ? T * 6 : T * 6 * Np) * es);
     if (!rc) rc = dalloc_bytes(c, &c->uref, (shared ? T * 2 : T * 2 * Np) * es);
@@ -1752,7 +1755,7 @@ int acoc_lqr_tracking(int device, int n, int TT, const double* params, int state
 {
     REQUIRE(n > 0 && TT >= 3 && params && Q && R && QT && xx_opt && uu_opt && delta && xx_reg && uu_reg, "acoc_lqr_tracking: bad argument");
     acoc_ctx* c = nullptr;
-    TRY(acoc_ctx_create(device, n, TT, (state_f64 ? ACOC_STATE_F64 : 0) | ACOC_REFS_SHARED, &c));
+    TRY(acoc_ctx_create(device, n, TT, (state_f64 ? ACOC_STATE_F64 : 0) | ACOC_REFS_SHARED | ACOC_CTX_LITE, &c));
     struct Guard { acoc_ctx* c; ~Guard() { acoc_ctx_destroy(c); } } guard{c};
     TRY(acoc_set_model(c, params));
     const Model M = c->P.M;
