@@ -1064,13 +1064,14 @@ static TileList tile_list(acoc_ctx* c, bool use_list = true)
 }
 // instance range and need-list counter of the current launch scope
 static int scope_i0(const acoc_ctx* c) { return c->ls_off * 32; }
-static int scope_i1(const acoc_ctx* c) { return (int)std::min<long long>(c->N, (long long)std::min(c->Np / 32, c->ls_end) * 32); }
+static int n_tiles(const acoc_ctx* c) { return (c->N + 31) / 32; }  // tiles that hold instances (a child context may use less than its capacity Np)
+static int scope_i1(const acoc_ctx* c) { return (int)std::min<long long>(c->N, (long long)std::min(n_tiles(c), c->ls_end) * 32); }
 static int* scope_need_count(acoc_ctx* c) { return c->counters + (c->ls_range == 0 ? 2 : 3 + c->ls_range); }
 // stream and grid of a sweep launch in the current launch scope (the whole padded batch, or a range of its tiles)
 static cudaStream_t sweep_stream(const acoc_ctx* c) { return c->ls_stream ? c->ls_stream : c->stream; }
 static int sweep_grid(const acoc_ctx* c, int threads)
 {
-    const int tiles = std::min(c->Np / 32, c->ls_end) - c->ls_off;
+    const int tiles = std::max(1, std::min(n_tiles(c), c->ls_end) - c->ls_off);
     return (tiles * 32 + threads - 1) / threads;
 }
 template <typename K>
@@ -1314,7 +1315,7 @@ int acoc_newton_iterate(acoc_ctx* c, int n_iters, int* n_active_out)
         // instance ranges on two streams (every kernel of an iteration takes a tile / instance range): one range's bandwidth-bound
         // forward and rollout sweeps fill the machine while the other's backward sweep is latency-bound, across iteration
         // boundaries too.  Instances are independent, so the split changes no result; the streams join before the call returns.
-        const int ctas = (c->Np / 32 + 1) / 2, wave = c->bwd_wave_ctas;
+        const int ctas = (n_tiles(c) + 1) / 2, wave = c->bwd_wave_ctas;
         if (use_tma(c) && is_lazy(c) && !prof && c->all_active && !(c->flags & ACOC_NO_SPLIT) && c->kk > 0 && wave > 0 && ctas > wave &&
             ctas % wave != 0)
             break;
@@ -1344,8 +1345,7 @@ int acoc_newton_iterate(acoc_ctx* c, int n_iters, int* n_active_out)
         ++c->kk;
     }
     if (it < n_iters && c->kk < c->O.max_iters - 1) {  // the remaining iterations as two independent ranges (see above)
-        const int ctas = (c->Np / 32 + 1) / 2, wave = c->bwd_wave_ctas;
-        const int tiles = c->Np / 32;
+        const int tiles = n_tiles(c), ctas = (tiles + 1) / 2, wave = c->bwd_wave_ctas;
         int bound[5] = {0, (ctas / wave) * wave * 2, tiles, tiles, tiles}, nr = 2;
         if (const char* e = getenv("ACOC_RANGES")) {  // tuning experiments: up to three ascending tile boundaries "a,b,c"
             nr = 1;

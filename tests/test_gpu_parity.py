@@ -456,11 +456,14 @@ def test_tma_rings_and_plain_loads_identical(gpu):
     assert np.array_equal(a[5][act], b[5][act]) and np.array_equal(a[6][0][act], b[6][0][act])
 
 
-def test_two_range_sweep_identical(gpu):
+@pytest.mark.parametrize("n", [40001, 90001])
+def test_two_range_sweep_identical(gpu, n):
     """A fully active batch with more backward CTAs than fit on the device at once (4 per SM x 148 SMs = 592 CTAs of 64 instances) is
     swept as two independent tile ranges on two streams.  Instances are independent, so results, histories and statistics must be
-    bit-identical to the single-stream sweep -- checked on a ragged 40,001-instance batch (626 CTAs) through a whole solve."""
-    n, TT = 40001, 48
+    bit-identical to the single-stream sweep -- checked on ragged 40,001- and 90,001-instance batches (626 / 1407 CTAs; the survivor
+    generations of the larger one are themselves big enough to be split while holding fewer instances than their capacity) through a
+    whole solve."""
+    TT = 48
     xr, ur, Q, R, QT = _random_batch(n, TT, 23, 0.048)
     out = []
     for split in (True, False):
