@@ -90,6 +90,18 @@ constexpr int CAND_MAXY = 10;              // candidates per CTA; more candidate
         else kernel<false, ACOC_UNPAREN targs><<<grid, block, 0, stream>>>(__VA_ARGS__);     \
     } while (0)
 #define ACOC_UNPAREN(...) __VA_ARGS__
+// k_candidates<Q32, F, MAXY>: ny = candidates per CTA (blockDim.y <= CAND_MAXY); the 9-wide instantiation when it fits
+#define LAUNCH_CAND(q32, F_, grid, ny, stream, ...)                                                        \
+    do {                                                                                                  \
+        const dim3 blk__(CAND_TILE, (ny));                                                                \
+        if ((ny) <= 9) {                                                                                  \
+            if (q32) k_candidates<true, F_, 9><<<grid, blk__, 0, stream>>>(__VA_ARGS__);                  \
+            else k_candidates<false, F_, 9><<<grid, blk__, 0, stream>>>(__VA_ARGS__);                     \
+        } else {                                                                                          \
+            if (q32) k_candidates<true, F_, CAND_MAXY><<<grid, blk__, 0, stream>>>(__VA_ARGS__);          \
+            else k_candidates<false, F_, CAND_MAXY><<<grid, blk__, 0, stream>>>(__VA_ARGS__);             \
+        }                                                                                                 \
+    } while (0)
 
 // pick the instantiation of a host-side launch template for a context: <F, XT> or <F>
 #define DISPATCH_FX(c, fn, ...) \
@@ -200,8 +212,10 @@ __global__ void __launch_bounds__(FWD_THREADS) k_forward(ProblemT<F> P, WorkList
 }
 
 // thread (x = position in the work list, y = candidate): J of candidate c0 + y for instance i
-template <bool Q32, typename F>
-__global__ void __launch_bounds__(CAND_TILE * CAND_MAXY, ACOC_CAND_MINB)
+// MAXY: most candidates (blockDim.y) per CTA.  9 (the lazy search: candidates 1..9) lets three CTAs per SM use 72 registers with
+// no spills to speak of; 10 (all candidates at once) gets 64.
+template <bool Q32, typename F, int MAXY>
+__global__ void __launch_bounds__(CAND_TILE * MAXY, ACOC_CAND_MINB)
 k_candidates(ProblemT<F> P, WorkList L, const F* __restrict__ U, const F* __restrict__ DU, const double* __restrict__ cand_steps, int c0,
              int c1, const int* __restrict__ status, double* __restrict__ Jcand)
 {
@@ -1203,26 +1217,23 @@ static int launch_armijo_t(acoc_ctx* c, bool* lazy_only)
         // few candidates (mean 2.6 / 1.9 candidates in iterations 0 / 1 of config 4): candidates 1..3 first, the rest only where
         // those failed too.  Later (float32-noise phase) the search usually runs to the end and one round of 1..9 is cheaper.
         const int split = (c->kk <= c->O.exact_after && nc > 5) ? 4 : nc;
-        dim3 block(CAND_TILE, std::min(split - 1, CAND_MAXY));
-        LAUNCH_Q32(c->P.q32, k_candidates, (F), (n + CAND_TILE - 1) / CAND_TILE, block, st, P, L, U, DU, c->cand_steps, 1, split, c->S.status,
-                   c->S.Jcand);
+        LAUNCH_CAND(c->P.q32, F, (n + CAND_TILE - 1) / CAND_TILE, std::min(split - 1, CAND_MAXY), st, P, L, U, DU, c->cand_steps, 1, split, c->S.status,
+                    c->S.Jcand);
         CK(cudaGetLastError());
         if (split < nc) {
             k_lazy_need<<<(n + 255) / 256, 256, 0, st>>>(c->O, c->S, c->cand_steps, i0, i1, Np, split, c->need2);
             CK(cudaGetLastError());
             k_build_list<<<1, 1024, 0, st>>>(c->need2, 1, n, 0, c->need_groups + i0, cnt, i0);
             CK(cudaGetLastError());
-            dim3 block2(CAND_TILE, std::min(nc - split, CAND_MAXY));
-            LAUNCH_Q32(c->P.q32, k_candidates, (F), (n + CAND_TILE - 1) / CAND_TILE, block2, st, P, L, U, DU, c->cand_steps, split, nc, c->S.status,
-                       c->S.Jcand);
+            LAUNCH_CAND(c->P.q32, F, (n + CAND_TILE - 1) / CAND_TILE, std::min(nc - split, CAND_MAXY), st, P, L, U, DU, c->cand_steps, split, nc,
+                        c->S.status, c->S.Jcand);
             CK(cudaGetLastError());
             c->launches += 3;
         }
         *lazy_only = true;
     } else {
-        dim3 block(CAND_TILE, std::min(nc, CAND_MAXY));
-        LAUNCH_Q32(c->P.q32, k_candidates, (F), (Np + CAND_TILE - 1) / CAND_TILE, block, c->stream, P, act_list(c), U, DU, c->cand_steps, 0, nc,
-                   c->S.status, c->S.Jcand);
+        LAUNCH_CAND(c->P.q32, F, (Np + CAND_TILE - 1) / CAND_TILE, std::min(nc, CAND_MAXY), c->stream, P, act_list(c), U, DU, c->cand_steps, 0, nc,
+                    c->S.status, c->S.Jcand);
         CK(cudaGetLastError());
         ++c->launches;
     }
@@ -1595,9 +1606,8 @@ static int launch_all_candidates_t(acoc_ctx* c)
     const int cur = c->kk % 3, N = c->N, nc = c->O.armijo_maxiters;
     WorkList L;
     L.groups = nullptr; L.count = c->counters + 1; L.shift = 0;
-    dim3 block(CAND_TILE, std::min(nc, CAND_MAXY));
-    LAUNCH_Q32(c->P.q32, k_candidates, (F), (N + CAND_TILE - 1) / CAND_TILE, block, c->stream, prob<F>(c), L, (const F*)c->U[cur], (const F*)c->DU,
-               c->cand_steps, 0, nc, c->S.status, c->S.Jcand);
+    LAUNCH_CAND(c->P.q32, F, (N + CAND_TILE - 1) / CAND_TILE, std::min(nc, CAND_MAXY), c->stream, prob<F>(c), L, (const F*)c->U[cur],
+                (const F*)c->DU, c->cand_steps, 0, nc, c->S.status, c->S.Jcand);
     CK(cudaGetLastError());
     return 0;
 }
