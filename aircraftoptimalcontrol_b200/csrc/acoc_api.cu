@@ -1162,7 +1162,19 @@ static int launch_forward_t(acoc_ctx* c)
 static int launch_forward(acoc_ctx* c) { return DISPATCH_FX(c, launch_forward_t, c); }
 // Armijo: fills S.step and the history row kk.  Returns through *lazy_only whether the update may skip
 // instances whose candidate 0 is already in the next slot.
-static bool is_lazy(const acoc_ctx* c) { return (c->flags & ACOC_ARMIJO_LAZY) && c->O.armijo_maxiters > 1; }
+// The lazy search saves work, the speculative one a sequential sweep: a small batch (a late survivor generation, a handful of
+// trajectories) is latency-bound -- about 1 ms per sweep whatever its size -- and some instance fails candidate 0 in nearly every
+// iteration of the float32-noise phase, so lazy costs five sweeps in a row there (backward, forward, candidate 0, candidates 1..9,
+// update) against four for speculative (backward, forward, all candidates, update).  Same results either way.
+#ifndef ACOC_SPECULATIVE_MAX_N
+#define ACOC_SPECULATIVE_MAX_N 4096
+#endif
+static bool is_lazy(const acoc_ctx* c)
+{
+    static const int spec_max = getenv("ACOC_SPECULATIVE_MAX_N") ? atoi(getenv("ACOC_SPECULATIVE_MAX_N")) : ACOC_SPECULATIVE_MAX_N;
+    // (in the Gauss-Newton iterations candidate 0 is accepted almost everywhere and lazy is three sweeps: keep it there)
+    return (c->flags & ACOC_ARMIJO_LAZY) && c->O.armijo_maxiters > 1 && (c->N > spec_max || c->kk <= c->O.exact_after);
+}
 
 // lazy Armijo, first round: candidate 0 for every active instance, written tentatively into the next slot
 template <typename F, typename XT>
