@@ -21,6 +21,7 @@ FP32 = 16
 X_F64 = 32
 NO_TMA = 64
 NO_SPLIT = 128
+NO_FUSED = 256
 
 INST_ACTIVE, INST_CONVERGED, INST_MAXITER, INST_NONFINITE = 0, 1, 2, 3
 

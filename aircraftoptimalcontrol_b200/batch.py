@@ -32,11 +32,13 @@ class BatchedNewton:
     (bit-identical results, A/B measurements).
     split: sweep a fully active batch that needs more than one round of resident backward CTAs as two tile ranges on two streams
     (default; identical results, A/B measurements).
+    fused: batches of at most 4096 instances (late survivor generations, single trajectories) run the LQ forward pass and the whole
+    Armijo search as one sweep and take get_update as a copy of the chosen candidate (default; identical results, A/B measurements).
     """
 
     def __init__(self, n_instances, TT=1000, device=0, state="f32", refs_shared=False, armijo="speculative", params=None, generations=True,
                  max_iters=200, stepsize_0=1.0, cc=0.5, beta=0.7, armijo_maxiters=10, term_cond=-1e-6, exact_after=8, precision="f64",
-                 x_storage="auto", tma=True, split=True):
+                 x_storage="auto", tma=True, split=True, fused=True):
         if state not in ("f32", "f64"):
             raise ValueError("state must be 'f32' or 'f64'")
         if armijo not in ("speculative", "lazy"):
@@ -50,7 +52,7 @@ class BatchedNewton:
         self.precision = precision
         flags = ((L.STATE_F64 if state == "f64" else 0) | (L.REFS_SHARED if refs_shared else 0) | (L.ARMIJO_LAZY if armijo == "lazy" else 0)
                  | (0 if generations else L.SOLVE_IN_PLACE) | (L.FP32 if precision == "f32" else 0) | (L.X_F64 if x_storage == "f64" else 0)
-                 | (0 if tma else L.NO_TMA) | (0 if split else L.NO_SPLIT))
+                 | (0 if tma else L.NO_TMA) | (0 if split else L.NO_SPLIT) | (0 if fused else L.NO_FUSED))
         self._h = C.c_void_p(None)
         L.check(L.lib().acoc_ctx_create(self.device, self.N, self.TT, flags, C.addressof(self._h)))
         self.opts = L.NewtonOptions(int(max_iters), int(armijo_maxiters), int(exact_after), 0, float(stepsize_0), float(cc), float(beta),

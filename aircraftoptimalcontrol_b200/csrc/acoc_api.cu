@@ -225,6 +225,151 @@ k_candidates(ProblemT<F> P, WorkList L, const F* __restrict__ U, const F* __rest
         Jcand[(size_t)c * P.Np + i] = rollout_instance<false, true, Q32>(P, U, DU, cand_steps[c], (F*)nullptr, (F*)nullptr, i);
 }
 
+// ---- small batches: the whole line search in ONE sweep -------------------------------------------------------------------------
+// A batch of a few thousand instances (a late survivor generation, a single trajectory) is latency-bound: every time sweep costs
+// about 1 us per step whatever the batch size, so an iteration costs as many milliseconds as it has sequential sweeps.  Both the LQ
+// forward pass and the Armijo rollouts run forward in time and candidate c needs du_t only at step t, so they run as ONE sweep:
+// CTA = one tile of 32 instances, warp y < n_rows = the rollout of step cand_steps[y] (the armijo_maxiters candidates and, as the last
+// row, the untested step the search falls back to on exhaustion, optcon.py:327), warp n_rows = the LQ forward pass one step ahead of
+// them, handing du_t over through a double-buffered shared-memory slot with one barrier per step.  Every row keeps its trajectory
+// (Xc / Uc: one trajectory slot per row), so that get_update is a copy of the chosen row (k_pick) instead of one more sweep.
+// Inputs of the next step are fetched into registers before the arithmetic of the current one.  Same per-step functions as the
+// separate sweeps (forward_step, rollout_step), so the results are bit-identical to them.
+constexpr int FUSE_MAXROWS = 11;
+template <bool Q32, typename F, typename XT>
+__global__ void __launch_bounds__(TILE * (FUSE_MAXROWS + 1))
+k_search_fused(ProblemT<F> P, TileList L, const XT* __restrict__ X, const F* __restrict__ U, const F* __restrict__ KSG, F* __restrict__ DU,
+               const double* __restrict__ cand_steps, int n_rows, XT* __restrict__ Xc, F* __restrict__ Uc, size_t row_x, size_t row_u,
+               const int* __restrict__ status, double* __restrict__ descent, double* __restrict__ Jcand)
+{
+    __shared__ F sdu[2][NI][TILE];
+    const int tile = warp_tile(L, blockIdx.x, P.Np);
+    if (tile < 0) return;  // (uniform over the CTA)
+    const int lane = threadIdx.x, row = threadIdx.y, TT = P.TT, Np = P.Np;
+    const int i = tile * TILE + lane;
+    const bool valid = i < P.N;
+    const bool fwd = row == n_rows;
+    // finished lanes of a live tile: the forward pass keeps writing du (scratch, whole lines); the rollouts skip them
+    const bool act = valid && (fwd || status[i] == ST_ACTIVE);
+    // forward-pass warp
+    F dx[NS] = {F(0.0), F(0.0), F(0.0), F(0.0), F(0.0), F(0.0)}, ksg_n[16];
+    XT xraw_n[NS];
+    double acc = 0.0;  // descent (forward warp) / cost (rollout warps)
+    // rollout warps
+    F x[NS], xr_n[NS], ur_n[NI];
+    F u_n[NI];  // both roles: u_t of the nominal iterate, fetched one step ahead
+    F s = F(0.0);
+    XT* Xn = nullptr;
+    F* Un = nullptr;
+    if (act) {
+#pragma unroll
+        for (int c = 0; c < NI; ++c) u_n[c] = U[at(0, NI, c, Np, i)];
+        if (fwd) {
+            load_x_raw(X, 0, Np, i, xraw_n);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) ksg_n[c] = KSG[at(0, 16, c, Np, i)];
+        } else {
+            s = (F)cand_steps[row];
+            Xn = Xc + (size_t)row * row_x;
+            Un = Uc + (size_t)row * row_u;
+#pragma unroll
+            for (int c = 0; c < NS; ++c) x[c] = P.x0[(size_t)c * Np + i];
+            load_ref(P, 0, i, xr_n, ur_n);
+        }
+    }
+    for (int tau = 0; tau < TT; ++tau) {
+        if (fwd) {
+            if (act && tau < TT - 1) {
+                F xx[NS], u[NI], ksg[16], du[NI];
+                finish_x(P, tau, i, xraw_n, xx);
+#pragma unroll
+                for (int c = 0; c < NI; ++c) u[c] = u_n[c];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) ksg[c] = ksg_n[c];
+                if (tau + 1 < TT - 1) {
+                    load_x_raw(X, tau + 1, Np, i, xraw_n);
+#pragma unroll
+                    for (int c = 0; c < NI; ++c) u_n[c] = U[at(tau + 1, NI, c, Np, i)];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) ksg_n[c] = KSG[at(tau + 1, 16, c, Np, i)];
+                }
+                forward_step(P.M, xx, u, ksg, dx, du, acc);
+                DU[at(tau, NI, 0, Np, i)] = du[0];
+                DU[at(tau, NI, 1, Np, i)] = du[1];
+                sdu[tau & 1][0][lane] = du[0];
+                sdu[tau & 1][1][lane] = du[1];
+            }
+        } else if (act && tau >= 1) {
+            const int t = tau - 1;
+            F u[NI], xr[NS], ur[NI];
+#pragma unroll
+            for (int c = 0; c < NI; ++c) u[c] = u_n[c] + s * sdu[t & 1][c][lane];  // optcon.py:197 / :253
+#pragma unroll
+            for (int c = 0; c < NS; ++c) xr[c] = xr_n[c];
+#pragma unroll
+            for (int c = 0; c < NI; ++c) ur[c] = ur_n[c];
+            if (t + 1 < TT - 1) {
+#pragma unroll
+                for (int c = 0; c < NI; ++c) u_n[c] = U[at(t + 1, NI, c, Np, i)];
+                load_ref(P, t + 1, i, xr_n, ur_n);
+            }
+            store_x(Xn, t, Np, i, x);
+#pragma unroll
+            for (int c = 0; c < NI; ++c) Un[at(t, NI, c, Np, i)] = u[c];
+            rollout_step<true, Q32>(P.M, P.W, x, u, xr, ur, acc);
+        }
+        __syncthreads();
+    }
+    if (!act) return;
+    if (fwd) {
+        DU[at(TT - 1, NI, 0, Np, i)] = F(0.0);  // uuout[:, TT-1] stays zero (optcon.py:694)
+        DU[at(TT - 1, NI, 1, Np, i)] = F(0.0);
+        if (status[i] == ST_ACTIVE) descent[i] = acc;
+    } else {
+        store_x(Xn, TT - 1, Np, i, x);
+        Un[at(TT - 1, NI, 0, Np, i)] = F(0.0);  // uu_temp[:, TT-1] is never written (optcon.py:193)
+        Un[at(TT - 1, NI, 1, Np, i)] = F(0.0);
+        F xr[NS], dxT[NS];
+        load_xref(P, TT - 1, i, xr);
+#pragma unroll
+        for (int c = 0; c < NS; ++c) dxT[c] = x[c] - xr[c];
+        acc += (double)term_cost(P.W, dxT);
+        Jcand[(size_t)row * Np + i] = acc;
+    }
+}
+
+// get_update as a copy: the row of the step k_select chose (row armijo_maxiters after exhaustion) becomes the next iterate; thread
+// (x = lane, y = time lane), blockIdx.x = position in the tile list, blockIdx.y strides over time.  Jpick[i] = cost of that row.
+template <typename F, typename XT>
+__global__ void k_pick(TileList L, NewtonOpts O, NewtonState S, const double* __restrict__ cand_steps, const XT* __restrict__ Xc,
+                       const F* __restrict__ Uc, size_t row_x, size_t row_u, XT* __restrict__ Xn, F* __restrict__ Un, int N, int Np, int TT,
+                       double* __restrict__ Jpick)
+{
+    const int tile = warp_tile(L, blockIdx.x, Np);
+    if (tile < 0) return;
+    const int i = tile * TILE + threadIdx.x;
+    if (i >= N || S.status[i] != ST_ACTIVE) return;
+    const double s = S.step[i];
+    int r = O.armijo_maxiters;
+    for (int c = 0; c < O.armijo_maxiters; ++c) if (cand_steps[c] == s) { r = c; break; }
+    const XT* xs = Xc + (size_t)r * row_x;
+    const F* us = Uc + (size_t)r * row_u;
+    for (int t = blockIdx.y * blockDim.y + threadIdx.y; t < TT; t += gridDim.y * blockDim.y) {
+#pragma unroll
+        for (int c = 0; c < NS; ++c) Xn[at(t, NS, c, Np, i)] = xs[at(t, NS, c, Np, i)];
+#pragma unroll
+        for (int c = 0; c < NI; ++c) Un[at(t, NI, c, Np, i)] = us[at(t, NI, c, Np, i)];
+    }
+    if (blockIdx.y == 0 && threadIdx.y == 0) Jpick[i] = S.Jcand[(size_t)r * Np + i];
+}
+
+// termination test and result-slot bookkeeping after k_pick (a separate launch: k_pick's CTAs read the status it changes)
+__global__ void k_finish(NewtonOpts O, NewtonState S, const double* __restrict__ Jpick, int kk, int N)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N && S.status[i] == ST_ACTIVE) newton_finish_instance(O, S, Jpick[i], kk, i);
+}
+
 // lazy Armijo, first round: candidate 0 for every active instance, writing the trajectory tentatively into
 // the next slot (it IS the update whenever the candidate is accepted)
 template <bool Q32, typename F, typename XT>
@@ -544,6 +689,11 @@ struct acoc_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
     bool all_active = false;    // more than half of the instances were active at the last host-side count (reset: all of them)
     int bwd_wave_ctas = 0;      // CTAs of the backward sweep that are resident at once on this device (occupancy x SMs)
+    // small batches: one trajectory slot per Armijo candidate (+ the exhausted step), see k_search_fused
+    void *candX = nullptr, *candU = nullptr;
+    double* candJ = nullptr;    // [Np] cost of the row k_pick copied
+    size_t cand_bytes_x = 0, cand_bytes_u = 0;
+    bool cand_failed = false;   // the buffers could not be allocated: separate sweeps
 };
 
 static int dalloc_bytes(acoc_ctx* c, void** p, size_t bytes)
@@ -1289,6 +1439,80 @@ static int launch_update(acoc_ctx* c, bool lazy_only, bool bookkeeping, bool use
     return DISPATCH_FX(c, launch_update_t, c, lazy_only, bookkeeping, use_list);
 }
 
+// ---- small batches: fused line search (k_search_fused, k_pick, k_finish) -----------------------------------------------------
+#ifndef ACOC_FUSED_MAX_N
+#define ACOC_FUSED_MAX_N 4096
+#endif
+// Whether this context runs its iterations with the fused line search; allocates the per-row trajectory slots on first use
+// (rows x ~40 KB per instance: 1.8 GB for 4096 instances) and falls back to the separate sweeps if that fails.
+template <typename F, typename XT>
+static bool fused_search_t(acoc_ctx* c)
+{
+    static const int fuse_max = getenv("ACOC_FUSED_MAX_N") ? atoi(getenv("ACOC_FUSED_MAX_N")) : ACOC_FUSED_MAX_N;
+    const size_t rows = (size_t)c->O.armijo_maxiters + 1;
+    if (ACOC_ACT_SHIFT != 5 || c->N > fuse_max || rows > (size_t)FUSE_MAXROWS || c->cand_failed || c->ls_identity || (c->flags & ACOC_NO_FUSED))
+        return false;
+    const size_t bx = rows * c->TT * NS * c->Np * sizeof(XT), bu = rows * c->TT * NI * c->Np * sizeof(F);
+    if (c->cand_bytes_x < bx) {
+        if (dalloc_bytes(c, &c->candX, bx)) { c->cand_failed = true; return false; }
+        c->cand_bytes_x = bx;
+    }
+    if (c->cand_bytes_u < bu) {
+        if (dalloc_bytes(c, &c->candU, bu)) { c->cand_failed = true; return false; }
+        c->cand_bytes_u = bu;
+    }
+    if (!c->candJ && dalloc(c, &c->candJ, (size_t)c->Np)) { c->cand_failed = true; return false; }
+    return true;
+}
+static bool fused_search(acoc_ctx* c) { return DISPATCH_FX(c, fused_search_t, c); }
+
+// LQ forward pass + every Armijo candidate (+ the exhausted step) in one sweep, trajectories kept per row
+template <typename F, typename XT>
+static int launch_fused_sweep_t(acoc_ctx* c)
+{
+    const int cur = c->kk % 3, rows = c->O.armijo_maxiters + 1;
+    const size_t rx = (size_t)c->TT * NS * c->Np, ru = (size_t)c->TT * NI * c->Np;
+    const dim3 blk(TILE, rows + 1);
+    if (c->P.q32)
+        k_search_fused<true, F, XT><<<n_tiles(c), blk, 0, c->stream>>>(prob<F>(c), tile_list(c), (const XT*)c->X[cur], (const F*)c->U[cur],
+                                                                      (const F*)c->KSG, (F*)c->DU, c->cand_steps, rows, (XT*)c->candX,
+                                                                      (F*)c->candU, rx, ru, c->S.status, c->S.descent, c->S.Jcand);
+    else
+        k_search_fused<false, F, XT><<<n_tiles(c), blk, 0, c->stream>>>(prob<F>(c), tile_list(c), (const XT*)c->X[cur], (const F*)c->U[cur],
+                                                                       (const F*)c->KSG, (F*)c->DU, c->cand_steps, rows, (XT*)c->candX,
+                                                                       (F*)c->candU, rx, ru, c->S.status, c->S.descent, c->S.Jcand);
+    CK(cudaGetLastError());
+    ++c->launches;
+    return 0;
+}
+static int launch_fused_sweep(acoc_ctx* c) { return DISPATCH_FX(c, launch_fused_sweep_t, c); }
+
+static int launch_fused_select(acoc_ctx* c)
+{
+    k_select<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->O, c->S, c->cand_steps, c->kk, 0, c->N, c->Np);
+    CK(cudaGetLastError());
+    ++c->launches;
+    return 0;
+}
+
+// get_update (copy of the chosen row into the next slot) + termination bookkeeping
+template <typename F, typename XT>
+static int launch_fused_pick_t(acoc_ctx* c)
+{
+    const int nxt = (c->kk + 1) % 3, tiles = n_tiles(c);
+    const size_t rx = (size_t)c->TT * NS * c->Np, ru = (size_t)c->TT * NI * c->Np;
+    const int gy = std::max(1, std::min((c->TT + 7) / 8, 1184 / tiles));
+    k_pick<F, XT><<<dim3(tiles, gy), dim3(TILE, 8), 0, c->stream>>>(tile_list(c), c->O, c->S, c->cand_steps, (const XT*)c->candX,
+                                                                    (const F*)c->candU, rx, ru, (XT*)c->X[nxt], (F*)c->U[nxt], c->N, c->Np,
+                                                                    c->TT, c->candJ);
+    CK(cudaGetLastError());
+    k_finish<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->O, c->S, c->candJ, c->kk, c->N);
+    CK(cudaGetLastError());
+    c->launches += 2;
+    return 0;
+}
+static int launch_fused_pick(acoc_ctx* c) { return DISPATCH_FX(c, launch_fused_pick_t, c); }
+
 static int count_active(acoc_ctx* c, int* n_active, long long* iters_sum)
 {
     CK(cudaMemsetAsync(c->counters, 0, sizeof(int), c->stream));
@@ -1313,6 +1537,11 @@ static int launch_iteration_body(acoc_ctx* c)
 {
     bool lazy_only = false;
     TRY(launch_backward(c, c->kk > c->O.exact_after));  // optcon.py:443
+    if (fused_search(c)) {
+        TRY(launch_fused_sweep(c));
+        TRY(launch_fused_select(c));
+        return launch_fused_pick(c);
+    }
     TRY(launch_forward(c));
     if (is_lazy(c)) TRY(launch_cand0(c));
     TRY(launch_armijo(c, &lazy_only));
@@ -1349,12 +1578,20 @@ int acoc_newton_iterate(acoc_ctx* c, int n_iters, int* n_active_out)
         if (prof) CK(cudaEventRecord(c->ev[1], c->stream));
         TRY(launch_backward(c, c->kk > c->O.exact_after));  // optcon.py:443
         if (prof) CK(cudaEventRecord(c->ev[2], c->stream));
-        TRY(launch_forward(c));
-        if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
-        if (is_lazy(c)) TRY(launch_cand0(c));
-        TRY(launch_armijo(c, &lazy_only));
-        if (prof) CK(cudaEventRecord(c->ev[4], c->stream));
-        TRY(launch_update(c, lazy_only, true, true));
+        if (fused_search(c)) {  // small batch: forward pass and line search in one sweep, get_update as a copy
+            TRY(launch_fused_sweep(c));
+            if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
+            TRY(launch_fused_select(c));
+            if (prof) CK(cudaEventRecord(c->ev[4], c->stream));
+            TRY(launch_fused_pick(c));
+        } else {
+            TRY(launch_forward(c));
+            if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
+            if (is_lazy(c)) TRY(launch_cand0(c));
+            TRY(launch_armijo(c, &lazy_only));
+            if (prof) CK(cudaEventRecord(c->ev[4], c->stream));
+            TRY(launch_update(c, lazy_only, true, true));
+        }
         if (prof) {
             CK(cudaEventRecord(c->ev[5], c->stream));
             CK(cudaEventSynchronize(c->ev[5]));

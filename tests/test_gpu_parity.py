@@ -485,3 +485,37 @@ def test_two_range_sweep_identical(gpu, n):
         assert np.array_equal(a[4][k], b[4][k]), k
     for k in ("iters", "status", "J", "descent", "n_reg"):
         assert np.array_equal(a[5][k], b[5][k]), k
+
+
+@pytest.mark.parametrize("state,armijo,n,TT", [("f32", "lazy", 1000, 1000), ("f32", "speculative", 37, 300), ("f64", "lazy", 300, 300)])
+def test_fused_search_identical(gpu, state, armijo, n, TT):
+    """Small batches run the LQ forward pass, every Armijo candidate and the exhausted step as ONE sweep (k_search_fused) and take
+    get_update as a copy of the chosen row (k_pick).  It is the same per-step arithmetic as the separate sweeps, so whole solves must
+    agree bit for bit with fused=False -- ragged batches (padding lanes, finished lanes inside live tiles), both state modes, both
+    Armijo modes, searches that run to exhaustion (the float32-noise phase), max_iters small enough that some instances stop at the
+    iteration limit (their result IS the last copied slot)."""
+    xr, ur, Q, R, QT = _random_batch(n, TT, 31, TT * 1e-3)
+    out = []
+    for fused in (True, False):
+        with gpu.BatchedNewton(n, TT=TT, armijo=armijo, state=state, fused=fused, max_iters=26) as bn:
+            bn.set_weights(Q, R, QT)
+            bn.set_refs(xr, ur)
+            bn.init_guess()
+            bn.iterate(2)
+            launches = bn.timing()["launches"]
+            mid = bn.iterate_at(0)
+            total = bn.solve()
+            out.append((total, mid, bn.result(), bn.iterate_at(0), bn.history(), bn.stats(), launches, bn.deltau()))
+    a, b = out
+    if armijo == "lazy":
+        assert a[6] != b[6]  # the fused path really ran (different number of launches per iteration; speculative: six either way)
+    assert a[0] == b[0]
+    for k in (1, 2, 3):
+        assert np.array_equal(a[k][0], b[k][0]) and np.array_equal(a[k][1], b[k][1]), k
+    for k in ("JJ", "descent", "stepsize", "n_armijo"):
+        assert np.array_equal(a[4][k], b[4][k]), k
+    for k in ("iters", "status", "J", "descent", "n_reg"):
+        assert np.array_equal(a[5][k], b[5][k]), k
+    assert np.any(a[4]["n_armijo"] == 10) and np.any(a[5]["status"] == 2) and np.any(a[5]["status"] == 1)
+    act = a[5]["iters"] == a[5]["iters"].max()
+    assert np.array_equal(a[7][act], b[7][act])
