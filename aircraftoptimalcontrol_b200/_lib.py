@@ -22,6 +22,7 @@ X_F64 = 32
 NO_TMA = 64
 NO_SPLIT = 128
 NO_FUSED = 256
+METHOD_NEWTON, METHOD_GRADIENT = 0, 1
 
 INST_ACTIVE, INST_CONVERGED, INST_MAXITER, INST_NONFINITE = 0, 1, 2, 3
 
@@ -31,7 +32,7 @@ class AcocError(RuntimeError):
 
 
 class NewtonOptions(C.Structure):
-    _fields_ = [("max_iters", C.c_int), ("armijo_maxiters", C.c_int), ("exact_after", C.c_int), ("reserved", C.c_int),
+    _fields_ = [("max_iters", C.c_int), ("armijo_maxiters", C.c_int), ("exact_after", C.c_int), ("method", C.c_int),
                 ("stepsize_0", C.c_double), ("cc", C.c_double), ("beta", C.c_double), ("term_cond", C.c_double)]
 
 
@@ -73,6 +74,8 @@ def _sig(lib):
         "acoc_backward": [vp, i],
         "acoc_forward": [vp, vp],
         "acoc_armijo": [vp, vp, vp],
+        "acoc_gradient": [vp, vp],
+        "acoc_armijo_sweep": [vp, i, vp, vp],
         "acoc_update": [vp, vp],
         "acoc_get_timing": [vp, vp, vp, vp],
         "acoc_set_profiling": [vp, i],

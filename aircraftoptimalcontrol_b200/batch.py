@@ -32,13 +32,17 @@ class BatchedNewton:
     (bit-identical results, A/B measurements).
     split: sweep a fully active batch that needs more than one round of resident backward CTAs as two tile ranges on two streams
     (default; identical results, A/B measurements).
+    method: "newton" runs NewtonMethod.optimize (optcon.py:341); "gradient" runs GradientMethod.optimize (optcon.py:27, steepest
+    descent) with the repaired line-search call described in include/acoc.h (ACOC_METHOD_GRADIENT).  In that mode the `descent`
+    entries of history() / stats() are the slope -sum|deltau|^2 handed to the Armijo test (the reference's descent[kk] is its
+    negative), `term_cond` keeps its meaning (stop when slope >= term_cond, i.e. descent <= 1e-6, optcon.py:52,157).
     fused: batches of at most 4096 instances (late survivor generations, single trajectories) run the LQ forward pass and the whole
     Armijo search as one sweep and take get_update as a copy of the chosen candidate (default; identical results, A/B measurements).
     """
 
     def __init__(self, n_instances, TT=1000, device=0, state="f32", refs_shared=False, armijo="speculative", params=None, generations=True,
                  max_iters=200, stepsize_0=1.0, cc=0.5, beta=0.7, armijo_maxiters=10, term_cond=-1e-6, exact_after=8, precision="f64",
-                 x_storage="auto", tma=True, split=True, fused=True):
+                 x_storage="auto", tma=True, split=True, fused=True, method="newton"):
         if state not in ("f32", "f64"):
             raise ValueError("state must be 'f32' or 'f64'")
         if armijo not in ("speculative", "lazy"):
@@ -47,6 +51,9 @@ class BatchedNewton:
             raise ValueError("precision must be 'f64' or 'f32'")
         if x_storage not in ("auto", "f64"):
             raise ValueError("x_storage must be 'auto' or 'f64'")
+        if method not in ("newton", "gradient"):
+            raise ValueError("method must be 'newton' or 'gradient'")
+        self.method = method
         self.N, self.TT, self.device = int(n_instances), int(TT), int(device)
         self.refs_shared = bool(refs_shared)
         self.precision = precision
@@ -55,7 +62,8 @@ class BatchedNewton:
                  | (0 if tma else L.NO_TMA) | (0 if split else L.NO_SPLIT) | (0 if fused else L.NO_FUSED))
         self._h = C.c_void_p(None)
         L.check(L.lib().acoc_ctx_create(self.device, self.N, self.TT, flags, C.addressof(self._h)))
-        self.opts = L.NewtonOptions(int(max_iters), int(armijo_maxiters), int(exact_after), 0, float(stepsize_0), float(cc), float(beta),
+        self.opts = L.NewtonOptions(int(max_iters), int(armijo_maxiters), int(exact_after),
+                                    L.METHOD_GRADIENT if method == "gradient" else L.METHOD_NEWTON, float(stepsize_0), float(cc), float(beta),
                                     float(term_cond))
         L.check(L.lib().acoc_set_options(self._h, C.addressof(self.opts)))
         if params is not None:
@@ -137,6 +145,21 @@ class BatchedNewton:
         d = np.zeros(self.N)
         L.check(L.lib().acoc_forward(self._h, L.ptr(d)))
         return d
+
+    def gradient(self):
+        """One costate sweep of GradientMethod.optimize (optcon.py:95-118) on the current iterate: writes deltau, returns the
+        reference's descent = sum_t |deltau_t|^2 per instance."""
+        d = np.zeros(self.N)
+        L.check(L.lib().acoc_gradient(self._h, L.ptr(d)))
+        return d
+
+    def armijo_sweep(self, steps):
+        """Costs (N, len(steps)) of the rollouts u + steps[k]*deltau: the data behind the reference's visu_armijo plot
+        (optcon.py:280-296, which uses np.linspace(0, stepsize_0, 10))."""
+        st = L.f64(np.asarray(steps, dtype=np.float64).reshape(-1), None, "steps")
+        costs = np.zeros((self.N, st.size))
+        L.check(L.lib().acoc_armijo_sweep(self._h, int(st.size), L.ptr(st), L.ptr(costs)))
+        return costs
 
     def set_deltau(self, deltau):
         du = L.f64(deltau, (self.N, 2, self.TT), "deltau")

@@ -211,6 +211,17 @@ __global__ void __launch_bounds__(FWD_THREADS) k_forward(ProblemT<F> P, WorkList
     if (status[i] == ST_ACTIVE) descent[i] = d;
 }
 
+// steepest-descent costate sweep (GradientMethod.optimize): deltau and the slope -sum |deltau|^2 (plain-load version)
+template <typename F, typename XT>
+__global__ void __launch_bounds__(FWD_THREADS) k_gradient(ProblemT<F> P, WorkList L, const XT* __restrict__ X, const F* __restrict__ U,
+                                                          F* __restrict__ DU, const int* __restrict__ status, double* __restrict__ descent)
+{
+    const int i = work_instance(L, blockIdx.x * blockDim.x + threadIdx.x, P.N);
+    if (i < 0) return;
+    const double sq = gradient_instance(P, X, U, DU, i);  // finished lanes of a live group: see k_backward
+    if (status[i] == ST_ACTIVE) descent[i] = -sq;
+}
+
 // thread (x = position in the work list, y = candidate): J of candidate c0 + y for instance i
 // MAXY: most candidates (blockDim.y) per CTA.  9 (the lazy search: candidates 1..9) lets three CTAs per SM use 72 registers with
 // no spills to speak of; 10 (all candidates at once) gets 64.
@@ -745,7 +756,7 @@ static int use_device(int device)
 static void default_opts(NewtonOpts* o)
 {
     o->max_iters = 200; o->armijo_maxiters = 10; o->exact_after = 8;
-    o->stepsize_0 = 1.0; o->cc = 0.5; o->beta = 0.7; o->term_cond = -1e-6;
+    o->stepsize_0 = 1.0; o->cc = 0.5; o->beta = 0.7; o->term_cond = -1e-6; o->method = 0;
 }
 
 static int alloc_history(acoc_ctx* c)
@@ -1114,9 +1125,10 @@ int acoc_set_options(acoc_ctx* c, const acoc_newton_options* o)
     REQUIRE(c && o, "NULL argument");
     REQUIRE(o->max_iters >= 2 && o->max_iters <= 100000, "max_iters out of range");
     REQUIRE(o->armijo_maxiters >= 1 && o->armijo_maxiters <= 30, "armijo_maxiters must be in 1..30");
+    REQUIRE(o->method == ACOC_METHOD_NEWTON || o->method == ACOC_METHOD_GRADIENT, "method must be ACOC_METHOD_NEWTON or ACOC_METHOD_GRADIENT");
     TRY(use_device(c->device));
     c->O.max_iters = o->max_iters; c->O.armijo_maxiters = o->armijo_maxiters; c->O.exact_after = o->exact_after;
-    c->O.stepsize_0 = o->stepsize_0; c->O.cc = o->cc; c->O.beta = o->beta; c->O.term_cond = o->term_cond;
+    c->O.stepsize_0 = o->stepsize_0; c->O.cc = o->cc; c->O.beta = o->beta; c->O.term_cond = o->term_cond; c->O.method = o->method;
     TRY(alloc_history(c));  // (old history buffers are released with the context)
     return reset_state(c);
 }
@@ -1293,6 +1305,28 @@ static int launch_backward_t(acoc_ctx* c, bool exact)
 }
 static int launch_backward(acoc_ctx* c, bool exact) { return DISPATCH_FX(c, launch_backward_t, c, exact); }
 
+// GradientMethod.optimize: costate sweep -> deltau, slope (replaces backward + forward of the Newton iteration)
+template <typename F, typename XT>
+static int launch_gradient_t(acoc_ctx* c)
+{
+    const int cur = c->kk % 3;
+    const ProblemT<F> P = prob<F>(c);
+    const XT* X = (const XT*)c->X[cur];
+    const F* U = (const F*)c->U[cur];
+    if (use_tma(c)) {
+        const size_t sm = WarpRing<BWD_STAGES, BwdStage<F, XT>::BYTES>::smem_bytes(BWD_THREADS / 32);
+        TRY(prefer_smem(k_gradient_tma<F, XT>));
+        k_gradient_tma<F, XT><<<sweep_grid(c, BWD_THREADS), BWD_THREADS, sm, sweep_stream(c)>>>(P, tile_list(c), X, U, (F*)c->DU, c->S.status,
+                                                                                             c->S.descent);
+    } else
+        k_gradient<F, XT><<<(c->Np + FWD_THREADS - 1) / FWD_THREADS, FWD_THREADS, 0, c->stream>>>(P, act_list(c), X, U, (F*)c->DU, c->S.status,
+                                                                                               c->S.descent);
+    CK(cudaGetLastError());
+    ++c->launches;
+    return 0;
+}
+static int launch_gradient(acoc_ctx* c) { return DISPATCH_FX(c, launch_gradient_t, c); }
+
 template <typename F, typename XT>
 static int launch_forward_t(acoc_ctx* c)
 {
@@ -1450,7 +1484,8 @@ static bool fused_search_t(acoc_ctx* c)
 {
     static const int fuse_max = getenv("ACOC_FUSED_MAX_N") ? atoi(getenv("ACOC_FUSED_MAX_N")) : ACOC_FUSED_MAX_N;
     const size_t rows = (size_t)c->O.armijo_maxiters + 1;
-    if (ACOC_ACT_SHIFT != 5 || c->N > fuse_max || rows > (size_t)FUSE_MAXROWS || c->cand_failed || c->ls_identity || (c->flags & ACOC_NO_FUSED))
+    if (ACOC_ACT_SHIFT != 5 || c->N > fuse_max || rows > (size_t)FUSE_MAXROWS || c->cand_failed || c->ls_identity || (c->flags & ACOC_NO_FUSED) ||
+        c->O.method != ACOC_METHOD_NEWTON)
         return false;
     const size_t bx = rows * c->TT * NS * c->Np * sizeof(XT), bu = rows * c->TT * NI * c->Np * sizeof(F);
     if (c->cand_bytes_x < bx) {
@@ -1568,17 +1603,25 @@ int acoc_newton_iterate(acoc_ctx* c, int n_iters, int* n_active_out)
         // forward and rollout sweeps fill the machine while the other's backward sweep is latency-bound, across iteration
         // boundaries too.  Instances are independent, so the split changes no result; the streams join before the call returns.
         const int ctas = (n_tiles(c) + 1) / 2, wave = c->bwd_wave_ctas;
+        const bool grad = c->O.method == ACOC_METHOD_GRADIENT;
         if (use_tma(c) && is_lazy(c) && !prof && c->all_active && !(c->flags & ACOC_NO_SPLIT) && c->kk > 0 && wave > 0 && ctas > wave &&
-            ctas % wave != 0)
+            ctas % wave != 0 && !grad)
             break;
         bool lazy_only = false;
         if (prof) CK(cudaEventRecord(c->ev[0], c->stream));
         TRY(launch_build_active(c));
         if (c->kk == 0) TRY(launch_cost(c));  // later iterations inherit the cost from the update rollout
         if (prof) CK(cudaEventRecord(c->ev[1], c->stream));
-        TRY(launch_backward(c, c->kk > c->O.exact_after));  // optcon.py:443
+        if (grad) TRY(launch_gradient(c));                       // optcon.py:95-118
+        else TRY(launch_backward(c, c->kk > c->O.exact_after));  // optcon.py:443
         if (prof) CK(cudaEventRecord(c->ev[2], c->stream));
-        if (fused_search(c)) {  // small batch: forward pass and line search in one sweep, get_update as a copy
+        if (grad) {  // the costate sweep already produced deltau and the slope: straight to the line search
+            if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
+            if (is_lazy(c)) TRY(launch_cand0(c));
+            TRY(launch_armijo(c, &lazy_only));
+            if (prof) CK(cudaEventRecord(c->ev[4], c->stream));
+            TRY(launch_update(c, lazy_only, true, true));
+        } else if (fused_search(c)) {  // small batch: forward pass and line search in one sweep, get_update as a copy
             TRY(launch_fused_sweep(c));
             if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
             TRY(launch_fused_select(c));
@@ -1684,8 +1727,8 @@ static int spawn_child(acoc_ctx* par, int n_active, acoc_ctx** out)
     acoc_ctx* ch = par->child;
     if (ch->O.max_iters != par->O.max_iters || ch->O.armijo_maxiters != par->O.armijo_maxiters) {
         acoc_newton_options o;
-        o.max_iters = par->O.max_iters; o.armijo_maxiters = par->O.armijo_maxiters; o.exact_after = par->O.exact_after; o.reserved = 0;
-        o.stepsize_0 = par->O.stepsize_0; o.cc = par->O.cc; o.beta = par->O.beta; o.term_cond = par->O.term_cond;
+        o.max_iters = par->O.max_iters; o.armijo_maxiters = par->O.armijo_maxiters; o.exact_after = par->O.exact_after;
+        o.stepsize_0 = par->O.stepsize_0; o.cc = par->O.cc; o.beta = par->O.beta; o.term_cond = par->O.term_cond; o.method = par->O.method;
         TRY(acoc_set_options(ch, &o));
     }
     ch->O = par->O;
@@ -1849,6 +1892,21 @@ int acoc_forward(acoc_ctx* c, double* descent)
     return 0;
 }
 
+int acoc_gradient(acoc_ctx* c, double* descent)
+{
+    TRY(ready(c));
+    TRY(launch_build_active(c));
+    TRY(launch_gradient(c));
+    if (descent) {  // the reference's descent[kk] = sum |deltau|^2 (optcon.py:118); the context keeps the slope -descent
+        std::vector<double> tmp(c->N);
+        CK(cudaMemcpyAsync(tmp.data(), c->S.descent, c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < c->N; ++i) descent[i] = -tmp[i];
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 template <typename F>
 static int launch_all_candidates_t(acoc_ctx* c)
 {
@@ -1878,6 +1936,42 @@ int acoc_armijo(acoc_ctx* c, double* stepsize, double* costs)
         for (int i = 0; i < N; ++i) for (int k = 0; k < nc; ++k) costs[(size_t)i * nc + k] = tmp[(size_t)k * c->Np + i];
     }
     return 0;
+}
+
+// cost of u + steps[k]*deltau for arbitrary step sizes, every instance (the visu_armijo sweep, optcon.py:282-296): the candidate
+// kernel with a caller-supplied step table, armijo_maxiters steps per launch
+template <typename F>
+static int launch_sweep_candidates_t(acoc_ctx* c, const double* dsteps, int n)
+{
+    const int cur = c->kk % 3, N = c->N;
+    WorkList L;
+    L.groups = nullptr; L.count = c->counters + 1; L.shift = 0;
+    LAUNCH_CAND(c->P.q32, F, (N + CAND_TILE - 1) / CAND_TILE, std::min(n, CAND_MAXY), c->stream, prob<F>(c), L, (const F*)c->U[cur],
+                (const F*)c->DU, dsteps, 0, n, c->S.status, c->S.Jcand);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int acoc_armijo_sweep(acoc_ctx* c, int n_steps, const double* steps, double* costs)
+{
+    TRY(ready(c));
+    REQUIRE(n_steps >= 1 && steps && costs, "need n_steps >= 1, steps and costs");
+    const int N = c->N, chunk = c->O.armijo_maxiters;
+    double* dsteps = nullptr;
+    CK(cudaMalloc(&dsteps, sizeof(double) * chunk));
+    std::vector<double> tmp((size_t)chunk * c->Np);
+    int rc = 0;
+    for (int k0 = 0; k0 < n_steps && !rc; k0 += chunk) {
+        const int n = std::min(chunk, n_steps - k0);
+        if (cudaMemcpyAsync(dsteps, steps + k0, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = fail(ACOC_ERR_CUDA, "H2D of the step table failed"); break; }
+        rc = DISPATCH_F(c, launch_sweep_candidates_t, c, dsteps, n);
+        if (rc) break;
+        if (cudaMemcpyAsync(tmp.data(), c->S.Jcand, (size_t)n * c->Np * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = fail(ACOC_ERR_CUDA, "D2H of the sweep costs failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        for (int i = 0; i < N; ++i) for (int k = 0; k < n; ++k) costs[(size_t)i * n_steps + k0 + k] = tmp[(size_t)k * c->Np + i];
+    }
+    cudaFree(dsteps);
+    return rc;
 }
 
 int acoc_update(acoc_ctx* c, const double* stepsize)

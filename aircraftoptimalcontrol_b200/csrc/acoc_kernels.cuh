@@ -345,6 +345,67 @@ ACOC_HD int backward_instance(const ProblemT<F>& P, const XT* X, const F* U, F* 
 }
 
 // ------------------------------------------------------------------------------------------------------
+// steepest-descent costate sweep (GradientMethod.optimize, optcon.py:95-118)
+// ------------------------------------------------------------------------------------------------------
+// one time step: (x_t, u_t, refs) and lam_{t+1} -> deltau_t = -B'lam_{t+1} - lu (:111), lam_t = A'lam_{t+1} + lx (:110),
+// sq += deltau_t'deltau_t (:118)
+template <typename F>
+ACOC_HD void gradient_step(const ModelT<F>& M, const WeightsT<F>& W, const F* x, const F* u, const F* xr, const F* ur, F* lam, F* du, double& sq)
+{
+    F dx[NS], dv[NI], q[NS], r[NI];
+#pragma unroll
+    for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
+#pragma unroll
+    for (int c = 0; c < NI; ++c) dv[c] = u[c] - ur[c];
+    wmul6(W.Q, W.diag, dx, q);   // aa = lx = Q dx   (aircraft_simplified.py:63)
+    wmul2(W.R, W.diag, dv, r);   // bb = lu = R du   (:64)
+    const Trig<F> tg = make_trig(x);
+    const Lin<F> l = linearize(M, x, u, tg);
+    du[0] = -fma_(l.b50, lam[5], fma_(l.b20, lam[2], r[0]));
+    du[1] = -fma_(M.b41, lam[4], r[1]);
+    sq = fma_((double)du[1], (double)du[1], fma_((double)du[0], (double)du[0], sq));
+    F Atl[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) Atl[i] = acol(l, M.dt, lam, i);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) lam[i] = Atl[i] + q[i];
+}
+
+// terminal costate lam_{T-1} = QT (x_{T-1} - xref_{T-1})  (optcon.py:98-99)
+template <typename F>
+ACOC_HD void gradient_terminal(const WeightsT<F>& W, const F* x, const F* xr, F* lam)
+{
+    F dx[NS];
+#pragma unroll
+    for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
+    wmul6(W.QT, W.diag, dx, lam);
+}
+
+// whole sweep of one instance: writes deltau (DU[TT-1] = 0: deltau[:,TT-1] is never assigned, optcon.py:74), returns sum_t |deltau_t|^2
+template <typename F, typename XT>
+ACOC_HD double gradient_instance(const ProblemT<F>& P, const XT* X, const F* U, F* DU, int i)
+{
+    const int TT = P.TT, Np = P.Np;
+    F lam[NS], x[NS], u[NI], xr[NS], ur[NI], du[NI];
+    load_xref(P, TT - 1, i, xr);
+    load_x(P, X, TT - 1, i, x);
+    gradient_terminal(P.W, x, xr, lam);
+    DU[at(TT - 1, NI, 0, Np, i)] = F(0.0);
+    DU[at(TT - 1, NI, 1, Np, i)] = F(0.0);
+    double sq = 0.0;
+    for (int t = TT - 2; t >= 0; --t) {
+        load_ref(P, t, i, xr, ur);
+        load_x(P, X, t, i, x);
+#pragma unroll
+        for (int c = 0; c < NI; ++c) u[c] = U[at(t, NI, c, Np, i)];
+        gradient_step(P.M, P.W, x, u, xr, ur, lam, du, sq);
+        DU[at(t, NI, 0, Np, i)] = du[0];
+        DU[at(t, NI, 1, Np, i)] = du[1];
+    }
+    return sq;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // LQ forward pass + descent
 // ------------------------------------------------------------------------------------------------------
 // du_t = sigma_t + K_t dx_t ; dx_{t+1} = A_t dx_t + B_t du_t (optcon.py:759-760 with x~ = [1; dx], x0 = 0);
@@ -469,6 +530,7 @@ struct NewtonOpts {
     int exact_after;       // exact Hessian iff kk > exact_after (:443; 8 in the reference)
     double stepsize_0, cc, beta;  // :224-229
     double term_cond;      // :368  (-1e-6, hard-coded in the reference)
+    int method;            // 0: NewtonMethod.optimize; 1: GradientMethod.optimize (steepest descent; S.descent holds the slope -|deltau|^2)
 };
 
 enum InstStatus : int { ST_ACTIVE = 0, ST_CONVERGED = 1, ST_MAXITER = 2, ST_NONFINITE = 3 };

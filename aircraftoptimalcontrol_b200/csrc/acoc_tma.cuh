@@ -335,4 +335,75 @@ __global__ void __launch_bounds__(64) k_backward_tma(ProblemT<F> P, TileList L, 
     if (live && nreg && status[i] == ST_ACTIVE) n_reg[i] += nreg;
 }
 
+// =================================================================================================================
+// steepest-descent costate sweep (gradient_instance): same ring as the backward sweep (x, u, references per step, walking
+// t = TT-2 .. 0); out deltau and the slope -sum |deltau|^2 the Armijo test uses
+// =================================================================================================================
+template <typename F, typename XT>
+__global__ void __launch_bounds__(64) k_gradient_tma(ProblemT<F> P, TileList L, const XT* __restrict__ X, const F* __restrict__ U,
+                                                     F* __restrict__ DU, const int* __restrict__ status, double* __restrict__ descent)
+{
+    using St = BwdStage<F, XT>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int tile = warp_tile(L, blockIdx.x * nw + warp, P.Np);
+    if (tile < 0) return;
+    WarpRing<BWD_STAGES, St::BYTES> ring;
+    ring.init(smem, warp, nw, lane);
+    const int TT = P.TT, Np = P.Np, i = tile * TILE + lane, nsteps = TT - 1;
+    const bool live = i < P.N;
+    const bool shared_ref = P.ref_shared != 0;
+    auto issue = [&](int k) {  // ring step k <-> time t = TT-2-k
+        const int t = TT - 2 - k;
+        unsigned char* st = ring.stage(k);
+        uint64_t* b = ring.barrier(k);
+        mbar_arrive_expect_tx(b, shared_ref ? St::U_B + St::X_B : St::BYTES);
+        tma_load(st + St::U_O, U + tile_base(t, NI, Np, tile), St::U_B, b);
+        tma_load(st + St::X_O, X + tile_base(t, NS, Np, tile), St::X_B, b);
+        if (!shared_ref) {
+            tma_load(st + St::UR_O, P.uref + tile_base(t, NI, Np, tile), St::U_B, b);
+            tma_load(st + St::XR_O, P.xref + tile_base(t, NS, Np, tile), St::XR_B, b);
+        }
+    };
+    if (lane == 0)
+        for (int k = 0; k < BWD_STAGES && k < nsteps; ++k) issue(k);
+    F lam[NS], x[NS], u[NI], xr[NS], ur[NI];
+    double sq = 0.0;
+    if (live) {
+        load_xref(P, TT - 1, i, xr);
+        load_x(P, X, TT - 1, i, x);
+        gradient_terminal(P.W, x, xr, lam);
+        DU[at(TT - 1, NI, 0, Np, i)] = F(0.0);
+        DU[at(TT - 1, NI, 1, Np, i)] = F(0.0);
+    }
+    for (int k = 0; k < nsteps; ++k) {
+        const int t = TT - 2 - k;
+        ring.wait(k);
+        const unsigned char* st = ring.stage(k);
+        XT xraw[NS];
+#pragma unroll
+        for (int c = 0; c < NS; ++c) xraw[c] = reinterpret_cast<const XT*>(st + St::X_O)[c * TILE + lane];
+#pragma unroll
+        for (int c = 0; c < NI; ++c) u[c] = reinterpret_cast<const F*>(st + St::U_O)[c * TILE + lane];
+        if (!shared_ref) {
+#pragma unroll
+            for (int c = 0; c < NI; ++c) ur[c] = reinterpret_cast<const F*>(st + St::UR_O)[c * TILE + lane];
+#pragma unroll
+            for (int c = 0; c < NS; ++c) xr[c] = reinterpret_cast<const F*>(st + St::XR_O)[c * TILE + lane];
+        }
+        __syncwarp();
+        if (lane == 0 && k + BWD_STAGES < nsteps) issue(k + BWD_STAGES);
+        if (live) {
+            if (shared_ref) load_ref(P, t, i, xr, ur);
+            finish_x(P, t, i, xraw, x);
+            F du[NI];
+            gradient_step(P.M, P.W, x, u, xr, ur, lam, du, sq);
+            F* out = DU + tile_base(t, NI, Np, tile) + lane;
+            out[0] = du[0];
+            out[TILE] = du[1];
+        }
+    }
+    if (live && status[i] == ST_ACTIVE) descent[i] = -sq;
+}
+
 }  // namespace acoc

@@ -8,11 +8,14 @@ Reference interface mirrored (paths into MohamedAtwan/AirCraftOptimalControl):
   .get_update(stepsize,uu,deltau,x0) -> (xx_temp,uu_temp)                               optcon.py:176-200
   .armijo_stepsize(uu,deltau,xx_ref,uu_ref,x0,TT,JJ,descent,JP) -> stepsize            optcon.py:204-327
   NewtonMethod.optimize(xx_init,uu_init,tf,dt) -> (xx_star,uu_star)                     optcon.py:341-529
+  GradientMethod.optimize(xx_init,uu_init,tf,dt) -> (xx_star,uu_star)                   optcon.py:27-174
 
 Differences that are deliberate and documented in DESIGN.md: shape errors raise ValueError instead of
-print()+exit() (optcon.py:585-596); the matplotlib figures (optcon.py:280-325, :513-528) are not drawn;
-GradientMethod.optimize (broken in the reference: optcon.py:125 passes 8 arguments to a 9-argument method)
-is not provided.
+print()+exit() (optcon.py:585-596); the matplotlib figures (optcon.py:167-174, :280-325, :513-528) are drawn only
+when matplotlib is importable (the data behind the visu_armijo figure is always available: `last_armijo_sweep`);
+GradientMethod.optimize is broken in the reference (optcon.py:125 passes 8 arguments to the 9-argument armijo_stepsize
+and raises TypeError) -- here it runs, with the missing JP = JJ[kk] supplied and the slope -descent[kk] handed to the
+line search (include/acoc.h, ACOC_METHOD_GRADIENT; the oracle applies the same repair to the live reference).
 """
 from __future__ import annotations
 
@@ -75,7 +78,8 @@ def ltv_LQR(AAin, BBin, QQin, RRin, SSin, QQfin, TT, x0, qq=None, rr=None, qqf=N
 
 
 class GradientMethod:
-    """Base class: holds the problem and the two line-search helpers (optcon.py:7-25, :176-327)."""
+    """Steepest-descent method and base class of NewtonMethod: the problem, the two line-search helpers (optcon.py:7-25, :176-327),
+    optimize (optcon.py:27-174) and the batched optimize_batch."""
 
     def __init__(self, Dynamics, cost, xx_ref, uu_ref, max_iters=200, stepsize_0=1e-2, cc=0.5, beta=0.7,
                  armijo_maxiters=20, term_cond=1e-6, visu_armijo=False):
@@ -87,17 +91,19 @@ class GradientMethod:
         self.cc, self.beta = cc, beta
         self.term_cond = term_cond
         self.armijo_maxiters = armijo_maxiters
-        self.visu_armijo = visu_armijo  # plotting only in the reference (optcon.py:280-325); ignored here
+        self.visu_armijo = visu_armijo  # optcon.py:280-325: armijo_stepsize then also evaluates the cost sweep behind the figure
 
     # -- helpers ----------------------------------------------------------------------------------------
     def _state(self):
         return getattr(self.dyn, "state", "f32")
 
+    _method = "gradient"   # which optimize() loop the batched driver runs (NewtonMethod overrides)
+
     def _solver(self, n, TT, xx_ref, uu_ref, armijo="speculative"):
         xr, ur = np.asarray(xx_ref, dtype=np.float64), np.asarray(uu_ref, dtype=np.float64)
         bn = BatchedNewton(n, TT=TT, device=getattr(self.dyn, "device", 0), state=self._state(), refs_shared=(xr.ndim == 2),
                            armijo=armijo, params=self.dyn.params, max_iters=self.max_iters, stepsize_0=self.stepsize_0,
-                           cc=self.cc, beta=self.beta, armijo_maxiters=self.armijo_maxiters)
+                           cc=self.cc, beta=self.beta, armijo_maxiters=self.armijo_maxiters, method=self._method)
         bn.set_weights(self.cst.QQt, self.cst.RRt, self.cst.QQT)
         bn.set_refs(xr, ur)
         return bn
@@ -135,19 +141,65 @@ class GradientMethod:
             bn.set_deltau(deltau[None])
             bn.set_scalars(J=np.array([float(np.asarray(JP).squeeze())]), descent=np.array([float(np.asarray(descent).squeeze())]))
             s, costs = bn.armijo()
+            if self.visu_armijo:   # the data of the reference's figure (optcon.py:282-296): cost along deltau on linspace(0, stepsize_0, 10)
+                steps = np.linspace(0, self.stepsize_0, 10)
+                self.last_armijo_sweep = dict(steps=steps, costs=bn.armijo_sweep(steps)[0], JP=float(np.asarray(JP).squeeze()),
+                                              descent=float(np.asarray(descent).squeeze()))
         self.last_armijo_costs = costs[0]
+        if self.visu_armijo:
+            self._plot_armijo(s[0])
         if s[0] != self._exhausted_step():
             print('Armijo stepsize = {}'.format(s[0]))   # optcon.py:272 prints only when a candidate is accepted
         return float(s[0])
 
+    def _plot_armijo(self, stepsize):
+        """The visu_armijo figure (optcon.py:298-325) from last_armijo_sweep; silently skipped without matplotlib."""
+        try:
+            import matplotlib.pyplot as plt
+        except Exception:
+            return
+        sw = self.last_armijo_sweep
+        plt.figure(1)
+        plt.clf()
+        plt.plot(sw["steps"], sw["costs"], color='g', label='$J(\\mathbf{u}^k - stepsize*d^k)$')
+        plt.plot(sw["steps"], sw["JP"] + sw["descent"] * sw["steps"], color='r', label='$J(\\mathbf{u}^k) - stepsize*\\nabla J^{\\top} d^k$')
+        plt.plot(sw["steps"], sw["JP"] + self.cc * sw["descent"] * sw["steps"], color='g', linestyle='dashed',
+                 label='$J(\\mathbf{u}^k) - stepsize*c*\\nabla J^{\\top} d^k$')
+        plt.scatter(stepsize, np.interp(stepsize, sw["steps"], sw["costs"]), marker='*')
+        plt.grid()
+        plt.xlabel('stepsize')
+        plt.legend()
+        plt.draw()
+        plt.show(block=False)
 
-class NewtonMethod(GradientMethod):
-    """Regularized Newton method of optcon.py:329-529 on the GPU."""
+    def _plot_history(self, descent, JJ):
+        """The two closing figures of optimize (optcon.py:167-174 / :513-528); silently skipped without matplotlib."""
+        try:
+            import matplotlib.pyplot as plt
+        except Exception:
+            return
+        k = np.arange(len(JJ))
+        plt.figure('descent direction')
+        plt.plot(k, np.abs(descent))
+        plt.xlabel('$k$')
+        plt.ylabel('||$\\nabla J(\\mathbf{u}^k)||$')
+        plt.yscale('log')
+        plt.grid()
+        plt.show(block=False)
+        plt.figure('cost')
+        plt.plot(k, JJ)
+        plt.xlabel('$k$')
+        plt.ylabel('$J(\\mathbf{u}^k)$')
+        plt.yscale('log')
+        plt.grid()
+        plt.show(block=False)
 
     def optimize_batch(self, xx_init, uu_init, tf, dt, xx_ref=None, uu_ref=None, armijo="speculative", return_solver=False):
         """N instances at once: xx_init (N,6,TT), uu_init (N,2,TT); references default to the constructor's
         (shared (6,TT) or per-instance (N,6,TT)).  Returns (xx_star (N,6,TT), uu_star (N,2,TT), info) where info has
-        per-instance histories JJ/descent/stepsize/n_armijo (N,max_iters) and iters/status/J/last_descent/n_reg (N,)."""
+        per-instance histories JJ/descent/stepsize/n_armijo (N,max_iters) and iters/status/J/last_descent/n_reg (N,).
+        `descent` follows the reference's sign convention of the method: sum g'deltau (negative) for NewtonMethod
+        (optcon.py:474-477), sum |deltau|^2 (positive) for GradientMethod (optcon.py:118)."""
         xx_init, uu_init = np.asarray(xx_init, dtype=np.float64), np.asarray(uu_init, dtype=np.float64)
         if xx_init.ndim != 3 or xx_init.shape[1] != 6:
             raise ValueError("xx_init must be (N,6,TT)")
@@ -163,7 +215,9 @@ class NewtonMethod(GradientMethod):
             xs, us = bn.result()
             info = bn.history()
             st = bn.stats()
-            info.update(iters=st["iters"], status=st["status"], J=st["J"], last_descent=st["descent"], n_reg=st["n_reg"], total_iters=total)
+            sign = -1.0 if self._method == "gradient" else 1.0   # the driver keeps the slope -descent in gradient mode
+            info["descent"] = sign * info["descent"]
+            info.update(iters=st["iters"], status=st["status"], J=st["J"], last_descent=sign * st["descent"], n_reg=st["n_reg"], total_iters=total)
         except Exception:
             bn.close()
             raise
@@ -171,6 +225,27 @@ class NewtonMethod(GradientMethod):
             return xs, us, info, bn
         bn.close()
         return xs, us, info
+
+    def optimize(self, xx_init, uu_init, tf, dt):
+        """Steepest descent of optcon.py:27-174: (xx_star, uu_star) = iterate kk-1 with uu_star[:,-1] = uu_star[:,-2] (:163-165).
+        Prints the lines of :78, :272, :155.  See the module docstring for the repaired line-search call."""
+        xs, us, info = self.optimize_batch(np.asarray(xx_init, dtype=np.float64)[None], np.asarray(uu_init, dtype=np.float64)[None], tf, dt)
+        print('-*-*-*-*-*-')
+        k = int(info["iters"][0])
+        self.history = {key: info[key][0, :k].copy() for key in ("JJ", "descent", "stepsize", "n_armijo")}
+        self.history["iters"] = k
+        for kk in range(k):
+            if info["stepsize"][0, kk] != self._exhausted_step():
+                print('Armijo stepsize = {}'.format(info["stepsize"][0, kk]))
+            print('Iter = {}\t Descent = {}\t Cost = {}'.format(kk, info["descent"][0, kk], info["JJ"][0, kk]))
+        self._plot_history(self.history["descent"], self.history["JJ"])
+        return xs[0], us[0]
+
+
+class NewtonMethod(GradientMethod):
+    """Regularized Newton method of optcon.py:329-529 on the GPU."""
+
+    _method = "newton"
 
     def optimize(self, xx_init, uu_init, tf, dt):
         """(xx_star, uu_star) = iterate kk-1 with uu_star[:,-1] = uu_star[:,-2], optcon.py:499-505.  Prints the
@@ -186,4 +261,5 @@ class NewtonMethod(GradientMethod):
                 print('Armijo stepsize = {}'.format(info["stepsize"][0, kk]))
             print('Iter = {}\t Descent = {}\t Cost = {}'.format(kk, info["descent"][0, kk], info["JJ"][0, kk]))
             print('term = {}'.format(-1e-6))
+        self._plot_history(self.history["descent"], self.history["JJ"])
         return xs[0], us[0]

@@ -59,6 +59,16 @@ typedef enum acoc_status {
 #define ACOC_INST_MAXITER 2     /* ran max_iters-1 loop bodies (optcon.py:415) */
 #define ACOC_INST_NONFINITE 3   /* NaN/Inf cost or descent: frozen */
 
+/* acoc_newton_options.method: which optimize() loop acoc_newton_iterate / acoc_newton_solve run.
+ *   ACOC_METHOD_NEWTON    NewtonMethod.optimize (optcon.py:341-529).
+ *   ACOC_METHOD_GRADIENT  GradientMethod.optimize (optcon.py:27-174), steepest descent: deltau_t = -B_t' lam_{t+1} - lu_t (:111),
+ *       descent = sum_t |deltau_t|^2 (:118), stop when descent <= -term_cond (1e-6 hard-coded at :52).  The reference's call of its own
+ *       line search (optcon.py:125) passes 8 of armijo_stepsize's 9 arguments and raises TypeError; the repair used here (and by the
+ *       oracle: oracle/pyref.py::run_gradient) supplies the missing JP = JJ[kk] and hands the search the directional derivative
+ *       -descent, so that the test of optcon.py:268 is the sufficient-decrease condition.  Histories report the slope -descent. */
+#define ACOC_METHOD_NEWTON 0
+#define ACOC_METHOD_GRADIENT 1
+
 typedef struct acoc_ctx acoc_ctx;
 
 /* NewtonMethod.__init__ keyword arguments (optcon.py:335-337) */
@@ -66,7 +76,7 @@ typedef struct acoc_newton_options {
     int max_iters;        /* 200 in the shipped scripts (main_newton_method.py:32) */
     int armijo_maxiters;  /* 10   (main_newton_method.py:38) */
     int exact_after;      /* exact Hessian iff kk > exact_after; the reference hard-codes 8 (optcon.py:443) */
-    int reserved;
+    int method;           /* ACOC_METHOD_NEWTON (0, default) or ACOC_METHOD_GRADIENT: which optimize() the driver runs (see below) */
     double stepsize_0;    /* 1    (main_newton_method.py:33) */
     double cc;            /* 0.5 */
     double beta;          /* 0.7 */
@@ -178,6 +188,12 @@ int acoc_set_scalars(acoc_ctx* ctx, const double* J, const double* descent);
 int acoc_backward(acoc_ctx* ctx, int exact);
 int acoc_forward(acoc_ctx* ctx, double* descent);
 int acoc_armijo(acoc_ctx* ctx, double* stepsize, double* costs);
+/* One costate sweep of GradientMethod.optimize (optcon.py:95-118) on the current iterate: deltau (readable with acoc_get_deltau)
+ * and descent[N] = sum_t |deltau_t|^2 (may be NULL).  The context keeps -descent as the slope of the following acoc_armijo. */
+int acoc_gradient(acoc_ctx* ctx, double* descent);
+/* The visu_armijo sweep (optcon.py:280-296): costs[N][n_steps] of the rollouts u + steps[k]*deltau for caller-chosen step sizes
+ * (the reference plots np.linspace(0, stepsize_0, 10)) along the current deltau. */
+int acoc_armijo_sweep(acoc_ctx* ctx, int n_steps, const double* steps, double* costs);
 int acoc_update(acoc_ctx* ctx, const double* stepsize);
 
 /* Device-side timing of the last acoc_newton_iterate call, in milliseconds (CUDA events on the context's

@@ -17,6 +17,7 @@
  *   optcon.py:176-200              get_update              -> orc_rollout
  *   optcon.py:204-273,327          armijo_stepsize         -> orc_armijo
  *   optcon.py:341-505              NewtonMethod.optimize   -> orc_newton
+ *   optcon.py:27-174               GradientMethod.optimize -> orc_gradient (line-search call repaired, see there)
  *   optcon.py:533-771              ltv_LQR                 -> orc_ltv_lqr
  *   lqr_tracking.py:245-283        lqr_tracking            -> orc_lqr_tracking
  *
@@ -537,6 +538,115 @@ int orc_newton_batch(int N, int n_threads, const double *prm, int quant_f32, int
                            hist_J ? hist_J + (size_t)n * max_iters : NULL, hist_descent ? hist_descent + (size_t)n * max_iters : NULL,
                            hist_step ? hist_step + (size_t)n * max_iters : NULL, hist_ncand ? hist_ncand + (size_t)n * max_iters : NULL,
                            iters ? iters + n : NULL, xx_star + n * nx, uu_star + n * nu, NULL, NULL, NULL);
+        if (r) rc = r;
+    }
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* GradientMethod.optimize, optcon.py:27-174 (steepest descent), with its line-search call repaired   */
+/* ------------------------------------------------------------------------------------------------ */
+/*
+ * The reference's loop body, literally: cost (:87-93), terminal costate (:98-99), backward costate sweep with
+ * deltau_t = -B'lam_{t+1} - lu and descent += deltau'deltau (:101-118), Armijo, get_update (:131), stop when
+ * descent <= 1e-6 (:52, :157).  The call at :125 passes 8 of armijo_stepsize's 9 arguments (TypeError in the
+ * reference); the repair restated here -- the same one oracle/pyref.py::run_gradient applies to the live
+ * reference through a call adapter -- is JP = JJ[kk] and slope = -descent[kk] for the test of :268.
+ * hist_descent receives the reference's descent[kk] = sum |deltau|^2 (positive).  Everything else as orc_newton.
+ */
+int orc_gradient(const double *prm, int quant_f32, int TT, const double *Q, const double *R, const double *QT,
+                 const double *xx_ref, const double *uu_ref, const double *xx_init, const double *uu_init,
+                 int max_iters, double stepsize_0, double cc, double beta, int armijo_maxiters, double term_cond,
+                 double *hist_J, double *hist_descent, double *hist_step, int *hist_ncand, int *iters,
+                 double *xx_star, double *uu_star, double *xx_last, double *uu_last, double *du_first)
+{
+    const size_t nx = (size_t)NS * TT, nu = (size_t)NI * TT;
+    double *X[3], *U[3];
+    for (int s = 0; s < 3; ++s) { X[s] = (double *)calloc(nx, sizeof(double)); U[s] = (double *)calloc(nu, sizeof(double)); }
+    double *du = (double *)calloc(nu, sizeof(double));
+    if (!X[2] || !U[2] || !du) return -1;
+    memcpy(X[0], xx_init, nx * sizeof(double));
+    memcpy(U[0], uu_init, nu * sizeof(double));
+    double x0[NS];
+    for (int i = 0; i < NS; ++i) x0[i] = xx_init[i * TT]; /* :69 */
+    int stop_at = -1, kk;
+    for (kk = 0; kk < max_iters - 1; ++kk) { /* :85 */
+        const double *xx = X[kk % 3], *uu = U[kk % 3];
+        const double JJ = orc_traj_cost(Q, R, QT, TT, xx, uu, xx_ref, uu_ref); /* :87-93 */
+        double x[NS], u[NI], xr[NS], ur[NI], lx[NS], lu[NI], lam[NS], lamn[NS], A[36], B[12];
+        for (int i = 0; i < NS; ++i) { x[i] = xx[i * TT + TT - 1]; xr[i] = xx_ref[i * TT + TT - 1]; }
+        orc_termcost(QT, x, xr, lam); /* :98-99 */
+        double descent = 0.0;
+        for (int t = TT - 2; t >= 0; --t) { /* :101-118 */
+            for (int i = 0; i < NS; ++i) { x[i] = xx[i * TT + t]; xr[i] = xx_ref[i * TT + t]; }
+            for (int a = 0; a < NI; ++a) { u[a] = uu[a * TT + t]; ur[a] = uu_ref[a * TT + t]; }
+            orc_stagecost(Q, R, x, u, xr, ur, lx, lu);
+            orc_step(prm, x, u, NULL, quant_f32, NULL, A, B, NULL, NULL);
+            for (int i = 0; i < NS; ++i) { /* lmbd_temp = AA.T@lmbd + aa, :110 */
+                double s = 0.0;
+                for (int j = 0; j < NS; ++j) s += A[j * 6 + i] * lam[j];
+                lamn[i] = s + lx[i];
+            }
+            double sq = 0.0;
+            for (int a = 0; a < NI; ++a) { /* deltau_temp = -BB.T@lmbd - bb, :111 */
+                double s = 0.0;
+                for (int i = 0; i < NS; ++i) s += B[i * 2 + a] * lam[i];
+                const double d = -s - lu[a];
+                du[a * TT + t] = d;
+                sq += d * d;
+            }
+            descent += sq; /* :118 */
+            memcpy(lam, lamn, sizeof(lam));
+        }
+        for (int a = 0; a < NI; ++a) du[a * TT + TT - 1] = 0.0;
+        if (kk == 0 && du_first) memcpy(du_first, du, nu * sizeof(double));
+        int ntried = 0, acc = 0;
+        const double s = orc_armijo(prm, quant_f32, TT, x0, uu, du, Q, R, QT, xx_ref, uu_ref, JJ, -descent,
+                                    stepsize_0, cc, beta, armijo_maxiters, NULL, &ntried, &acc); /* :125, repaired */
+        orc_rollout(prm, quant_f32, TT, x0, uu, du, s, NULL, NULL, NULL, NULL, NULL, X[(kk + 1) % 3], U[(kk + 1) % 3]); /* :131 */
+        if (hist_J) hist_J[kk] = JJ;
+        if (hist_descent) hist_descent[kk] = descent;
+        if (hist_step) hist_step[kk] = s;
+        if (hist_ncand) hist_ncand[kk] = ntried;
+        if (descent <= term_cond) { stop_at = kk; ++kk; break; } /* :157-161 */
+    }
+    const int executed = kk;
+    if (iters) *iters = executed;
+    if (xx_last) memcpy(xx_last, X[executed % 3], nx * sizeof(double));
+    if (uu_last) memcpy(uu_last, U[executed % 3], nu * sizeof(double));
+    if (stop_at == 0) { /* :163 with max_iters = 0: slot -1, never written */
+        memset(xx_star, 0, nx * sizeof(double)); memset(uu_star, 0, nu * sizeof(double));
+    } else if (stop_at > 0) {
+        memcpy(xx_star, X[(stop_at - 1) % 3], nx * sizeof(double));
+        memcpy(uu_star, U[(stop_at - 1) % 3], nu * sizeof(double));
+    } else {
+        memcpy(xx_star, X[executed % 3], nx * sizeof(double));
+        memcpy(uu_star, U[executed % 3], nu * sizeof(double));
+    }
+    for (int a = 0; a < NI; ++a) uu_star[a * TT + TT - 1] = uu_star[a * TT + TT - 2]; /* :165 */
+    for (int s = 0; s < 3; ++s) { free(X[s]); free(U[s]); }
+    free(du);
+    return 0;
+}
+
+int orc_gradient_batch(int N, int n_threads, const double *prm, int quant_f32, int TT, const double *Q, const double *R, const double *QT,
+                       const double *xx_ref, long ref_stride_x, const double *uu_ref, long ref_stride_u,
+                       const double *xx_init, const double *uu_init,
+                       int max_iters, double stepsize_0, double cc, double beta, int armijo_maxiters, double term_cond,
+                       double *hist_J, double *hist_descent, double *hist_step, int *hist_ncand, int *iters,
+                       double *xx_star, double *uu_star)
+{
+    int rc = 0;
+    const size_t nx = (size_t)NS * TT, nu = (size_t)NI * TT;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads > 0 ? n_threads : 1)
+#endif
+    for (int n = 0; n < N; ++n) {
+        int r = orc_gradient(prm, quant_f32, TT, Q, R, QT, xx_ref + (size_t)n * ref_stride_x, uu_ref + (size_t)n * ref_stride_u,
+                             xx_init + n * nx, uu_init + n * nu, max_iters, stepsize_0, cc, beta, armijo_maxiters, term_cond,
+                             hist_J ? hist_J + (size_t)n * max_iters : NULL, hist_descent ? hist_descent + (size_t)n * max_iters : NULL,
+                             hist_step ? hist_step + (size_t)n * max_iters : NULL, hist_ncand ? hist_ncand + (size_t)n * max_iters : NULL,
+                             iters ? iters + n : NULL, xx_star + n * nx, uu_star + n * nu, NULL, NULL, NULL);
         if (r) rc = r;
     }
     return rc;

@@ -184,6 +184,46 @@ def newton_batch(xx_ref, uu_ref, xx_init, uu_init, Q, R, QT, params=DEFAULT_PARA
     return dict(JJ=hJ, descent=hD, stepsize=hS, n_armijo=hN, iters=iters, xx_star=xs, uu_star=us, threads=nt)
 
 
+def gradient(xx_ref, uu_ref, xx_init, uu_init, Q, R, QT, params=DEFAULT_PARAMS, quant_f32=True, max_iters=200,
+             stepsize_0=1e-2, cc=0.5, beta=0.7, armijo_maxiters=20, term_cond=1e-6):
+    """GradientMethod.optimize (optcon.py:27) with the repaired line-search call, one instance; history dict like
+    oracle.pyref.run_gradient (descent = sum |deltau|^2, positive, as the reference stores it)."""
+    TT = xx_ref.shape[1]
+    hJ, hD, hS = np.zeros(max_iters), np.zeros(max_iters), np.zeros(max_iters)
+    hN = np.zeros(max_iters, dtype=np.int32)
+    iters = C.c_int(0)
+    xs, us, xl, ul, du0 = np.zeros((6, TT)), np.zeros((2, TT)), np.zeros((6, TT)), np.zeros((2, TT)), np.zeros((2, TT))
+    rc = lib().orc_gradient(_p(_c(params)), C.c_int(int(quant_f32)), C.c_int(TT), _p(_c(Q)), _p(_c(R)), _p(_c(QT)),
+                            _p(_c(xx_ref)), _p(_c(uu_ref)), _p(_c(xx_init)), _p(_c(uu_init)), C.c_int(max_iters),
+                            C.c_double(stepsize_0), C.c_double(cc), C.c_double(beta), C.c_int(armijo_maxiters), C.c_double(term_cond),
+                            _p(hJ), _p(hD), _p(hS), _p(hN), C.byref(iters), _p(xs), _p(us), _p(xl), _p(ul), _p(du0))
+    assert rc == 0
+    k = iters.value
+    return dict(JJ=hJ[:k].copy(), descent=hD[:k].copy(), stepsize=hS[:k].copy(), n_armijo=hN[:k].copy(), iters=k,
+                xx_star=xs, uu_star=us, xx_last=xl, uu_last=ul, deltau_first=du0)
+
+
+def gradient_batch(xx_ref, uu_ref, xx_init, uu_init, Q, R, QT, params=DEFAULT_PARAMS, quant_f32=True, max_iters=200,
+                   stepsize_0=1e-2, cc=0.5, beta=0.7, armijo_maxiters=20, term_cond=1e-6, n_threads=0):
+    xx_init, uu_init = _c(xx_init), _c(uu_init)
+    N, _, TT = xx_init.shape
+    xr, ur = _c(xx_ref), _c(uu_ref)
+    sx = 6 * TT if xr.ndim == 3 else 0
+    su = 2 * TT if ur.ndim == 3 else 0
+    hJ, hD, hS = (np.zeros((N, max_iters)) for _ in range(3))
+    hN = np.zeros((N, max_iters), dtype=np.int32)
+    iters = np.zeros(N, dtype=np.int32)
+    xs, us = np.zeros((N, 6, TT)), np.zeros((N, 2, TT))
+    nt = n_threads if n_threads > 0 else max_threads()
+    rc = lib().orc_gradient_batch(C.c_int(N), C.c_int(nt), _p(_c(params)), C.c_int(int(quant_f32)), C.c_int(TT),
+                                  _p(_c(Q)), _p(_c(R)), _p(_c(QT)), _p(xr), C.c_long(sx), _p(ur), C.c_long(su),
+                                  _p(xx_init), _p(uu_init), C.c_int(max_iters), C.c_double(stepsize_0), C.c_double(cc),
+                                  C.c_double(beta), C.c_int(armijo_maxiters), C.c_double(term_cond),
+                                  _p(hJ), _p(hD), _p(hS), _p(hN), _p(iters), _p(xs), _p(us))
+    assert rc == 0
+    return dict(JJ=hJ, descent=hD, stepsize=hS, n_armijo=hN, iters=iters, xx_star=xs, uu_star=us, threads=nt)
+
+
 def lqr_tracking(xx_opt, uu_opt, Q, R, QT, delta, params=DEFAULT_PARAMS, quant_f32=True, n_threads=0):
     """lqr_tracking (lqr_tracking.py:245) for N perturbations delta (N,6); returns (xx_reg (N,6,TT), uu_reg (N,2,TT), K (2,6,TT))."""
     TT = xx_opt.shape[1]

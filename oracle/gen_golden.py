@@ -17,6 +17,8 @@ Fixtures
   lq_forced_reg.npz     ltv_LQR on a synthetic indefinite problem that takes the +0.5*I branch
   lqr_tracking.npz      lqr_tracking.py on Data/xx_star.npy with the shipped delta and random deltas
   newton_quirks.npz     optimize()'s return-slot corner cases: max_iters exhausted, and convergence at kk = 0 (zeros)
+  gradient_<cfg>_<q>.npz  GradientMethod.optimize histories (line-search call repaired by pyref.run_gradient's call adapter) on the
+                        problems of newton_<cfg>_<q>.npz (inputs are read from there): stepsize_0 = 1, 10 candidates, 25 / 12 iterations
 """
 from __future__ import annotations
 
@@ -272,6 +274,28 @@ def gen_newton_quirks():
           b_xx_star=b["xx_star"], b_uu_star=b["uu_star"])
 
 
+def _gradient_job(args):
+    cfg, f64, max_iters = args
+    tag = "%s_%s" % (cfg, "f64" if f64 else "f32")
+    d = np.load(os.path.join(GOLD, "newton_%s.npz" % tag))
+    t0 = time.time()
+    h = pyref.run_gradient(pyref.load(f64), d["xx_ref"], d["uu_ref"], d["xx_init"], d["uu_init"], d["Q"], d["R"], d["QT"],
+                           max_iters=max_iters, stepsize_0=1.0, cc=0.5, beta=0.7, armijo_maxiters=10)
+    wall = time.time() - t0
+    _save("gradient_%s.npz" % tag, base="newton_%s.npz" % tag, max_iters=max_iters, stepsize_0=1.0, cc=0.5, beta=0.7, armijo_maxiters=10,
+          JJ=h["JJ"], descent=h["descent"], stepsize=h["stepsize"], n_armijo=h["n_armijo"], iters=h["iters"],
+          xx_star=h["xx_star"], uu_star=h["uu_star"], xx_last=h["xx_last"], uu_last=h["uu_last"], deltau_first=h["deltau_first"],
+          ref_wall_s=wall)
+    return tag, h["iters"], wall
+
+
+def gen_gradient(jobs):
+    work = [("step", False, 26), ("step", True, 26), ("acro", False, 13)]
+    with ProcessPoolExecutor(max_workers=jobs) as ex:
+        for tag, iters, wall in ex.map(_gradient_job, work):
+            print("gradient %s: %d iterations, %.1f s" % (tag, iters, wall), flush=True)
+
+
 GENERATORS = {
     "step_kat": lambda a: gen_step_kat(),
     "cost_kat": lambda a: gen_cost_kat(),
@@ -279,6 +303,7 @@ GENERATORS = {
     "lqr_tracking": lambda a: gen_lqr_tracking(),
     "newton": lambda a: gen_newton(a.jobs),
     "newton_quirks": lambda a: gen_newton_quirks(),
+    "gradient": lambda a: gen_gradient(a.jobs),
 }
 
 

@@ -177,6 +177,68 @@ def run_newton(mods: RefModules, xx_ref, uu_ref, xx_init, uu_init, QQt, RRt, QQT
     return hist
 
 
+# ----------------------------------------------------------------------------------------
+# GradientMethod.optimize (optcon.py:27-174).  The reference's own call of its line search
+# (optcon.py:125) passes 8 of armijo_stepsize's 9 arguments and raises TypeError, so the
+# method cannot run as shipped.  The reference SOURCE stays untouched here: the instance's
+# armijo_stepsize is replaced by a call adapter that accepts the 8 arguments :125 passes and
+# forwards them to the original method with the missing JP = JJ[kk] and with the directional
+# derivative -descent[kk] (descent[kk] = sum |deltau|^2 > 0, :118) as the slope of the
+# sufficient-decrease test (:268).  This is the repair include/acoc.h documents for
+# ACOC_METHOD_GRADIENT and oracle/acoc_oracle.c::orc_gradient restates.
+# ----------------------------------------------------------------------------------------
+def run_gradient(mods: RefModules, xx_ref, uu_ref, xx_init, uu_init, QQt, RRt, QQT,
+                 tf=1, dt=1e-3, max_iters=200, stepsize_0=1e-2, cc=0.5, beta=0.7, armijo_maxiters=20, keep_iterates=()):
+    """History dict like run_newton (descent = the reference's positive descent[kk]); deltau_first = deltau of iteration 0."""
+    ac, oc = mods.aircraft, mods.optcon
+    dyn = ac.Dynamics()
+    dyn.dt = dt
+    cst = ac.Cost(QQt, RRt, QQT)
+    GM = oc.GradientMethod(dyn, cst, xx_ref, uu_ref, max_iters=max_iters, stepsize_0=stepsize_0, cc=cc, beta=beta,
+                           armijo_maxiters=armijo_maxiters, term_cond=1e-6)
+    hist = dict(JJ=[], descent=[], stepsize=[], n_armijo=[], iterates={})
+    orig_armijo, orig_update, orig_step = GM.armijo_stepsize, GM.get_update, dyn.step
+    state = dict(in_armijo=False, steps=0, k=0)
+
+    def step_counting(*a):
+        if state["in_armijo"]:
+            state["steps"] += 1
+        return orig_step(*a)
+
+    def armijo_adapter(uu, deltau, xr, ur, x0, TT, JJk, descentk):   # the 8 arguments of optcon.py:125
+        if state["k"] == 0:
+            hist["deltau_first"] = np.array(deltau)
+        state["in_armijo"], state["steps"] = True, 0
+        s = orig_armijo(uu, deltau, xr, ur, x0, TT, JJk, -descentk, JJk)
+        state["in_armijo"] = False
+        hist["JJ"].append(float(JJk))
+        hist["descent"].append(float(descentk))
+        hist["stepsize"].append(float(s))
+        hist["n_armijo"].append(state["steps"] // (TT - 1))
+        return s
+
+    def update(stepsize, uu, deltau, x0):
+        xx_t, uu_t = orig_update(stepsize, uu, deltau, x0)
+        k = state["k"]
+        if k in keep_iterates:
+            hist["iterates"][k] = (xx_t.copy(), uu_t.copy())
+        hist["xx_last"], hist["uu_last"] = xx_t.copy(), uu_t.copy()
+        state["k"] = k + 1
+        return xx_t, uu_t
+
+    dyn.step = step_counting
+    GM.armijo_stepsize = armijo_adapter
+    GM.get_update = update
+    with redirect_stdout(io.StringIO()):
+        xs, us = GM.optimize(np.array(xx_init, dtype=np.float64), np.array(uu_init, dtype=np.float64), tf, dt)
+    hist["xx_star"], hist["uu_star"] = np.array(xs), np.array(us)
+    hist["iters"] = len(hist["JJ"])
+    for k in ("JJ", "descent", "stepsize"):
+        hist[k] = np.array(hist[k], dtype=np.float64)
+    hist["n_armijo"] = np.array(hist["n_armijo"], dtype=np.int32)
+    return hist
+
+
 def run_script(name: str, workdir: str | None = None, skip_optimize: bool = False):
     """Run one of the reference's scripts unmodified (runpy) from a writable copy; returns its globals.
 

@@ -73,6 +73,7 @@ struct NewtonArgs {
     int *hist_ncand, *iters, *status;
     double *xx_star, *uu_star, *xx_last, *uu_last, *du_last, *K_last, *sigma_last;
     int* n_reg_out;
+    int method;  // 0 NewtonMethod.optimize, 1 GradientMethod.optimize (ACOC_METHOD_GRADIENT)
 };
 
 // The lock-step Newton driver of acoc_api.cu (acoc_newton_iterate) replayed on the host for one <F, XT> instantiation.
@@ -102,7 +103,7 @@ int newton_impl(const NewtonArgs& a)
     P.xref = xref.data(); P.uref = uref.data(); P.x0 = x0.data();
     NewtonOpts O;
     O.max_iters = max_iters; O.armijo_maxiters = armijo_maxiters; O.exact_after = a.exact_after;
-    O.stepsize_0 = a.stepsize_0; O.cc = a.cc; O.beta = a.beta; O.term_cond = a.term_cond;
+    O.stepsize_0 = a.stepsize_0; O.cc = a.cc; O.beta = a.beta; O.term_cond = a.term_cond; O.method = a.method;
     std::vector<int> st(Np, ST_ACTIVE), its(Np, 0), slot(Np, 0), ncand((size_t)max_iters * Np, 0), nreg(Np, 0);
     std::vector<double> Jcur(Np, 0.0), desc(Np, 0.0), step(Np, 0.0), Jc((size_t)(armijo_maxiters + 1) * Np, 0.0);
     std::vector<double> hJ((size_t)max_iters * Np, 0.0), hD((size_t)max_iters * Np, 0.0), hS((size_t)max_iters * Np, 0.0);
@@ -128,8 +129,11 @@ int newton_impl(const NewtonArgs& a)
         for (int i = 0; i < N; ++i) {
             if (st[i] != ST_ACTIVE) continue;
             if (kk == 0) Jcur[i] = traj_cost_instance(P, Xc, Uc, i);
-            nreg[i] += (kk > a.exact_after) ? backward_instance<true>(P, Xc, Uc, KSG.data(), i) : backward_instance<false>(P, Xc, Uc, KSG.data(), i);
-            desc[i] = forward_lq_instance(P, Xc, Uc, KSG.data(), DU.data(), (F*)nullptr, i);
+            if (a.method == 1) desc[i] = -gradient_instance(P, Xc, Uc, DU.data(), i);  // k_gradient_tma: slope = -sum |deltau|^2
+            else {
+                nreg[i] += (kk > a.exact_after) ? backward_instance<true>(P, Xc, Uc, KSG.data(), i) : backward_instance<false>(P, Xc, Uc, KSG.data(), i);
+                desc[i] = forward_lq_instance(P, Xc, Uc, KSG.data(), DU.data(), (F*)nullptr, i);
+            }
             bool cand0_in_place = false;
             if (a.lazy && armijo_maxiters > 1) {
                 Jc[i] = rollout_q<true, true>(P, Uc, DU.data(), cs[0], Xn, Un, i);
@@ -222,7 +226,8 @@ int emul_newton_batch(int N, int TT, const double* params, int state_f64, const 
 {
     const NewtonArgs a{N, TT, params, state_f64, Q, R, QT, xx_ref, uu_ref, ref_shared, xx_init, uu_init, max_iters, stepsize_0, cc, beta,
                        armijo_maxiters, exact_after, term_cond, n_iters_cap, lazy, hist_J, hist_descent, hist_step, hist_ncand, iters, status,
-                       xx_star, uu_star, xx_last, uu_last, du_last, K_last, sigma_last, n_reg_out};
+                       xx_star, uu_star, xx_last, uu_last, du_last, K_last, sigma_last, n_reg_out, mode >> 8};
+    mode &= 255;  // (bits 8.. of `mode`: the method, so that the signature stays what emul.py binds)
     if (mode == 2) return newton_impl<float, float>(a);
     bool x_float = false;
     if (mode == 0 && !state_f64) {

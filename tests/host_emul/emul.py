@@ -72,8 +72,9 @@ def ltv_lqr(A, B, Q, R, S, Qf, x0, q=None, r=None, qf=None):
 
 
 def newton_batch(xx_ref, uu_ref, xx_init, uu_init, Q, R, QT, params=DEFAULT_PARAMS, state_f64=False, max_iters=200,
-                 stepsize_0=1.0, cc=0.5, beta=0.7, armijo_maxiters=10, exact_after=8, term_cond=-1e-6, n_iters_cap=0, lazy=False, mode=0):
-    """mode 0: float64 arithmetic, float state slots when exact (the library's default); 1: float64 state slots; 2: FP32 mode"""
+                 stepsize_0=1.0, cc=0.5, beta=0.7, armijo_maxiters=10, exact_after=8, term_cond=-1e-6, n_iters_cap=0, lazy=False, mode=0, method=0):
+    """method 0: NewtonMethod.optimize, 1: GradientMethod.optimize (ACOC_METHOD_GRADIENT; `descent` is then the slope -sum|deltau|^2).
+    mode 0: float64 arithmetic, float state slots when exact (the library's default); 1: float64 state slots; 2: FP32 mode"""
     xx_init, uu_init = _c(xx_init), _c(uu_init)
     N, _, TT = xx_init.shape
     xr, ur = _c(xx_ref), _c(uu_ref)
@@ -87,7 +88,7 @@ def newton_batch(xx_ref, uu_ref, xx_init, uu_init, Q, R, QT, params=DEFAULT_PARA
                                  _p(xr), _p(ur), C.c_int(shared), _p(xx_init), _p(uu_init), C.c_int(max_iters), C.c_double(stepsize_0),
                                  C.c_double(cc), C.c_double(beta), C.c_int(armijo_maxiters), C.c_int(exact_after), C.c_double(term_cond),
                                  C.c_int(n_iters_cap), C.c_int(int(lazy)), _p(hJ), _p(hD), _p(hS), _p(hN), _p(iters), _p(status),
-                                 _p(xs), _p(us), _p(xl), _p(ul), _p(dul), _p(Kl), _p(sl), _p(nreg), C.c_int(int(mode)))
+                                 _p(xs), _p(us), _p(xl), _p(ul), _p(dul), _p(Kl), _p(sl), _p(nreg), C.c_int(int(mode) | (int(method) << 8)))
     return dict(JJ=hJ, descent=hD, stepsize=hS, n_armijo=hN, iters=iters, status=status, xx_star=xs, uu_star=us, xx_last=xl,
                 uu_last=ul, deltau=dul, K=Kl.reshape(N, 2, 6, TT), sigma=sl, n_reg=nreg, kk=kk)
 

@@ -121,3 +121,67 @@ def test_headless_scripts(gpu, tmp_path):
                         "--out", str(out)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert np.array_equal(np.load(out / "xx_lqr.npy"), t["xx_reg"][0])
+
+
+@pytest.mark.parametrize("name", ["step_f32", "step_f64", "acro_f32"])
+def test_gradient_method_optimize(gpu, name):
+    """GradientMethod(...).optimize(xx_init, uu_init, tf, dt) (optcon.py:27-174; the reference's own line-search call at :125 raises
+    TypeError, repaired as the module docstring says) against the live reference run through oracle/pyref.py::run_gradient's call
+    adapter: every Armijo step and candidate count identical, cost / descent history and trajectories within 1e-9."""
+    from aircraftoptimalcontrol_b200.aircraft_simplified import Cost, Dynamics
+    from aircraftoptimalcontrol_b200.optcon import GradientMethod
+    g = golden("gradient_%s.npz" % name)
+    d = golden(str(g["base"]))
+    dyn = Dynamics()
+    dyn.dt = 1e-3
+    if name.endswith("f64"):
+        dyn.state = "f64"
+    GM = GradientMethod(dyn, Cost(d["Q"], d["R"], d["QT"]), d["xx_ref"], d["uu_ref"], max_iters=int(g["max_iters"]), stepsize_0=float(g["stepsize_0"]),
+                        cc=float(g["cc"]), beta=float(g["beta"]), armijo_maxiters=int(g["armijo_maxiters"]))
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        xx_star, uu_star = GM.optimize(d["xx_init"], d["uu_init"], 1, 1e-3)
+    k = int(g["iters"])
+    assert buf.getvalue().count("Iter = ") == k and "term = " not in buf.getvalue()
+    h = GM.history
+    assert h["iters"] == k
+    assert np.array_equal(h["stepsize"], g["stepsize"]) and np.array_equal(h["n_armijo"], g["n_armijo"])
+    assert np.max(np.abs(h["JJ"] - g["JJ"]) / g["JJ"]) < 1e-9 and np.max(np.abs(h["descent"] - g["descent"]) / g["descent"]) < 1e-9
+    assert relerr(g["xx_star"], xx_star) < 1e-9 and relerr(g["uu_star"], uu_star) < 1e-9
+    assert np.array_equal(uu_star[:, -1], uu_star[:, -2])  # optcon.py:165
+
+
+def test_gradient_sweep_and_armijo_sweep(gpu, oracle):
+    """One costate sweep (acoc_gradient: deltau, descent of optcon.py:101-118) against the live reference's first iteration, and the
+    visu_armijo cost sweep (acoc_armijo_sweep, optcon.py:282-296) against oracle rollouts at the same step sizes."""
+    import aircraftoptimalcontrol_b200 as pkg
+    from aircraftoptimalcontrol_b200.aircraft_simplified import Cost, Dynamics
+    from aircraftoptimalcontrol_b200.optcon import GradientMethod
+    g = golden("gradient_step_f32.npz")
+    d = golden(str(g["base"]))
+    with pkg.BatchedNewton(3, TT=1000, refs_shared=True, method="gradient") as bn:
+        bn.set_weights(d["Q"], d["R"], d["QT"])
+        bn.set_refs(d["xx_ref"], d["uu_ref"])
+        bn.set_init(np.repeat(d["xx_init"][None], 3, 0), np.repeat(d["uu_init"][None], 3, 0))
+        desc = bn.gradient()
+        du = bn.deltau()
+        steps = np.linspace(0, 1.0, 10)          # optcon.py:282
+        more = np.linspace(0.0, 0.3, 23)         # more steps than armijo_maxiters: evaluated in chunks
+        costs, costs2 = bn.armijo_sweep(steps), bn.armijo_sweep(more)
+    assert relerr(g["deltau_first"], du[0]) < 1e-12 and np.array_equal(du[0], du[2])
+    assert abs(desc[1] - g["descent"][0]) < 1e-12 * g["descent"][0]
+    x0 = d["xx_init"][:, 0]
+    for k, s in enumerate(steps):
+        Jo = oracle.rollout(x0, d["uu_init"], du[0], s, cost=(d["Q"], d["R"], d["QT"]), xr=d["xx_ref"], ur=d["uu_ref"])[2]
+        assert abs(costs[0, k] - Jo) < 1e-12 * Jo, k
+    assert abs(costs[0, 0] - g["JJ"][0]) < 1e-4 * g["JJ"][0]       # step 0 re-rolls the current inputs (the reference's initial guess is
+                                                                   # only ~1e-5 from a float64-arithmetic rollout, DESIGN.md section 2)
+    for k in (0, 9, 10, 22):
+        Jo = oracle.rollout(x0, d["uu_init"], du[0], more[k], cost=(d["Q"], d["R"], d["QT"]), xr=d["xx_ref"], ur=d["uu_ref"])[2]
+        assert abs(costs2[1, k] - Jo) < 1e-12 * Jo, k
+    # the drop-in method with visu_armijo=True keeps the data of the reference's figure
+    GM = GradientMethod(Dynamics(), Cost(d["Q"], d["R"], d["QT"]), d["xx_ref"], d["uu_ref"], stepsize_0=1.0, armijo_maxiters=10, visu_armijo=True)
+    with redirect_stdout(io.StringIO()):
+        s = GM.armijo_stepsize(d["uu_init"], du[0], d["xx_ref"], d["uu_ref"], x0, 1000, g["JJ"][0], -g["descent"][0], g["JJ"][0])
+    assert s == g["stepsize"][0]
+    assert np.allclose(GM.last_armijo_sweep["costs"], costs[0], rtol=1e-13) and GM.last_armijo_sweep["steps"].shape == (10,)

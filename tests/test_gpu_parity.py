@@ -516,6 +516,33 @@ def test_fused_search_identical(gpu, state, armijo, n, TT):
         assert np.array_equal(a[4][k], b[4][k]), k
     for k in ("iters", "status", "J", "descent", "n_reg"):
         assert np.array_equal(a[5][k], b[5][k]), k
-    assert np.any(a[4]["n_armijo"] == 10) and np.any(a[5]["status"] == 2) and np.any(a[5]["status"] == 1)
+    assert np.any(a[5]["status"] == 1)
+    if state == "f32":  # float32-noise phase: searches that run to exhaustion, instances stopped by the iteration limit
+        assert np.any(a[4]["n_armijo"] == 10) and np.any(a[5]["status"] == 2)
     act = a[5]["iters"] == a[5]["iters"].max()
     assert np.array_equal(a[7][act], b[7][act])
+
+
+@pytest.mark.parametrize("tma", [True, False])
+def test_gradient_method_batch_matches_oracle(gpu, oracle, tma):
+    """GradientMethod.optimize as a batch (ACOC_METHOD_GRADIENT): 70 randomised step references (ragged: padding lanes), lazy Armijo,
+    12 iterations, against the C oracle (itself pinned to the live reference) -- Armijo steps and candidate counts identical,
+    histories and iterates within 1e-9; TMA-ring and plain-load costate sweeps."""
+    n, TT = 70, 1000
+    xr, ur, Q, R, QT = _random_batch(n, TT, 77, 1.0)
+    with gpu.BatchedNewton(n, TT=TT, armijo="lazy", method="gradient", max_iters=13, tma=tma) as bn:
+        bn.set_weights(Q, R, QT)
+        bn.set_refs(xr, ur)
+        bn.init_guess()
+        xi, ui = bn.iterate_at(0)
+        total = bn.solve()
+        xs, us = bn.result()
+        xl, ul = bn.iterate_at(0)
+        h, st = bn.history(), bn.stats()
+    o = oracle.gradient_batch(xr, ur, xi, ui, Q, R, QT, max_iters=13, stepsize_0=1.0, armijo_maxiters=10)
+    assert total == 12 * n and np.all(st["iters"] == 12) and np.all(o["iters"] == 12) and np.all(st["status"] == 2)
+    assert np.array_equal(h["stepsize"][:, :12], o["stepsize"][:, :12]) and np.array_equal(h["n_armijo"][:, :12], o["n_armijo"][:, :12])
+    assert len(np.unique(h["stepsize"][:, :12])) >= 4   # the searches really backtrack
+    assert np.max(np.abs(h["JJ"][:, :12] - o["JJ"][:, :12]) / o["JJ"][:, :12]) < 1e-9
+    assert np.max(np.abs(-h["descent"][:, :12] - o["descent"][:, :12]) / o["descent"][:, :12]) < 1e-9
+    assert relerr(o["xx_star"], xs) < 1e-9 and relerr(o["uu_star"], us) < 1e-9

@@ -162,3 +162,23 @@ def test_fp32_mode_on_host(emul):
     assert abs(h["JJ"][0, k - 1] - d["JJ"][-1]) / d["JJ"][-1] < 2e-6
     assert np.max(np.abs(h["xx_last"][0] - d["xx_last"])) < 2e-3
     assert np.max(np.abs(h["uu_last"][0] - d["uu_last"])) < 2e-4 * np.max(np.abs(d["uu_last"]))
+
+
+@pytest.mark.parametrize("name", ["step_f32", "step_f64", "acro_f32"])
+@pytest.mark.parametrize("lazy", [False, True])
+def test_gradient_kernels_reproduce_reference(emul, name, lazy):
+    """GradientMethod.optimize (optcon.py:27-174, line-search call repaired as include/acoc.h describes): the costate sweep of
+    k_gradient_tma + candidate rollouts + select + update, driven like acoc_newton_iterate, reproduce the live reference run through
+    oracle/pyref.py::run_gradient -- every Armijo step and candidate count, cost/descent history, iterates."""
+    g = golden("gradient_%s.npz" % name)
+    d = golden(str(g["base"]))
+    h = emul.newton_batch(d["xx_ref"], d["uu_ref"], d["xx_init"][None], d["uu_init"][None], d["Q"], d["R"], d["QT"], state_f64=name.endswith("f64"),
+                          lazy=lazy, method=1, max_iters=int(g["max_iters"]), stepsize_0=float(g["stepsize_0"]), armijo_maxiters=int(g["armijo_maxiters"]))
+    k = int(g["iters"])
+    assert h["iters"][0] == k and h["status"][0] == 2  # ran max_iters-1 bodies (optcon.py:85), like the reference did
+    assert np.array_equal(h["stepsize"][0, :k], g["stepsize"])
+    assert np.array_equal(h["n_armijo"][0, :k], g["n_armijo"])
+    assert np.max(np.abs(h["JJ"][0, :k] - g["JJ"]) / np.abs(g["JJ"])) < 1e-12
+    assert np.max(np.abs(-h["descent"][0, :k] - g["descent"]) / np.abs(g["descent"])) < 1e-9
+    assert relerr(g["xx_last"], h["xx_last"][0]) < 1e-9 and relerr(g["uu_last"], h["uu_last"][0]) < 1e-9
+    assert relerr(g["xx_star"], h["xx_star"][0]) < 1e-9 and relerr(g["uu_star"], h["uu_star"][0]) < 1e-9

@@ -133,3 +133,22 @@ def test_newton_return_slot_quirks(oracle):
     b = oracle.newton(d["xx_ref"], d["uu_ref"], d["b_xx_init"], d["b_uu_init"], d["Q"], d["R"], d["QT"], quant_f32=False)
     assert b["iters"] == int(d["b_iters"]) == 1 and np.array_equal(b["stepsize"], d["b_stepsize"])
     assert not b["xx_star"].any() and not b["uu_star"].any() and not d["b_xx_star"].any()
+
+
+@pytest.mark.parametrize("name", ["step_f32", "step_f64", "acro_f32"])
+def test_gradient_method_pinned(oracle, name):
+    """orc_gradient (GradientMethod.optimize, optcon.py:27-174, with the repaired line-search call) against the live reference run
+    through the call adapter of oracle/pyref.py::run_gradient: identical Armijo steps and candidate counts, histories, iterates."""
+    g = golden("gradient_%s.npz" % name)
+    d = golden(str(g["base"]))
+    o = oracle.gradient(d["xx_ref"], d["uu_ref"], d["xx_init"], d["uu_init"], d["Q"], d["R"], d["QT"], quant_f32=name.endswith("f32"),
+                        max_iters=int(g["max_iters"]), stepsize_0=float(g["stepsize_0"]), cc=float(g["cc"]), beta=float(g["beta"]),
+                        armijo_maxiters=int(g["armijo_maxiters"]))
+    assert o["iters"] == int(g["iters"])
+    assert np.array_equal(o["stepsize"], g["stepsize"]) and np.array_equal(o["n_armijo"], g["n_armijo"])
+    assert np.max(np.abs(o["JJ"] - g["JJ"]) / g["JJ"]) < 1e-12 and np.max(np.abs(o["descent"] - g["descent"]) / g["descent"]) < 1e-9
+    assert relerr(g["deltau_first"], o["deltau_first"]) < 1e-12
+    if name.endswith("f32"):
+        assert np.array_equal(o["xx_last"], g["xx_last"]) and np.array_equal(o["xx_star"], g["xx_star"])
+    assert relerr(g["xx_last"], o["xx_last"]) < 1e-9 and relerr(g["uu_last"], o["uu_last"]) < 1e-9
+    assert relerr(g["uu_star"], o["uu_star"]) < 1e-9

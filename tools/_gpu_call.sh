@@ -1,3 +1,1 @@
-timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -15
-timeout 300 python tools/time_small_batch.py > gpurun_out/small_batch.json 2> gpurun_out/small_batch.err; tail -3 gpurun_out/small_batch.err; cat gpurun_out/small_batch.json
-for v in 0 2048 4096 8192; do echo "ACOC_FUSED_MAX_N=$v"; ACOC_FUSED_MAX_N=$v timeout 300 python bench.py --no-cpu --no-roofline --steps 8 --warmup 3 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(' value', round(d['value']), 'ms/iter', round(d['ms_per_step'],3), 'whole solve ms', round(d['whole_solve']['device_ms'],1), 'e2e', d['e2e'])"; done 2>&1 | tee gpurun_out/tune_fused.txt
+timeout 1500 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "fused_search or gradient" 2>&1 | tail -15
