@@ -242,18 +242,22 @@ k_candidates(ProblemT<F> P, WorkList L, const F* __restrict__ U, const F* __rest
 // forward pass and the Armijo rollouts run forward in time and candidate c needs du_t only at step t, so they run as ONE sweep:
 // CTA = one tile of 32 instances, warp y < n_rows = the rollout of step cand_steps[y] (the armijo_maxiters candidates and, as the last
 // row, the untested step the search falls back to on exhaustion, optcon.py:327), warp n_rows = the LQ forward pass one step ahead of
-// them, handing du_t over through a double-buffered shared-memory slot with one barrier per step.  Every row keeps its trajectory
+// them, handing du_t over through double-buffered shared-memory blocks of FUSE_BLOCK steps (one barrier per block).  Every row keeps its trajectory
 // (Xc / Uc: one trajectory slot per row), so that get_update is a copy of the chosen row (k_pick) instead of one more sweep.
 // Inputs of the next step are fetched into registers before the arithmetic of the current one.  Same per-step functions as the
 // separate sweeps (forward_step, rollout_step), so the results are bit-identical to them.
 constexpr int FUSE_MAXROWS = 11;
+#ifndef ACOC_FUSE_BLOCK
+#define ACOC_FUSE_BLOCK 8
+#endif
+constexpr int FUSE_BLOCK = ACOC_FUSE_BLOCK;  // steps between two CTA-wide barriers
 template <bool Q32, typename F, typename XT>
 __global__ void __launch_bounds__(TILE * (FUSE_MAXROWS + 1))
 k_search_fused(ProblemT<F> P, TileList L, const XT* __restrict__ X, const F* __restrict__ U, const F* __restrict__ KSG, F* __restrict__ DU,
                const double* __restrict__ cand_steps, int n_rows, XT* __restrict__ Xc, F* __restrict__ Uc, size_t row_x, size_t row_u,
                const int* __restrict__ status, double* __restrict__ descent, double* __restrict__ Jcand)
 {
-    __shared__ F sdu[2][NI][TILE];
+    __shared__ F sdu[2][FUSE_BLOCK][NI][TILE];
     const int tile = warp_tile(L, blockIdx.x, P.Np);
     if (tile < 0) return;  // (uniform over the CTA)
     const int lane = threadIdx.x, row = threadIdx.y, TT = P.TT, Np = P.Np;
@@ -262,16 +266,23 @@ k_search_fused(ProblemT<F> P, TileList L, const XT* __restrict__ X, const F* __r
     const bool fwd = row == n_rows;
     // finished lanes of a live tile: the forward pass keeps writing du (scratch, whole lines); the rollouts skip them
     const bool act = valid && (fwd || status[i] == ST_ACTIVE);
-    // forward-pass warp
-    F dx[NS] = {F(0.0), F(0.0), F(0.0), F(0.0), F(0.0), F(0.0)}, ksg_n[16];
+    // The two roles overlay their loop-carried state in one register array (a warp has one role for its whole life, but the compiler
+    // would otherwise keep both sets live across the loop):
+    //   forward pass: st[0..5] = dx, st[6..21] = K, sigma, g of the next step      rollout: st[0..5] = x, st[6..11] / st[12..13] = refs of the next step
+    F st[22];
+    F* const dx = st;
+    F* const ksg_n = st + 6;
+    F* const x = st;
+    F* const xr_n = st + 6;
+    F* const ur_n = st + 12;
     XT xraw_n[NS];
     double acc = 0.0;  // descent (forward warp) / cost (rollout warps)
-    // rollout warps
-    F x[NS], xr_n[NS], ur_n[NI];
     F u_n[NI];  // both roles: u_t of the nominal iterate, fetched one step ahead
     F s = F(0.0);
     XT* Xn = nullptr;
     F* Un = nullptr;
+#pragma unroll
+    for (int c = 0; c < 22; ++c) st[c] = F(0.0);
     if (act) {
 #pragma unroll
         for (int c = 0; c < NI; ++c) u_n[c] = U[at(0, NI, c, Np, i)];
@@ -288,46 +299,55 @@ k_search_fused(ProblemT<F> P, TileList L, const XT* __restrict__ X, const F* __r
             load_ref(P, 0, i, xr_n, ur_n);
         }
     }
-    for (int tau = 0; tau < TT; ++tau) {
+    // blocks of FUSE_BLOCK steps: in block b the forward warp produces du of steps [b*FUSE_BLOCK, ...) into buffer b & 1 while the rollout
+    // warps consume the steps of block b - 1 from the other buffer; one barrier per block, warps run freely inside a block
+    const int nsteps = TT - 1, nblk = (nsteps + FUSE_BLOCK - 1) / FUSE_BLOCK;
+    for (int b = 0; b <= nblk; ++b) {
         if (fwd) {
-            if (act && tau < TT - 1) {
-                F xx[NS], u[NI], ksg[16], du[NI];
-                finish_x(P, tau, i, xraw_n, xx);
+            if (act && b < nblk) {
+                for (int j = 0; j < FUSE_BLOCK; ++j) {
+                    const int tau = b * FUSE_BLOCK + j;
+                    if (tau >= nsteps) break;
+                    F xx[NS], u[NI], du[NI];
+                    forward_du(ksg_n, dx, du, acc);  // (K, sigma, g of this step are dead from here on: their registers take the next step's)
+                    DU[at(tau, NI, 0, Np, i)] = du[0];
+                    DU[at(tau, NI, 1, Np, i)] = du[1];
+                    sdu[b & 1][j][0][lane] = du[0];
+                    sdu[b & 1][j][1][lane] = du[1];
+                    finish_x(P, tau, i, xraw_n, xx);
 #pragma unroll
-                for (int c = 0; c < NI; ++c) u[c] = u_n[c];
+                    for (int c = 0; c < NI; ++c) u[c] = u_n[c];
+                    if (tau + 1 < nsteps) {
+                        load_x_raw(X, tau + 1, Np, i, xraw_n);
 #pragma unroll
-                for (int c = 0; c < 16; ++c) ksg[c] = ksg_n[c];
-                if (tau + 1 < TT - 1) {
-                    load_x_raw(X, tau + 1, Np, i, xraw_n);
+                        for (int c = 0; c < NI; ++c) u_n[c] = U[at(tau + 1, NI, c, Np, i)];
 #pragma unroll
-                    for (int c = 0; c < NI; ++c) u_n[c] = U[at(tau + 1, NI, c, Np, i)];
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) ksg_n[c] = KSG[at(tau + 1, 16, c, Np, i)];
+                        for (int c = 0; c < 16; ++c) ksg_n[c] = KSG[at(tau + 1, 16, c, Np, i)];
+                    }
+                    forward_advance(P.M, xx, u, du, dx);
                 }
-                forward_step(P.M, xx, u, ksg, dx, du, acc);
-                DU[at(tau, NI, 0, Np, i)] = du[0];
-                DU[at(tau, NI, 1, Np, i)] = du[1];
-                sdu[tau & 1][0][lane] = du[0];
-                sdu[tau & 1][1][lane] = du[1];
             }
-        } else if (act && tau >= 1) {
-            const int t = tau - 1;
-            F u[NI], xr[NS], ur[NI];
+        } else if (act && b >= 1) {
+            for (int j = 0; j < FUSE_BLOCK; ++j) {
+                const int t = (b - 1) * FUSE_BLOCK + j;
+                if (t >= nsteps) break;
+                F u[NI], xr[NS], ur[NI];
 #pragma unroll
-            for (int c = 0; c < NI; ++c) u[c] = u_n[c] + s * sdu[t & 1][c][lane];  // optcon.py:197 / :253
+                for (int c = 0; c < NI; ++c) u[c] = u_n[c] + s * sdu[(b - 1) & 1][j][c][lane];  // optcon.py:197 / :253
 #pragma unroll
-            for (int c = 0; c < NS; ++c) xr[c] = xr_n[c];
+                for (int c = 0; c < NS; ++c) xr[c] = xr_n[c];
 #pragma unroll
-            for (int c = 0; c < NI; ++c) ur[c] = ur_n[c];
-            if (t + 1 < TT - 1) {
+                for (int c = 0; c < NI; ++c) ur[c] = ur_n[c];
+                if (t + 1 < nsteps) {
 #pragma unroll
-                for (int c = 0; c < NI; ++c) u_n[c] = U[at(t + 1, NI, c, Np, i)];
-                load_ref(P, t + 1, i, xr_n, ur_n);
+                    for (int c = 0; c < NI; ++c) u_n[c] = U[at(t + 1, NI, c, Np, i)];
+                    load_ref(P, t + 1, i, xr_n, ur_n);
+                }
+                store_x(Xn, t, Np, i, x);
+#pragma unroll
+                for (int c = 0; c < NI; ++c) Un[at(t, NI, c, Np, i)] = u[c];
+                rollout_step<true, Q32>(P.M, P.W, x, u, xr, ur, acc);
             }
-            store_x(Xn, t, Np, i, x);
-#pragma unroll
-            for (int c = 0; c < NI; ++c) Un[at(t, NI, c, Np, i)] = u[c];
-            rollout_step<true, Q32>(P.M, P.W, x, u, xr, ur, acc);
         }
         __syncthreads();
     }

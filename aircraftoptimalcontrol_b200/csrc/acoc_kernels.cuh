@@ -413,13 +413,19 @@ ACOC_HD double gradient_instance(const ProblemT<F>& P, const XT* X, const F* U, 
 // stored by the backward sweep (12 doubles per step of HBM traffic saved for ~60 flops and two sincos).
 // DX (optional, warp-tiled like X) receives the state increments for the drop-in ltv_LQR-style outputs.
 // one time step: ksg = (K row-major 2x6, sigma, g) of this step; dx is advanced in place, du returned, descent accumulated
+// (two halves so that a caller can drop ksg -- 16 values -- before the trigonometry of the second half)
 template <typename F>
-ACOC_HD void forward_step(const ModelT<F>& M, const F* x, const F* u, const F* ksg, F* dx, F* du, double& descent)
+ACOC_HD void forward_du(const F* ksg, const F* dx, F* du, double& descent)
 {
     du[0] = ksg[12]; du[1] = ksg[13];
 #pragma unroll
     for (int c = 0; c < NS; ++c) { du[0] = fma_(ksg[c], dx[c], du[0]); du[1] = fma_(ksg[NS + c], dx[c], du[1]); }
     descent = fma_((double)ksg[15], (double)du[1], fma_((double)ksg[14], (double)du[0], descent));
+}
+
+template <typename F>
+ACOC_HD void forward_advance(const ModelT<F>& M, const F* x, const F* u, const F* du, F* dx)
+{
     const Trig<F> tg = make_trig(x);
     const Lin<F> l = linearize(M, x, u, tg);
     F nx[NS];
@@ -431,6 +437,13 @@ ACOC_HD void forward_step(const ModelT<F>& M, const F* x, const F* u, const F* k
     nx[5] = fma_(l.b50, du[0], fma_(l.a55, dx[5], fma_(l.a53, dx[3], l.a52 * dx[2])));
 #pragma unroll
     for (int c = 0; c < NS; ++c) dx[c] = nx[c];
+}
+
+template <typename F>
+ACOC_HD void forward_step(const ModelT<F>& M, const F* x, const F* u, const F* ksg, F* dx, F* du, double& descent)
+{
+    forward_du(ksg, dx, du, descent);
+    forward_advance(M, x, u, du, dx);
 }
 
 template <typename F, typename XT>
