@@ -38,6 +38,42 @@ def test_cost_batch_kat(gpu):
         assert relerr(d["lx"][m], lx) < 1e-14 and relerr(d["lu"][m], lu) < 1e-14 and relerr(d["lTx"][m], lTx) < 1e-14
 
 
+def test_step_and_cost_10k_random_samples(gpu, oracle):
+    """SURVEY 8(c) parity protocol: Dynamics.step / Cost on 10^4 random (x, u, lambda) with V in [5, 30] against the C oracle (itself
+    pinned to the live reference on the 256-sample KAT): float32-rounded next state bit-exact, float64 next state 1e-15, Jacobians and
+    costate-contracted Hessians 1e-12, costs and gradients 1e-13."""
+    from aircraftoptimalcontrol_b200.aircraft_simplified import Cost, Dynamics
+    rng = np.random.default_rng(424242)
+    n = 10000
+    X = np.stack([rng.uniform(-50, 50, n), rng.uniform(-20, 20, n), rng.uniform(5, 30, n), rng.uniform(-1.2, 1.2, n), rng.uniform(-3, 3, n),
+                  rng.uniform(-1.2, 1.2, n)], axis=1)
+    U = np.stack([rng.uniform(-200, 600, n), rng.uniform(-150, 150, n)], axis=1)
+    LAM = rng.normal(size=(n, 6)) * np.array([1, 10, 0.1, 1, 0.01, 1])
+    r32 = Dynamics(state="f32").step_batch(X, U)
+    r64 = Dynamics(state="f64").step_batch(X, U, LAM)
+    bad32 = 0
+    e64 = eA = eB = eH = eS = 0.0
+    for k in range(n):
+        o32 = oracle.step(X[k], U[k], quant_f32=True)
+        o64 = oracle.step(X[k], U[k], LAM[k], quant_f32=False)
+        bad32 += not np.array_equal(o32[0], r32["xxp"][k])
+        e64 = max(e64, relerr(o64[0], r64["xxp"][k]))
+        eA, eB = max(eA, relerr(o32[1], r32["A"][k].T)), max(eB, relerr(o32[2], r32["B"][k].T))
+        eH, eS = max(eH, relerr(o64[3], r64["fxx"][k])), max(eS, relerr(o64[5], r64["fux"][k]))
+    assert bad32 == 0 and e64 < 1e-15 and eA < 1e-12 and eB < 1e-12 and eH < 1e-12 and eS < 1e-12, (bad32, e64, eA, eB, eH, eS)
+    Q, R, QT = (rng.normal(size=(6, 6)), rng.normal(size=(2, 2)), rng.normal(size=(6, 6)))
+    Q, R, QT = Q @ Q.T, R @ R.T, QT @ QT.T
+    XR, UR = X + rng.normal(size=(n, 6)), U + rng.normal(size=(n, 2)) * 10
+    c = Cost(Q, R, QT)
+    ll, lx, lu = c.stagecost_batch(X, U, XR, UR)
+    llT, lTx = c.termcost_batch(X, XR)
+    for k in range(0, n, 7):
+        ol, olx, olu = oracle.stagecost(Q, R, X[k], U[k], XR[k], UR[k])
+        oT, oTx = oracle.termcost(QT, X[k], XR[k])
+        assert abs(ll[k] - ol) < 1e-13 * abs(ol) and abs(llT[k] - oT) < 1e-13 * abs(oT), k
+        assert relerr(olx, lx[k]) < 1e-13 and relerr(olu, lu[k]) < 1e-13 and relerr(oTx, lTx[k]) < 1e-13, k
+
+
 def test_ltv_lqr_forced_regularisation(gpu):
     from aircraftoptimalcontrol_b200.optcon import ltv_LQR
     d = golden("lq_forced_reg.npz")
@@ -546,3 +582,24 @@ def test_gradient_method_batch_matches_oracle(gpu, oracle, tma):
     assert np.max(np.abs(h["JJ"][:, :12] - o["JJ"][:, :12]) / o["JJ"][:, :12]) < 1e-9
     assert np.max(np.abs(-h["descent"][:, :12] - o["descent"][:, :12]) / o["descent"][:, :12]) < 1e-9
     assert relerr(o["xx_star"], xs) < 1e-9 and relerr(o["uu_star"], us) < 1e-9
+
+
+def test_gradient_method_fp32_mode(gpu):
+    """The optional FP32 mode also covers the gradient method: 12 steepest-descent iterations of a 64-instance batch stay within the
+    FP32 tolerances of the float64 path (final cost 2e-6 relative, inputs 2e-4 of their range)."""
+    n, TT = 64, 1000
+    xr, ur, Q, R, QT = _random_batch(n, TT, 91, 1.0)
+    res = {}
+    for prec in ("f64", "f32"):
+        with gpu.BatchedNewton(n, TT=TT, armijo="lazy", method="gradient", max_iters=13, precision=prec) as bn:
+            bn.set_weights(Q, R, QT)
+            bn.set_refs(xr, ur)
+            bn.init_guess()
+            bn.solve()
+            res[prec] = (bn.iterate_at(0), bn.stats(), bn.history())
+    (x64, u64), s64, h64 = res["f64"]
+    (x32, u32), s32, h32 = res["f32"]
+    assert np.all(s32["iters"] == 12) and np.all(s64["iters"] == 12)
+    assert np.max(np.abs(s32["J"] - s64["J"]) / s64["J"]) < 1e-4      # 12 line searches on float32 noise: same descent path, not the same floats
+    assert np.max(np.abs(h32["JJ"][:, 0] - h64["JJ"][:, 0]) / h64["JJ"][:, 0]) < FP32_TOL["J_rel"]
+    assert np.max(np.abs(u32 - u64)) < 50 * FP32_TOL["u_rel_range"] * np.max(np.abs(u64))

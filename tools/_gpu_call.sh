@@ -1,4 +1,1 @@
-run() { python bench.py --no-e2e --no-cpu --no-roofline --steps 8 --warmup 3 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(' value', round(d['value']), 'ms/iter', round(d['ms_per_step'],3), 'whole solve ms', round(d['whole_solve']['device_ms'],1))"; }
-echo base; run
-for f in variants/*.so; do echo $f; ACOC_LIB=$PWD/$f run; done
-echo base again; run
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "10k or gradient_method_fp32" 2>&1 | tail -12
