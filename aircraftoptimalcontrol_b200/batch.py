@@ -36,8 +36,9 @@ class BatchedNewton:
     descent) with the repaired line-search call described in include/acoc.h (ACOC_METHOD_GRADIENT).  In that mode the `descent`
     entries of history() / stats() are the slope -sum|deltau|^2 handed to the Armijo test (the reference's descent[kk] is its
     negative), `term_cond` keeps its meaning (stop when slope >= term_cond, i.e. descent <= 1e-6, optcon.py:52,157).
-    fused: batches of at most 4096 instances (late survivor generations, single trajectories) run the LQ forward pass and the whole
-    Armijo search as one sweep and take get_update as a copy of the chosen candidate (default; identical results, A/B measurements).
+    fused: fuse the LQ forward pass with the line-search rollouts that follow it -- with candidate 0 of the lazy search in one sweep
+    (any batch size), and, for batches of at most 4096 instances (late survivor generations, single trajectories), with the whole
+    Armijo search, get_update then being a copy of the chosen candidate (default; identical results, A/B measurements).
     """
 
     def __init__(self, n_instances, TT=1000, device=0, state="f32", refs_shared=False, armijo="speculative", params=None, generations=True,

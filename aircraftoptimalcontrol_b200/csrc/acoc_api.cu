@@ -1409,6 +1409,35 @@ static int launch_cand0_t(acoc_ctx* c)
 }
 static int launch_cand0(acoc_ctx* c) { return DISPATCH_FX(c, launch_cand0_t, c); }
 
+// lazy Armijo on the TMA path: the LQ forward pass and candidate 0 as one sweep (k_forward_cand0_tma)
+static bool fwd_cand0_fused(const acoc_ctx* c)
+{
+    static const bool off = getenv("ACOC_NO_FWD_CAND0") != nullptr;  // tuning experiments
+    return use_tma(c) && is_lazy(c) && !(c->flags & ACOC_NO_FUSED) && c->O.method == ACOC_METHOD_NEWTON && !off;
+}
+template <typename F, typename XT>
+static int launch_forward_cand0_t(acoc_ctx* c)
+{
+    const int cur = c->kk % 3, nxt = (c->kk + 1) % 3;
+    const ProblemT<F> P = prob<F>(c);
+    const size_t sm = WarpRing<FC_STAGES, FwdCandStage<F, XT>::BYTES>::smem_bytes(FWD_THREADS / 32);
+    const int g = sweep_grid(c, FWD_THREADS);
+    cudaStream_t st = sweep_stream(c);
+    if (c->P.q32) {
+        TRY(prefer_smem(k_forward_cand0_tma<true, F, XT>));
+        k_forward_cand0_tma<true, F, XT><<<g, FWD_THREADS, sm, st>>>(P, tile_list(c), c->S, (const XT*)c->X[cur], (const F*)c->U[cur], (const F*)c->KSG,
+                                                                    (F*)c->DU, c->cand_steps, (XT*)c->X[nxt], (F*)c->U[nxt]);
+    } else {
+        TRY(prefer_smem(k_forward_cand0_tma<false, F, XT>));
+        k_forward_cand0_tma<false, F, XT><<<g, FWD_THREADS, sm, st>>>(P, tile_list(c), c->S, (const XT*)c->X[cur], (const F*)c->U[cur], (const F*)c->KSG,
+                                                                     (F*)c->DU, c->cand_steps, (XT*)c->X[nxt], (F*)c->U[nxt]);
+    }
+    CK(cudaGetLastError());
+    ++c->launches;
+    return 0;
+}
+static int launch_forward_cand0(acoc_ctx* c) { return DISPATCH_FX(c, launch_forward_cand0_t, c); }
+
 // Armijo after candidate 0 (lazy) or all candidates at once (speculative): fills S.step and the history row kk.  Returns through
 // *lazy_only whether the update may skip instances whose candidate 0 is already in the next slot.
 template <typename F, typename XT>
@@ -1597,8 +1626,11 @@ static int launch_iteration_body(acoc_ctx* c)
         TRY(launch_fused_select(c));
         return launch_fused_pick(c);
     }
-    TRY(launch_forward(c));
-    if (is_lazy(c)) TRY(launch_cand0(c));
+    if (fwd_cand0_fused(c)) TRY(launch_forward_cand0(c));
+    else {
+        TRY(launch_forward(c));
+        if (is_lazy(c)) TRY(launch_cand0(c));
+    }
     TRY(launch_armijo(c, &lazy_only));
     TRY(launch_update(c, lazy_only, true, true));
     return 0;
@@ -1648,9 +1680,14 @@ int acoc_newton_iterate(acoc_ctx* c, int n_iters, int* n_active_out)
             if (prof) CK(cudaEventRecord(c->ev[4], c->stream));
             TRY(launch_fused_pick(c));
         } else {
-            TRY(launch_forward(c));
-            if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
-            if (is_lazy(c)) TRY(launch_cand0(c));
+            if (fwd_cand0_fused(c)) {  // (the "forward" phase of the profile then contains candidate 0)
+                TRY(launch_forward_cand0(c));
+                if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
+            } else {
+                TRY(launch_forward(c));
+                if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
+                if (is_lazy(c)) TRY(launch_cand0(c));
+            }
             TRY(launch_armijo(c, &lazy_only));
             if (prof) CK(cudaEventRecord(c->ev[4], c->stream));
             TRY(launch_update(c, lazy_only, true, true));

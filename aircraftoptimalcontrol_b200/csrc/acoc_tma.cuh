@@ -258,6 +258,114 @@ __global__ void __launch_bounds__(64, 7) k_rollout_write_tma(ProblemT<F> P, Tile
 }
 
 // =================================================================================================================
+// LQ forward pass + candidate 0 of the lazy Armijo search in ONE sweep (k_forward_tma followed by k_rollout_write_tma<.,0>):
+// both walk forward in time and the rollout needs du_t only at step t, so du never makes the round trip through HBM before
+// its first use and u_t is fetched once.  In: K/sigma/g, (V,theta,gamma), u, references per step; out: du, the tentative next
+// iterate, descent and the cost of candidate 0.  Same per-step functions in the same order: bit-identical to the two sweeps.
+// =================================================================================================================
+constexpr int FC_STAGES = 2;
+template <typename F, typename XT>
+struct FwdCandStage {
+    using Fw = FwdStage<F, XT>;
+    static constexpr int U_B = Fw::U_B, XR_B = NS * TILE * sizeof(F);
+    static constexpr int KSG_O = Fw::KSG_O, X23_O = Fw::X23_O, X5_O = Fw::X5_O, U_O = Fw::U_O, UR_O = Fw::U_O + U_B, XR_O = UR_O + U_B,
+                         BYTES = XR_O + XR_B;
+};
+
+template <bool Q32, typename F, typename XT>
+__global__ void __launch_bounds__(64, 7) k_forward_cand0_tma(ProblemT<F> P, TileList L, NewtonState S, const XT* __restrict__ X,
+                                                              const F* __restrict__ U, const F* __restrict__ KSG, F* __restrict__ DU,
+                                                              const double* __restrict__ cand_steps, XT* __restrict__ Xn, F* __restrict__ Un)
+{
+    using St = FwdCandStage<F, XT>;
+    using Fw = FwdStage<F, XT>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int tile = warp_tile(L, blockIdx.x * nw + warp, P.Np);
+    if (tile < 0) return;  // warp-uniform
+    WarpRing<FC_STAGES, St::BYTES> ring;
+    ring.init(smem, warp, nw, lane);
+    const int TT = P.TT, Np = P.Np, i = tile * TILE + lane, nsteps = TT - 1;
+    const bool live = i < P.N;                          // the forward pass runs for finished lanes of a live tile too (whole du lines)
+    const bool act = live && S.status[i] == ST_ACTIVE;  // the rollout only for instances that are still iterating
+    const bool shared_ref = P.ref_shared != 0;
+    auto issue = [&](int t) {
+        unsigned char* st = ring.stage(t);
+        uint64_t* b = ring.barrier(t);
+        mbar_arrive_expect_tx(b, Fw::BYTES_TX + (shared_ref ? 0 : St::U_B + St::XR_B));
+        tma_load(st + St::KSG_O, KSG + tile_base(t, 16, Np, tile), Fw::KSG_B, b);
+        tma_load(st + St::X23_O, X + tile_base(t, NS, Np, tile) + 2 * TILE, 2 * Fw::XC_B, b);
+        tma_load(st + St::X5_O, X + tile_base(t, NS, Np, tile) + 5 * TILE, Fw::XC_B, b);
+        tma_load(st + St::U_O, U + tile_base(t, NI, Np, tile), St::U_B, b);
+        if (!shared_ref) {
+            tma_load(st + St::UR_O, P.uref + tile_base(t, NI, Np, tile), St::U_B, b);
+            tma_load(st + St::XR_O, P.xref + tile_base(t, NS, Np, tile), St::XR_B, b);
+        }
+    };
+    if (lane == 0)
+        for (int t = 0; t < FC_STAGES && t < nsteps; ++t) issue(t);
+    const F s = (F)cand_steps[0];
+    F dx[NS] = {0, 0, 0, 0, 0, 0}, xc[NS];  // LQ state increment; state of the candidate rollout
+    double d = 0.0, J = 0.0;
+#pragma unroll
+    for (int c = 0; c < NS; ++c) xc[c] = live ? P.x0[(size_t)c * Np + i] : F(0.0);
+    for (int t = 0; t < nsteps; ++t) {
+        ring.wait(t);
+        const unsigned char* st = ring.stage(t);
+        F ksg[16], u[NI], xr[NS], ur[NI];
+        XT xraw[NS];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) ksg[c] = reinterpret_cast<const F*>(st + St::KSG_O)[c * TILE + lane];
+        xraw[0] = xraw[1] = xraw[4] = XT(0);  // X, Z, q do not enter the linearisation
+        xraw[2] = reinterpret_cast<const XT*>(st + St::X23_O)[lane];
+        xraw[3] = reinterpret_cast<const XT*>(st + St::X23_O)[TILE + lane];
+        xraw[5] = reinterpret_cast<const XT*>(st + St::X5_O)[lane];
+#pragma unroll
+        for (int c = 0; c < NI; ++c) u[c] = reinterpret_cast<const F*>(st + St::U_O)[c * TILE + lane];
+        if (!shared_ref) {
+#pragma unroll
+            for (int c = 0; c < NI; ++c) ur[c] = reinterpret_cast<const F*>(st + St::UR_O)[c * TILE + lane];
+#pragma unroll
+            for (int c = 0; c < NS; ++c) xr[c] = reinterpret_cast<const F*>(st + St::XR_O)[c * TILE + lane];
+        }
+        __syncwarp();  // every lane has read the stage: it can be refilled
+        if (lane == 0 && t + FC_STAGES < nsteps) issue(t + FC_STAGES);
+        if (live) {
+            F du[NI], xnom[NS];
+            forward_du(ksg, dx, du, d);
+            DU[at(t, NI, 0, Np, i)] = du[0];
+            DU[at(t, NI, 1, Np, i)] = du[1];
+            finish_x(P, t, i, xraw, xnom);
+            forward_advance(P.M, xnom, u, du, dx);
+            if (act) {
+                if (shared_ref) load_ref(P, t, i, xr, ur);
+                F uc[NI];
+#pragma unroll
+                for (int c = 0; c < NI; ++c) uc[c] = u[c] + s * du[c];  // optcon.py:197 / :253
+                store_x(Xn, t, Np, i, xc);
+#pragma unroll
+                for (int c = 0; c < NI; ++c) Un[at(t, NI, c, Np, i)] = uc[c];
+                rollout_step<true, Q32>(P.M, P.W, xc, uc, xr, ur, J);
+            }
+        }
+    }
+    if (!live) return;
+    DU[at(TT - 1, NI, 0, Np, i)] = F(0.0);  // uuout[:, TT-1] stays zero (optcon.py:694)
+    DU[at(TT - 1, NI, 1, Np, i)] = F(0.0);
+    if (!act) return;
+    S.descent[i] = d;
+    store_x(Xn, TT - 1, Np, i, xc);
+    Un[at(TT - 1, NI, 0, Np, i)] = F(0.0);  // uu_temp[:, TT-1] is never written (optcon.py:193)
+    Un[at(TT - 1, NI, 1, Np, i)] = F(0.0);
+    F xrT[NS], dxT[NS];
+    load_xref(P, TT - 1, i, xrT);
+#pragma unroll
+    for (int c = 0; c < NS; ++c) dxT[c] = xc[c] - xrT[c];
+    J += (double)term_cost(P.W, dxT);
+    S.Jcand[i] = J;
+}
+
+// =================================================================================================================
 // fused backward sweep (backward_instance): in x, u, references per step (walking t = TT-2 .. 0); out K/sigma/g
 // =================================================================================================================
 constexpr int BWD_STAGES = 3;

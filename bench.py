@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--x-storage", default="auto", choices=["auto", "f64"], help="f64: keep float32-valued states in float64 buffers (A/B)")
     ap.add_argument("--no-tma", action="store_true", help="plain-load sweeps instead of the TMA rings (A/B)")
     ap.add_argument("--no-split", action="store_true", help="one stream for the whole batch instead of the two-range sweep (A/B)")
+    ap.add_argument("--no-fused", action="store_true", help="separate LQ forward pass / candidate sweeps instead of the fused ones (A/B)")
     ap.add_argument("--cpu-sample", type=int, default=16384, help="instances of the bounded CPU sample (about 10 s of work on 16 host threads)")
     ap.add_argument("--chunks", type=int, default=8, help="sub-batches of the pipelined end-to-end solve")
     ap.add_argument("--no-e2e", action="store_true")
@@ -224,7 +225,8 @@ def main():
     K, W = args.steps, args.warmup
 
     xr, ur, dx0, (Q, R, QT) = make_problem(args.workload, n_total, (rank, world))
-    bn = pkg.BatchedNewton(n, TT=TT, device=local, state=args.state, armijo=args.armijo, precision=args.precision, x_storage=args.x_storage, tma=not args.no_tma, split=not args.no_split)
+    bn = pkg.BatchedNewton(n, TT=TT, device=local, state=args.state, armijo=args.armijo, precision=args.precision, x_storage=args.x_storage, tma=not args.no_tma, split=not args.no_split,
+                           fused=not args.no_fused)
     bn.set_weights(Q, R, QT)
     bn.set_refs(xr, ur)
     bn.init_guess(dx0=dx0)
@@ -277,12 +279,25 @@ def main():
         ncand = h["n_armijo"][:, W:W + K].astype(np.float64)
         steps_per = float(TT - 1)
         # algorithmic bytes / flops of every phase over the K timed iterations (SURVEY.md 8(d) per-unit figures)
+        # lazy search on the TMA path: the LQ forward pass and candidate 0 are ONE sweep (k_forward_cand0_tma); its time is the
+        # "forward" phase and it is accounted with the algorithmic bytes / flops of both (SURVEY.md 8(d) counts du written and read
+        # back and u read twice: 368 B; the fused kernel moves 276 B of them with float state slots)
+        fused_fc = args.armijo == "lazy" and not args.no_tma and not args.no_fused
+        MB = moved_bytes(args)
+        fwd_bytes, fwd_flops, fwd_moved = BYTES["forward"], FLOPS["forward"], MB["forward"]
+        if fused_fc:
+            fwd_bytes += BYTES["candidate_write"]
+            fwd_flops += FLOPS["candidate"]
+            # minus the du read-back and the second read of u, minus the state components the ring does not fetch (only V, theta, gamma)
+            x_float = args.precision == "f32" or MB["forward"] != BYTES["forward"]
+            fwd_moved += MB["candidate_write"] - (16 if args.precision == "f32" else 32) - (12 if x_float else 24)
         if args.armijo == "lazy":
             # candidate 0 for everyone, written tentatively (it is the update when accepted); the other 9 candidates and a
             # separate update rollout only for instances whose candidate 0 failed
             n_fail = float(np.sum(ncand > 1))
-            cand_bytes = steps_per * (ncand.size * BYTES["candidate_write"] + 9 * n_fail * BYTES["candidate"])
-            cand_flops = steps_per * (ncand.size + 9 * n_fail) * FLOPS["candidate"]
+            n_c0 = 0.0 if fused_fc else float(ncand.size)
+            cand_bytes = steps_per * (n_c0 * BYTES["candidate_write"] + 9 * n_fail * BYTES["candidate"])
+            cand_flops = steps_per * (n_c0 + 9 * n_fail) * FLOPS["candidate"]
             upd_units = n_fail
         else:
             cand_bytes = steps_per * ncand.size * 10 * BYTES["candidate"]
@@ -291,15 +306,14 @@ def main():
         phases = tp["phases"]
         per_launch_ms = {k: v / K for k, v in phases.items()}
         dom = max(("backward", "forward", "candidates", "update"), key=lambda k: phases[k])
-        tot_bytes = {"backward": steps_per * n * K * BYTES["backward"], "forward": steps_per * n * K * BYTES["forward"],
+        tot_bytes = {"backward": steps_per * n * K * BYTES["backward"], "forward": steps_per * n * K * fwd_bytes,
                      "candidates": cand_bytes, "update": steps_per * upd_units * BYTES["update"]}
-        tot_flops = {"backward": steps_per * n * K * FLOPS["backward"], "forward": steps_per * n * K * FLOPS["forward"],
+        tot_flops = {"backward": steps_per * n * K * FLOPS["backward"], "forward": steps_per * n * K * fwd_flops,
                      "candidates": cand_flops, "update": steps_per * upd_units * FLOPS["update"]}
         fp64_peak = _lib.measure_fp64_peak(local)
-        MB = moved_bytes(args)
-        moved_ratio = {"backward": MB["backward"] / BYTES["backward"], "forward": MB["forward"] / BYTES["forward"],
+        moved_ratio = {"backward": MB["backward"] / BYTES["backward"], "forward": fwd_moved / fwd_bytes,
                        "update": MB["update"] / BYTES["update"],
-                       "candidates": ((ncand.size * MB["candidate_write"] + 9 * n_fail * MB["candidate"]) / (ncand.size * BYTES["candidate_write"] + 9 * n_fail * BYTES["candidate"])
+                       "candidates": ((n_c0 * MB["candidate_write"] + 9 * n_fail * MB["candidate"]) / max(n_c0 * BYTES["candidate_write"] + 9 * n_fail * BYTES["candidate"], 1.0)
                                       if args.armijo == "lazy" else MB["candidate"] / BYTES["candidate"])}
         tbl = {}
         for k in ("backward", "forward", "candidates", "update"):
@@ -328,7 +342,8 @@ def main():
                     "fp64": {"achieved_algorithmic_tflops": d["fp64_tflops"], "peak_tflops": fp64_peak, "frac_algorithmic": d["fp64_frac"],
                              "peak_source": "DFMA microbenchmark run in this process (acoc_measure_fp64_peak)",
                              "note": "algorithmic = dense ns=6/ni=2 flop count of SURVEY.md 8(d); executed flops are lower (structure-exploiting sweep)"},
-                    "per_kernel": tbl, "share_of_step": phases[dom] / max(sum(phases.values()), 1e-9),
+                    "per_kernel": tbl, "forward_phase": ("k_forward_cand0_tma: LQ forward pass + candidate 0 in one sweep" if fused_fc else "k_forward"),
+                    "share_of_step": phases[dom] / max(sum(phases.values()), 1e-9),
                     "algorithmic": {"bytes_per_instance_step": BYTES, "flops_per_instance_step": FLOPS,
                                     "note": "SURVEY.md 8(d) per-unit figures x (TT-1) x instances per launch"},
                     "moved": {"bytes_per_instance_step": MB, "achieved": d["hbm_gbs_moved"], "frac": d["hbm_frac_moved"],

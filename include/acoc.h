@@ -48,8 +48,9 @@ typedef enum acoc_status {
 #define ACOC_NO_TMA 64u          /* run the sweeps with plain global loads instead of the warp-private TMA (bulk async copy) rings;
                                     results are bit-identical, this is for A/B measurements */
 #define ACOC_NO_SPLIT 128u        /* never sweep a fully active batch as two tile ranges on two streams (A/B measurements; identical results) */
-#define ACOC_NO_FUSED 256u       /* small batches (<= 4096 instances): never run the LQ forward pass and the whole Armijo search as one sweep
-                                    (k_search_fused); use the separate sweeps of the large-batch path instead (A/B tests; identical results) */
+#define ACOC_NO_FUSED 256u       /* never fuse the LQ forward pass with line-search rollouts: neither with candidate 0 of the lazy search
+                                    (k_forward_cand0_tma, any batch size) nor with the whole search of small batches (k_search_fused, <= 4096
+                                    instances); the separate sweeps run instead (A/B tests; identical results) */
 #define ACOC_X_F64 32u           /* keep the state iterates in float64 device buffers even when every stored state is a float32 value
                                     (ACOC_STATE_F32); results are bit-identical either way, this only costs bandwidth (A/B tests) */
 
