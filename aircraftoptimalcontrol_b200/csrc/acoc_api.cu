@@ -676,6 +676,8 @@ __global__ void k_copy(const double2* __restrict__ a, double2* __restrict__ b, s
 // ======================================================================================================
 // context
 // ======================================================================================================
+constexpr int MAX_RANGES = 8;  // independent tile ranges of a fully active batch (acoc_newton_iterate)
+
 struct acoc_ctx {
     int device = 0, N = 0, Np = 0, TT = 0;
     unsigned flags = 0;
@@ -716,8 +718,10 @@ struct acoc_ctx {
     int ls_off = 0, ls_end = 0x7fffffff;
     bool ls_identity = false;
     int ls_range = 0;           // index of the current range (its need-list counter)
-    cudaStream_t rstream[4] = {nullptr, nullptr, nullptr, nullptr};  // streams of ranges 1..3 (range 0 uses `stream`)
-    cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t rstream[MAX_RANGES] = {};  // streams of ranges 1.. (range 0 uses `stream`)
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_RANGES] = {};
+    int last_need = -1;         // instances whose candidate 0 failed in the last iteration of the previous call (lazy search); -1: unknown
+    int sm_count = 0;
     bool all_active = false;    // more than half of the instances were active at the last host-side count (reset: all of them)
     int bwd_wave_ctas = 0;      // CTAs of the backward sweep that are resident at once on this device (occupancy x SMs)
     // small batches: one trajectory slot per Armijo candidate (+ the exhausted step), see k_search_fused
@@ -815,6 +819,7 @@ static int reset_state(acoc_ctx* c)
     CK(cudaGetLastError());
     c->kk = 0;
     c->all_active = true;
+    c->last_need = -1;
     return 0;
 }
 
@@ -1067,7 +1072,8 @@ int acoc_ctx_create(int device, int n_instances, int TT, unsigned flags, acoc_ct
     if (!rc) rc = dalloc(c, &c->need2, Np);
     if (!rc) rc = dalloc(c, &c->slot_tmp, Np);
     if (!rc) rc = dalloc(c, &c->origin, Np);
-    if (!rc) rc = dalloc(c, &c->counters, 8);
+    if (!rc) rc = dalloc(c, &c->counters, 4 + 2 * MAX_RANGES);  // [0] active count, [1] tile list, [2] need list of range 0, [3 + r] of range r >= 1,
+                                                               // [4 + MAX_RANGES + r] second-stage need list of range r
     if (!rc) rc = dalloc(c, &c->act_groups, Np);
     if (!rc) rc = dalloc(c, &c->need_groups, Np);
     if (!rc) rc = dalloc(c, &c->iters_sum, 2);
@@ -1086,7 +1092,7 @@ int acoc_ctx_create(int device, int n_instances, int TT, unsigned flags, acoc_ct
     for (int e = 0; e < 8; ++e) if (cudaEventCreate(&c->ev[e]) != cudaSuccess) return bail(fail(ACOC_ERR_CUDA, "cudaEventCreate failed"));
     c->ev_ok = true;
     if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(fail(ACOC_ERR_CUDA, "event creation failed"));
-    for (int r = 1; r < 4; ++r)
+    for (int r = 1; r < MAX_RANGES; ++r)
         if (cudaStreamCreateWithFlags(&c->rstream[r], cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->ev_join[r], cudaEventDisableTiming) != cudaSuccess)
             return bail(fail(ACOC_ERR_CUDA, "stream/event creation failed"));
@@ -1106,7 +1112,7 @@ int acoc_ctx_destroy(acoc_ctx* c)
     for (void* p : c->allocs) cudaFree(p);
     if (c->ev_ok) for (int e = 0; e < 8; ++e) cudaEventDestroy(c->ev[e]);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-    for (int r = 1; r < 4; ++r) {
+    for (int r = 1; r < MAX_RANGES; ++r) {
         if (c->ev_join[r]) cudaEventDestroy(c->ev_join[r]);
         if (c->rstream[r]) { cudaStreamSynchronize(c->rstream[r]); cudaStreamDestroy(c->rstream[r]); }
     }
@@ -1263,6 +1269,7 @@ static int scope_i0(const acoc_ctx* c) { return c->ls_off * 32; }
 static int n_tiles(const acoc_ctx* c) { return (c->N + 31) / 32; }  // tiles that hold instances (a child context may use less than its capacity Np)
 static int scope_i1(const acoc_ctx* c) { return (int)std::min<long long>(c->N, (long long)std::min(n_tiles(c), c->ls_end) * 32); }
 static int* scope_need_count(acoc_ctx* c) { return c->counters + (c->ls_range == 0 ? 2 : 3 + c->ls_range); }
+static int* scope_need2_count(acoc_ctx* c) { return c->counters + 4 + MAX_RANGES + c->ls_range; }  // second-stage list of the Gauss-Newton split
 // stream and grid of a sweep launch in the current launch scope (the whole padded batch, or a range of its tiles)
 static cudaStream_t sweep_stream(const acoc_ctx* c) { return c->ls_stream ? c->ls_stream : c->stream; }
 static int sweep_grid(const acoc_ctx* c, int threads)
@@ -1316,6 +1323,7 @@ static int launch_backward_t(acoc_ctx* c, bool exact)
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_backward_tma<true, F, XT>, BWD_THREADS, sm));
             CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
             c->bwd_wave_ctas = std::max(1, nb * sms);
+            c->sm_count = sms;
         }
     } else if (exact) k_backward<true, F, XT><<<g, BWD_THREADS, 0, c->stream>>>(P, act_list(c), X, U, (F*)c->KSG, c->S.status, c->S.n_reg);
     else k_backward<false, F, XT><<<g, BWD_THREADS, 0, c->stream>>>(P, act_list(c), X, U, (F*)c->KSG, c->S.status, c->S.n_reg);
@@ -1468,7 +1476,9 @@ static int launch_armijo_t(acoc_ctx* c, bool* lazy_only)
         if (split < nc) {
             k_lazy_need<<<(n + 255) / 256, 256, 0, st>>>(c->O, c->S, c->cand_steps, i0, i1, Np, split, c->need2);
             CK(cudaGetLastError());
-            k_build_list<<<1, 1024, 0, st>>>(c->need2, 1, n, 0, c->need_groups + i0, cnt, i0);
+            int* cnt2 = scope_need2_count(c);  // (a counter of its own: the first-stage count tells the host how many searches failed candidate 0)
+            L.count = cnt2;
+            k_build_list<<<1, 1024, 0, st>>>(c->need2, 1, n, 0, c->need_groups + i0, cnt2, i0);
             CK(cudaGetLastError());
             LAUNCH_CAND(c->P.q32, F, (n + CAND_TILE - 1) / CAND_TILE, std::min(nc - split, CAND_MAXY), st, P, L, U, DU, c->cand_steps, split, nc,
                         c->S.status, c->S.Jcand);
@@ -1644,7 +1654,9 @@ int acoc_newton_iterate(acoc_ctx* c, int n_iters, int* n_active_out)
     c->total_ms = 0; for (int p = 0; p < 6; ++p) c->phase_ms[p] = 0;
     c->launches = 0;
     CK(cudaEventRecord(c->ev[6], c->stream));
-    int it = 0;
+    int it = 0, nr_last = 1;
+    const int kk_in = c->kk;
+    const bool fused_small = fused_search(c);  // (no need lists in that mode)
     for (; it < n_iters; ++it) {
         if (c->kk >= c->O.max_iters - 1) break;  // for kk in range(max_iters-1), optcon.py:415
         // Two ranges.  The backward sweep keeps only bwd_wave_ctas CTAs resident (216 registers per thread), so a batch with more
@@ -1706,16 +1718,26 @@ int acoc_newton_iterate(acoc_ctx* c, int n_iters, int* n_active_out)
     }
     if (it < n_iters && c->kk < c->O.max_iters - 1) {  // the remaining iterations as two independent ranges (see above)
         const int tiles = n_tiles(c), ctas = (tiles + 1) / 2, wave = c->bwd_wave_ctas;
-        int bound[5] = {0, (ctas / wave) * wave * 2, tiles, tiles, tiles}, nr = 2;
-        if (const char* e = getenv("ACOC_RANGES")) {  // tuning experiments: up to three ascending tile boundaries "a,b,c"
+        int bound[MAX_RANGES + 1] = {0, (ctas / wave) * wave * 2}, nr = 2;
+        // Clean phase (candidate 0 was accepted by practically every instance in the last iteration the host knows of): every iteration
+        // is backward -> forward + candidate 0, one latency-bound and one bandwidth-bound sweep, and they overlap the better the more
+        // ranges there are -- ranges of about one backward CTA per SM (2 x SMs tiles).  With failing searches the compute-bound
+        // candidate kernels of many small ranges cost more than the overlap gains, so two ranges are kept there.
+        static const bool many = getenv("ACOC_NO_MANY_RANGES") == nullptr;
+        if (many && c->last_need >= 0 && (long long)c->last_need * 2048 < c->N && c->sm_count > 0) {
+            nr = std::max(2, std::min(MAX_RANGES, (tiles + 2 * c->sm_count - 1) / (2 * c->sm_count)));
+            const int size = ((tiles + nr - 1) / nr + 1) / 2 * 2;  // whole CTAs (two tiles)
+            for (int r = 1; r < nr; ++r) bound[r] = std::min(tiles, r * size);
+        }
+        if (const char* e = getenv("ACOC_RANGES")) {  // tuning experiments: ascending tile boundaries "a,b,c,..."
             nr = 1;
-            for (const char* q = e; *q && nr < 4; ++nr) {
+            for (const char* q = e; *q && nr < MAX_RANGES; ++nr) {
                 bound[nr] = std::max(bound[nr - 1] + 2, std::min(tiles - 2, atoi(q)));
                 while (*q && *q != ',') ++q;
                 if (*q == ',') ++q;
             }
-            for (int r = nr; r < 5; ++r) bound[r] = tiles;
         }
+        for (int r = nr; r <= MAX_RANGES; ++r) bound[r] = tiles;
         const int kk0 = c->kk;
         const int todo = std::min(n_iters - it, c->O.max_iters - 1 - c->kk);
         CK(cudaEventRecord(c->ev_fork, c->stream));
@@ -1737,9 +1759,20 @@ int acoc_newton_iterate(acoc_ctx* c, int n_iters, int* n_active_out)
             CK(cudaEventRecord(c->ev_join[r], c->rstream[r]));
             CK(cudaStreamWaitEvent(c->stream, c->ev_join[r], 0));
         }
+        nr_last = nr;
     }
+    // instances whose candidate 0 failed in the last iteration (lengths of the need lists of the lazy search): decides between the
+    // clean-phase and the two-range split of the next call
+    int hc[4 + MAX_RANGES] = {};
+    const bool lazy_counts = (c->flags & ACOC_ARMIJO_LAZY) && c->O.armijo_maxiters > 1 && c->kk > kk_in && !fused_small && is_lazy(c) &&
+                             c->O.method == ACOC_METHOD_NEWTON;
+    if (lazy_counts) CK(cudaMemcpyAsync(hc, c->counters, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaEventRecord(c->ev[7], c->stream));
     CK(cudaEventSynchronize(c->ev[7]));
+    if (lazy_counts) {
+        c->last_need = hc[2];
+        for (int r = 1; r < nr_last; ++r) c->last_need += hc[3 + r];
+    }
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]));
     c->total_ms = ms;
@@ -1876,8 +1909,11 @@ int acoc_newton_solve(acoc_ctx* c, long long* total_iters)
     std::vector<acoc_ctx*> chain{c};
     acoc_ctx* cur = c;
     while (active > 0 && cur->kk < cur->O.max_iters - 1) {
-        // check for completion every 4 iterations: one tiny D2H per check keeps the stream busy in between
-        TRY(acoc_newton_iterate(cur, 4, &active));
+        // check for completion every 4 iterations: one tiny D2H per check keeps the stream busy in between.  In the clean phase (no
+        // failing search in the last iteration seen) nothing converges yet and the many-range split of acoc_newton_iterate needs
+        // longer calls to amortise its fill and drain: 8 iterations per call there.
+        const bool clean = cur->last_need >= 0 && (long long)cur->last_need * 2048 < cur->N;
+        TRY(acoc_newton_iterate(cur, clean ? 8 : 4, &active));
         total_ms += cur->total_ms; launches += cur->launches;
         for (int p = 0; p < 6; ++p) phase[p] += cur->phase_ms[p];
         if (active > 0 && !(c->flags & ACOC_SOLVE_IN_PLACE) && cur->N >= ACOC_GEN_MIN && 2 * active <= cur->N && cur->kk < cur->O.max_iters - 1) {
