@@ -196,7 +196,7 @@ def main():
     ap.add_argument("--no-split", action="store_true", help="one stream for the whole batch instead of the two-range sweep (A/B)")
     ap.add_argument("--no-fused", action="store_true", help="separate LQ forward pass / candidate sweeps instead of the fused ones (A/B)")
     ap.add_argument("--cpu-sample", type=int, default=16384, help="instances of the bounded CPU sample (about 10 s of work on 16 host threads)")
-    ap.add_argument("--chunks", type=int, default=8, help="sub-batches of the pipelined end-to-end solve")
+    ap.add_argument("--chunks", type=int, default=4, help="sub-batches of the pipelined end-to-end solve (4: 0.42 s, 8: 0.44-0.46 s, 12: 0.52 s)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")

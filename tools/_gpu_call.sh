@@ -1,4 +1,2 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "two_range or fused_search or ragged or batch_solve" 2>&1 | tail -3
-timeout 600 python bench.py --no-e2e --no-cpu --no-roofline > gpurun_out/bench_short.json 2>/dev/null; python -c "import json; d=json.load(open('gpurun_out/bench_short.json')); print(round(d['value']), d['ms_per_step'], d['whole_solve']['device_ms'], d['gpu_launches'])"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_r01e.csv python bench.py --no-e2e --no-cpu --no-roofline > gpurun_out/ncu_launches.log 2>&1; tail -c 300 gpurun_out/ncu_launches.log
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_forward_cand0_tma" -c 1 -o gpurun_out/prof_r01e_fwdcand0_full -f python bench.py --no-e2e --no-cpu --no-roofline --steps 1 --warmup 1 > gpurun_out/ncu_fc.log 2>&1; tail -1 gpurun_out/ncu_fc.log
+run() { python bench.py --no-cpu --no-roofline --steps 8 --warmup 3 $1 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(' e2e wall', round(d['e2e']['wall_s'],4), 'e2e it/s', round(d['e2e']['value']))"; }
+for c in 4 2 3 5 4; do echo "chunks=$c"; run "--chunks $c"; done
