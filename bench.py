@@ -129,6 +129,8 @@ def cpu_port_rate(workload, sample, W, K, state):
         xi[i], ui[i] = corcl.initial_trajectory(xref_i if dx0 is not None else xr[i], quant_f32=(state == "f32"))
     nt = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     kw = dict(quant_f32=(state == "f32"), n_threads=nt)
+    m = min(sample, nt)   # untimed: starts the OpenMP thread pool and faults in the library
+    corcl.newton_batch(xr[:m], ur[:m], xi[:m], ui[:m], Q, R, QT, n_iters_cap=1, **kw)
     t0 = time.perf_counter()
     a = corcl.newton_batch(xr, ur, xi, ui, Q, R, QT, n_iters_cap=W, **kw) if W > 0 else None
     t1 = time.perf_counter()
@@ -136,6 +138,8 @@ def cpu_port_rate(workload, sample, W, K, state):
     t2 = time.perf_counter()
     its = int(b["iters"].sum()) - (int(a["iters"].sum()) if a is not None else 0)
     dt = (t2 - t1) - (t1 - t0 if a is not None else 0.0)
+    if dt <= 0 or its <= 0:  # (only with samples so small that timer noise exceeds K iterations: time the W+K run as a whole)
+        dt, its = t2 - t1, int(b["iters"].sum())
     return its / dt, nt, dt, its
 
 

@@ -606,3 +606,34 @@ def test_gradient_method_fp32_mode(gpu):
     assert np.max(np.abs(s32["J"] - s64["J"]) / s64["J"]) < 1e-4      # 12 line searches on float32 noise: same descent path, not the same floats
     assert np.max(np.abs(h32["JJ"][:, 0] - h64["JJ"][:, 0]) / h64["JJ"][:, 0]) < FP32_TOL["J_rel"]
     assert np.max(np.abs(u32 - u64)) < 50 * FP32_TOL["u_rel_range"] * np.max(np.abs(u64))
+
+
+def test_gradient_method_survivor_generations(gpu):
+    """The gradient method shares the driver's survivor generations: with a loose termination threshold the instances of an
+    8192-instance batch stop at different iterations, the survivors move into smaller contexts, and everything must equal iterating in
+    place bit for bit."""
+    n, TT = 8192, 100
+    xr, ur, Q, R, QT = _random_batch(n, TT, 55, 0.1)
+    out = []
+    for gen in (True, False):
+        with gpu.BatchedNewton(n, TT=TT, armijo="lazy", method="gradient", max_iters=40, generations=gen) as bn:
+            bn.set_weights(Q, R, QT)
+            bn.set_refs(xr, ur)
+            bn.init_guess()
+            d0 = bn.gradient()
+        thr = float(np.median(d0)) * 0.25   # |deltau|^2 threshold between the instances' starting values and zero
+        with gpu.BatchedNewton(n, TT=TT, armijo="lazy", method="gradient", max_iters=40, generations=gen, term_cond=-thr) as bn:
+            bn.set_weights(Q, R, QT)
+            bn.set_refs(xr, ur)
+            bn.init_guess()
+            total = bn.solve()
+            out.append((total, bn.result(), bn.history(), bn.stats()))
+    a, b = out
+    assert a[0] == b[0]
+    assert np.array_equal(a[1][0], b[1][0]) and np.array_equal(a[1][1], b[1][1])
+    for k in ("JJ", "descent", "stepsize", "n_armijo"):
+        assert np.array_equal(a[2][k], b[2][k]), k
+    for k in ("iters", "status", "J", "descent"):
+        assert np.array_equal(a[3][k], b[3][k]), k
+    it = a[3]["iters"]
+    assert it.min() < it.max() and np.sum(a[3]["status"] == 1) > n // 2   # they really stopped at different iterations
