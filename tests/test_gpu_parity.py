@@ -609,23 +609,25 @@ def test_gradient_method_fp32_mode(gpu):
 
 
 def test_gradient_method_survivor_generations(gpu):
-    """The gradient method shares the driver's survivor generations: with a loose termination threshold the instances of an
-    8192-instance batch stop at different iterations, the survivors move into smaller contexts, and everything must equal iterating in
-    place bit for bit."""
+    """The gradient method shares the driver's survivor generations: with a loose termination threshold (chosen from a probing run so
+    that about half of the instances cross it within 11 iterations, at different iterations) the survivors of an 8192-instance batch move
+    into smaller contexts, and everything must equal iterating in place bit for bit."""
     n, TT = 8192, 100
     xr, ur, Q, R, QT = _random_batch(n, TT, 55, 0.1)
+
+    def solver(**kw):
+        bn = gpu.BatchedNewton(n, TT=TT, armijo="lazy", method="gradient", **kw)
+        bn.set_weights(Q, R, QT)
+        bn.set_refs(xr, ur)
+        bn.init_guess()
+        return bn
+
+    with solver(max_iters=13, generations=False) as bn:
+        bn.solve()
+        thr = float(np.median(np.min(-bn.history()["descent"][:, :12], axis=1)))   # history holds the slope -|deltau|^2
     out = []
     for gen in (True, False):
-        with gpu.BatchedNewton(n, TT=TT, armijo="lazy", method="gradient", max_iters=40, generations=gen) as bn:
-            bn.set_weights(Q, R, QT)
-            bn.set_refs(xr, ur)
-            bn.init_guess()
-            d0 = bn.gradient()
-        thr = float(np.median(d0)) * 0.25   # |deltau|^2 threshold between the instances' starting values and zero
-        with gpu.BatchedNewton(n, TT=TT, armijo="lazy", method="gradient", max_iters=40, generations=gen, term_cond=-thr) as bn:
-            bn.set_weights(Q, R, QT)
-            bn.set_refs(xr, ur)
-            bn.init_guess()
+        with solver(max_iters=40, generations=gen, term_cond=-thr) as bn:
             total = bn.solve()
             out.append((total, bn.result(), bn.history(), bn.stats()))
     a, b = out
@@ -636,4 +638,4 @@ def test_gradient_method_survivor_generations(gpu):
     for k in ("iters", "status", "J", "descent"):
         assert np.array_equal(a[3][k], b[3][k]), k
     it = a[3]["iters"]
-    assert it.min() < it.max() and np.sum(a[3]["status"] == 1) > n // 2   # they really stopped at different iterations
+    assert np.sum(a[3]["status"] == 1) >= n // 2 and len(np.unique(it[a[3]["status"] == 1])) >= 2   # they stopped, at different iterations
