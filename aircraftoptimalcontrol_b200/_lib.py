@@ -23,6 +23,7 @@ NO_TMA = 64
 NO_SPLIT = 128
 NO_FUSED = 256
 METHOD_NEWTON, METHOD_GRADIENT = 0, 1
+PRIORITY_SHIFT = 16
 
 INST_ACTIVE, INST_CONVERGED, INST_MAXITER, INST_NONFINITE = 0, 1, 2, 3
 

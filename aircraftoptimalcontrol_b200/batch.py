@@ -36,6 +36,8 @@ class BatchedNewton:
     descent) with the repaired line-search call described in include/acoc.h (ACOC_METHOD_GRADIENT).  In that mode the `descent`
     entries of history() / stats() are the slope -sum|deltau|^2 handed to the Armijo test (the reference's descent[kk] is its
     negative), `term_cond` keeps its meaning (stop when slope >= term_cond, i.e. descent <= 1e-6, optcon.py:52,157).
+    priority: stream priority level 0..15 of this context (ACOC_PRIORITY): of several contexts working on one GPU at the same time the
+    one with the higher level gets the SMs first (used by PipelinedNewton to stagger its sub-batches); no effect on results.
     fused: fuse the LQ forward pass with the line-search rollouts that follow it -- with candidate 0 of the lazy search in one sweep
     (any batch size), and, for batches of at most 4096 instances (late survivor generations, single trajectories), with the whole
     Armijo search, get_update then being a copy of the chosen candidate (default; identical results, A/B measurements).
@@ -43,7 +45,7 @@ class BatchedNewton:
 
     def __init__(self, n_instances, TT=1000, device=0, state="f32", refs_shared=False, armijo="speculative", params=None, generations=True,
                  max_iters=200, stepsize_0=1.0, cc=0.5, beta=0.7, armijo_maxiters=10, term_cond=-1e-6, exact_after=8, precision="f64",
-                 x_storage="auto", tma=True, split=True, fused=True, method="newton"):
+                 x_storage="auto", tma=True, split=True, fused=True, method="newton", priority=0):
         if state not in ("f32", "f64"):
             raise ValueError("state must be 'f32' or 'f64'")
         if armijo not in ("speculative", "lazy"):
@@ -60,7 +62,8 @@ class BatchedNewton:
         self.precision = precision
         flags = ((L.STATE_F64 if state == "f64" else 0) | (L.REFS_SHARED if refs_shared else 0) | (L.ARMIJO_LAZY if armijo == "lazy" else 0)
                  | (0 if generations else L.SOLVE_IN_PLACE) | (L.FP32 if precision == "f32" else 0) | (L.X_F64 if x_storage == "f64" else 0)
-                 | (0 if tma else L.NO_TMA) | (0 if split else L.NO_SPLIT) | (0 if fused else L.NO_FUSED))
+                 | (0 if tma else L.NO_TMA) | (0 if split else L.NO_SPLIT) | (0 if fused else L.NO_FUSED)
+                 | ((max(0, min(15, int(priority))) & 15) << L.PRIORITY_SHIFT))
         self._h = C.c_void_p(None)
         L.check(L.lib().acoc_ctx_create(self.device, self.N, self.TT, flags, C.addressof(self._h)))
         self.opts = L.NewtonOptions(int(max_iters), int(armijo_maxiters), int(exact_after),
@@ -238,11 +241,14 @@ class PipelinedNewton:
     reused across `solve` calls.
     """
 
-    def __init__(self, n_instances, n_chunks=4, TT=1000, device=0, **solver_kw):
+    def __init__(self, n_instances, n_chunks=4, TT=1000, device=0, stagger=True, **solver_kw):
         self.N, self.TT = int(n_instances), int(TT)
         n_chunks = max(1, min(int(n_chunks), self.N))
         self.bounds = [(self.N * k) // n_chunks for k in range(n_chunks + 1)]
-        self.parts = [BatchedNewton(self.bounds[k + 1] - self.bounds[k], TT=TT, device=device, **solver_kw) for k in range(n_chunks)]
+        # stagger: earlier sub-batches get a higher stream priority, so that they finish (and download) one after the other while the
+        # later ones still iterate, instead of all sub-batches finishing together with every download left for the end
+        self.parts = [BatchedNewton(self.bounds[k + 1] - self.bounds[k], TT=TT, device=device,
+                                    priority=(min(15, n_chunks - k) if stagger and n_chunks > 1 else 0), **solver_kw) for k in range(n_chunks)]
 
     def close(self):
         for p in self.parts:

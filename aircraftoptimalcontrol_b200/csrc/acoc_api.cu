@@ -720,6 +720,7 @@ struct acoc_ctx {
     int ls_range = 0;           // index of the current range (its need-list counter)
     cudaStream_t rstream[MAX_RANGES] = {};  // streams of ranges 1.. (range 0 uses `stream`)
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_RANGES] = {};
+    int stream_priority = 0;    // CUDA priority of the context's streams (ACOC_PRIORITY)
     int last_need = -1;         // instances whose candidate 0 failed in the last iteration of the previous call (lazy search); -1: unknown
     int sm_count = 0;
     bool all_active = false;    // more than half of the instances were active at the last host-side count (reset: all of them)
@@ -1046,7 +1047,14 @@ int acoc_ctx_create(int device, int n_instances, int TT, unsigned flags, acoc_ct
     memset(&c->P, 0, sizeof(c->P)); memset(&c->S, 0, sizeof(c->S));
     default_opts(&c->O);
     auto bail = [&](int rc) { acoc_ctx_destroy(c); return rc; };
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(ACOC_ERR_CUDA, "cudaStreamCreate failed"));
+    // ACOC_PRIORITY(level): the context's streams are scheduled before those of contexts with a lower level (see acoc.h)
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);  // numerically smaller = higher priority
+    const int level = (int)((flags >> ACOC_PRIORITY_SHIFT) & 15u);
+    const int prio = std::max(prio_greatest, prio_least - level);
+    c->stream_priority = prio;
+    if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio) != cudaSuccess)
+        return bail(fail(ACOC_ERR_CUDA, "cudaStreamCreate failed"));
     const size_t Np = c->Np, T = TT;
     c->fp32 = (flags & ACOC_FP32) != 0;
     c->x_float = c->fp32;
@@ -1093,7 +1101,7 @@ int acoc_ctx_create(int device, int n_instances, int TT, unsigned flags, acoc_ct
     c->ev_ok = true;
     if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(fail(ACOC_ERR_CUDA, "event creation failed"));
     for (int r = 1; r < MAX_RANGES; ++r)
-        if (cudaStreamCreateWithFlags(&c->rstream[r], cudaStreamNonBlocking) != cudaSuccess ||
+        if (cudaStreamCreateWithPriority(&c->rstream[r], cudaStreamNonBlocking, c->stream_priority) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->ev_join[r], cudaEventDisableTiming) != cudaSuccess)
             return bail(fail(ACOC_ERR_CUDA, "stream/event creation failed"));
     rc = reset_state(c);

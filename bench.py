@@ -201,6 +201,7 @@ def main():
     ap.add_argument("--no-fused", action="store_true", help="separate LQ forward pass / candidate sweeps instead of the fused ones (A/B)")
     ap.add_argument("--cpu-sample", type=int, default=16384, help="instances of the bounded CPU sample (about 10 s of work on 16 host threads)")
     ap.add_argument("--chunks", type=int, default=4, help="sub-batches of the pipelined end-to-end solve (4: 0.42 s, 8: 0.44-0.46 s, 12: 0.52 s)")
+    ap.add_argument("--no-stagger", action="store_true", help="end-to-end leg: same stream priority for every sub-batch (A/B)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -378,7 +379,8 @@ def main():
         xs_t = torch.empty((n, 6, TT), dtype=torch.float64, pin_memory=True)
         us_t = torch.empty((n, 2, TT), dtype=torch.float64, pin_memory=True)
         pn = pkg.PipelinedNewton(n, n_chunks=args.chunks, TT=TT, device=local, state=args.state, armijo=args.armijo, precision=args.precision,
-                                 x_storage=args.x_storage, tma=not args.no_tma, split=not args.no_split)
+                                 x_storage=args.x_storage, tma=not args.no_tma, split=not args.no_split, fused=not args.no_fused,
+                                 stagger=not args.no_stagger)
         pn.set_weights(Q, R, QT)
         pn.solve(xr_p.numpy(), ur_p.numpy(), dx0=dx0, out=(xs_t.numpy(), us_t.numpy()))   # untimed warm-up of the whole path
         barrier()
@@ -405,7 +407,7 @@ def main():
                "wall_s": wall, "total_newton_iterations": tot, "solver_steps": steps_e2e,
                "converged": int((g["status"] == 1).sum()), "instances": n_total, "mean_iters": float(g["iters"].mean()),
                "stats_gather_s": t2 - t1,
-               "chunks": args.chunks,
+               "chunks": args.chunks, "staggered_priorities": not args.no_stagger,
                "what": "PipelinedNewton.solve(pinned host refs): per sub-batch set_refs (H2D) -> init_guess (device) -> solve() to descent >= -1e-6 "
                        "-> result()/stats() (D2H to pinned host); sub-batches overlap copies with compute"}
 

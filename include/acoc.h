@@ -51,6 +51,13 @@ typedef enum acoc_status {
 #define ACOC_NO_FUSED 256u       /* never fuse the LQ forward pass with line-search rollouts: neither with candidate 0 of the lazy search
                                     (k_forward_cand0_tma, any batch size) nor with the whole search of small batches (k_search_fused, <= 4096
                                     instances); the separate sweeps run instead (A/B tests; identical results) */
+#define ACOC_PRIORITY_SHIFT 16
+#define ACOC_PRIORITY(level) (((unsigned)(level) & 15u) << ACOC_PRIORITY_SHIFT)
+                                 /* stream priority level of the context, 0 (default) .. 15: the device schedules the thread blocks of a
+                                    context with a higher level first (clamped to the device's priority range).  Contexts that solve
+                                    concurrently on one GPU (the sub-batches of a pipelined solve) then finish one after the other instead of
+                                    all at the end, so that the device->host copy of one overlaps the iterations of the next.  No effect
+                                    on results. */
 #define ACOC_X_F64 32u           /* keep the state iterates in float64 device buffers even when every stored state is a float32 value
                                     (ACOC_STATE_F32); results are bit-identical either way, this only costs bandwidth (A/B tests) */
 
