@@ -639,3 +639,41 @@ def test_gradient_method_survivor_generations(gpu):
         assert np.array_equal(a[3][k], b[3][k]), k
     it = a[3]["iters"]
     assert np.sum(a[3]["status"] == 1) >= n // 2 and len(np.unique(it[a[3]["status"] == 1])) >= 2   # they stopped, at different iterations
+
+
+def test_dense_weights_and_model_parameters(gpu, oracle):
+    """Dense (non-diagonal, symmetric) Q/R/QT take the general cost path of the sweeps, and non-default Dynamics attributes (heavier
+    aircraft, other drag/lift coefficients, dt = 2e-3) go through acoc_set_model: 7 Newton iterations with the exact Hessian from
+    iteration 3 on (exact_after = 2), a 5-instance batch, against the oracle with the same weights and parameters."""
+    d = golden("newton_step_f32.npz")
+    rng = np.random.default_rng(11)
+    n, TT = 5, 160
+    sl = slice(0, TT)
+    xr = np.repeat(d["xx_ref"][None, :, sl], n, 0) * (1.0 + 0.02 * rng.normal(size=(n, 6, 1)))
+    ur = np.repeat(d["uu_ref"][None, :, sl], n, 0)
+    E = rng.normal(size=(6, 6)) * 1e-4
+    Q = d["Q"] + E @ E.T
+    QT = d["QT"] + 3 * (E @ E.T)
+    R = d["R"] + 1e-7 * np.array([[1.0, 0.3], [0.3, 2.0]])
+    params = np.array([0.19, 2.1, 3.4, 14.0, 9.81, 0.61, 1.2, 0.3, 2e-3])   # cd0, cda, cla, m, g, S, rho, J, dt
+    xi = np.zeros((n, 6, TT))
+    ui = np.zeros((n, 2, TT))
+    for i in range(n):
+        xi[i], ui[i] = oracle.initial_trajectory(xr[i], params=params)
+    o = oracle.newton_batch(xr, ur, xi, ui, Q, R, QT, params=params, exact_after=2, max_iters=8)
+    assert o["iters"].min() >= 4 and len(np.unique(o["stepsize"][:, :4])) >= 4   # exact-Hessian iterations that backtrack
+    for armijo in ("lazy", "speculative"):
+        with gpu.BatchedNewton(n, TT=TT, armijo=armijo, params=params, exact_after=2, max_iters=8) as bn:
+            bn.set_weights(Q, R, QT)
+            bn.set_refs(xr, ur)
+            bn.set_init(xi, ui)
+            bn.solve()
+            xs, us = bn.result()
+            h, st = bn.history(), bn.stats()
+        assert np.array_equal(st["iters"], o["iters"])
+        for i in range(n):
+            k = int(o["iters"][i])
+            assert np.array_equal(h["stepsize"][i, :k], o["stepsize"][i, :k]) and np.array_equal(h["n_armijo"][i, :k], o["n_armijo"][i, :k])
+            assert np.max(np.abs(h["JJ"][i, :k] - o["JJ"][i, :k]) / np.abs(o["JJ"][i, :k])) < 1e-9
+            assert np.max(np.abs(h["descent"][i, :k] - o["descent"][i, :k]) / np.abs(o["descent"][i, :k])) < 1e-9
+        assert relerr(o["xx_star"], xs) < 1e-9 and relerr(o["uu_star"], us) < 1e-9
