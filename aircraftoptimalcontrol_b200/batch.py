@@ -290,6 +290,8 @@ class PipelinedNewton:
             try:
                 with turn:
                     turn.wait_for(lambda: state["next_upload"] == k or errors)
+                if errors:  # another sub-batch failed: do not upload / solve this one
+                    return
                 try:
                     bn.set_refs(xx_ref[lo:hi], uu_ref[lo:hi])
                     if xx_init is not None:

@@ -22,6 +22,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -698,8 +699,9 @@ struct acoc_ctx {
     int *need = nullptr, *need2 = nullptr, *counters = nullptr, *slot_tmp = nullptr;
     int *act_groups = nullptr, *need_groups = nullptr;  // work lists (see WorkList); counts live in counters[1], counters[2]
     long long* iters_sum = nullptr;
-    std::vector<void*> allocs;
+    std::vector<std::pair<void*, size_t>> allocs;
     unsigned long long bytes = 0;
+    int hist_iters = 0, hist_cand = 0;  // sizes the history / candidate-cost buffers were allocated for
     // timing
     bool profiling = false;
     cudaEvent_t ev[8];
@@ -742,10 +744,24 @@ static int dalloc_bytes(acoc_ctx* c, void** p, size_t bytes)
     }
     e = cudaMemsetAsync(q, 0, bytes, c->stream);
     if (e != cudaSuccess) return fail(ACOC_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
-    c->allocs.push_back(q);
+    c->allocs.push_back({q, bytes});
     c->bytes += bytes;
     *p = q;
     return 0;
+}
+// release one buffer of the context before the context itself goes away (option changes resize the histories)
+template <typename T>
+static void dfree(acoc_ctx* c, T** p)
+{
+    if (!*p) return;
+    for (size_t k = 0; k < c->allocs.size(); ++k)
+        if (c->allocs[k].first == (void*)*p) {
+            c->bytes -= c->allocs[k].second;
+            c->allocs.erase(c->allocs.begin() + k);
+            break;
+        }
+    cudaFree(*p);
+    *p = nullptr;
 }
 template <typename T>
 static int dalloc(acoc_ctx* c, T** p, size_t n)
@@ -784,21 +800,40 @@ static void default_opts(NewtonOpts* o)
     o->stepsize_0 = 1.0; o->cc = 0.5; o->beta = 0.7; o->term_cond = -1e-6; o->method = 0;
 }
 
-static int alloc_history(acoc_ctx* c)
+// the Armijo step table cand_steps[c] = stepsize_0 * beta^c (length armijo_maxiters + 1), on the context's stream
+static int write_cand_steps(acoc_ctx* c)
 {
-    const size_t Np = c->Np;
-    TRY(dalloc(c, &c->S.hist_J, (size_t)c->O.max_iters * Np));
-    TRY(dalloc(c, &c->S.hist_descent, (size_t)c->O.max_iters * Np));
-    TRY(dalloc(c, &c->S.hist_step, (size_t)c->O.max_iters * Np));
-    TRY(dalloc(c, &c->S.hist_ncand, (size_t)c->O.max_iters * Np));
-    TRY(dalloc(c, &c->S.Jcand, (size_t)(c->O.armijo_maxiters + 1) * Np));
-    TRY(dalloc(c, &c->cand_steps, (size_t)c->O.armijo_maxiters + 2));
     std::vector<double> cs(c->O.armijo_maxiters + 1);
     double s = c->O.stepsize_0;
     for (int k = 0; k <= c->O.armijo_maxiters; ++k) { cs[k] = s; s = c->O.beta * s; }  // stepsize = beta*stepsize, optcon.py:270
     CK(cudaMemcpyAsync(c->cand_steps, cs.data(), cs.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return 0;
+}
+
+// histories [max_iters][Np] and candidate costs [armijo_maxiters + 1][Np]: (re)allocated when the option that sizes them changes
+static int alloc_history(acoc_ctx* c)
+{
+    const size_t Np = c->Np;
+    if (c->hist_iters != c->O.max_iters) {
+        CK(cudaStreamSynchronize(c->stream));
+        dfree(c, &c->S.hist_J); dfree(c, &c->S.hist_descent); dfree(c, &c->S.hist_step); dfree(c, &c->S.hist_ncand);
+        c->hist_iters = 0;
+        TRY(dalloc(c, &c->S.hist_J, (size_t)c->O.max_iters * Np));
+        TRY(dalloc(c, &c->S.hist_descent, (size_t)c->O.max_iters * Np));
+        TRY(dalloc(c, &c->S.hist_step, (size_t)c->O.max_iters * Np));
+        TRY(dalloc(c, &c->S.hist_ncand, (size_t)c->O.max_iters * Np));
+        c->hist_iters = c->O.max_iters;
+    }
+    if (c->hist_cand != c->O.armijo_maxiters) {
+        CK(cudaStreamSynchronize(c->stream));
+        dfree(c, &c->S.Jcand); dfree(c, &c->cand_steps);
+        c->hist_cand = 0;
+        TRY(dalloc(c, &c->S.Jcand, (size_t)(c->O.armijo_maxiters + 1) * Np));
+        TRY(dalloc(c, &c->cand_steps, (size_t)c->O.armijo_maxiters + 2));
+        c->hist_cand = c->O.armijo_maxiters;
+    }
+    return write_cand_steps(c);
 }
 
 static int reset_state(acoc_ctx* c)
@@ -928,16 +963,51 @@ int acoc_device_info(int device, char* name, int len, int* sm_count, unsigned lo
 // ======================================================================================================
 // pointwise entry points
 // ======================================================================================================
+// Device scratch of the pointwise entry points (acoc_step_batch, acoc_cost_batch, acoc_ltv_lqr, acoc_lqr_tracking): one cached
+// arena per device, carved up by bump allocation, so that a call costs no cudaMalloc / cudaFree once the arena has grown to the
+// call's size (a Dynamics.step of one sample was ~10 allocations + frees before).  Calls that do not fit take individual
+// allocations for the overflow and the arena is regrown for the next call.  The arena lock makes these entry points serialise
+// per process; the batched contexts do not use it.
+struct Arena { char* base = nullptr; size_t cap = 0; };
+static std::mutex g_arena_mu;
+static Arena g_arena[64];
+
 struct TmpBuf {
-    std::vector<void*> p;
-    ~TmpBuf() { for (void* q : p) cudaFree(q); }
+    std::unique_lock<std::mutex> lk;
+    Arena* a;
+    size_t used = 0, want = 0;
+    std::vector<void*> extra;
+    explicit TmpBuf(int device) : lk(g_arena_mu), a(&g_arena[device & 63]) {}
+    ~TmpBuf()
+    {
+        for (void* q : extra) cudaFree(q);
+        if (want > a->cap) {  // regrow for the next call of this size (the work of this call has been synchronised by DOWN / sync)
+            cudaDeviceSynchronize();
+            if (a->base) cudaFree(a->base);
+            a->base = nullptr; a->cap = 0;
+            void* q = nullptr;
+            const size_t cap = want + want / 4 + 4096;
+            if (cudaMalloc(&q, cap) == cudaSuccess) { a->base = (char*)q; a->cap = cap; }
+            else cudaGetLastError();
+        }
+    }
+    int take(void** d, size_t bytes)
+    {
+        const size_t b = (std::max<size_t>(bytes, 8) + 255) & ~(size_t)255;
+        want += b;
+        if (used + b <= a->cap) { *d = a->base + used; used += b; return 0; }
+        void* q;
+        CK(cudaMalloc(&q, b));
+        extra.push_back(q);
+        *d = q;
+        return 0;
+    }
     template <typename T> int up(T** d, const T* h, size_t n)
     {
         *d = nullptr;
         if (!h) return 0;
         void* q;
-        CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
-        p.push_back(q);
+        TRY(take(&q, n * sizeof(T)));
         CK(cudaMemcpy(q, h, n * sizeof(T), cudaMemcpyHostToDevice));
         *d = (T*)q;
         return 0;
@@ -947,8 +1017,7 @@ struct TmpBuf {
         *d = nullptr;
         if (!h) return 0;
         void* q;
-        CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
-        p.push_back(q);
+        TRY(take(&q, n * sizeof(T)));
         CK(cudaMemset(q, 0, n * sizeof(T)));
         *d = (T*)q;
         return 0;
@@ -962,7 +1031,7 @@ int acoc_step_batch(int device, int n, const double* params, int state_f64, cons
     REQUIRE(n > 0 && params && x && u, "acoc_step_batch: n > 0 and params, x, u must be given");
     TRY(use_device(device));
     const Model M = make_model(params);
-    TmpBuf t;
+    TmpBuf t(device);
     double *dx, *du, *dl, *oxp, *oA, *oB, *oxx, *oux;
     const size_t nxx = lmbd ? 36 : 216, nux = lmbd ? 12 : 72;
     TRY(t.up(&dx, x, (size_t)n * 6)); TRY(t.up(&du, u, (size_t)n * 2)); TRY(t.up(&dl, lmbd, (size_t)n * 6));
@@ -985,7 +1054,7 @@ int acoc_cost_batch(int device, int n, const double* Q, const double* R, const d
     TRY(use_device(device));
     Weights W;
     fill_weights(&W, Q, R, QT);
-    TmpBuf t;
+    TmpBuf t(device);
     double *dx, *du, *dxr, *dur, *oll, *olx, *olu, *ollT, *olTx;
     TRY(t.up(&dx, x, (size_t)n * 6)); TRY(t.up(&du, u, (size_t)n * 2)); TRY(t.up(&dxr, xr, (size_t)n * 6)); TRY(t.up(&dur, ur, (size_t)n * 2));
     TRY(t.out(&oll, ll, n)); TRY(t.out(&olx, lx, (size_t)n * 6)); TRY(t.out(&olu, lu, (size_t)n * 2));
@@ -1018,7 +1087,7 @@ int acoc_ltv_lqr(int device, int nb, int TT, const double* A, const double* B, c
     TRY(use_device(device));
     const int n = aug ? 7 : 6;
     const size_t T = (size_t)nb * TT;
-    TmpBuf t;
+    TmpBuf t(device);
     double *dA, *dB, *dQ, *dR, *dS, *dQf, *dx0, *dq, *dr, *dqf, *oK, *oP, *ox, *ou;
     int* onr;
     TRY(t.up(&dA, A, T * 36)); TRY(t.up(&dB, B, T * 12)); TRY(t.up(&dQ, Q, T * 36)); TRY(t.up(&dR, R, T * 4)); TRY(t.up(&dS, S, T * 12));
@@ -1117,7 +1186,7 @@ int acoc_ctx_destroy(acoc_ctx* c)
     if (c->child) acoc_ctx_destroy(c->child);
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (void* p : c->allocs) cudaFree(p);
+    for (auto& p : c->allocs) cudaFree(p.first);
     if (c->ev_ok) for (int e = 0; e < 8; ++e) cudaEventDestroy(c->ev[e]);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (int r = 1; r < MAX_RANGES; ++r) {
@@ -1163,7 +1232,7 @@ int acoc_set_options(acoc_ctx* c, const acoc_newton_options* o)
     TRY(use_device(c->device));
     c->O.max_iters = o->max_iters; c->O.armijo_maxiters = o->armijo_maxiters; c->O.exact_after = o->exact_after;
     c->O.stepsize_0 = o->stepsize_0; c->O.cc = o->cc; c->O.beta = o->beta; c->O.term_cond = o->term_cond; c->O.method = o->method;
-    TRY(alloc_history(c));  // (old history buffers are released with the context)
+    TRY(alloc_history(c));  // resizes the history buffers if needed, rewrites the Armijo step table
     return reset_state(c);
 }
 
@@ -1556,10 +1625,12 @@ static bool fused_search_t(acoc_ctx* c)
         return false;
     const size_t bx = rows * c->TT * NS * c->Np * sizeof(XT), bu = rows * c->TT * NI * c->Np * sizeof(F);
     if (c->cand_bytes_x < bx) {
+        dfree(c, &c->candX);
         if (dalloc_bytes(c, &c->candX, bx)) { c->cand_failed = true; return false; }
         c->cand_bytes_x = bx;
     }
     if (c->cand_bytes_u < bu) {
+        dfree(c, &c->candU);
         if (dalloc_bytes(c, &c->candU, bu)) { c->cand_failed = true; return false; }
         c->cand_bytes_u = bu;
     }
@@ -1830,6 +1901,7 @@ static int spawn_child(acoc_ctx* par, int n_active, acoc_ctx** out)
         TRY(acoc_set_options(ch, &o));
     }
     ch->O = par->O;
+    TRY(write_cand_steps(ch));  // stepsize_0 / beta may differ from what the child last ran with (its table is per context)
     ch->N = n_active;
     ch->P.M = par->P.M; ch->P.W = par->P.W; ch->P.q32 = par->P.q32; ch->P.N = n_active;
     ch->have_model = ch->have_weights = ch->have_refs = ch->have_init = true;
@@ -2217,21 +2289,23 @@ int acoc_lqr_tracking(int device, int n, int TT, const double* params, int state
     TRY(upload_soa(c, xx_opt, c->xref, 1, 6, 1));
     TRY(upload_soa(c, uu_opt, c->uref, 1, 2, 1));
     // linearise along the nominal at all TT points (lqr_tracking.py:268-273): one thread per time step
-    TmpBuf t;
+    TmpBuf t(device);
     double *dA, *dB, *dQ, *dR, *dS, *dQf, *dx0, *dK, *dxo, *duo, *dstart;
     TRY(t.out(&dA, xx_reg, (size_t)TT * 36)); TRY(t.out(&dB, xx_reg, (size_t)TT * 12)); TRY(t.out(&dS, xx_reg, (size_t)TT * 12));
     TRY(t.out(&dK, xx_reg, (size_t)TT * 12)); TRY(t.out(&dxo, xx_reg, (size_t)TT * 6)); TRY(t.out(&duo, xx_reg, (size_t)TT * 2));
     std::vector<double> Qrep((size_t)TT * 36), Rrep((size_t)TT * 4);
     for (int k = 0; k < TT; ++k) { memcpy(&Qrep[(size_t)k * 36], Q, 36 * sizeof(double)); memcpy(&Rrep[(size_t)k * 4], R, 4 * sizeof(double)); }  // .repeat(TT), optcon.py:603-606
     TRY(t.up(&dQ, Qrep.data(), Qrep.size())); TRY(t.up(&dR, Rrep.data(), Rrep.size())); TRY(t.up(&dQf, QT, 36)); TRY(t.up(&dx0, delta, 6));
-    const double *d_xopt = (const double*)c->xref, *d_uopt = (const double*)c->uref;
-    k_step_batch<<<(TT + 127) / 128, 128, 0, c->stream>>>(M, c->P.q32, TT, d_xopt, d_uopt, nullptr, nullptr, dA, dB, nullptr, nullptr);
-    CK(cudaGetLastError());
-    TRY(lq_dense_dev(1, TT, false, dA, dB, dQ, dR, dS, dQf, dx0, nullptr, nullptr, nullptr, dK, nullptr, dxo, duo, nullptr, c->stream));
     // perturbed initial states: x_start[c][i] = xx_opt[c][0] + delta[i][c]   (lqr_tracking.py:265)
     std::vector<double> xs((size_t)6 * c->Np, 0.0);
     for (int i = 0; i < n; ++i) for (int k = 0; k < 6; ++k) xs[(size_t)k * c->Np + i] = xx_opt[(size_t)k * TT] + delta[(size_t)i * 6 + k];
     TRY(t.up(&dstart, xs.data(), xs.size()));
+    // the uploads and memsets above ran on the legacy default stream; the context's stream is non-blocking, so order them explicitly
+    CK(cudaDeviceSynchronize());
+    const double *d_xopt = (const double*)c->xref, *d_uopt = (const double*)c->uref;
+    k_step_batch<<<(TT + 127) / 128, 128, 0, c->stream>>>(M, c->P.q32, TT, d_xopt, d_uopt, nullptr, nullptr, dA, dB, nullptr, nullptr);
+    CK(cudaGetLastError());
+    TRY(lq_dense_dev(1, TT, false, dA, dB, dQ, dR, dS, dQf, dx0, nullptr, nullptr, nullptr, dK, nullptr, dxo, duo, nullptr, c->stream));
     const Problem P = prob<double>(c);
     if (c->P.q32) k_track<true><<<(n + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, 0, c->stream>>>(P, dK, d_xopt, d_uopt, dstart, (double*)c->X[0], (double*)c->U[0]);
     else k_track<false><<<(n + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, 0, c->stream>>>(P, dK, d_xopt, d_uopt, dstart, (double*)c->X[0], (double*)c->U[0]);
@@ -2239,6 +2313,7 @@ int acoc_lqr_tracking(int device, int n, int TT, const double* params, int state
     TRY(download_soa(c, c->X[0], nullptr, nullptr, nullptr, xx_reg, n, 6, c->Np, 0));
     TRY(download_soa(c, c->U[0], nullptr, nullptr, nullptr, uu_reg, n, 2, c->Np, 0));
     if (K) CK(cudaMemcpy(K, dK, (size_t)TT * 12 * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

@@ -141,8 +141,8 @@ class GradientMethod:
             bn.set_deltau(deltau[None])
             bn.set_scalars(J=np.array([float(np.asarray(JP).squeeze())]), descent=np.array([float(np.asarray(descent).squeeze())]))
             s, costs = bn.armijo()
-            if self.visu_armijo:   # the data of the reference's figure (optcon.py:282-296): cost along deltau on linspace(0, stepsize_0, 10)
-                steps = np.linspace(0, self.stepsize_0, 10)
+            if self.visu_armijo:   # the data of the reference's figure (optcon.py:282-296): cost along deltau on linspace(0, stepsize_0, armijo_maxiters)
+                steps = np.linspace(0, self.stepsize_0, int(self.armijo_maxiters))
                 self.last_armijo_sweep = dict(steps=steps, costs=bn.armijo_sweep(steps)[0], JP=float(np.asarray(JP).squeeze()),
                                               descent=float(np.asarray(descent).squeeze()))
         self.last_armijo_costs = costs[0]

@@ -140,7 +140,12 @@ int acoc_ctx_destroy(acoc_ctx* ctx);
 int acoc_ctx_device_bytes(const acoc_ctx* ctx, unsigned long long* bytes);
 
 int acoc_set_model(acoc_ctx* ctx, const double* params);                                  /* Dynamics() attrs */
-int acoc_set_weights(acoc_ctx* ctx, const double* Q, const double* R, const double* QT);  /* Cost(QQt,RRt,QQT) */
+/* Cost(QQt,RRt,QQT), aircraft_simplified.py:20-23.  Q, R and QT must be SYMMETRIC here (ACOC_ERR_INVALID otherwise): the fused
+ * backward sweep carries the Riccati matrix as its upper triangle.  This is a documented deviation: the reference accepts any matrix
+ * (aircraft_simplified.py:61-68) -- a non-symmetric Q there makes the gradient Q dx inconsistent with the cost dx'Q dx, which no
+ * shipped configuration does.  The pointwise acoc_cost_batch and the literal acoc_ltv_lqr accept arbitrary matrices like the
+ * reference (tests: test_weight_symmetry_contract). */
+int acoc_set_weights(acoc_ctx* ctx, const double* Q, const double* R, const double* QT);
 int acoc_set_options(acoc_ctx* ctx, const acoc_newton_options* opt);                      /* NewtonMethod(...) */
 /* xx_ref (N,6,TT) / uu_ref (N,2,TT), or (6,TT) / (2,TT) when the context was created with ACOC_REFS_SHARED */
 int acoc_set_refs(acoc_ctx* ctx, const double* xx_ref, const double* uu_ref);

@@ -1,0 +1,227 @@
+"""Round-2 parity cases (through the C ABI, libacoc.so): BASELINE.json configs[4] as a batch, a sample of the real
+65,536-instance pipelined solve, the non-finite freeze, the weight-symmetry contract, armijo_maxiters > 10 and survivor
+generations with non-default Armijo parameters.  Same bar as tests/test_gpu_parity.py: identical iteration counts and
+Armijo steps, histories / trajectories within 1e-9 relative of the CPU oracle (itself pinned to the live reference)."""
+import numpy as np
+import pytest
+
+from tests.util import golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_against_oracle(o, h, st, xs, us, idx=None, tol=1e-9):
+    """o: oracle.newton_batch result of the sampled instances; h/st/xs/us: GPU history, stats, results; idx: their indices."""
+    idx = np.arange(len(o["iters"])) if idx is None else np.asarray(idx)
+    assert np.array_equal(st["iters"][idx], o["iters"]), (st["iters"][idx], o["iters"])
+    for j, i in enumerate(idx):
+        k = int(o["iters"][j])
+        assert np.array_equal(h["stepsize"][i, :k], o["stepsize"][j, :k]), (i, h["stepsize"][i, :k], o["stepsize"][j, :k])
+        assert np.array_equal(h["n_armijo"][i, :k], o["n_armijo"][j, :k]), i
+        assert np.max(np.abs(h["JJ"][i, :k] - o["JJ"][j, :k]) / np.abs(o["JJ"][j, :k])) < tol, i
+        assert np.max(np.abs(h["descent"][i, :k] - o["descent"][j, :k]) / np.abs(o["descent"][j, :k])) < tol, i
+    assert relerr(o["xx_star"], xs[idx]) < tol and relerr(o["uu_star"], us[idx]) < tol
+
+
+@pytest.mark.parametrize("armijo", ["lazy", "speculative"])
+def test_config5_batch_matches_oracle(gpu, oracle, armijo):
+    """BASELINE.json configs[4] (acrobatic_newton.py:133-196 with x0 + delta, bump height zf ~ U(2.0, 3.4), seed 7; optcon.py:398):
+    the first 64 instances of the 1,048,576-instance batch at TT = 1000, device-side initial guess from the perturbed x0, solved to
+    the reference's criterion -- iteration counts, every Armijo step / candidate count, histories and results vs the oracle."""
+    from aircraftoptimalcontrol_b200 import refgen
+    n, TT = 64, 1000
+    xr, ur, dx0, Q, R, QT = refgen.config5(1048576, seed=7, lo=0, hi=n, TT=TT)
+    with gpu.BatchedNewton(n, TT=TT, armijo=armijo) as bn:
+        bn.set_weights(Q, R, QT)
+        bn.set_refs(xr, ur)
+        bn.init_guess(dx0=dx0)
+        xi, ui = bn.iterate_at(0)
+        total = bn.solve()
+        xs, us = bn.result()
+        h, st = bn.history(), bn.stats()
+    assert np.array_equal(xi[:, :, 0], xr[:, :, 0] + dx0)  # x0 = xx_init[:,0] is the perturbed state, exactly
+    o = oracle.newton_batch(xr, ur, xi, ui, Q, R, QT)
+    assert total == int(o["iters"].sum()) and np.all(st["status"] == 1)
+    assert len(np.unique(o["iters"])) > 2  # the perturbations / bump heights give different iteration counts
+    _check_against_oracle(o, h, st, xs, us)
+
+
+def test_pipelined_65536_sample_matches_oracle(gpu, oracle):
+    """The benchmarked configuration itself: BASELINE.json configs[3], 65,536 instances at TT = 1000 through PipelinedNewton (4
+    sub-batches, tile ranges, survivor generations, lazy search, fused sweeps) -- 64 instances sampled out of that solve are
+    compared with the oracle run on the same inputs: iteration counts, every Armijo step, histories, results."""
+    from aircraftoptimalcontrol_b200 import refgen
+    n, TT = 65536, 1000
+    xr, ur, Q, R, QT = refgen.config4(n, 2024, TT=TT)
+    with gpu.PipelinedNewton(n, n_chunks=4, TT=TT, armijo="lazy") as pn:
+        pn.set_weights(Q, R, QT)
+        xs, us, st = pn.solve(xr, ur)
+        idx = np.concatenate([np.arange(0, n, 1040), [n - 1]])[:64]   # every sub-batch, different tiles and lanes
+        rows = {k: [] for k in ("stepsize", "n_armijo", "JJ", "descent")}
+        for k, p in enumerate(pn.parts):
+            lo, hi = pn.bounds[k], pn.bounds[k + 1]
+            sel = idx[(idx >= lo) & (idx < hi)] - lo
+            hk = p.history()
+            for key in rows:
+                rows[key].append(hk[key][sel])
+    h = {key: np.concatenate(v) for key, v in rows.items()}
+    assert np.all(st["status"] == 1) and st["iters"].min() >= 10
+    xi = np.zeros((len(idx), 6, TT))
+    ui = np.zeros((len(idx), 2, TT))
+    for j, i in enumerate(idx):  # the device initial guess is bit-identical to this one (test_rollouts_bit_exact_at_scale)
+        xi[j], ui[j] = oracle.initial_trajectory(xr[i])
+    o = oracle.newton_batch(xr[idx], ur[idx], xi, ui, Q, R, QT)
+    sub = dict(iters=st["iters"][idx])
+    _check_against_oracle(o, h, sub, xs[idx], us[idx])
+
+
+def test_nonfinite_instance_freezes_alone(gpu):
+    """aircraft_simplified.py:310,321,363 divide by V: an instance with V = 0 in x0 (and one with a NaN input) must be frozen with
+    ACOC_INST_NONFINITE after its first loop body while every other instance of its tile and batch is bit-identical to the same batch
+    without the poisoned inputs."""
+    n, TT = 96, 300
+    from aircraftoptimalcontrol_b200 import refgen
+    rng = np.random.default_rng(12)
+    xr, ur = refgen.step_problem(rng.uniform(14, 18, n), rng.uniform(1.5, 3.5, n), tf=0.3, TT=TT)
+    Q, R, QT = refgen.weights("step")
+    with gpu.BatchedNewton(n, TT=TT) as bn:
+        bn.set_weights(Q, R, QT)
+        bn.set_refs(xr, ur)
+        bn.init_guess()
+        xi, ui = bn.iterate_at(0)
+    bad = [5, 40]
+    xb, ub = xi.copy(), ui.copy()
+    xb[5, 2, 0] = 0.0          # V = 0 at t = 0: 1/V in the linearisation and in every rollout
+    ub[40, 0, 150] = np.nan    # NaN thrust in the middle of the horizon
+    out = []
+    for armijo in ("lazy", "speculative"):
+        for x_, u_ in ((xi, ui), (xb, ub)):
+            with gpu.BatchedNewton(n, TT=TT, armijo=armijo) as bn:
+                bn.set_weights(Q, R, QT)
+                bn.set_refs(xr, ur)
+                bn.set_init(x_, u_)
+                bn.solve()
+                out.append((bn.result(), bn.history(), bn.stats()))
+    good = np.setdiff1d(np.arange(n), bad)
+    for a, b in ((out[0], out[1]), (out[2], out[3]), (out[0], out[2])):
+        (xa, ua), ha, sa = a
+        (xb_, ub_), hb, sb = b
+        assert np.array_equal(xa[good], xb_[good]) and np.array_equal(ua[good], ub_[good])
+        for k in ("JJ", "descent", "stepsize", "n_armijo"):
+            assert np.array_equal(ha[k][good], hb[k][good]), k
+        for k in ("iters", "status", "J", "descent", "n_reg"):
+            assert np.array_equal(sa[k][good], sb[k][good]), k
+    for (_, _), _, s in (out[1], out[3]):
+        assert list(s["status"][bad]) == [3, 3] and list(s["iters"][bad]) == [1, 1]
+        assert np.all(s["status"][good] == 1)
+    assert np.all(out[0][2]["status"] == 1)
+
+
+def test_weight_symmetry_contract(gpu):
+    """Documented deviation (include/acoc.h, acoc_set_weights): the batched Newton context rejects non-symmetric Q / R / QT, the
+    pointwise Cost entry points accept any matrix like aircraft_simplified.py:61-68."""
+    from aircraftoptimalcontrol_b200 import _lib
+    from aircraftoptimalcontrol_b200.aircraft_simplified import Cost
+    rng = np.random.default_rng(8)
+    Qn, Rn, QTn = rng.normal(size=(6, 6)), rng.normal(size=(2, 2)), rng.normal(size=(6, 6))
+    Qs, Rs, QTs = Qn + Qn.T, Rn + Rn.T, QTn + QTn.T
+    with gpu.BatchedNewton(4, TT=20) as bn:
+        for args in ((Qn, Rs, QTs), (Qs, Rn, QTs), (Qs, Rs, QTn)):
+            with pytest.raises(_lib.AcocError, match="symmetric"):
+                bn.set_weights(*args)
+        bn.set_weights(Qs, Rs, QTs)  # symmetric dense weights are fine
+    x, u, xr, ur = rng.normal(size=(50, 6)), rng.normal(size=(50, 2)), rng.normal(size=(50, 6)), rng.normal(size=(50, 2))
+    c = Cost(Qn, Rn, QTn)
+    ll, lx, lu = c.stagecost_batch(x, u, xr, ur)
+    llT, lTx = c.termcost_batch(x, xr)
+    dx, du = x - xr, u - ur
+    ref_ll = 0.5 * np.einsum("ni,ij,nj->n", dx, Qn, dx) + 0.5 * np.einsum("ni,ij,nj->n", du, Rn, du)
+    assert np.max(np.abs(ll - ref_ll)) < 1e-12 * np.max(np.abs(ref_ll))
+    assert relerr(dx @ Qn.T, lx) < 1e-13 and relerr(du @ Rn.T, lu) < 1e-13           # lx = Q dx, lu = R du (:63-64)
+    assert np.max(np.abs(llT - 0.5 * np.einsum("ni,ij,nj->n", dx, QTn, dx))) < 1e-12 * np.max(np.abs(llT))
+    assert relerr(dx @ QTn.T, lTx) < 1e-13                                           # lTx = QT dx (:94)
+
+
+def test_armijo_maxiters_20_single_trajectory(gpu, oracle):
+    """NewtonMethod's constructor default armijo_maxiters = 20 (optcon.py:335) on config 1: more candidates than one candidate CTA
+    holds (the kernel strides inside the thread) and no fused small-batch search -- vs the oracle, lazy and speculative."""
+    d = golden("newton_step_f32.npz")
+    TT = d["xx_ref"].shape[1]
+    o = oracle.newton(d["xx_ref"], d["uu_ref"], d["xx_init"], d["uu_init"], d["Q"], d["R"], d["QT"], armijo_maxiters=20)
+    k = int(o["iters"])
+    assert o["n_armijo"].max() > 10  # the longer search is actually used
+    for armijo in ("lazy", "speculative"):
+        with gpu.BatchedNewton(1, TT=TT, refs_shared=True, armijo=armijo, armijo_maxiters=20) as bn:
+            bn.set_weights(d["Q"], d["R"], d["QT"])
+            bn.set_refs(d["xx_ref"], d["uu_ref"])
+            bn.set_init(d["xx_init"][None], d["uu_init"][None])
+            total = bn.solve()
+            xs, us = bn.result()
+            h = bn.history()
+        assert total == k
+        assert np.array_equal(h["stepsize"][0, :k], o["stepsize"]) and np.array_equal(h["n_armijo"][0, :k], o["n_armijo"])
+        assert np.max(np.abs(h["JJ"][0, :k] - o["JJ"]) / np.abs(o["JJ"])) < 1e-9
+        assert relerr(o["xx_star"], xs[0]) < 1e-9 and relerr(o["uu_star"], us[0]) < 1e-9
+
+
+def _short_batch(n, TT, seed):
+    from aircraftoptimalcontrol_b200 import refgen
+    rng = np.random.default_rng(seed)
+    xr, ur = refgen.step_problem(rng.uniform(14, 18, n), rng.uniform(1.5, 3.5, n), tf=TT * 1e-3, TT=TT)
+    return (xr, ur) + refgen.weights("step")
+
+
+def test_armijo_maxiters_20_batch(gpu, oracle):
+    """armijo_maxiters = 20 on a batch of more than 4096 instances (lazy search over the need lists, candidates 1..19 in one launch,
+    survivor generations): a 64-instance sample vs the oracle."""
+    n, TT = 4608, 200
+    xr, ur, Q, R, QT = _short_batch(n, TT, 21)
+    with gpu.BatchedNewton(n, TT=TT, armijo="lazy", armijo_maxiters=20) as bn:
+        bn.set_weights(Q, R, QT)
+        bn.set_refs(xr, ur)
+        bn.init_guess()
+        xi, ui = bn.iterate_at(0)
+        bn.solve()
+        xs, us = bn.result()
+        h, st = bn.history(), bn.stats()
+    idx = np.arange(0, n, 72)
+    o = oracle.newton_batch(xr[idx], ur[idx], xi[idx], ui[idx], Q, R, QT, armijo_maxiters=20)
+    _check_against_oracle(o, h, st, xs, us, idx)
+
+
+@pytest.mark.parametrize("kw", [dict(stepsize_0=0.5), dict(beta=0.5)])
+def test_generations_with_nondefault_armijo_table(gpu, oracle, kw):
+    """Survivor generations must search with the PARENT's step table: only stepsize_0 or beta changed (max_iters / armijo_maxiters at
+    their defaults, so the child context is not re-created) -- bit-identical to iterating in place, sample vs the oracle."""
+    n, TT = 8192, 200
+    xr, ur, Q, R, QT = _short_batch(n, TT, 31)
+    out = []
+    for gen in (True, False):
+        with gpu.BatchedNewton(n, TT=TT, armijo="lazy", generations=gen, **kw) as bn:
+            bn.set_weights(Q, R, QT)
+            bn.set_refs(xr, ur)
+            bn.init_guess()
+            xi, ui = bn.iterate_at(0)
+            bn.solve()
+            out.append((bn.result(), bn.history(), bn.stats()))
+    ((x0, u0), h0, s0), ((x1, u1), h1, s1) = out
+    assert len(np.unique(s0["iters"])) > 3
+    assert np.array_equal(x0, x1) and np.array_equal(u0, u1)
+    for k in ("JJ", "descent", "stepsize", "n_armijo"):
+        assert np.array_equal(h0[k], h1[k]), k
+    for k in ("iters", "status", "J"):
+        assert np.array_equal(s0[k], s1[k]), k
+    idx = np.arange(0, n, 128)
+    o = oracle.newton_batch(xr[idx], ur[idx], xi[idx], ui[idx], Q, R, QT, **kw)
+    _check_against_oracle(o, h0, s0, x0, u0, idx)
+
+
+def test_options_can_be_changed_without_growing_the_context(gpu):
+    """acoc_set_options resizes / reuses the history buffers instead of stacking new ones."""
+    with gpu.BatchedNewton(256, TT=50) as bn:
+        b0 = bn.device_bytes
+        import ctypes as C
+        from aircraftoptimalcontrol_b200 import _lib as L
+        for _ in range(3):
+            L.check(L.lib().acoc_set_options(bn._h, C.addressof(bn.opts)))
+        assert bn.device_bytes == b0
