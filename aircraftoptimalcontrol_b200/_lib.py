@@ -51,6 +51,7 @@ def _sig(lib):
         "acoc_cost_batch": [i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "acoc_ltv_lqr": [i, i, i] + [vp] * 15,
         "acoc_lqr_tracking": [i, i, i, vp, i] + [vp] * 9,
+        "acoc_last_pointwise_timing": [vp],
         "acoc_ctx_create": [i, i, i, C.c_uint, vp],
         "acoc_ctx_destroy": [vp],
         "acoc_ctx_device_bytes": [vp, vp],
@@ -58,6 +59,9 @@ def _sig(lib):
         "acoc_set_weights": [vp, vp, vp, vp],
         "acoc_set_options": [vp, vp],
         "acoc_set_refs": [vp, vp, vp],
+        "acoc_set_refs_generated": [vp] * 8,
+        "acoc_get_refs": [vp, vp, vp],
+        "acoc_get_result_f32": [vp, vp, vp, vp],
         "acoc_set_init": [vp, vp, vp],
         "acoc_init_guess": [vp, d, d, vp],
         "acoc_newton_iterate": [vp, i, vp],

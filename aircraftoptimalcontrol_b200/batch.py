@@ -112,6 +112,40 @@ class BatchedNewton:
         xr, ur = L.f64(xx_ref, sx, "xx_ref"), L.f64(uu_ref, su, "uu_ref")
         L.check(L.lib().acoc_set_refs(self._h, L.ptr(xr), L.ptr(ur)))
 
+    def set_refs_generated(self, tt, zshape, vshape, zf, vx, xconst, uconst):
+        """acoc_set_refs_generated: build the per-instance references on the device from per-instance (zf, vx) and shared time bases."""
+        if self.refs_shared:
+            raise ValueError("generated references are per instance (refs_shared=False)")
+        tt, zs = L.f64(tt, (self.TT,), "tt"), L.f64(zshape, (self.TT,), "zshape")
+        vs = None if vshape is None else L.f64(vshape, (self.TT,), "vshape")
+        zf = L.f64(np.broadcast_to(np.asarray(zf, dtype=np.float64), (self.N,)), (self.N,), "zf")
+        vx = L.f64(np.broadcast_to(np.asarray(vx, dtype=np.float64), (self.N,)), (self.N,), "vx")
+        xc, uc = L.f64(xconst, (6,), "xconst"), L.f64(uconst, (2,), "uconst")
+        L.check(L.lib().acoc_set_refs_generated(self._h, L.ptr(tt), L.ptr(zs), L.ptr(vs), L.ptr(zf), L.ptr(vx), L.ptr(xc), L.ptr(uc)))
+
+    def set_refs_step(self, zf, xf, tf=1):
+        """The step-maneuver references of main_newton_method.py:96-142 for final heights zf (N,) and final positions xf (N,), built on
+        the device; bit-identical to set_refs(*refgen.step_problem(xf, zf, tf, TT))."""
+        from . import refgen
+        tt, s, ds = refgen.step_bases(tf, self.TT)
+        vx = (np.asarray(xf, dtype=np.float64) - 0) / tf
+        self.set_refs_generated(tt, s, ds, zf, vx, *refgen.STEP_CONST)
+
+    def set_refs_acrobatic(self, zf, xf=18, tf=1):
+        """The acrobatic references of acrobatic_newton.py:99-154 for bump heights zf (N,), built on the device; bit-identical to
+        set_refs(*refgen.acrobatic_problem(zf, xf, tf, TT))."""
+        from . import refgen
+        tt, bump = refgen.acrobatic_bases(tf, self.TT)
+        self.set_refs_generated(tt, bump, None, zf, (xf - 0) / tf, *refgen.ACRO_CONST)
+
+    def refs(self):
+        """(xx_ref, uu_ref) held by the context, in set_refs' layout."""
+        sx = (6, self.TT) if self.refs_shared else (self.N, 6, self.TT)
+        su = (2, self.TT) if self.refs_shared else (self.N, 2, self.TT)
+        xr, ur = np.empty(sx), np.empty(su)
+        L.check(L.lib().acoc_get_refs(self._h, L.ptr(xr), L.ptr(ur)))
+        return xr, ur
+
     def set_init(self, xx_init, uu_init):
         xi, ui = L.f64(xx_init, (self.N, 6, self.TT), "xx_init"), L.f64(uu_init, (self.N, 2, self.TT), "uu_init")
         L.check(L.lib().acoc_set_init(self._h, L.ptr(xi), L.ptr(ui)))
@@ -193,6 +227,20 @@ class BatchedNewton:
         L.check(L.lib().acoc_get_result(self._h, L.ptr(xs), L.ptr(us)))
         return xs, us
 
+    def result_f32(self, out=None):
+        """(xx_star float32 (N,6,TT), uu_star float64 (N,2,TT), x0 float64 (N,6)): the result with the states as the float32 values
+        they are under the reference's state quantisation (aircraft_simplified.py:300) -- lossless, 40 instead of 64 bytes per time
+        step over the bus.  xx_star[:, :, 0] is float32(x0); the exact x0 comes back separately.  Raises for float64-state contexts."""
+        if out is None:
+            xs, us = np.empty((self.N, 6, self.TT), dtype=np.float32), np.empty((self.N, 2, self.TT))
+        else:
+            xs, us = out
+            if xs.dtype != np.float32 or us.dtype != np.float64:
+                raise ValueError("result_f32 needs a float32 state array and a float64 input array")
+        x0 = np.empty((self.N, 6))
+        L.check(L.lib().acoc_get_result_f32(self._h, L.ptr(xs), L.ptr(us), L.ptr(x0)))
+        return xs, us, x0
+
     def iterate_at(self, which=0):
         xs, us = np.empty((self.N, 6, self.TT)), np.empty((self.N, 2, self.TT))
         L.check(L.lib().acoc_get_iterate(self._h, int(which), L.ptr(xs), L.ptr(us)))
@@ -265,16 +313,24 @@ class PipelinedNewton:
         for p in self.parts:
             p.set_weights(QQt, RRt, QQT)
 
-    def solve(self, xx_ref, uu_ref, xx_init=None, uu_init=None, dx0=None, out=None):
-        """xx_ref (N,6,TT), uu_ref (N,2,TT) per-instance references (pinned host memory makes the copies fast); initial
+    def solve(self, xx_ref=None, uu_ref=None, xx_init=None, uu_init=None, dx0=None, out=None, refs=None, x_dtype=np.float64):
+        """xx_ref (N,6,TT), uu_ref (N,2,TT) per-instance references (pinned host memory makes the copies fast), or
+        refs = ("step", zf (N,), xf (N,)[, tf]) / ("acrobatic", zf (N,)[, xf, tf]): the scripts' reference generators run on the device
+        (BatchedNewton.set_refs_step / set_refs_acrobatic; bit-identical arrays, 16 bytes per instance over the bus).  Initial
         guess = (xx_init, uu_init) if given, else the device P-law rollout (optionally started at xx_ref[:,0] + dx0).
+        x_dtype = np.float32 downloads the states as the float32 values they are (BatchedNewton.result_f32; column 0 then holds
+        float32(x0), the exact x0 is stats["x0"]).
         Returns (xx_star, uu_star, stats) with stats = dict(iters, status, J, descent, n_reg), each of length N."""
         import threading
 
         N, TT = self.N, self.TT
-        xs, us = out if out is not None else (np.empty((N, 6, TT)), np.empty((N, 2, TT)))
+        f32 = np.dtype(x_dtype) == np.float32
+        if (xx_ref is None) == (refs is None):
+            raise ValueError("give either xx_ref/uu_ref or refs=(kind, ...)")
+        xs, us = out if out is not None else (np.empty((N, 6, TT), dtype=x_dtype), np.empty((N, 2, TT)))
         stats = dict(iters=np.zeros(N, dtype=np.int32), status=np.zeros(N, dtype=np.int32), J=np.zeros(N), descent=np.zeros(N),
                      n_reg=np.zeros(N, dtype=np.int32))
+        x0_out = np.zeros((N, 6)) if f32 else None
         errors = []
         # The host<->device link is the shared resource of the two copy phases, so they are serialised across sub-batches
         # (uploads in sub-batch order, downloads as sub-batches finish): sub-batch 0 starts iterating as soon as ITS references
@@ -293,7 +349,14 @@ class PipelinedNewton:
                 if errors:  # another sub-batch failed: do not upload / solve this one
                     return
                 try:
-                    bn.set_refs(xx_ref[lo:hi], uu_ref[lo:hi])
+                    if refs is None:
+                        bn.set_refs(xx_ref[lo:hi], uu_ref[lo:hi])
+                    elif refs[0] == "step":
+                        bn.set_refs_step(np.asarray(refs[1])[lo:hi], np.asarray(refs[2])[lo:hi], *refs[3:])
+                    elif refs[0] == "acrobatic":
+                        bn.set_refs_acrobatic(np.asarray(refs[1])[lo:hi], *refs[2:])
+                    else:
+                        raise ValueError("refs[0] must be 'step' or 'acrobatic'")
                     if xx_init is not None:
                         bn.set_init(xx_init[lo:hi], uu_init[lo:hi])
                 finally:
@@ -304,7 +367,10 @@ class PipelinedNewton:
                     bn.init_guess(dx0=None if dx0 is None else dx0[lo:hi])
                 bn.solve()
                 with download:
-                    bn.result(out=(xs[lo:hi], us[lo:hi]))
+                    if f32:
+                        x0_out[lo:hi] = bn.result_f32(out=(xs[lo:hi], us[lo:hi]))[2]
+                    else:
+                        bn.result(out=(xs[lo:hi], us[lo:hi]))
                     st = bn.stats()
                 for key in stats:
                     stats[key][lo:hi] = st[key]
@@ -320,4 +386,6 @@ class PipelinedNewton:
             t.join()
         if errors:
             raise errors[0]
+        if f32:
+            stats["x0"] = x0_out
         return xs, us, stats

@@ -36,6 +36,7 @@ using namespace acoc;
 // error plumbing
 // ======================================================================================================
 static thread_local std::string g_err;
+static thread_local double g_pt_ms[3] = {0, 0, 0};  // device time of the kernels of the last acoc_lqr_tracking call (acoc_last_pointwise_timing)
 
 static int fail(int code, const char* fmt, ...)
 {
@@ -559,11 +560,12 @@ __global__ void k_to_soa(const double* __restrict__ src, D* __restrict__ dst, in
 
 // s0..s2: up to three source slots; slot[i] selects per instance (-1 -> zeros; NULL -> s0); dup_last: t = TT-1 reads TT-2
 // row0 (optional, [C][Np]): exact t = 0 column of float state slots (see acoc_kernels.cuh "Types")
-template <typename D>
+// O: element type of the host-side chunk (double: the reference's layout; float: the lossless float32 download of float state slots)
+template <typename D, typename O>
 __global__ void k_from_soa(const D* __restrict__ s0, const D* __restrict__ s1, const D* __restrict__ s2, const int* __restrict__ slot,
-                           const double* __restrict__ row0, double* __restrict__ dst, int n0, int nchunk, int C, int TT, int Np, int dup_last)
+                           const double* __restrict__ row0, O* __restrict__ dst, int n0, int nchunk, int C, int TT, int Np, int dup_last)
 {
-    __shared__ double tile[32][33];
+    __shared__ O tile[32][33];
     const int c = blockIdx.z, tb = blockIdx.x * 32, nb = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         int t = tb + r;
@@ -572,13 +574,40 @@ __global__ void k_from_soa(const D* __restrict__ s0, const D* __restrict__ s1, c
             if (dup_last && t == TT - 1 && TT > 1) t = TT - 2;
             const int sl = slot ? slot[n0 + n] : 0;
             const D* s = sl == 0 ? s0 : (sl == 1 ? s1 : s2);
-            tile[r][threadIdx.x] = sl < 0 ? 0.0 : ((row0 && t == 0) ? row0[(size_t)c * Np + n0 + n] : (double)s[Np == 1 ? (size_t)t * C + c : at(t, C, c, Np, n0 + n)]);
+            tile[r][threadIdx.x] = sl < 0 ? O(0) : ((row0 && t == 0) ? (O)row0[(size_t)c * Np + n0 + n] : (O)s[Np == 1 ? (size_t)t * C + c : at(t, C, c, Np, n0 + n)]);
         }
     }
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int n = nb + r, t = tb + threadIdx.x;
         if (n < nchunk && t < TT) dst[((size_t)n * C + c) * TT + t] = tile[threadIdx.x][r];
+    }
+}
+
+// ---- reference generators of the scripts, on the device ---------------------------------------------------
+// xref / uref of instance i from per-instance parameters and shared time bases, in the operation order of the scripts' numpy code
+// (main_newton_method.py:96-142, acrobatic_newton.py:99-154; restated in refgen.py) so that the result is bit-identical to it:
+//   X_t = x0 + vx_i * tt_t            (x0 = 0)                      Z_t = p0 + zshape_t * (zf_i - p0)   (p0 = 0)
+//   V_t = ((vshape_t * zf_i)**2 + vx_i**2)**0.5  (numpy: square, square, add, sqrt), or the constant xc[2] when vshape == NULL
+//   theta, q, gamma = xc[3..5];  uref = uc[0..1]
+struct RefConst { double xc[6], uc[2]; };
+template <typename F>
+__global__ void __launch_bounds__(128) k_gen_refs(int N, int Np, int TT, const double* __restrict__ tt, const double* __restrict__ zshape,
+                                                  const double* __restrict__ vshape, const double* __restrict__ zf, const double* __restrict__ vx,
+                                                  RefConst K, F* __restrict__ xref, F* __restrict__ uref)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double z = zf[i], v = vx[i], v2 = v * v;
+    for (int t = blockIdx.y; t < TT; t += gridDim.y) {
+        const double X = 0.0 + v * tt[t];
+        const double Z = 0.0 + zshape[t] * (z - 0.0);
+        double V = K.xc[2];
+        if (vshape) { const double zd = vshape[t] * (z - 0.0); V = sqrt(zd * zd + v2); }
+        F* xo = xref + at(t, NS, 0, Np, i);
+        xo[0] = (F)X; xo[TILE] = (F)Z; xo[2 * TILE] = (F)V; xo[3 * TILE] = (F)K.xc[3]; xo[4 * TILE] = (F)K.xc[4]; xo[5 * TILE] = (F)K.xc[5];
+        F* uo = uref + at(t, NI, 0, Np, i);
+        uo[0] = (F)K.uc[0]; uo[TILE] = (F)K.uc[1];
     }
 }
 
@@ -883,19 +912,19 @@ static int upload_soa(acoc_ctx* c, const double* host, void* dst, int n, int C, 
                    : upload_soa_t<double, double>(c, host, dst, n, C, Np, nullptr, nullptr);
 }
 
-template <typename D>
-static int download_soa_t(acoc_ctx* c, const void* s0, const void* s1, const void* s2, const int* slot, const double* row0, double* host, int n,
+template <typename D, typename O = double>
+static int download_soa_t(acoc_ctx* c, const void* s0, const void* s1, const void* s2, const int* slot, const double* row0, O* host, int n,
                           int C, int Np, int dup_last)
 {
     const int TT = c->TT;
     const size_t per = (size_t)C * TT;
-    int chunk = (int)std::min<size_t>((size_t)n, std::max<size_t>(1, c->stage_doubles / per));
+    int chunk = (int)std::min<size_t>((size_t)n, std::max<size_t>(1, c->stage_doubles * (sizeof(double) / sizeof(O)) / per));
     for (int n0 = 0; n0 < n; n0 += chunk) {
         const int nc = std::min(chunk, n - n0);
         dim3 grid((TT + 31) / 32, (nc + 31) / 32, C), block(32, 8);
-        k_from_soa<D><<<grid, block, 0, c->stream>>>((const D*)s0, (const D*)s1, (const D*)s2, slot, row0, c->stage, n0, nc, C, TT, Np, dup_last);
+        k_from_soa<D, O><<<grid, block, 0, c->stream>>>((const D*)s0, (const D*)s1, (const D*)s2, slot, row0, (O*)c->stage, n0, nc, C, TT, Np, dup_last);
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(host + (size_t)n0 * per, c->stage, (size_t)nc * per * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(host + (size_t)n0 * per, c->stage, (size_t)nc * per * sizeof(O), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     }
     return 0;
@@ -1247,6 +1276,36 @@ int acoc_set_refs(acoc_ctx* c, const double* xx_ref, const double* uu_ref)
         TRY(upload_soa(c, xx_ref, c->xref, c->N, 6, c->Np));
         TRY(upload_soa(c, uu_ref, c->uref, c->N, 2, c->Np));
     }
+    c->have_refs = true;
+    return 0;
+}
+
+int acoc_set_refs_generated(acoc_ctx* c, const double* tt, const double* zshape, const double* vshape, const double* zf, const double* vx,
+                            const double* xconst, const double* uconst)
+{
+    REQUIRE(c && tt && zshape && zf && vx && xconst && uconst, "NULL argument");
+    REQUIRE(!c->P.ref_shared, "acoc_set_refs_generated needs per-instance reference storage (no ACOC_REFS_SHARED)");
+    TRY(use_device(c->device));
+    const size_t T = c->TT, N = c->N;
+    REQUIRE(3 * T + 2 * N <= c->stage_doubles, "staging buffer too small for the generator inputs");
+    double* d = c->stage;  // [tt | zshape | vshape | zf | vx]
+    CK(cudaMemcpyAsync(d, tt, T * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d + T, zshape, T * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (vshape) CK(cudaMemcpyAsync(d + 2 * T, vshape, T * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d + 3 * T, zf, N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d + 3 * T + N, vx, N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    RefConst K;
+    for (int k = 0; k < 6; ++k) K.xc[k] = xconst[k];
+    K.uc[0] = uconst[0]; K.uc[1] = uconst[1];
+    const dim3 grid((unsigned)((N + 127) / 128), (unsigned)std::min<size_t>(T, 64));
+    if (c->fp32)
+        k_gen_refs<float><<<grid, 128, 0, c->stream>>>(c->N, c->Np, c->TT, d, d + T, vshape ? d + 2 * T : nullptr, d + 3 * T, d + 3 * T + N, K,
+                                                       (float*)c->xref, (float*)c->uref);
+    else
+        k_gen_refs<double><<<grid, 128, 0, c->stream>>>(c->N, c->Np, c->TT, d, d + T, vshape ? d + 2 * T : nullptr, d + 3 * T, d + 3 * T + N, K,
+                                                        (double*)c->xref, (double*)c->uref);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));  // the staging buffer is free again; the host arrays may be reused
     c->have_refs = true;
     return 0;
 }
@@ -2189,6 +2248,45 @@ int acoc_get_result(acoc_ctx* c, double* xx_star, double* uu_star)
     return 0;
 }
 
+int acoc_get_refs(acoc_ctx* c, double* xx_ref, double* uu_ref)
+{
+    REQUIRE(c && (xx_ref || uu_ref), "NULL argument");
+    if (!c->have_refs) return fail(ACOC_ERR_STATE, "acoc_get_refs: no references set");
+    TRY(use_device(c->device));
+    const int n = c->P.ref_shared ? 1 : c->N, Np = c->P.ref_shared ? 1 : c->Np;
+    if (xx_ref) TRY(download_soa(c, c->xref, nullptr, nullptr, nullptr, xx_ref, n, 6, Np, 0));
+    if (uu_ref) TRY(download_soa(c, c->uref, nullptr, nullptr, nullptr, uu_ref, n, 2, Np, 0));
+    return 0;
+}
+
+int acoc_get_result_f32(acoc_ctx* c, float* xx_star, double* uu_star, double* x0)
+{
+    TRY(ready(c));
+    REQUIRE(xx_star && uu_star, "NULL output");
+    if (!c->x_float)
+        return fail(ACOC_ERR_STATE, "acoc_get_result_f32: the state iterates of this context are not float32 values (ACOC_STATE_F64, "
+                                    "ACOC_X_F64 or an initial trajectory with float64 states); use acoc_get_result");
+    k_result_slot_default<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->S.status, c->slot_tmp, c->S.result_slot, c->kk % 3, c->N);
+    CK(cudaGetLastError());
+    TRY((download_soa_t<float, float>(c, c->X[0], c->X[1], c->X[2], c->slot_tmp, nullptr, xx_star, c->N, 6, c->Np, 0)));
+    TRY(download_soa(c, c->U[0], c->U[1], c->U[2], c->slot_tmp, uu_star, c->N, 2, c->Np, 1));  // uu_star[:,-1] = uu_star[:,-2], optcon.py:505
+    if (x0) {  // device [6][Np] -> host (N,6); float64 unless the context computes in FP32
+        const size_t Np = c->Np;
+        if (c->fp32) {
+            std::vector<float> tmp(6 * Np);
+            CK(cudaMemcpyAsync(tmp.data(), c->x0, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            for (int i = 0; i < c->N; ++i) for (int k = 0; k < 6; ++k) x0[(size_t)i * 6 + k] = tmp[k * Np + i];
+        } else {
+            std::vector<double> tmp(6 * Np);
+            CK(cudaMemcpyAsync(tmp.data(), c->x0, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            for (int i = 0; i < c->N; ++i) for (int k = 0; k < 6; ++k) x0[(size_t)i * 6 + k] = tmp[k * Np + i];
+        }
+    }
+    return 0;
+}
+
 int acoc_get_iterate(acoc_ctx* c, int which, double* xx, double* uu)
 {
     TRY(ready(c));
@@ -2303,17 +2401,33 @@ int acoc_lqr_tracking(int device, int n, int TT, const double* params, int state
     // the uploads and memsets above ran on the legacy default stream; the context's stream is non-blocking, so order them explicitly
     CK(cudaDeviceSynchronize());
     const double *d_xopt = (const double*)c->xref, *d_uopt = (const double*)c->uref;
+    CK(cudaEventRecord(c->ev[0], c->stream));
     k_step_batch<<<(TT + 127) / 128, 128, 0, c->stream>>>(M, c->P.q32, TT, d_xopt, d_uopt, nullptr, nullptr, dA, dB, nullptr, nullptr);
     CK(cudaGetLastError());
     TRY(lq_dense_dev(1, TT, false, dA, dB, dQ, dR, dS, dQf, dx0, nullptr, nullptr, nullptr, dK, nullptr, dxo, duo, nullptr, c->stream));
+    CK(cudaEventRecord(c->ev[1], c->stream));
     const Problem P = prob<double>(c);
     if (c->P.q32) k_track<true><<<(n + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, 0, c->stream>>>(P, dK, d_xopt, d_uopt, dstart, (double*)c->X[0], (double*)c->U[0]);
     else k_track<false><<<(n + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, 0, c->stream>>>(P, dK, d_xopt, d_uopt, dstart, (double*)c->X[0], (double*)c->U[0]);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev[2], c->stream));
     TRY(download_soa(c, c->X[0], nullptr, nullptr, nullptr, xx_reg, n, 6, c->Np, 0));
     TRY(download_soa(c, c->U[0], nullptr, nullptr, nullptr, uu_reg, n, 2, c->Np, 0));
+    {
+        float a = 0, b = 0;
+        CK(cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
+        CK(cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
+        g_pt_ms[0] = (double)a + b; g_pt_ms[1] = a; g_pt_ms[2] = b;
+    }
     if (K) CK(cudaMemcpy(K, dK, (size_t)TT * 12 * sizeof(double), cudaMemcpyDeviceToHost));
     CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int acoc_last_pointwise_timing(double* ms)
+{
+    REQUIRE(ms, "NULL output");
+    for (int k = 0; k < 3; ++k) ms[k] = g_pt_ms[k];
     return 0;
 }
 

@@ -118,6 +118,28 @@ def acrobatic_problem(zf=2.71, xf=18, tf=1, TT=1000):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# shared time bases for the device-side generators (acoc_set_refs_generated): the per-instance references above are
+#   X = 0 + vx*tt,  Z = 0 + zshape*(zf - 0),  V = ((vshape*zf)**2 + vx**2)**0.5   (step)   /   V = const (acrobatic)
+# with these tables, which are computed by the very functions above (so np.exp is numpy's, as in the scripts)
+# ---------------------------------------------------------------------------------------------------------
+def step_bases(tf=1, TT=1000):
+    """(tt, zshape, vshape) of step_problem: zshape = sigmoid, vshape = its derivative term (main_newton_method.py:96-114)."""
+    tt = np.linspace(0, tf, TT)
+    s, ds = sigmoid_fcn(tt - tt[-1] / 2, tt.shape[0] * 1)
+    return tt, s, ds
+
+
+def acrobatic_bases(tf=1, TT=1000):
+    """(tt, zshape) of acrobatic_problem: the unit-height bump (acrobatic_newton.py:99-126 with pT = 1)."""
+    tt = np.linspace(0, tf, TT)
+    return tt, reference_position_acrobatic(tt, 0, 1.0)[0]
+
+
+STEP_CONST = (np.zeros(6), np.array([TRIM_THRUST_INT, 0.0]))
+ACRO_CONST = (np.array([0.0, 0.0, TRIM_V, 0.0, 0.0, TRIM_GAMMA]), np.array([TRIM_THRUST_INT * 10, -60.0]))
+
+
+# ---------------------------------------------------------------------------------------------------------
 # batched configurations of BASELINE.json (SURVEY.md 8(d))
 # ---------------------------------------------------------------------------------------------------------
 def config3_deltas(n=4096, seed=1234):

@@ -1,27 +1,31 @@
 #!/usr/bin/env python
-"""bench.py -- trajectory-Newton-iterations / second on B200 (BASELINE.json metric).
+"""bench.py -- trajectory-Newton-iterations / second on B200 (BASELINE.json metric) and the other BASELINE configurations.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--instances M] [--workload step|acro]
-                    [--armijo lazy|speculative] [--state f32|f64] [--no-e2e] [--no-cpu]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload step|acro|track|single-step|single-acro]
+                    [--instances M] [--precision f64|f32] [--armijo lazy|speculative] [--state f32|f64] [--no-e2e] [--no-cpu]
     torchrun --nproc-per-node N bench.py --gpus N ...          (one rank per GPU, launched by the driver)
 
-Workload (config.workload): BASELINE.json configs[3] -- "batched step-maneuver Newton, 65,536 randomised step
-references", per GPU (weak scaling: rank r of world w holds instances r::w of a 65,536*w batch).  A "step" is ONE
-Newton iteration (loop body of optcon.py:415-501: fused backward Riccati/costate sweep, LQ forward pass + descent,
-Armijo candidate rollouts, update rollout) over the whole batch.  W warm-up iterations, then K timed ones -- these
-are the iterations W..W+K-1 of the real solve from the device-generated initial guess; every instance is still
-active there.  Time = CUDA events on the context's stream around the K iterations, max over ranks.
+Workloads (config.workload):
+  step         BASELINE.json configs[3] (default, the configuration the metric is quoted on): 65,536 randomised step references per
+               GPU (weak scaling: rank r of world w holds instances r::w of a 65,536*w batch).
+  acro         configs[4]: acrobatic batch with perturbed x0 (1,048,576 instances = --instances 131072 on 8 GPUs).
+  track        configs[2]: lqr_tracking of Data/xx_star.npy from 4096 perturbed initial states (unit: closed-loop rollout steps / s).
+  single-step  configs[0] / single-acro configs[1]: ONE trajectory (latency: ms per Newton iteration, whole solve).
+A "step" of the Newton workloads is ONE Newton iteration (loop body of optcon.py:415-501: fused backward Riccati/costate sweep, LQ
+forward pass + descent, Armijo candidate rollouts, update) over the whole batch: W warm-up iterations, then K timed ones -- iterations
+W..W+K-1 of the real solve from the device-generated initial guess.  Time = CUDA events on the context's stream, max over ranks.
 
-The JSON line carries: value (device-resident), e2e (full solve through the Python API from pinned host buffers:
-H2D of the references, device initial guess, solve to the reference's criterion, D2H of results and stats),
-roofline for the dominant kernel (HBM GB/s against MEASURED_PEAKS.json, FP64 TFLOP/s against a DFMA microbenchmark
-run here), cpu_baseline (the C port of the reference in oracle/, OpenMP over instances, bounded sample), clocks.
+The JSON line carries: value (device-resident inputs), e2e (full solve through the Python API / C ABI from host buffers with the
+copies inside the timed wall), whole_solve, roofline (dominant kernel; per-kernel table with bytes / FP64 instructions counted from
+the per-iteration ACTIVE instance counts), cpu_baseline (C port of the reference on the host cores + the Python reference, live when
+its tree is present, else the recorded measurement), clocks.
 
---impl reference times that CPU port alone (the reference itself is Python and is not present on the GPU box).
+--impl reference times the CPU port alone on the same workload (the reference itself is Python and is not present on the GPU box).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -38,7 +42,7 @@ METRIC = "trajectory_newton_iterations_per_second"
 UNIT = "traj-Newton-it/s"
 TT = 1000
 
-# algorithmic FP64 flops / HBM bytes per instance per time step (dense ns=6, ni=2 accounting)
+# algorithmic FP64 flops / HBM bytes per instance per time step (dense ns=6, ni=2 accounting, float64 storage)
 FLOPS = dict(backward=2106, forward=126 + 30, cost=107, candidate=159, update=52 + 107)
 BYTES = dict(backward=128 + 128, forward=128 + 64 + 16, cost=128, candidate=32 + 64, candidate_write=32 + 64 + 64, update=32 + 64 + 64)
 
@@ -62,6 +66,28 @@ def load_peaks():
         except Exception:
             pass
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+def source_sha16():
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "aircraftoptimalcontrol_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def kernel_counters():
+    """Per-launch DRAM bytes and executed FP64-pipe instructions of the sweep kernels from the committed `ncu --set full` capture of
+    THIS build (profiles/r02_kernel_counters.json, written by profiles/summarize_ncu.py --counters); None if the capture belongs
+    to another build of the kernels."""
+    p = os.path.join(ROOT, "profiles", "r02_kernel_counters.json")
+    try:
+        kc = json.load(open(p))
+    except Exception:
+        return None, "no capture committed"
+    if kc.get("source_sha16") != source_sha16():
+        return None, "profiles/r02_kernel_counters.json was captured from another build of csrc/ (%s != %s)" % (kc.get("source_sha16"), source_sha16())
+    return kc, "profiles/r02_kernel_counters.json (ncu --set full of this build, per launch, %d instances)" % kc.get("instances", 0)
 
 
 class ClockSampler(threading.Thread):
@@ -95,16 +121,20 @@ class ClockSampler(threading.Thread):
 
 
 def make_problem(workload, n_total, lo_hi_stride, seed=None):
-    """Per-rank shard of the batched configuration: instances rank::world of the n_total-instance batch."""
+    """Per-rank shard of the batched configuration: instances rank::world of the n_total-instance batch.
+    Returns (xx_ref, uu_ref, dx0, weights, gen) with gen = the arguments of PipelinedNewton.solve(refs=...) that generate the same
+    references on the device."""
     from aircraftoptimalcontrol_b200 import refgen
     r, w = lo_hi_stride
     if workload == "step":
         zf, xf = refgen.config4_params(n_total, 2024 if seed is None else seed)
-        xr, ur = refgen.step_problem(xf[r::w], zf[r::w], TT=TT)
-        return xr, ur, None, refgen.weights("step")
+        zf, xf = np.ascontiguousarray(zf[r::w]), np.ascontiguousarray(xf[r::w])
+        xr, ur = refgen.step_problem(xf, zf, TT=TT)
+        return xr, ur, None, refgen.weights("step"), ("step", zf, xf)
     dx0, zf = refgen.config5_params(n_total, 7 if seed is None else seed)
-    xr, ur = refgen.acrobatic_problem(zf[r::w], TT=TT)
-    return xr, ur, np.ascontiguousarray(dx0[r::w]), refgen.weights("acro")
+    zf = np.ascontiguousarray(zf[r::w])
+    xr, ur = refgen.acrobatic_problem(zf, TT=TT)
+    return xr, ur, np.ascontiguousarray(dx0[r::w]), refgen.weights("acro"), ("acrobatic", zf)
 
 
 def pinned_like(a):
@@ -115,11 +145,15 @@ def pinned_like(a):
     return t  # keep the tensor alive; .numpy() is the view
 
 
+def host_threads():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
 def cpu_port_rate(workload, sample, W, K, state):
     """Newton iterations W..W+K-1 of `sample` instances with the C port of the reference on all host threads."""
     from oracle import corcl
     corcl.build()
-    xr, ur, dx0, (Q, R, QT) = make_problem(workload, sample, (0, 1))
+    xr, ur, dx0, (Q, R, QT), _ = make_problem(workload, sample, (0, 1))
     xi = np.zeros((sample, 6, TT))
     ui = np.zeros((sample, 2, TT))
     for i in range(sample):  # the initial guess is an input of the hot path (float64 P-law rollout, same as the GPU's)
@@ -127,7 +161,7 @@ def cpu_port_rate(workload, sample, W, K, state):
         if dx0 is not None:
             xref_i[:, 0] += dx0[i]
         xi[i], ui[i] = corcl.initial_trajectory(xref_i if dx0 is not None else xr[i], quant_f32=(state == "f32"))
-    nt = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    nt = host_threads()
     kw = dict(quant_f32=(state == "f32"), n_threads=nt)
     m = min(sample, nt)   # untimed: starts the OpenMP thread pool and faults in the library
     corcl.newton_batch(xr[:m], ur[:m], xi[:m], ui[:m], Q, R, QT, n_iters_cap=1, **kw)
@@ -143,6 +177,64 @@ def cpu_port_rate(workload, sample, W, K, state):
     return its / dt, nt, dt, its
 
 
+def python_reference_baseline(workload):
+    """SURVEY.md 8(d) lines (i)/(ii): the unmodified Python reference.  Live (3 Newton iterations of instance 0 of the workload, one
+    core) when the reference tree is present; otherwise the measurement recorded in the build container."""
+    rec = None
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r02_python_reference_cpu.json")))
+    except Exception:
+        pass
+    out = {"unit": UNIT}
+    key = "acro" if workload in ("acro", "single-acro") else "step"
+    if rec is not None:
+        w = rec["workloads"][key]
+        out["recorded"] = {"one_core": w["one_core"], "all_cores": w["all_cores"], "machine": rec["machine"], "what": rec["what"],
+                           "whole_solves_configs_1_2": rec.get("whole_solves_configs_1_2"),
+                           "source": "profiles/r02_python_reference_cpu.json (oracle/time_python_reference.py; the reference tree does not travel to the GPU box)"}
+    try:
+        from oracle import pyref
+        if pyref.available():
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import time_python_reference as tpr
+            done, dt = tpr.time_one((key, 0, 3))
+            out["live"] = {"value": done / dt, "cores": 1, "iterations": done, "wall_s": dt,
+                           "what": "unmodified reference at %s, NewtonMethod.optimize, 3 iterations of instance 0" % pyref.REFERENCE_ROOT}
+    except Exception as e:  # never let the optional baseline break the bench line
+        out["live_error"] = repr(e)[:200]
+    src = out.get("live") or (out.get("recorded", {}).get("one_core"))
+    if src:
+        out["value"] = src["value"]
+        out["cores"] = 1
+        out["kind"] = "reference (live)" if "live" in out else "reference (recorded)"
+    return out
+
+
+def emit(line: dict):
+    """Print the ONE JSON line on the process's original stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+
+
+def config_dict(args, n_per_gpu, world):
+    names = {"step": "BASELINE.json configs[3]: batched step-maneuver Newton, randomised step references (zf~U(1.5,3.5), xf~U(14,18), seed 2024)",
+             "acro": "BASELINE.json configs[4]: acrobatic Newton OCP batch (x0 perturbed, bump height zf~U(2.0,3.4), seed 7)"}
+    return {"workload": names[args.workload],
+            "instances_per_gpu": n_per_gpu, "instances_total": n_per_gpu * world, "TT": TT, "ns": 6, "ni": 2,
+            "state_quant": args.state, "precision": args.precision,
+            "state_storage": "float32 in HBM (lossless: quantised states are float32 values)" if moved_bytes(args)["backward"] == 232 else
+                             ("float32" if args.precision == "f32" else "float64"),
+            "armijo": args.armijo, "armijo_maxiters": 10, "max_iters": 200,
+            "step": "one Newton iteration over the whole batch (iterations W..W+K-1 of the solve)",
+            "l2": "working set per GPU (%.1f GB) >> 126 MB L2, no flush needed" % (n_per_gpu * 400e3 / 1e9),
+            "parallelism": "instances sharded round-robin, %d per GPU, no hot-path collective" % n_per_gpu}
+
+
+# =====================================================================================================================
+# batched Newton workloads (configs 4 and 5)
+# =====================================================================================================================
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -154,68 +246,122 @@ def run_reference_arm(args, rank, world):
         "data": "synthetic", "config": config_dict(args, sample, world=1),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": nt, "kind": "port",
                          "sample": "%d instances x Newton iterations %d..%d of the workload, C port of the reference (oracle/acoc_oracle.c), "
-                                   "OpenMP over instances; time(W+K iterations) - time(W iterations)" % (sample, args.warmup, args.warmup + args.steps - 1)},
+                                   "OpenMP over instances; time(W+K iterations) - time(W iterations)" % (sample, args.warmup, args.warmup + args.steps - 1),
+                         "python_reference": python_reference_baseline(args.workload)},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
 
 
-def config_dict(args, n_per_gpu, world):
-    return {"workload": ("BASELINE.json configs[3]: batched step-maneuver Newton, randomised step references (zf~U(1.5,3.5), xf~U(14,18), seed 2024)"
-                         if args.workload == "step" else
-                         "BASELINE.json configs[4]: acrobatic Newton OCP batch (x0 perturbed, bump height zf~U(2.0,3.4), seed 7)"),
-            "instances_per_gpu": n_per_gpu, "instances_total": n_per_gpu * world, "TT": TT, "ns": 6, "ni": 2,
-            "state_quant": args.state, "precision": args.precision,
-            "state_storage": "float32 in HBM (lossless: quantised states are float32 values)" if moved_bytes(args)["backward"] == 232 else
-                             ("float32" if args.precision == "f32" else "float64"),
-            "armijo": args.armijo, "armijo_maxiters": 10, "max_iters": 200,
-            "step": "one Newton iteration over the whole batch (iterations W..W+K-1 of the solve)",
-            "l2": "working set per GPU (%.1f GB) >> 126 MB L2, no flush needed" % (n_per_gpu * 400e3 / 1e9),
-            "parallelism": "instances sharded round-robin, %d per GPU, no hot-path collective" % n_per_gpu}
+def roofline_tables(args, n, K, W, hist, phases, peaks, peak_src, fp64_peak, fused_fc):
+    """Per-kernel accounting of the K profiled iterations.  Units come from the history of the profiled run: an instance is ACTIVE in
+    iteration k iff it executed it (n_armijo[:, k] > 0); the sweeps process every lane of every tile (32 instances) that still holds
+    an active instance."""
+    steps_per = float(TT - 1)
+    ncand = hist["n_armijo"][:, W:W + K]
+    act = ncand > 0                                        # (N, K) instance executed iteration W+k
+    pad = (-act.shape[0]) % 32
+    act_t = np.pad(act, ((0, pad), (0, 0))).reshape(-1, 32, K)
+    a_k = act.sum(0).astype(np.float64)                    # active instances per iteration
+    lanes_k = act_t.any(1).sum(0).astype(np.float64) * 32  # lanes the tile-granular sweeps process per iteration
+    fail = ncand > 1                                       # candidate 0 failed
+    fail_k = fail.sum(0).astype(np.float64)
+    fail_lanes_k = np.pad(fail, ((0, pad), (0, 0))).reshape(-1, 32, K).any(1).sum(0).astype(np.float64) * 32
+    exact = (np.arange(W, W + K) > 8)                      # optcon.py:443
+    # candidate rollouts executed after candidate 0 (lazy search: 1..9 at once in the exact-Hessian iterations; 1..3, then 4..9
+    # where those failed too, in the Gauss-Newton iterations)
+    if args.armijo == "lazy":
+        roll_k = np.where(exact, 9.0 * fail_k, 3.0 * fail_k + 6.0 * (ncand > 4).sum(0))
+        cand0_units = 0.0 if fused_fc else float(a_k.sum())
+        upd_k = fail_k
+        upd_lanes_k = fail_lanes_k
+    else:
+        roll_k = 10.0 * a_k
+        cand0_units = 0.0
+        upd_k = a_k
+        upd_lanes_k = lanes_k
+    MB = moved_bytes(args)
+    x_float = MB["forward"] != BYTES["forward"]
+    fwd_alg = BYTES["forward"] + (BYTES["candidate_write"] if fused_fc else 0)
+    fwd_flops = FLOPS["forward"] + (FLOPS["candidate"] if fused_fc else 0)
+    # the fused forward + candidate-0 sweep does not write du and re-read it, reads u once, and fetches only V, theta, gamma of x
+    fwd_moved = MB["forward"] + ((MB["candidate_write"] - (16 if args.precision == "f32" else 32) - (12 if x_float else 24)) if fused_fc else 0)
+    kc, kc_src = kernel_counters()
+
+    def counters(name):
+        if not kc:
+            return None
+        return kc["kernels"].get(name)
+
+    names = {"backward": "k_backward_tma" if not args.no_tma else "k_backward",
+             "forward": ("k_forward_cand0_tma" if fused_fc else ("k_forward_tma" if not args.no_tma else "k_forward")),
+             "candidates": "k_candidates", "update": "k_rollout_write_tma<.,1>" if not args.no_tma else "k_update"}
+    units = {  # (useful instance-sweeps, processed lane-sweeps) over the K iterations
+        "backward": (a_k.sum(), lanes_k.sum()), "forward": (a_k.sum(), lanes_k.sum()),
+        "candidates": (roll_k.sum() + cand0_units, roll_k.sum() + cand0_units), "update": (upd_k.sum(), upd_lanes_k.sum())}
+    alg_b = {"backward": BYTES["backward"], "forward": fwd_alg, "candidates": BYTES["candidate"], "update": BYTES["update"]}
+    mov_b = {"backward": MB["backward"], "forward": fwd_moved, "candidates": MB["candidate"], "update": MB["update"]}
+    alg_f = {"backward": FLOPS["backward"], "forward": fwd_flops, "candidates": FLOPS["candidate"], "update": FLOPS["update"]}
+    bound = {"backward": "hbm", "forward": "hbm", "candidates": "fp64", "update": "hbm"}
+    tbl = {}
+    for k in ("backward", "forward", "candidates", "update"):
+        ms = phases[k]
+        useful, lanes = units[k]
+        if ms <= 0 or useful <= 0:
+            continue
+        sec = ms * 1e-3
+        e = {"kernel": names[k], "bound": bound[k], "ms_per_iteration": ms / K, "instance_sweeps_useful": useful, "lane_sweeps_processed": lanes}
+        c = counters(names[k])
+        if c and c.get("fp64_inst_per_lane_step"):   # executed FP64-pipe instructions (ncu: sm__inst_executed_pipe_fp64 of this build)
+            ex = c["fp64_inst_per_lane_step"] * lanes * steps_per
+            e["fp64_executed_ginst_per_s"] = ex / sec / 1e9
+            e["fp64_executed_frac"] = ex / sec / (fp64_peak * 1e12 / 2.0)
+        if bound[k] == "hbm":
+            gbs = useful * steps_per * alg_b[k] / sec / 1e9
+            e.update({"hbm_gbs": gbs, "hbm_frac": gbs / peaks["hbm_gbs"],
+                      "hbm_gbs_moved": lanes * steps_per * mov_b[k] / sec / 1e9})
+            e["hbm_frac_moved"] = e["hbm_gbs_moved"] / peaks["hbm_gbs"]
+        else:  # FP64-bound: the inputs of the 9 candidate rollouts of an instance are shared through L1, HBM is not the limiter
+            e["fp64_algorithmic_tflops"] = useful * steps_per * alg_f[k] / sec / 1e12
+        if c:
+            e["ncu_dram_bytes_per_instance_step"] = c.get("dram_bytes_per_lane_step")
+        tbl[k] = e
+    tot_ms = sum(phases[k] for k in ("backward", "forward", "candidates", "update"))
+    whole_b = sum(units[k][0] * steps_per * alg_b[k] for k in ("backward", "forward", "update"))
+    tbl["whole_iteration"] = {"ms_per_iteration": tot_ms / K, "hbm_gbs": whole_b / (tot_ms * 1e-3) / 1e9,
+                              "hbm_frac": whole_b / (tot_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                              "note": "bytes of the HBM-bound sweeps over the whole profiled time (candidates included in the time only)"}
+    dom = max(("backward", "forward", "candidates", "update"), key=lambda k: phases[k])
+    d = tbl[dom]
+    c = counters(names[dom])
+    n_launch_lanes = units[dom][1] / K
+    traffic = c["dram_bytes_per_lane_step"] * n_launch_lanes * steps_per if c and c.get("dram_bytes_per_lane_step") else None
+    alg_per_launch = units[dom][0] / K * steps_per * alg_b[dom]
+    if bound[dom] == "hbm":
+        achieved, peak, unit, frac = d["hbm_gbs"], peaks["hbm_gbs"], "GB/s", d["hbm_frac"]
+    else:
+        achieved, peak, unit = d.get("fp64_executed_ginst_per_s"), fp64_peak * 1e3 / 2.0, "G FP64-inst/s (thread-level)"
+        frac = d.get("fp64_executed_frac")
+    roofline = {"kernel": names[dom] + ("<EXACT>" if dom == "backward" and exact.any() else ""), "bound": "hbm" if bound[dom] == "hbm" else "fp64 (tensor cores unused by design)",
+                "achieved": achieved, "peak": peak, "unit": unit, "frac": frac, "traffic": traffic, "traffic_source": kc_src,
+                "algorithmic_bytes_per_launch": alg_per_launch, "peak_source": peak_src,
+                "units": {"active_instances_per_iteration": a_k.tolist(), "lanes_processed_per_iteration": lanes_k.tolist(),
+                          "failed_candidate0_per_iteration": fail_k.tolist(),
+                          "note": "achieved = SURVEY.md 8(d) bytes x (TT-1) x ACTIVE instances of each profiled iteration / that kernel's summed "
+                                  "time; the sweeps also process the finished lanes of live tiles (lanes_processed)"},
+                "fp64": {"peak_tflops": fp64_peak, "peak_source": "DFMA microbenchmark run in this process (acoc_measure_fp64_peak)",
+                         "executed_frac_dominant_kernel": d.get("fp64_executed_frac"),
+                         "note": "executed FP64-pipe instructions per lane and step from the ncu capture of this build x lanes processed, against the "
+                                 "measured DFMA issue rate; null when no capture of this build is committed"},
+                "per_kernel": tbl, "share_of_step": phases[dom] / max(tot_ms, 1e-9),
+                "algorithmic": {"bytes_per_instance_step": BYTES, "flops_per_instance_step": FLOPS, "note": "SURVEY.md 8(d) per-unit figures"},
+                "moved": {"bytes_per_instance_step": dict(MB, forward_fused=fwd_moved),
+                          "note": "bytes the kernels move in this mode (float32-valued states stored as float: -24 B per state access)"}}
+    return roofline
 
 
-def emit(line: dict):
-    """Print the ONE JSON line on the process's original stdout."""
-    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
-
-
-_REAL_STDOUT = os.dup(1)
-
-
-def main():
-    os.dup2(2, 1)  # anything native code prints to fd 1 (e.g. the NCCL version banner) lands on stderr
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--instances", type=int, default=65536, help="instances per GPU")
-    ap.add_argument("--workload", default="step", choices=["step", "acro"])
-    ap.add_argument("--armijo", default="lazy", choices=["lazy", "speculative"])
-    ap.add_argument("--state", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--precision", default="f64", choices=["f64", "f32"], help="f64 = the parity path (default); f32 = the optional FP32 mode")
-    ap.add_argument("--x-storage", default="auto", choices=["auto", "f64"], help="f64: keep float32-valued states in float64 buffers (A/B)")
-    ap.add_argument("--no-tma", action="store_true", help="plain-load sweeps instead of the TMA rings (A/B)")
-    ap.add_argument("--no-split", action="store_true", help="one stream for the whole batch instead of the two-range sweep (A/B)")
-    ap.add_argument("--no-fused", action="store_true", help="separate LQ forward pass / candidate sweeps instead of the fused ones (A/B)")
-    ap.add_argument("--cpu-sample", type=int, default=16384, help="instances of the bounded CPU sample (about 10 s of work on 16 host threads)")
-    ap.add_argument("--chunks", type=int, default=4, help="sub-batches of the pipelined end-to-end solve (4: 0.42 s, 8: 0.44-0.46 s, 12: 0.52 s)")
-    ap.add_argument("--no-stagger", action="store_true", help="end-to-end leg: same stream priority for every sub-batch (A/B)")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-roofline", action="store_true")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 0)
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-
-    if args.impl == "reference":
-        run_reference_arm(args, rank, world)
-        return
-
+def run_batched(args, rank, world, local):
     import aircraftoptimalcontrol_b200 as pkg
     from aircraftoptimalcontrol_b200 import _lib, dist as D
 
@@ -229,9 +375,10 @@ def main():
     n_total = n * world
     K, W = args.steps, args.warmup
 
-    xr, ur, dx0, (Q, R, QT) = make_problem(args.workload, n_total, (rank, world))
-    bn = pkg.BatchedNewton(n, TT=TT, device=local, state=args.state, armijo=args.armijo, precision=args.precision, x_storage=args.x_storage, tma=not args.no_tma, split=not args.no_split,
-                           fused=not args.no_fused)
+    xr, ur, dx0, (Q, R, QT), gen = make_problem(args.workload, n_total, (rank, world))
+    kw = dict(TT=TT, device=local, state=args.state, armijo=args.armijo, precision=args.precision, x_storage=args.x_storage, tma=not args.no_tma,
+              split=not args.no_split, fused=not args.no_fused)
+    bn = pkg.BatchedNewton(n, **kw)
     bn.set_weights(Q, R, QT)
     bn.set_refs(xr, ur)
     bn.init_guess(dx0=dx0)
@@ -249,7 +396,7 @@ def main():
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        sampler.start()  # keeps sampling through the timed region, the per-phase re-run and the end-to-end solve
+        sampler.start()  # keeps sampling through the timed region, the per-phase re-run and the end-to-end solves
     its_before = int(bn.stats()["iters"].astype(np.int64).sum())
     barrier()
     bn.iterate(K, count_active=False)  # K Newton iterations, timed by CUDA events inside the library
@@ -268,9 +415,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         ms, launches, its_done = float(tmax[0]), int(t[1]), int(t[2])
     n_active = int((st["status"] == 0).sum())
-    value = its_done / (ms * 1e-3)   # = instances x K while every instance is still iterating (the default W, K)
+    value = its_done / (ms * 1e-3)   # = instances x K while every instance is still iterating
 
-    # ---- roofline of the dominant kernel (rank 0): re-run iterations with per-phase events --------------------
+    # ---- roofline (rank 0): the same iterations re-run with per-phase events (one stream, no tile ranges) ------------
     roofline = fp64 = phases = None
     peaks, peak_src = load_peaks()
     if rank == 0 and not args.no_roofline:
@@ -280,80 +427,10 @@ def main():
         bn.iterate(K, count_active=False)
         tp = bn.timing()
         bn.set_profiling(False)
-        h = bn.history()
-        ncand = h["n_armijo"][:, W:W + K].astype(np.float64)
-        steps_per = float(TT - 1)
-        # algorithmic bytes / flops of every phase over the K timed iterations (SURVEY.md 8(d) per-unit figures)
-        # lazy search on the TMA path: the LQ forward pass and candidate 0 are ONE sweep (k_forward_cand0_tma); its time is the
-        # "forward" phase and it is accounted with the algorithmic bytes / flops of both (SURVEY.md 8(d) counts du written and read
-        # back and u read twice: 368 B; the fused kernel moves 276 B of them with float state slots)
-        fused_fc = args.armijo == "lazy" and not args.no_tma and not args.no_fused
-        MB = moved_bytes(args)
-        fwd_bytes, fwd_flops, fwd_moved = BYTES["forward"], FLOPS["forward"], MB["forward"]
-        if fused_fc:
-            fwd_bytes += BYTES["candidate_write"]
-            fwd_flops += FLOPS["candidate"]
-            # minus the du read-back and the second read of u, minus the state components the ring does not fetch (only V, theta, gamma)
-            x_float = args.precision == "f32" or MB["forward"] != BYTES["forward"]
-            fwd_moved += MB["candidate_write"] - (16 if args.precision == "f32" else 32) - (12 if x_float else 24)
-        if args.armijo == "lazy":
-            # candidate 0 for everyone, written tentatively (it is the update when accepted); the other 9 candidates and a
-            # separate update rollout only for instances whose candidate 0 failed
-            n_fail = float(np.sum(ncand > 1))
-            n_c0 = 0.0 if fused_fc else float(ncand.size)
-            cand_bytes = steps_per * (n_c0 * BYTES["candidate_write"] + 9 * n_fail * BYTES["candidate"])
-            cand_flops = steps_per * (n_c0 + 9 * n_fail) * FLOPS["candidate"]
-            upd_units = n_fail
-        else:
-            cand_bytes = steps_per * ncand.size * 10 * BYTES["candidate"]
-            cand_flops = steps_per * ncand.size * 10 * FLOPS["candidate"]
-            upd_units = float(ncand.size)
         phases = tp["phases"]
-        per_launch_ms = {k: v / K for k, v in phases.items()}
-        dom = max(("backward", "forward", "candidates", "update"), key=lambda k: phases[k])
-        tot_bytes = {"backward": steps_per * n * K * BYTES["backward"], "forward": steps_per * n * K * fwd_bytes,
-                     "candidates": cand_bytes, "update": steps_per * upd_units * BYTES["update"]}
-        tot_flops = {"backward": steps_per * n * K * FLOPS["backward"], "forward": steps_per * n * K * fwd_flops,
-                     "candidates": cand_flops, "update": steps_per * upd_units * FLOPS["update"]}
         fp64_peak = _lib.measure_fp64_peak(local)
-        moved_ratio = {"backward": MB["backward"] / BYTES["backward"], "forward": fwd_moved / fwd_bytes,
-                       "update": MB["update"] / BYTES["update"],
-                       "candidates": ((n_c0 * MB["candidate_write"] + 9 * n_fail * MB["candidate"]) / max(n_c0 * BYTES["candidate_write"] + 9 * n_fail * BYTES["candidate"], 1.0)
-                                      if args.armijo == "lazy" else MB["candidate"] / BYTES["candidate"])}
-        tbl = {}
-        for k in ("backward", "forward", "candidates", "update"):
-            if phases[k] <= 0 or tot_bytes[k] <= 0:
-                continue
-            gbs = tot_bytes[k] / (phases[k] * 1e-3) / 1e9
-            tfs = tot_flops[k] / (phases[k] * 1e-3) / 1e12
-            tbl[k] = {"ms_per_iteration": per_launch_ms[k], "hbm_gbs": gbs, "hbm_frac": gbs / peaks["hbm_gbs"], "fp64_tflops": tfs, "fp64_frac": tfs / fp64_peak,
-                      "hbm_gbs_moved": gbs * moved_ratio[k], "hbm_frac_moved": gbs * moved_ratio[k] / peaks["hbm_gbs"]}
-        whole = sum(tot_bytes.values()) / (sum(phases.values()) * 1e-3) / 1e9
-        tbl["whole_iteration"] = {"ms_per_iteration": sum(phases.values()) / K, "hbm_gbs": whole, "hbm_frac": whole / peaks["hbm_gbs"]}
-        d = tbl[dom]
-        # HBM is the binding resource: the bytes are irreducible, while the kernels execute far fewer flops than the dense
-        # accounting of SURVEY.md 8(d) (sparsity of A, B and symmetry of P), so the FP64 figure is reported beside it.
-        traffic = None
-        try:  # DRAM bytes per launch of the dominant kernel from the committed ncu capture, scaled to this instance count
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            traffic = (tj.get("float_state", {}) if MB["backward"] == 232 else tj).get("k_" + dom) if args.precision == "f64" else None
-            if traffic is not None:
-                traffic = traffic * n / tj["instances"]
-        except Exception:
-            pass
-        roofline = {"kernel": "k_" + dom, "bound": "hbm", "achieved": d["hbm_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": d["hbm_frac"], "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu --set full, per launch)",
-                    "algorithmic_bytes_per_launch": tot_bytes[dom] / K, "peak_source": peak_src,
-                    "fp64": {"achieved_algorithmic_tflops": d["fp64_tflops"], "peak_tflops": fp64_peak, "frac_algorithmic": d["fp64_frac"],
-                             "peak_source": "DFMA microbenchmark run in this process (acoc_measure_fp64_peak)",
-                             "note": "algorithmic = dense ns=6/ni=2 flop count of SURVEY.md 8(d); executed flops are lower (structure-exploiting sweep)"},
-                    "per_kernel": tbl, "forward_phase": ("k_forward_cand0_tma: LQ forward pass + candidate 0 in one sweep" if fused_fc else "k_forward"),
-                    "share_of_step": phases[dom] / max(sum(phases.values()), 1e-9),
-                    "algorithmic": {"bytes_per_instance_step": BYTES, "flops_per_instance_step": FLOPS,
-                                    "note": "SURVEY.md 8(d) per-unit figures x (TT-1) x instances per launch"},
-                    "moved": {"bytes_per_instance_step": MB, "achieved": d["hbm_gbs_moved"], "frac": d["hbm_frac_moved"],
-                              "note": "bytes the kernels move in this mode (float32-valued states stored as float: -24 B per state access); "
-                                      "'achieved'/'frac' above use the SURVEY.md 8(d) float64 accounting, so they can exceed the moved figure"}}
+        fused_fc = args.armijo == "lazy" and not args.no_tma and not args.no_fused
+        roofline = roofline_tables(args, n, K, W, bn.history(), phases, peaks, peak_src, fp64_peak, fused_fc)
         fp64 = {"peak_tflops_measured": fp64_peak, "dependent_dfma_latency_cycles": _lib.measure_fp64_latency(local)}
 
     # ---- whole solve, device-resident (every instance to the reference's criterion; includes the float32-noise phase
@@ -368,48 +445,79 @@ def main():
              "survivor_generation_moves_ms": tsolve["phases"]["select"], "scope": "this rank"}
 
     device_bytes = bn.device_bytes
-    bn.close()  # the end-to-end leg below builds its own contexts: release this one (and its survivor generations) first
+    bn.close()  # the end-to-end legs below build their own contexts: release this one (and its survivor generations) first
     state["bn_open"] = False
 
     # ---- end to end through the public API, host buffers, full solve -----------------------------------------
-    e2e = None
+    e2e = e2e_host = None
     if not args.no_e2e:
-        xr_p, ur_p = pinned_like(xr), pinned_like(ur)
         import torch
-        xs_t = torch.empty((n, 6, TT), dtype=torch.float64, pin_memory=True)
-        us_t = torch.empty((n, 2, TT), dtype=torch.float64, pin_memory=True)
-        pn = pkg.PipelinedNewton(n, n_chunks=args.chunks, TT=TT, device=local, state=args.state, armijo=args.armijo, precision=args.precision,
-                                 x_storage=args.x_storage, tma=not args.no_tma, split=not args.no_split, fused=not args.no_fused,
-                                 stagger=not args.no_stagger)
+        if dist is not None:  # warm the communicator the statistics gather uses (its first collective builds the NCCL channels)
+            D.gather_stats({"iters": np.zeros(n, dtype=np.int32), "status": np.zeros(n, dtype=np.int32), "J": np.zeros(n), "descent": np.zeros(n),
+                            "n_reg": np.zeros(n, dtype=np.int32)}, n_total)
+        pn = pkg.PipelinedNewton(n, n_chunks=args.chunks, stagger=not args.no_stagger, **kw)
         pn.set_weights(Q, R, QT)
-        pn.solve(xr_p.numpy(), ur_p.numpy(), dx0=dx0, out=(xs_t.numpy(), us_t.numpy()))   # untimed warm-up of the whole path
-        barrier()
-        t0 = time.perf_counter()
-        # H2D references -> device initial guess (N1) -> solve every instance to descent >= -1e-6 -> D2H trajectories + stats,
-        # pipelined over independent sub-batches
-        _, _, st2 = pn.solve(xr_p.numpy(), ur_p.numpy(), dx0=dx0, out=(xs_t.numpy(), us_t.numpy()))
-        barrier()
-        t1 = time.perf_counter()
+
+        def timed(solve):
+            solve()          # untimed warm-up of the whole path
+            barrier()
+            t0 = time.perf_counter()
+            st2 = solve()
+            barrier()
+            wall = time.perf_counter() - t0
+            t1 = time.perf_counter()
+            g = D.gather_stats(st2, n_total)   # NCCL all_gather of the per-instance statistics (off the hot path), timed alone
+            gather_s = time.perf_counter() - t1
+            if dist is not None:
+                tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+                wall = float(tw[0])
+            return wall, g, gather_s
+
+        def describe(wall, g, gather_s, h2d, d2h, what):
+            tot = int(g["iters"].sum())
+            steps_e2e = int(g["iters"].max())
+            return {"value": tot / wall, "unit": UNIT, "h2d_bytes_per_step": h2d / max(steps_e2e, 1), "d2h_bytes_per_step": d2h / max(steps_e2e, 1),
+                    "h2d_bytes_per_solve": h2d, "d2h_bytes_per_solve": d2h,
+                    "wall_s": wall, "total_newton_iterations": tot, "solver_steps": steps_e2e,
+                    "converged": int((g["status"] == 1).sum()), "instances": n_total, "mean_iters": float(g["iters"].mean()),
+                    "stats_gather_s": gather_s, "chunks": args.chunks, "staggered_priorities": not args.no_stagger, "what": what}
+
+        # (a) headline: the randomisation parameters are the host inputs (16-56 B per instance); the scripts' reference generators run on
+        #     the device (bit-identical arrays, tests/test_gpu_parity_r2.py); states come back as the float32 values they are
+        f32_dl = args.precision == "f64" and args.state == "f32" and args.x_storage == "auto"
+        par_t = [pinned_like(np.asarray(p, dtype=np.float64)) for p in gen[1:]]
+        dx0_t = pinned_like(dx0) if dx0 is not None else None
+        xs32_t = torch.empty((n, 6, TT), dtype=torch.float32 if f32_dl else torch.float64, pin_memory=True)
+        us_t = torch.empty((n, 2, TT), dtype=torch.float64, pin_memory=True)
+        refs = (gen[0],) + tuple(p.numpy() for p in par_t)
+
+        def solve_generated():
+            return pn.solve(refs=refs, dx0=None if dx0_t is None else dx0_t.numpy(), out=(xs32_t.numpy(), us_t.numpy()),
+                            x_dtype=np.float32 if f32_dl else np.float64)[2]
+
+        wall, g, gs = timed(solve_generated)
+        h2d = (sum(p.numel() for p in par_t) * 8 + (dx0_t.numel() * 8 if dx0_t is not None else 0) + 3 * TT * 8 * args.chunks) * world
+        d2h = (xs32_t.numel() * xs32_t.element_size() + us_t.numel() * 8 + (n * 48 if f32_dl else 0)) * world + n_total * 28
+        e2e = describe(wall, g, gs, h2d, d2h,
+                       "PipelinedNewton.solve(refs=(kind, per-instance parameters) in pinned host memory): per sub-batch H2D of the parameters -> "
+                       "reference generators + initial guess on the device -> solve() to descent >= -1e-6 -> D2H of xx_star (%s), uu_star "
+                       "(float64) and the statistics into pinned host memory; sub-batches overlap copies with compute"
+                       % ("float32: lossless, the quantised states are float32 values" if f32_dl else "float64"))
+        del xs32_t
+        # (b) the same solve with the reference ARRAYS uploaded from the host and float64 results (the round-1 path, still available)
+        if not args.no_e2e_host:
+            xr_p, ur_p = pinned_like(xr), pinned_like(ur)
+            xs_t = torch.empty((n, 6, TT), dtype=torch.float64, pin_memory=True)
+
+            def solve_host():
+                return pn.solve(xr_p.numpy(), ur_p.numpy(), dx0=dx0, out=(xs_t.numpy(), us_t.numpy()))[2]
+
+            wall, g, gs = timed(solve_host)
+            e2e_host = describe(wall, g, gs, (xr.nbytes + ur.nbytes) * world, (xs_t.numel() + us_t.numel()) * 8 * world + n_total * 28,
+                                "PipelinedNewton.solve(xx_ref, uu_ref in pinned host memory): per sub-batch set_refs (H2D of 64 KB per instance) -> "
+                                "init_guess (device) -> solve() -> result()/stats() (D2H, float64)")
         pn.close()
-        wall = t1 - t0
-        g = D.gather_stats(st2, n_total)                 # NCCL all_gather of the per-instance statistics (off the hot path)
-        t2 = time.perf_counter()
-        tot = int(g["iters"].sum())
-        if dist is not None:
-            import torch
-            tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-            wall = float(tw[0])
-        steps_e2e = int(g["iters"].max())
-        h2d = (xr.nbytes + ur.nbytes) * world
-        d2h = (xs_t.numel() + us_t.numel()) * 8 * world + n_total * 28
-        e2e = {"value": tot / wall, "unit": UNIT, "h2d_bytes_per_step": h2d / max(steps_e2e, 1), "d2h_bytes_per_step": d2h / max(steps_e2e, 1),
-               "wall_s": wall, "total_newton_iterations": tot, "solver_steps": steps_e2e,
-               "converged": int((g["status"] == 1).sum()), "instances": n_total, "mean_iters": float(g["iters"].mean()),
-               "stats_gather_s": t2 - t1,
-               "chunks": args.chunks, "staggered_priorities": not args.no_stagger,
-               "what": "PipelinedNewton.solve(pinned host refs): per sub-batch set_refs (H2D) -> init_guess (device) -> solve() to descent >= -1e-6 "
-                       "-> result()/stats() (D2H to pinned host); sub-batches overlap copies with compute"}
 
     clocks = sampler.summary() if sampler else None
     cpu = None
@@ -417,18 +525,271 @@ def main():
         rate, nt, dt, its = cpu_port_rate(args.workload, args.cpu_sample, W, K, args.state)
         cpu = {"value": rate, "unit": UNIT, "cores": nt, "kind": "port",
                "sample": "%d instances x Newton iterations %d..%d of the same workload, C port of the reference (oracle/acoc_oracle.c), OpenMP over "
-                         "instances, %.1f s" % (args.cpu_sample, W, W + K - 1, dt)}
+                         "instances, %.1f s" % (args.cpu_sample, W, W + K - 1, dt),
+               "python_reference": python_reference_baseline(args.workload)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / max(K, 1),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-                "config": config_dict(args, n, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "active_after_timed_region": n_active, "instance_iterations_timed": its_done, "whole_solve": whole, "roofline": roofline, "fp64": fp64, "phase_ms": phases, "cpu_baseline": cpu,
-                "device": pkg.device_info(local)["name"], "device_bytes": device_bytes}
+                "config": config_dict(args, n, world), "clocks": clocks, "e2e": e2e, "e2e_host_refs": e2e_host, "gpu_launches": launches,
+                "active_after_timed_region": n_active, "instance_iterations_timed": its_done, "whole_solve": whole, "roofline": roofline, "fp64": fp64,
+                "phase_ms": phases, "cpu_baseline": cpu, "device": pkg.device_info(local)["name"], "device_bytes": device_bytes}
         emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# =====================================================================================================================
+# config 3: lqr_tracking of the saved optimum from 4096 perturbed initial states
+# =====================================================================================================================
+TRACK_UNIT = "rollout-steps/s"
+
+
+def track_inputs(n):
+    from aircraftoptimalcontrol_b200 import refgen
+    d = np.load(os.path.join(ROOT, "tests", "golden", "lqr_tracking.npz"))   # Data/xx_star.npy, uu_star.npy of the reference (inputs)
+    return d["xx_opt"], d["uu_opt"], refgen.config3_deltas(n), (d["Q"], d["R"], d["QT"])
+
+
+def track_config(n):
+    return {"workload": "BASELINE.json configs[2]: lqr_tracking.py LQR tracking of Data/xx_star.npy with %d perturbed initial states (instance 0: "
+                        "delta = 0.1, the rest U(-0.1,0.1)^6, seed 1234)" % n,
+            "instances_per_gpu": n, "TT": TT, "step": "one lqr_tracking_batch call: linearise along the nominal (TT points), ONE shared LQ solve, "
+            "%d closed-loop rollouts of %d steps" % (n, TT - 1), "l2": "outputs (%.0f MB) exceed the 126 MB L2; the shared gains are L1/L2 resident by design" % (n * 64e3 / 1e6)}
+
+
+def run_track(args, rank, world, local):
+    import aircraftoptimalcontrol_b200 as pkg
+    from aircraftoptimalcontrol_b200 import _lib
+    from aircraftoptimalcontrol_b200.aircraft_simplified import Dynamics
+    from aircraftoptimalcontrol_b200.lqr_tracking import lqr_tracking_batch
+    import ctypes as C
+    n = args.instances if args.instances_given else 4096
+    K, W = args.steps, max(args.warmup, 3)
+    xo, uo, deltas, (Q, R, QT) = track_inputs(n * world)
+    deltas = np.ascontiguousarray(deltas[rank::world])
+    dyn = Dynamics(device=local)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms3 = (C.c_double * 3)()
+    dev, walls = [], []
+    for k in range(W + K):
+        t0 = time.perf_counter()
+        lqr_tracking_batch(xo, uo, deltas, dyn=dyn, QQt=Q, RRt=R, QQT=QT)
+        t1 = time.perf_counter()
+        _lib.check(_lib.lib().acoc_last_pointwise_timing(C.addressof(ms3)))
+        if k >= W:
+            dev.append((ms3[0], ms3[1], ms3[2]))
+            walls.append(t1 - t0)
+    dev = np.array(dev)
+    units = n * (TT - 1)
+    ms = float(dev[:, 0].mean())
+    wall = float(np.mean(walls))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        t = torch.tensor([ms, wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, wall = float(t[0]), float(t[1])
+    peaks, peak_src = load_peaks()
+    trk_ms, lq_ms = float(dev[:, 2].mean()), float(dev[:, 1].mean())
+    out_bytes = units * 64.0   # x_t (float64 here) and u_t written once; the shared K_t, x_opt, u_opt stay in L1/L2
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = track_cpu(n, args.state)
+    if rank == 0:
+        line = {"metric": "closed_loop_rollout_steps_per_second", "value": units * world / (ms * 1e-3), "unit": TRACK_UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": track_config(n), "clocks": sampler.summary() if sampler else None,
+                "e2e": {"value": units * world / wall, "unit": TRACK_UNIT, "h2d_bytes_per_step": float(deltas.nbytes + xo.nbytes + uo.nbytes + 76 * 8),
+                        "d2h_bytes_per_step": float(n * 8 * TT * 8), "wall_s": wall,
+                        "what": "lqr_tracking_batch(xx_opt, uu_opt, delta) through the C ABI (acoc_lqr_tracking) with host numpy buffers"},
+                "gpu_launches": 3 * K,
+                "phase_ms": {"linearise_and_shared_lq_solve": lq_ms, "closed_loop_rollouts": trk_ms},
+                "roofline": {"kernel": "k_track", "bound": "hbm", "achieved": out_bytes / (trk_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": out_bytes / (trk_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": out_bytes,
+                             "note": "latency-bound by construction: %d instances are %d warps on 148 SMs, each walking 999 dependent steps (about 1 us per "
+                                     "step); the shared LQ solve is ONE thread's literal dense recursion (lqr_tracking.py:276).  The roofline "
+                                     "fraction says how far such a small batch is from bandwidth, not kernel quality" % (n, (n + 31) // 32),
+                             "share_of_step": trk_ms / max(ms, 1e-9)},
+                "cpu_baseline": cpu, "device": pkg.device_info(local)["name"]}
+        emit(line)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def track_cpu(n, state):
+    from oracle import corcl
+    corcl.build()
+    xo, uo, deltas, (Q, R, QT) = track_inputs(n)
+    nt = host_threads()
+    corcl.lqr_tracking(xo, uo, Q, R, QT, deltas[:nt], quant_f32=(state == "f32"), n_threads=nt)
+    t0 = time.perf_counter()
+    corcl.lqr_tracking(xo, uo, Q, R, QT, deltas, quant_f32=(state == "f32"), n_threads=nt)
+    dt = time.perf_counter() - t0
+    return {"value": n * (TT - 1) / dt, "unit": TRACK_UNIT, "cores": nt, "kind": "port",
+            "sample": "the whole workload (%d instances) with the C port of the reference (oracle/acoc_oracle.c), OpenMP over instances, %.2f s; the Python "
+                      "reference needs 1.43 s for ONE instance (SURVEY.md 8(a) a9)" % (n, dt)}
+
+
+def run_track_reference(args, rank):
+    if rank != 0:
+        return
+    n = args.instances if args.instances_given else 4096
+    c = track_cpu(n, args.state)
+    emit({"impl": "reference", "metric": "closed_loop_rollout_steps_per_second", "value": c["value"], "unit": TRACK_UNIT, "n_gpus": args.gpus, "steps": args.steps,
+          "warmup": args.warmup, "ms_per_step": 1e3 * n * (TT - 1) / c["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+          "data": "synthetic", "config": track_config(n), "cpu_baseline": c,
+          "e2e": {"value": c["value"], "unit": TRACK_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+
+
+# =====================================================================================================================
+# configs 1 and 2: one trajectory (latency)
+# =====================================================================================================================
+def single_inputs(workload):
+    d = np.load(os.path.join(ROOT, "tests", "golden", "newton_step_f32.npz" if workload == "single-step" else "newton_acro_f32.npz"))
+    return d
+
+
+def single_config(workload):
+    return {"workload": ("BASELINE.json configs[0]: main_newton_method.py step maneuver, single trajectory" if workload == "single-step" else
+                         "BASELINE.json configs[1]: acrobatic_newton.py acrobatic maneuver, single trajectory"),
+            "instances_per_gpu": 1, "TT": TT, "inputs": "xx_ref, uu_ref, xx_init, uu_init of the live reference run (tests/golden/*.npz)",
+            "step": "one Newton iteration of the single trajectory (iterations W..W+K-1)", "l2": "working set 0.4 MB: L2-resident by nature of the configuration"}
+
+
+def run_single(args, rank, world, local):
+    import aircraftoptimalcontrol_b200 as pkg
+    if rank != 0:   # a single trajectory does not shard: replicas would only repeat rank 0
+        return
+    d = single_inputs(args.workload)
+    K, W = args.steps, args.warmup
+    iters_ref = int(d["iters"])
+    K = min(K, iters_ref - W - 1)
+    sampler = ClockSampler(local)
+    sampler.start()
+    with pkg.BatchedNewton(1, TT=TT, device=local, state=args.state, refs_shared=True, armijo=args.armijo, precision=args.precision) as bn:
+        bn.set_weights(d["Q"], d["R"], d["QT"])
+        bn.set_refs(d["xx_ref"], d["uu_ref"])
+        bn.set_init(d["xx_init"][None], d["uu_init"][None])
+        bn.iterate(W, count_active=False)
+        bn.iterate(K, count_active=False)
+        tm = bn.timing()
+        ms, launches = tm["total_ms"], tm["launches"]
+        solves = []
+        for _ in range(3):
+            bn.set_init(d["xx_init"][None], d["uu_init"][None])
+            tot = bn.solve()
+            solves.append(bn.timing()["total_ms"])
+        # end to end through the drop-in signature: host arrays in, optimize()'s result out
+        walls = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            bn.set_refs(d["xx_ref"], d["uu_ref"])
+            bn.set_init(d["xx_init"][None], d["uu_init"][None])
+            tot = bn.solve()
+            bn.result()
+            walls.append(time.perf_counter() - t0)
+    cpu = None
+    if not args.no_cpu:
+        cpu = single_cpu(args.workload, W, K, args.state)
+    peaks, peak_src = load_peaks()
+    per_it = ms / K
+    line = {"metric": METRIC, "value": K / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": per_it, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": single_config(args.workload),
+            "clocks": sampler.summary(),
+            "e2e": {"value": tot / min(walls), "unit": UNIT, "h2d_bytes_per_step": float(2 * 8 * 8 * TT) / tot, "d2h_bytes_per_step": float(8 * 8 * TT) / tot,
+                    "wall_s": min(walls), "total_newton_iterations": int(tot),
+                    "what": "set_refs + set_init (H2D) -> solve() to descent >= -1e-6 -> result() (D2H), host numpy buffers, best of 3"},
+            "gpu_launches": launches,
+            "whole_solve": {"device_ms": min(solves), "total_newton_iterations": int(tot), "reference_iterations": iters_ref, "value": tot / (min(solves) * 1e-3), "unit": UNIT},
+            "roofline": {"kernel": "k_backward_tma + k_search_fused (one warp / 12 warps)", "bound": "hbm",
+                         "achieved": (TT - 1) * (BYTES["backward"] + BYTES["forward"] + 11 * BYTES["candidate"]) / (per_it * 1e-3) / 1e9,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (TT - 1) * (BYTES["backward"] + BYTES["forward"] + 11 * BYTES["candidate"]) / (per_it * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "one trajectory is one warp lane: the iteration is two dependent sweeps of 999 sequential steps, i.e. pure arithmetic "
+                                 "latency (%.2f us per backward+search step pair); no roofline is within reach of a single trajectory" % (per_it * 1e3 / (TT - 1))},
+            "cpu_baseline": cpu, "device": pkg.device_info(local)["name"]}
+    emit(line)
+
+
+def single_cpu(workload, W, K, state):
+    from oracle import corcl
+    corcl.build()
+    d = single_inputs(workload)
+    a = (d["xx_ref"], d["uu_ref"], d["xx_init"], d["uu_init"], d["Q"], d["R"], d["QT"])
+    corcl.newton(*a, quant_f32=(state == "f32"), n_iters_cap=1)
+    t0 = time.perf_counter()
+    if W:
+        corcl.newton(*a, quant_f32=(state == "f32"), n_iters_cap=W)
+    t1 = time.perf_counter()
+    corcl.newton(*a, quant_f32=(state == "f32"), n_iters_cap=W + K)
+    t2 = time.perf_counter()
+    dt = (t2 - t1) - (t1 - t0 if W else 0.0)
+    return {"value": K / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "Newton iterations %d..%d of the same trajectory, C port of the reference (oracle/acoc_oracle.c), one thread, %.3f s" % (W, W + K - 1, dt),
+            "python_reference": python_reference_baseline(workload)}
+
+
+def run_single_reference(args, rank):
+    if rank != 0:
+        return
+    d = single_inputs(args.workload)
+    K = min(args.steps, int(d["iters"]) - args.warmup - 1)
+    c = single_cpu(args.workload, args.warmup, K, args.state)
+    emit({"impl": "reference", "metric": METRIC, "value": c["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": args.warmup,
+          "ms_per_step": 1e3 / c["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+          "config": single_config(args.workload), "cpu_baseline": c,
+          "e2e": {"value": c["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+
+
+def main():
+    os.dup2(2, 1)  # anything native code prints to fd 1 (e.g. the NCCL version banner) lands on stderr
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--instances", type=int, default=None, help="instances per GPU (default 65536; 4096 for --workload track)")
+    ap.add_argument("--workload", default="step", choices=["step", "acro", "track", "single-step", "single-acro"])
+    ap.add_argument("--armijo", default="lazy", choices=["lazy", "speculative"])
+    ap.add_argument("--state", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"], help="f64 = the parity path (default); f32 = the optional FP32 mode")
+    ap.add_argument("--x-storage", default="auto", choices=["auto", "f64"], help="f64: keep float32-valued states in float64 buffers (A/B)")
+    ap.add_argument("--no-tma", action="store_true", help="plain-load sweeps instead of the TMA rings (A/B)")
+    ap.add_argument("--no-split", action="store_true", help="one stream for the whole batch instead of the tile-range sweep (A/B)")
+    ap.add_argument("--no-fused", action="store_true", help="separate LQ forward pass / candidate sweeps instead of the fused ones (A/B)")
+    ap.add_argument("--cpu-sample", type=int, default=16384, help="instances of the bounded CPU sample (about 10 s of work on 16 host threads)")
+    ap.add_argument("--chunks", type=int, default=4, help="sub-batches of the pipelined end-to-end solve")
+    ap.add_argument("--no-stagger", action="store_true", help="end-to-end leg: same stream priority for every sub-batch (A/B)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-host", action="store_true", help="skip the second end-to-end leg (reference arrays uploaded from the host)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    args.instances_given = args.instances is not None
+    if args.instances is None:
+        args.instances = 65536
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.workload == "track":
+        return run_track_reference(args, rank) if args.impl == "reference" else run_track(args, rank, world, local)
+    if args.workload.startswith("single"):
+        return run_single_reference(args, rank) if args.impl == "reference" else run_single(args, rank, world, local)
+    if args.impl == "reference":
+        return run_reference_arm(args, rank, world)
+    run_batched(args, rank, world, local)
 
 
 if __name__ == "__main__":

@@ -131,6 +131,10 @@ int acoc_lqr_tracking(int device, int n, int TT, const double* params, int state
                       const double* R, const double* QT, const double* xx_opt, const double* uu_opt,
                       const double* delta, double* xx_reg, double* uu_reg, double* K);
 
+/* Device time (CUDA events, ms) of the kernels of this thread's last acoc_lqr_tracking call: ms[0] total, ms[1] linearisation along
+ * the nominal + the shared LQ solve (k_step_batch + k_lq_dense<6>), ms[2] the closed-loop rollouts (k_track). */
+int acoc_last_pointwise_timing(double* ms);
+
 /* ------------------------------------------------- batched Newton context ---------------------------- */
 /* One context = one GPU, one CUDA stream, N OCP instances with horizon TT held struct-of-arrays in HBM.
  * A context is not thread-safe; different contexts are independent. */
@@ -149,6 +153,16 @@ int acoc_set_weights(acoc_ctx* ctx, const double* Q, const double* R, const doub
 int acoc_set_options(acoc_ctx* ctx, const acoc_newton_options* opt);                      /* NewtonMethod(...) */
 /* xx_ref (N,6,TT) / uu_ref (N,2,TT), or (6,TT) / (2,TT) when the context was created with ACOC_REFS_SHARED */
 int acoc_set_refs(acoc_ctx* ctx, const double* xx_ref, const double* uu_ref);
+/* The reference generators of the scripts, on the device (main_newton_method.py:96-142, acrobatic_newton.py:99-154): per-instance
+ * xx_ref / uu_ref are built in HBM from per-instance parameters zf[N] (final / bump height), vx[N] (= (xf - x0)/tf) and shared time
+ * bases tt[TT], zshape[TT], vshape[TT] (NULL: V_ref = xconst[2]) that the caller computed with the scripts' own numpy code:
+ *   X = 0 + vx*tt,  Z = 0 + zshape*(zf - 0),  V = ((vshape*zf)**2 + vx**2)**0.5,  theta, q, gamma = xconst[3..5],  uu_ref = uconst[0..1]
+ * in the scripts' operation order, so the arrays are bit-identical to what the scripts build on the host and acoc_set_refs would
+ * upload (16 B per instance cross the bus instead of 64 KB).  Not for ACOC_REFS_SHARED contexts. */
+int acoc_set_refs_generated(acoc_ctx* ctx, const double* tt, const double* zshape, const double* vshape, const double* zf,
+                            const double* vx, const double* xconst, const double* uconst);
+/* the references held by the context, in acoc_set_refs' layout (either pointer may be NULL) */
+int acoc_get_refs(acoc_ctx* ctx, double* xx_ref, double* uu_ref);
 /* xx_init (N,6,TT), uu_init (N,2,TT): NewtonMethod.optimize(xx_init, uu_init, tf, dt), optcon.py:341, :395-398.
  * Resets the Newton state (iteration counter, histories). */
 int acoc_set_init(acoc_ctx* ctx, const double* xx_init, const double* uu_init);
@@ -171,6 +185,11 @@ int acoc_sync(acoc_ctx* ctx);
 
 /* What NewtonMethod.optimize returns (optcon.py:503-505): iterate kk-1 with uu[:, -1] = uu[:, -2]. */
 int acoc_get_result(acoc_ctx* ctx, double* xx_star, double* uu_star);
+/* The same result with the states as float32 (N,6,TT): LOSSLESS whenever the context keeps its state iterates as float (float32
+ * state quantisation of aircraft_simplified.py:300, the default): every x_t, t >= 1, is a float32 value.  Column t = 0 holds
+ * float32(x0); the exact float64 x0 = xx_init[:,0] (optcon.py:398) is returned in x0 (N,6) when non-NULL.  uu_star stays float64.
+ * ACOC_ERR_STATE if the context holds float64 states (ACOC_STATE_F64, ACOC_X_F64, or acoc_set_init with non-float32 states). */
+int acoc_get_result_f32(acoc_ctx* ctx, float* xx_star, double* uu_star, double* x0);
 /* which: 0 = the newest iterate (last get_update), 1 = the one before it. */
 int acoc_get_iterate(acoc_ctx* ctx, int which, double* xx, double* uu);
 /* Descent direction of the last iteration: deltau (N,2,TT) (optcon.py:468).  deltau and the gains are per-iteration

@@ -225,3 +225,87 @@ def test_options_can_be_changed_without_growing_the_context(gpu):
         for _ in range(3):
             L.check(L.lib().acoc_set_options(bn._h, C.addressof(bn.opts)))
         assert bn.device_bytes == b0
+
+
+def test_device_reference_generators_bit_identical(gpu):
+    """acoc_set_refs_generated (main_newton_method.py:96-142, acrobatic_newton.py:99-154 on the device) vs the host arrays of
+    refgen (pinned bit for bit to the scripts' globals in tests/test_refgen.py): identical references, hence identical solves."""
+    from aircraftoptimalcontrol_b200 import refgen
+    n, TT = 200, 1000
+    zf, xf = refgen.config4_params(n, 2024)
+    xr, ur = refgen.step_problem(xf, zf, TT=TT)
+    with gpu.BatchedNewton(n, TT=TT, armijo="lazy") as bn:
+        bn.set_refs_step(zf, xf)
+        gx, gu = bn.refs()
+        assert np.array_equal(gx, xr) and np.array_equal(gu, ur)
+    dx0, zf5 = refgen.config5_params(n, 7)
+    xr5, ur5 = refgen.acrobatic_problem(zf5, TT=TT)
+    with gpu.BatchedNewton(n, TT=TT, armijo="lazy") as bn:
+        bn.set_refs_acrobatic(zf5)
+        gx, gu = bn.refs()
+        assert np.array_equal(gx, xr5) and np.array_equal(gu, ur5)
+    # other horizons / durations
+    for TT2, tf in ((37, 0.037), (300, 0.3)):
+        a, b = refgen.step_problem(xf[:40], zf[:40], tf=tf, TT=TT2)
+        with gpu.BatchedNewton(40, TT=TT2) as bn:
+            bn.set_refs_step(zf[:40], xf[:40], tf=tf)
+            gx, gu = bn.refs()
+        assert np.array_equal(gx, a) and np.array_equal(gu, b)
+    with gpu.BatchedNewton(4, TT=50, refs_shared=True) as bn:
+        with pytest.raises(ValueError):
+            bn.set_refs_step(zf[:4], xf[:4])
+
+
+def test_float32_state_download_is_lossless(gpu):
+    """acoc_get_result_f32: the states of a float32-quantised solve downloaded as float32 equal the float64 download exactly (t >= 1),
+    column 0 is float32(x0) with the exact x0 returned beside it; float64-state contexts refuse."""
+    from aircraftoptimalcontrol_b200 import _lib, refgen
+    n, TT = 300, 200
+    xr, ur, Q, R, QT = _short_batch(n, TT, 41)
+    dx0 = np.random.default_rng(2).normal(size=(n, 6)) * np.array([.05, .05, .2, .02, .05, .02])
+    with gpu.BatchedNewton(n, TT=TT, armijo="lazy", max_iters=9) as bn:   # mixed result slots: some converge, some hit max_iters
+        bn.set_weights(Q, R, QT)
+        bn.set_refs(xr, ur)
+        bn.init_guess(dx0=dx0)
+        bn.solve()
+        x64, u64 = bn.result()
+        x32, u32, x0 = bn.result_f32()
+    assert x32.dtype == np.float32 and np.array_equal(x32[:, :, 1:].astype(np.float64), x64[:, :, 1:]) and np.array_equal(u32, u64)
+    assert np.array_equal(x0, xr[:, :, 0] + dx0) and np.array_equal(x0, x64[:, :, 0])
+    assert np.array_equal(x32[:, :, 0], x0.astype(np.float32))
+    with gpu.BatchedNewton(8, TT=TT, state="f64") as bn:
+        bn.set_weights(Q, R, QT)
+        bn.set_refs(xr[:8], ur[:8])
+        bn.init_guess()
+        bn.iterate(1)
+        with pytest.raises(_lib.AcocError, match="float32"):
+            bn.result_f32()
+
+
+def test_pipelined_generated_refs_and_f32_download_equal_host_path(gpu):
+    """PipelinedNewton with refs=("step"|"acrobatic", ...) and x_dtype=float32 (16 B per instance up, 40 B per step down) returns
+    exactly what the host-buffer path returns."""
+    from aircraftoptimalcontrol_b200 import refgen
+    n, TT = 400, 300
+    rng = np.random.default_rng(5)
+    zf, xf = rng.uniform(1.5, 3.5, n), rng.uniform(14, 18, n)
+    xr, ur = refgen.step_problem(xf, zf, tf=0.3, TT=TT)
+    Q, R, QT = refgen.weights("step")
+    with gpu.PipelinedNewton(n, n_chunks=3, TT=TT, armijo="lazy") as pn:
+        pn.set_weights(Q, R, QT)
+        xa, ua, sa = pn.solve(xr, ur)
+        xb, ub, sb = pn.solve(refs=("step", zf, xf, 0.3), x_dtype=np.float32)
+    assert np.array_equal(xa[:, :, 1:], xb[:, :, 1:].astype(np.float64)) and np.array_equal(ua, ub)
+    assert np.array_equal(sb["x0"], xa[:, :, 0])
+    for k in ("iters", "status", "J", "descent"):
+        assert np.array_equal(sa[k], sb[k]), k
+    dx0 = rng.normal(size=(n, 6)) * np.array([.05, .05, .2, .02, .05, .02])
+    zf5 = rng.uniform(2.0, 3.4, n)
+    xr5, ur5 = refgen.acrobatic_problem(zf5, tf=0.3, TT=TT)
+    Q, R, QT = refgen.weights("acro")
+    with gpu.PipelinedNewton(n, n_chunks=2, TT=TT, armijo="lazy", max_iters=12) as pn:
+        pn.set_weights(Q, R, QT)
+        xa, ua, sa = pn.solve(xr5, ur5, dx0=dx0)
+        xb, ub, sb = pn.solve(refs=("acrobatic", zf5, 18, 0.3), dx0=dx0, x_dtype=np.float32)
+    assert np.array_equal(xa[:, :, 1:], xb[:, :, 1:].astype(np.float64)) and np.array_equal(ua, ub)
+    assert np.array_equal(sa["iters"], sb["iters"]) and np.array_equal(sa["J"], sb["J"])

@@ -41,3 +41,26 @@ def test_tracking_weights():
     d = golden("lqr_tracking.npz")
     Q, R, QT = refgen.weights("track")
     assert np.array_equal(Q, d["Q"]) and np.array_equal(R, d["R"]) and np.array_equal(QT, d["QT"])
+
+
+def test_generator_formula_of_the_device_kernel_matches_the_scripts():
+    """acoc_set_refs_generated builds X = 0 + vx*tt, Z = 0 + zshape*(zf - 0), V = sqrt((vshape*zf)^2 + vx^2) from refgen's shared time
+    bases; with this numpy those expressions are bit-identical to the scripts' arrays (`**2` is a multiply, `**0.5` a sqrt)."""
+    rng = np.random.default_rng(0)
+    n = 512
+    zf, xf = rng.uniform(1.5, 3.5, n), rng.uniform(14, 18, n)
+    xr, ur = refgen.step_problem(xf, zf)
+    tt, s, ds = refgen.step_bases()
+    vx = (xf - 0) / 1
+    zd = ds * (zf[:, None] - 0.0)
+    assert np.array_equal(0.0 + vx[:, None] * tt, xr[:, 0]) and np.array_equal(0.0 + s * (zf[:, None] - 0.0), xr[:, 1])
+    assert np.array_equal(np.sqrt(zd * zd + (vx * vx)[:, None]), xr[:, 2]) and not xr[:, 3:].any()
+    assert np.all(ur[:, 0] == refgen.STEP_CONST[1][0]) and not ur[:, 1].any()
+    zf = rng.uniform(2.0, 3.4, n)
+    xr, ur = refgen.acrobatic_problem(zf)
+    tt, bump = refgen.acrobatic_bases()
+    xc, uc = refgen.ACRO_CONST
+    assert np.array_equal(0.0 + bump * (zf[:, None] - 0.0), xr[:, 1]) and np.array_equal(np.broadcast_to(0.0 + 18.0 * tt, (n, 1000)), xr[:, 0])
+    for c in (2, 3, 4, 5):
+        assert np.all(xr[:, c] == xc[c])
+    assert np.all(ur[:, 0] == uc[0]) and np.all(ur[:, 1] == uc[1])
