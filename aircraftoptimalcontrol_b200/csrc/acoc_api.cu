@@ -124,20 +124,7 @@ __global__ void __launch_bounds__(128) k_traj_cost(ProblemT<F> P, const XT* __re
 // remaining Armijo candidates.  Threads are therefore mapped to instances through a compacted, ORDERED list of
 // groups of G = 2^shift consecutive instances that still contain work.  G = 32 (one tile = one warp = one TMA block) for the
 // sweeps; G = 1 for the compute-bound candidate rollouts.
-struct WorkList {
-    const int* groups;  // nullptr: identity (thread j -> instance j)
-    const int* count;   // number of valid groups (device memory)
-    int shift;
-};
-
-__device__ __forceinline__ int work_instance(const WorkList& L, int j, int N)
-{
-    if (!L.groups) return j < N ? j : -1;
-    const int g = j >> L.shift;
-    if (g >= *L.count) return -1;
-    const int i = (L.groups[g] << L.shift) + (j & ((1 << L.shift) - 1));
-    return i < N ? i : -1;
-}
+// (struct WorkList / work_instance: acoc_tma.cuh)
 
 // One CTA, ordered stream compaction.  mode 0: group alive iff any status[i] == ST_ACTIVE; mode 1: iff any flag[i] != 0.
 // Every thread owns a contiguous range of groups: count, one block-wide exclusive scan, write (two passes over the flags, which
@@ -726,7 +713,7 @@ struct acoc_ctx {
     double* stage = nullptr;  // device staging for layout conversion (always float64: the host side of the ABI)
     size_t stage_doubles = 0;
     int *need = nullptr, *need2 = nullptr, *counters = nullptr, *slot_tmp = nullptr;
-    int *act_groups = nullptr, *need_groups = nullptr;  // work lists (see WorkList); counts live in counters[1], counters[2]
+    int *act_groups = nullptr, *need_groups = nullptr, *need_groups2 = nullptr;  // work lists (see WorkList); counts live in counters[1], counters[2]
     long long* iters_sum = nullptr;
     std::vector<std::pair<void*, size_t>> allocs;
     unsigned long long bytes = 0;
@@ -1182,6 +1169,7 @@ int acoc_ctx_create(int device, int n_instances, int TT, unsigned flags, acoc_ct
                                                                // [4 + MAX_RANGES + r] second-stage need list of range r
     if (!rc) rc = dalloc(c, &c->act_groups, Np);
     if (!rc) rc = dalloc(c, &c->need_groups, Np);
+    if (!rc) rc = dalloc(c, &c->need_groups2, Np);
     if (!rc) rc = dalloc(c, &c->iters_sum, 2);
     // staging: up to 256 MiB or the whole batch, whichever is smaller (at least one instance of 6*TT doubles)
     c->stage_doubles = std::max<size_t>(16 * T, std::min<size_t>((size_t)n_instances * 16 * T, (size_t)32 << 20));
@@ -1447,16 +1435,18 @@ static int launch_backward_t(acoc_ctx* c, bool exact)
         const size_t sm = WarpRing<BWD_STAGES, BwdStage<F, XT>::BYTES>::smem_bytes(BWD_THREADS / 32);
         const int gs = sweep_grid(c, BWD_THREADS);
         cudaStream_t st = sweep_stream(c);
-        if (exact) {
-            TRY(prefer_smem(k_backward_tma<true, F, XT>));
-            k_backward_tma<true, F, XT><<<gs, BWD_THREADS, sm, st>>>(P, tile_list(c), X, U, (F*)c->KSG, c->S.status, c->S.n_reg);
-        } else {
-            TRY(prefer_smem(k_backward_tma<false, F, XT>));
-            k_backward_tma<false, F, XT><<<gs, BWD_THREADS, sm, st>>>(P, tile_list(c), X, U, (F*)c->KSG, c->S.status, c->S.n_reg);
-        }
+        const bool dg = c->P.W.diag != 0;
+#define ACOC_BWD_LAUNCH(EX, DG)                                                                                                  \
+        do {                                                                                                                     \
+            TRY(prefer_smem(k_backward_tma<EX, F, XT, DG>));                                                                     \
+            k_backward_tma<EX, F, XT, DG><<<gs, BWD_THREADS, sm, st>>>(P, tile_list(c), X, U, (F*)c->KSG, c->S.status, c->S.n_reg); \
+        } while (0)
+        if (exact) { if (dg) ACOC_BWD_LAUNCH(true, 1); else ACOC_BWD_LAUNCH(true, 0); }
+        else { if (dg) ACOC_BWD_LAUNCH(false, 1); else ACOC_BWD_LAUNCH(false, 0); }
+#undef ACOC_BWD_LAUNCH
         if (!c->bwd_wave_ctas) {  // resident CTAs of this sweep on the whole device (for the two-range split of acoc_newton_iterate)
             int nb = 0, sms = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_backward_tma<true, F, XT>, BWD_THREADS, sm));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_backward_tma<true, F, XT, 1>, BWD_THREADS, sm));
             CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
             c->bwd_wave_ctas = std::max(1, nb * sms);
             c->sm_count = sms;
@@ -1535,15 +1525,16 @@ static int launch_cand0_t(acoc_ctx* c)
         const size_t sm = WarpRing<ROLL_STAGES, RollStage<F>::BYTES>::smem_bytes(ROLL_THREADS / 32);
         const int g = sweep_grid(c, ROLL_THREADS);
         cudaStream_t st = sweep_stream(c);
-        if (c->P.q32) {
-            TRY(prefer_smem(k_rollout_write_tma<true, F, XT, 0>));
-            k_rollout_write_tma<true, F, XT, 0><<<g, ROLL_THREADS, sm, st>>>(P, tile_list(c), c->O, c->S, U, DU, c->cand_steps, (XT*)c->X[nxt],
-                                                                            (F*)c->U[nxt], nullptr, c->kk, 0);
-        } else {
-            TRY(prefer_smem(k_rollout_write_tma<false, F, XT, 0>));
-            k_rollout_write_tma<false, F, XT, 0><<<g, ROLL_THREADS, sm, st>>>(P, tile_list(c), c->O, c->S, U, DU, c->cand_steps, (XT*)c->X[nxt],
-                                                                             (F*)c->U[nxt], nullptr, c->kk, 0);
-        }
+        const bool dg = c->P.W.diag != 0;
+#define ACOC_RW0_LAUNCH(Q, DG)                                                                                                    \
+        do {                                                                                                                      \
+            TRY(prefer_smem(k_rollout_write_tma<Q, F, XT, 0, DG>));                                                               \
+            k_rollout_write_tma<Q, F, XT, 0, DG><<<g, ROLL_THREADS, sm, st>>>(P, tile_list(c), c->O, c->S, U, DU, c->cand_steps, (XT*)c->X[nxt], \
+                                                                             (F*)c->U[nxt], nullptr, c->kk, 0);                     \
+        } while (0)
+        if (c->P.q32) { if (dg) ACOC_RW0_LAUNCH(true, 1); else ACOC_RW0_LAUNCH(true, 0); }
+        else { if (dg) ACOC_RW0_LAUNCH(false, 1); else ACOC_RW0_LAUNCH(false, 0); }
+#undef ACOC_RW0_LAUNCH
     } else
         LAUNCH_Q32(c->P.q32, k_candidate0_write, (F, XT), (Np + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, c->stream, P, act_list(c), U, DU,
                    c->cand_steps, (XT*)c->X[nxt], (F*)c->U[nxt], c->S.status, c->S.Jcand);
@@ -1567,20 +1558,63 @@ static int launch_forward_cand0_t(acoc_ctx* c)
     const size_t sm = WarpRing<FC_STAGES, FwdCandStage<F, XT>::BYTES>::smem_bytes(FWD_THREADS / 32);
     const int g = sweep_grid(c, FWD_THREADS);
     cudaStream_t st = sweep_stream(c);
-    if (c->P.q32) {
-        TRY(prefer_smem(k_forward_cand0_tma<true, F, XT>));
-        k_forward_cand0_tma<true, F, XT><<<g, FWD_THREADS, sm, st>>>(P, tile_list(c), c->S, (const XT*)c->X[cur], (const F*)c->U[cur], (const F*)c->KSG,
-                                                                    (F*)c->DU, c->cand_steps, (XT*)c->X[nxt], (F*)c->U[nxt]);
-    } else {
-        TRY(prefer_smem(k_forward_cand0_tma<false, F, XT>));
-        k_forward_cand0_tma<false, F, XT><<<g, FWD_THREADS, sm, st>>>(P, tile_list(c), c->S, (const XT*)c->X[cur], (const F*)c->U[cur], (const F*)c->KSG,
-                                                                     (F*)c->DU, c->cand_steps, (XT*)c->X[nxt], (F*)c->U[nxt]);
-    }
+    const bool dg = c->P.W.diag != 0;
+#define ACOC_FC_LAUNCH(Q, DG)                                                                                                       \
+    do {                                                                                                                            \
+        TRY(prefer_smem(k_forward_cand0_tma<Q, F, XT, DG>));                                                                        \
+        k_forward_cand0_tma<Q, F, XT, DG><<<g, FWD_THREADS, sm, st>>>(P, tile_list(c), c->S, (const XT*)c->X[cur], (const F*)c->U[cur],  \
+                                                                     (const F*)c->KSG, (F*)c->DU, c->cand_steps, (XT*)c->X[nxt], (F*)c->U[nxt]); \
+    } while (0)
+    if (c->P.q32) { if (dg) ACOC_FC_LAUNCH(true, 1); else ACOC_FC_LAUNCH(true, 0); }
+    else { if (dg) ACOC_FC_LAUNCH(false, 1); else ACOC_FC_LAUNCH(false, 0); }
+#undef ACOC_FC_LAUNCH
     CK(cudaGetLastError());
     ++c->launches;
     return 0;
 }
 static int launch_forward_cand0(acoc_ctx* c) { return DISPATCH_FX(c, launch_forward_cand0_t, c); }
+
+// candidates c0..c1-1 of the instances on a per-instance work list (n list slots at most): the ring kernel of acoc_tma.cuh (one
+// producer warp gathers the inputs for all candidate warps of a CTA) or, with ACOC_NO_TMA, the plain-load kernel
+constexpr int LIST_ROWS = 9;  // candidate warps per CTA of k_candidates_list (more candidates: several passes)
+template <typename K>
+static int list_smem_attr(K kernel, size_t bytes)
+{
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (bytes > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+static bool list_ring(const acoc_ctx* c)
+{
+    static const bool off = getenv("ACOC_NO_LIST_RING") != nullptr;  // tuning experiments
+    return use_tma(c) && !off;
+}
+template <typename F>
+static int launch_list_candidates(acoc_ctx* c, const WorkList& L, int n, int c0, int c1, cudaStream_t st)
+{
+    const int cur = c->kk % 3;
+    const ProblemT<F> P = prob<F>(c);
+    const F *U = (const F*)c->U[cur], *DU = (const F*)c->DU;
+    if (list_ring(c)) {
+        const int rows = std::min(c1 - c0, LIST_ROWS);
+        const dim3 blk(TILE, rows + 1);
+        const size_t sm = candidates_list_smem<F>();
+        const bool dg = c->P.W.diag != 0, sh = c->P.ref_shared != 0;
+#define ACOC_CL_LAUNCH(Q, DG, SH)                                                                                                   \
+        do {                                                                                                                        \
+            TRY(list_smem_attr(k_candidates_list<Q, F, LIST_ROWS, DG, SH>, sm));                                                    \
+            k_candidates_list<Q, F, LIST_ROWS, DG, SH><<<(n + TILE - 1) / TILE, blk, sm, st>>>(P, L, U, DU, c->cand_steps, c0, c1, c->S.Jcand); \
+        } while (0)
+#define ACOC_CL_LAUNCH2(Q, DG) do { if (sh) ACOC_CL_LAUNCH(Q, DG, true); else ACOC_CL_LAUNCH(Q, DG, false); } while (0)
+        if (c->P.q32) { if (dg) ACOC_CL_LAUNCH2(true, 1); else ACOC_CL_LAUNCH2(true, 0); }
+        else { if (dg) ACOC_CL_LAUNCH2(false, 1); else ACOC_CL_LAUNCH2(false, 0); }
+#undef ACOC_CL_LAUNCH2
+#undef ACOC_CL_LAUNCH
+    } else
+        LAUNCH_CAND(c->P.q32, F, (n + CAND_TILE - 1) / CAND_TILE, std::min(c1 - c0, CAND_MAXY), st, P, L, U, DU, c->cand_steps, c0, c1, c->S.status, c->S.Jcand);
+    CK(cudaGetLastError());
+    return 0;
+}
 
 // Armijo after candidate 0 (lazy) or all candidates at once (speculative): fills S.step and the history row kk.  Returns through
 // *lazy_only whether the update may skip instances whose candidate 0 is already in the next slot.
@@ -1606,19 +1640,16 @@ static int launch_armijo_t(acoc_ctx* c, bool* lazy_only)
         // few candidates (mean 2.6 / 1.9 candidates in iterations 0 / 1 of config 4): candidates 1..3 first, the rest only where
         // those failed too.  Later (float32-noise phase) the search usually runs to the end and one round of 1..9 is cheaper.
         const int split = (c->kk <= c->O.exact_after && nc > 5) ? 4 : nc;
-        LAUNCH_CAND(c->P.q32, F, (n + CAND_TILE - 1) / CAND_TILE, std::min(split - 1, CAND_MAXY), st, P, L, U, DU, c->cand_steps, 1, split, c->S.status,
-                    c->S.Jcand);
-        CK(cudaGetLastError());
+        TRY(launch_list_candidates<F>(c, L, n, 1, split, st));
         if (split < nc) {
             k_lazy_need<<<(n + 255) / 256, 256, 0, st>>>(c->O, c->S, c->cand_steps, i0, i1, Np, split, c->need2);
             CK(cudaGetLastError());
             int* cnt2 = scope_need2_count(c);  // (a counter of its own: the first-stage count tells the host how many searches failed candidate 0)
             L.count = cnt2;
-            k_build_list<<<1, 1024, 0, st>>>(c->need2, 1, n, 0, c->need_groups + i0, cnt2, i0);
+            L.groups = c->need_groups2 + i0;  // (the first-stage list stays: the update rolls exactly those instances)
+            k_build_list<<<1, 1024, 0, st>>>(c->need2, 1, n, 0, c->need_groups2 + i0, cnt2, i0);
             CK(cudaGetLastError());
-            LAUNCH_CAND(c->P.q32, F, (n + CAND_TILE - 1) / CAND_TILE, std::min(nc - split, CAND_MAXY), st, P, L, U, DU, c->cand_steps, split, nc,
-                        c->S.status, c->S.Jcand);
-            CK(cudaGetLastError());
+            TRY(launch_list_candidates<F>(c, L, n, split, nc, st));
             c->launches += 3;
         }
         *lazy_only = true;
@@ -1645,17 +1676,17 @@ static int launch_update_t(acoc_ctx* c, bool lazy_only, bool bookkeeping, bool u
         const size_t sm = WarpRing<ROLL_STAGES, RollStage<F>::BYTES>::smem_bytes(ROLL_THREADS / 32);
         const int g = sweep_grid(c, ROLL_THREADS);
         const int* only = lazy_only ? c->need : nullptr;
-        if (c->P.q32) {
-            TRY(prefer_smem(k_rollout_write_tma<true, F, XT, 1>));
-            k_rollout_write_tma<true, F, XT, 1><<<g, ROLL_THREADS, sm, sweep_stream(c)>>>(prob<F>(c), tile_list(c, use_list), c->O, c->S, (const F*)c->U[cur],
-                                                                                   (const F*)c->DU, c->cand_steps, (XT*)c->X[nxt], (F*)c->U[nxt], only,
-                                                                                   c->kk, bookkeeping ? 1 : 0);
-        } else {
-            TRY(prefer_smem(k_rollout_write_tma<false, F, XT, 1>));
-            k_rollout_write_tma<false, F, XT, 1><<<g, ROLL_THREADS, sm, sweep_stream(c)>>>(prob<F>(c), tile_list(c, use_list), c->O, c->S, (const F*)c->U[cur],
-                                                                                    (const F*)c->DU, c->cand_steps, (XT*)c->X[nxt], (F*)c->U[nxt], only,
-                                                                                    c->kk, bookkeeping ? 1 : 0);
-        }
+        const bool dg = c->P.W.diag != 0;
+#define ACOC_RW1_LAUNCH(Q, DG)                                                                                                      \
+        do {                                                                                                                        \
+            TRY(prefer_smem(k_rollout_write_tma<Q, F, XT, 1, DG>));                                                                 \
+            k_rollout_write_tma<Q, F, XT, 1, DG><<<g, ROLL_THREADS, sm, sweep_stream(c)>>>(prob<F>(c), tile_list(c, use_list), c->O, c->S,        \
+                                                                                          (const F*)c->U[cur], (const F*)c->DU, c->cand_steps,   \
+                                                                                          (XT*)c->X[nxt], (F*)c->U[nxt], only, c->kk, bookkeeping ? 1 : 0); \
+        } while (0)
+        if (c->P.q32) { if (dg) ACOC_RW1_LAUNCH(true, 1); else ACOC_RW1_LAUNCH(true, 0); }
+        else { if (dg) ACOC_RW1_LAUNCH(false, 1); else ACOC_RW1_LAUNCH(false, 0); }
+#undef ACOC_RW1_LAUNCH
     } else
         LAUNCH_Q32(c->P.q32, k_update, (F, XT), (c->Np + ROLL_THREADS - 1) / ROLL_THREADS, ROLL_THREADS, c->stream, prob<F>(c), L, c->O, c->S,
                    (const F*)c->U[cur], (const F*)c->DU, (XT*)c->X[nxt], (F*)c->U[nxt], lazy_only ? c->need : nullptr, c->kk, bookkeeping ? 1 : 0);
@@ -1758,7 +1789,10 @@ static int count_active(acoc_ctx* c, int* n_active, long long* iters_sum)
     CK(cudaStreamSynchronize(c->stream));
     if (n_active) *n_active = h;
     if (iters_sum) *iters_sum = s;
-    c->all_active = 2LL * h > c->N;  // (tile-granular lists are practically the identity until well below half of the batch)
+    // ranged iterations sweep every tile; the tile-granular work lists of the single-scope path only start to drop tiles when a few
+    // percent of the instances are left (a tile of 32 is finished with probability (1-p)^32), so the ranges stay until then
+    static const int active_div = getenv("ACOC_ACTIVE_DIV") ? atoi(getenv("ACOC_ACTIVE_DIV")) : 16;  // tuning experiments
+    c->all_active = (long long)active_div * h > c->N;
     return 0;
 }
 
@@ -1784,133 +1818,171 @@ static int launch_iteration_body(acoc_ctx* c)
     return 0;
 }
 
+// Whether the next iteration(s) of this context run as independent tile ranges (see acoc_newton_iterate)
+static bool ranged_mode(const acoc_ctx* c)
+{
+    const int ctas = (n_tiles(c) + 1) / 2, wave = c->bwd_wave_ctas;
+    return use_tma(c) && is_lazy(c) && !c->profiling && c->all_active && !(c->flags & ACOC_NO_SPLIT) && c->kk > 0 && wave > 0 && ctas > wave &&
+           ctas % wave != 0 && c->O.method != ACOC_METHOD_GRADIENT;
+}
+
+// one iteration on the context's stream over the work lists (any batch, any mode; per-phase events when profiling)
+static int single_scope_iteration(acoc_ctx* c)
+{
+    const bool prof = c->profiling, grad = c->O.method == ACOC_METHOD_GRADIENT;
+    bool lazy_only = false;
+    if (prof) CK(cudaEventRecord(c->ev[0], c->stream));
+    TRY(launch_build_active(c));
+    if (c->kk == 0) TRY(launch_cost(c));  // later iterations inherit the cost from the update rollout
+    if (prof) CK(cudaEventRecord(c->ev[1], c->stream));
+    if (grad) TRY(launch_gradient(c));                       // optcon.py:95-118
+    else TRY(launch_backward(c, c->kk > c->O.exact_after));  // optcon.py:443
+    if (prof) CK(cudaEventRecord(c->ev[2], c->stream));
+    if (grad) {  // the costate sweep already produced deltau and the slope: straight to the line search
+        if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
+        if (is_lazy(c)) TRY(launch_cand0(c));
+        TRY(launch_armijo(c, &lazy_only));
+        if (prof) CK(cudaEventRecord(c->ev[4], c->stream));
+        TRY(launch_update(c, lazy_only, true, true));
+    } else if (fused_search(c)) {  // small batch: forward pass and line search in one sweep, get_update as a copy
+        TRY(launch_fused_sweep(c));
+        if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
+        TRY(launch_fused_select(c));
+        if (prof) CK(cudaEventRecord(c->ev[4], c->stream));
+        TRY(launch_fused_pick(c));
+    } else {
+        if (fwd_cand0_fused(c)) {  // (the "forward" phase of the profile then contains candidate 0)
+            TRY(launch_forward_cand0(c));
+            if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
+        } else {
+            TRY(launch_forward(c));
+            if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
+            if (is_lazy(c)) TRY(launch_cand0(c));
+        }
+        TRY(launch_armijo(c, &lazy_only));
+        if (prof) CK(cudaEventRecord(c->ev[4], c->stream));
+        TRY(launch_update(c, lazy_only, true, true));
+    }
+    if (prof) {
+        CK(cudaEventRecord(c->ev[5], c->stream));
+        CK(cudaEventSynchronize(c->ev[5]));
+        // phases: cost, backward, forward, candidates+select, (select folded), update
+        for (int p = 0; p < 5; ++p) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, c->ev[p], c->ev[p + 1]));
+            c->phase_ms[p == 4 ? 5 : p] += ms;
+        }
+    }
+    ++c->kk;
+    return 0;
+}
+
+// `todo` iterations as independent tile ranges on their own streams, joined on the context's stream.  Returns the number of ranges.
+// Why ranges: the backward sweep keeps only bwd_wave_ctas CTAs resident (216 registers per thread), so a batch with more CTAs than that
+// runs in rounds, and the last, partial round leaves most of the machine idle while every warp of it still needs its full
+// latency-bound sweep time.  While most of the batch is active, tile ranges therefore run their iterations independently of each
+// other (every kernel of an iteration takes a tile / instance range): one range's bandwidth-bound forward and rollout sweeps fill the
+// machine while another's backward sweep is latency-bound, across iteration boundaries too.  Instances are independent, so the split
+// changes no result.
+static int ranged_iterations(acoc_ctx* c, int todo, int* nr_out)
+{
+    const int tiles = n_tiles(c), ctas = (tiles + 1) / 2, wave = c->bwd_wave_ctas;
+    int bound[MAX_RANGES + 1] = {0, (ctas / wave) * wave * 2}, nr = 2;  // default: the full rounds of resident backward CTAs | the partial round
+    // Clean phase (candidate 0 was accepted by practically every instance in the last iteration the host knows of): every iteration
+    // is backward -> forward + candidate 0, one latency-bound and one bandwidth-bound sweep, and they overlap the better the more
+    // ranges there are -- ranges of about one backward CTA per SM (2 x SMs tiles).  With failing searches the compute-bound
+    // candidate kernels of many small ranges cost more than the overlap gains, so fewer ranges are used there.
+    static const bool many = getenv("ACOC_NO_MANY_RANGES") == nullptr;
+    // (with failing searches: up to four ranges -- 9.06 vs 9.26 ms per iteration over iterations 5..24 with two, gpurun_out r2_ab4)
+    static const int noisy_nr = getenv("ACOC_NOISY_RANGES") ? atoi(getenv("ACOC_NOISY_RANGES")) : 4;
+    const bool clean = c->last_need >= 0 && (long long)c->last_need * 2048 < c->N;
+    if (many && (clean || noisy_nr > 1) && c->sm_count > 0) {
+        nr = std::max(2, std::min(MAX_RANGES, (tiles + 2 * c->sm_count - 1) / (2 * c->sm_count)));
+        if (!clean) nr = std::min(nr, noisy_nr);
+        const int size = ((tiles + nr - 1) / nr + 1) / 2 * 2;  // whole CTAs (two tiles)
+        for (int r = 1; r < nr; ++r) bound[r] = std::min(tiles, r * size);
+    }
+    if (const char* e = getenv("ACOC_RANGES")) {  // tuning experiments: ascending tile boundaries "a,b,c,..."
+        nr = 1;
+        for (const char* q = e; *q && nr < MAX_RANGES; ++nr) {
+            bound[nr] = std::max(bound[nr - 1] + 2, std::min(tiles - 2, atoi(q)));
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+    }
+    for (int r = nr; r <= MAX_RANGES; ++r) bound[r] = tiles;
+    const int kk0 = c->kk;
+    CK(cudaEventRecord(c->ev_fork, c->stream));
+    for (int r = 1; r < nr; ++r) CK(cudaStreamWaitEvent(c->rstream[r], c->ev_fork, 0));
+    int rc = 0;
+    for (int r = 0; r < nr && !rc; ++r) {
+        c->ls_identity = true;
+        c->ls_range = r;
+        c->ls_stream = r == 0 ? c->stream : c->rstream[r];
+        c->ls_off = bound[r];
+        c->ls_end = bound[r + 1];
+        c->kk = kk0;
+        for (int j = 0; j < todo && !rc; ++j, ++c->kk) rc = launch_iteration_body(c);
+    }
+    scope_reset(c);
+    c->kk = kk0 + todo;
+    if (rc) return rc;
+    for (int r = 1; r < nr; ++r) {
+        CK(cudaEventRecord(c->ev_join[r], c->rstream[r]));
+        CK(cudaStreamWaitEvent(c->stream, c->ev_join[r], 0));
+    }
+    *nr_out = nr;
+    return 0;
+}
+
+// lengths of the need lists of the lazy search in the last iteration (instances whose candidate 0 failed), summed over the ranges:
+// decides between the clean-phase and the two-range split of the following iterations
+static int read_last_need(acoc_ctx* c, int nr_last)
+{
+    int hc[4 + MAX_RANGES] = {};
+    CK(cudaMemcpyAsync(hc, c->counters, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->last_need = hc[2];
+    for (int r = 1; r < nr_last; ++r) c->last_need += hc[3 + r];
+    return 0;
+}
+
 int acoc_newton_iterate(acoc_ctx* c, int n_iters, int* n_active_out)
 {
     TRY(ready(c));
     REQUIRE(n_iters >= 0, "n_iters must be >= 0");
-    const bool prof = c->profiling;
     c->total_ms = 0; for (int p = 0; p < 6; ++p) c->phase_ms[p] = 0;
     c->launches = 0;
     CK(cudaEventRecord(c->ev[6], c->stream));
     int it = 0, nr_last = 1;
     const int kk_in = c->kk;
     const bool fused_small = fused_search(c);  // (no need lists in that mode)
-    for (; it < n_iters; ++it) {
-        if (c->kk >= c->O.max_iters - 1) break;  // for kk in range(max_iters-1), optcon.py:415
-        // Two ranges.  The backward sweep keeps only bwd_wave_ctas CTAs resident (216 registers per thread), so a batch with more
-        // CTAs than that runs in rounds, and the last, partial round leaves most of the machine idle while every warp of it still
-        // needs its full latency-bound sweep time.  While most of the batch is active, the tiles of the full rounds (range A) and
-        // the tiles of the partial round (range B) therefore run all remaining iterations of this call as two independent
-        // instance ranges on two streams (every kernel of an iteration takes a tile / instance range): one range's bandwidth-bound
-        // forward and rollout sweeps fill the machine while the other's backward sweep is latency-bound, across iteration
-        // boundaries too.  Instances are independent, so the split changes no result; the streams join before the call returns.
-        const int ctas = (n_tiles(c) + 1) / 2, wave = c->bwd_wave_ctas;
-        const bool grad = c->O.method == ACOC_METHOD_GRADIENT;
-        if (use_tma(c) && is_lazy(c) && !prof && c->all_active && !(c->flags & ACOC_NO_SPLIT) && c->kk > 0 && wave > 0 && ctas > wave &&
-            ctas % wave != 0 && !grad)
-            break;
-        bool lazy_only = false;
-        if (prof) CK(cudaEventRecord(c->ev[0], c->stream));
-        TRY(launch_build_active(c));
-        if (c->kk == 0) TRY(launch_cost(c));  // later iterations inherit the cost from the update rollout
-        if (prof) CK(cudaEventRecord(c->ev[1], c->stream));
-        if (grad) TRY(launch_gradient(c));                       // optcon.py:95-118
-        else TRY(launch_backward(c, c->kk > c->O.exact_after));  // optcon.py:443
-        if (prof) CK(cudaEventRecord(c->ev[2], c->stream));
-        if (grad) {  // the costate sweep already produced deltau and the slope: straight to the line search
-            if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
-            if (is_lazy(c)) TRY(launch_cand0(c));
-            TRY(launch_armijo(c, &lazy_only));
-            if (prof) CK(cudaEventRecord(c->ev[4], c->stream));
-            TRY(launch_update(c, lazy_only, true, true));
-        } else if (fused_search(c)) {  // small batch: forward pass and line search in one sweep, get_update as a copy
-            TRY(launch_fused_sweep(c));
-            if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
-            TRY(launch_fused_select(c));
-            if (prof) CK(cudaEventRecord(c->ev[4], c->stream));
-            TRY(launch_fused_pick(c));
-        } else {
-            if (fwd_cand0_fused(c)) {  // (the "forward" phase of the profile then contains candidate 0)
-                TRY(launch_forward_cand0(c));
-                if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
-            } else {
-                TRY(launch_forward(c));
-                if (prof) CK(cudaEventRecord(c->ev[3], c->stream));
-                if (is_lazy(c)) TRY(launch_cand0(c));
-            }
-            TRY(launch_armijo(c, &lazy_only));
-            if (prof) CK(cudaEventRecord(c->ev[4], c->stream));
-            TRY(launch_update(c, lazy_only, true, true));
+    while (it < n_iters && c->kk < c->O.max_iters - 1) {  // for kk in range(max_iters-1), optcon.py:415
+        if (!ranged_mode(c)) {
+            TRY(single_scope_iteration(c));
+            nr_last = 1;
+            ++it;
+            continue;
         }
-        if (prof) {
-            CK(cudaEventRecord(c->ev[5], c->stream));
-            CK(cudaEventSynchronize(c->ev[5]));
-            // phases: cost, backward, forward, candidates+select, (select folded), update
-            for (int p = 0; p < 5; ++p) {
-                float ms = 0;
-                CK(cudaEventElapsedTime(&ms, c->ev[p], c->ev[p + 1]));
-                c->phase_ms[p == 4 ? 5 : p] += ms;
-            }
+        // Ranged iterations come in chunks, and the host looks at the device state between chunks: how many searches failed candidate 0
+        // (picks the number of ranges) and how many instances are still active (the ranges sweep every tile; once half of the batch
+        // has finished the work lists of the single-scope path are cheaper).  8 iterations per chunk while the phase is clean -- nothing
+        // converges there and the many-range split needs longer runs to amortise its fill and drain -- else 4.
+        const bool clean = c->last_need >= 0 && (long long)c->last_need * 2048 < c->N;
+        static const int noisy_chunk = getenv("ACOC_NOISY_CHUNK") ? atoi(getenv("ACOC_NOISY_CHUNK")) : 4;  // tuning experiments
+        const int todo = std::min(std::min(n_iters - it, c->O.max_iters - 1 - c->kk), clean ? 8 : noisy_chunk);
+        TRY(ranged_iterations(c, todo, &nr_last));
+        it += todo;
+        if (it < n_iters && c->kk < c->O.max_iters - 1) {
+            TRY(read_last_need(c, nr_last));
+            TRY(count_active(c, nullptr, nullptr));
         }
-        ++c->kk;
     }
-    if (it < n_iters && c->kk < c->O.max_iters - 1) {  // the remaining iterations as two independent ranges (see above)
-        const int tiles = n_tiles(c), ctas = (tiles + 1) / 2, wave = c->bwd_wave_ctas;
-        int bound[MAX_RANGES + 1] = {0, (ctas / wave) * wave * 2}, nr = 2;
-        // Clean phase (candidate 0 was accepted by practically every instance in the last iteration the host knows of): every iteration
-        // is backward -> forward + candidate 0, one latency-bound and one bandwidth-bound sweep, and they overlap the better the more
-        // ranges there are -- ranges of about one backward CTA per SM (2 x SMs tiles).  With failing searches the compute-bound
-        // candidate kernels of many small ranges cost more than the overlap gains, so two ranges are kept there.
-        static const bool many = getenv("ACOC_NO_MANY_RANGES") == nullptr;
-        if (many && c->last_need >= 0 && (long long)c->last_need * 2048 < c->N && c->sm_count > 0) {
-            nr = std::max(2, std::min(MAX_RANGES, (tiles + 2 * c->sm_count - 1) / (2 * c->sm_count)));
-            const int size = ((tiles + nr - 1) / nr + 1) / 2 * 2;  // whole CTAs (two tiles)
-            for (int r = 1; r < nr; ++r) bound[r] = std::min(tiles, r * size);
-        }
-        if (const char* e = getenv("ACOC_RANGES")) {  // tuning experiments: ascending tile boundaries "a,b,c,..."
-            nr = 1;
-            for (const char* q = e; *q && nr < MAX_RANGES; ++nr) {
-                bound[nr] = std::max(bound[nr - 1] + 2, std::min(tiles - 2, atoi(q)));
-                while (*q && *q != ',') ++q;
-                if (*q == ',') ++q;
-            }
-        }
-        for (int r = nr; r <= MAX_RANGES; ++r) bound[r] = tiles;
-        const int kk0 = c->kk;
-        const int todo = std::min(n_iters - it, c->O.max_iters - 1 - c->kk);
-        CK(cudaEventRecord(c->ev_fork, c->stream));
-        for (int r = 1; r < nr; ++r) CK(cudaStreamWaitEvent(c->rstream[r], c->ev_fork, 0));
-        int rc = 0;
-        for (int r = 0; r < nr && !rc; ++r) {
-            c->ls_identity = true;
-            c->ls_range = r;
-            c->ls_stream = r == 0 ? c->stream : c->rstream[r];
-            c->ls_off = bound[r];
-            c->ls_end = bound[r + 1];
-            c->kk = kk0;
-            for (int j = 0; j < todo && !rc; ++j, ++c->kk) rc = launch_iteration_body(c);
-        }
-        scope_reset(c);
-        c->kk = kk0 + todo;
-        if (rc) return rc;
-        for (int r = 1; r < nr; ++r) {
-            CK(cudaEventRecord(c->ev_join[r], c->rstream[r]));
-            CK(cudaStreamWaitEvent(c->stream, c->ev_join[r], 0));
-        }
-        nr_last = nr;
-    }
-    // instances whose candidate 0 failed in the last iteration (lengths of the need lists of the lazy search): decides between the
-    // clean-phase and the two-range split of the next call
-    int hc[4 + MAX_RANGES] = {};
     const bool lazy_counts = (c->flags & ACOC_ARMIJO_LAZY) && c->O.armijo_maxiters > 1 && c->kk > kk_in && !fused_small && is_lazy(c) &&
                              c->O.method == ACOC_METHOD_NEWTON;
-    if (lazy_counts) CK(cudaMemcpyAsync(hc, c->counters, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
+    if (lazy_counts) TRY(read_last_need(c, nr_last));
     CK(cudaEventRecord(c->ev[7], c->stream));
     CK(cudaEventSynchronize(c->ev[7]));
-    if (lazy_counts) {
-        c->last_need = hc[2];
-        for (int r = 1; r < nr_last; ++r) c->last_need += hc[3 + r];
-    }
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]));
     c->total_ms = ms;
@@ -2052,8 +2124,13 @@ int acoc_newton_solve(acoc_ctx* c, long long* total_iters)
         // failing search in the last iteration seen) nothing converges yet and the many-range split of acoc_newton_iterate needs
         // longer calls to amortise its fill and drain: 8 iterations per call there.
         const bool clean = cur->last_need >= 0 && (long long)cur->last_need * 2048 < cur->N;
+        const int kk_before = cur->kk;
         TRY(acoc_newton_iterate(cur, clean ? 8 : 4, &active));
         total_ms += cur->total_ms; launches += cur->launches;
+        static const bool trace = getenv("ACOC_TRACE") != nullptr;  // diagnostics: one line per call of the lock-step driver
+        if (trace)
+            fprintf(stderr, "acoc_trace gen=%zu n=%d kk=%d..%d active_after=%d need_last=%d ms=%.3f launches=%lld\n", chain.size() - 1, cur->N, kk_before,
+                    cur->kk - 1, active, cur->last_need, cur->total_ms, cur->launches);
         for (int p = 0; p < 6; ++p) phase[p] += cur->phase_ms[p];
         if (active > 0 && !(c->flags & ACOC_SOLVE_IN_PLACE) && cur->N >= ACOC_GEN_MIN && 2 * active <= cur->N && cur->kk < cur->O.max_iters - 1) {
             acoc_ctx* ch = nullptr;

@@ -168,7 +168,7 @@ ACOC_HD double traj_cost_instance(const ProblemT<F>& P, const XT* X, const F* U,
 //   Mx = B'PA + S,  m = B'p + r/2,  G = R + B'PB
 //   P_t = Q + A'PA - Mx' G^-1 Mx          p_t = q/2 + A'p - Mx' G^-1 m
 //   MM  = G, or G + 0.5 I when G has a non-positive eigenvalue;  K = -MM^-1 Mx,  sigma = -MM^-1 m
-template <bool EXACT, typename F>
+template <bool EXACT, int DG = -1, typename F>
 ACOC_HD int riccati_step(const ModelT<F>& M, const WeightsT<F>& W, const Lin<F>& l, const Hess<F>& h, const F* q, const F* r,
                          F* Pm, F* p, F* lam, F* K, F* sig, F* g)
 {
@@ -248,9 +248,12 @@ ACOC_HD int riccati_step(const ModelT<F>& M, const WeightsT<F>& W, const Lin<F>&
     for (int i = 0; i < NS; ++i) {
 #pragma unroll
         for (int j = i; j < NS; ++j) {
-            F qij = W.diag ? (i == j ? W.Q[i * 7] : F(0.0)) : W.Q[i * 6 + j];
             const F corr = fma_(Mx1[i], Y1[j], Mx0[i] * Y0[j]);
-            Pm[sym(i, j)] = (Pn[sym(i, j)] + qij) - corr;
+            if (DG == 1 && i != j) Pm[sym(i, j)] = Pn[sym(i, j)] - corr;  // (the structural zero of a diagonal Q is not added)
+            else {
+                const F qij = weights_diag<DG>(W) ? (i == j ? W.Q[i * 7] : F(0.0)) : W.Q[i * 6 + j];
+                Pm[sym(i, j)] = (Pn[sym(i, j)] + qij) - corr;
+            }
         }
         p[i] = fma_(F(0.5), q[i], Atp[i]) - fma_(Mx1[i], y1, Mx0[i] * y0);
         lam[i] = Atl[i] + q[i];  // optcon.py:461
@@ -268,24 +271,24 @@ ACOC_HD int riccati_step(const ModelT<F>& M, const WeightsT<F>& W, const Lin<F>&
 // KSG[t][0..11] = K_t (row-major 2x6), [12..13] = sigma_t, [14..15] = g_t ; t = 0..TT-2.
 // Returns the number of steps whose gain took the +0.5 I branch.
 // terminal condition: lam_{T-1} = QT dx (optcon.py:429-432), P_{T-1} = QT, p_{T-1} = lam/2 (:688-690, :716)
-template <typename F>
+template <int DG = -1, typename F>
 ACOC_HD void backward_terminal(const WeightsT<F>& W, const F* x, const F* xr, F* Pm, F* p, F* lam)
 {
     F dx[NS];
 #pragma unroll
     for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
-    wmul6(W.QT, W.diag, dx, lam);
+    wmul6(W.QT, (int)weights_diag<DG>(W), dx, lam);
 #pragma unroll
     for (int a = 0; a < NS; ++a) {
         p[a] = F(0.5) * lam[a];
 #pragma unroll
-        for (int b = a; b < NS; ++b) Pm[sym(a, b)] = W.diag ? (a == b ? W.QT[a * 7] : F(0.0)) : W.QT[a * 6 + b];
+        for (int b = a; b < NS; ++b) Pm[sym(a, b)] = weights_diag<DG>(W) ? (a == b ? W.QT[a * 7] : F(0.0)) : W.QT[a * 6 + b];
     }
 }
 
 // one time step of the backward sweep: (x_t, u_t, refs) and the carried (P, p, lam) -> K_t, sigma_t, g_t.  Returns 1 if the
 // gain took the +0.5 I branch.
-template <bool EXACT, typename F>
+template <bool EXACT, int DG = -1, typename F>
 ACOC_HD int backward_step(const ModelT<F>& M, const WeightsT<F>& W, const F* x, const F* u, const F* xr, const F* ur, F* Pm, F* p, F* lam,
                           F* K, F* sig, F* g)
 {
@@ -294,13 +297,13 @@ ACOC_HD int backward_step(const ModelT<F>& M, const WeightsT<F>& W, const F* x, 
     for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
 #pragma unroll
     for (int c = 0; c < NI; ++c) du[c] = u[c] - ur[c];
-    wmul6(W.Q, W.diag, dx, q);   // lx = Q dx   (aircraft_simplified.py:63)
-    wmul2(W.R, W.diag, du, r);   // lu = R du   (:64)
+    wmul6(W.Q, (int)weights_diag<DG>(W), dx, q);   // lx = Q dx   (aircraft_simplified.py:63)
+    wmul2(W.R, (int)weights_diag<DG>(W), du, r);   // lu = R du   (:64)
     const Trig<F> tg = make_trig(x);
     const Lin<F> l = linearize(M, x, u, tg);
     Hess<F> h;
     if (EXACT) h = hess_contract(M, x, u, tg, l, lam);
-    return riccati_step<EXACT, F>(M, W, l, h, q, r, Pm, p, lam, K, sig, g);
+    return riccati_step<EXACT, DG, F>(M, W, l, h, q, r, Pm, p, lam, K, sig, g);
 }
 
 template <bool EXACT, typename F, typename XT>
@@ -482,7 +485,7 @@ ACOC_HD double forward_lq_instance(const ProblemT<F>& P, const XT* X, const F* U
 // open-loop rollout of u' = u + s*du from x0: one Armijo candidate (COST) and/or get_update (WRITE)
 // ------------------------------------------------------------------------------------------------------
 // one step of a rollout: stage cost of (x_t, u_t) (COST) and x_{t+1} = f(x_t, u_t) in place
-template <bool COST, bool Q32, typename F>
+template <bool COST, bool Q32, int DG = -1, typename F>
 ACOC_HD void rollout_step(const ModelT<F>& M, const WeightsT<F>& W, F* x, const F* u, const F* xr, const F* ur, double& J)
 {
     if (COST) {
@@ -491,7 +494,7 @@ ACOC_HD void rollout_step(const ModelT<F>& M, const WeightsT<F>& W, F* x, const 
         for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
 #pragma unroll
         for (int c = 0; c < NI; ++c) du[c] = u[c] - ur[c];
-        J += (double)stage_cost(W, dx, du);
+        J += (double)stage_cost<DG>(W, dx, du);
     }
     const Trig<F> tg = make_trig(x);
     F xn[NS];

@@ -318,12 +318,18 @@ ACOC_HD Hess<F> hess_contract(const ModelT<F>& M, const F* x, const F* u, const 
     return h;
 }
 
+// DG: what the caller knows about the weights at compile time -- 1: diagonal, 0: dense, -1: look at W.diag at run time.  The hot
+// kernels are instantiated for DG = 1 (every shipped configuration) and DG = 0, which removes the dense arm, its branches and the
+// additions of structural zeros from their time loops; same arithmetic on the entries that exist.
+template <int DG, typename F>
+ACOC_HD bool weights_diag(const WeightsT<F>& W) { return DG < 0 ? W.diag != 0 : DG != 0; }
+
 // Stage cost (aircraft_simplified.py:61): 0.5*dx'(Q dx) + 0.5*du'(R du), sums in ascending index order.
-template <typename F>
+template <int DG = -1, typename F>
 ACOC_HD F stage_cost(const WeightsT<F>& W, const F* dx, const F* du)
 {
     F sx = F(0.0), su = F(0.0);
-    if (W.diag) {
+    if (weights_diag<DG>(W)) {
 #pragma unroll
         for (int i = 0; i < NS; ++i) sx += dx[i] * (W.Q[i * 7] * dx[i]);
 #pragma unroll
@@ -348,11 +354,11 @@ ACOC_HD F stage_cost(const WeightsT<F>& W, const F* dx, const F* du)
 }
 
 // Terminal cost (aircraft_simplified.py:92): ((0.5*dx') QT) dx.
-template <typename F>
+template <int DG = -1, typename F>
 ACOC_HD F term_cost(const WeightsT<F>& W, const F* dx)
 {
     F s = F(0.0);
-    if (W.diag) {
+    if (weights_diag<DG>(W)) {
 #pragma unroll
         for (int j = 0; j < NS; ++j) s += ((F(0.5) * dx[j]) * W.QT[j * 7]) * dx[j];
     } else {

@@ -90,6 +90,22 @@ __device__ __forceinline__ int warp_tile(const TileList& L, int w, int Np)
     return e < *L.count ? L.tiles[e] : -1;
 }
 
+// compacted, ORDERED list of groups of 2^shift consecutive instances that still contain work (shift = 0: a per-instance list)
+struct WorkList {
+    const int* groups;  // nullptr: identity (thread j -> instance j)
+    const int* count;   // number of valid groups (device memory)
+    int shift;
+};
+
+__device__ __forceinline__ int work_instance(const WorkList& L, int j, int N)
+{
+    if (!L.groups) return j < N ? j : -1;
+    const int g = j >> L.shift;
+    if (g >= *L.count) return -1;
+    const int i = (L.groups[g] << L.shift) + (j & ((1 << L.shift) - 1));
+    return i < N ? i : -1;
+}
+
 // first element of the block of tile `tile` at time t in a warp-tiled array with C components
 __device__ __forceinline__ size_t tile_base(int t, int C, int Np, int tile) { return ((size_t)t * (size_t)(Np / TILE) + tile) * C * TILE; }
 
@@ -172,7 +188,7 @@ struct RollStage {
     static constexpr int U_O = 0, DU_O = U_B, UR_O = 2 * U_B, XR_O = 3 * U_B, BYTES = 3 * U_B + XR_B;
 };
 
-template <bool Q32, typename F, typename XT, int MODE>
+template <bool Q32, typename F, typename XT, int MODE, int DG>
 __global__ void __launch_bounds__(64, 7) k_rollout_write_tma(ProblemT<F> P, TileList L, NewtonOpts O, NewtonState S, const F* __restrict__ U,
                                                           const F* __restrict__ DU, const double* __restrict__ cand_steps,
                                                           XT* __restrict__ Xn, F* __restrict__ Un, const int* __restrict__ only, int kk,
@@ -233,7 +249,7 @@ __global__ void __launch_bounds__(64, 7) k_rollout_write_tma(ProblemT<F> P, Tile
                 store_x(Xn, t, Np, i, x);
 #pragma unroll
                 for (int c = 0; c < NI; ++c) Un[at(t, NI, c, Np, i)] = u[c];
-                rollout_step<true, Q32>(P.M, P.W, x, u, xr, ur, J);
+                rollout_step<true, Q32, DG>(P.M, P.W, x, u, xr, ur, J);
             }
         }
         if (roll) {
@@ -244,7 +260,7 @@ __global__ void __launch_bounds__(64, 7) k_rollout_write_tma(ProblemT<F> P, Tile
             F dx[NS];
 #pragma unroll
             for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
-            J += (double)term_cost(P.W, dx);
+            J += (double)term_cost<DG>(P.W, dx);
         }
     }
     if (!act) return;
@@ -272,7 +288,7 @@ struct FwdCandStage {
                          BYTES = XR_O + XR_B;
 };
 
-template <bool Q32, typename F, typename XT>
+template <bool Q32, typename F, typename XT, int DG>
 __global__ void __launch_bounds__(64, 7) k_forward_cand0_tma(ProblemT<F> P, TileList L, NewtonState S, const XT* __restrict__ X,
                                                               const F* __restrict__ U, const F* __restrict__ KSG, F* __restrict__ DU,
                                                               const double* __restrict__ cand_steps, XT* __restrict__ Xn, F* __restrict__ Un)
@@ -345,7 +361,7 @@ __global__ void __launch_bounds__(64, 7) k_forward_cand0_tma(ProblemT<F> P, Tile
                 store_x(Xn, t, Np, i, xc);
 #pragma unroll
                 for (int c = 0; c < NI; ++c) Un[at(t, NI, c, Np, i)] = uc[c];
-                rollout_step<true, Q32>(P.M, P.W, xc, uc, xr, ur, J);
+                rollout_step<true, Q32, DG>(P.M, P.W, xc, uc, xr, ur, J);
             }
         }
     }
@@ -361,7 +377,7 @@ __global__ void __launch_bounds__(64, 7) k_forward_cand0_tma(ProblemT<F> P, Tile
     load_xref(P, TT - 1, i, xrT);
 #pragma unroll
     for (int c = 0; c < NS; ++c) dxT[c] = xc[c] - xrT[c];
-    J += (double)term_cost(P.W, dxT);
+    J += (double)term_cost<DG>(P.W, dxT);
     S.Jcand[i] = J;
 }
 
@@ -375,7 +391,7 @@ struct BwdStage {
     static constexpr int U_O = 0, UR_O = U_B, XR_O = 2 * U_B, X_O = 2 * U_B + XR_B, BYTES = 2 * U_B + XR_B + X_B;
 };
 
-template <bool EXACT, typename F, typename XT>
+template <bool EXACT, typename F, typename XT, int DG>
 __global__ void __launch_bounds__(64) k_backward_tma(ProblemT<F> P, TileList L, const XT* __restrict__ X, const F* __restrict__ U,
                                                      F* __restrict__ KSG, const int* __restrict__ status, int* __restrict__ n_reg)
 {
@@ -409,7 +425,7 @@ __global__ void __launch_bounds__(64) k_backward_tma(ProblemT<F> P, TileList L, 
     if (live) {
         load_xref(P, TT - 1, i, xr);
         load_x(P, X, TT - 1, i, x);
-        backward_terminal(P.W, x, xr, Pm, p, lam);
+        backward_terminal<DG>(P.W, x, xr, Pm, p, lam);
     }
     for (int k = 0; k < nsteps; ++k) {
         const int t = TT - 2 - k;
@@ -432,7 +448,7 @@ __global__ void __launch_bounds__(64) k_backward_tma(ProblemT<F> P, TileList L, 
             if (shared_ref) load_ref(P, t, i, xr, ur);
             finish_x(P, t, i, xraw, x);
             F K[2 * NS], sig[NI], g[NI];
-            nreg += backward_step<EXACT>(P.M, P.W, x, u, xr, ur, Pm, p, lam, K, sig, g);
+            nreg += backward_step<EXACT, DG>(P.M, P.W, x, u, xr, ur, Pm, p, lam, K, sig, g);
             F* out = KSG + tile_base(t, 16, Np, tile) + lane;
 #pragma unroll
             for (int c = 0; c < 12; ++c) out[c * TILE] = K[c];
@@ -512,6 +528,149 @@ __global__ void __launch_bounds__(64) k_gradient_tma(ProblemT<F> P, TileList L, 
         }
     }
     if (live && status[i] == ST_ACTIVE) descent[i] = -sq;
+}
+
+
+// =================================================================================================================
+// Armijo candidates over a per-instance work list (the instances whose candidate 0 failed): rollout_instance<false, true>, one
+// consumer warp per candidate.
+//
+// The lanes of a CTA are 32 list entries -- arbitrary instances, so their inputs are not one contiguous block and the bulk-TMA rings
+// above do not apply.  Instead ONE producer warp gathers u, du and the references of the next steps of its 32 instances into a
+// shared-memory ring with 8-byte cp.async copies (completion counted on an mbarrier by cp.async.mbarrier.arrive), CR_SB time steps
+// per stage, and every candidate warp of the CTA reads them from there: the nine candidate rollouts of an instance used to issue the
+// same twelve global loads each, with their 64-bit address arithmetic, and wait for them every step (4.1 long-scoreboard stall
+// cycles per issued instruction in the round-1 profile); now the loads are in flight CR_STAGES stages ahead of the arithmetic and
+// are issued once per CTA.  Same per-step function (rollout_step) as every other rollout kernel: bit-identical costs.
+// (get_update over the same list was measured too: with one consumer warp per CTA the gathers are not amortised -- 17.8 GB of
+// 32-byte sectors for 8-byte elements -- and the tile-granular TMA sweep k_rollout_write_tma<.,1> stays faster: 2.1 vs 2.9 ms.)
+// =================================================================================================================
+#ifndef ACOC_CR_SB
+#define ACOC_CR_SB 4
+#endif
+#ifndef ACOC_CR_STAGES
+#define ACOC_CR_STAGES 3
+#endif
+#ifndef ACOC_CAND_MINB
+#define ACOC_CAND_MINB 3  // resident candidate CTAs per SM the register allocation is bounded for
+#endif
+constexpr int CR_SB = ACOC_CR_SB, CR_STAGES = ACOC_CR_STAGES;
+constexpr int CR_NV = 2 * NI + NI + NS;  // u, du, uref, xref
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the mbarrier receives one arrival when every cp.async issued so far by this thread has landed (the count is part of init)
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async_elem(void* dst_smem, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "n"(BYTES) : "memory");
+}
+
+template <typename F>
+constexpr size_t candidates_list_smem() { return (size_t)CR_STAGES * CR_SB * CR_NV * TILE * sizeof(F) + 2 * CR_STAGES * sizeof(uint64_t); }
+
+// blockDim = (32, rows + 1): warps 0..rows-1 roll candidate c0 + pass*rows + y (as many passes as it takes to reach c1), warp `rows`
+// gathers.  Jcand[c][i] receives the cost.
+template <bool Q32, typename F, int MAXROWS, int DG, bool SHARED>
+__global__ void __launch_bounds__(TILE * (MAXROWS + 1), ACOC_CAND_MINB)
+k_candidates_list(ProblemT<F> P, WorkList L, const F* __restrict__ U, const F* __restrict__ DU, const double* __restrict__ steps, int c0, int c1,
+                  double* __restrict__ Jcand)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    F* const data = reinterpret_cast<F*>(smem);
+    uint64_t* const full = reinterpret_cast<uint64_t*>(smem + (size_t)CR_STAGES * CR_SB * CR_NV * TILE * sizeof(F));
+    uint64_t* const empty = full + CR_STAGES;
+    const int lane = threadIdx.x, row = threadIdx.y, rows = blockDim.y - 1;
+    if (work_instance(L, blockIdx.x * TILE, P.N) < 0) return;  // no list entry for this CTA (uniform: the list is dense from the front)
+    const int i = work_instance(L, blockIdx.x * TILE + lane, P.N);
+    if (lane == 0 && row == 0) {
+        for (int s = 0; s < CR_STAGES; ++s) { mbar_init(full + s, TILE); mbar_init(empty + s, rows); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int TT = P.TT, Np = P.Np, nsteps = TT - 1, nst = (nsteps + CR_SB - 1) / CR_SB;
+    constexpr bool shared_ref = SHARED;  // (P.ref_shared, known at compile time here)
+    const int passes = (c1 - c0 + rows - 1) / rows;
+    if (row == rows) {  // ---- producer warp
+        const size_t tstride_u = (size_t)(Np / TILE) * NI * TILE, tstride_x = (size_t)(Np / TILE) * NS * TILE;
+        const size_t ou = i >= 0 ? at(0, NI, 0, Np, i) : 0, ox = i >= 0 ? at(0, NS, 0, Np, i) : 0;
+        for (int g = 0; g < passes * nst; ++g) {
+            const int st = g % CR_STAGES, sidx = g % nst;
+            if (g >= CR_STAGES) mbar_wait(empty + st, (uint32_t)((g / CR_STAGES - 1) & 1));
+            if (i >= 0) {
+                F* d = data + (size_t)st * CR_SB * CR_NV * TILE + lane;
+                for (int k = 0; k < CR_SB; ++k, d += CR_NV * TILE) {
+                    const int t = sidx * CR_SB + k;
+                    if (t >= nsteps) break;
+                    const F* pu = U + ou + (size_t)t * tstride_u;
+                    const F* pd = DU + ou + (size_t)t * tstride_u;
+                    cp_async_elem<sizeof(F)>(d, pu);
+                    cp_async_elem<sizeof(F)>(d + TILE, pu + TILE);
+                    cp_async_elem<sizeof(F)>(d + 2 * TILE, pd);
+                    cp_async_elem<sizeof(F)>(d + 3 * TILE, pd + TILE);
+                    if (!shared_ref) {
+                        const F* pr = P.uref + ou + (size_t)t * tstride_u;
+                        const F* px = P.xref + ox + (size_t)t * tstride_x;
+                        cp_async_elem<sizeof(F)>(d + 4 * TILE, pr);
+                        cp_async_elem<sizeof(F)>(d + 5 * TILE, pr + TILE);
+#pragma unroll
+                        for (int c = 0; c < NS; ++c) cp_async_elem<sizeof(F)>(d + (6 + c) * TILE, px + c * TILE);
+                    }
+                }
+            }
+            cp_async_mbar_arrive(full + st);
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");  // no copy may be in flight when the warp exits
+        return;
+    }
+    // ---- candidate warps
+    for (int pass = 0; pass < passes; ++pass) {
+        const int c = c0 + pass * rows + row;
+        const bool work = i >= 0 && c < c1;
+        const F s = (F)(c < c1 ? steps[c] : 0.0);
+        F x[NS], u[NI], xr[NS], ur[NI];
+        double J = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < NS; ++cc) x[cc] = work ? P.x0[(size_t)cc * Np + i] : F(0.0);
+        for (int sidx = 0; sidx < nst; ++sidx) {
+            const int g = pass * nst + sidx, st = g % CR_STAGES;
+            mbar_wait(full + st, (uint32_t)((g / CR_STAGES) & 1));
+            if (work) {
+                const F* d = data + (size_t)st * CR_SB * CR_NV * TILE + lane;
+#pragma unroll 1
+                for (int k = 0; k < CR_SB; ++k, d += CR_NV * TILE) {  // (not unrolled: 64 registers hold one step without spills)
+                    const int t = sidx * CR_SB + k;
+                    if (t >= nsteps) break;
+#pragma unroll
+                    for (int cc = 0; cc < NI; ++cc) u[cc] = d[cc * TILE] + s * d[(2 + cc) * TILE];  // optcon.py:197 / :253
+                    if (shared_ref) load_ref(P, t, i, xr, ur);
+                    else {
+#pragma unroll
+                        for (int cc = 0; cc < NI; ++cc) ur[cc] = d[(4 + cc) * TILE];
+#pragma unroll
+                        for (int cc = 0; cc < NS; ++cc) xr[cc] = d[(6 + cc) * TILE];
+                    }
+                    rollout_step<true, Q32, DG>(P.M, P.W, x, u, xr, ur, J);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + st);
+        }
+        if (work) {
+            load_xref(P, TT - 1, i, xr);
+            F dx[NS];
+#pragma unroll
+            for (int cc = 0; cc < NS; ++cc) dx[cc] = x[cc] - xr[cc];
+            J += (double)term_cost<DG>(P.W, dx);
+            Jcand[(size_t)c * Np + i] = J;
+        }
+    }
 }
 
 }  // namespace acoc

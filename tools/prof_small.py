@@ -26,7 +26,7 @@ if what == "sanitize":   # tiny: every kernel family once, short horizon
     print("sanitize workload done")
 else:
     n = 4096 if what == "newton" else 65536
-    xr, ur, dx0, (Q, R, QT) = bench.make_problem("step", n, (0, 1))
+    xr, ur, dx0, (Q, R, QT) = bench.make_problem("step", n, (0, 1))[:4]
     with pkg.BatchedNewton(n, TT=bench.TT, armijo="lazy", method=what, generations=False) as bn:
         bn.set_weights(Q, R, QT)
         bn.set_refs(xr, ur)

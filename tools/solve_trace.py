@@ -20,7 +20,7 @@ ap.add_argument("--armijo", default="lazy")
 ap.add_argument("--state", default="f32")
 a = ap.parse_args()
 n = a.instances
-xr, ur, dx0, (Q, R, QT) = bench.make_problem(a.workload, n, (0, 1))
+xr, ur, dx0, (Q, R, QT), _ = bench.make_problem(a.workload, n, (0, 1))
 xr_p, ur_p = bench.pinned_like(xr), bench.pinned_like(ur)
 import torch
 xs_t = torch.empty((n, 6, bench.TT), dtype=torch.float64, pin_memory=True)

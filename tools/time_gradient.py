@@ -10,7 +10,7 @@ import bench  # noqa: E402
 import aircraftoptimalcontrol_b200 as pkg  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
-xr, ur, dx0, (Q, R, QT) = bench.make_problem("step", n, (0, 1))
+xr, ur, dx0, (Q, R, QT) = bench.make_problem("step", n, (0, 1))[:4]
 out = {"instances": n}
 for tma in (True, False):
     with pkg.BatchedNewton(n, TT=bench.TT, armijo="lazy", method="gradient", max_iters=40, tma=tma) as bn:

@@ -14,7 +14,7 @@ import aircraftoptimalcontrol_b200 as pkg  # noqa: E402
 sizes = [int(a) for a in sys.argv[1:]] or [1, 256, 2048, 4096]
 out = {}
 for n in sizes:
-    xr, ur, dx0, (Q, R, QT) = bench.make_problem("step", n, (0, 1))
+    xr, ur, dx0, (Q, R, QT), _ = bench.make_problem("step", n, (0, 1))
     for fused in (True, False):
         with pkg.BatchedNewton(n, TT=bench.TT, armijo="lazy", fused=fused, generations=False) as bn:
             bn.set_weights(Q, R, QT)
