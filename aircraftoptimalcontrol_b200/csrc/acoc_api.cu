@@ -952,6 +952,7 @@ static void fill_weights(Weights* W, const double* Q, const double* R, const dou
 // (the functions below are declared extern "C" in acoc.h, which gives these definitions C linkage)
 
 int acoc_version(void) { return ACOC_VERSION; }
+
 const char* acoc_last_error(void) { return g_err.c_str(); }
 
 int acoc_device_count(int* count)

@@ -168,14 +168,31 @@ ACOC_HD double traj_cost_instance(const ProblemT<F>& P, const XT* X, const F* U,
 //   Mx = B'PA + S,  m = B'p + r/2,  G = R + B'PB
 //   P_t = Q + A'PA - Mx' G^-1 Mx          p_t = q/2 + A'p - Mx' G^-1 m
 //   MM  = G, or G + 0.5 I when G has a non-positive eigenvalue;  K = -MM^-1 Mx,  sigma = -MM^-1 m
+// The step has two halves that share only the linearisation: the COSTATE half (g, lambda_t: needs lambda_{t+1} only) and the MATRIX
+// half (G, m, the column sweep, gains, P_t, p_t: needs P_{t+1}, p_{t+1} only).  riccati_step() is their composition.  (Running the
+// halves in two warps of a CTA -- costate warp one step ahead, linearisation handed over through shared memory -- was measured in
+// round 2: the matrix half alone needs ~230 registers to stay spill-free, so only 4 tiles per SM are resident instead of 8 and the
+// sweep takes 4.0 ms instead of 3.2; bounded to 168 / 128 registers it spills and takes 5.0 / 6.4 ms.  Not kept; profiles/README.md.)
+
+// costate half: g = B' lam_{t+1} + r (optcon.py:475), lam_t = A' lam_{t+1} + q (:461)
+template <typename F>
+ACOC_HD void riccati_costate(const ModelT<F>& M, const Lin<F>& l, const F* q, const F* r, F* lam, F* g)
+{
+    g[0] = fma_(l.b50, lam[5], fma_(l.b20, lam[2], r[0]));
+    g[1] = fma_(M.b41, lam[4], r[1]);
+    F Atl[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) Atl[i] = acol(l, M.dt, lam, i);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) lam[i] = Atl[i] + q[i];
+}
+
+// matrix half: Pm, p at t+1 -> K_t, sigma_t, Pm, p at t.  Returns 1 if the gain took the +0.5 I branch.
 template <bool EXACT, int DG = -1, typename F>
-ACOC_HD int riccati_step(const ModelT<F>& M, const WeightsT<F>& W, const Lin<F>& l, const Hess<F>& h, const F* q, const F* r,
-                         F* Pm, F* p, F* lam, F* K, F* sig, F* g)
+ACOC_HD int riccati_matrix(const ModelT<F>& M, const WeightsT<F>& W, const Lin<F>& l, const Hess<F>& h, const F* q, const F* r,
+                           F* Pm, F* p, F* K, F* sig)
 {
     const F dt = M.dt, b41 = M.b41;
-    // g = B' lam_{t+1} + r  (optcon.py:475)
-    g[0] = fma_(l.b50, lam[5], fma_(l.b20, lam[2], r[0]));
-    g[1] = fma_(b41, lam[4], r[1]);
     // G = R + B'PB, m = B'p + r/2  (need P_{t+1}, p_{t+1})
     const F P22 = Pm[sym(2, 2)], P25 = Pm[sym(2, 5)], P55 = Pm[sym(5, 5)], P24 = Pm[sym(2, 4)], P45 = Pm[sym(4, 5)], P44 = Pm[sym(4, 4)];
     const F pb2 = fma_(l.b50, P25, l.b20 * P22), pb5 = fma_(l.b50, P55, l.b20 * P25);
@@ -204,10 +221,10 @@ ACOC_HD int riccati_step(const ModelT<F>& M, const WeightsT<F>& W, const Lin<F>&
     }
     if (EXACT) { Mx0[2] += h.s2; Mx0[3] += h.s3; Mx0[5] += h.s5; }  // S = lux + fux (optcon.py:446)
 
-    // A'p and A'lam
-    F Atp[NS], Atl[NS];
+    // A'p
+    F Atp[NS];
 #pragma unroll
-    for (int i = 0; i < NS; ++i) { Atp[i] = acol(l, dt, p, i); Atl[i] = acol(l, dt, lam, i); }
+    for (int i = 0; i < NS; ++i) Atp[i] = acol(l, dt, p, i);
 
     // G^-1 (explicit inverse, optcon.py:728)
     const F det = fma_(G00, G11, -(G01 * G01));
@@ -243,7 +260,7 @@ ACOC_HD int riccati_step(const ModelT<F>& M, const WeightsT<F>& W, const Lin<F>&
         sig[1] = -fma_(hi11, m1, hi01 * m0);
     }
 
-    // P_t, p_t, lam_t
+    // P_t, p_t
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
 #pragma unroll
@@ -256,12 +273,20 @@ ACOC_HD int riccati_step(const ModelT<F>& M, const WeightsT<F>& W, const Lin<F>&
             }
         }
         p[i] = fma_(F(0.5), q[i], Atp[i]) - fma_(Mx1[i], y1, Mx0[i] * y0);
-        lam[i] = Atl[i] + q[i];  // optcon.py:461
     }
     if (EXACT) {  // Q_t = lxx + fxx (optcon.py:444)
         Pm[sym(2, 2)] += h.h22; Pm[sym(2, 3)] += h.h23; Pm[sym(2, 5)] += h.h25;
         Pm[sym(3, 3)] += h.h33; Pm[sym(3, 5)] += h.h35; Pm[sym(5, 5)] += h.h55;
     }
+    return reg;
+}
+
+template <bool EXACT, int DG = -1, typename F>
+ACOC_HD int riccati_step(const ModelT<F>& M, const WeightsT<F>& W, const Lin<F>& l, const Hess<F>& h, const F* q, const F* r,
+                         F* Pm, F* p, F* lam, F* K, F* sig, F* g)
+{
+    const int reg = riccati_matrix<EXACT, DG, F>(M, W, l, h, q, r, Pm, p, K, sig);
+    riccati_costate(M, l, q, r, lam, g);   // (after the matrix half only for the order of the statements; the halves share no state)
     return reg;
 }
 

@@ -207,6 +207,9 @@ ACOC_HD F div_const(F a, F d, F rd)
 }
 
 // aircraft_simplified.py:300 -- the reference stores the next state in a float32 array.  (FP32 mode: identity.)
+// (The round trip is two F2F instructions at ~7.5 cycles per warp each on B200 -- tools/microbench/f2f.cu -- but they run beside the
+// FP64 pipe, which is the busy one in the rollouts: replacing them by the two-addition rounding trick (v + 1.5*2^(e+29)) - 1.5*2^(e+29),
+// bit-identical on 1.4e9 test values, made the candidate kernel 9 % SLOWER.  Measured in round 2, not kept.)
 template <bool Q32>
 ACOC_HD double quant_(double v) { return Q32 ? (double)(float)v : v; }
 template <bool Q32>

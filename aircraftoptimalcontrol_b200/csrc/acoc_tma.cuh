@@ -46,12 +46,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         "r"(parity)
         : "memory");
 }
+// plain arrival (release at CTA scope): hands a shared-memory stage from one warp to another
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // global -> shared bulk copy (TMA, 1-D): 16-byte aligned addresses, size a multiple of 16
 __device__ __forceinline__ void tma_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// Hand a ring stage back after every lane has read it, so that lane 0 may issue the bulk copy that refills it.
+// The reads are ordinary shared-memory loads (generic proxy); the refill is written by the bulk-copy engine (async proxy).  Program
+// order and bar.warp.sync order generic-proxy accesses only: without a proxy fence the refill of a stage is NOT ordered behind the
+// loads that read its previous contents, even when the same thread issues both.  Round 1 shipped without the fence and passed; in
+// round 2 a re-scheduled backward sweep (nothing consumed the loaded registers before the copy was issued any more) showed the hazard
+// whenever several tile ranges ran concurrently on an L2-resident batch: about one tile in a thousand per sweep read the references of
+// step t+3 at step t (tools/det_check.py; membar.cta alone did not help, fence.proxy.async does).
+__device__ __forceinline__ void stage_release()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
 }
 
 // ---- warp-private ring ---------------------------------------------------------------------------------------
@@ -161,7 +179,7 @@ __global__ void __launch_bounds__(64) k_forward_tma(ProblemT<F> P, TileList L, c
         xraw[5] = reinterpret_cast<const XT*>(st + St::X5_O)[lane];
 #pragma unroll
         for (int c = 0; c < NI; ++c) u[c] = reinterpret_cast<const F*>(st + St::U_O)[c * TILE + lane];
-        __syncwarp();  // every lane has read the stage: it can be refilled
+        stage_release();  // every lane has read the stage: it can be refilled
         if (lane == 0 && t + FWD_STAGES < nsteps) issue(t + FWD_STAGES);
         if (live) {
             finish_x(P, t, i, xraw, x);
@@ -240,7 +258,7 @@ __global__ void __launch_bounds__(64, 7) k_rollout_write_tma(ProblemT<F> P, Tile
 #pragma unroll
                 for (int c = 0; c < NS; ++c) xr[c] = reinterpret_cast<const F*>(st + St::XR_O)[c * TILE + lane];
             }
-            __syncwarp();
+            stage_release();
             if (lane == 0 && t + ROLL_STAGES < nsteps) issue(t + ROLL_STAGES);
             if (roll) {
                 if (shared_ref) load_ref(P, t, i, xr, ur);
@@ -344,7 +362,7 @@ __global__ void __launch_bounds__(64, 7) k_forward_cand0_tma(ProblemT<F> P, Tile
 #pragma unroll
             for (int c = 0; c < NS; ++c) xr[c] = reinterpret_cast<const F*>(st + St::XR_O)[c * TILE + lane];
         }
-        __syncwarp();  // every lane has read the stage: it can be refilled
+        stage_release();  // every lane has read the stage: it can be refilled
         if (lane == 0 && t + FC_STAGES < nsteps) issue(t + FC_STAGES);
         if (live) {
             F du[NI], xnom[NS];
@@ -442,7 +460,7 @@ __global__ void __launch_bounds__(64) k_backward_tma(ProblemT<F> P, TileList L, 
 #pragma unroll
             for (int c = 0; c < NS; ++c) xr[c] = reinterpret_cast<const F*>(st + St::XR_O)[c * TILE + lane];
         }
-        __syncwarp();
+        stage_release();
         if (lane == 0 && k + BWD_STAGES < nsteps) issue(k + BWD_STAGES);
         if (live) {
             if (shared_ref) load_ref(P, t, i, xr, ur);
@@ -515,7 +533,7 @@ __global__ void __launch_bounds__(64) k_gradient_tma(ProblemT<F> P, TileList L, 
 #pragma unroll
             for (int c = 0; c < NS; ++c) xr[c] = reinterpret_cast<const F*>(st + St::XR_O)[c * TILE + lane];
         }
-        __syncwarp();
+        stage_release();
         if (lane == 0 && k + BWD_STAGES < nsteps) issue(k + BWD_STAGES);
         if (live) {
             if (shared_ref) load_ref(P, t, i, xr, ur);
@@ -557,10 +575,6 @@ __global__ void __launch_bounds__(64) k_gradient_tma(ProblemT<F> P, TileList L, 
 constexpr int CR_SB = ACOC_CR_SB, CR_STAGES = ACOC_CR_STAGES;
 constexpr int CR_NV = 2 * NI + NI + NS;  // u, du, uref, xref
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 // the mbarrier receives one arrival when every cp.async issued so far by this thread has landed (the count is part of init)
 __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar)
 {
@@ -659,7 +673,7 @@ k_candidates_list(ProblemT<F> P, WorkList L, const F* __restrict__ U, const F* _
                     rollout_step<true, Q32, DG>(P.M, P.W, x, u, xr, ur, J);
                 }
             }
-            __syncwarp();
+            stage_release();
             if (lane == 0) mbar_arrive(empty + st);
         }
         if (work) {
