@@ -22,6 +22,7 @@ X_F64 = 32
 NO_TMA = 64
 NO_SPLIT = 128
 NO_FUSED = 256
+REFS_EXPANDED = 512
 METHOD_NEWTON, METHOD_GRADIENT = 0, 1
 PRIORITY_SHIFT = 16
 

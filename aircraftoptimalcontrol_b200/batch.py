@@ -41,11 +41,14 @@ class BatchedNewton:
     fused: fuse the LQ forward pass with the line-search rollouts that follow it -- with candidate 0 of the lazy search in one sweep
     (any batch size), and, for batches of at most 4096 instances (late survivor generations, single trajectories), with the whole
     Armijo search, get_update then being a copy of the chosen candidate (default; identical results, A/B measurements).
+    refs_compact: keep references built by set_refs_step / set_refs_acrobatic in their parametric form in HBM (default; the sweeps then
+    move 8 or 0 instead of 64 bytes of references per instance and step); False writes them out as per-instance arrays (ACOC_REFS_EXPANDED;
+    identical results, A/B measurements).
     """
 
     def __init__(self, n_instances, TT=1000, device=0, state="f32", refs_shared=False, armijo="speculative", params=None, generations=True,
                  max_iters=200, stepsize_0=1.0, cc=0.5, beta=0.7, armijo_maxiters=10, term_cond=-1e-6, exact_after=8, precision="f64",
-                 x_storage="auto", tma=True, split=True, fused=True, method="newton", priority=0):
+                 x_storage="auto", tma=True, split=True, fused=True, method="newton", priority=0, refs_compact=True):
         if state not in ("f32", "f64"):
             raise ValueError("state must be 'f32' or 'f64'")
         if armijo not in ("speculative", "lazy"):
@@ -62,7 +65,7 @@ class BatchedNewton:
         self.precision = precision
         flags = ((L.STATE_F64 if state == "f64" else 0) | (L.REFS_SHARED if refs_shared else 0) | (L.ARMIJO_LAZY if armijo == "lazy" else 0)
                  | (0 if generations else L.SOLVE_IN_PLACE) | (L.FP32 if precision == "f32" else 0) | (L.X_F64 if x_storage == "f64" else 0)
-                 | (0 if tma else L.NO_TMA) | (0 if split else L.NO_SPLIT) | (0 if fused else L.NO_FUSED)
+                 | (0 if tma else L.NO_TMA) | (0 if split else L.NO_SPLIT) | (0 if fused else L.NO_FUSED) | (0 if refs_compact else L.REFS_EXPANDED)
                  | ((max(0, min(15, int(priority))) & 15) << L.PRIORITY_SHIFT))
         self._h = C.c_void_p(None)
         L.check(L.lib().acoc_ctx_create(self.device, self.N, self.TT, flags, C.addressof(self._h)))

@@ -598,6 +598,35 @@ __global__ void __launch_bounds__(128) k_gen_refs(int N, int Np, int TT, const d
     }
 }
 
+// compact storage of the same references: only the speed reference is a per-instance array ([TT][Np/32][1][32]); X and Z are formed
+// in the sweeps from the tables (ProblemT, "parametric references").  Same expression as k_gen_refs: bit-identical values.
+__global__ void __launch_bounds__(128) k_gen_vref(int N, int Np, int TT, const double* __restrict__ vshape, const double* __restrict__ zf,
+                                                  const double* __restrict__ vx, double* __restrict__ vref)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double z = zf[i], v = vx[i], v2 = v * v;
+    for (int t = blockIdx.y; t < TT; t += gridDim.y) {
+        const double zd = vshape[t] * (z - 0.0);
+        vref[at(t, 1, 0, Np, i)] = sqrt(zd * zd + v2);
+    }
+}
+
+// parametric references written out in the expanded layout (acoc_get_refs)
+__global__ void __launch_bounds__(128) k_expand_refs(Problem P, double* __restrict__ xref, double* __restrict__ uref)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.N) return;
+    for (int t = blockIdx.y; t < P.TT; t += gridDim.y) {
+        double xr[NS], ur[NI];
+        load_ref(P, t, i, xr, ur);
+#pragma unroll
+        for (int c = 0; c < NS; ++c) xref[at(t, NS, c, P.Np, i)] = xr[c];
+#pragma unroll
+        for (int c = 0; c < NI; ++c) uref[at(t, NI, c, P.Np, i)] = ur[c];
+    }
+}
+
 __global__ void k_fill_int(int* p, int n, int v_lo, int n_lo, int v_hi)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -709,6 +738,9 @@ struct acoc_ctx {
     bool fp32 = false, x_float = false;
     void *X[3] = {nullptr, nullptr, nullptr}, *U[3] = {nullptr, nullptr, nullptr};
     void *DU = nullptr, *KSG = nullptr, *xref = nullptr, *uref = nullptr, *x0 = nullptr;
+    // parametric references (acoc_set_refs_generated): shared tables [TT], per-instance parameters [Np], stored speed reference
+    void *rp_tt = nullptr, *rp_zs = nullptr, *rp_zf = nullptr, *rp_vx = nullptr, *rp_v = nullptr;
+    bool rp_has_v = false;
     double* cand_steps = nullptr;
     double* stage = nullptr;  // device staging for layout conversion (always float64: the host side of the ABI)
     size_t stage_doubles = 0;
@@ -796,6 +828,11 @@ static ProblemT<F> prob(const acoc_ctx* c)
     P.W = weights_as<F>(c->P.W);
     P.N = c->P.N; P.Np = c->P.Np; P.TT = c->P.TT; P.q32 = c->P.q32; P.ref_shared = c->P.ref_shared;
     P.xref = (const F*)c->xref; P.uref = (const F*)c->uref; P.x0 = (const F*)c->x0;
+    P.ref_param = c->P.ref_param;
+    P.rp_tt = (const F*)c->rp_tt; P.rp_zs = (const F*)c->rp_zs; P.rp_zf = (const F*)c->rp_zf; P.rp_vx = (const F*)c->rp_vx;
+    P.rp_v = c->rp_has_v ? (const F*)c->rp_v : nullptr;
+    for (int k = 0; k < NS; ++k) P.rp_xc[k] = (F)c->P.rp_xc[k];
+    for (int k = 0; k < NI; ++k) P.rp_uc[k] = (F)c->P.rp_uc[k];
     return P;
 }
 #define TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
@@ -1265,7 +1302,21 @@ int acoc_set_refs(acoc_ctx* c, const double* xx_ref, const double* uu_ref)
         TRY(upload_soa(c, xx_ref, c->xref, c->N, 6, c->Np));
         TRY(upload_soa(c, uu_ref, c->uref, c->N, 2, c->Np));
     }
+    c->P.ref_param = 0;
     c->have_refs = true;
+    return 0;
+}
+
+// device buffers of the parametric references (allocated on first use: tables, per-instance parameters, speed reference)
+static int ensure_param_buffers(acoc_ctx* c)
+{
+    if (c->rp_tt) return 0;
+    const size_t T = c->TT, Np = c->Np;
+    TRY(dalloc_bytes(c, &c->rp_tt, T * sizeof(double)));
+    TRY(dalloc_bytes(c, &c->rp_zs, T * sizeof(double)));
+    TRY(dalloc_bytes(c, &c->rp_zf, Np * sizeof(double)));
+    TRY(dalloc_bytes(c, &c->rp_vx, Np * sizeof(double)));
+    TRY(dalloc_bytes(c, &c->rp_v, T * Np * sizeof(double)));
     return 0;
 }
 
@@ -1287,6 +1338,24 @@ int acoc_set_refs_generated(acoc_ctx* c, const double* tt, const double* zshape,
     for (int k = 0; k < 6; ++k) K.xc[k] = xconst[k];
     K.uc[0] = uconst[0]; K.uc[1] = uconst[1];
     const dim3 grid((unsigned)((N + 127) / 128), (unsigned)std::min<size_t>(T, 64));
+    if (!c->fp32 && !(c->flags & ACOC_REFS_EXPANDED)) {
+        // compact (parametric) storage: tables + parameters + the speed reference; the sweeps form X and Z themselves
+        TRY(ensure_param_buffers(c));
+        CK(cudaMemcpyAsync(c->rp_tt, d, T * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->rp_zs, d + T, T * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->rp_zf, d + 3 * T, N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->rp_vx, d + 3 * T + N, N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        if (vshape) k_gen_vref<<<grid, 128, 0, c->stream>>>(c->N, c->Np, c->TT, d + 2 * T, d + 3 * T, d + 3 * T + N, (double*)c->rp_v);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(c->stream));
+        c->rp_has_v = vshape != nullptr;
+        c->P.ref_param = 1;
+        for (int k = 0; k < 6; ++k) c->P.rp_xc[k] = xconst[k];
+        c->P.rp_uc[0] = uconst[0]; c->P.rp_uc[1] = uconst[1];
+        c->have_refs = true;
+        return 0;
+    }
+    c->P.ref_param = 0;
     if (c->fp32)
         k_gen_refs<float><<<grid, 128, 0, c->stream>>>(c->N, c->Np, c->TT, d, d + T, vshape ? d + 2 * T : nullptr, d + 3 * T, d + 3 * T + N, K,
                                                        (float*)c->xref, (float*)c->uref);
@@ -1600,13 +1669,14 @@ static int launch_list_candidates(acoc_ctx* c, const WorkList& L, int n, int c0,
         const int rows = std::min(c1 - c0, LIST_ROWS);
         const dim3 blk(TILE, rows + 1);
         const size_t sm = candidates_list_smem<F>();
-        const bool dg = c->P.W.diag != 0, sh = c->P.ref_shared != 0;
+        const bool dg = c->P.W.diag != 0;
+        const int rf = c->P.ref_param ? 2 : (c->P.ref_shared ? 1 : 0);
 #define ACOC_CL_LAUNCH(Q, DG, SH)                                                                                                   \
         do {                                                                                                                        \
             TRY(list_smem_attr(k_candidates_list<Q, F, LIST_ROWS, DG, SH>, sm));                                                    \
             k_candidates_list<Q, F, LIST_ROWS, DG, SH><<<(n + TILE - 1) / TILE, blk, sm, st>>>(P, L, U, DU, c->cand_steps, c0, c1, c->S.Jcand); \
         } while (0)
-#define ACOC_CL_LAUNCH2(Q, DG) do { if (sh) ACOC_CL_LAUNCH(Q, DG, true); else ACOC_CL_LAUNCH(Q, DG, false); } while (0)
+#define ACOC_CL_LAUNCH2(Q, DG) do { if (rf == 2) ACOC_CL_LAUNCH(Q, DG, 2); else if (rf == 1) ACOC_CL_LAUNCH(Q, DG, 1); else ACOC_CL_LAUNCH(Q, DG, 0); } while (0)
         if (c->P.q32) { if (dg) ACOC_CL_LAUNCH2(true, 1); else ACOC_CL_LAUNCH2(true, 0); }
         else { if (dg) ACOC_CL_LAUNCH2(false, 1); else ACOC_CL_LAUNCH2(false, 0); }
 #undef ACOC_CL_LAUNCH2
@@ -2054,7 +2124,18 @@ static int spawn_child(acoc_ctx* par, int n_active, acoc_ctx** out)
         TRY(move_rows_e(par, ch, par->X[sl], ch->X[sl], 6 * TT, true, xf, 6));
         TRY(move_rows_e(par, ch, par->U[sl], ch->U[sl], 2 * TT, true, ff, 2));
     }
-    if (par->flags & ACOC_REFS_SHARED) {
+    ch->P.ref_param = par->P.ref_param;
+    if (par->P.ref_param) {  // parametric references: tables, per-instance parameters and the stored speed reference of the survivors
+        TRY(ensure_param_buffers(ch));
+        CK(cudaMemcpyAsync(ch->rp_tt, par->rp_tt, (size_t)TT * sizeof(double), cudaMemcpyDeviceToDevice, par->stream));
+        CK(cudaMemcpyAsync(ch->rp_zs, par->rp_zs, (size_t)TT * sizeof(double), cudaMemcpyDeviceToDevice, par->stream));
+        TRY(move_rows(par, ch, (double*)par->rp_zf, (double*)ch->rp_zf, 1, true));
+        TRY(move_rows(par, ch, (double*)par->rp_vx, (double*)ch->rp_vx, 1, true));
+        if (par->rp_has_v) TRY(move_rows(par, ch, (double*)par->rp_v, (double*)ch->rp_v, TT, true, 1));
+        ch->rp_has_v = par->rp_has_v;
+        for (int k = 0; k < NS; ++k) ch->P.rp_xc[k] = par->P.rp_xc[k];
+        for (int k = 0; k < NI; ++k) ch->P.rp_uc[k] = par->P.rp_uc[k];
+    } else if (par->flags & ACOC_REFS_SHARED) {
         const size_t es = ff ? sizeof(float) : sizeof(double);
         CK(cudaMemcpyAsync(ch->xref, par->xref, (size_t)TT * 6 * es, cudaMemcpyDeviceToDevice, par->stream));
         CK(cudaMemcpyAsync(ch->uref, par->uref, (size_t)TT * 2 * es, cudaMemcpyDeviceToDevice, par->stream));
@@ -2332,6 +2413,11 @@ int acoc_get_refs(acoc_ctx* c, double* xx_ref, double* uu_ref)
     if (!c->have_refs) return fail(ACOC_ERR_STATE, "acoc_get_refs: no references set");
     TRY(use_device(c->device));
     const int n = c->P.ref_shared ? 1 : c->N, Np = c->P.ref_shared ? 1 : c->Np;
+    if (c->P.ref_param) {  // write the parametric references out in the expanded layout (the arrays are otherwise unused in this mode)
+        const dim3 grid((unsigned)((c->N + 127) / 128), (unsigned)std::min(c->TT, 64));
+        k_expand_refs<<<grid, 128, 0, c->stream>>>(prob<double>(c), (double*)c->xref, (double*)c->uref);
+        CK(cudaGetLastError());
+    }
     if (xx_ref) TRY(download_soa(c, c->xref, nullptr, nullptr, nullptr, xx_ref, n, 6, Np, 0));
     if (uu_ref) TRY(download_soa(c, c->uref, nullptr, nullptr, nullptr, uu_ref, n, 2, Np, 0));
     return 0;

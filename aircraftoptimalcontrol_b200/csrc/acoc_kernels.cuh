@@ -48,6 +48,18 @@ struct ProblemT {
     const F* xref;  // warp-tiled [TT][Np/32][6][32], or [TT][6] when shared
     const F* uref;  // warp-tiled [TT][Np/32][2][32], or [TT][2] when shared
     const F* x0;    // [6][Np]   x0 = xx_init[:,0]  (optcon.py:398)
+    // Parametric references (acoc_set_refs_generated): the references of the scripts are a two-parameter family per instance,
+    //   X_t = vx_i * tt_t,  Z_t = zs_t * zf_i,  V_t = v_{t,i} (stored, step maneuver) or xc[2],  theta, q, gamma = xc[3..5],  uref = uc
+    // (main_newton_method.py:96-142, acrobatic_newton.py:99-154), so the sweeps form X_t and Z_t with one multiplication each from two
+    // shared tables instead of streaming 64 bytes per instance and step: 8 bytes (V) or none.  The products are the ones the
+    // generator kernel stores in the expanded layout, so both layouts give bit-identical references.
+    int ref_param;     // 1: xref / uref are not used
+    const F* rp_tt;    // [TT] time grid
+    const F* rp_zs;    // [TT] height shape
+    const F* rp_zf;    // [Np] final / bump height per instance
+    const F* rp_vx;    // [Np] (xf - x0)/tf per instance
+    const F* rp_v;     // warp-tiled [TT][Np/32][1][32] speed reference, or nullptr: V_ref = rp_xc[2]
+    F rp_xc[NS], rp_uc[NI];
 };
 using Problem = ProblemT<double>;
 
@@ -59,9 +71,25 @@ ACOC_HD size_t at(int t, int C, int c, int Np, int i)
 }
 
 // references: per instance (warp-tiled like the trajectories) or one shared trajectory stored time-major [TT][C]
+// parametric references of instance i at time t from its parameters (zf, vx) and, if stored, its speed reference v
+template <typename F>
+ACOC_HD void param_xref(const ProblemT<F>& P, int t, F zf, F vx, F v, F* xr)
+{
+    xr[0] = vx * P.rp_tt[t];
+    xr[1] = P.rp_zs[t] * zf;
+    xr[2] = v;
+    xr[3] = P.rp_xc[3]; xr[4] = P.rp_xc[4]; xr[5] = P.rp_xc[5];
+}
+template <typename F>
+ACOC_HD F param_vref(const ProblemT<F>& P, int t, int i) { return P.rp_v ? P.rp_v[at(t, 1, 0, P.Np, i)] : P.rp_xc[2]; }
+
 template <typename F>
 ACOC_HD void load_xref(const ProblemT<F>& P, int t, int i, F* xr)
 {
+    if (P.ref_param) {
+        param_xref(P, t, P.rp_zf[i], P.rp_vx[i], param_vref(P, t, i), xr);
+        return;
+    }
     if (P.ref_shared) {
 #pragma unroll
         for (int c = 0; c < NS; ++c) xr[c] = P.xref[(size_t)t * NS + c];
@@ -74,6 +102,7 @@ template <typename F>
 ACOC_HD void load_ref(const ProblemT<F>& P, int t, int i, F* xr, F* ur)
 {
     load_xref(P, t, i, xr);
+    if (P.ref_param) { ur[0] = P.rp_uc[0]; ur[1] = P.rp_uc[1]; return; }
     if (P.ref_shared) {
 #pragma unroll
         for (int c = 0; c < NI; ++c) ur[c] = P.uref[(size_t)t * NI + c];

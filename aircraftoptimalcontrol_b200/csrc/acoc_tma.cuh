@@ -127,6 +127,30 @@ __device__ __forceinline__ int work_instance(const WorkList& L, int j, int N)
 // first element of the block of tile `tile` at time t in a warp-tiled array with C components
 __device__ __forceinline__ size_t tile_base(int t, int C, int Np, int tile) { return ((size_t)t * (size_t)(Np / TILE) + tile) * C * TILE; }
 
+// How a sweep gets the references of a step (ProblemT): per-instance arrays (one block per tile and step through the ring), one shared
+// trajectory (plain loads, L1-resident), or the parametric family (two multiplications from shared tables; the stored speed reference,
+// if there is one, is the only block that still travels through the ring, in the place of the xref block).
+template <typename F>
+struct RefMode {
+    bool shared, param, tiled, has_v;
+    F zf, vx;   // parameters of this lane's instance (parametric mode)
+    __device__ __forceinline__ RefMode(const ProblemT<F>& P, int i, bool live)
+    {
+        shared = P.ref_shared != 0; param = P.ref_param != 0; tiled = !shared && !param; has_v = param && P.rp_v != nullptr;
+        zf = (param && live) ? P.rp_zf[i] : F(0.0);
+        vx = (param && live) ? P.rp_vx[i] : F(0.0);
+    }
+    // references of (t, i) for the modes that do not come out of the ring stage; v = this lane's entry of the stage's V block
+    __device__ __forceinline__ void fill(const ProblemT<F>& P, int t, int i, F v, F* xr, F* ur) const
+    {
+        if (shared) load_ref(P, t, i, xr, ur);
+        else if (param) {
+            param_xref(P, t, zf, vx, has_v ? v : P.rp_xc[2], xr);
+            ur[0] = P.rp_uc[0]; ur[1] = P.rp_uc[1];
+        }
+    }
+};
+
 // =================================================================================================================
 // LQ forward pass + descent (forward_lq_instance): in K/sigma/g, x, u per step; out du
 // =================================================================================================================
@@ -225,17 +249,18 @@ __global__ void __launch_bounds__(64, 7) k_rollout_write_tma(ProblemT<F> P, Tile
     if (__any_sync(0xffffffffu, roll)) {
         WarpRing<ROLL_STAGES, St::BYTES> ring;
         ring.init(smem, warp, nw, lane);
-        const bool shared_ref = P.ref_shared != 0;
+        const RefMode<F> rm(P, i, i < P.N);
         auto issue = [&](int t) {
             unsigned char* st = ring.stage(t);
             uint64_t* b = ring.barrier(t);
-            mbar_arrive_expect_tx(b, shared_ref ? 2 * St::U_B : St::BYTES);
+            mbar_arrive_expect_tx(b, 2 * St::U_B + (rm.tiled ? St::U_B + St::XR_B : 0) + (rm.has_v ? (uint32_t)(TILE * sizeof(F)) : 0));
             tma_load(st + St::U_O, U + tile_base(t, NI, Np, tile), St::U_B, b);
             tma_load(st + St::DU_O, DU + tile_base(t, NI, Np, tile), St::U_B, b);
-            if (!shared_ref) {
+            if (rm.tiled) {
                 tma_load(st + St::UR_O, P.uref + tile_base(t, NI, Np, tile), St::U_B, b);
                 tma_load(st + St::XR_O, P.xref + tile_base(t, NS, Np, tile), St::XR_B, b);
-            }
+            } else if (rm.has_v)
+                tma_load(st + St::XR_O, P.rp_v + tile_base(t, 1, Np, tile), (uint32_t)(TILE * sizeof(F)), b);
         };
         if (lane == 0)
             for (int t = 0; t < ROLL_STAGES && t < nsteps; ++t) issue(t);
@@ -252,16 +277,17 @@ __global__ void __launch_bounds__(64, 7) k_rollout_write_tma(ProblemT<F> P, Tile
                 u[c] = reinterpret_cast<const F*>(st + St::U_O)[c * TILE + lane];
                 du[c] = reinterpret_cast<const F*>(st + St::DU_O)[c * TILE + lane];
             }
-            if (!shared_ref) {
+            F vv = F(0.0);
+            if (rm.tiled) {
 #pragma unroll
                 for (int c = 0; c < NI; ++c) ur[c] = reinterpret_cast<const F*>(st + St::UR_O)[c * TILE + lane];
 #pragma unroll
                 for (int c = 0; c < NS; ++c) xr[c] = reinterpret_cast<const F*>(st + St::XR_O)[c * TILE + lane];
-            }
+            } else if (rm.has_v) vv = reinterpret_cast<const F*>(st + St::XR_O)[lane];
             stage_release();
             if (lane == 0 && t + ROLL_STAGES < nsteps) issue(t + ROLL_STAGES);
             if (roll) {
-                if (shared_ref) load_ref(P, t, i, xr, ur);
+                rm.fill(P, t, i, vv, xr, ur);
 #pragma unroll
                 for (int c = 0; c < NI; ++c) u[c] = u[c] + s * du[c];  // optcon.py:197 / :253
                 store_x(Xn, t, Np, i, x);
@@ -322,19 +348,20 @@ __global__ void __launch_bounds__(64, 7) k_forward_cand0_tma(ProblemT<F> P, Tile
     const int TT = P.TT, Np = P.Np, i = tile * TILE + lane, nsteps = TT - 1;
     const bool live = i < P.N;                          // the forward pass runs for finished lanes of a live tile too (whole du lines)
     const bool act = live && S.status[i] == ST_ACTIVE;  // the rollout only for instances that are still iterating
-    const bool shared_ref = P.ref_shared != 0;
+    const RefMode<F> rm(P, i, live);
     auto issue = [&](int t) {
         unsigned char* st = ring.stage(t);
         uint64_t* b = ring.barrier(t);
-        mbar_arrive_expect_tx(b, Fw::BYTES_TX + (shared_ref ? 0 : St::U_B + St::XR_B));
+        mbar_arrive_expect_tx(b, Fw::BYTES_TX + (rm.tiled ? St::U_B + St::XR_B : 0) + (rm.has_v ? (uint32_t)(TILE * sizeof(F)) : 0));
         tma_load(st + St::KSG_O, KSG + tile_base(t, 16, Np, tile), Fw::KSG_B, b);
         tma_load(st + St::X23_O, X + tile_base(t, NS, Np, tile) + 2 * TILE, 2 * Fw::XC_B, b);
         tma_load(st + St::X5_O, X + tile_base(t, NS, Np, tile) + 5 * TILE, Fw::XC_B, b);
         tma_load(st + St::U_O, U + tile_base(t, NI, Np, tile), St::U_B, b);
-        if (!shared_ref) {
+        if (rm.tiled) {
             tma_load(st + St::UR_O, P.uref + tile_base(t, NI, Np, tile), St::U_B, b);
             tma_load(st + St::XR_O, P.xref + tile_base(t, NS, Np, tile), St::XR_B, b);
-        }
+        } else if (rm.has_v)
+            tma_load(st + St::XR_O, P.rp_v + tile_base(t, 1, Np, tile), (uint32_t)(TILE * sizeof(F)), b);
     };
     if (lane == 0)
         for (int t = 0; t < FC_STAGES && t < nsteps; ++t) issue(t);
@@ -356,12 +383,13 @@ __global__ void __launch_bounds__(64, 7) k_forward_cand0_tma(ProblemT<F> P, Tile
         xraw[5] = reinterpret_cast<const XT*>(st + St::X5_O)[lane];
 #pragma unroll
         for (int c = 0; c < NI; ++c) u[c] = reinterpret_cast<const F*>(st + St::U_O)[c * TILE + lane];
-        if (!shared_ref) {
+        F vv = F(0.0);
+        if (rm.tiled) {
 #pragma unroll
             for (int c = 0; c < NI; ++c) ur[c] = reinterpret_cast<const F*>(st + St::UR_O)[c * TILE + lane];
 #pragma unroll
             for (int c = 0; c < NS; ++c) xr[c] = reinterpret_cast<const F*>(st + St::XR_O)[c * TILE + lane];
-        }
+        } else if (rm.has_v) vv = reinterpret_cast<const F*>(st + St::XR_O)[lane];
         stage_release();  // every lane has read the stage: it can be refilled
         if (lane == 0 && t + FC_STAGES < nsteps) issue(t + FC_STAGES);
         if (live) {
@@ -372,7 +400,7 @@ __global__ void __launch_bounds__(64, 7) k_forward_cand0_tma(ProblemT<F> P, Tile
             finish_x(P, t, i, xraw, xnom);
             forward_advance(P.M, xnom, u, du, dx);
             if (act) {
-                if (shared_ref) load_ref(P, t, i, xr, ur);
+                rm.fill(P, t, i, vv, xr, ur);
                 F uc[NI];
 #pragma unroll
                 for (int c = 0; c < NI; ++c) uc[c] = u[c] + s * du[c];  // optcon.py:197 / :253
@@ -422,19 +450,20 @@ __global__ void __launch_bounds__(64) k_backward_tma(ProblemT<F> P, TileList L, 
     ring.init(smem, warp, nw, lane);
     const int TT = P.TT, Np = P.Np, i = tile * TILE + lane, nsteps = TT - 1;
     const bool live = i < P.N;
-    const bool shared_ref = P.ref_shared != 0;
+    const RefMode<F> rm(P, i, live);
     // ring step k <-> time t = TT-2-k
     auto issue = [&](int k) {
         const int t = TT - 2 - k;
         unsigned char* st = ring.stage(k);
         uint64_t* b = ring.barrier(k);
-        mbar_arrive_expect_tx(b, shared_ref ? St::U_B + St::X_B : St::BYTES);
+        mbar_arrive_expect_tx(b, St::U_B + St::X_B + (rm.tiled ? St::U_B + St::XR_B : 0) + (rm.has_v ? (uint32_t)(TILE * sizeof(F)) : 0));
         tma_load(st + St::U_O, U + tile_base(t, NI, Np, tile), St::U_B, b);
         tma_load(st + St::X_O, X + tile_base(t, NS, Np, tile), St::X_B, b);
-        if (!shared_ref) {
+        if (rm.tiled) {
             tma_load(st + St::UR_O, P.uref + tile_base(t, NI, Np, tile), St::U_B, b);
             tma_load(st + St::XR_O, P.xref + tile_base(t, NS, Np, tile), St::XR_B, b);
-        }
+        } else if (rm.has_v)
+            tma_load(st + St::XR_O, P.rp_v + tile_base(t, 1, Np, tile), (uint32_t)(TILE * sizeof(F)), b);
     };
     if (lane == 0)
         for (int k = 0; k < BWD_STAGES && k < nsteps; ++k) issue(k);
@@ -454,16 +483,17 @@ __global__ void __launch_bounds__(64) k_backward_tma(ProblemT<F> P, TileList L, 
         for (int c = 0; c < NS; ++c) xraw[c] = reinterpret_cast<const XT*>(st + St::X_O)[c * TILE + lane];
 #pragma unroll
         for (int c = 0; c < NI; ++c) u[c] = reinterpret_cast<const F*>(st + St::U_O)[c * TILE + lane];
-        if (!shared_ref) {
+        F vv = F(0.0);
+        if (rm.tiled) {
 #pragma unroll
             for (int c = 0; c < NI; ++c) ur[c] = reinterpret_cast<const F*>(st + St::UR_O)[c * TILE + lane];
 #pragma unroll
             for (int c = 0; c < NS; ++c) xr[c] = reinterpret_cast<const F*>(st + St::XR_O)[c * TILE + lane];
-        }
+        } else if (rm.has_v) vv = reinterpret_cast<const F*>(st + St::XR_O)[lane];
         stage_release();
         if (lane == 0 && k + BWD_STAGES < nsteps) issue(k + BWD_STAGES);
         if (live) {
-            if (shared_ref) load_ref(P, t, i, xr, ur);
+            rm.fill(P, t, i, vv, xr, ur);
             finish_x(P, t, i, xraw, x);
             F K[2 * NS], sig[NI], g[NI];
             nreg += backward_step<EXACT, DG>(P.M, P.W, x, u, xr, ur, Pm, p, lam, K, sig, g);
@@ -494,18 +524,19 @@ __global__ void __launch_bounds__(64) k_gradient_tma(ProblemT<F> P, TileList L, 
     ring.init(smem, warp, nw, lane);
     const int TT = P.TT, Np = P.Np, i = tile * TILE + lane, nsteps = TT - 1;
     const bool live = i < P.N;
-    const bool shared_ref = P.ref_shared != 0;
+    const RefMode<F> rm(P, i, live);
     auto issue = [&](int k) {  // ring step k <-> time t = TT-2-k
         const int t = TT - 2 - k;
         unsigned char* st = ring.stage(k);
         uint64_t* b = ring.barrier(k);
-        mbar_arrive_expect_tx(b, shared_ref ? St::U_B + St::X_B : St::BYTES);
+        mbar_arrive_expect_tx(b, St::U_B + St::X_B + (rm.tiled ? St::U_B + St::XR_B : 0) + (rm.has_v ? (uint32_t)(TILE * sizeof(F)) : 0));
         tma_load(st + St::U_O, U + tile_base(t, NI, Np, tile), St::U_B, b);
         tma_load(st + St::X_O, X + tile_base(t, NS, Np, tile), St::X_B, b);
-        if (!shared_ref) {
+        if (rm.tiled) {
             tma_load(st + St::UR_O, P.uref + tile_base(t, NI, Np, tile), St::U_B, b);
             tma_load(st + St::XR_O, P.xref + tile_base(t, NS, Np, tile), St::XR_B, b);
-        }
+        } else if (rm.has_v)
+            tma_load(st + St::XR_O, P.rp_v + tile_base(t, 1, Np, tile), (uint32_t)(TILE * sizeof(F)), b);
     };
     if (lane == 0)
         for (int k = 0; k < BWD_STAGES && k < nsteps; ++k) issue(k);
@@ -527,16 +558,17 @@ __global__ void __launch_bounds__(64) k_gradient_tma(ProblemT<F> P, TileList L, 
         for (int c = 0; c < NS; ++c) xraw[c] = reinterpret_cast<const XT*>(st + St::X_O)[c * TILE + lane];
 #pragma unroll
         for (int c = 0; c < NI; ++c) u[c] = reinterpret_cast<const F*>(st + St::U_O)[c * TILE + lane];
-        if (!shared_ref) {
+        F vv = F(0.0);
+        if (rm.tiled) {
 #pragma unroll
             for (int c = 0; c < NI; ++c) ur[c] = reinterpret_cast<const F*>(st + St::UR_O)[c * TILE + lane];
 #pragma unroll
             for (int c = 0; c < NS; ++c) xr[c] = reinterpret_cast<const F*>(st + St::XR_O)[c * TILE + lane];
-        }
+        } else if (rm.has_v) vv = reinterpret_cast<const F*>(st + St::XR_O)[lane];
         stage_release();
         if (lane == 0 && k + BWD_STAGES < nsteps) issue(k + BWD_STAGES);
         if (live) {
-            if (shared_ref) load_ref(P, t, i, xr, ur);
+            rm.fill(P, t, i, vv, xr, ur);
             finish_x(P, t, i, xraw, x);
             F du[NI];
             gradient_step(P.M, P.W, x, u, xr, ur, lam, du, sq);
@@ -591,7 +623,7 @@ constexpr size_t candidates_list_smem() { return (size_t)CR_STAGES * CR_SB * CR_
 
 // blockDim = (32, rows + 1): warps 0..rows-1 roll candidate c0 + pass*rows + y (as many passes as it takes to reach c1), warp `rows`
 // gathers.  Jcand[c][i] receives the cost.
-template <bool Q32, typename F, int MAXROWS, int DG, bool SHARED>
+template <bool Q32, typename F, int MAXROWS, int DG, int REFS>
 __global__ void __launch_bounds__(TILE * (MAXROWS + 1), ACOC_CAND_MINB)
 k_candidates_list(ProblemT<F> P, WorkList L, const F* __restrict__ U, const F* __restrict__ DU, const double* __restrict__ steps, int c0, int c1,
                   double* __restrict__ Jcand)
@@ -609,7 +641,8 @@ k_candidates_list(ProblemT<F> P, WorkList L, const F* __restrict__ U, const F* _
     }
     __syncthreads();
     const int TT = P.TT, Np = P.Np, nsteps = TT - 1, nst = (nsteps + CR_SB - 1) / CR_SB;
-    constexpr bool shared_ref = SHARED;  // (P.ref_shared, known at compile time here)
+    constexpr bool shared_ref = REFS == 1, param_ref = REFS == 2;  // 0: per-instance arrays (P.ref_shared / P.ref_param, known at compile time here)
+    const bool has_v = param_ref && P.rp_v != nullptr;
     const int passes = (c1 - c0 + rows - 1) / rows;
     if (row == rows) {  // ---- producer warp
         const size_t tstride_u = (size_t)(Np / TILE) * NI * TILE, tstride_x = (size_t)(Np / TILE) * NS * TILE;
@@ -628,14 +661,15 @@ k_candidates_list(ProblemT<F> P, WorkList L, const F* __restrict__ U, const F* _
                     cp_async_elem<sizeof(F)>(d + TILE, pu + TILE);
                     cp_async_elem<sizeof(F)>(d + 2 * TILE, pd);
                     cp_async_elem<sizeof(F)>(d + 3 * TILE, pd + TILE);
-                    if (!shared_ref) {
+                    if (!shared_ref && !param_ref) {
                         const F* pr = P.uref + ou + (size_t)t * tstride_u;
                         const F* px = P.xref + ox + (size_t)t * tstride_x;
                         cp_async_elem<sizeof(F)>(d + 4 * TILE, pr);
                         cp_async_elem<sizeof(F)>(d + 5 * TILE, pr + TILE);
 #pragma unroll
                         for (int c = 0; c < NS; ++c) cp_async_elem<sizeof(F)>(d + (6 + c) * TILE, px + c * TILE);
-                    }
+                    } else if (has_v)
+                        cp_async_elem<sizeof(F)>(d + 8 * TILE, P.rp_v + at(t, 1, 0, Np, i));  // (the slot of xref[2])
                 }
             }
             cp_async_mbar_arrive(full + st);
@@ -648,6 +682,7 @@ k_candidates_list(ProblemT<F> P, WorkList L, const F* __restrict__ U, const F* _
         const int c = c0 + pass * rows + row;
         const bool work = i >= 0 && c < c1;
         const F s = (F)(c < c1 ? steps[c] : 0.0);
+        const F zf_i = (param_ref && work) ? P.rp_zf[i] : F(0.0), vx_i = (param_ref && work) ? P.rp_vx[i] : F(0.0);
         F x[NS], u[NI], xr[NS], ur[NI];
         double J = 0.0;
 #pragma unroll
@@ -664,7 +699,10 @@ k_candidates_list(ProblemT<F> P, WorkList L, const F* __restrict__ U, const F* _
 #pragma unroll
                     for (int cc = 0; cc < NI; ++cc) u[cc] = d[cc * TILE] + s * d[(2 + cc) * TILE];  // optcon.py:197 / :253
                     if (shared_ref) load_ref(P, t, i, xr, ur);
-                    else {
+                    else if (param_ref) {
+                        param_xref(P, t, zf_i, vx_i, has_v ? d[8 * TILE] : P.rp_xc[2], xr);
+                        ur[0] = P.rp_uc[0]; ur[1] = P.rp_uc[1];
+                    } else {
 #pragma unroll
                         for (int cc = 0; cc < NI; ++cc) ur[cc] = d[(4 + cc) * TILE];
 #pragma unroll

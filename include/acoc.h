@@ -58,6 +58,9 @@ typedef enum acoc_status {
                                     concurrently on one GPU (the sub-batches of a pipelined solve) then finish one after the other instead of
                                     all at the end, so that the device->host copy of one overlaps the iterations of the next.  No effect
                                     on results. */
+#define ACOC_REFS_EXPANDED 512u  /* acoc_set_refs_generated: write the generated references out as per-instance arrays (64 B per
+                                    instance and step, as acoc_set_refs would hold them) instead of keeping them in their parametric
+                                    form (8 B or none); bit-identical results, A/B tests */
 #define ACOC_X_F64 32u           /* keep the state iterates in float64 device buffers even when every stored state is a float32 value
                                     (ACOC_STATE_F32); results are bit-identical either way, this only costs bandwidth (A/B tests) */
 
@@ -157,8 +160,11 @@ int acoc_set_refs(acoc_ctx* ctx, const double* xx_ref, const double* uu_ref);
  * xx_ref / uu_ref are built in HBM from per-instance parameters zf[N] (final / bump height), vx[N] (= (xf - x0)/tf) and shared time
  * bases tt[TT], zshape[TT], vshape[TT] (NULL: V_ref = xconst[2]) that the caller computed with the scripts' own numpy code:
  *   X = 0 + vx*tt,  Z = 0 + zshape*(zf - 0),  V = ((vshape*zf)**2 + vx**2)**0.5,  theta, q, gamma = xconst[3..5],  uu_ref = uconst[0..1]
- * in the scripts' operation order, so the arrays are bit-identical to what the scripts build on the host and acoc_set_refs would
- * upload (16 B per instance cross the bus instead of 64 KB).  Not for ACOC_REFS_SHARED contexts. */
+ * in the scripts' operation order, so the references are bit-identical to what the scripts build on the host and acoc_set_refs
+ * would upload (16 B per instance cross the bus instead of 64 KB).  The context keeps them in this parametric form -- the sweeps form
+ * X and Z from the tables with one multiplication each, only V (step maneuver) is a stored per-instance array -- which removes 56-64 of
+ * the ~230-280 bytes a sweep moves per instance and step (ACOC_REFS_EXPANDED keeps per-instance arrays instead; same results up to the
+ * sign of a zero reference).  Not for ACOC_REFS_SHARED contexts. */
 int acoc_set_refs_generated(acoc_ctx* ctx, const double* tt, const double* zshape, const double* vshape, const double* zf,
                             const double* vx, const double* xconst, const double* uconst);
 /* the references held by the context, in acoc_set_refs' layout (either pointer may be NULL) */

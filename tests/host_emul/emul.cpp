@@ -99,7 +99,7 @@ int newton_impl(const NewtonArgs& a)
     ProblemT<F> P;
     P.M = model_as<F>(make_model(a.params));
     P.W = weights_as<F>(W64);
-    P.N = N; P.Np = Np; P.TT = TT; P.q32 = a.state_f64 ? 0 : 1; P.ref_shared = a.ref_shared;
+    P.N = N; P.Np = Np; P.TT = TT; P.q32 = a.state_f64 ? 0 : 1; P.ref_shared = a.ref_shared; P.ref_param = 0;
     P.xref = xref.data(); P.uref = uref.data(); P.x0 = x0.data();
     NewtonOpts O;
     O.max_iters = max_iters; O.armijo_maxiters = armijo_maxiters; O.exact_after = a.exact_after;
@@ -251,7 +251,7 @@ void emul_rollout_batch(int N, int TT, const double* params, int state_f64, cons
     for (int i = 0; i < N; ++i) for (int c = 0; c < 6; ++c) x0s[(size_t)c * Np + i] = x0[(size_t)i * 6 + c];
     Problem P;
     P.M = make_model(params); fill_weights(&P.W, Q, R, QT);
-    P.N = N; P.Np = Np; P.TT = TT; P.q32 = state_f64 ? 0 : 1; P.ref_shared = 0;
+    P.N = N; P.Np = Np; P.TT = TT; P.q32 = state_f64 ? 0 : 1; P.ref_shared = 0; P.ref_param = 0;
     P.xref = xr.data(); P.uref = ur.data(); P.x0 = x0s.data();
     for (int i = 0; i < N; ++i) {
         J[i] = rollout_q<true, true>(P, (const double*)U.data(), (const double*)DU.data(), s[i], Xn.data(), Un.data(), i);
@@ -277,7 +277,7 @@ void emul_lqr_tracking(int N, int TT, const double* params, int state_f64, const
     std::vector<double> xs((size_t)6 * Np, 0.0), Xn((size_t)TT * 6 * Np), Un((size_t)TT * 2 * Np);
     for (int i = 0; i < N; ++i) for (int c = 0; c < 6; ++c) xs[(size_t)c * Np + i] = xx_opt[(size_t)c * TT] + delta[(size_t)i * 6 + c];
     Problem P;
-    P.M = M; P.N = N; P.Np = Np; P.TT = TT; P.q32 = state_f64 ? 0 : 1; P.ref_shared = 1;
+    P.M = M; P.N = N; P.Np = Np; P.TT = TT; P.q32 = state_f64 ? 0 : 1; P.ref_shared = 1; P.ref_param = 0;
     P.xref = xo.data(); P.uref = uo.data(); P.x0 = xs.data();
     for (int i = 0; i < N; ++i) {
         if (P.q32) track_instance<true>(P, Kt.data(), xo.data(), uo.data(), xs.data(), Xn.data(), Un.data(), i);
@@ -293,7 +293,7 @@ void emul_init_guess(int N, int TT, const double* params, int state_f64, const d
     std::vector<double> xr((size_t)TT * 6 * Np), Xn((size_t)TT * 6 * Np), Un((size_t)TT * 2 * Np);
     to_soa(xx_ref, xr.data(), N, 6, TT, Np);
     Problem P;
-    P.M = make_model(params); P.N = N; P.Np = Np; P.TT = TT; P.q32 = state_f64 ? 0 : 1; P.ref_shared = 0;
+    P.M = make_model(params); P.N = N; P.Np = Np; P.TT = TT; P.q32 = state_f64 ? 0 : 1; P.ref_shared = 0; P.ref_param = 0;
     P.xref = xr.data(); P.uref = nullptr; P.x0 = nullptr;
     for (int i = 0; i < N; ++i) {
         if (P.q32) init_guess_instance<true>(P, kp, kt, (const double*)nullptr, Xn.data(), Un.data(), (double*)nullptr, i);

@@ -309,3 +309,53 @@ def test_pipelined_generated_refs_and_f32_download_equal_host_path(gpu):
         xb, ub, sb = pn.solve(refs=("acrobatic", zf5, 18, 0.3), dx0=dx0, x_dtype=np.float32)
     assert np.array_equal(xa[:, :, 1:], xb[:, :, 1:].astype(np.float64)) and np.array_equal(ua, ub)
     assert np.array_equal(sa["iters"], sb["iters"]) and np.array_equal(sa["J"], sb["J"])
+
+
+@pytest.mark.parametrize("kind,n,TT,kw", [("step", 4500, 200, dict(armijo="lazy")), ("step", 300, 300, dict(armijo="speculative")),
+                                          ("acrobatic", 4500, 200, dict(armijo="lazy", max_iters=14)), ("step", 700, 150, dict(armijo="lazy", tma=False)),
+                                          ("step", 40001, 48, dict(armijo="lazy"))])
+def test_compact_references_identical_solves(gpu, kind, n, TT, kw):
+    """References built on the device are kept in their parametric form (X, Z formed in the sweeps from shared tables, only V stored:
+    8 or 0 instead of 64 bytes per instance and step).  Whole solves must be bit-identical to the same references written out as
+    per-instance arrays (refs_compact=False) and to the host arrays uploaded with set_refs -- through the TMA sweeps, the candidate
+    ring, the fused small-batch search, the plain-load kernels, tile ranges and survivor generations."""
+    from aircraftoptimalcontrol_b200 import refgen
+    rng = np.random.default_rng(n + TT)
+    tf = TT * 1e-3
+    dx0 = None
+    if kind == "step":
+        zf, xf = rng.uniform(1.5, 3.5, n), rng.uniform(14, 18, n)
+        xr, ur = refgen.step_problem(xf, zf, tf=tf, TT=TT)
+        Q, R, QT = refgen.weights("step")
+    else:
+        zf = rng.uniform(2.0, 3.4, n)
+        xr, ur = refgen.acrobatic_problem(zf, tf=tf, TT=TT)
+        dx0 = rng.normal(size=(n, 6)) * np.array([.05, .05, .2, .02, .05, .02])
+        Q, R, QT = refgen.weights("acro")
+    out = []
+    for mode in ("host", "expanded", "compact"):
+        with gpu.BatchedNewton(n, TT=TT, refs_compact=(mode != "expanded"), **kw) as bn:
+            bn.set_weights(Q, R, QT)
+            if mode == "host":
+                bn.set_refs(xr, ur)
+            elif kind == "step":
+                bn.set_refs_step(zf, xf, tf=tf)
+            else:
+                bn.set_refs_acrobatic(zf, tf=tf)
+            bn.init_guess(dx0=dx0)
+            first = bn.iterate_at(0)
+            total = bn.solve()
+            out.append((total, first, bn.result(), bn.iterate_at(0), bn.history(), bn.stats()))
+            if mode == "compact":
+                gx, gu = bn.refs()
+                assert np.array_equal(gx, xr) and np.array_equal(gu, ur)
+    a = out[0]
+    assert a[0] > n
+    for b in out[1:]:
+        assert a[0] == b[0]
+        for k in (1, 2, 3):
+            assert np.array_equal(a[k][0], b[k][0]) and np.array_equal(a[k][1], b[k][1]), k
+        for k in ("JJ", "descent", "stepsize", "n_armijo"):
+            assert np.array_equal(a[4][k], b[4][k]), k
+        for k in ("iters", "status", "J", "descent", "n_reg"):
+            assert np.array_equal(a[5][k], b[5][k]), k
