@@ -149,6 +149,16 @@ struct RefMode {
             ur[0] = P.rp_uc[0]; ur[1] = P.rp_uc[1];
         }
     }
+    // the same with the table entries tt_t, zs_t already in registers (the latency-bound backward sweep fetches them one step ahead)
+    __device__ __forceinline__ void fill(const ProblemT<F>& P, int t, int i, F v, F tt_t, F zs_t, F* xr, F* ur) const
+    {
+        if (shared) load_ref(P, t, i, xr, ur);
+        else if (param) {
+            xr[0] = vx * tt_t; xr[1] = zs_t * zf; xr[2] = has_v ? v : P.rp_xc[2];
+            xr[3] = P.rp_xc[3]; xr[4] = P.rp_xc[4]; xr[5] = P.rp_xc[5];
+            ur[0] = P.rp_uc[0]; ur[1] = P.rp_uc[1];
+        }
+    }
 };
 
 // =================================================================================================================
@@ -474,8 +484,12 @@ __global__ void __launch_bounds__(64) k_backward_tma(ProblemT<F> P, TileList L, 
         load_x(P, X, TT - 1, i, x);
         backward_terminal<DG>(P.W, x, xr, Pm, p, lam);
     }
+    F tt_n = F(0.0), zs_n = F(0.0);  // parametric references: table entries of the next step, fetched one step ahead
+    if (rm.param) { tt_n = P.rp_tt[TT - 2]; zs_n = P.rp_zs[TT - 2]; }
     for (int k = 0; k < nsteps; ++k) {
         const int t = TT - 2 - k;
+        const F tt_c = tt_n, zs_c = zs_n;
+        if (rm.param && t > 0) { tt_n = P.rp_tt[t - 1]; zs_n = P.rp_zs[t - 1]; }
         ring.wait(k);
         const unsigned char* st = ring.stage(k);
         XT xraw[NS];
@@ -493,7 +507,7 @@ __global__ void __launch_bounds__(64) k_backward_tma(ProblemT<F> P, TileList L, 
         stage_release();
         if (lane == 0 && k + BWD_STAGES < nsteps) issue(k + BWD_STAGES);
         if (live) {
-            rm.fill(P, t, i, vv, xr, ur);
+            rm.fill(P, t, i, vv, tt_c, zs_c, xr, ur);
             finish_x(P, t, i, xraw, x);
             F K[2 * NS], sig[NI], g[NI];
             nreg += backward_step<EXACT, DG>(P.M, P.W, x, u, xr, ur, Pm, p, lam, K, sig, g);

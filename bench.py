@@ -49,13 +49,20 @@ BYTES = dict(backward=128 + 128, forward=128 + 64 + 16, cost=128, candidate=32 +
 
 def moved_bytes(args):
     """Bytes per instance per time step the kernels actually move in the selected mode.  The parity path stores the float32-quantised
-    states as float (24 instead of 48 B per state read/write, bit-identical results); the FP32 mode halves everything."""
+    states as float (24 instead of 48 B per state read/write, bit-identical results); references built on the device stay parametric
+    (8 B of stored speed reference for the step maneuver, nothing for the acrobatic one, instead of 64 B); the FP32 mode halves
+    everything (and keeps expanded references)."""
     if args.precision == "f32":
         return {k: v // 2 for k, v in BYTES.items()}
+    mb = dict(BYTES)
     if args.state == "f32" and args.x_storage == "auto":
-        return dict(backward=BYTES["backward"] - 24, forward=BYTES["forward"] - 24, cost=BYTES["cost"] - 24, candidate=BYTES["candidate"],
-                    candidate_write=BYTES["candidate_write"] - 24, update=BYTES["update"] - 24)
-    return dict(BYTES)
+        for k in ("backward", "forward", "cost", "candidate_write", "update"):
+            mb[k] -= 24
+    if args.refs == "compact":
+        saved = 56 if args.workload == "step" else 64
+        for k in ("backward", "cost", "candidate", "candidate_write", "update"):
+            mb[k] -= saved
+    return mb
 
 
 def load_peaks():
@@ -224,8 +231,10 @@ def config_dict(args, n_per_gpu, world):
     return {"workload": names[args.workload],
             "instances_per_gpu": n_per_gpu, "instances_total": n_per_gpu * world, "TT": TT, "ns": 6, "ni": 2,
             "state_quant": args.state, "precision": args.precision,
-            "state_storage": "float32 in HBM (lossless: quantised states are float32 values)" if moved_bytes(args)["backward"] == 232 else
+            "state_storage": "float32 in HBM (lossless: quantised states are float32 values)" if (args.precision == "f64" and args.state == "f32" and args.x_storage == "auto") else
                              ("float32" if args.precision == "f32" else "float64"),
+            "references": {"compact": "built on the device (acoc_set_refs_generated), kept parametric in HBM", "expanded": "built on the device, per-instance arrays",
+                           "host": "per-instance arrays uploaded from the host"}[args.refs if args.precision == "f64" else ("expanded" if args.refs == "compact" else args.refs)],
             "armijo": args.armijo, "armijo_maxiters": 10, "max_iters": 200,
             "step": "one Newton iteration over the whole batch (iterations W..W+K-1 of the solve)",
             "l2": "working set per GPU (%.1f GB) >> 126 MB L2, no flush needed" % (n_per_gpu * 400e3 / 1e9),
@@ -282,7 +291,7 @@ def roofline_tables(args, n, K, W, hist, phases, peaks, peak_src, fp64_peak, fus
         upd_k = a_k
         upd_lanes_k = lanes_k
     MB = moved_bytes(args)
-    x_float = MB["forward"] != BYTES["forward"]
+    x_float = args.precision == "f64" and args.state == "f32" and args.x_storage == "auto"
     fwd_alg = BYTES["forward"] + (BYTES["candidate_write"] if fused_fc else 0)
     fwd_flops = FLOPS["forward"] + (FLOPS["candidate"] if fused_fc else 0)
     # the fused forward + candidate-0 sweep does not write du and re-read it, reads u once, and fetches only V, theta, gamma of x
@@ -378,9 +387,15 @@ def run_batched(args, rank, world, local):
     xr, ur, dx0, (Q, R, QT), gen = make_problem(args.workload, n_total, (rank, world))
     kw = dict(TT=TT, device=local, state=args.state, armijo=args.armijo, precision=args.precision, x_storage=args.x_storage, tma=not args.no_tma,
               split=not args.no_split, fused=not args.no_fused)
+    kw["refs_compact"] = args.refs != "expanded"
     bn = pkg.BatchedNewton(n, **kw)
     bn.set_weights(Q, R, QT)
-    bn.set_refs(xr, ur)
+    if args.refs == "host":
+        bn.set_refs(xr, ur)                  # per-instance arrays uploaded from the host
+    elif gen[0] == "step":
+        bn.set_refs_step(gen[1], gen[2])     # the scripts' generators on the device (bit-identical references)
+    else:
+        bn.set_refs_acrobatic(gen[1])
     bn.init_guess(dx0=dx0)
     if W:
         bn.iterate(W, count_active=False)
@@ -763,6 +778,9 @@ def main():
     ap.add_argument("--state", default="f32", choices=["f32", "f64"])
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"], help="f64 = the parity path (default); f32 = the optional FP32 mode")
     ap.add_argument("--x-storage", default="auto", choices=["auto", "f64"], help="f64: keep float32-valued states in float64 buffers (A/B)")
+    ap.add_argument("--refs", default="compact", choices=["compact", "expanded", "host"],
+                    help="references of the batched workloads: built on the device and kept parametric (default), built on the device and written "
+                         "out as per-instance arrays, or per-instance arrays uploaded from the host (A/B; identical results)")
     ap.add_argument("--no-tma", action="store_true", help="plain-load sweeps instead of the TMA rings (A/B)")
     ap.add_argument("--no-split", action="store_true", help="one stream for the whole batch instead of the tile-range sweep (A/B)")
     ap.add_argument("--no-fused", action="store_true", help="separate LQ forward pass / candidate sweeps instead of the fused ones (A/B)")
