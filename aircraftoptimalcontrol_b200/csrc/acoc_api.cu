@@ -1494,6 +1494,19 @@ static int launch_build_active(acoc_ctx* c)
     ++c->launches;
     return 0;
 }
+// the warp-specialised backward sweep: batches of at most two tiles per SM (9,472 instances on a B200) -- all resident at once with room
+// to spare for the kernels of other contexts (the sub-batches of a pipelined solve); its register budget allows four per SM
+#ifndef ACOC_BWD_SPLIT_TILES_PER_SM
+#define ACOC_BWD_SPLIT_TILES_PER_SM 2
+#endif
+static bool bwd_split(const acoc_ctx* c)
+{
+    static const bool off = getenv("ACOC_NO_BWD_SPLIT") != nullptr;  // A/B: the single-warp sweep k_backward_tma
+    static const int per_sm = getenv("ACOC_BWD_SPLIT_TILES_PER_SM") ? atoi(getenv("ACOC_BWD_SPLIT_TILES_PER_SM")) : ACOC_BWD_SPLIT_TILES_PER_SM;
+    int sms = c->sm_count;
+    if (sms <= 0) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    return !off && n_tiles(c) <= per_sm * sms;
+}
 template <typename F, typename XT>
 static int launch_backward_t(acoc_ctx* c, bool exact)
 {
@@ -1501,7 +1514,20 @@ static int launch_backward_t(acoc_ctx* c, bool exact)
     const ProblemT<F> P = prob<F>(c);
     const XT* X = (const XT*)c->X[cur];
     const F* U = (const F*)c->U[cur];
-    if (use_tma(c)) {
+    if (use_tma(c) && bwd_split(c)) {  // small batch: costate warp + matrix warp per tile (k_backward_split)
+        const int gs = sweep_grid(c, TILE);
+        cudaStream_t st = sweep_stream(c);
+        const bool dg = c->P.W.diag != 0;
+#define ACOC_BS_LAUNCH(EX, DG)                                                                                                        \
+        do {                                                                                                                          \
+            const size_t sm = backward_split_smem<EX, F, XT>();                                                                       \
+            TRY(prefer_smem(k_backward_split<EX, F, XT, DG>));                                                                        \
+            k_backward_split<EX, F, XT, DG><<<gs, 64, sm, st>>>(P, tile_list(c), X, U, (F*)c->KSG, c->S.status, c->S.n_reg);         \
+        } while (0)
+        if (exact) { if (dg) ACOC_BS_LAUNCH(true, 1); else ACOC_BS_LAUNCH(true, 0); }
+        else { if (dg) ACOC_BS_LAUNCH(false, 1); else ACOC_BS_LAUNCH(false, 0); }
+#undef ACOC_BS_LAUNCH
+    } else if (use_tma(c)) {
         const size_t sm = WarpRing<BWD_STAGES, BwdStage<F, XT>::BYTES>::smem_bytes(BWD_THREADS / 32);
         const int gs = sweep_grid(c, BWD_THREADS);
         cudaStream_t st = sweep_stream(c);

@@ -522,6 +522,183 @@ __global__ void __launch_bounds__(64) k_backward_tma(ProblemT<F> P, TileList L, 
 }
 
 // =================================================================================================================
+// fused backward sweep of SMALL batches, warp-specialised: one CTA = one tile of 32 instances = two warps with one role each.
+//   warp 0 (COSTATE): TMA ring of x, u, references (as in k_backward_tma) -> dx, lx, lu, trigonometry, linearisation, lambda-contracted
+//                     Hessians, g_t, lambda_t.  Hands the linearisation (12 numbers), lx (6), lu (2) and the Hessian terms (7) of the
+//                     step to warp 1 through a shared-memory message ring, writes g_t.
+//   warp 1 (MATRIX):  carries P, p; G, m, the column sweep P A / A'PA / B'PA, gains, P_t, p_t.  Writes K_t, sigma_t.
+// The two halves of a step share nothing but that message (riccati_costate / riccati_matrix), so warp 0 runs ahead of warp 1 by the
+// depth of the message ring and the chain of dependent instructions per step -- which is all a batch of a few thousand instances
+// pays for: a lone warp needs ~1.45 us per step -- is cut to the matrix half.  The matrix half needs ~230 registers, so only four
+// tiles fit on an SM: the kernel is used when the whole batch is resident at once (late survivor generations, single trajectories);
+// big batches keep k_backward_tma, where eight tiles per SM matter more (4.0 vs 3.2 ms at 65,536 instances).  Arithmetic per entry is
+// unchanged: bit-identical results (ACOC_NO_BWD_SPLIT for A/B).
+// =================================================================================================================
+#ifndef ACOC_BS_XSTAGES
+#define ACOC_BS_XSTAGES 2
+#endif
+constexpr int BS_XSTAGES = ACOC_BS_XSTAGES;
+template <bool EXACT>
+struct BsMsg { static constexpr int N = 12 + NS + NI + (EXACT ? 7 : 0); };
+template <bool EXACT, typename F, typename XT>
+constexpr size_t backward_split_smem()
+{
+    return (size_t)BWD_STAGES * BwdStage<F, XT>::BYTES + (size_t)BS_XSTAGES * BsMsg<EXACT>::N * TILE * sizeof(F) +
+           (BWD_STAGES + 2 * BS_XSTAGES) * sizeof(uint64_t);
+}
+
+template <bool EXACT, typename F, typename XT, int DG>
+__global__ void __launch_bounds__(64, 4) k_backward_split(ProblemT<F> P, TileList L, const XT* __restrict__ X, const F* __restrict__ U,
+                                                          F* __restrict__ KSG, const int* __restrict__ status, int* __restrict__ n_reg)
+{
+    using St = BwdStage<F, XT>;
+    constexpr int NMSG = BsMsg<EXACT>::N;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    const int tile = warp_tile(L, blockIdx.x, P.Np);
+    if (tile < 0) return;  // (uniform over the CTA)
+    unsigned char* const ring = smem;
+    F* const msg = reinterpret_cast<F*>(smem + (size_t)BWD_STAGES * St::BYTES);
+    uint64_t* const bar_in = reinterpret_cast<uint64_t*>(smem + (size_t)BWD_STAGES * St::BYTES + (size_t)BS_XSTAGES * NMSG * TILE * sizeof(F));
+    uint64_t* const xfull = bar_in + BWD_STAGES;
+    uint64_t* const xempty = xfull + BS_XSTAGES;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < BWD_STAGES; ++s) mbar_init(bar_in + s, 1);
+        for (int s = 0; s < BS_XSTAGES; ++s) { mbar_init(xfull + s, 1); mbar_init(xempty + s, 1); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int TT = P.TT, Np = P.Np, i = tile * TILE + lane, nsteps = TT - 1;
+    const bool live = i < P.N;
+    F x[NS], xr[NS];
+    if (live) {  // terminal condition: both roles need x_{T-1} - xref_{T-1}
+        load_xref(P, TT - 1, i, xr);
+        load_x(P, X, TT - 1, i, x);
+    }
+    if (role == 0) {
+        // ---------------------------------------------------------------- costate warp
+        const RefMode<F> rm(P, i, live);
+        auto issue = [&](int k) {  // ring step k <-> time t = TT-2-k
+            const int t = TT - 2 - k;
+            unsigned char* st = ring + (k % BWD_STAGES) * St::BYTES;
+            uint64_t* b = bar_in + (k % BWD_STAGES);
+            mbar_arrive_expect_tx(b, St::U_B + St::X_B + (rm.tiled ? St::U_B + St::XR_B : 0) + (rm.has_v ? (uint32_t)(TILE * sizeof(F)) : 0));
+            tma_load(st + St::U_O, U + tile_base(t, NI, Np, tile), St::U_B, b);
+            tma_load(st + St::X_O, X + tile_base(t, NS, Np, tile), St::X_B, b);
+            if (rm.tiled) {
+                tma_load(st + St::UR_O, P.uref + tile_base(t, NI, Np, tile), St::U_B, b);
+                tma_load(st + St::XR_O, P.xref + tile_base(t, NS, Np, tile), St::XR_B, b);
+            } else if (rm.has_v)
+                tma_load(st + St::XR_O, P.rp_v + tile_base(t, 1, Np, tile), (uint32_t)(TILE * sizeof(F)), b);
+        };
+        if (lane == 0)
+            for (int k = 0; k < BWD_STAGES && k < nsteps; ++k) issue(k);
+        F lam[NS], u[NI], ur[NI];
+        if (live) {
+            F dxT[NS];
+#pragma unroll
+            for (int c = 0; c < NS; ++c) dxT[c] = x[c] - xr[c];
+            wmul6(P.W.QT, (int)weights_diag<DG>(P.W), dxT, lam);  // lam_{T-1} = QT dx (optcon.py:429-432)
+        }
+        for (int k = 0; k < nsteps; ++k) {
+            const int t = TT - 2 - k;
+            mbar_wait(bar_in + (k % BWD_STAGES), (uint32_t)((k / BWD_STAGES) & 1));
+            const unsigned char* st = ring + (k % BWD_STAGES) * St::BYTES;
+            XT xraw[NS];
+#pragma unroll
+            for (int c = 0; c < NS; ++c) xraw[c] = reinterpret_cast<const XT*>(st + St::X_O)[c * TILE + lane];
+#pragma unroll
+            for (int c = 0; c < NI; ++c) u[c] = reinterpret_cast<const F*>(st + St::U_O)[c * TILE + lane];
+            F vv = F(0.0);
+            if (rm.tiled) {
+#pragma unroll
+                for (int c = 0; c < NI; ++c) ur[c] = reinterpret_cast<const F*>(st + St::UR_O)[c * TILE + lane];
+#pragma unroll
+                for (int c = 0; c < NS; ++c) xr[c] = reinterpret_cast<const F*>(st + St::XR_O)[c * TILE + lane];
+            } else if (rm.has_v) vv = reinterpret_cast<const F*>(st + St::XR_O)[lane];
+            stage_release();
+            if (lane == 0 && k + BWD_STAGES < nsteps) issue(k + BWD_STAGES);
+            const int s = k % BS_XSTAGES;
+            F* const m = msg + (size_t)s * NMSG * TILE + lane;
+            F q[NS], r[NI];
+            Lin<F> l;
+            if (live) {
+                rm.fill(P, t, i, vv, xr, ur);
+                finish_x(P, t, i, xraw, x);
+                F dx[NS], du[NI];
+#pragma unroll
+                for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
+#pragma unroll
+                for (int c = 0; c < NI; ++c) du[c] = u[c] - ur[c];
+                wmul6(P.W.Q, (int)weights_diag<DG>(P.W), dx, q);   // lx = Q dx   (aircraft_simplified.py:63)
+                wmul2(P.W.R, (int)weights_diag<DG>(P.W), du, r);   // lu = R du   (:64)
+                const Trig<F> tg = make_trig(x);
+                l = linearize(P.M, x, u, tg);
+                Hess<F> h;
+                if (EXACT) h = hess_contract(P.M, x, u, tg, l, lam);
+                if (k >= BS_XSTAGES) mbar_wait(xempty + s, (uint32_t)((k / BS_XSTAGES - 1) & 1));
+                m[0 * TILE] = l.a02; m[1 * TILE] = l.a05; m[2 * TILE] = l.a12; m[3 * TILE] = l.a15; m[4 * TILE] = l.a22; m[5 * TILE] = l.a23;
+                m[6 * TILE] = l.a25; m[7 * TILE] = l.a52; m[8 * TILE] = l.a53; m[9 * TILE] = l.a55; m[10 * TILE] = l.b20; m[11 * TILE] = l.b50;
+#pragma unroll
+                for (int c = 0; c < NS; ++c) m[(12 + c) * TILE] = q[c];
+                m[18 * TILE] = r[0]; m[19 * TILE] = r[1];
+                if (EXACT) {
+                    m[20 * TILE] = h.h22; m[21 * TILE] = h.h23; m[22 * TILE] = h.h25; m[23 * TILE] = h.h33; m[24 * TILE] = h.h55;
+                    m[25 * TILE] = h.s2; m[26 * TILE] = h.s3;
+                }
+            } else if (k >= BS_XSTAGES) mbar_wait(xempty + s, (uint32_t)((k / BS_XSTAGES - 1) & 1));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(xfull + s);
+            if (live) {
+                F g[NI];
+                riccati_costate(P.M, l, q, r, lam, g);
+                F* out = KSG + tile_base(t, 16, Np, tile) + lane;
+                out[14 * TILE] = g[0]; out[15 * TILE] = g[1];
+            }
+        }
+        return;
+    }
+    // ---------------------------------------------------------------- matrix warp
+    F Pm[21], p[NS];
+    int nreg = 0;
+    if (live) {
+        F lamT[NS];
+        backward_terminal<DG>(P.W, x, xr, Pm, p, lamT);  // P_{T-1} = QT, p_{T-1} = lam_{T-1}/2 (optcon.py:688-690, :716)
+    }
+    for (int k = 0; k < nsteps; ++k) {
+        const int t = TT - 2 - k, s = k % BS_XSTAGES;
+        mbar_wait(xfull + s, (uint32_t)((k / BS_XSTAGES) & 1));
+        const F* const m = msg + (size_t)s * NMSG * TILE + lane;
+        Lin<F> l;
+        Hess<F> h;
+        F q[NS], r[NI];
+        if (live) {
+            l.a02 = m[0 * TILE]; l.a05 = m[1 * TILE]; l.a12 = m[2 * TILE]; l.a15 = m[3 * TILE]; l.a22 = m[4 * TILE]; l.a23 = m[5 * TILE];
+            l.a25 = m[6 * TILE]; l.a52 = m[7 * TILE]; l.a53 = m[8 * TILE]; l.a55 = m[9 * TILE]; l.b20 = m[10 * TILE]; l.b50 = m[11 * TILE];
+#pragma unroll
+            for (int c = 0; c < NS; ++c) q[c] = m[(12 + c) * TILE];
+            r[0] = m[18 * TILE]; r[1] = m[19 * TILE];
+            if (EXACT) {
+                h.h22 = m[20 * TILE]; h.h23 = m[21 * TILE]; h.h25 = m[22 * TILE]; h.h33 = m[23 * TILE]; h.h55 = m[24 * TILE];
+                h.s2 = m[25 * TILE]; h.s3 = m[26 * TILE];
+                h.h35 = -h.h33; h.s5 = -h.s3;  // (as hess_contract forms them)
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(xempty + s);
+        if (live) {
+            F K[2 * NS], sig[NI];
+            nreg += riccati_matrix<EXACT, DG, F>(P.M, P.W, l, h, q, r, Pm, p, K, sig);
+            F* out = KSG + tile_base(t, 16, Np, tile) + lane;
+#pragma unroll
+            for (int c = 0; c < 12; ++c) out[c * TILE] = K[c];
+            out[12 * TILE] = sig[0]; out[13 * TILE] = sig[1];
+        }
+    }
+    if (live && nreg && status[i] == ST_ACTIVE) n_reg[i] += nreg;
+}
+
+// =================================================================================================================
 // steepest-descent costate sweep (gradient_instance): same ring as the backward sweep (x, u, references per step, walking
 // t = TT-2 .. 0); out deltau and the slope -sum |deltau|^2 the Armijo test uses
 // =================================================================================================================

@@ -470,7 +470,7 @@ def run_batched(args, rank, world, local):
         if dist is not None:  # warm the communicator the statistics gather uses (its first collective builds the NCCL channels)
             D.gather_stats({"iters": np.zeros(n, dtype=np.int32), "status": np.zeros(n, dtype=np.int32), "J": np.zeros(n), "descent": np.zeros(n),
                             "n_reg": np.zeros(n, dtype=np.int32)}, n_total)
-        pn = pkg.PipelinedNewton(n, n_chunks=args.chunks, stagger=not args.no_stagger, **kw)
+        pn = pkg.PipelinedNewton(n, n_chunks=args.chunks_generated, stagger=not args.no_stagger, **kw)
         pn.set_weights(Q, R, QT)
 
         def timed(solve):
@@ -489,14 +489,14 @@ def run_batched(args, rank, world, local):
                 wall = float(tw[0])
             return wall, g, gather_s
 
-        def describe(wall, g, gather_s, h2d, d2h, what):
+        def describe(wall, g, gather_s, h2d, d2h, what, chunks):
             tot = int(g["iters"].sum())
             steps_e2e = int(g["iters"].max())
             return {"value": tot / wall, "unit": UNIT, "h2d_bytes_per_step": h2d / max(steps_e2e, 1), "d2h_bytes_per_step": d2h / max(steps_e2e, 1),
                     "h2d_bytes_per_solve": h2d, "d2h_bytes_per_solve": d2h,
                     "wall_s": wall, "total_newton_iterations": tot, "solver_steps": steps_e2e,
                     "converged": int((g["status"] == 1).sum()), "instances": n_total, "mean_iters": float(g["iters"].mean()),
-                    "stats_gather_s": gather_s, "chunks": args.chunks, "staggered_priorities": not args.no_stagger, "what": what}
+                    "stats_gather_s": gather_s, "chunks": chunks, "staggered_priorities": not args.no_stagger, "what": what}
 
         # (a) headline: the randomisation parameters are the host inputs (16-56 B per instance); the scripts' reference generators run on
         #     the device (bit-identical arrays, tests/test_gpu_parity_r2.py); states come back as the float32 values they are
@@ -512,16 +512,19 @@ def run_batched(args, rank, world, local):
                             x_dtype=np.float32 if f32_dl else np.float64)[2]
 
         wall, g, gs = timed(solve_generated)
-        h2d = (sum(p.numel() for p in par_t) * 8 + (dx0_t.numel() * 8 if dx0_t is not None else 0) + 3 * TT * 8 * args.chunks) * world
+        h2d = (sum(p.numel() for p in par_t) * 8 + (dx0_t.numel() * 8 if dx0_t is not None else 0) + 3 * TT * 8 * args.chunks_generated) * world
         d2h = (xs32_t.numel() * xs32_t.element_size() + us_t.numel() * 8 + (n * 48 if f32_dl else 0)) * world + n_total * 28
         e2e = describe(wall, g, gs, h2d, d2h,
                        "PipelinedNewton.solve(refs=(kind, per-instance parameters) in pinned host memory): per sub-batch H2D of the parameters -> "
                        "reference generators + initial guess on the device -> solve() to descent >= -1e-6 -> D2H of xx_star (%s), uu_star "
                        "(float64) and the statistics into pinned host memory; sub-batches overlap copies with compute"
-                       % ("float32: lossless, the quantised states are float32 values" if f32_dl else "float64"))
+                       % ("float32: lossless, the quantised states are float32 values" if f32_dl else "float64"), args.chunks_generated)
         del xs32_t
+        pn.close()
         # (b) the same solve with the reference ARRAYS uploaded from the host and float64 results (the round-1 path, still available)
         if not args.no_e2e_host:
+            pn = pkg.PipelinedNewton(n, n_chunks=args.chunks, stagger=not args.no_stagger, **kw)
+            pn.set_weights(Q, R, QT)
             xr_p, ur_p = pinned_like(xr), pinned_like(ur)
             xs_t = torch.empty((n, 6, TT), dtype=torch.float64, pin_memory=True)
 
@@ -531,8 +534,8 @@ def run_batched(args, rank, world, local):
             wall, g, gs = timed(solve_host)
             e2e_host = describe(wall, g, gs, (xr.nbytes + ur.nbytes) * world, (xs_t.numel() + us_t.numel()) * 8 * world + n_total * 28,
                                 "PipelinedNewton.solve(xx_ref, uu_ref in pinned host memory): per sub-batch set_refs (H2D of 64 KB per instance) -> "
-                                "init_guess (device) -> solve() -> result()/stats() (D2H, float64)")
-        pn.close()
+                                "init_guess (device) -> solve() -> result()/stats() (D2H, float64)", args.chunks)
+            pn.close()
 
     clocks = sampler.summary() if sampler else None
     cpu = None
@@ -785,7 +788,9 @@ def main():
     ap.add_argument("--no-split", action="store_true", help="one stream for the whole batch instead of the tile-range sweep (A/B)")
     ap.add_argument("--no-fused", action="store_true", help="separate LQ forward pass / candidate sweeps instead of the fused ones (A/B)")
     ap.add_argument("--cpu-sample", type=int, default=16384, help="instances of the bounded CPU sample (about 10 s of work on 16 host threads)")
-    ap.add_argument("--chunks", type=int, default=4, help="sub-batches of the pipelined end-to-end solve")
+    ap.add_argument("--chunks", type=int, default=4, help="sub-batches of the pipelined end-to-end solve with reference arrays uploaded from the host")
+    ap.add_argument("--chunks-generated", type=int, default=2, help="sub-batches of the headline end-to-end solve (references generated on the device: "
+                    "little to upload, so fewer, larger sub-batches win: 1: 0.322 s, 2: 0.325 s, 4: 0.338 s, 8: 0.345 s)")
     ap.add_argument("--no-stagger", action="store_true", help="end-to-end leg: same stream priority for every sub-batch (A/B)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-host", action="store_true", help="skip the second end-to-end leg (reference arrays uploaded from the host)")
