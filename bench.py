@@ -789,8 +789,9 @@ def main():
     ap.add_argument("--no-fused", action="store_true", help="separate LQ forward pass / candidate sweeps instead of the fused ones (A/B)")
     ap.add_argument("--cpu-sample", type=int, default=16384, help="instances of the bounded CPU sample (about 10 s of work on 16 host threads)")
     ap.add_argument("--chunks", type=int, default=4, help="sub-batches of the pipelined end-to-end solve with reference arrays uploaded from the host")
-    ap.add_argument("--chunks-generated", type=int, default=2, help="sub-batches of the headline end-to-end solve (references generated on the device: "
-                    "little to upload, so fewer, larger sub-batches win: 1: 0.322 s, 2: 0.325 s, 4: 0.338 s, 8: 0.345 s)")
+    ap.add_argument("--chunks-generated", type=int, default=None, help="sub-batches of the headline end-to-end solve (references generated on the device: "
+                    "little to upload, so fewer, larger sub-batches win on one GPU -- 1: 0.322 s, 2: 0.325 s, 4: 0.338 s, 8: 0.345 s; with 8 GPUs "
+                    "sharing the host 4 is best -- 2: 0.500 s, 4: 0.490 s, 8: 0.514 s); default 2, or 4 from four GPUs on")
     ap.add_argument("--no-stagger", action="store_true", help="end-to-end leg: same stream priority for every sub-batch (A/B)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-host", action="store_true", help="skip the second end-to-end leg (reference arrays uploaded from the host)")
@@ -799,6 +800,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     args.instances_given = args.instances is not None
+    if args.chunks_generated is None:
+        args.chunks_generated = 4 if int(os.environ.get("WORLD_SIZE", "1")) >= 4 else 2
     if args.instances is None:
         args.instances = 65536
 
