@@ -67,6 +67,7 @@ def _sig(lib):
         "acoc_init_guess": [vp, d, d, vp],
         "acoc_newton_iterate": [vp, i, vp],
         "acoc_newton_solve": [vp, vp],
+        "acoc_newton_solve_deliver": [vp, vp, i, vp, vp, vp],
         "acoc_sync": [vp],
         "acoc_get_result": [vp, vp, vp],
         "acoc_get_iterate": [vp, i, vp, vp],

@@ -170,6 +170,19 @@ class BatchedNewton:
         L.check(L.lib().acoc_newton_solve(self._h, C.addressof(tot)))
         return tot.value
 
+    def solve_deliver(self, out, x0=None):
+        """solve() and the read-back of the result in one call: out = (xx_star (N,6,TT) float32 or float64, uu_star (N,2,TT) float64).
+        With page-locked arrays (e.g. torch pin_memory) the results are written straight into them and the finished instances are
+        delivered while the last ones still iterate (acoc_newton_solve_deliver); pageable arrays get the same values through
+        solve() + result().  Returns (total Newton iterations, x0 (N,6))."""
+        xs, us = out
+        if xs.dtype not in (np.float32, np.float64) or us.dtype != np.float64 or xs.shape != (self.N, 6, self.TT) or us.shape != (self.N, 2, self.TT):
+            raise ValueError("solve_deliver needs xx_star (N,6,TT) float32/float64 and uu_star (N,2,TT) float64")
+        x0 = np.empty((self.N, 6)) if x0 is None else x0
+        tot = C.c_longlong(0)
+        L.check(L.lib().acoc_newton_solve_deliver(self._h, L.ptr(xs), int(xs.dtype == np.float32), L.ptr(us), L.ptr(x0), C.addressof(tot)))
+        return tot.value, x0
+
     def sync(self):
         L.check(L.lib().acoc_sync(self._h))
 
@@ -316,13 +329,14 @@ class PipelinedNewton:
         for p in self.parts:
             p.set_weights(QQt, RRt, QQT)
 
-    def solve(self, xx_ref=None, uu_ref=None, xx_init=None, uu_init=None, dx0=None, out=None, refs=None, x_dtype=np.float64):
+    def solve(self, xx_ref=None, uu_ref=None, xx_init=None, uu_init=None, dx0=None, out=None, refs=None, x_dtype=np.float64, direct=True):
         """xx_ref (N,6,TT), uu_ref (N,2,TT) per-instance references (pinned host memory makes the copies fast), or
         refs = ("step", zf (N,), xf (N,)[, tf]) / ("acrobatic", zf (N,)[, xf, tf]): the scripts' reference generators run on the device
         (BatchedNewton.set_refs_step / set_refs_acrobatic; bit-identical arrays, 16 bytes per instance over the bus).  Initial
         guess = (xx_init, uu_init) if given, else the device P-law rollout (optionally started at xx_ref[:,0] + dx0).
         x_dtype = np.float32 downloads the states as the float32 values they are (BatchedNewton.result_f32; column 0 then holds
-        float32(x0), the exact x0 is stats["x0"]).
+        float32(x0), the exact x0 is stats["x0"]).  direct: deliver through BatchedNewton.solve_deliver (results written straight into
+        page-locked `out` arrays while the last instances still iterate; pageable arrays: same values, staged download).
         Returns (xx_star, uu_star, stats) with stats = dict(iters, status, J, descent, n_reg), each of length N."""
         import threading
 
@@ -368,13 +382,19 @@ class PipelinedNewton:
                         turn.notify_all()
                 if xx_init is None:
                     bn.init_guess(dx0=None if dx0 is None else dx0[lo:hi])
-                bn.solve()
-                with download:
+                if direct:   # results written straight into the (page-locked) output arrays, overlapping the tail of the solve
+                    x0c = bn.solve_deliver((xs[lo:hi], us[lo:hi]))[1]
                     if f32:
-                        x0_out[lo:hi] = bn.result_f32(out=(xs[lo:hi], us[lo:hi]))[2]
-                    else:
-                        bn.result(out=(xs[lo:hi], us[lo:hi]))
+                        x0_out[lo:hi] = x0c
                     st = bn.stats()
+                else:
+                    bn.solve()
+                    with download:
+                        if f32:
+                            x0_out[lo:hi] = bn.result_f32(out=(xs[lo:hi], us[lo:hi]))[2]
+                        else:
+                            bn.result(out=(xs[lo:hi], us[lo:hi]))
+                        st = bn.stats()
                 for key in stats:
                     stats[key][lo:hi] = st[key]
             except Exception as e:  # surfaced after the join

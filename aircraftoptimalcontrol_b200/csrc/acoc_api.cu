@@ -571,6 +571,63 @@ __global__ void k_from_soa(const D* __restrict__ s0, const D* __restrict__ s1, c
     }
 }
 
+// ---- result delivery straight into page-locked host memory ----------------------------------------------------------------------
+// What optimize() returns (optcon.py:503-505) for every instance of this context whose status is FINAL, written into the caller's
+// (N, C, TT) array at row uidx[n] (the instance's index in the caller's batch; NULL: identity) by the layout-conversion kernel itself:
+// dst is the device alias of page-locked host memory, so no staging buffer, no separate copy, and any subset of instances costs only
+// its own bytes.  acoc_newton_solve_deliver launches it for a batch's finished instances at the moment the still-iterating ones move
+// on to a survivor generation, so that the transfer overlaps the latency-bound tail of the solve.
+// row0 (optional, [C][Np]): exact t = 0 column of float state slots; dup_last: t = TT-1 reads TT-2 (uu_star[:,-1] = uu_star[:,-2]).
+template <typename D, typename O>
+__global__ void k_deliver(const D* __restrict__ s0, const D* __restrict__ s1, const D* __restrict__ s2, const int* __restrict__ result_slot,
+                          const int* __restrict__ status, const int* __restrict__ uidx, const double* __restrict__ row0, O* __restrict__ dst,
+                          int N, int C, int TT, int Np, int dup_last)
+{
+    // A small persistent grid (64 CTAs) walks the (instance tile, time tile, component) blocks.  The stores drain at the speed of the
+    // host link and back up in the memory pipe of the SMs that issue them; on every SM they slow the solver's own kernels -- the
+    // latency-bound tail this transfer is meant to hide behind -- by 3x, on 64 of the 148 SMs by a quarter, at 35 of the 40 GB/s the
+    // machine-filling grid reaches.
+    __shared__ O tile[32][33];
+    __shared__ int row_of[32];
+    const int nt = (TT + 31) / 32, nn = (N + 31) / 32;
+    const long long nblk = (long long)nn * nt * C;
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const int c = (int)(blk % C), tb = (int)((blk / C) % nt) * 32, nb = (int)(blk / ((long long)C * nt)) * 32;
+        int mine = 0;
+        __syncthreads();  // (the previous block's tile / row_of have been read)
+        if (threadIdx.y == 0) {
+            const int n = nb + threadIdx.x;
+            int row = -1;
+            if (n < N) { const int st = status[n]; if (st == ST_CONVERGED || st == ST_MAXITER || st == ST_NONFINITE) row = uidx ? uidx[n] : n; }
+            row_of[threadIdx.x] = row;
+            mine = row >= 0;
+        }
+        if (!__syncthreads_or(mine)) continue;  // no finished instance in this tile
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+            int t = tb + r;
+            const int n = nb + threadIdx.x;
+            if (n < N && t < TT && row_of[threadIdx.x] >= 0) {
+                if (dup_last && t == TT - 1 && TT > 1) t = TT - 2;
+                const int sl = result_slot[n];
+                const D* s = sl == 0 ? s0 : (sl == 1 ? s1 : s2);
+                tile[r][threadIdx.x] = sl < 0 ? O(0) : ((row0 && t == 0) ? (O)row0[(size_t)c * Np + n] : (O)s[at(t, C, c, Np, n)]);
+            }
+        }
+        __syncthreads();
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+            const int t = tb + threadIdx.x, row = row_of[r];
+            if (row >= 0 && t < TT) dst[((size_t)row * C + c) * TT + t] = tile[threadIdx.x][r];
+        }
+    }
+}
+
+// index of a child generation's instances in the caller's batch: uidx_child[j] = uidx_parent[origin[j]] (parent NULL: the root, identity)
+__global__ void k_compose_uidx(const int* __restrict__ origin, const int* __restrict__ uidx_parent, int* __restrict__ uidx_child, int n)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) { const int o = origin[j]; uidx_child[j] = uidx_parent ? uidx_parent[o] : o; }
+}
+
 // ---- reference generators of the scripts, on the device ---------------------------------------------------
 // xref / uref of instance i from per-instance parameters and shared time bases, in the operation order of the scripts' numpy code
 // (main_newton_method.py:96-142, acrobatic_newton.py:99-154; restated in refgen.py) so that the result is bit-identical to it:
@@ -760,6 +817,8 @@ struct acoc_ctx {
     // survivor generations (see acoc_newton_solve)
     acoc_ctx* child = nullptr;  // reusable smaller context (capacity N/2) for the instances that are still iterating
     int* origin = nullptr;      // [capacity] index in the PARENT of each instance of this context (child contexts only)
+    int* uidx = nullptr;        // [capacity] index in the caller's batch (child contexts during acoc_newton_solve_deliver)
+    cudaStream_t dstream = nullptr;  // result delivery (root context)
     int cap = 0;                // instance capacity (N may be smaller in a child)
     int spawn_kk = 0;           // iteration at which this child took over its instances
     double gen_ms = 0;          // device time spent moving instances between generations in the last solve
@@ -1248,6 +1307,7 @@ int acoc_ctx_destroy(acoc_ctx* c)
         if (c->ev_join[r]) cudaEventDestroy(c->ev_join[r]);
         if (c->rstream[r]) { cudaStreamSynchronize(c->rstream[r]); cudaStreamDestroy(c->rstream[r]); }
     }
+    if (c->dstream) { cudaStreamSynchronize(c->dstream); cudaStreamDestroy(c->dstream); }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -2219,7 +2279,42 @@ static int fold_child(acoc_ctx* par, acoc_ctx* ch)
 #define ACOC_GEN_MIN 4096  // smallest batch that still spawns a survivor generation
 #endif
 
-int acoc_newton_solve(acoc_ctx* c, long long* total_iters)
+// where acoc_newton_solve_deliver puts the results: device-accessible aliases of the caller's page-locked arrays
+struct Delivery {
+    void* xx = nullptr;      // (N,6,TT) float or double
+    bool x_f32 = false;
+    double* uu = nullptr;    // (N,2,TT)
+    cudaStream_t stream = nullptr;
+};
+
+// optimize()'s result of every instance of `ctx` that is final now, straight into the caller's arrays (k_deliver), on the delivery stream
+static int deliver_finished(acoc_ctx* ctx, const Delivery& dv)
+{
+    const dim3 block(32, 8);
+    static const int ctas = getenv("ACOC_DELIVER_CTAS") ? atoi(getenv("ACOC_DELIVER_CTAS")) : 64;  // (8: 536 ms, 16: 373, 32: 293, 64: 281 ms end to end; a machine-filling grid: 320)
+    const int gx = std::max(1, ctas), gu = gx;
+    const int *rs = ctx->S.result_slot, *stt = ctx->S.status, *ui = ctx->uidx;
+    const int N = ctx->N, TT = ctx->TT, Np = ctx->Np;
+    if (ctx->x_float) {
+        const float *a = (const float*)ctx->X[0], *b = (const float*)ctx->X[1], *c2 = (const float*)ctx->X[2];
+        if (dv.x_f32) k_deliver<float, float><<<gx, block, 0, dv.stream>>>(a, b, c2, rs, stt, ui, nullptr, (float*)dv.xx, N, 6, TT, Np, 0);
+        else k_deliver<float, double><<<gx, block, 0, dv.stream>>>(a, b, c2, rs, stt, ui, ctx->fp32 ? nullptr : (const double*)ctx->x0, (double*)dv.xx, N, 6, TT, Np, 0);
+    } else {
+        const double *a = (const double*)ctx->X[0], *b = (const double*)ctx->X[1], *c2 = (const double*)ctx->X[2];
+        k_deliver<double, double><<<gx, block, 0, dv.stream>>>(a, b, c2, rs, stt, ui, nullptr, (double*)dv.xx, N, 6, TT, Np, 0);
+    }
+    CK(cudaGetLastError());
+    if (ctx->fp32)
+        k_deliver<float, double><<<gu, block, 0, dv.stream>>>((const float*)ctx->U[0], (const float*)ctx->U[1], (const float*)ctx->U[2], rs, stt, ui, nullptr,
+                                                                dv.uu, N, 2, TT, Np, 1);
+    else
+        k_deliver<double, double><<<gu, block, 0, dv.stream>>>((const double*)ctx->U[0], (const double*)ctx->U[1], (const double*)ctx->U[2], rs, stt, ui,
+                                                                 nullptr, dv.uu, N, 2, TT, Np, 1);  // uu_star[:,-1] = uu_star[:,-2], optcon.py:505
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int solve_impl(acoc_ctx* c, long long* total_iters, const Delivery* dv)
 {
     TRY(ready(c));
     int active = 1;
@@ -2246,15 +2341,28 @@ int acoc_newton_solve(acoc_ctx* c, long long* total_iters)
             int rc = spawn_child(cur, active, &ch);
             if (rc < 0) return rc;
             if (rc == 0 && ch) {
+                if (dv) {
+                    // the finished instances of `cur` are final: deliver them now, while the survivors iterate in the child
+                    if (!ch->uidx) TRY(dalloc(ch, &ch->uidx, (size_t)ch->Np));
+                    k_compose_uidx<<<(active + 255) / 256, 256, 0, cur->stream>>>(ch->origin, cur->uidx, ch->uidx, active);
+                    CK(cudaGetLastError());
+                }
                 CK(cudaEventRecord(cur->ev[7], cur->stream));
                 CK(cudaEventSynchronize(cur->ev[7]));
                 float ms = 0;
                 CK(cudaEventElapsedTime(&ms, cur->ev[6], cur->ev[7]));
                 gen_ms += ms;
+                if (dv) TRY(deliver_finished(cur, *dv));
                 chain.push_back(ch);
                 cur = ch;
             }
         }
+    }
+    if (dv) {
+        // whatever `cur` (the last generation, or the batch itself) still holds: instances that ran out of iterations while active get
+        // their status from the driver, so everything is final here
+        TRY(deliver_finished(cur, *dv));
+        CK(cudaStreamSynchronize(dv->stream));  // (the folds below rewrite rows of the parents; keep them behind the deliveries)
     }
     for (size_t k = chain.size() - 1; k >= 1; --k) {
         acoc_ctx* par = chain[k - 1];
@@ -2270,6 +2378,52 @@ int acoc_newton_solve(acoc_ctx* c, long long* total_iters)
     for (int p = 0; p < 6; ++p) c->phase_ms[p] = phase[p];
     c->phase_ms[4] = gen_ms;  // reported as the "select" slot of acoc_get_timing: time spent moving instances between generations
     if (total_iters) TRY(count_active(c, nullptr, total_iters));
+    return 0;
+}
+
+int acoc_newton_solve(acoc_ctx* c, long long* total_iters) { return solve_impl(c, total_iters, nullptr); }
+
+// device alias of a page-locked host pointer, or NULL for pageable memory
+static void* pinned_alias(const void* host)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return at.devicePointer;
+}
+
+int acoc_newton_solve_deliver(acoc_ctx* c, void* xx_star, int x_is_f32, double* uu_star, double* x0, long long* total_iters)
+{
+    TRY(ready(c));
+    REQUIRE(xx_star && uu_star, "NULL output");
+    if (x_is_f32 && !(c->x_float))
+        return fail(ACOC_ERR_STATE, "acoc_newton_solve_deliver: float32 states requested but the state iterates of this context are not float32 values");
+    void* dx = pinned_alias(xx_star);
+    void* du = pinned_alias(uu_star);
+    if (!dx || !du) {  // pageable buffers: solve, then the staged download
+        TRY(solve_impl(c, total_iters, nullptr));
+        if (x_is_f32) return acoc_get_result_f32(c, (float*)xx_star, uu_star, x0);
+        TRY(acoc_get_result(c, (double*)xx_star, uu_star));
+    } else {
+        if (!c->dstream) CK(cudaStreamCreateWithFlags(&c->dstream, cudaStreamNonBlocking));
+        Delivery dv;
+        dv.xx = dx; dv.x_f32 = x_is_f32 != 0; dv.uu = (double*)du; dv.stream = c->dstream;
+        TRY(solve_impl(c, total_iters, &dv));
+    }
+    if (x0) {  // exact x0 = xx_init[:,0] (optcon.py:398): device [6][Np] -> host (N,6)
+        const size_t Np = c->Np;
+        std::vector<double> tmp(6 * Np);
+        if (c->fp32) {
+            std::vector<float> t32(6 * Np);
+            CK(cudaMemcpyAsync(t32.data(), c->x0, t32.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            for (size_t k = 0; k < t32.size(); ++k) tmp[k] = t32[k];
+        } else {
+            CK(cudaMemcpyAsync(tmp.data(), c->x0, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+        }
+        for (int i = 0; i < c->N; ++i) for (int k = 0; k < 6; ++k) x0[(size_t)i * 6 + k] = tmp[k * Np + i];
+    }
     return 0;
 }
 

@@ -187,6 +187,13 @@ int acoc_newton_iterate(acoc_ctx* ctx, int n_iters, int* n_active_out);
  * results, histories and statistics are exactly those of iterating in place (ACOC_SOLVE_IN_PLACE disables this). */
 int acoc_newton_solve(acoc_ctx* ctx, long long* total_iters);
 /* Block until all work queued on the context's stream has finished. */
+/* acoc_newton_solve and the read-back of what optimize() returns in ONE call.  xx_star: (N,6,TT) float32 if x_is_f32 (lossless under the
+ * float32 state quantisation, see acoc_get_result_f32; column 0 then holds float32(x0)) else float64; uu_star (N,2,TT) float64; x0 (N,6)
+ * or NULL receives the exact initial states.  When xx_star and uu_star are PAGE-LOCKED host memory (cudaHostAlloc / cudaHostRegister,
+ * e.g. torch pin_memory) the layout-conversion kernels write straight into them, and the instances that have finished are delivered at
+ * the moment the still-iterating ones move on to a survivor generation, so the transfer overlaps the latency-bound tail of the solve.
+ * Pageable buffers: same results through acoc_newton_solve + acoc_get_result[_f32]. */
+int acoc_newton_solve_deliver(acoc_ctx* ctx, void* xx_star, int x_is_f32, double* uu_star, double* x0, long long* total_iters);
 int acoc_sync(acoc_ctx* ctx);
 
 /* What NewtonMethod.optimize returns (optcon.py:503-505): iterate kk-1 with uu[:, -1] = uu[:, -2]. */

@@ -359,3 +359,87 @@ def test_compact_references_identical_solves(gpu, kind, n, TT, kw):
             assert np.array_equal(a[4][k], b[4][k]), k
         for k in ("iters", "status", "J", "descent", "n_reg"):
             assert np.array_equal(a[5][k], b[5][k]), k
+
+
+def _pinned(shape, dtype):
+    import torch
+    t = torch.empty(shape, dtype=torch.float32 if dtype == np.float32 else torch.float64, pin_memory=True)
+    return t, t.numpy()
+
+
+@pytest.mark.parametrize("n,TT,kw", [(8192, 200, dict()), (300, 200, dict(max_iters=9)), (9000, 120, dict(state="f64")), (5000, 150, dict(max_iters=22))])
+def test_solve_deliver_equals_solve_and_result(gpu, n, TT, kw):
+    """acoc_newton_solve_deliver writes optimize()'s results straight into page-locked host arrays, the finished instances of a batch
+    at the moment the rest moves on to a survivor generation.  Must equal solve() + result() / result_f32() exactly -- float32 and
+    float64 states, batches with and without generations, mixed result slots (converged / max_iters), pageable arrays (staged path)."""
+    xr, ur, Q, R, QT = _short_batch(n, TT, n)
+    dx0 = np.random.default_rng(n).normal(size=(n, 6)) * np.array([.05, .05, .2, .02, .05, .02])
+    f64_state = kw.get("state") == "f64"
+
+    def fresh():
+        bn = gpu.BatchedNewton(n, TT=TT, armijo="lazy", **kw)
+        bn.set_weights(Q, R, QT)
+        bn.set_refs(xr, ur)
+        bn.init_guess(dx0=dx0)
+        return bn
+
+    with fresh() as bn:
+        total = bn.solve()
+        x64, u64 = bn.result()
+        st = bn.stats()
+        h = bn.history()
+    for x_dtype, pinned in ((np.float64, True), (np.float32, True), (np.float64, False)):
+        if x_dtype == np.float32 and f64_state:
+            continue
+        if pinned:
+            keep_x, xs = _pinned((n, 6, TT), x_dtype)
+            keep_u, us = _pinned((n, 2, TT), np.float64)
+        else:
+            xs, us = np.empty((n, 6, TT), dtype=x_dtype), np.empty((n, 2, TT))
+        xs[...] = -7.0
+        us[...] = -7.0
+        with fresh() as bn:
+            tot2, x0 = bn.solve_deliver((xs, us))
+            st2, h2 = bn.stats(), bn.history()
+            xr2, ur2 = bn.result()     # the context itself is in the same state as after solve()
+        assert tot2 == total and np.array_equal(x0, xr[:, :, 0] + dx0)
+        assert np.array_equal(us, u64)
+        if x_dtype == np.float64:
+            assert np.array_equal(xs, x64)
+        else:
+            assert np.array_equal(xs[:, :, 1:].astype(np.float64), x64[:, :, 1:])
+            conv0 = st["iters"] > 1    # (an instance that stops at kk = 0 returns the all-zero slot, column 0 included)
+            assert np.array_equal(xs[conv0, :, 0], x0[conv0].astype(np.float32))
+        assert np.array_equal(xr2, x64) and np.array_equal(ur2, u64)
+        for k in ("iters", "status", "J"):
+            assert np.array_equal(st[k], st2[k]), k
+        assert np.array_equal(h["stepsize"], h2["stepsize"])
+
+
+def test_solve_deliver_zero_slot_and_pipelined(gpu):
+    """The all-zero result of an instance that stops at kk = 0 (optcon.py:503 with kk = 0) through the direct delivery, and
+    PipelinedNewton with page-locked outputs (direct delivery per sub-batch) against pageable outputs."""
+    d = golden("newton_quirks.npz")
+    xi = np.stack([d["a_xx_init"], d["b_xx_init"]])
+    ui = np.stack([d["a_uu_init"], d["b_uu_init"]])
+    keep_x, xs = _pinned((2, 6, 1000), np.float64)
+    keep_u, us = _pinned((2, 2, 1000), np.float64)
+    xs[...] = 5.0
+    us[...] = 5.0
+    with gpu.BatchedNewton(2, TT=1000, state="f64", refs_shared=True, max_iters=4) as bn:
+        bn.set_weights(d["Q"], d["R"], d["QT"])
+        bn.set_refs(d["xx_ref"], d["uu_ref"])
+        bn.set_init(xi, ui)
+        tot, _ = bn.solve_deliver((xs, us))
+    assert tot == 4 and relerr(d["a_xx_star"], xs[0]) < 1e-9 and relerr(d["a_uu_star"], us[0]) < 1e-9
+    assert not xs[1].any() and not us[1].any()
+    n, TT = 9000, 150
+    xr, ur, Q, R, QT = _short_batch(n, TT, 77)
+    keep_x2, xp = _pinned((n, 6, TT), np.float32)
+    keep_u2, up = _pinned((n, 2, TT), np.float64)
+    with gpu.PipelinedNewton(n, n_chunks=2, TT=TT, armijo="lazy") as pn:
+        pn.set_weights(Q, R, QT)
+        xa, ua, sa = pn.solve(xr, ur, x_dtype=np.float32)                       # pageable outputs: staged download
+        xb, ub, sb = pn.solve(xr, ur, x_dtype=np.float32, out=(xp, up))         # page-locked outputs: direct delivery
+    assert np.array_equal(xa, xb) and np.array_equal(ua, ub) and np.array_equal(sa["x0"], sb["x0"])
+    assert np.array_equal(sa["iters"], sb["iters"]) and np.array_equal(sa["J"], sb["J"])
