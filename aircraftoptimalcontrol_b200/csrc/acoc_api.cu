@@ -578,9 +578,10 @@ __global__ void k_from_soa(const D* __restrict__ s0, const D* __restrict__ s1, c
 // its own bytes.  acoc_newton_solve_deliver launches it for a batch's finished instances at the moment the still-iterating ones move
 // on to a survivor generation, so that the transfer overlaps the latency-bound tail of the solve.
 // row0 (optional, [C][Np]): exact t = 0 column of float state slots; dup_last: t = TT-1 reads TT-2 (uu_star[:,-1] = uu_star[:,-2]).
+// rows[n]: destination row of instance n in this delivery, or -1 (k_deliver_select)
 template <typename D, typename O>
 __global__ void k_deliver(const D* __restrict__ s0, const D* __restrict__ s1, const D* __restrict__ s2, const int* __restrict__ result_slot,
-                          const int* __restrict__ status, const int* __restrict__ uidx, const double* __restrict__ row0, O* __restrict__ dst,
+                          const int* __restrict__ rows, const double* __restrict__ row0, O* __restrict__ dst,
                           int N, int C, int TT, int Np, int dup_last)
 {
     // A small persistent grid (64 CTAs) walks the (instance tile, time tile, component) blocks.  The stores drain at the speed of the
@@ -597,8 +598,7 @@ __global__ void k_deliver(const D* __restrict__ s0, const D* __restrict__ s1, co
         __syncthreads();  // (the previous block's tile / row_of have been read)
         if (threadIdx.y == 0) {
             const int n = nb + threadIdx.x;
-            int row = -1;
-            if (n < N) { const int st = status[n]; if (st == ST_CONVERGED || st == ST_MAXITER || st == ST_NONFINITE) row = uidx ? uidx[n] : n; }
+            const int row = n < N ? rows[n] : -1;
             row_of[threadIdx.x] = row;
             mine = row >= 0;
         }
@@ -619,6 +619,24 @@ __global__ void k_deliver(const D* __restrict__ s0, const D* __restrict__ s1, co
             if (row >= 0 && t < TT) dst[((size_t)row * C + c) * TT + t] = tile[threadIdx.x][r];
         }
     }
+}
+
+// the instances of a context that are final and have not been delivered yet: rows[n] = their row in the caller's batch (uidx; NULL:
+// identity), else -1; marks them delivered.  Runs on the SOLVER's stream between two calls of the lock-step driver, so it sees a
+// consistent snapshot; the trajectories of a final instance never change again, so the delivery itself may run beside later iterations.
+__global__ void k_deliver_select(const int* __restrict__ status, const int* __restrict__ uidx, int* __restrict__ delivered, int* __restrict__ rows,
+                                 int* __restrict__ count, int N)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int st = status[n];
+    int row = -1;
+    if ((st == ST_CONVERGED || st == ST_MAXITER || st == ST_NONFINITE) && !delivered[n]) {
+        row = uidx ? uidx[n] : n;
+        delivered[n] = 1;
+        atomicAdd(count, 1);
+    }
+    rows[n] = row;
 }
 
 // index of a child generation's instances in the caller's batch: uidx_child[j] = uidx_parent[origin[j]] (parent NULL: the root, identity)
@@ -818,6 +836,9 @@ struct acoc_ctx {
     acoc_ctx* child = nullptr;  // reusable smaller context (capacity N/2) for the instances that are still iterating
     int* origin = nullptr;      // [capacity] index in the PARENT of each instance of this context (child contexts only)
     int* uidx = nullptr;        // [capacity] index in the caller's batch (child contexts during acoc_newton_solve_deliver)
+    int *delivered = nullptr, *deliver_rows = nullptr;  // [capacity] delivery bookkeeping of acoc_newton_solve_deliver
+    cudaEvent_t ev_deliver = nullptr;
+    int n_delivered = 0;        // instances of this context handed to the delivery stream so far (host-side count)
     cudaStream_t dstream = nullptr;  // result delivery (root context)
     int cap = 0;                // instance capacity (N may be smaller in a child)
     int spawn_kk = 0;           // iteration at which this child took over its instances
@@ -1308,6 +1329,7 @@ int acoc_ctx_destroy(acoc_ctx* c)
         if (c->rstream[r]) { cudaStreamSynchronize(c->rstream[r]); cudaStreamDestroy(c->rstream[r]); }
     }
     if (c->dstream) { cudaStreamSynchronize(c->dstream); cudaStreamDestroy(c->dstream); }
+    if (c->ev_deliver) cudaEventDestroy(c->ev_deliver);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -2287,36 +2309,66 @@ struct Delivery {
     cudaStream_t stream = nullptr;
 };
 
-// optimize()'s result of every instance of `ctx` that is final now, straight into the caller's arrays (k_deliver), on the delivery stream
-static int deliver_finished(acoc_ctx* ctx, const Delivery& dv)
+// optimize()'s result of every instance of `ctx` that is final and not delivered yet, straight into the caller's arrays: selection on
+// the context's own stream (which must be idle: call between two driver calls), copies on the delivery stream behind it.
+// Returns through *n_new how many instances this delivery carries (0: nothing launched).
+static int deliver_finished(acoc_ctx* ctx, const Delivery& dv, int* n_new)
 {
+    const int N = ctx->N, TT = ctx->TT, Np = ctx->Np;
+    if (!ctx->delivered) {
+        TRY(dalloc(ctx, &ctx->delivered, (size_t)Np));
+        TRY(dalloc(ctx, &ctx->deliver_rows, (size_t)Np));
+        CK(cudaEventCreateWithFlags(&ctx->ev_deliver, cudaEventDisableTiming));
+    }
+    int* cnt = ctx->counters + 3;
+    CK(cudaMemsetAsync(cnt, 0, sizeof(int), ctx->stream));
+    // (the rows table of the previous delivery of this context may still be in use: wait for it on the solver's stream)
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_deliver, 0));
+    k_deliver_select<<<(N + 255) / 256, 256, 0, ctx->stream>>>(ctx->S.status, ctx->uidx, ctx->delivered, ctx->deliver_rows, cnt, N);
+    CK(cudaGetLastError());
+    int h = 0;
+    CK(cudaMemcpyAsync(&h, cnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_deliver, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n_new) *n_new = h;
+    ctx->n_delivered += h;
+    if (h == 0) return 0;
+    CK(cudaStreamWaitEvent(dv.stream, ctx->ev_deliver, 0));
     const dim3 block(32, 8);
     static const int ctas = getenv("ACOC_DELIVER_CTAS") ? atoi(getenv("ACOC_DELIVER_CTAS")) : 64;  // (8: 536 ms, 16: 373, 32: 293, 64: 281 ms end to end; a machine-filling grid: 320)
     const int gx = std::max(1, ctas), gu = gx;
-    const int *rs = ctx->S.result_slot, *stt = ctx->S.status, *ui = ctx->uidx;
-    const int N = ctx->N, TT = ctx->TT, Np = ctx->Np;
+    const int *rs = ctx->S.result_slot, *rows = ctx->deliver_rows;
     if (ctx->x_float) {
         const float *a = (const float*)ctx->X[0], *b = (const float*)ctx->X[1], *c2 = (const float*)ctx->X[2];
-        if (dv.x_f32) k_deliver<float, float><<<gx, block, 0, dv.stream>>>(a, b, c2, rs, stt, ui, nullptr, (float*)dv.xx, N, 6, TT, Np, 0);
-        else k_deliver<float, double><<<gx, block, 0, dv.stream>>>(a, b, c2, rs, stt, ui, ctx->fp32 ? nullptr : (const double*)ctx->x0, (double*)dv.xx, N, 6, TT, Np, 0);
+        if (dv.x_f32) k_deliver<float, float><<<gx, block, 0, dv.stream>>>(a, b, c2, rs, rows, nullptr, (float*)dv.xx, N, 6, TT, Np, 0);
+        else k_deliver<float, double><<<gx, block, 0, dv.stream>>>(a, b, c2, rs, rows, ctx->fp32 ? nullptr : (const double*)ctx->x0, (double*)dv.xx, N, 6, TT, Np, 0);
     } else {
         const double *a = (const double*)ctx->X[0], *b = (const double*)ctx->X[1], *c2 = (const double*)ctx->X[2];
-        k_deliver<double, double><<<gx, block, 0, dv.stream>>>(a, b, c2, rs, stt, ui, nullptr, (double*)dv.xx, N, 6, TT, Np, 0);
+        k_deliver<double, double><<<gx, block, 0, dv.stream>>>(a, b, c2, rs, rows, nullptr, (double*)dv.xx, N, 6, TT, Np, 0);
     }
     CK(cudaGetLastError());
     if (ctx->fp32)
-        k_deliver<float, double><<<gu, block, 0, dv.stream>>>((const float*)ctx->U[0], (const float*)ctx->U[1], (const float*)ctx->U[2], rs, stt, ui, nullptr,
+        k_deliver<float, double><<<gu, block, 0, dv.stream>>>((const float*)ctx->U[0], (const float*)ctx->U[1], (const float*)ctx->U[2], rs, rows, nullptr,
                                                                 dv.uu, N, 2, TT, Np, 1);
     else
-        k_deliver<double, double><<<gu, block, 0, dv.stream>>>((const double*)ctx->U[0], (const double*)ctx->U[1], (const double*)ctx->U[2], rs, stt, ui,
+        k_deliver<double, double><<<gu, block, 0, dv.stream>>>((const double*)ctx->U[0], (const double*)ctx->U[1], (const double*)ctx->U[2], rs, rows,
                                                                  nullptr, dv.uu, N, 2, TT, Np, 1);  // uu_star[:,-1] = uu_star[:,-2], optcon.py:505
     CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev_deliver, dv.stream));  // the rows table is free again once these copies are done
+    return 0;
+}
+
+static int reset_delivery(acoc_ctx* ctx)
+{
+    ctx->n_delivered = 0;
+    if (ctx->delivered) CK(cudaMemsetAsync(ctx->delivered, 0, (size_t)ctx->Np * sizeof(int), ctx->stream));
     return 0;
 }
 
 static int solve_impl(acoc_ctx* c, long long* total_iters, const Delivery* dv)
 {
     TRY(ready(c));
+    if (dv) TRY(reset_delivery(c));
     int active = 1;
     double total_ms = 0, phase[6] = {0, 0, 0, 0, 0, 0}, gen_ms = 0;
     long long launches = 0;
@@ -2335,6 +2387,11 @@ static int solve_impl(acoc_ctx* c, long long* total_iters, const Delivery* dv)
             fprintf(stderr, "acoc_trace gen=%zu n=%d kk=%d..%d active_after=%d need_last=%d ms=%.3f launches=%lld\n", chain.size() - 1, cur->N, kk_before,
                     cur->kk - 1, active, cur->last_need, cur->total_ms, cur->launches);
         for (int p = 0; p < 6; ++p) phase[p] += cur->phase_ms[p];
+        // (Deliveries between spawns -- whenever another 1/deliver_div of the batch has finished -- were measured too: the copies then run
+        // beside the throughput-bound iterations of the noise phase and slow them by more than they hide: 0.317 s end to end against
+        // 0.295 s with deliveries at the spawns only.  Off by default.)
+        static const int deliver_div = getenv("ACOC_DELIVER_DIV") ? atoi(getenv("ACOC_DELIVER_DIV")) : 0;
+        if (dv && deliver_div > 0 && active > 0 && (long long)(cur->N - active - cur->n_delivered) * deliver_div >= cur->N) TRY(deliver_finished(cur, *dv, nullptr));
         if (active > 0 && !(c->flags & ACOC_SOLVE_IN_PLACE) && cur->N >= ACOC_GEN_MIN && 2 * active <= cur->N && cur->kk < cur->O.max_iters - 1) {
             acoc_ctx* ch = nullptr;
             CK(cudaEventRecord(cur->ev[6], cur->stream));
@@ -2343,6 +2400,7 @@ static int solve_impl(acoc_ctx* c, long long* total_iters, const Delivery* dv)
             if (rc == 0 && ch) {
                 if (dv) {
                     // the finished instances of `cur` are final: deliver them now, while the survivors iterate in the child
+                    TRY(reset_delivery(ch));
                     if (!ch->uidx) TRY(dalloc(ch, &ch->uidx, (size_t)ch->Np));
                     k_compose_uidx<<<(active + 255) / 256, 256, 0, cur->stream>>>(ch->origin, cur->uidx, ch->uidx, active);
                     CK(cudaGetLastError());
@@ -2352,7 +2410,7 @@ static int solve_impl(acoc_ctx* c, long long* total_iters, const Delivery* dv)
                 float ms = 0;
                 CK(cudaEventElapsedTime(&ms, cur->ev[6], cur->ev[7]));
                 gen_ms += ms;
-                if (dv) TRY(deliver_finished(cur, *dv));
+                if (dv) TRY(deliver_finished(cur, *dv, nullptr));
                 chain.push_back(ch);
                 cur = ch;
             }
@@ -2361,7 +2419,7 @@ static int solve_impl(acoc_ctx* c, long long* total_iters, const Delivery* dv)
     if (dv) {
         // whatever `cur` (the last generation, or the batch itself) still holds: instances that ran out of iterations while active get
         // their status from the driver, so everything is final here
-        TRY(deliver_finished(cur, *dv));
+        TRY(deliver_finished(cur, *dv, nullptr));
         CK(cudaStreamSynchronize(dv->stream));  // (the folds below rewrite rows of the parents; keep them behind the deliveries)
     }
     for (size_t k = chain.size() - 1; k >= 1; --k) {

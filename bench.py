@@ -517,7 +517,8 @@ def run_batched(args, rank, world, local):
         e2e = describe(wall, g, gs, h2d, d2h,
                        "PipelinedNewton.solve(refs=(kind, per-instance parameters) in pinned host memory): per sub-batch H2D of the parameters -> "
                        "reference generators + initial guess on the device -> solve() to descent >= -1e-6 -> D2H of xx_star (%s), uu_star "
-                       "(float64) and the statistics into pinned host memory; sub-batches overlap copies with compute"
+                       "(float64) straight into the pinned host arrays by the delivery kernel (finished instances while the survivor generations "
+                       "still iterate), statistics"
                        % ("float32: lossless, the quantised states are float32 values" if f32_dl else "float64"), args.chunks_generated)
         del xs32_t
         pn.close()
@@ -791,7 +792,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=4, help="sub-batches of the pipelined end-to-end solve with reference arrays uploaded from the host")
     ap.add_argument("--chunks-generated", type=int, default=None, help="sub-batches of the headline end-to-end solve (references generated on the device: "
                     "little to upload, so fewer, larger sub-batches win on one GPU -- 1: 0.322 s, 2: 0.325 s, 4: 0.338 s, 8: 0.345 s; with 8 GPUs "
-                    "sharing the host 4 is best -- 2: 0.500 s, 4: 0.490 s, 8: 0.514 s); default 2, or 4 from four GPUs on")
+                    "sharing the host 4 is best -- 2: 0.500 s, 4: 0.490 s, 8: 0.514 s); default 1, or 4 from four GPUs on")
     ap.add_argument("--no-stagger", action="store_true", help="end-to-end leg: same stream priority for every sub-batch (A/B)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-host", action="store_true", help="skip the second end-to-end leg (reference arrays uploaded from the host)")
@@ -801,7 +802,7 @@ def main():
     args.warmup = max(args.warmup, 0)
     args.instances_given = args.instances is not None
     if args.chunks_generated is None:
-        args.chunks_generated = 4 if int(os.environ.get("WORLD_SIZE", "1")) >= 4 else 2
+        args.chunks_generated = 4 if int(os.environ.get("WORLD_SIZE", "1")) >= 4 else 1
     if args.instances is None:
         args.instances = 65536
 
