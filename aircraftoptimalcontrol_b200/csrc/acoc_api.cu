@@ -2780,9 +2780,16 @@ int acoc_lqr_tracking(int device, int n, int TT, const double* params, int state
                       const double* xx_opt, const double* uu_opt, const double* delta, double* xx_reg, double* uu_reg, double* K)
 {
     REQUIRE(n > 0 && TT >= 3 && params && Q && R && QT && xx_opt && uu_opt && delta && xx_reg && uu_reg, "acoc_lqr_tracking: bad argument");
-    acoc_ctx* c = nullptr;
-    TRY(acoc_ctx_create(device, n, TT, (state_f64 ? ACOC_STATE_F64 : 0) | ACOC_REFS_SHARED | ACOC_CTX_LITE, &c));
-    struct Guard { acoc_ctx* c; ~Guard() { acoc_ctx_destroy(c); } } guard{c};
+    // the rollout context (one trajectory slot for n instances + staging) is kept between calls of the same size: creating it costs
+    // more than the tracking itself (~0.5 GB of cudaMalloc + memset for 4096 instances)
+    static std::mutex mu;
+    static acoc_ctx* cached = nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    const unsigned flags = (state_f64 ? ACOC_STATE_F64 : 0) | ACOC_REFS_SHARED | ACOC_CTX_LITE;
+    if (cached && (cached->device != device || cached->N != n || cached->TT != TT || cached->flags != flags)) { acoc_ctx_destroy(cached); cached = nullptr; }
+    if (!cached) TRY(acoc_ctx_create(device, n, TT, flags, &cached));
+    acoc_ctx* c = cached;
+    TRY(use_device(device));
     TRY(acoc_set_model(c, params));
     const Model M = c->P.M;
     // nominal trajectory, time-major [TT][6] / [TT][2] (this is exactly the "shared reference" SoA layout)
