@@ -32,6 +32,14 @@ def main(path):
             if w in hdr:
                 i = hdr.index(w)
                 print("%-90s %s %s" % (w, r[i], units[i]))
+        for i, h in enumerate(hdr):  # every other stall reason that matters
+            if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and "not_issued" not in h and h not in WANT:
+                try:
+                    v = float(r[i])
+                except ValueError:
+                    continue
+                if v > 0.15:
+                    print("%-90s %s %s" % (h, r[i], units[i]))
 
 
 if __name__ == "__main__":
