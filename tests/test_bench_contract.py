@@ -41,7 +41,7 @@ def test_our_arm_needs_a_gpu():
 
 
 def test_committed_bench_line_has_every_contract_key():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r01e_bench.json")))
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench.json")))
     for k in BASE_KEYS + ("clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
         assert k in d, k
     assert d["metric"] == "trajectory_newton_iterations_per_second" and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0
@@ -52,5 +52,7 @@ def test_committed_bench_line_has_every_contract_key():
         assert k in d["cpu_baseline"], k
     for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
         assert k in d["e2e"], k
-    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["value"] < d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] < d["value"]
+    assert d["e2e_host_refs"]["h2d_bytes_per_step"] > 1e6 and d["roofline"]["traffic"] > 0 and d["roofline"]["frac"] <= 1.2
+    assert d["cpu_baseline"]["python_reference"]["value"] > 0
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
