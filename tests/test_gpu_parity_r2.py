@@ -443,3 +443,45 @@ def test_solve_deliver_zero_slot_and_pipelined(gpu):
         xb, ub, sb = pn.solve(xr, ur, x_dtype=np.float32, out=(xp, up))         # page-locked outputs: direct delivery
     assert np.array_equal(xa, xb) and np.array_equal(ua, ub) and np.array_equal(sa["x0"], sb["x0"])
     assert np.array_equal(sa["iters"], sb["iters"]) and np.array_equal(sa["J"], sb["J"])
+
+
+def test_compact_references_gradient_method_and_fp32_delivery(gpu):
+    """Two remaining combinations of the round-2 paths: the steepest-descent sweep (k_gradient_tma) with parametric references against
+    host arrays, and the direct delivery from an FP32-mode context against its own staged download."""
+    from aircraftoptimalcontrol_b200 import refgen
+    n, TT = 4500, 150
+    rng = np.random.default_rng(91)
+    zf, xf = rng.uniform(1.5, 3.5, n), rng.uniform(14, 18, n)
+    xr, ur = refgen.step_problem(xf, zf, tf=TT * 1e-3, TT=TT)
+    Q, R, QT = refgen.weights("step")
+    out = []
+    for host in (True, False):
+        with gpu.BatchedNewton(n, TT=TT, armijo="lazy", method="gradient", max_iters=8) as bn:
+            bn.set_weights(Q, R, QT)
+            if host:
+                bn.set_refs(xr, ur)
+            else:
+                bn.set_refs_step(zf, xf, tf=TT * 1e-3)
+            bn.init_guess()
+            bn.solve()
+            out.append((bn.result(), bn.history(), bn.stats()))
+    ((xa, ua), ha, sa), ((xb, ub), hb, sb) = out
+    assert np.array_equal(xa, xb) and np.array_equal(ua, ub)
+    for k in ("JJ", "descent", "stepsize", "n_armijo"):
+        assert np.array_equal(ha[k], hb[k]), k
+    assert np.array_equal(sa["iters"], sb["iters"]) and sa["iters"].max() == 7
+    keep_x, xs = _pinned((n, 6, TT), np.float32)
+    keep_u, us = _pinned((n, 2, TT), np.float64)
+    res = []
+    for direct in (False, True):
+        with gpu.BatchedNewton(n, TT=TT, armijo="lazy", precision="f32", max_iters=16) as bn:
+            bn.set_weights(Q, R, QT)
+            bn.set_refs_step(zf, xf, tf=TT * 1e-3)     # (FP32 mode keeps expanded references)
+            bn.init_guess()
+            if direct:
+                bn.solve_deliver((xs, us))
+                res.append((xs.copy(), us.copy()))
+            else:
+                bn.solve()
+                res.append(bn.result_f32()[:2])
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
