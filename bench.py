@@ -217,6 +217,34 @@ def python_reference_baseline(workload):
     return out
 
 
+def bind_to_gpu_numa_node(local):
+    """Multi-GPU runs: keep this rank's threads (and with them the page-locked host buffers it allocates, which follow the allocating
+    thread's NUMA policy) on the NUMA node its GPU hangs off, so that eight ranks do not push their results through one socket's
+    memory controllers.  Best effort: returns a description of what was done, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
+        if len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"gpu": local, "pci": bdf, "numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        return None
+
+
 def emit(line: dict):
     """Print the ONE JSON line on the process's original stdout."""
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
@@ -375,7 +403,9 @@ def run_batched(args, rank, world, local):
     from aircraftoptimalcontrol_b200 import _lib, dist as D
 
     dist = None
+    numa = None
     if world > 1:
+        numa = None if args.no_numa_bind else bind_to_gpu_numa_node(local)
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -552,7 +582,7 @@ def run_batched(args, rank, world, local):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": config_dict(args, n, world), "clocks": clocks, "e2e": e2e, "e2e_host_refs": e2e_host, "gpu_launches": launches,
                 "active_after_timed_region": n_active, "instance_iterations_timed": its_done, "whole_solve": whole, "roofline": roofline, "fp64": fp64,
-                "phase_ms": phases, "cpu_baseline": cpu, "device": pkg.device_info(local)["name"], "device_bytes": device_bytes}
+                "phase_ms": phases, "cpu_baseline": cpu, "device": pkg.device_info(local)["name"], "device_bytes": device_bytes, "numa_binding_rank0": numa}
         emit(line)
     if dist is not None:
         dist.barrier()
@@ -794,6 +824,7 @@ def main():
                     "little to upload, so fewer, larger sub-batches win on one GPU -- 1: 0.322 s, 2: 0.325 s, 4: 0.338 s, 8: 0.345 s; with 8 GPUs "
                     "sharing the host 4 is best -- 2: 0.500 s, 4: 0.490 s, 8: 0.514 s); default 1, or 4 from four GPUs on")
     ap.add_argument("--no-stagger", action="store_true", help="end-to-end leg: same stream priority for every sub-batch (A/B)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="multi-GPU: do not bind the rank to its GPU's NUMA node (A/B)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-host", action="store_true", help="skip the second end-to-end leg (reference arrays uploaded from the host)")
     ap.add_argument("--no-cpu", action="store_true")
