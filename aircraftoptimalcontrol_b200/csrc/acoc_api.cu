@@ -1589,6 +1589,20 @@ static bool bwd_split(const acoc_ctx* c)
     if (sms <= 0) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     return !off && n_tiles(c) <= per_sm * sms;
 }
+// the backward sweep as a pipeline of warp roles (k_backward_cols, 11 warps per tile: linearisation ahead of time in three warps, costate
+// warp, gain warp, one warp per column of the Riccati matrix): the shortest chain of instructions per step, for batches in which every
+// tile has an SM of its own (4,736 instances on a B200)
+#ifndef ACOC_BWD_COLS_TILES_PER_SM
+#define ACOC_BWD_COLS_TILES_PER_SM 1
+#endif
+static bool bwd_cols(const acoc_ctx* c)
+{
+    static const bool off = getenv("ACOC_NO_BWD_COLS") != nullptr;  // A/B: k_backward_split / k_backward_tma
+    static const int per_sm = getenv("ACOC_BWD_COLS_TILES_PER_SM") ? atoi(getenv("ACOC_BWD_COLS_TILES_PER_SM")) : ACOC_BWD_COLS_TILES_PER_SM;
+    int sms = c->sm_count;
+    if (sms <= 0) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    return !off && n_tiles(c) <= per_sm * sms;
+}
 template <typename F, typename XT>
 static int launch_backward_t(acoc_ctx* c, bool exact)
 {
@@ -1596,7 +1610,21 @@ static int launch_backward_t(acoc_ctx* c, bool exact)
     const ProblemT<F> P = prob<F>(c);
     const XT* X = (const XT*)c->X[cur];
     const F* U = (const F*)c->U[cur];
-    if (use_tma(c) && bwd_split(c)) {  // small batch: costate warp + matrix warp per tile (k_backward_split)
+    if (use_tma(c) && bwd_cols(c)) {  // small batch: warp-role pipeline per tile (k_backward_cols)
+        const int gs = sweep_grid(c, TILE);
+        cudaStream_t st = sweep_stream(c);
+        const bool dg = c->P.W.diag != 0;
+#define ACOC_BC_LAUNCH(EX, DG)                                                                                                        \
+        do {                                                                                                                          \
+            const size_t sm = backward_cols_smem<EX, F, XT>();                                                                        \
+            TRY(prefer_smem(k_backward_cols<EX, F, XT, DG>));                                                                         \
+            if (sm > 48 * 1024) CK(cudaFuncSetAttribute(k_backward_cols<EX, F, XT, DG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+            k_backward_cols<EX, F, XT, DG><<<gs, BC_THREADS, sm, st>>>(P, tile_list(c), X, U, (F*)c->KSG, c->S.status, c->S.n_reg);  \
+        } while (0)
+        if (exact) { if (dg) ACOC_BC_LAUNCH(true, 1); else ACOC_BC_LAUNCH(true, 0); }
+        else { if (dg) ACOC_BC_LAUNCH(false, 1); else ACOC_BC_LAUNCH(false, 0); }
+#undef ACOC_BC_LAUNCH
+    } else if (use_tma(c) && bwd_split(c)) {  // small batch: costate warp + matrix warp per tile (k_backward_split)
         const int gs = sweep_grid(c, TILE);
         cudaStream_t st = sweep_stream(c);
         const bool dg = c->P.W.diag != 0;

@@ -310,6 +310,129 @@ ACOC_HD int riccati_matrix(const ModelT<F>& M, const WeightsT<F>& W, const Lin<F
     return reg;
 }
 
+// ---- the matrix half BY COLUMNS (k_backward_cols: one warp per column of P, small batches) -----------------------------
+// riccati_matrix() cut along the columns j of the sweep.  Everything column j produces -- W = P A e_j, N(i,j) = (A'W)_i for i <= j,
+// Mx(:,j), (A'p)_j, then Y(:,j), K(:,j), P_t(i,j) for i <= j and p_t(j) -- needs, beside the old P, p and the linearisation, only the
+// 2x2 gain block (computed redundantly by every column: riccati_gain) and Mx(:,i) of the columns i < j (exchanged once per step).
+// Every number is formed by the same expression as in riccati_matrix(), so the two are bit-identical (tests/test_kernel_math_host.py
+// replays both on the host).
+template <typename F>
+struct RicGain {
+    F gi00, gi01, gi11;  // G^-1 (the Riccati update always uses the plain inverse, optcon.py:728)
+    F k00, k01, k11;     // the inverse the GAIN uses: G^-1, or (G + 0.5 I)^-1 when G has a non-positive eigenvalue (optcon.py:743-749)
+    F m0, m1, y0, y1;    // m = B'p + r/2, y = G^-1 m
+    int reg;
+};
+
+template <typename F>
+ACOC_HD RicGain<F> riccati_gain(const ModelT<F>& M, const WeightsT<F>& W, const Lin<F>& l, const F* r, const F* Pm, const F* p)
+{
+    RicGain<F> o;
+    const F b41 = M.b41;
+    const F P22 = Pm[sym(2, 2)], P25 = Pm[sym(2, 5)], P55 = Pm[sym(5, 5)], P24 = Pm[sym(2, 4)], P45 = Pm[sym(4, 5)], P44 = Pm[sym(4, 4)];
+    const F pb2 = fma_(l.b50, P25, l.b20 * P22), pb5 = fma_(l.b50, P55, l.b20 * P25);
+    const F G00 = fma_(l.b50, pb5, fma_(l.b20, pb2, W.R[0]));
+    const F G01 = fma_(b41, fma_(l.b50, P45, l.b20 * P24), W.R[1]);
+    const F G11 = fma_(b41 * b41, P44, W.R[3]);
+    o.m0 = fma_(l.b50, p[5], fma_(l.b20, p[2], F(0.5) * r[0]));
+    o.m1 = fma_(b41, p[4], F(0.5) * r[1]);
+    const F det = fma_(G00, G11, -(G01 * G01));
+    const F idet = F(1.0) / det;
+    o.gi00 = G11 * idet; o.gi01 = -G01 * idet; o.gi11 = G00 * idet;
+    o.y0 = fma_(o.gi01, o.m1, o.gi00 * o.m0); o.y1 = fma_(o.gi11, o.m1, o.gi01 * o.m0);
+    const F hd = F(0.5) * (G00 - G11), mid = F(0.5) * (G00 + G11);
+    const F rad = sqrt_(fma_(hd, hd, G01 * G01));
+    if (mid - rad > F(0.0)) { o.reg = 0; o.k00 = o.gi00; o.k01 = o.gi01; o.k11 = o.gi11; }
+    else {
+        o.reg = 1;
+        const F H00 = G00 + F(0.5), H11 = G11 + F(0.5);
+        const F id2 = F(1.0) / fma_(H00, H11, -(G01 * G01));
+        o.k00 = H11 * id2; o.k01 = -G01 * id2; o.k11 = H00 * id2;
+    }
+    return o;
+}
+
+// first half of column J: PnJ[i] = N(i,J) for i <= J, Mx(:,J), (A'p)_J
+template <bool EXACT, int J, typename F>
+ACOC_HD void riccati_col_sweep(const ModelT<F>& M, const Lin<F>& l, const Hess<F>& h, const F* Pm, const F* p, F* PnJ, F& mx0, F& mx1, F& atp)
+{
+    F Wc[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        F row[NS];
+#pragma unroll
+        for (int c = 0; c < NS; ++c) row[c] = Pm[sym(k, c)];
+        Wc[k] = acol(l, M.dt, row, J);
+    }
+#pragma unroll
+    for (int i = 0; i <= J; ++i) PnJ[i] = acol(l, M.dt, Wc, i);
+    mx0 = fma_(l.b50, Wc[5], l.b20 * Wc[2]);
+    mx1 = M.b41 * Wc[4];
+    if (EXACT) {  // S = lux + fux (optcon.py:446)
+        if (J == 2) mx0 += h.s2;
+        if (J == 3) mx0 += h.s3;
+        if (J == 5) mx0 += h.s5;
+    }
+    atp = acol(l, M.dt, p, J);
+}
+
+// second half of column J: Mx0[i], Mx1[i] for i <= J (own column included) -> K(:,J), P_t(i,J) for i <= J, p_t(J)
+template <bool EXACT, int DG, int J, typename F>
+ACOC_HD void riccati_col_finish(const WeightsT<F>& W, const Hess<F>& h, F qJ, const RicGain<F>& gn, const F* PnJ, const F* Mx0, const F* Mx1,
+                                F atp, F* PJ, F& pJ, F& K0, F& K1)
+{
+    const F Y0 = fma_(gn.gi01, Mx1[J], gn.gi00 * Mx0[J]);
+    const F Y1 = fma_(gn.gi11, Mx1[J], gn.gi01 * Mx0[J]);
+    K0 = -fma_(gn.k01, Mx1[J], gn.k00 * Mx0[J]);
+    K1 = -fma_(gn.k11, Mx1[J], gn.k01 * Mx0[J]);
+#pragma unroll
+    for (int i = 0; i <= J; ++i) {
+        const F corr = fma_(Mx1[i], Y1, Mx0[i] * Y0);
+        if (DG == 1 && i != J) PJ[i] = PnJ[i] - corr;
+        else {
+            const F qij = weights_diag<DG>(W) ? (i == J ? W.Q[i * 7] : F(0.0)) : W.Q[i * 6 + J];
+            PJ[i] = (PnJ[i] + qij) - corr;
+        }
+    }
+    pJ = fma_(F(0.5), qJ, atp) - fma_(Mx1[J], gn.y1, Mx0[J] * gn.y0);
+    if (EXACT) {  // Q_t = lxx + fxx (optcon.py:444)
+        if (J == 2) PJ[2] += h.h22;
+        if (J == 3) { PJ[2] += h.h23; PJ[3] += h.h33; }
+        if (J == 5) { PJ[2] += h.h25; PJ[3] += h.h35; PJ[5] += h.h55; }
+    }
+}
+
+// riccati_matrix() recomposed from the column pieces (host replay of k_backward_cols' arithmetic; the kernel runs the six columns in
+// six warps and exchanges Mx and the new P through shared memory)
+template <bool EXACT, int DG, int J, typename F>
+ACOC_HD void riccati_cols_a_(const ModelT<F>& M, const Lin<F>& l, const Hess<F>& h, const F* Pm, const F* p, F (*Pn)[NS], F* Mx0, F* Mx1, F* Atp)
+{
+    riccati_col_sweep<EXACT, J, F>(M, l, h, Pm, p, Pn[J], Mx0[J], Mx1[J], Atp[J]);
+    if constexpr (J + 1 < NS) riccati_cols_a_<EXACT, DG, J + 1, F>(M, l, h, Pm, p, Pn, Mx0, Mx1, Atp);
+}
+template <bool EXACT, int DG, int J, typename F>
+ACOC_HD void riccati_cols_b_(const WeightsT<F>& W, const Hess<F>& h, const F* q, const RicGain<F>& gn, F (*Pn)[NS], const F* Mx0, const F* Mx1,
+                             const F* Atp, F* Pm, F* p, F* K)
+{
+    F PJ[NS];
+    riccati_col_finish<EXACT, DG, J, F>(W, h, q[J], gn, Pn[J], Mx0, Mx1, Atp[J], PJ, p[J], K[J], K[NS + J]);
+#pragma unroll
+    for (int i = 0; i <= J; ++i) Pm[sym(i, J)] = PJ[i];
+    if constexpr (J + 1 < NS) riccati_cols_b_<EXACT, DG, J + 1, F>(W, h, q, gn, Pn, Mx0, Mx1, Atp, Pm, p, K);
+}
+template <bool EXACT, int DG = -1, typename F>
+ACOC_HD int riccati_matrix_by_columns(const ModelT<F>& M, const WeightsT<F>& W, const Lin<F>& l, const Hess<F>& h, const F* q, const F* r,
+                                      F* Pm, F* p, F* K, F* sig)
+{
+    const RicGain<F> gn = riccati_gain(M, W, l, r, Pm, p);
+    F Pn[NS][NS], Mx0[NS], Mx1[NS], Atp[NS];
+    riccati_cols_a_<EXACT, DG, 0, F>(M, l, h, Pm, p, Pn, Mx0, Mx1, Atp);            // every column reads the OLD P, p
+    riccati_cols_b_<EXACT, DG, 0, F>(W, h, q, gn, Pn, Mx0, Mx1, Atp, Pm, p, K);    // ... and only then are they overwritten
+    sig[0] = -fma_(gn.k01, gn.m1, gn.k00 * gn.m0);
+    sig[1] = -fma_(gn.k11, gn.m1, gn.k01 * gn.m0);
+    return gn.reg;
+}
+
 template <bool EXACT, int DG = -1, typename F>
 ACOC_HD int riccati_step(const ModelT<F>& M, const WeightsT<F>& W, const Lin<F>& l, const Hess<F>& h, const F* q, const F* r,
                          F* Pm, F* p, F* lam, F* K, F* sig, F* g)

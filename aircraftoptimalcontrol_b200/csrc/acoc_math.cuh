@@ -321,6 +321,52 @@ ACOC_HD Hess<F> hess_contract(const ModelT<F>& M, const F* x, const F* u, const 
     return h;
 }
 
+// hess_contract() cut at lambda: hess_pre() forms everything that does not depend on the costate (one warp of k_backward_cols runs it
+// ahead of time, several time steps in parallel), hess_post() the fused multiply-adds with lambda_{t+1} (the warp that carries the
+// costate recurrence).  Same expressions as hess_contract(), so hess_post(hess_pre(..), lam) is bit-identical to it (host replay test).
+template <typename F>
+struct HessPre { F v22, v23, v33, v55, g22, g23, g25, g33, g55, c0, c1, c2, c3, e2, e3a, e3b; };
+
+template <typename F>
+ACOC_HD HessPre<F> hess_pre(const ModelT<F>& M, const F* x, const Trig<F>& t, const Lin<F>& l)
+{
+    HessPre<F> a;
+    const F V = x[2], al = t.alpha, iV = l.iV, iV2 = iV * iV;
+    const F cv2 = M.cdk * V * V;
+    a.v22 = -M.dt_m * M.k * l.drag_c;
+    a.v23 = -M.dt_m * M.cdk * V * (F(2.0) * al);
+    a.v33 = -M.dt_m * (cv2 + l.tca);
+    a.v55 = -M.dt_m * (cv2 + l.tca - M.gm * t.sg);
+    const F w = fma_(l.lift, al, l.tsa) - M.gm * t.cg;
+    const F clkdtm = M.clk * M.dt_m;
+    a.g22 = fma_(F(2.0) * M.dt_m * w * iV2, iV, -clkdtm * al * iV);
+    a.g23 = fma_(-M.dt_m * l.liftT, iV2, clkdtm);
+    a.g25 = fma_(M.dt_m * (l.liftT - M.gm * t.sg), iV2, -clkdtm);
+    a.g33 = -M.dt_m * l.tsa * iV;
+    a.g55 = -M.dt_m * (l.tsa - M.gm * t.cg) * iV;
+    const F dtV = M.dt * V;
+    a.c0 = -M.dt * t.sg; a.c1 = -M.dt * t.cg; a.c2 = -dtV * t.cg; a.c3 = dtV * t.sg;
+    a.e2 = -M.dt_m * t.sa * iV2; a.e3a = -M.dt_m * t.sa; a.e3b = M.dt_m * t.ca * iV;
+    return a;
+}
+
+template <typename F>
+ACOC_HD Hess<F> hess_post(const HessPre<F>& a, const F* lam)
+{
+    Hess<F> h;
+    const F l0 = lam[0], l1 = lam[1], l2 = lam[2], l5 = lam[5];
+    h.h22 = fma_(l2, a.v22, l5 * a.g22);
+    h.h23 = fma_(l2, a.v23, l5 * a.g23);
+    h.h25 = fma_(l0, a.c0, fma_(l1, a.c1, fma_(l2, -a.v23, l5 * a.g25)));
+    h.h33 = fma_(l2, a.v33, l5 * a.g33);
+    h.h35 = -h.h33;
+    h.h55 = fma_(l0, a.c2, fma_(l1, a.c3, fma_(l2, a.v55, l5 * a.g55)));
+    h.s2 = l5 * a.e2;
+    h.s3 = fma_(l2, a.e3a, l5 * a.e3b);
+    h.s5 = -h.s3;
+    return h;
+}
+
 // DG: what the caller knows about the weights at compile time -- 1: diagonal, 0: dense, -1: look at W.diag at run time.  The hot
 // kernels are instantiated for DG = 1 (every shipped configuration) and DG = 0, which removes the dense arm, its branches and the
 // additions of structural zeros from their time loops; same arithmetic on the entries that exist.

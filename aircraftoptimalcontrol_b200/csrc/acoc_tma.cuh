@@ -537,6 +537,7 @@ __global__ void __launch_bounds__(64) k_backward_tma(ProblemT<F> P, TileList L, 
 #ifndef ACOC_BS_XSTAGES
 #define ACOC_BS_XSTAGES 2
 #endif
+
 constexpr int BS_XSTAGES = ACOC_BS_XSTAGES;
 template <bool EXACT>
 struct BsMsg { static constexpr int N = 12 + NS + NI + (EXACT ? 7 : 0); };
@@ -545,6 +546,98 @@ constexpr size_t backward_split_smem()
 {
     return (size_t)BWD_STAGES * BwdStage<F, XT>::BYTES + (size_t)BS_XSTAGES * BsMsg<EXACT>::N * TILE * sizeof(F) +
            (BWD_STAGES + 2 * BS_XSTAGES) * sizeof(uint64_t);
+}
+
+// The COSTATE role of the warp-specialised backward sweeps (one warp per tile): TMA ring of x, u, references -> dx, lx, lu, trigonometry,
+// linearisation, lambda-contracted Hessians; hands the step's message (BsMsg) to the consumer warp(s) through the XS-deep message ring
+// (xfull: one arrival by this warp; xempty: one arrival per consumer warp), then g_t, lambda_t.
+template <bool EXACT, typename F, typename XT, int DG, int XS>
+__device__ __forceinline__ void bs_costate_role(const ProblemT<F>& P, int tile, int lane, bool live, F* x, F* xr, unsigned char* ring, F* msg,
+                                                uint64_t* bar_in, uint64_t* xfull, uint64_t* xempty, const XT* __restrict__ X,
+                                                const F* __restrict__ U, F* __restrict__ KSG)
+{
+    using St = BwdStage<F, XT>;
+    constexpr int NMSG = BsMsg<EXACT>::N;
+    const int TT = P.TT, Np = P.Np, i = tile * TILE + lane, nsteps = TT - 1;
+    const RefMode<F> rm(P, i, live);
+    auto issue = [&](int k) {  // ring step k <-> time t = TT-2-k
+        const int t = TT - 2 - k;
+        unsigned char* st = ring + (k % BWD_STAGES) * St::BYTES;
+        uint64_t* b = bar_in + (k % BWD_STAGES);
+        mbar_arrive_expect_tx(b, St::U_B + St::X_B + (rm.tiled ? St::U_B + St::XR_B : 0) + (rm.has_v ? (uint32_t)(TILE * sizeof(F)) : 0));
+        tma_load(st + St::U_O, U + tile_base(t, NI, Np, tile), St::U_B, b);
+        tma_load(st + St::X_O, X + tile_base(t, NS, Np, tile), St::X_B, b);
+        if (rm.tiled) {
+            tma_load(st + St::UR_O, P.uref + tile_base(t, NI, Np, tile), St::U_B, b);
+            tma_load(st + St::XR_O, P.xref + tile_base(t, NS, Np, tile), St::XR_B, b);
+        } else if (rm.has_v)
+            tma_load(st + St::XR_O, P.rp_v + tile_base(t, 1, Np, tile), (uint32_t)(TILE * sizeof(F)), b);
+    };
+    if (lane == 0)
+        for (int k = 0; k < BWD_STAGES && k < nsteps; ++k) issue(k);
+    F lam[NS], u[NI], ur[NI];
+    if (live) {
+        F dxT[NS];
+#pragma unroll
+        for (int c = 0; c < NS; ++c) dxT[c] = x[c] - xr[c];
+        wmul6(P.W.QT, (int)weights_diag<DG>(P.W), dxT, lam);  // lam_{T-1} = QT dx (optcon.py:429-432)
+    }
+    for (int k = 0; k < nsteps; ++k) {
+        const int t = TT - 2 - k;
+        mbar_wait(bar_in + (k % BWD_STAGES), (uint32_t)((k / BWD_STAGES) & 1));
+        const unsigned char* st = ring + (k % BWD_STAGES) * St::BYTES;
+        XT xraw[NS];
+#pragma unroll
+        for (int c = 0; c < NS; ++c) xraw[c] = reinterpret_cast<const XT*>(st + St::X_O)[c * TILE + lane];
+#pragma unroll
+        for (int c = 0; c < NI; ++c) u[c] = reinterpret_cast<const F*>(st + St::U_O)[c * TILE + lane];
+        F vv = F(0.0);
+        if (rm.tiled) {
+#pragma unroll
+            for (int c = 0; c < NI; ++c) ur[c] = reinterpret_cast<const F*>(st + St::UR_O)[c * TILE + lane];
+#pragma unroll
+            for (int c = 0; c < NS; ++c) xr[c] = reinterpret_cast<const F*>(st + St::XR_O)[c * TILE + lane];
+        } else if (rm.has_v) vv = reinterpret_cast<const F*>(st + St::XR_O)[lane];
+        stage_release();
+        if (lane == 0 && k + BWD_STAGES < nsteps) issue(k + BWD_STAGES);
+        const int s = k % XS;
+        F* const m = msg + (size_t)s * NMSG * TILE + lane;
+        F q[NS], r[NI];
+        Lin<F> l;
+        if (live) {
+            rm.fill(P, t, i, vv, xr, ur);
+            finish_x(P, t, i, xraw, x);
+            F dx[NS], du[NI];
+#pragma unroll
+            for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
+#pragma unroll
+            for (int c = 0; c < NI; ++c) du[c] = u[c] - ur[c];
+            wmul6(P.W.Q, (int)weights_diag<DG>(P.W), dx, q);   // lx = Q dx   (aircraft_simplified.py:63)
+            wmul2(P.W.R, (int)weights_diag<DG>(P.W), du, r);   // lu = R du   (:64)
+            const Trig<F> tg = make_trig(x);
+            l = linearize(P.M, x, u, tg);
+            Hess<F> h;
+            if (EXACT) h = hess_contract(P.M, x, u, tg, l, lam);
+            if (k >= XS) mbar_wait(xempty + s, (uint32_t)((k / XS - 1) & 1));
+            m[0 * TILE] = l.a02; m[1 * TILE] = l.a05; m[2 * TILE] = l.a12; m[3 * TILE] = l.a15; m[4 * TILE] = l.a22; m[5 * TILE] = l.a23;
+            m[6 * TILE] = l.a25; m[7 * TILE] = l.a52; m[8 * TILE] = l.a53; m[9 * TILE] = l.a55; m[10 * TILE] = l.b20; m[11 * TILE] = l.b50;
+#pragma unroll
+            for (int c = 0; c < NS; ++c) m[(12 + c) * TILE] = q[c];
+            m[18 * TILE] = r[0]; m[19 * TILE] = r[1];
+            if (EXACT) {
+                m[20 * TILE] = h.h22; m[21 * TILE] = h.h23; m[22 * TILE] = h.h25; m[23 * TILE] = h.h33; m[24 * TILE] = h.h55;
+                m[25 * TILE] = h.s2; m[26 * TILE] = h.s3;
+            }
+        } else if (k >= XS) mbar_wait(xempty + s, (uint32_t)((k / XS - 1) & 1));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(xfull + s);
+        if (live) {
+            F g[NI];
+            riccati_costate(P.M, l, q, r, lam, g);
+            F* out = KSG + tile_base(t, 16, Np, tile) + lane;
+            out[14 * TILE] = g[0]; out[15 * TILE] = g[1];
+        }
+    }
 }
 
 template <bool EXACT, typename F, typename XT, int DG>
@@ -576,86 +669,7 @@ __global__ void __launch_bounds__(64, 4) k_backward_split(ProblemT<F> P, TileLis
         load_x(P, X, TT - 1, i, x);
     }
     if (role == 0) {
-        // ---------------------------------------------------------------- costate warp
-        const RefMode<F> rm(P, i, live);
-        auto issue = [&](int k) {  // ring step k <-> time t = TT-2-k
-            const int t = TT - 2 - k;
-            unsigned char* st = ring + (k % BWD_STAGES) * St::BYTES;
-            uint64_t* b = bar_in + (k % BWD_STAGES);
-            mbar_arrive_expect_tx(b, St::U_B + St::X_B + (rm.tiled ? St::U_B + St::XR_B : 0) + (rm.has_v ? (uint32_t)(TILE * sizeof(F)) : 0));
-            tma_load(st + St::U_O, U + tile_base(t, NI, Np, tile), St::U_B, b);
-            tma_load(st + St::X_O, X + tile_base(t, NS, Np, tile), St::X_B, b);
-            if (rm.tiled) {
-                tma_load(st + St::UR_O, P.uref + tile_base(t, NI, Np, tile), St::U_B, b);
-                tma_load(st + St::XR_O, P.xref + tile_base(t, NS, Np, tile), St::XR_B, b);
-            } else if (rm.has_v)
-                tma_load(st + St::XR_O, P.rp_v + tile_base(t, 1, Np, tile), (uint32_t)(TILE * sizeof(F)), b);
-        };
-        if (lane == 0)
-            for (int k = 0; k < BWD_STAGES && k < nsteps; ++k) issue(k);
-        F lam[NS], u[NI], ur[NI];
-        if (live) {
-            F dxT[NS];
-#pragma unroll
-            for (int c = 0; c < NS; ++c) dxT[c] = x[c] - xr[c];
-            wmul6(P.W.QT, (int)weights_diag<DG>(P.W), dxT, lam);  // lam_{T-1} = QT dx (optcon.py:429-432)
-        }
-        for (int k = 0; k < nsteps; ++k) {
-            const int t = TT - 2 - k;
-            mbar_wait(bar_in + (k % BWD_STAGES), (uint32_t)((k / BWD_STAGES) & 1));
-            const unsigned char* st = ring + (k % BWD_STAGES) * St::BYTES;
-            XT xraw[NS];
-#pragma unroll
-            for (int c = 0; c < NS; ++c) xraw[c] = reinterpret_cast<const XT*>(st + St::X_O)[c * TILE + lane];
-#pragma unroll
-            for (int c = 0; c < NI; ++c) u[c] = reinterpret_cast<const F*>(st + St::U_O)[c * TILE + lane];
-            F vv = F(0.0);
-            if (rm.tiled) {
-#pragma unroll
-                for (int c = 0; c < NI; ++c) ur[c] = reinterpret_cast<const F*>(st + St::UR_O)[c * TILE + lane];
-#pragma unroll
-                for (int c = 0; c < NS; ++c) xr[c] = reinterpret_cast<const F*>(st + St::XR_O)[c * TILE + lane];
-            } else if (rm.has_v) vv = reinterpret_cast<const F*>(st + St::XR_O)[lane];
-            stage_release();
-            if (lane == 0 && k + BWD_STAGES < nsteps) issue(k + BWD_STAGES);
-            const int s = k % BS_XSTAGES;
-            F* const m = msg + (size_t)s * NMSG * TILE + lane;
-            F q[NS], r[NI];
-            Lin<F> l;
-            if (live) {
-                rm.fill(P, t, i, vv, xr, ur);
-                finish_x(P, t, i, xraw, x);
-                F dx[NS], du[NI];
-#pragma unroll
-                for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
-#pragma unroll
-                for (int c = 0; c < NI; ++c) du[c] = u[c] - ur[c];
-                wmul6(P.W.Q, (int)weights_diag<DG>(P.W), dx, q);   // lx = Q dx   (aircraft_simplified.py:63)
-                wmul2(P.W.R, (int)weights_diag<DG>(P.W), du, r);   // lu = R du   (:64)
-                const Trig<F> tg = make_trig(x);
-                l = linearize(P.M, x, u, tg);
-                Hess<F> h;
-                if (EXACT) h = hess_contract(P.M, x, u, tg, l, lam);
-                if (k >= BS_XSTAGES) mbar_wait(xempty + s, (uint32_t)((k / BS_XSTAGES - 1) & 1));
-                m[0 * TILE] = l.a02; m[1 * TILE] = l.a05; m[2 * TILE] = l.a12; m[3 * TILE] = l.a15; m[4 * TILE] = l.a22; m[5 * TILE] = l.a23;
-                m[6 * TILE] = l.a25; m[7 * TILE] = l.a52; m[8 * TILE] = l.a53; m[9 * TILE] = l.a55; m[10 * TILE] = l.b20; m[11 * TILE] = l.b50;
-#pragma unroll
-                for (int c = 0; c < NS; ++c) m[(12 + c) * TILE] = q[c];
-                m[18 * TILE] = r[0]; m[19 * TILE] = r[1];
-                if (EXACT) {
-                    m[20 * TILE] = h.h22; m[21 * TILE] = h.h23; m[22 * TILE] = h.h25; m[23 * TILE] = h.h33; m[24 * TILE] = h.h55;
-                    m[25 * TILE] = h.s2; m[26 * TILE] = h.s3;
-                }
-            } else if (k >= BS_XSTAGES) mbar_wait(xempty + s, (uint32_t)((k / BS_XSTAGES - 1) & 1));
-            __syncwarp();
-            if (lane == 0) mbar_arrive(xfull + s);
-            if (live) {
-                F g[NI];
-                riccati_costate(P.M, l, q, r, lam, g);
-                F* out = KSG + tile_base(t, 16, Np, tile) + lane;
-                out[14 * TILE] = g[0]; out[15 * TILE] = g[1];
-            }
-        }
+        bs_costate_role<EXACT, F, XT, DG, BS_XSTAGES>(P, tile, lane, live, x, xr, ring, msg, bar_in, xfull, xempty, X, U, KSG);
         return;
     }
     // ---------------------------------------------------------------- matrix warp
@@ -696,6 +710,361 @@ __global__ void __launch_bounds__(64, 4) k_backward_split(ProblemT<F> P, TileLis
         }
     }
     if (live && nreg && status[i] == ST_ACTIVE) n_reg[i] += nreg;
+}
+
+// =================================================================================================================
+// fused backward sweep of SMALL batches as a pipeline of warp roles: one CTA = one tile of 32 instances = 5 + NS warps.
+// A lone warp pays ~4-6 cycles per instruction of a backward step whatever it does (dependent FP64 chains, in-order issue), so what a
+// latency-bound batch pays per step is the instruction count of the LONGEST role.  The step is cut along its true recurrences:
+//   PRE warps (BC_NPRE of them; warp w takes the steps k = w mod BC_NPRE -- nothing here depends on another step): own TMA ring of
+//       x, u, references -> dx, lx, lu, trigonometry, linearisation, and the costate-independent part of the Hessian terms (hess_pre).
+//       Message A per step: linearisation (12), lx (6), lu (2), hess_pre (16).
+//   LAMBDA warp: the costate recurrence lam_t = A'lam_{t+1} + lx and g_t, and the fused multiply-adds of the Hessian terms with
+//       lam_{t+1} (hess_post).  Message B per step: the 7 Hessian terms the matrix half needs.
+//   GAIN warp:   G = R + B'PB, G^-1, y = G^-1 m, the eigenvalue test and the regularised inverse, sigma_t (riccati_gain).
+//   COLUMN warps j = 0..5: the matrix half cut along the columns of the sweep (riccati_col_sweep / riccati_col_finish): W = P A e_j,
+//       N(i<=j, j), Mx(:,j), (A'p)_j; after ONE exchange of Mx and the gain block through shared memory (named barrier of the GAIN and
+//       COLUMN warps) Y(:,j), K(:,j), P_t(i<=j, j), p_t(j); the new column goes back into the shared P (second barrier).
+// Messages travel through shared-memory rings with full/empty mbarriers (the producer's lane 0 arrives on "full" after a __syncwarp,
+// every consumer warp's lane 0 on "empty"), P / p / Mx / the gain block through plain shared arrays ordered by the two named barriers.
+// The sweep executes more instructions than k_backward_tma and holds 11 warps per tile, so it is used only while every tile has an SM
+// of its own (late survivor generations, single trajectories).  Every number is formed by the same expression as in the one-thread
+// sweep: bit-identical results (ACOC_NO_BWD_COLS for A/B; the host replay checks the decomposition,
+// tests/test_kernel_math_host.py::test_riccati_by_columns_bit_identical; every small-batch parity test on the GPU runs through it).
+// =================================================================================================================
+#ifndef ACOC_BC_NPRE
+#define ACOC_BC_NPRE 3
+#endif
+constexpr int BC_NPRE = ACOC_BC_NPRE;
+constexpr int BC_XA = 2 * BC_NPRE;  // slots of message ring A (a PRE warp owns the slots w, w + BC_NPRE)
+constexpr int BC_XB = 4;            // slots of message ring B
+constexpr int BC_WARPS = BC_NPRE + 2 + NS;
+constexpr int BC_THREADS = BC_WARPS * TILE;
+constexpr int BC_SYNC_THREADS = (1 + NS) * TILE;  // GAIN + COLUMN warps
+constexpr int BC_PB = 21 + NS;  // shared P (21 entries of the upper triangle) and p (6)
+constexpr int BC_GB = 8;        // gain block: gi00 gi01 gi11 k00 k01 k11 y0 y1
+constexpr int BC_MSGB = 7;      // h22 h23 h25 h33 h55 s2 s3
+template <bool EXACT>
+struct BcMsgA { static constexpr int N = 12 + NS + NI + (EXACT ? 16 : 0); };
+template <bool EXACT, typename F, typename XT>
+constexpr size_t backward_cols_smem()
+{
+    return (size_t)BC_NPRE * BWD_STAGES * BwdStage<F, XT>::BYTES +
+           ((size_t)BC_XA * BcMsgA<EXACT>::N + (size_t)BC_XB * BC_MSGB + BC_PB + 2 * NS + BC_GB) * TILE * sizeof(F) +
+           (BC_NPRE * BWD_STAGES + 2 * BC_XA + 2 * BC_XB) * sizeof(uint64_t);
+}
+// barrier of the GAIN and COLUMN warps (barrier 0 is __syncthreads)
+__device__ __forceinline__ void bc_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(BC_SYNC_THREADS) : "memory"); }
+
+template <typename F>
+struct BcShared {
+    F *msgA, *msgB, *PB, *MX, *GB;
+    uint64_t *afull, *aempty, *bfull, *bempty;
+};
+
+// ---- PRE warp w: steps k = w, w + BC_NPRE, ...
+template <bool EXACT, typename F, typename XT, int DG>
+__device__ __forceinline__ void bc_pre_role(const ProblemT<F>& P, int tile, int lane, bool live, int w, unsigned char* ring, uint64_t* bar_in,
+                                            const BcShared<F>& sh, const XT* __restrict__ X, const F* __restrict__ U)
+{
+    using St = BwdStage<F, XT>;
+    constexpr int NA = BcMsgA<EXACT>::N;
+    const int TT = P.TT, Np = P.Np, i = tile * TILE + lane, nsteps = TT - 1;
+    const int nmine = nsteps > w ? (nsteps - w + BC_NPRE - 1) / BC_NPRE : 0;
+    const RefMode<F> rm(P, i, live);
+    auto issue = [&](int j) {  // own step j <-> ring step k = w + j*BC_NPRE <-> time t = TT-2-k
+        const int t = TT - 2 - (w + j * BC_NPRE);
+        unsigned char* st = ring + (j % BWD_STAGES) * St::BYTES;
+        uint64_t* b = bar_in + (j % BWD_STAGES);
+        mbar_arrive_expect_tx(b, St::U_B + St::X_B + (rm.tiled ? St::U_B + St::XR_B : 0) + (rm.has_v ? (uint32_t)(TILE * sizeof(F)) : 0));
+        tma_load(st + St::U_O, U + tile_base(t, NI, Np, tile), St::U_B, b);
+        tma_load(st + St::X_O, X + tile_base(t, NS, Np, tile), St::X_B, b);
+        if (rm.tiled) {
+            tma_load(st + St::UR_O, P.uref + tile_base(t, NI, Np, tile), St::U_B, b);
+            tma_load(st + St::XR_O, P.xref + tile_base(t, NS, Np, tile), St::XR_B, b);
+        } else if (rm.has_v)
+            tma_load(st + St::XR_O, P.rp_v + tile_base(t, 1, Np, tile), (uint32_t)(TILE * sizeof(F)), b);
+    };
+    if (lane == 0)
+        for (int j = 0; j < BWD_STAGES && j < nmine; ++j) issue(j);
+    F x[NS], xr[NS], u[NI], ur[NI];
+    for (int j = 0; j < nmine; ++j) {
+        const int k = w + j * BC_NPRE, t = TT - 2 - k;
+        mbar_wait(bar_in + (j % BWD_STAGES), (uint32_t)((j / BWD_STAGES) & 1));
+        const unsigned char* st = ring + (j % BWD_STAGES) * St::BYTES;
+        XT xraw[NS];
+#pragma unroll
+        for (int c = 0; c < NS; ++c) xraw[c] = reinterpret_cast<const XT*>(st + St::X_O)[c * TILE + lane];
+#pragma unroll
+        for (int c = 0; c < NI; ++c) u[c] = reinterpret_cast<const F*>(st + St::U_O)[c * TILE + lane];
+        F vv = F(0.0);
+        if (rm.tiled) {
+#pragma unroll
+            for (int c = 0; c < NI; ++c) ur[c] = reinterpret_cast<const F*>(st + St::UR_O)[c * TILE + lane];
+#pragma unroll
+            for (int c = 0; c < NS; ++c) xr[c] = reinterpret_cast<const F*>(st + St::XR_O)[c * TILE + lane];
+        } else if (rm.has_v) vv = reinterpret_cast<const F*>(st + St::XR_O)[lane];
+        stage_release();
+        if (lane == 0 && j + BWD_STAGES < nmine) issue(j + BWD_STAGES);
+        const int s = k % BC_XA;
+        F* const m = sh.msgA + (size_t)s * NA * TILE + lane;
+        if (live) {
+            rm.fill(P, t, i, vv, xr, ur);
+            finish_x(P, t, i, xraw, x);
+            F dx[NS], du[NI], q[NS], r[NI];
+#pragma unroll
+            for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
+#pragma unroll
+            for (int c = 0; c < NI; ++c) du[c] = u[c] - ur[c];
+            wmul6(P.W.Q, (int)weights_diag<DG>(P.W), dx, q);   // lx = Q dx   (aircraft_simplified.py:63)
+            wmul2(P.W.R, (int)weights_diag<DG>(P.W), du, r);   // lu = R du   (:64)
+            const Trig<F> tg = make_trig(x);
+            const Lin<F> l = linearize(P.M, x, u, tg);
+            HessPre<F> a;
+            if (EXACT) a = hess_pre(P.M, x, tg, l);
+            if (k >= BC_XA) mbar_wait(sh.aempty + s, (uint32_t)((k / BC_XA - 1) & 1));
+            m[0 * TILE] = l.a02; m[1 * TILE] = l.a05; m[2 * TILE] = l.a12; m[3 * TILE] = l.a15; m[4 * TILE] = l.a22; m[5 * TILE] = l.a23;
+            m[6 * TILE] = l.a25; m[7 * TILE] = l.a52; m[8 * TILE] = l.a53; m[9 * TILE] = l.a55; m[10 * TILE] = l.b20; m[11 * TILE] = l.b50;
+#pragma unroll
+            for (int c = 0; c < NS; ++c) m[(12 + c) * TILE] = q[c];
+            m[18 * TILE] = r[0]; m[19 * TILE] = r[1];
+            if (EXACT) {
+                m[20 * TILE] = a.v22; m[21 * TILE] = a.v23; m[22 * TILE] = a.v33; m[23 * TILE] = a.v55; m[24 * TILE] = a.g22; m[25 * TILE] = a.g23;
+                m[26 * TILE] = a.g25; m[27 * TILE] = a.g33; m[28 * TILE] = a.g55; m[29 * TILE] = a.c0; m[30 * TILE] = a.c1; m[31 * TILE] = a.c2;
+                m[32 * TILE] = a.c3; m[33 * TILE] = a.e2; m[34 * TILE] = a.e3a; m[35 * TILE] = a.e3b;
+            }
+        } else if (k >= BC_XA) mbar_wait(sh.aempty + s, (uint32_t)((k / BC_XA - 1) & 1));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sh.afull + s);
+    }
+}
+
+// the linearisation out of a message-A slot
+template <typename F>
+__device__ __forceinline__ void bc_read_lin(const F* m, Lin<F>& l)
+{
+    l.a02 = m[0 * TILE]; l.a05 = m[1 * TILE]; l.a12 = m[2 * TILE]; l.a15 = m[3 * TILE]; l.a22 = m[4 * TILE]; l.a23 = m[5 * TILE];
+    l.a25 = m[6 * TILE]; l.a52 = m[7 * TILE]; l.a53 = m[8 * TILE]; l.a55 = m[9 * TILE]; l.b20 = m[10 * TILE]; l.b50 = m[11 * TILE];
+}
+
+// ---- LAMBDA warp
+template <bool EXACT, typename F, int DG>
+__device__ __forceinline__ void bc_lambda_role(const ProblemT<F>& P, int tile, int lane, bool live, const F* x, const F* xr, const BcShared<F>& sh,
+                                               F* __restrict__ KSG)
+{
+    constexpr int NA = BcMsgA<EXACT>::N;
+    const int TT = P.TT, Np = P.Np, nsteps = TT - 1;
+    F lam[NS];
+    if (live) {
+        F dxT[NS];
+#pragma unroll
+        for (int c = 0; c < NS; ++c) dxT[c] = x[c] - xr[c];
+        wmul6(P.W.QT, (int)weights_diag<DG>(P.W), dxT, lam);  // lam_{T-1} = QT dx (optcon.py:429-432)
+    }
+    for (int k = 0; k < nsteps; ++k) {
+        const int t = TT - 2 - k, s = k % BC_XA, sb = k % BC_XB;
+        mbar_wait(sh.afull + s, (uint32_t)((k / BC_XA) & 1));
+        const F* const m = sh.msgA + (size_t)s * NA * TILE + lane;
+        Lin<F> l;
+        HessPre<F> a;
+        F q[NS], r[NI];
+        if (live) {
+            bc_read_lin(m, l);
+#pragma unroll
+            for (int c = 0; c < NS; ++c) q[c] = m[(12 + c) * TILE];
+            r[0] = m[18 * TILE]; r[1] = m[19 * TILE];
+            if (EXACT) {
+                a.v22 = m[20 * TILE]; a.v23 = m[21 * TILE]; a.v33 = m[22 * TILE]; a.v55 = m[23 * TILE]; a.g22 = m[24 * TILE]; a.g23 = m[25 * TILE];
+                a.g25 = m[26 * TILE]; a.g33 = m[27 * TILE]; a.g55 = m[28 * TILE]; a.c0 = m[29 * TILE]; a.c1 = m[30 * TILE]; a.c2 = m[31 * TILE];
+                a.c3 = m[32 * TILE]; a.e2 = m[33 * TILE]; a.e3a = m[34 * TILE]; a.e3b = m[35 * TILE];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sh.aempty + s);
+        if (EXACT) {
+            if (k >= BC_XB) mbar_wait(sh.bempty + sb, (uint32_t)((k / BC_XB - 1) & 1));
+            if (live) {
+                const Hess<F> h = hess_post(a, lam);   // with lam_{t+1} (optcon.py:437)
+                F* const mb = sh.msgB + (size_t)sb * BC_MSGB * TILE + lane;
+                mb[0 * TILE] = h.h22; mb[1 * TILE] = h.h23; mb[2 * TILE] = h.h25; mb[3 * TILE] = h.h33; mb[4 * TILE] = h.h55;
+                mb[5 * TILE] = h.s2; mb[6 * TILE] = h.s3;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sh.bfull + sb);
+        }
+        if (live) {
+            F g[NI];
+            riccati_costate(P.M, l, q, r, lam, g);
+            F* out = KSG + tile_base(t, 16, Np, tile) + lane;
+            out[14 * TILE] = g[0]; out[15 * TILE] = g[1];
+        }
+    }
+}
+
+// ---- GAIN warp
+template <bool EXACT, typename F>
+__device__ __forceinline__ void bc_gain_role(const ProblemT<F>& P, int tile, int lane, bool live, const BcShared<F>& sh, F* __restrict__ KSG,
+                                             const int* __restrict__ status, int* __restrict__ n_reg)
+{
+    constexpr int NA = BcMsgA<EXACT>::N;
+    const int TT = P.TT, Np = P.Np, i = tile * TILE + lane, nsteps = TT - 1;
+    bc_bar(2);  // the COLUMN warps have stored the terminal P, p
+    int nreg = 0;
+    for (int k = 0; k < nsteps; ++k) {
+        const int t = TT - 2 - k, s = k % BC_XA;
+        mbar_wait(sh.afull + s, (uint32_t)((k / BC_XA) & 1));
+        const F* const m = sh.msgA + (size_t)s * NA * TILE + lane;
+        Lin<F> l;
+        F r[NI], Pm[21], p[NS];
+        if (live) {
+            l.b20 = m[10 * TILE]; l.b50 = m[11 * TILE];
+            r[0] = m[18 * TILE]; r[1] = m[19 * TILE];
+            Pm[sym(2, 2)] = sh.PB[sym(2, 2) * TILE + lane]; Pm[sym(2, 5)] = sh.PB[sym(2, 5) * TILE + lane]; Pm[sym(5, 5)] = sh.PB[sym(5, 5) * TILE + lane];
+            Pm[sym(2, 4)] = sh.PB[sym(2, 4) * TILE + lane]; Pm[sym(4, 5)] = sh.PB[sym(4, 5) * TILE + lane]; Pm[sym(4, 4)] = sh.PB[sym(4, 4) * TILE + lane];
+            p[2] = sh.PB[(21 + 2) * TILE + lane]; p[4] = sh.PB[(21 + 4) * TILE + lane]; p[5] = sh.PB[(21 + 5) * TILE + lane];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sh.aempty + s);
+        RicGain<F> gn;
+        gn.reg = 0;
+        if (live) {
+            gn = riccati_gain(P.M, P.W, l, r, Pm, p);
+            F* const gb = sh.GB + lane;
+            gb[0 * TILE] = gn.gi00; gb[1 * TILE] = gn.gi01; gb[2 * TILE] = gn.gi11; gb[3 * TILE] = gn.k00; gb[4 * TILE] = gn.k01;
+            gb[5 * TILE] = gn.k11; gb[6 * TILE] = gn.y0; gb[7 * TILE] = gn.y1;
+        }
+        bc_bar(1);  // Mx of every column and the gain block are in shared memory; every warp has read the old P, p
+        if (live) {
+            F* out = KSG + tile_base(t, 16, Np, tile) + lane;
+            out[12 * TILE] = -fma_(gn.k01, gn.m1, gn.k00 * gn.m0);
+            out[13 * TILE] = -fma_(gn.k11, gn.m1, gn.k01 * gn.m0);
+            nreg += gn.reg;
+        }
+        bc_bar(2);  // the new P, p are in shared memory; Mx and the gain block may be overwritten
+    }
+    if (live && nreg && status[i] == ST_ACTIVE) n_reg[i] += nreg;
+}
+
+// ---- COLUMN warp J
+template <bool EXACT, int DG, int J, typename F>
+__device__ __forceinline__ void bc_column_role(const ProblemT<F>& P, int tile, int lane, bool live, const F* x, const F* xr, const BcShared<F>& sh,
+                                               F* __restrict__ KSG)
+{
+    constexpr int NA = BcMsgA<EXACT>::N;
+    constexpr bool NEEDS_H = EXACT && (J == 2 || J == 3 || J == 5);
+    const int TT = P.TT, Np = P.Np, nsteps = TT - 1;
+    F* const PB = sh.PB;
+    if (live) {  // terminal condition P_{T-1} = QT, p_{T-1} = lam_{T-1}/2 (optcon.py:688-690, :716): every warp forms it, column J stores its part
+        F Pm[21], p[NS], lamT[NS];
+        backward_terminal<DG>(P.W, x, xr, Pm, p, lamT);
+#pragma unroll
+        for (int a = 0; a <= J; ++a) PB[sym(a, J) * TILE + lane] = Pm[sym(a, J)];
+        PB[(21 + J) * TILE + lane] = p[J];
+    }
+    bc_bar(2);
+    for (int k = 0; k < nsteps; ++k) {
+        const int t = TT - 2 - k, s = k % BC_XA, sb = k % BC_XB;
+        mbar_wait(sh.afull + s, (uint32_t)((k / BC_XA) & 1));
+        const F* const m = sh.msgA + (size_t)s * NA * TILE + lane;
+        Lin<F> l;
+        Hess<F> h;
+        F qJ = F(0.0), Pm[21], p[NS];
+        if (live) {
+            bc_read_lin(m, l);
+            qJ = m[(12 + J) * TILE];
+#pragma unroll
+            for (int e = 0; e < 21; ++e) Pm[e] = PB[e * TILE + lane];   // (entries this column does not touch are dead loads)
+#pragma unroll
+            for (int c = 0; c < NS; ++c) p[c] = PB[(21 + c) * TILE + lane];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sh.aempty + s);
+        if (NEEDS_H) {   // ring B is consumed by the columns 2, 3, 5 only
+            mbar_wait(sh.bfull + sb, (uint32_t)((k / BC_XB) & 1));
+            if (live) {
+                const F* const mb = sh.msgB + (size_t)sb * BC_MSGB * TILE + lane;
+                h.h22 = mb[0 * TILE]; h.h23 = mb[1 * TILE]; h.h25 = mb[2 * TILE]; h.h33 = mb[3 * TILE]; h.h55 = mb[4 * TILE];
+                h.s2 = mb[5 * TILE]; h.s3 = mb[6 * TILE];
+                h.h35 = -h.h33; h.s5 = -h.s3;  // (as hess_contract forms them)
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sh.bempty + sb);
+        }
+        F PnJ[NS], mx0 = F(0.0), mx1 = F(0.0), atp = F(0.0);
+        if (live) {
+            riccati_col_sweep<EXACT, J, F>(P.M, l, h, Pm, p, PnJ, mx0, mx1, atp);
+            sh.MX[J * TILE + lane] = mx0; sh.MX[(NS + J) * TILE + lane] = mx1;
+        }
+        bc_bar(1);  // Mx of every column and the gain block are in shared memory; every warp has read the old P, p
+        if (live) {
+            RicGain<F> gn;
+            const F* const gb = sh.GB + lane;
+            gn.gi00 = gb[0 * TILE]; gn.gi01 = gb[1 * TILE]; gn.gi11 = gb[2 * TILE]; gn.k00 = gb[3 * TILE]; gn.k01 = gb[4 * TILE];
+            gn.k11 = gb[5 * TILE]; gn.y0 = gb[6 * TILE]; gn.y1 = gb[7 * TILE];
+            F Mx0[NS], Mx1[NS], PJ[NS], pJ, K0, K1;
+#pragma unroll
+            for (int a = 0; a < J; ++a) { Mx0[a] = sh.MX[a * TILE + lane]; Mx1[a] = sh.MX[(NS + a) * TILE + lane]; }
+            Mx0[J] = mx0; Mx1[J] = mx1;
+            riccati_col_finish<EXACT, DG, J, F>(P.W, h, qJ, gn, PnJ, Mx0, Mx1, atp, PJ, pJ, K0, K1);
+#pragma unroll
+            for (int a = 0; a <= J; ++a) PB[sym(a, J) * TILE + lane] = PJ[a];
+            PB[(21 + J) * TILE + lane] = pJ;
+            F* out = KSG + tile_base(t, 16, Np, tile) + lane;
+            out[J * TILE] = K0; out[(NS + J) * TILE] = K1;
+        }
+        bc_bar(2);  // the new P, p are in shared memory; Mx and the gain block may be overwritten
+    }
+}
+
+template <bool EXACT, typename F, typename XT, int DG>
+__global__ void __launch_bounds__(BC_THREADS, 1) k_backward_cols(ProblemT<F> P, TileList L, const XT* __restrict__ X, const F* __restrict__ U,
+                                                                 F* __restrict__ KSG, const int* __restrict__ status, int* __restrict__ n_reg)
+{
+    using St = BwdStage<F, XT>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    const int tile = warp_tile(L, blockIdx.x, P.Np);
+    if (tile < 0) return;  // (uniform over the CTA)
+    BcShared<F> sh;
+    unsigned char* const rings = smem;
+    sh.msgA = reinterpret_cast<F*>(smem + (size_t)BC_NPRE * BWD_STAGES * St::BYTES);
+    sh.msgB = sh.msgA + (size_t)BC_XA * BcMsgA<EXACT>::N * TILE;
+    sh.PB = sh.msgB + (size_t)BC_XB * BC_MSGB * TILE;
+    sh.MX = sh.PB + (size_t)BC_PB * TILE;
+    sh.GB = sh.MX + (size_t)2 * NS * TILE;
+    uint64_t* const bar_in = reinterpret_cast<uint64_t*>(sh.GB + (size_t)BC_GB * TILE);
+    sh.afull = bar_in + BC_NPRE * BWD_STAGES;
+    sh.aempty = sh.afull + BC_XA;
+    sh.bfull = sh.aempty + BC_XA;
+    sh.bempty = sh.bfull + BC_XB;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < BC_NPRE * BWD_STAGES; ++s) mbar_init(bar_in + s, 1);
+        for (int s = 0; s < BC_XA; ++s) { mbar_init(sh.afull + s, 1); mbar_init(sh.aempty + s, 2 + NS); }  // consumers: LAMBDA, GAIN, 6 COLUMN
+        for (int s = 0; s < BC_XB; ++s) { mbar_init(sh.bfull + s, 1); mbar_init(sh.bempty + s, 3); }       // consumers: COLUMN 2, 3, 5
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int i = tile * TILE + lane;
+    const bool live = i < P.N;
+    F x[NS], xr[NS];
+    if (live && role >= BC_NPRE && role != BC_NPRE + 1) {  // terminal condition: LAMBDA and the COLUMN warps need x_{T-1} - xref_{T-1}
+        load_xref(P, P.TT - 1, i, xr);
+        load_x(P, X, P.TT - 1, i, x);
+    }
+    if (role < BC_NPRE) {
+        bc_pre_role<EXACT, F, XT, DG>(P, tile, lane, live, role, rings + (size_t)role * BWD_STAGES * St::BYTES, bar_in + role * BWD_STAGES, sh, X, U);
+        return;
+    }
+    switch (role - BC_NPRE) {
+        case 0: bc_lambda_role<EXACT, F, DG>(P, tile, lane, live, x, xr, sh, KSG); break;
+        case 1: bc_gain_role<EXACT, F>(P, tile, lane, live, sh, KSG, status, n_reg); break;
+        case 2: bc_column_role<EXACT, DG, 0, F>(P, tile, lane, live, x, xr, sh, KSG); break;
+        case 3: bc_column_role<EXACT, DG, 1, F>(P, tile, lane, live, x, xr, sh, KSG); break;
+        case 4: bc_column_role<EXACT, DG, 2, F>(P, tile, lane, live, x, xr, sh, KSG); break;
+        case 5: bc_column_role<EXACT, DG, 3, F>(P, tile, lane, live, x, xr, sh, KSG); break;
+        case 6: bc_column_role<EXACT, DG, 4, F>(P, tile, lane, live, x, xr, sh, KSG); break;
+        default: bc_column_role<EXACT, DG, 5, F>(P, tile, lane, live, x, xr, sh, KSG); break;
+    }
 }
 
 // =================================================================================================================

@@ -182,6 +182,51 @@ int newton_impl(const NewtonArgs& a)
 }
 }  // namespace
 
+// riccati_matrix() against its decomposition by columns (k_backward_cols), driven along the backward sweep of a real trajectory so that
+// P, p, the linearisation and the Hessian terms have their real magnitudes: both variants carry their own (P, p) and every K, sigma,
+// P, p is compared bit for bit.  scale_R < 1 shrinks R so that the +0.5 I branch is taken too.  Returns the number of differing
+// numbers (0 = identical); *n_reg_out = steps that took the regularised branch.
+template <bool EXACT, int DG>
+static long cols_check(const Model& M, const Weights& W, int TT, const double* xx, const double* uu, const double* xr_, const double* ur_, int* n_reg_out)
+{
+    double Pa[21], pa[NS], Pb[21], pb[NS], lam[NS], x[NS], xr[NS], u[NI], ur[NI];
+    for (int c = 0; c < NS; ++c) { x[c] = xx[(size_t)c * TT + TT - 1]; xr[c] = xr_[(size_t)c * TT + TT - 1]; }
+    backward_terminal<DG>(W, x, xr, Pa, pa, lam);
+    memcpy(Pb, Pa, sizeof(Pa)); memcpy(pb, pa, sizeof(pa));
+    long bad = 0;
+    int nreg = 0;
+    for (int t = TT - 2; t >= 0; --t) {
+        for (int c = 0; c < NS; ++c) { x[c] = xx[(size_t)c * TT + t]; xr[c] = xr_[(size_t)c * TT + t]; }
+        for (int c = 0; c < NI; ++c) { u[c] = uu[(size_t)c * TT + t]; ur[c] = ur_[(size_t)c * TT + t]; }
+        double dx[NS], du[NI], q[NS], r[NI], g[NI];
+        for (int c = 0; c < NS; ++c) dx[c] = x[c] - xr[c];
+        for (int c = 0; c < NI; ++c) du[c] = u[c] - ur[c];
+        wmul6(W.Q, (int)weights_diag<DG>(W), dx, q);
+        wmul2(W.R, (int)weights_diag<DG>(W), du, r);
+        const Trig<double> tg = make_trig(x);
+        const Lin<double> l = linearize(M, x, u, tg);
+        Hess<double> h = Hess<double>();
+        if (EXACT) h = hess_contract(M, x, u, tg, l, lam);
+        double Ka[12], sa[2], Kb[12], sb[2];
+        const int ra = riccati_matrix<EXACT, DG, double>(M, W, l, h, q, r, Pa, pa, Ka, sa);
+        Hess<double> h2 = Hess<double>();
+        if (EXACT) {   // the kernel's warps form the Hessian terms in two pieces
+            h2 = hess_post(hess_pre(M, x, tg, l), lam);
+            bad += memcmp(&h, &h2, sizeof(h)) != 0;
+        }
+        const int rb = riccati_matrix_by_columns<EXACT, DG, double>(M, W, l, h2, q, r, Pb, pb, Kb, sb);
+        riccati_costate(M, l, q, r, lam, g);
+        nreg += ra;
+        bad += ra != rb;
+        bad += memcmp(Ka, Kb, sizeof(Ka)) != 0;
+        bad += memcmp(sa, sb, sizeof(sa)) != 0;
+        bad += memcmp(Pa, Pb, sizeof(Pa)) != 0;
+        bad += memcmp(pa, pb, sizeof(pa)) != 0;
+    }
+    if (n_reg_out) *n_reg_out = nreg;
+    return bad;
+}
+
 extern "C" {
 
 void emul_step_batch(int n, const double* params, int state_f64, const double* x, const double* u, const double* lam,
@@ -202,6 +247,16 @@ void emul_cost_batch(int n, const double* Q, const double* R, const double* QT, 
     for (int s = 0; s < n; ++s)
         cost_sample(W, x + (size_t)s * 6, u + (size_t)s * 2, xr + (size_t)s * 6, ur + (size_t)s * 2, ll + s, lx + (size_t)s * 6, lu + (size_t)s * 2,
                     llT + s, lTx + (size_t)s * 6);
+}
+
+long emul_riccati_cols_check(int TT, const double* params, const double* Q, const double* R, const double* QT, const double* xx, const double* uu,
+                             const double* xx_ref, const double* uu_ref, int exact, int* n_reg_out)
+{
+    const Model M = make_model(params);
+    Weights W;
+    fill_weights(&W, Q, R, QT);
+    if (W.diag) return exact ? cols_check<true, 1>(M, W, TT, xx, uu, xx_ref, uu_ref, n_reg_out) : cols_check<false, 1>(M, W, TT, xx, uu, xx_ref, uu_ref, n_reg_out);
+    return exact ? cols_check<true, 0>(M, W, TT, xx, uu, xx_ref, uu_ref, n_reg_out) : cols_check<false, 0>(M, W, TT, xx, uu, xx_ref, uu_ref, n_reg_out);
 }
 
 void emul_ltv_lqr(int TT, const double* A, const double* B, const double* Q, const double* R, const double* S, const double* Qf,

@@ -118,3 +118,16 @@ def init_guess(xx_ref, params=DEFAULT_PARAMS, state_f64=False, kp=5.0, kt=2.5):
     xx, uu = np.zeros((N, 6, TT)), np.zeros((N, 2, TT))
     lib().emul_init_guess(C.c_int(N), C.c_int(TT), _p(_c(params)), C.c_int(int(state_f64)), _p(xr), C.c_double(kp), C.c_double(kt), _p(xx), _p(uu))
     return xx, uu
+
+
+def riccati_cols_check(xx, uu, xx_ref, uu_ref, Q, R, QT, exact=True, params=DEFAULT_PARAMS):
+    """riccati_matrix() vs its decomposition by columns along the backward sweep of one trajectory (6,TT)/(2,TT).
+    Returns (number of differing results, steps that took the +0.5 I branch)."""
+    xx = _c(xx)
+    TT = xx.shape[1]
+    nreg = C.c_int(0)
+    f = lib().emul_riccati_cols_check
+    f.restype = C.c_long
+    bad = f(C.c_int(TT), _p(_c(params)), _p(_c(Q)), _p(_c(R)), _p(_c(QT)), _p(xx), _p(_c(uu)), _p(_c(xx_ref)), _p(_c(uu_ref)),
+            C.c_int(int(exact)), C.byref(nreg))
+    return int(bad), nreg.value

@@ -182,3 +182,22 @@ def test_gradient_kernels_reproduce_reference(emul, name, lazy):
     assert np.max(np.abs(-h["descent"][0, :k] - g["descent"]) / np.abs(g["descent"])) < 1e-9
     assert relerr(g["xx_last"], h["xx_last"][0]) < 1e-9 and relerr(g["uu_last"], h["uu_last"][0]) < 1e-9
     assert relerr(g["xx_star"], h["xx_star"][0]) < 1e-9 and relerr(g["uu_star"], h["uu_star"][0]) < 1e-9
+
+
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("weights", ["diag", "dense", "tiny_R"])
+def test_riccati_by_columns_bit_identical(emul, exact, weights):
+    """k_backward_cols runs the matrix half of the Riccati step as one warp per column; the column pieces must reproduce
+    riccati_matrix() bit for bit (K, sigma, P, p of every step of a real backward sweep), +0.5 I branch included."""
+    d = golden("newton_acro_f32.npz")
+    Q, R, QT = d["Q"].copy(), d["R"].copy(), d["QT"].copy()
+    if weights == "dense":
+        E = np.random.default_rng(5).normal(size=(6, 6)) * 1e-4
+        Q, QT, R = Q + E @ E.T, QT + 3 * (E @ E.T), R + 1e-7 * np.array([[1.0, 0.3], [0.3, 2.0]])
+    if weights == "tiny_R":   # G = R + B'PB loses positive definiteness somewhere along the sweep -> the regularised gain is exercised
+        R = -np.abs(R) * 50.0
+    for xx, uu in ((d["xx_init"], d["uu_init"]), (d["xx_star"], d["uu_star"])):
+        bad, nreg = emul.riccati_cols_check(xx, uu, d["xx_ref"], d["uu_ref"], Q, R, QT, exact=exact)
+        assert bad == 0
+        if weights == "tiny_R":
+            assert nreg > 0
