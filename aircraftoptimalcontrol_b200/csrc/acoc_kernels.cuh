@@ -312,49 +312,63 @@ ACOC_HD int riccati_matrix(const ModelT<F>& M, const WeightsT<F>& W, const Lin<F
 
 // ---- the matrix half BY COLUMNS (k_backward_cols: one warp per column of P, small batches) -----------------------------
 // riccati_matrix() cut along the columns j of the sweep.  Everything column j produces -- W = P A e_j, N(i,j) = (A'W)_i for i <= j,
-// Mx(:,j), (A'p)_j, then Y(:,j), K(:,j), P_t(i,j) for i <= j and p_t(j) -- needs, beside the old P, p and the linearisation, only the
-// 2x2 gain block (computed redundantly by every column: riccati_gain) and Mx(:,i) of the columns i < j (exchanged once per step).
+// Mx(:,j), then Y(:,j) and P_t(i,j) for i <= j -- needs, beside the old P and the linearisation, only the inverse of the 2x2 block G
+// (riccati_gain, its own warp) and Mx(:,i) of the columns i < j (exchanged once per step); the affine term p and the outputs K, sigma
+// are separate pieces as well.
 // Every number is formed by the same expression as in riccati_matrix(), so the two are bit-identical (tests/test_kernel_math_host.py
 // replays both on the host).
 template <typename F>
 struct RicGain {
+    F G00, G01, G11;     // G = R + B'PB
     F gi00, gi01, gi11;  // G^-1 (the Riccati update always uses the plain inverse, optcon.py:728)
     F k00, k01, k11;     // the inverse the GAIN uses: G^-1, or (G + 0.5 I)^-1 when G has a non-positive eigenvalue (optcon.py:743-749)
     F m0, m1, y0, y1;    // m = B'p + r/2, y = G^-1 m
     int reg;
 };
 
+// what the recurrence needs: G, m, G^-1, y
+template <typename F>
+ACOC_HD void riccati_gain_core(const ModelT<F>& M, const WeightsT<F>& W, const Lin<F>& l, const F* r, const F* Pm, const F* p, RicGain<F>& o)
+{
+    const F b41 = M.b41;
+    const F P22 = Pm[sym(2, 2)], P25 = Pm[sym(2, 5)], P55 = Pm[sym(5, 5)], P24 = Pm[sym(2, 4)], P45 = Pm[sym(4, 5)], P44 = Pm[sym(4, 4)];
+    const F pb2 = fma_(l.b50, P25, l.b20 * P22), pb5 = fma_(l.b50, P55, l.b20 * P25);
+    o.G00 = fma_(l.b50, pb5, fma_(l.b20, pb2, W.R[0]));
+    o.G01 = fma_(b41, fma_(l.b50, P45, l.b20 * P24), W.R[1]);
+    o.G11 = fma_(b41 * b41, P44, W.R[3]);
+    o.m0 = fma_(l.b50, p[5], fma_(l.b20, p[2], F(0.5) * r[0]));
+    o.m1 = fma_(b41, p[4], F(0.5) * r[1]);
+    const F det = fma_(o.G00, o.G11, -(o.G01 * o.G01));
+    const F idet = F(1.0) / det;
+    o.gi00 = o.G11 * idet; o.gi01 = -o.G01 * idet; o.gi11 = o.G00 * idet;
+    o.y0 = fma_(o.gi01, o.m1, o.gi00 * o.m0); o.y1 = fma_(o.gi11, o.m1, o.gi01 * o.m0);
+}
+// what only the outputs K, sigma need: the positive-definiteness test on G (eigenvalues of the symmetric 2x2) and the inverse the gain uses
+template <typename F>
+ACOC_HD void riccati_gain_test(RicGain<F>& o)
+{
+    const F hd = F(0.5) * (o.G00 - o.G11), mid = F(0.5) * (o.G00 + o.G11);
+    const F rad = sqrt_(fma_(hd, hd, o.G01 * o.G01));
+    if (mid - rad > F(0.0)) { o.reg = 0; o.k00 = o.gi00; o.k01 = o.gi01; o.k11 = o.gi11; }
+    else {  // regularised gain MM = G + 0.5 I; the Riccati update still uses the plain G^-1
+        o.reg = 1;
+        const F H00 = o.G00 + F(0.5), H11 = o.G11 + F(0.5);
+        const F id2 = F(1.0) / fma_(H00, H11, -(o.G01 * o.G01));
+        o.k00 = H11 * id2; o.k01 = -o.G01 * id2; o.k11 = H00 * id2;
+    }
+}
 template <typename F>
 ACOC_HD RicGain<F> riccati_gain(const ModelT<F>& M, const WeightsT<F>& W, const Lin<F>& l, const F* r, const F* Pm, const F* p)
 {
     RicGain<F> o;
-    const F b41 = M.b41;
-    const F P22 = Pm[sym(2, 2)], P25 = Pm[sym(2, 5)], P55 = Pm[sym(5, 5)], P24 = Pm[sym(2, 4)], P45 = Pm[sym(4, 5)], P44 = Pm[sym(4, 4)];
-    const F pb2 = fma_(l.b50, P25, l.b20 * P22), pb5 = fma_(l.b50, P55, l.b20 * P25);
-    const F G00 = fma_(l.b50, pb5, fma_(l.b20, pb2, W.R[0]));
-    const F G01 = fma_(b41, fma_(l.b50, P45, l.b20 * P24), W.R[1]);
-    const F G11 = fma_(b41 * b41, P44, W.R[3]);
-    o.m0 = fma_(l.b50, p[5], fma_(l.b20, p[2], F(0.5) * r[0]));
-    o.m1 = fma_(b41, p[4], F(0.5) * r[1]);
-    const F det = fma_(G00, G11, -(G01 * G01));
-    const F idet = F(1.0) / det;
-    o.gi00 = G11 * idet; o.gi01 = -G01 * idet; o.gi11 = G00 * idet;
-    o.y0 = fma_(o.gi01, o.m1, o.gi00 * o.m0); o.y1 = fma_(o.gi11, o.m1, o.gi01 * o.m0);
-    const F hd = F(0.5) * (G00 - G11), mid = F(0.5) * (G00 + G11);
-    const F rad = sqrt_(fma_(hd, hd, G01 * G01));
-    if (mid - rad > F(0.0)) { o.reg = 0; o.k00 = o.gi00; o.k01 = o.gi01; o.k11 = o.gi11; }
-    else {
-        o.reg = 1;
-        const F H00 = G00 + F(0.5), H11 = G11 + F(0.5);
-        const F id2 = F(1.0) / fma_(H00, H11, -(G01 * G01));
-        o.k00 = H11 * id2; o.k01 = -G01 * id2; o.k11 = H00 * id2;
-    }
+    riccati_gain_core(M, W, l, r, Pm, p, o);
+    riccati_gain_test(o);
     return o;
 }
 
-// first half of column J: PnJ[i] = N(i,J) for i <= J, Mx(:,J), (A'p)_J
+// first half of column J: PnJ[i] = N(i,J) for i <= J, Mx(:,J)
 template <bool EXACT, int J, typename F>
-ACOC_HD void riccati_col_sweep(const ModelT<F>& M, const Lin<F>& l, const Hess<F>& h, const F* Pm, const F* p, F* PnJ, F& mx0, F& mx1, F& atp)
+ACOC_HD void riccati_col_sweep(const ModelT<F>& M, const Lin<F>& l, const Hess<F>& h, const F* Pm, F* PnJ, F& mx0, F& mx1)
 {
     F Wc[NS];
 #pragma unroll
@@ -373,18 +387,14 @@ ACOC_HD void riccati_col_sweep(const ModelT<F>& M, const Lin<F>& l, const Hess<F
         if (J == 3) mx0 += h.s3;
         if (J == 5) mx0 += h.s5;
     }
-    atp = acol(l, M.dt, p, J);
 }
 
-// second half of column J: Mx0[i], Mx1[i] for i <= J (own column included) -> K(:,J), P_t(i,J) for i <= J, p_t(J)
+// second half of column J: Mx0[i], Mx1[i] for i <= J (own column included) and G^-1 -> P_t(i,J) for i <= J
 template <bool EXACT, int DG, int J, typename F>
-ACOC_HD void riccati_col_finish(const WeightsT<F>& W, const Hess<F>& h, F qJ, const RicGain<F>& gn, const F* PnJ, const F* Mx0, const F* Mx1,
-                                F atp, F* PJ, F& pJ, F& K0, F& K1)
+ACOC_HD void riccati_col_finish(const WeightsT<F>& W, const Hess<F>& h, F gi00, F gi01, F gi11, const F* PnJ, const F* Mx0, const F* Mx1, F* PJ)
 {
-    const F Y0 = fma_(gn.gi01, Mx1[J], gn.gi00 * Mx0[J]);
-    const F Y1 = fma_(gn.gi11, Mx1[J], gn.gi01 * Mx0[J]);
-    K0 = -fma_(gn.k01, Mx1[J], gn.k00 * Mx0[J]);
-    K1 = -fma_(gn.k11, Mx1[J], gn.k01 * Mx0[J]);
+    const F Y0 = fma_(gi01, Mx1[J], gi00 * Mx0[J]);
+    const F Y1 = fma_(gi11, Mx1[J], gi01 * Mx0[J]);
 #pragma unroll
     for (int i = 0; i <= J; ++i) {
         const F corr = fma_(Mx1[i], Y1, Mx0[i] * Y0);
@@ -394,7 +404,6 @@ ACOC_HD void riccati_col_finish(const WeightsT<F>& W, const Hess<F>& h, F qJ, co
             PJ[i] = (PnJ[i] + qij) - corr;
         }
     }
-    pJ = fma_(F(0.5), qJ, atp) - fma_(Mx1[J], gn.y1, Mx0[J] * gn.y0);
     if (EXACT) {  // Q_t = lxx + fxx (optcon.py:444)
         if (J == 2) PJ[2] += h.h22;
         if (J == 3) { PJ[2] += h.h23; PJ[3] += h.h33; }
@@ -402,23 +411,49 @@ ACOC_HD void riccati_col_finish(const WeightsT<F>& W, const Hess<F>& h, F qJ, co
     }
 }
 
-// riccati_matrix() recomposed from the column pieces (host replay of k_backward_cols' arithmetic; the kernel runs the six columns in
-// six warps and exchanges Mx and the new P through shared memory)
-template <bool EXACT, int DG, int J, typename F>
-ACOC_HD void riccati_cols_a_(const ModelT<F>& M, const Lin<F>& l, const Hess<F>& h, const F* Pm, const F* p, F (*Pn)[NS], F* Mx0, F* Mx1, F* Atp)
+// the affine term: A'p before the exchange, p_t after it (one of the light column warps carries it)
+template <typename F>
+ACOC_HD void riccati_p_sweep(const ModelT<F>& M, const Lin<F>& l, const F* p, F* Atp)
 {
-    riccati_col_sweep<EXACT, J, F>(M, l, h, Pm, p, Pn[J], Mx0[J], Mx1[J], Atp[J]);
-    if constexpr (J + 1 < NS) riccati_cols_a_<EXACT, DG, J + 1, F>(M, l, h, Pm, p, Pn, Mx0, Mx1, Atp);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) Atp[i] = acol(l, M.dt, p, i);
+}
+template <typename F>
+ACOC_HD void riccati_p_finish(const F* q, const F* Atp, const F* Mx0, const F* Mx1, F y0, F y1, F* p)
+{
+#pragma unroll
+    for (int i = 0; i < NS; ++i) p[i] = fma_(F(0.5), q[i], Atp[i]) - fma_(Mx1[i], y1, Mx0[i] * y0);
+}
+
+// the outputs of the step from the gain block and Mx (the GAIN warp forms them after the exchange, beside the columns' second half)
+template <typename F>
+ACOC_HD void riccati_gain_out(const RicGain<F>& gn, const F* Mx0, const F* Mx1, F* K, F* sig)
+{
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        K[j] = -fma_(gn.k01, Mx1[j], gn.k00 * Mx0[j]);
+        K[NS + j] = -fma_(gn.k11, Mx1[j], gn.k01 * Mx0[j]);
+    }
+    sig[0] = -fma_(gn.k01, gn.m1, gn.k00 * gn.m0);
+    sig[1] = -fma_(gn.k11, gn.m1, gn.k01 * gn.m0);
+}
+
+// riccati_matrix() recomposed from these pieces (host replay of k_backward_cols' arithmetic; the kernel runs them in eight warps and
+// exchanges Mx, the gain block and the new P, p through shared memory)
+template <bool EXACT, int DG, int J, typename F>
+ACOC_HD void riccati_cols_a_(const ModelT<F>& M, const Lin<F>& l, const Hess<F>& h, const F* Pm, F (*Pn)[NS], F* Mx0, F* Mx1)
+{
+    riccati_col_sweep<EXACT, J, F>(M, l, h, Pm, Pn[J], Mx0[J], Mx1[J]);
+    if constexpr (J + 1 < NS) riccati_cols_a_<EXACT, DG, J + 1, F>(M, l, h, Pm, Pn, Mx0, Mx1);
 }
 template <bool EXACT, int DG, int J, typename F>
-ACOC_HD void riccati_cols_b_(const WeightsT<F>& W, const Hess<F>& h, const F* q, const RicGain<F>& gn, F (*Pn)[NS], const F* Mx0, const F* Mx1,
-                             const F* Atp, F* Pm, F* p, F* K)
+ACOC_HD void riccati_cols_b_(const WeightsT<F>& W, const Hess<F>& h, const RicGain<F>& gn, F (*Pn)[NS], const F* Mx0, const F* Mx1, F* Pm)
 {
     F PJ[NS];
-    riccati_col_finish<EXACT, DG, J, F>(W, h, q[J], gn, Pn[J], Mx0, Mx1, Atp[J], PJ, p[J], K[J], K[NS + J]);
+    riccati_col_finish<EXACT, DG, J, F>(W, h, gn.gi00, gn.gi01, gn.gi11, Pn[J], Mx0, Mx1, PJ);
 #pragma unroll
     for (int i = 0; i <= J; ++i) Pm[sym(i, J)] = PJ[i];
-    if constexpr (J + 1 < NS) riccati_cols_b_<EXACT, DG, J + 1, F>(W, h, q, gn, Pn, Mx0, Mx1, Atp, Pm, p, K);
+    if constexpr (J + 1 < NS) riccati_cols_b_<EXACT, DG, J + 1, F>(W, h, gn, Pn, Mx0, Mx1, Pm);
 }
 template <bool EXACT, int DG = -1, typename F>
 ACOC_HD int riccati_matrix_by_columns(const ModelT<F>& M, const WeightsT<F>& W, const Lin<F>& l, const Hess<F>& h, const F* q, const F* r,
@@ -426,10 +461,11 @@ ACOC_HD int riccati_matrix_by_columns(const ModelT<F>& M, const WeightsT<F>& W, 
 {
     const RicGain<F> gn = riccati_gain(M, W, l, r, Pm, p);
     F Pn[NS][NS], Mx0[NS], Mx1[NS], Atp[NS];
-    riccati_cols_a_<EXACT, DG, 0, F>(M, l, h, Pm, p, Pn, Mx0, Mx1, Atp);            // every column reads the OLD P, p
-    riccati_cols_b_<EXACT, DG, 0, F>(W, h, q, gn, Pn, Mx0, Mx1, Atp, Pm, p, K);    // ... and only then are they overwritten
-    sig[0] = -fma_(gn.k01, gn.m1, gn.k00 * gn.m0);
-    sig[1] = -fma_(gn.k11, gn.m1, gn.k01 * gn.m0);
+    riccati_cols_a_<EXACT, DG, 0, F>(M, l, h, Pm, Pn, Mx0, Mx1);   // every column reads the OLD P
+    riccati_p_sweep(M, l, p, Atp);
+    riccati_cols_b_<EXACT, DG, 0, F>(W, h, gn, Pn, Mx0, Mx1, Pm);  // ... and only then is it overwritten
+    riccati_p_finish(q, Atp, Mx0, Mx1, gn.y0, gn.y1, p);
+    riccati_gain_out(gn, Mx0, Mx1, K, sig);
     return gn.reg;
 }
 

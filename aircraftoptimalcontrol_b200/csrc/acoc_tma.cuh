@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(64, 4) k_backward_split(ProblemT<F> P, TileLis
 }
 
 // =================================================================================================================
-// fused backward sweep of SMALL batches as a pipeline of warp roles: one CTA = one tile of 32 instances = 5 + NS warps.
+// fused backward sweep of SMALL batches as a pipeline of warp roles: one CTA = one tile of 32 instances = BC_NPRE + 3 + NS = 12 warps.
 // A lone warp pays ~4-6 cycles per instruction of a backward step whatever it does (dependent FP64 chains, in-order issue), so what a
 // latency-bound batch pays per step is the instruction count of the LONGEST role.  The step is cut along its true recurrences:
 //   PRE warps (BC_NPRE of them; warp w takes the steps k = w mod BC_NPRE -- nothing here depends on another step): own TMA ring of
@@ -721,13 +721,16 @@ __global__ void __launch_bounds__(64, 4) k_backward_split(ProblemT<F> P, TileLis
 //       Message A per step: linearisation (12), lx (6), lu (2), hess_pre (16).
 //   LAMBDA warp: the costate recurrence lam_t = A'lam_{t+1} + lx and g_t, and the fused multiply-adds of the Hessian terms with
 //       lam_{t+1} (hess_post).  Message B per step: the 7 Hessian terms the matrix half needs.
-//   GAIN warp:   G = R + B'PB, G^-1, y = G^-1 m, the eigenvalue test and the regularised inverse, sigma_t (riccati_gain).
+//   GAIN warp:   G = R + B'PB, m, G^-1, y = G^-1 m (riccati_gain_core) -- what the recurrence needs of the 2x2 block.
+//   OUT warp:    the outputs K_t, sigma_t: eigenvalue test on G, regularised inverse (riccati_gain_test), -(MM^-1) Mx (riccati_gain_out).
+//       Nothing depends on it, so it works on step k from double-buffered copies of Mx and the gain block while the others run step k+1.
 //   COLUMN warps j = 0..5: the matrix half cut along the columns of the sweep (riccati_col_sweep / riccati_col_finish): W = P A e_j,
-//       N(i<=j, j), Mx(:,j), (A'p)_j; after ONE exchange of Mx and the gain block through shared memory (named barrier of the GAIN and
-//       COLUMN warps) Y(:,j), K(:,j), P_t(i<=j, j), p_t(j); the new column goes back into the shared P (second barrier).
+//       N(i<=j, j), Mx(:,j); after ONE exchange of Mx and G^-1 through shared memory (named barrier of the GAIN, OUT and COLUMN warps)
+//       Y(:,j) and P_t(i<=j, j); the new column goes back into the shared P (second barrier).  Column 0, the lightest, also carries
+//       the affine term (A'p before the exchange, p_t after it).
 // Messages travel through shared-memory rings with full/empty mbarriers (the producer's lane 0 arrives on "full" after a __syncwarp,
 // every consumer warp's lane 0 on "empty"), P / p / Mx / the gain block through plain shared arrays ordered by the two named barriers.
-// The sweep executes more instructions than k_backward_tma and holds 11 warps per tile, so it is used only while every tile has an SM
+// The sweep executes more instructions than k_backward_tma and holds 12 warps per tile, so it is used only while every tile has an SM
 // of its own (late survivor generations, single trajectories).  Every number is formed by the same expression as in the one-thread
 // sweep: bit-identical results (ACOC_NO_BWD_COLS for A/B; the host replay checks the decomposition,
 // tests/test_kernel_math_host.py::test_riccati_by_columns_bit_identical; every small-batch parity test on the GPU runs through it).
@@ -738,11 +741,12 @@ __global__ void __launch_bounds__(64, 4) k_backward_split(ProblemT<F> P, TileLis
 constexpr int BC_NPRE = ACOC_BC_NPRE;
 constexpr int BC_XA = 2 * BC_NPRE;  // slots of message ring A (a PRE warp owns the slots w, w + BC_NPRE)
 constexpr int BC_XB = 4;            // slots of message ring B
-constexpr int BC_WARPS = BC_NPRE + 2 + NS;
+constexpr int BC_WARPS = BC_NPRE + 3 + NS;
 constexpr int BC_THREADS = BC_WARPS * TILE;
-constexpr int BC_SYNC_THREADS = (1 + NS) * TILE;  // GAIN + COLUMN warps
+constexpr int BC_SYNC1_THREADS = (2 + NS) * TILE;  // barrier 1: GAIN, OUT and the COLUMN warps
+constexpr int BC_SYNC2_THREADS = (1 + NS) * TILE;  // barrier 2: GAIN and the COLUMN warps
 constexpr int BC_PB = 21 + NS;  // shared P (21 entries of the upper triangle) and p (6)
-constexpr int BC_GB = 8;        // gain block: gi00 gi01 gi11 k00 k01 k11 y0 y1
+constexpr int BC_GB = 10;       // gain block: gi00 gi01 gi11 y0 y1 | G00 G01 G11 m0 m1 (the second half for the OUT warp)
 constexpr int BC_MSGB = 7;      // h22 h23 h25 h33 h55 s2 s3
 template <bool EXACT>
 struct BcMsgA { static constexpr int N = 12 + NS + NI + (EXACT ? 16 : 0); };
@@ -750,16 +754,26 @@ template <bool EXACT, typename F, typename XT>
 constexpr size_t backward_cols_smem()
 {
     return (size_t)BC_NPRE * BWD_STAGES * BwdStage<F, XT>::BYTES +
-           ((size_t)BC_XA * BcMsgA<EXACT>::N + (size_t)BC_XB * BC_MSGB + BC_PB + 2 * NS + BC_GB) * TILE * sizeof(F) +
+           ((size_t)BC_XA * BcMsgA<EXACT>::N + (size_t)BC_XB * BC_MSGB + BC_PB + 2 * (2 * NS + BC_GB)) * TILE * sizeof(F) +
            (BC_NPRE * BWD_STAGES + 2 * BC_XA + 2 * BC_XB) * sizeof(uint64_t);
 }
-// barrier of the GAIN and COLUMN warps (barrier 0 is __syncthreads)
-__device__ __forceinline__ void bc_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(BC_SYNC_THREADS) : "memory"); }
+// named barriers of the matrix-half warps (barrier 0 is __syncthreads)
+__device__ __forceinline__ void bc_bar1() { asm volatile("bar.sync 1, %0;" ::"n"(BC_SYNC1_THREADS) : "memory"); }
+__device__ __forceinline__ void bc_bar2() { asm volatile("bar.sync 2, %0;" ::"n"(BC_SYNC2_THREADS) : "memory"); }
 
 template <typename F>
 struct BcShared {
     F *msgA, *msgB, *PB, *MX, *GB;
     uint64_t *afull, *aempty, *bfull, *bempty;
+};
+
+// ring position without a division per step: slot and phase parity of message-ring use number k
+struct BcSlot {
+    int s;
+    uint32_t par;
+    __device__ __forceinline__ BcSlot() : s(0), par(0) {}
+    template <int N>
+    __device__ __forceinline__ void next() { if (++s == N) { s = 0; par ^= 1u; } }
 };
 
 // ---- PRE warp w: steps k = w, w + BC_NPRE, ...
@@ -806,7 +820,7 @@ __device__ __forceinline__ void bc_pre_role(const ProblemT<F>& P, int tile, int 
         } else if (rm.has_v) vv = reinterpret_cast<const F*>(st + St::XR_O)[lane];
         stage_release();
         if (lane == 0 && j + BWD_STAGES < nmine) issue(j + BWD_STAGES);
-        const int s = k % BC_XA;
+        const int s = k % BC_XA;   // (= w or w + BC_NPRE, alternating)
         F* const m = sh.msgA + (size_t)s * NA * TILE + lane;
         if (live) {
             rm.fill(P, t, i, vv, xr, ur);
@@ -861,9 +875,10 @@ __device__ __forceinline__ void bc_lambda_role(const ProblemT<F>& P, int tile, i
         for (int c = 0; c < NS; ++c) dxT[c] = x[c] - xr[c];
         wmul6(P.W.QT, (int)weights_diag<DG>(P.W), dxT, lam);  // lam_{T-1} = QT dx (optcon.py:429-432)
     }
-    for (int k = 0; k < nsteps; ++k) {
-        const int t = TT - 2 - k, s = k % BC_XA, sb = k % BC_XB;
-        mbar_wait(sh.afull + s, (uint32_t)((k / BC_XA) & 1));
+    BcSlot sa, sbs;
+    for (int k = 0; k < nsteps; ++k, sa.next<BC_XA>(), sbs.next<BC_XB>()) {
+        const int t = TT - 2 - k, s = sa.s, sb = sbs.s;
+        mbar_wait(sh.afull + s, sa.par);
         const F* const m = sh.msgA + (size_t)s * NA * TILE + lane;
         Lin<F> l;
         HessPre<F> a;
@@ -882,7 +897,7 @@ __device__ __forceinline__ void bc_lambda_role(const ProblemT<F>& P, int tile, i
         __syncwarp();
         if (lane == 0) mbar_arrive(sh.aempty + s);
         if (EXACT) {
-            if (k >= BC_XB) mbar_wait(sh.bempty + sb, (uint32_t)((k / BC_XB - 1) & 1));
+            if (k >= BC_XB) mbar_wait(sh.bempty + sb, sbs.par ^ 1u);
             if (live) {
                 const Hess<F> h = hess_post(a, lam);   // with lam_{t+1} (optcon.py:437)
                 F* const mb = sh.msgB + (size_t)sb * BC_MSGB * TILE + lane;
@@ -901,19 +916,17 @@ __device__ __forceinline__ void bc_lambda_role(const ProblemT<F>& P, int tile, i
     }
 }
 
-// ---- GAIN warp
+// ---- GAIN warp: G, m, G^-1, y (riccati_gain_core) into the gain block of the step
 template <bool EXACT, typename F>
-__device__ __forceinline__ void bc_gain_role(const ProblemT<F>& P, int tile, int lane, bool live, const BcShared<F>& sh, F* __restrict__ KSG,
-                                             const int* __restrict__ status, int* __restrict__ n_reg)
+__device__ __forceinline__ void bc_gain_role(const ProblemT<F>& P, int lane, bool live, const BcShared<F>& sh)
 {
     constexpr int NA = BcMsgA<EXACT>::N;
-    const int TT = P.TT, Np = P.Np, i = tile * TILE + lane, nsteps = TT - 1;
-    bc_bar(2);  // the COLUMN warps have stored the terminal P, p
-    int nreg = 0;
-    for (int k = 0; k < nsteps; ++k) {
-        const int t = TT - 2 - k, s = k % BC_XA;
-        mbar_wait(sh.afull + s, (uint32_t)((k / BC_XA) & 1));
-        const F* const m = sh.msgA + (size_t)s * NA * TILE + lane;
+    const int nsteps = P.TT - 1;
+    bc_bar2();  // the COLUMN warps have stored the terminal P, p
+    BcSlot sa;
+    for (int k = 0; k < nsteps; ++k, sa.next<BC_XA>()) {
+        mbar_wait(sh.afull + sa.s, sa.par);
+        const F* const m = sh.msgA + (size_t)sa.s * NA * TILE + lane;
         Lin<F> l;
         F r[NI], Pm[21], p[NS];
         if (live) {
@@ -924,95 +937,127 @@ __device__ __forceinline__ void bc_gain_role(const ProblemT<F>& P, int tile, int
             p[2] = sh.PB[(21 + 2) * TILE + lane]; p[4] = sh.PB[(21 + 4) * TILE + lane]; p[5] = sh.PB[(21 + 5) * TILE + lane];
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(sh.aempty + s);
-        RicGain<F> gn;
-        gn.reg = 0;
+        if (lane == 0) mbar_arrive(sh.aempty + sa.s);
         if (live) {
-            gn = riccati_gain(P.M, P.W, l, r, Pm, p);
-            F* const gb = sh.GB + lane;
-            gb[0 * TILE] = gn.gi00; gb[1 * TILE] = gn.gi01; gb[2 * TILE] = gn.gi11; gb[3 * TILE] = gn.k00; gb[4 * TILE] = gn.k01;
-            gb[5 * TILE] = gn.k11; gb[6 * TILE] = gn.y0; gb[7 * TILE] = gn.y1;
+            RicGain<F> gn;
+            riccati_gain_core(P.M, P.W, l, r, Pm, p, gn);
+            F* const gb = sh.GB + (size_t)(k & 1) * BC_GB * TILE + lane;
+            gb[0 * TILE] = gn.gi00; gb[1 * TILE] = gn.gi01; gb[2 * TILE] = gn.gi11; gb[3 * TILE] = gn.y0; gb[4 * TILE] = gn.y1;
+            gb[5 * TILE] = gn.G00; gb[6 * TILE] = gn.G01; gb[7 * TILE] = gn.G11; gb[8 * TILE] = gn.m0; gb[9 * TILE] = gn.m1;
         }
-        bc_bar(1);  // Mx of every column and the gain block are in shared memory; every warp has read the old P, p
+        bc_bar1();  // Mx of every column and the gain block of step k are in shared memory (buffer k & 1); every warp has read the old P, p
+        bc_bar2();  // the new P, p are in shared memory
+    }
+}
+
+// ---- OUT warp: the outputs K_t, sigma_t (eigenvalue test, regularised inverse, riccati_gain_out) from Mx and the gain block of the step.
+// Takes part in barrier 1 only: Mx and the gain block are double-buffered, so it works on step k while the other warps are already in
+// the first half of step k+1 (buffer k & 1 is rewritten in step k+2, after barrier 1 of step k+1, which this warp reaches after its reads).
+template <typename F>
+__device__ __forceinline__ void bc_out_role(const ProblemT<F>& P, int tile, int lane, bool live, const BcShared<F>& sh, F* __restrict__ KSG,
+                                            const int* __restrict__ status, int* __restrict__ n_reg)
+{
+    const int TT = P.TT, Np = P.Np, i = tile * TILE + lane, nsteps = TT - 1;
+    int nreg = 0;
+    F* out = KSG + tile_base(TT - 2, 16, Np, tile) + lane;
+    const size_t ostride = (size_t)(Np / TILE) * 16 * TILE;
+    for (int k = 0; k < nsteps; ++k, out -= ostride) {
+        bc_bar1();
         if (live) {
-            F* out = KSG + tile_base(t, 16, Np, tile) + lane;
-            out[12 * TILE] = -fma_(gn.k01, gn.m1, gn.k00 * gn.m0);
-            out[13 * TILE] = -fma_(gn.k11, gn.m1, gn.k01 * gn.m0);
+            const F* const gb = sh.GB + (size_t)(k & 1) * BC_GB * TILE + lane;
+            const F* const mx = sh.MX + (size_t)(k & 1) * 2 * NS * TILE + lane;
+            RicGain<F> gn;
+            gn.gi00 = gb[0 * TILE]; gn.gi01 = gb[1 * TILE]; gn.gi11 = gb[2 * TILE];
+            gn.G00 = gb[5 * TILE]; gn.G01 = gb[6 * TILE]; gn.G11 = gb[7 * TILE]; gn.m0 = gb[8 * TILE]; gn.m1 = gb[9 * TILE];
+            F Mx0[NS], Mx1[NS], K[2 * NS], sig[NI];
+#pragma unroll
+            for (int a = 0; a < NS; ++a) { Mx0[a] = mx[a * TILE]; Mx1[a] = mx[(NS + a) * TILE]; }
+            riccati_gain_test(gn);
+            riccati_gain_out(gn, Mx0, Mx1, K, sig);
+#pragma unroll
+            for (int c = 0; c < 12; ++c) out[c * TILE] = K[c];
+            out[12 * TILE] = sig[0]; out[13 * TILE] = sig[1];
             nreg += gn.reg;
         }
-        bc_bar(2);  // the new P, p are in shared memory; Mx and the gain block may be overwritten
     }
     if (live && nreg && status[i] == ST_ACTIVE) n_reg[i] += nreg;
 }
 
-// ---- COLUMN warp J
+// ---- COLUMN warp J (column 0, the lightest, also carries the affine term p)
 template <bool EXACT, int DG, int J, typename F>
-__device__ __forceinline__ void bc_column_role(const ProblemT<F>& P, int tile, int lane, bool live, const F* x, const F* xr, const BcShared<F>& sh,
-                                               F* __restrict__ KSG)
+__device__ __forceinline__ void bc_column_role(const ProblemT<F>& P, int tile, int lane, bool live, const F* x, const F* xr, const BcShared<F>& sh)
 {
     constexpr int NA = BcMsgA<EXACT>::N;
     constexpr bool NEEDS_H = EXACT && (J == 2 || J == 3 || J == 5);
-    const int TT = P.TT, Np = P.Np, nsteps = TT - 1;
+    constexpr bool HAS_P = J == 0;
+    const int nsteps = P.TT - 1;
     F* const PB = sh.PB;
     if (live) {  // terminal condition P_{T-1} = QT, p_{T-1} = lam_{T-1}/2 (optcon.py:688-690, :716): every warp forms it, column J stores its part
         F Pm[21], p[NS], lamT[NS];
         backward_terminal<DG>(P.W, x, xr, Pm, p, lamT);
 #pragma unroll
         for (int a = 0; a <= J; ++a) PB[sym(a, J) * TILE + lane] = Pm[sym(a, J)];
-        PB[(21 + J) * TILE + lane] = p[J];
+        if (HAS_P) {
+#pragma unroll
+            for (int c = 0; c < NS; ++c) PB[(21 + c) * TILE + lane] = p[c];
+        }
     }
-    bc_bar(2);
-    for (int k = 0; k < nsteps; ++k) {
-        const int t = TT - 2 - k, s = k % BC_XA, sb = k % BC_XB;
-        mbar_wait(sh.afull + s, (uint32_t)((k / BC_XA) & 1));
-        const F* const m = sh.msgA + (size_t)s * NA * TILE + lane;
+    bc_bar2();
+    BcSlot sa, sb;
+    for (int k = 0; k < nsteps; ++k, sa.next<BC_XA>(), sb.next<BC_XB>()) {
+        mbar_wait(sh.afull + sa.s, sa.par);
+        const F* const m = sh.msgA + (size_t)sa.s * NA * TILE + lane;
         Lin<F> l;
         Hess<F> h;
-        F qJ = F(0.0), Pm[21], p[NS];
+        F q[NS], Pm[21], p[NS];
         if (live) {
             bc_read_lin(m, l);
-            qJ = m[(12 + J) * TILE];
 #pragma unroll
             for (int e = 0; e < 21; ++e) Pm[e] = PB[e * TILE + lane];   // (entries this column does not touch are dead loads)
+            if (HAS_P) {
 #pragma unroll
-            for (int c = 0; c < NS; ++c) p[c] = PB[(21 + c) * TILE + lane];
+                for (int c = 0; c < NS; ++c) { q[c] = m[(12 + c) * TILE]; p[c] = PB[(21 + c) * TILE + lane]; }
+            }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(sh.aempty + s);
+        if (lane == 0) mbar_arrive(sh.aempty + sa.s);
         if (NEEDS_H) {   // ring B is consumed by the columns 2, 3, 5 only
-            mbar_wait(sh.bfull + sb, (uint32_t)((k / BC_XB) & 1));
+            mbar_wait(sh.bfull + sb.s, sb.par);
             if (live) {
-                const F* const mb = sh.msgB + (size_t)sb * BC_MSGB * TILE + lane;
+                const F* const mb = sh.msgB + (size_t)sb.s * BC_MSGB * TILE + lane;
                 h.h22 = mb[0 * TILE]; h.h23 = mb[1 * TILE]; h.h25 = mb[2 * TILE]; h.h33 = mb[3 * TILE]; h.h55 = mb[4 * TILE];
                 h.s2 = mb[5 * TILE]; h.s3 = mb[6 * TILE];
                 h.h35 = -h.h33; h.s5 = -h.s3;  // (as hess_contract forms them)
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(sh.bempty + sb);
+            if (lane == 0) mbar_arrive(sh.bempty + sb.s);
         }
-        F PnJ[NS], mx0 = F(0.0), mx1 = F(0.0), atp = F(0.0);
+        F PnJ[NS], Atp[NS], mx0 = F(0.0), mx1 = F(0.0);
         if (live) {
-            riccati_col_sweep<EXACT, J, F>(P.M, l, h, Pm, p, PnJ, mx0, mx1, atp);
-            sh.MX[J * TILE + lane] = mx0; sh.MX[(NS + J) * TILE + lane] = mx1;
+            riccati_col_sweep<EXACT, J, F>(P.M, l, h, Pm, PnJ, mx0, mx1);
+            F* const mx = sh.MX + (size_t)(k & 1) * 2 * NS * TILE + lane;
+            mx[J * TILE] = mx0; mx[(NS + J) * TILE] = mx1;
+            if (HAS_P) riccati_p_sweep(P.M, l, p, Atp);
         }
-        bc_bar(1);  // Mx of every column and the gain block are in shared memory; every warp has read the old P, p
+        bc_bar1();  // Mx of every column and the gain block are in shared memory; every warp has read the old P, p
         if (live) {
-            RicGain<F> gn;
-            const F* const gb = sh.GB + lane;
-            gn.gi00 = gb[0 * TILE]; gn.gi01 = gb[1 * TILE]; gn.gi11 = gb[2 * TILE]; gn.k00 = gb[3 * TILE]; gn.k01 = gb[4 * TILE];
-            gn.k11 = gb[5 * TILE]; gn.y0 = gb[6 * TILE]; gn.y1 = gb[7 * TILE];
-            F Mx0[NS], Mx1[NS], PJ[NS], pJ, K0, K1;
+            const F* const gb = sh.GB + (size_t)(k & 1) * BC_GB * TILE + lane;
+            const F* const mx = sh.MX + (size_t)(k & 1) * 2 * NS * TILE + lane;
+            const F gi00 = gb[0 * TILE], gi01 = gb[1 * TILE], gi11 = gb[2 * TILE];
+            F Mx0[NS], Mx1[NS], PJ[NS];
 #pragma unroll
-            for (int a = 0; a < J; ++a) { Mx0[a] = sh.MX[a * TILE + lane]; Mx1[a] = sh.MX[(NS + a) * TILE + lane]; }
+            for (int a = 0; a < (HAS_P ? NS : J); ++a) { Mx0[a] = mx[a * TILE]; Mx1[a] = mx[(NS + a) * TILE]; }
             Mx0[J] = mx0; Mx1[J] = mx1;
-            riccati_col_finish<EXACT, DG, J, F>(P.W, h, qJ, gn, PnJ, Mx0, Mx1, atp, PJ, pJ, K0, K1);
+            riccati_col_finish<EXACT, DG, J, F>(P.W, h, gi00, gi01, gi11, PnJ, Mx0, Mx1, PJ);
 #pragma unroll
             for (int a = 0; a <= J; ++a) PB[sym(a, J) * TILE + lane] = PJ[a];
-            PB[(21 + J) * TILE + lane] = pJ;
-            F* out = KSG + tile_base(t, 16, Np, tile) + lane;
-            out[J * TILE] = K0; out[(NS + J) * TILE] = K1;
+            if (HAS_P) {
+                riccati_p_finish(q, Atp, Mx0, Mx1, gb[3 * TILE], gb[4 * TILE], p);
+#pragma unroll
+                for (int c = 0; c < NS; ++c) PB[(21 + c) * TILE + lane] = p[c];
+            }
         }
-        bc_bar(2);  // the new P, p are in shared memory; Mx and the gain block may be overwritten
+        bc_bar2();  // the new P, p are in shared memory
     }
 }
 
@@ -1031,15 +1076,15 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_backward_cols(ProblemT<F> P, 
     sh.msgB = sh.msgA + (size_t)BC_XA * BcMsgA<EXACT>::N * TILE;
     sh.PB = sh.msgB + (size_t)BC_XB * BC_MSGB * TILE;
     sh.MX = sh.PB + (size_t)BC_PB * TILE;
-    sh.GB = sh.MX + (size_t)2 * NS * TILE;
-    uint64_t* const bar_in = reinterpret_cast<uint64_t*>(sh.GB + (size_t)BC_GB * TILE);
+    sh.GB = sh.MX + (size_t)2 * 2 * NS * TILE;
+    uint64_t* const bar_in = reinterpret_cast<uint64_t*>(sh.GB + (size_t)2 * BC_GB * TILE);
     sh.afull = bar_in + BC_NPRE * BWD_STAGES;
     sh.aempty = sh.afull + BC_XA;
     sh.bfull = sh.aempty + BC_XA;
     sh.bempty = sh.bfull + BC_XB;
     if (threadIdx.x == 0) {
         for (int s = 0; s < BC_NPRE * BWD_STAGES; ++s) mbar_init(bar_in + s, 1);
-        for (int s = 0; s < BC_XA; ++s) { mbar_init(sh.afull + s, 1); mbar_init(sh.aempty + s, 2 + NS); }  // consumers: LAMBDA, GAIN, 6 COLUMN
+        for (int s = 0; s < BC_XA; ++s) { mbar_init(sh.afull + s, 1); mbar_init(sh.aempty + s, 2 + NS); }  // consumers: LAMBDA, GAIN, 6 COLUMN (OUT reads no message)
         for (int s = 0; s < BC_XB; ++s) { mbar_init(sh.bfull + s, 1); mbar_init(sh.bempty + s, 3); }       // consumers: COLUMN 2, 3, 5
         mbar_fence_init();
     }
@@ -1047,7 +1092,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_backward_cols(ProblemT<F> P, 
     const int i = tile * TILE + lane;
     const bool live = i < P.N;
     F x[NS], xr[NS];
-    if (live && role >= BC_NPRE && role != BC_NPRE + 1) {  // terminal condition: LAMBDA and the COLUMN warps need x_{T-1} - xref_{T-1}
+    if (live && (role == BC_NPRE || role >= BC_NPRE + 3)) {  // terminal condition: LAMBDA and the COLUMN warps need x_{T-1} - xref_{T-1}
         load_xref(P, P.TT - 1, i, xr);
         load_x(P, X, P.TT - 1, i, x);
     }
@@ -1057,13 +1102,14 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_backward_cols(ProblemT<F> P, 
     }
     switch (role - BC_NPRE) {
         case 0: bc_lambda_role<EXACT, F, DG>(P, tile, lane, live, x, xr, sh, KSG); break;
-        case 1: bc_gain_role<EXACT, F>(P, tile, lane, live, sh, KSG, status, n_reg); break;
-        case 2: bc_column_role<EXACT, DG, 0, F>(P, tile, lane, live, x, xr, sh, KSG); break;
-        case 3: bc_column_role<EXACT, DG, 1, F>(P, tile, lane, live, x, xr, sh, KSG); break;
-        case 4: bc_column_role<EXACT, DG, 2, F>(P, tile, lane, live, x, xr, sh, KSG); break;
-        case 5: bc_column_role<EXACT, DG, 3, F>(P, tile, lane, live, x, xr, sh, KSG); break;
-        case 6: bc_column_role<EXACT, DG, 4, F>(P, tile, lane, live, x, xr, sh, KSG); break;
-        default: bc_column_role<EXACT, DG, 5, F>(P, tile, lane, live, x, xr, sh, KSG); break;
+        case 1: bc_gain_role<EXACT, F>(P, lane, live, sh); break;
+        case 2: bc_out_role<F>(P, tile, lane, live, sh, KSG, status, n_reg); break;
+        case 3: bc_column_role<EXACT, DG, 0, F>(P, tile, lane, live, x, xr, sh); break;
+        case 4: bc_column_role<EXACT, DG, 1, F>(P, tile, lane, live, x, xr, sh); break;
+        case 5: bc_column_role<EXACT, DG, 2, F>(P, tile, lane, live, x, xr, sh); break;
+        case 6: bc_column_role<EXACT, DG, 3, F>(P, tile, lane, live, x, xr, sh); break;
+        case 7: bc_column_role<EXACT, DG, 4, F>(P, tile, lane, live, x, xr, sh); break;
+        default: bc_column_role<EXACT, DG, 5, F>(P, tile, lane, live, x, xr, sh); break;
     }
 }
 
