@@ -201,7 +201,10 @@ ACOC_HD double traj_cost_instance(const ProblemT<F>& P, const XT* X, const F* U,
 // half (G, m, the column sweep, gains, P_t, p_t: needs P_{t+1}, p_{t+1} only).  riccati_step() is their composition.  (Running the
 // halves in two warps of a CTA -- costate warp one step ahead, linearisation handed over through shared memory -- was measured in
 // round 2: the matrix half alone needs ~230 registers to stay spill-free, so only 4 tiles per SM are resident instead of 8 and the
-// sweep takes 4.0 ms instead of 3.2; bounded to 168 / 128 registers it spills and takes 5.0 / 6.4 ms.  Not kept; profiles/README.md.)
+// sweep takes 4.0 ms instead of 3.2; bounded to 168 / 128 registers it spills and takes 5.0 / 6.4 ms.  Big batches therefore keep the
+// one-thread step below; batches that leave the machine idle run it as warp roles: k_backward_split (two halves) up to two tiles per
+// SM, k_backward_cols (the halves cut further: linearisation ahead of time, costate, gain block, outputs, one warp per column of the
+// matrix half -- the pieces further down) up to one tile per SM.  acoc_tma.cuh, profiles/README.md.)
 
 // costate half: g = B' lam_{t+1} + r (optcon.py:475), lam_t = A' lam_{t+1} + q (:461)
 template <typename F>

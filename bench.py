@@ -759,12 +759,12 @@ def run_single(args, rank, world, local):
                     "what": "set_refs + set_init (H2D) -> solve() to descent >= -1e-6 -> result() (D2H), host numpy buffers, best of 3"},
             "gpu_launches": launches,
             "whole_solve": {"device_ms": min(solves), "total_newton_iterations": int(tot), "reference_iterations": iters_ref, "value": tot / (min(solves) * 1e-3), "unit": UNIT},
-            "roofline": {"kernel": "k_backward_tma + k_search_fused (one warp / 12 warps)", "bound": "hbm",
+            "roofline": {"kernel": "k_backward_cols + k_search_fused (12 warp roles / 12 warps per tile)", "bound": "hbm",
                          "achieved": (TT - 1) * (BYTES["backward"] + BYTES["forward"] + 11 * BYTES["candidate"]) / (per_it * 1e-3) / 1e9,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (TT - 1) * (BYTES["backward"] + BYTES["forward"] + 11 * BYTES["candidate"]) / (per_it * 1e-3) / 1e9 / peaks["hbm_gbs"],
                          "traffic": None, "peak_source": peak_src,
-                         "note": "one trajectory is one warp lane: the iteration is two dependent sweeps of 999 sequential steps, i.e. pure arithmetic "
-                                 "latency (%.2f us per backward+search step pair); no roofline is within reach of a single trajectory" % (per_it * 1e3 / (TT - 1))},
+                         "note": "one trajectory is one lane of every warp role: the iteration is two dependent sweeps of 999 sequential steps, i.e. pure "
+                                 "arithmetic latency (%.2f us per backward+search step pair); no roofline is within reach of a single trajectory" % (per_it * 1e3 / (TT - 1))},
             "cpu_baseline": cpu, "device": pkg.device_info(local)["name"]}
     emit(line)
 

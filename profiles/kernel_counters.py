@@ -20,7 +20,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TT = 1000
 KEYS = [("k_backward_tma", "k_backward_tma"), ("k_forward_cand0_tma", "k_forward_cand0_tma"), ("k_candidates_list", "k_candidates"),
-        ("k_rollout_write_tma", "k_rollout_write_tma<.,1>"), ("k_backward_split", "k_backward_split"), ("k_search_fused", "k_search_fused")]
+        ("k_rollout_write_tma", "k_rollout_write_tma<.,1>"), ("k_backward_split", "k_backward_split"), ("k_backward_cols", "k_backward_cols"), ("k_search_fused", "k_search_fused")]
 
 
 def source_sha16():
