@@ -485,3 +485,54 @@ def test_compact_references_gradient_method_and_fp32_delivery(gpu):
                 bn.solve()
                 res.append(bn.result_f32()[:2])
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+
+
+_BWD_KERNELS_SCRIPT = r"""
+import sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import aircraftoptimalcontrol_b200 as pkg
+from aircraftoptimalcontrol_b200 import refgen
+out = {}
+for tag, n, TT, dense, state in (("a", 333, 160, False, "f32"), ("b", 70, 90, True, "f64")):
+    rng = np.random.default_rng(31)
+    xr, ur = refgen.step_problem(rng.uniform(14, 18, n), rng.uniform(1.5, 3.5, n), tf=TT * 1e-3, TT=TT)
+    Q, R, QT = refgen.weights("step")
+    if dense:
+        E = rng.normal(size=(6, 6)) * 1e-4
+        Q, QT, R = Q + E @ E.T, QT + 3 * (E @ E.T), R + 1e-7 * np.array([[1.0, 0.3], [0.3, 2.0]])
+    with pkg.BatchedNewton(n, TT=TT, armijo="lazy", state=state, exact_after=2, max_iters=12) as bn:
+        bn.set_weights(Q, R, QT)
+        bn.set_refs(xr, ur)
+        bn.init_guess()
+        bn.solve()
+        (xs, us), h, st, (K, sig) = bn.result(), bn.history(), bn.stats(), bn.gains()[:2]
+    out.update({tag + "_x": xs, tag + "_u": us, tag + "_K": K, tag + "_sig": sig, tag + "_JJ": h["JJ"], tag + "_descent": h["descent"],
+                tag + "_step": h["stepsize"], tag + "_iters": st["iters"], tag + "_nreg": st["n_reg"]})
+np.savez(sys.argv[2], **out)
+"""
+
+
+def test_backward_kernels_identical(gpu, tmp_path):
+    """The three backward sweeps of the TMA path -- k_backward_cols (pipeline of 12 warp roles, the default up to one tile per SM),
+    k_backward_split (two warps per tile) and k_backward_tma (one thread per instance) -- run the same expression for every number
+    (optcon.py:429-464, :716-751): whole solves must agree bit for bit, gains of the last sweep included.  The choice is made per
+    process (environment), hence the subprocesses.  Ragged batches (padding lanes), Gauss-Newton and exact-Hessian iterations,
+    diagonal and dense weights, float and float64 state slots."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "bwd.py"
+    script.write_text(_BWD_KERNELS_SCRIPT)
+    res = {}
+    for name, env in (("cols", {}), ("split", {"ACOC_NO_BWD_COLS": "1"}), ("tma", {"ACOC_NO_BWD_COLS": "1", "ACOC_NO_BWD_SPLIT": "1"})):
+        f = tmp_path / (name + ".npz")
+        e = dict(os.environ)
+        e.update(env)
+        subprocess.run([sys.executable, str(script), root, str(f)], check=True, env=e, timeout=300)
+        res[name] = dict(np.load(f))
+    assert res["cols"]["a_iters"].max() >= 6   # exact-Hessian iterations were run
+    for other in ("split", "tma"):
+        for k, v in res["cols"].items():
+            assert np.array_equal(v, res[other][k]), (other, k)
