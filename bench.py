@@ -280,7 +280,10 @@ def run_reference_arm(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": config_dict(args, sample, world=1),
+        # the configuration of our arm (the driver compares the two lines' config); what the CPU actually ran is the bounded sample below
+        "data": "synthetic", "config": config_dict(args, args.instances, world),
+        "sample": {"instances": sample, "newton_iterations": [args.warmup, args.warmup + args.steps - 1], "cpu_seconds": dt,
+                   "note": "a throughput metric: the rate of the sample stands for the workload (instances are independent)"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": nt, "kind": "port",
                          "sample": "%d instances x Newton iterations %d..%d of the workload, C port of the reference (oracle/acoc_oracle.c), "
                                    "OpenMP over instances; time(W+K iterations) - time(W iterations)" % (sample, args.warmup, args.warmup + args.steps - 1),
@@ -334,6 +337,8 @@ def roofline_tables(args, n, K, W, hist, phases, peaks, peak_src, fp64_peak, fus
     names = {"backward": "k_backward_tma" if not args.no_tma else "k_backward",
              "forward": ("k_forward_cand0_tma" if fused_fc else ("k_forward_tma" if not args.no_tma else "k_forward")),
              "candidates": "k_candidates", "update": "k_rollout_write_tma<.,1>" if not args.no_tma else "k_update"}
+    # kernel names as launched (the counters file keeps the candidate stage under "k_candidates" whichever kernel ran it)
+    shown = dict(names, candidates="k_candidates_list" if (args.armijo == "lazy" and not args.no_tma) else "k_candidates")
     units = {  # (useful instance-sweeps, processed lane-sweeps) over the K iterations
         "backward": (a_k.sum(), lanes_k.sum()), "forward": (a_k.sum(), lanes_k.sum()),
         "candidates": (roll_k.sum() + cand0_units, roll_k.sum() + cand0_units), "update": (upd_k.sum(), upd_lanes_k.sum())}
@@ -348,7 +353,7 @@ def roofline_tables(args, n, K, W, hist, phases, peaks, peak_src, fp64_peak, fus
         if ms <= 0 or useful <= 0:
             continue
         sec = ms * 1e-3
-        e = {"kernel": names[k], "bound": bound[k], "ms_per_iteration": ms / K, "instance_sweeps_useful": useful, "lane_sweeps_processed": lanes}
+        e = {"kernel": shown[k], "bound": bound[k], "ms_per_iteration": ms / K, "instance_sweeps_useful": useful, "lane_sweeps_processed": lanes}
         c = counters(names[k])
         if c and c.get("fp64_inst_per_lane_step"):   # executed FP64-pipe instructions (ncu: sm__inst_executed_pipe_fp64 of this build)
             ex = c["fp64_inst_per_lane_step"] * lanes * steps_per
@@ -380,7 +385,7 @@ def roofline_tables(args, n, K, W, hist, phases, peaks, peak_src, fp64_peak, fus
     else:
         achieved, peak, unit = d.get("fp64_executed_ginst_per_s"), fp64_peak * 1e3 / 2.0, "G FP64-inst/s (thread-level)"
         frac = d.get("fp64_executed_frac")
-    roofline = {"kernel": names[dom] + ("<EXACT>" if dom == "backward" and exact.any() else ""), "bound": "hbm" if bound[dom] == "hbm" else "fp64 (tensor cores unused by design)",
+    roofline = {"kernel": shown[dom] + ("<EXACT>" if dom == "backward" and exact.any() else ""), "bound": "hbm" if bound[dom] == "hbm" else "fp64 (tensor cores unused by design)",
                 "achieved": achieved, "peak": peak, "unit": unit, "frac": frac, "traffic": traffic, "traffic_source": kc_src,
                 "algorithmic_bytes_per_launch": alg_per_launch, "peak_source": peak_src,
                 "units": {"active_instances_per_iteration": a_k.tolist(), "lanes_processed_per_iteration": lanes_k.tolist(),

@@ -56,3 +56,18 @@ def test_committed_bench_line_has_every_contract_key():
     assert d["e2e_host_refs"]["h2d_bytes_per_step"] > 1e6 and d["roofline"]["traffic"] > 0 and d["roofline"]["frac"] <= 1.2
     assert d["cpu_baseline"]["python_reference"]["value"] > 0
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    """The driver launches the reference arm exactly like ours (torchrun for N > 1): rank 0 alone works and prints, the other ranks
+    exit 0; the line carries OUR arm's config (the bounded CPU sample is described beside it)."""
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29731", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1",
+                        "--cpu-sample", "32"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["gpu_launches"] == 0
+    assert d["config"]["instances_per_gpu"] == 65536 and d["config"]["instances_total"] == 2 * 65536
+    assert d["sample"]["instances"] == 32 and d["cpu_baseline"]["sample"].startswith("32 instances")
