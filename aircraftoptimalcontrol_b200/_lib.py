@@ -122,8 +122,24 @@ def ptr(a):
     """Address of a C-contiguous numpy array (or None)."""
     if a is None:
         return None
-    assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+    if not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("array must be C-contiguous")
     return a.ctypes.data
+
+
+def out_array(a, shape, dtypes, name="out"):
+    """Validate a caller-supplied OUTPUT array before its address crosses the C boundary (the library writes prod(shape) elements of
+    the dtype it was told, whatever the array really is): numpy array, exact shape, one of `dtypes`, C-contiguous, writeable."""
+    dtypes = tuple(np.dtype(d) for d in (dtypes if isinstance(dtypes, (tuple, list)) else (dtypes,)))
+    if not isinstance(a, np.ndarray):
+        raise ValueError("%s must be a numpy array" % name)
+    if tuple(a.shape) != tuple(shape):
+        raise ValueError("%s has shape %s, expected %s" % (name, a.shape, tuple(shape)))
+    if a.dtype not in dtypes:
+        raise ValueError("%s has dtype %s, expected %s" % (name, a.dtype, " or ".join(str(d) for d in dtypes)))
+    if not a.flags["C_CONTIGUOUS"] or not a.flags["WRITEABLE"]:
+        raise ValueError("%s must be C-contiguous and writeable" % name)
+    return a
 
 
 def f64(a, shape=None, name="array"):

@@ -176,9 +176,9 @@ class BatchedNewton:
         delivered while the last ones still iterate (acoc_newton_solve_deliver); pageable arrays get the same values through
         solve() + result().  Returns (total Newton iterations, x0 (N,6))."""
         xs, us = out
-        if xs.dtype not in (np.float32, np.float64) or us.dtype != np.float64 or xs.shape != (self.N, 6, self.TT) or us.shape != (self.N, 2, self.TT):
-            raise ValueError("solve_deliver needs xx_star (N,6,TT) float32/float64 and uu_star (N,2,TT) float64")
-        x0 = np.empty((self.N, 6)) if x0 is None else x0
+        L.out_array(xs, (self.N, 6, self.TT), (np.float32, np.float64), "xx_star")
+        L.out_array(us, (self.N, 2, self.TT), np.float64, "uu_star")
+        x0 = np.empty((self.N, 6)) if x0 is None else L.out_array(x0, (self.N, 6), np.float64, "x0")
         tot = C.c_longlong(0)
         L.check(L.lib().acoc_newton_solve_deliver(self._h, L.ptr(xs), int(xs.dtype == np.float32), L.ptr(us), L.ptr(x0), C.addressof(tot)))
         return tot.value, x0
@@ -240,6 +240,8 @@ class BatchedNewton:
             xs, us = np.empty((self.N, 6, self.TT)), np.empty((self.N, 2, self.TT))
         else:
             xs, us = out
+            L.out_array(xs, (self.N, 6, self.TT), np.float64, "xx_star")
+            L.out_array(us, (self.N, 2, self.TT), np.float64, "uu_star")
         L.check(L.lib().acoc_get_result(self._h, L.ptr(xs), L.ptr(us)))
         return xs, us
 
@@ -251,8 +253,8 @@ class BatchedNewton:
             xs, us = np.empty((self.N, 6, self.TT), dtype=np.float32), np.empty((self.N, 2, self.TT))
         else:
             xs, us = out
-            if xs.dtype != np.float32 or us.dtype != np.float64:
-                raise ValueError("result_f32 needs a float32 state array and a float64 input array")
+            L.out_array(xs, (self.N, 6, self.TT), np.float32, "xx_star")
+            L.out_array(us, (self.N, 2, self.TT), np.float64, "uu_star")
         x0 = np.empty((self.N, 6))
         L.check(L.lib().acoc_get_result_f32(self._h, L.ptr(xs), L.ptr(us), L.ptr(x0)))
         return xs, us, x0
@@ -344,7 +346,18 @@ class PipelinedNewton:
         f32 = np.dtype(x_dtype) == np.float32
         if (xx_ref is None) == (refs is None):
             raise ValueError("give either xx_ref/uu_ref or refs=(kind, ...)")
+        if np.dtype(x_dtype) not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise ValueError("x_dtype must be float32 or float64")
         xs, us = out if out is not None else (np.empty((N, 6, TT), dtype=x_dtype), np.empty((N, 2, TT)))
+        L.out_array(xs, (N, 6, TT), x_dtype, "xx_star")     # (the sub-batches write into slices of these arrays)
+        L.out_array(us, (N, 2, TT), np.float64, "uu_star")
+        for name, a, cols in (("xx_ref", xx_ref, 6), ("uu_ref", uu_ref, 2), ("xx_init", xx_init, 6), ("uu_init", uu_init, 2)):
+            if a is not None and tuple(np.shape(a)) != (N, cols, TT):
+                raise ValueError("%s has shape %s, expected %s" % (name, np.shape(a), (N, cols, TT)))
+        if (xx_ref is None) != (uu_ref is None) or (xx_init is None) != (uu_init is None):
+            raise ValueError("xx_ref/uu_ref and xx_init/uu_init are given in pairs")
+        if dx0 is not None and tuple(np.shape(dx0)) != (N, 6):
+            raise ValueError("dx0 has shape %s, expected %s" % (np.shape(dx0), (N, 6)))
         stats = dict(iters=np.zeros(N, dtype=np.int32), status=np.zeros(N, dtype=np.int32), J=np.zeros(N), descent=np.zeros(N),
                      n_reg=np.zeros(N, dtype=np.int32))
         x0_out = np.zeros((N, 6)) if f32 else None
