@@ -389,6 +389,9 @@ class PipelinedNewton:
                         raise ValueError("refs[0] must be 'step' or 'acrobatic'")
                     if xx_init is not None:
                         bn.set_init(xx_init[lo:hi], uu_init[lo:hi])
+                except Exception as e:   # recorded BEFORE the turn is handed on, so that the next sub-batch sees it and stays out
+                    errors.append(e)
+                    raise
                 finally:
                     with turn:
                         state["next_upload"] = k + 1
@@ -411,7 +414,8 @@ class PipelinedNewton:
                 for key in stats:
                     stats[key][lo:hi] = st[key]
             except Exception as e:  # surfaced after the join
-                errors.append(e)
+                if not any(e is x for x in errors):
+                    errors.append(e)
                 with turn:
                     turn.notify_all()
 

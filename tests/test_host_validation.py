@@ -73,3 +73,68 @@ def test_pipelined_solve_arguments_are_checked_before_any_upload():
     # with nothing to complain about and no sub-batches the call returns the (untouched) outputs
     xs, us, st = pn.solve(xr, ur)
     assert xs.shape == (n, 6, TT) and us.shape == (n, 2, TT) and st["iters"].shape == (n,)
+
+
+class _FakePart:
+    """Stands in for a BatchedNewton sub-batch: records what the pipeline asks of it, fails on request."""
+
+    def __init__(self, n, TT, fail_in=None, log=None):
+        self.N, self.TT, self.fail_in, self.log = n, TT, fail_in, log if log is not None else []
+
+    def _step(self, what):
+        self.log.append((what, self.N))
+        if self.fail_in == what:
+            raise RuntimeError("sub-batch of %d failed in %s" % (self.N, what))
+
+    def set_refs(self, xr, ur):
+        assert xr.shape == (self.N, 6, self.TT) and ur.shape == (self.N, 2, self.TT)
+        self._step("set_refs")
+
+    def init_guess(self, dx0=None):
+        assert dx0 is None or dx0.shape == (self.N, 6)
+        self._step("init_guess")
+
+    def solve_deliver(self, out):
+        self._step("solve_deliver")
+        out[0][...] = self.N
+        out[1][...] = -self.N
+        return 7 * self.N, np.full((self.N, 6), 0.5)
+
+    def stats(self):
+        z = np.zeros(self.N)
+        return dict(iters=np.full(self.N, 7, dtype=np.int32), status=np.ones(self.N, dtype=np.int32), J=z + self.N, descent=z, n_reg=z.astype(np.int32))
+
+
+def _fake_pipeline(sizes, TT, fail=None):
+    pn = PipelinedNewton.__new__(PipelinedNewton)
+    pn.N, pn.TT = sum(sizes), TT
+    pn.bounds = [0] + list(np.cumsum(sizes))
+    log = []
+    pn.parts = [_FakePart(n, TT, fail_in=(fail[1] if fail and fail[0] == k else None), log=log) for k, n in enumerate(sizes)]
+    return pn, log
+
+
+def test_pipeline_hands_every_sub_batch_its_slice_in_upload_order():
+    sizes, TT = [3, 5, 4], 8
+    pn, log = _fake_pipeline(sizes, TT)
+    n = sum(sizes)
+    xs, us, st = pn.solve(np.zeros((n, 6, TT)), np.zeros((n, 2, TT)), dx0=np.zeros((n, 6)), x_dtype=np.float32)
+    assert [e for e in log if e[0] == "set_refs"] == [("set_refs", k) for k in sizes]       # uploads are serialised in sub-batch order
+    lo = 0
+    for k in sizes:   # every sub-batch wrote its own slice of the outputs and of the statistics
+        assert (xs[lo:lo + k] == k).all() and (us[lo:lo + k] == -k).all() and (st["J"][lo:lo + k] == k).all()
+        lo += k
+    assert xs.dtype == np.float32 and st["x0"].shape == (n, 6) and (st["x0"] == 0.5).all() and (st["iters"] == 7).all()
+
+
+@pytest.mark.parametrize("where", ["set_refs", "init_guess", "solve_deliver"])
+def test_pipeline_surfaces_a_failing_sub_batch_and_does_not_hang(where):
+    """A sub-batch that fails must not leave the others waiting for their upload turn, and later sub-batches do not start once an
+    error is recorded during the upload phase (round-1 advisory finding)."""
+    sizes, TT = [4, 4, 4, 4], 6
+    pn, log = _fake_pipeline(sizes, TT, fail=(1, where))
+    n = sum(sizes)
+    with pytest.raises(RuntimeError, match="failed in " + where):
+        pn.solve(np.zeros((n, 6, TT)), np.zeros((n, 2, TT)))
+    if where == "set_refs":   # the failure happened while the others still waited for their turn: they never uploaded
+        assert [e[0] for e in log].count("set_refs") == 2
