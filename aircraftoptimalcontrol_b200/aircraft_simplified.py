@@ -11,6 +11,8 @@ Reference interface mirrored (paths into MohamedAtwan/AirCraftOptimalControl):
   Dynamics.step(xx,uu,*args)           :263-393 -> (xxp float32 (6,), fx (6,6), fu (2,6), fxx, fuu, fux)
   Dynamics.get_initial_trajectory      :126-148
   Dynamics.get_equilibrium             :152-178
+  Dynamics.dragForce / liftForce       :212-261 -> (value, gradient (6,1))   (host-side helpers)
+  round_theta(th)                      :6-14
   tensorCont(P, a)                     :397-404
 
 Every call is one kernel launch on a batch of one; the `*_batch` variants take a leading sample axis and
@@ -21,6 +23,14 @@ from __future__ import annotations
 import numpy as np
 
 from . import _lib as L
+
+
+def round_theta(th):
+    """An angle brought back into [-2*pi, 2*pi] by whole turns (aircraft_simplified.py:6-14; never called by the reference itself)."""
+    two_pi = 2 * np.pi
+    while abs(th) > two_pi:
+        th = th + two_pi if th < -two_pi else th - two_pi
+    return th
 
 
 def tensorCont(P, a):
@@ -77,12 +87,37 @@ class Dynamics:
         self.m, self.g, self.S, self.rho, self.J = 12, 9.81, 0.61, 1.2, 0.24
         self.ns, self.ni = 6, 2
         self.dt = 1e-3
+        # attributes the reference's constructor also sets (:120-124); nothing on the path reads them
+        self.Temp = None
+        self.eps_init, self.eps_end, self.speedLimit = 1.5, 0.1, 480
+        self.epsilon = self.eps_init
         self.device = device
         self.state = state  # "f32": next state rounded to float32 like the reference (:300); "f64": not
 
     @property
     def params(self):
         return np.array([self.cd0, self.cda, self.cla, self.m, self.g, self.S, self.rho, self.J, self.dt], dtype=np.float64)
+
+    def _aero(self, xx, coeff_of_alpha):
+        """0.5*rho*V^2*S*c(alpha) and its gradient w.r.t. the state (nonzero for V, theta, gamma only), c given as (c, dc/dalpha)."""
+        x = np.asarray(xx, dtype=np.float64).reshape(-1)
+        V, alpha = x[2], x[3] - x[5]
+        c, dc = coeff_of_alpha(alpha)
+        qS = 0.5 * self.rho * V ** 2 * self.S
+        grad = np.zeros((self.ns, 1))
+        grad[2, 0] = self.rho * V * self.S * c
+        grad[3, 0] = qS * dc
+        grad[5, 0] = -qS * dc
+        return qS * c, grad
+
+    def dragForce(self, xx):
+        """(D, dD_x (6,1)): drag and its state gradient, aircraft_simplified.py:212-236.  Host-side helper of the reference's public
+        interface (the kernels evaluate the same formula inside `step`, csrc/acoc_math.cuh)."""
+        return self._aero(xx, lambda a: (self.cd0 + self.cda * a ** 2, 2 * self.cda * a))
+
+    def liftForce(self, xx):
+        """(L, dL_x (6,1)): lift and its state gradient, aircraft_simplified.py:238-261 (host-side helper, see dragForce)."""
+        return self._aero(xx, lambda a: (self.cla * a, self.cla))
 
     def step_batch(self, xx, uu, lmbd=None):
         """n samples: xx (n,6), uu (n,2), lmbd (n,6) or None.  Returns dict(xxp (n,6) float64, A (n,6,6) = fx.T,

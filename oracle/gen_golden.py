@@ -73,6 +73,24 @@ def gen_step_kat():
     _save("step_kat.npz", x=X, u=U, lam=LAM, **{k: np.array(v) for k, v in out.items()})
 
 
+def gen_aero_kat():
+    """Dynamics.dragForce / liftForce (aircraft_simplified.py:212-261), get_equilibrium (:152-178) and round_theta (:6-14) of the live
+    reference on the states of the step KAT."""
+    kat = np.load(os.path.join(GOLD, "step_kat.npz"))
+    ac = pyref.load(False).aircraft
+    d = ac.Dynamics()
+    D, dD, Lf, dL = [], [], [], []
+    for x in kat["x"][:64]:
+        a, b = d.dragForce(x.copy())
+        D.append(a); dD.append(b)
+        a, b = d.liftForce(x.copy())
+        Lf.append(a); dL.append(b)
+    th = np.array([0.3, -7.0, 7.0, 13.0, -20.5, 2 * np.pi, -2 * np.pi, 100.0])
+    xe, ue = d.get_equilibrium(np.array([0.0, 0.0, 16.0, 0.0, 0.0, 0.0]), np.linspace(0, 1, 1000))
+    _save("aero_kat.npz", x=kat["x"][:64], D=np.array(D), dD=np.array(dD), L=np.array(Lf), dL=np.array(dL), th=th,
+          th_rounded=np.array([ac.round_theta(t) for t in th]), xe=np.asarray(xe, dtype=np.float64), ue=np.asarray(ue, dtype=np.float64))
+
+
 def _config_weights(cfg):
     """Weights of main_newton_method.py:52-63 / acrobatic_newton.py:55-65 (restated, checked against the scripts below)."""
     m, g, J = 12, 9.81, 0.24
@@ -299,6 +317,7 @@ def gen_gradient(jobs):
 GENERATORS = {
     "step_kat": lambda a: gen_step_kat(),
     "cost_kat": lambda a: gen_cost_kat(),
+    "aero_kat": lambda a: gen_aero_kat(),
     "lq_forced_reg": lambda a: gen_lq_forced_reg(),
     "lqr_tracking": lambda a: gen_lqr_tracking(),
     "newton": lambda a: gen_newton(a.jobs),

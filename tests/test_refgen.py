@@ -64,3 +64,24 @@ def test_generator_formula_of_the_device_kernel_matches_the_scripts():
     for c in (2, 3, 4, 5):
         assert np.all(xr[:, c] == xc[c])
     assert np.all(ur[:, 0] == uc[0]) and np.all(ur[:, 1] == uc[1])
+
+
+def test_aero_helpers_and_equilibrium_match_the_reference():
+    """Host-side helpers of the drop-in Dynamics that the reference exposes next to `step`: dragForce / liftForce
+    (aircraft_simplified.py:212-261), get_equilibrium with its int-truncated thrust (:152-178), round_theta (:6-14), against values of
+    the live reference (tests/golden/aero_kat.npz, oracle/gen_golden.py::gen_aero_kat)."""
+    import os
+    from aircraftoptimalcontrol_b200.aircraft_simplified import Dynamics, round_theta
+    from tests.util import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "aero_kat.npz"))
+    d = Dynamics()
+    for k, x in enumerate(g["x"]):
+        D, dD = d.dragForce(x)
+        Lf, dL = d.liftForce(x)
+        assert dD.shape == (6, 1) and dL.shape == (6, 1)
+        assert abs(D - g["D"][k]) <= 1e-13 * abs(g["D"][k]) and abs(Lf - g["L"][k]) <= 1e-13 * max(abs(g["L"][k]), 1e-300)
+        assert np.allclose(dD, g["dD"][k], rtol=1e-13, atol=0) and np.allclose(dL, g["dL"][k], rtol=1e-13, atol=0)
+    assert np.allclose([round_theta(t) for t in g["th"]], g["th_rounded"], rtol=0, atol=1e-12)
+    xe, ue = d.get_equilibrium(np.array([0.0, 0.0, 16.0, 0.0, 0.0, 0.0]), np.linspace(0, 1, 1000))
+    assert np.allclose(xe, g["xe"], rtol=1e-9, atol=1e-12) and np.array_equal(np.asarray(ue, dtype=np.float64), g["ue"]) and ue[0] == 46
+    assert (d.Temp, d.eps_init, d.eps_end, d.speedLimit, d.epsilon) == (None, 1.5, 0.1, 480, 1.5)   # constructor attributes (:120-124)
