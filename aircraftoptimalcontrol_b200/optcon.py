@@ -41,8 +41,9 @@ def _stack(M, TT, rows, cols, name):
     return np.ascontiguousarray(np.moveaxis(M[:, :, :TT], 2, 0))
 
 
-def ltv_LQR(AAin, BBin, QQin, RRin, SSin, QQfin, TT, x0, qq=None, rr=None, qqf=None, device=0, return_nreg=False):
-    """LQR for an LTV system with (time-varying) affine cost, optcon.py:533-771, for ns = 6, ni = 2."""
+def _lq_problem(AAin, BBin, QQin, RRin, SSin, QQfin, TT, x0, qq, rr, qqf):
+    """One problem of ltv_LQR in the library's time-major layout: (A, B, Q, R, S, Qf, x0, q, r, qf), the last three None in the
+    non-augmented branch (optcon.py:614)."""
     ns, ni = 6, 2
     A = _stack(AAin, TT, ns, ns, "AAin")
     B = _stack(BBin, TT, ns, ni, "BBin")
@@ -67,14 +68,47 @@ def ltv_LQR(AAin, BBin, QQin, RRin, SSin, QQfin, TT, x0, qq=None, rr=None, qqf=N
             return np.ascontiguousarray(v[:, :TT].T)
         q, r = aff(qq, ns, "qq"), aff(rr, ni, "rr")
         qf = np.zeros(ns) if qqf is None else L.f64(np.asarray(qqf, dtype=np.float64).reshape(-1), (ns,), "qqf")
+    return A, B, Q, R, S, Qf, x0, q, r, qf
+
+
+def _lq_solve(problems, TT, device):
+    """acoc_ltv_lqr on nb problems that are all augmented or all plain -> K (nb,TT,2,n), P (nb,TT,n,n), x (nb,TT,6), u (nb,TT,2), n_reg (nb,)."""
+    nb, ns, ni = len(problems), 6, 2
+    aug = problems[0][7] is not None
+    if any((p[7] is not None) != aug for p in problems):
+        raise ValueError("the problems of one batch must all have affine terms (qq/rr/qqf) or none")
     n = ns + 1 if aug else ns
-    K, P = np.zeros((TT, ni, n)), np.zeros((TT, n, n))
-    xo, uo = np.zeros((TT, ns)), np.zeros((TT, ni))
-    nreg = C.c_int(0)
-    L.check(L.lib().acoc_ltv_lqr(device, 1, TT, L.ptr(A), L.ptr(B), L.ptr(Q), L.ptr(R), L.ptr(S), L.ptr(Qf), L.ptr(x0),
-                                 L.ptr(q), L.ptr(r), L.ptr(qf), L.ptr(K), L.ptr(P), L.ptr(xo), L.ptr(uo), C.addressof(nreg)))
-    out = (np.moveaxis(K, 0, 2).copy(), np.moveaxis(P, 0, 2).copy(), xo.T.copy(), uo.T.copy())
-    return out + (nreg.value,) if return_nreg else out
+    cat = [np.ascontiguousarray(np.stack([p[k] for p in problems])) if (k < 7 or aug) else None for k in range(10)]
+    K, P = np.zeros((nb, TT, ni, n)), np.zeros((nb, TT, n, n))
+    xo, uo = np.zeros((nb, TT, ns)), np.zeros((nb, TT, ni))
+    nreg = np.zeros(nb, dtype=np.int32)
+    L.check(L.lib().acoc_ltv_lqr(device, nb, TT, *[L.ptr(a) for a in cat], L.ptr(K), L.ptr(P), L.ptr(xo), L.ptr(uo), L.ptr(nreg)))
+    return K, P, xo, uo, nreg
+
+
+def ltv_LQR(AAin, BBin, QQin, RRin, SSin, QQfin, TT, x0, qq=None, rr=None, qqf=None, device=0, return_nreg=False):
+    """LQR for an LTV system with (time-varying) affine cost, optcon.py:533-771, for ns = 6, ni = 2."""
+    K, P, xo, uo, nreg = _lq_solve([_lq_problem(AAin, BBin, QQin, RRin, SSin, QQfin, TT, x0, qq, rr, qqf)], TT, device)
+    out = (np.moveaxis(K[0], 0, 2).copy(), np.moveaxis(P[0], 0, 2).copy(), xo[0].T.copy(), uo[0].T.copy())
+    return out + (int(nreg[0]),) if return_nreg else out
+
+
+def ltv_LQR_batch(problems, TT, device=0):
+    """nb independent ltv_LQR problems in ONE launch (one thread per problem, acoc_ltv_lqr with nb > 1).  `problems` is a sequence of
+    argument tuples (AAin, BBin, QQin, RRin, SSin, QQfin, x0[, qq, rr, qqf]) with ltv_LQR's shapes; all of them with affine terms or
+    none.  Returns (KK (nb,2,n,TT), PP (nb,n,n,TT), xxout (nb,6,TT), uuout (nb,2,TT), n_reg (nb,)), problem b equal to what
+    ltv_LQR(*problems[b]) returns."""
+    if len(problems) == 0:
+        raise ValueError("no problem given")
+    prob = []
+    for pr in problems:
+        pr = tuple(pr)
+        if len(pr) not in (7, 10):
+            raise ValueError("a problem is (AAin, BBin, QQin, RRin, SSin, QQfin, x0[, qq, rr, qqf])")
+        prob.append(_lq_problem(*pr[:6], TT, pr[6], *(pr[7:] if len(pr) == 10 else (None, None, None))))
+    K, P, xo, uo, nreg = _lq_solve(prob, TT, device)
+    return (np.ascontiguousarray(np.moveaxis(K, 1, 3)), np.ascontiguousarray(np.moveaxis(P, 1, 3)), np.ascontiguousarray(np.moveaxis(xo, 1, 2)),
+            np.ascontiguousarray(np.moveaxis(uo, 1, 2)), nreg)
 
 
 class GradientMethod:

@@ -94,6 +94,37 @@ def test_ltv_lqr_forced_regularisation(gpu):
         ltv_LQR(d["A"], d["B"], np.eye(5), d["R"], d["S"], d["Qf"], TT, d["x0"])
 
 
+def test_ltv_lqr_batch_equals_single_calls(gpu, oracle):
+    """acoc_ltv_lqr with nb > 1 (optcon.ltv_LQR_batch): several independent problems in one launch, each equal to its own ltv_LQR call
+    bit for bit and to the oracle's ltv_LQR (optcon.py:533-771) to 1e-9 -- augmented and plain branches, one problem that takes the
+    +0.5*I branch and two that do not."""
+    from aircraftoptimalcontrol_b200.optcon import ltv_LQR, ltv_LQR_batch
+    d = golden("lq_forced_reg.npz")
+    TT = d["A"].shape[2]
+    rng = np.random.default_rng(5)
+    Qpd = d["Q"] + 5.0 * np.eye(6)[:, :, None]   # positive definite: no regularised step
+    base = [(d["A"], d["B"], d["Q"], d["R"], d["S"], d["Qf"], d["x0"]),
+            (d["A"], d["B"], Qpd, d["R"] + np.eye(2)[:, :, None], 0 * d["S"], np.eye(6), rng.normal(size=6)),
+            (d["A"] * 0.9, d["B"], Qpd[:, :, 0], np.eye(2), 0 * d["S"], 2 * np.eye(6), rng.normal(size=6))]
+    for aug in (False, True):
+        probs = [p + ((d["q"] * (k + 1), d["r"], d["qf"] * (1 - k)) if aug else ()) for k, p in enumerate(base)]
+        K, P, x, u, nreg = ltv_LQR_batch(probs, TT)
+        n = 7 if aug else 6
+        assert K.shape == (3, 2, n, TT) and P.shape == (3, n, n, TT) and x.shape == (3, 6, TT) and u.shape == (3, 2, TT)
+        assert nreg[0] > 0 and nreg[1] == 0 and nreg[2] == 0
+        for b, p in enumerate(probs):
+            args = p[:6] + (TT, p[6]) + tuple(p[7:])
+            K1, P1, x1, u1, n1 = ltv_LQR(*args, return_nreg=True)
+            assert np.array_equal(K[b], K1) and np.array_equal(P[b], P1) and np.array_equal(x[b], x1) and np.array_equal(u[b], u1) and nreg[b] == n1
+            Q3 = p[2] if np.ndim(p[2]) == 3 else np.repeat(p[2][:, :, None], TT, 2)
+            R3 = p[3] if np.ndim(p[3]) == 3 else np.repeat(p[3][:, :, None], TT, 2)
+            Ko, Po, xo, uo = oracle.ltv_lqr(p[0], p[1], Q3, R3, p[4], p[5], TT, p[6], *p[7:])[:4]
+            for got, ref in ((K[b], Ko), (P[b], Po), (x[b], xo), (u[b], uo)):
+                assert relerr(ref, got) < 1e-9
+    with pytest.raises(ValueError):
+        ltv_LQR_batch([base[0], base[1] + (d["q"], d["r"], d["qf"])], TT)   # mixed branches
+
+
 @pytest.mark.parametrize("name", ["newton_step_f32", "newton_step_f64", "newton_acro_f32", "newton_acro_f64"])
 @pytest.mark.parametrize("armijo", ["speculative", "lazy"])
 def test_newton_configs_1_2(gpu, name, armijo):
