@@ -178,6 +178,47 @@ def gen_newton(jobs):
             print("newton %s f64=%s: %d iterations, %.1f s" % (cfg, f64, iters, wall), flush=True)
 
 
+def _batched_instance_job(args):
+    """One instance of a BATCHED configuration (BASELINE configs[3] / [4]) through the live reference's NewtonMethod.optimize."""
+    cfg, idx = args
+    sys.path.insert(0, ROOT)
+    from aircraftoptimalcontrol_b200 import refgen   # pinned to the scripts' globals by tests/test_refgen.py
+    from oracle import corcl
+    if cfg == "config4":
+        zf, xf = refgen.config4_params()
+        xr, ur = refgen.step_problem(xf[idx:idx + 1], zf[idx:idx + 1])
+        Q, R, QT = refgen.weights("step")
+        par, dx0 = np.array([zf[idx], xf[idx]]), np.zeros(6)
+    else:
+        dx0_all, zf = refgen.config5_params()
+        xr, ur = refgen.acrobatic_problem(zf[idx:idx + 1])
+        Q, R, QT = refgen.weights("acro")
+        par, dx0 = np.array([zf[idx]]), dx0_all[idx]
+    xr, ur = xr[0], ur[0]
+    start = xr.copy()
+    start[:, 0] += dx0                                      # x0 = xx_ref[:,0] + dx0 (SURVEY 8(d) config 5); zero for config 4
+    xi, ui = corcl.initial_trajectory(start, quant_f32=True)   # the initial guess is an INPUT: the same arrays go to both sides
+    t0 = time.time()
+    h = pyref.run_newton(pyref.load(False), xr, ur, xi, ui, Q, R, QT)
+    return cfg, idx, par, dx0, xi, ui, h, time.time() - t0
+
+
+def gen_batched_instances(jobs):
+    """the C oracle that the GPU's batched parity tests compare with is itself validated against the Python reference on
+    >= 4 instances of the batched configurations: instances 0, 1 of config 4 (65,536 step references, seed 2024) and instances 0, 1 of
+    config 5 (1,048,576 acrobatic instances with perturbed x0, seed 7) -- the same instances the GPU tests sample."""
+    work = [("config4", 0), ("config4", 1), ("config5", 0), ("config5", 1)]
+    arrs = {}
+    with ProcessPoolExecutor(max_workers=jobs) as ex:
+        for cfg, idx, par, dx0, xi, ui, h, wall in ex.map(_batched_instance_job, work):
+            tag = "%s_%d_" % (cfg, idx)
+            arrs.update({tag + "par": par, tag + "dx0": dx0, tag + "xx_init": xi, tag + "uu_init": ui, tag + "JJ": h["JJ"],
+                         tag + "descent": h["descent"], tag + "stepsize": h["stepsize"], tag + "n_armijo": h["n_armijo"],
+                         tag + "iters": h["iters"], tag + "xx_star": h["xx_star"], tag + "uu_star": h["uu_star"], tag + "ref_wall_s": wall})
+            print("batched instance %s[%d]: %d iterations, %.1f s" % (cfg, idx, h["iters"], wall), flush=True)
+    _save("newton_batched_instances.npz", **arrs)
+
+
 # ------------------------------------------------------------------------------------------------
 def gen_lq_forced_reg():
     """A problem whose R + B'PB is indefinite at some steps, so optcon.py:745-749 adds 0.5*I."""
@@ -322,6 +363,7 @@ GENERATORS = {
     "lqr_tracking": lambda a: gen_lqr_tracking(),
     "newton": lambda a: gen_newton(a.jobs),
     "newton_quirks": lambda a: gen_newton_quirks(),
+    "batched_instances": lambda a: gen_batched_instances(a.jobs),
     "gradient": lambda a: gen_gradient(a.jobs),
 }
 

@@ -201,3 +201,33 @@ def test_riccati_by_columns_bit_identical(emul, exact, weights):
         assert bad == 0
         if weights == "tiny_R":
             assert nreg > 0
+
+
+@pytest.mark.parametrize("lazy", [False, True])
+def test_kernels_reproduce_reference_on_batched_config_instances(emul, lazy):
+    """The kernels' per-instance code (host replay, driven like acoc_newton_iterate) on the four instances of BASELINE configs[3] / [4]
+    that the live Python reference solved (tests/golden/newton_batched_instances.npz): the two step-maneuver instances in ONE batch
+    with per-instance references, the two acrobatic ones with their perturbed x0 -- iteration counts, every Armijo step and candidate
+    count identical, histories 1e-12 / 1e-9, float32-quantised results bit-identical."""
+    from aircraftoptimalcontrol_b200 import refgen
+    d = golden("newton_batched_instances.npz")
+    for cfg in ("config4", "config5"):
+        if cfg == "config4":
+            zf, xf = refgen.config4_params()
+            xr, ur = refgen.step_problem(xf[:2], zf[:2])
+            Q, R, QT = refgen.weights("step")
+        else:
+            _, zf = refgen.config5_params()
+            xr, ur = refgen.acrobatic_problem(zf[:2])
+            Q, R, QT = refgen.weights("acro")
+        xi = np.stack([d["%s_%d_xx_init" % (cfg, i)] for i in range(2)])
+        ui = np.stack([d["%s_%d_uu_init" % (cfg, i)] for i in range(2)])
+        h = emul.newton_batch(xr, ur, xi, ui, Q, R, QT, lazy=lazy)
+        for i in range(2):
+            t = "%s_%d_" % (cfg, i)
+            k = int(d[t + "iters"])
+            assert h["iters"][i] == k and h["status"][i] == 1
+            assert np.array_equal(h["stepsize"][i, :k], d[t + "stepsize"]) and np.array_equal(h["n_armijo"][i, :k], d[t + "n_armijo"])
+            assert np.max(np.abs(h["JJ"][i, :k] - d[t + "JJ"]) / np.abs(d[t + "JJ"])) < 1e-12
+            assert np.max(np.abs(h["descent"][i, :k] - d[t + "descent"]) / np.abs(d[t + "descent"])) < 1e-9
+            assert np.array_equal(h["xx_star"][i], d[t + "xx_star"]) and relerr(d[t + "uu_star"], h["uu_star"][i]) < 1e-9

@@ -152,3 +152,34 @@ def test_gradient_method_pinned(oracle, name):
         assert np.array_equal(o["xx_last"], g["xx_last"]) and np.array_equal(o["xx_star"], g["xx_star"])
     assert relerr(g["xx_last"], o["xx_last"]) < 1e-9 and relerr(g["uu_last"], o["uu_last"]) < 1e-9
     assert relerr(g["uu_star"], o["uu_star"]) < 1e-9
+
+
+@pytest.mark.parametrize("cfg,idx", [("config4", 0), ("config4", 1), ("config5", 0), ("config5", 1)])
+def test_batched_config_instances_pinned_to_the_reference(oracle, cfg, idx):
+    """the oracle the GPU's batched parity tests compare with is itself validated against the live Python reference on
+    instances of the BATCHED configurations -- instances 0, 1 of config 4 (randomised step references, seed 2024) and of config 5
+    (acrobatic, x0 + delta, bump height, seed 7), TT = 1000, float32-quantised state: same iteration count, every Armijo step and
+    candidate count, histories to 1e-12 / 1e-9, result bit-identical (oracle/gen_golden.py::gen_batched_instances)."""
+    from aircraftoptimalcontrol_b200 import refgen
+    d = golden("newton_batched_instances.npz")
+    t = "%s_%d_" % (cfg, idx)
+    if cfg == "config4":
+        zf, xf = refgen.config4_params()
+        assert np.array_equal(d[t + "par"], [zf[idx], xf[idx]])
+        xr, ur = refgen.step_problem(xf[idx:idx + 1], zf[idx:idx + 1])
+        Q, R, QT = refgen.weights("step")
+    else:
+        dx0, zf = refgen.config5_params()
+        assert np.array_equal(d[t + "par"], [zf[idx]]) and np.array_equal(d[t + "dx0"], dx0[idx])
+        xr, ur = refgen.acrobatic_problem(zf[idx:idx + 1])
+        Q, R, QT = refgen.weights("acro")
+    start = xr[0].copy()
+    start[:, 0] += d[t + "dx0"]
+    xi, ui = oracle.initial_trajectory(start, quant_f32=True)
+    assert np.array_equal(xi, d[t + "xx_init"]) and np.array_equal(ui, d[t + "uu_init"])   # the input both sides were given
+    h = oracle.newton(xr[0], ur[0], xi, ui, Q, R, QT, quant_f32=True)
+    assert h["iters"] == int(d[t + "iters"])
+    assert np.array_equal(h["stepsize"], d[t + "stepsize"]) and np.array_equal(h["n_armijo"], d[t + "n_armijo"])
+    assert np.max(np.abs(h["JJ"] - d[t + "JJ"]) / np.abs(d[t + "JJ"])) < 1e-12
+    assert np.max(np.abs(h["descent"] - d[t + "descent"]) / np.abs(d[t + "descent"])) < 1e-9
+    assert np.array_equal(h["xx_star"], d[t + "xx_star"]) and relerr(d[t + "uu_star"], h["uu_star"]) < 1e-9
