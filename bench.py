@@ -385,6 +385,14 @@ def roofline_tables(args, n, K, W, hist, phases, peaks, peak_src, fp64_peak, fus
     else:
         achieved, peak, unit = d.get("fp64_executed_ginst_per_s"), fp64_peak * 1e3 / 2.0, "G FP64-inst/s (thread-level)"
         frac = d.get("fp64_executed_frac")
+    # the same fraction for ONE launch over a fully active batch, from the committed ncu capture of this build (duration under ncu:
+    # serialised, cold cache); the window above also sweeps the finished lanes of live tiles, which lowers `frac`
+    full_launch = None
+    if c and c.get("duration_ms") and kc and bound[dom] == "hbm":
+        fb = float(kc["instances"]) * (kc["TT"] - 1) * alg_b[dom]
+        full_launch = {"instances": kc["instances"], "ms": c["duration_ms"], "algorithmic_bytes": fb, "achieved": fb / (c["duration_ms"] * 1e-3) / 1e9,
+                       "frac": fb / (c["duration_ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": c.get("dram_bytes"),
+                       "source": "profiles/r02_kernel_counters.json (ncu --set full of this build; recorded, not re-measured in this run)"}
     roofline = {"kernel": shown[dom] + ("<EXACT>" if dom == "backward" and exact.any() else ""), "bound": "hbm" if bound[dom] == "hbm" else "fp64 (tensor cores unused by design)",
                 "achieved": achieved, "peak": peak, "unit": unit, "frac": frac, "traffic": traffic, "traffic_source": kc_src,
                 "algorithmic_bytes_per_launch": alg_per_launch, "peak_source": peak_src,
@@ -396,6 +404,7 @@ def roofline_tables(args, n, K, W, hist, phases, peaks, peak_src, fp64_peak, fus
                          "executed_frac_dominant_kernel": d.get("fp64_executed_frac"),
                          "note": "executed FP64-pipe instructions per lane and step from the ncu capture of this build x lanes processed, against the "
                                  "measured DFMA issue rate; null when no capture of this build is committed"},
+                "fully_active_launch": full_launch,
                 "per_kernel": tbl, "share_of_step": phases[dom] / max(tot_ms, 1e-9),
                 "algorithmic": {"bytes_per_instance_step": BYTES, "flops_per_instance_step": FLOPS, "note": "SURVEY.md 8(d) per-unit figures"},
                 "moved": {"bytes_per_instance_step": dict(MB, forward_fused=fwd_moved),
